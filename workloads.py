@@ -1,0 +1,81 @@
+"""Synthetic descriptor banks for bench.py and the parity tests.
+
+Not part of the product path and not part of the oracle: it only manufactures
+inputs.  Recipes follow SURVEY.md §8(d) "Synthetic inputs".
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def sift_like_image(i: int, n_rows: int, prev: np.ndarray | None = None, planted: float = 0.30,
+                    seed_base: int = 1000) -> np.ndarray:
+    """One image's SIFT-like descriptors: uint8 [n_rows, 128], integer-valued like cv::SIFT.
+
+    gamma(0.6) -> L2-normalise -> clip 0.2 -> renormalise -> rint(512 x) clipped to 0..255;
+    the first ``planted`` fraction of rows are noisy copies (sigma 6) of random rows of
+    ``prev`` so that the ratio test has survivors."""
+    rng = np.random.Generator(np.random.PCG64(seed_base + i))
+    x = rng.gamma(0.6, size=(n_rows, 128)).astype(np.float32)
+    x /= np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    np.minimum(x, 0.2, out=x)
+    x /= np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    d = np.clip(np.rint(512.0 * x), 0, 255).astype(np.uint8)
+    if prev is not None and prev.shape[0] > 0 and planted > 0:
+        k = int(n_rows * planted)
+        src = rng.integers(0, prev.shape[0], size=k)
+        noisy = prev[src].astype(np.float32) + rng.normal(0.0, 6.0, size=(k, 128)).astype(np.float32)
+        d[:k] = np.clip(np.rint(noisy), 0, 255).astype(np.uint8)
+    return d
+
+
+def sift_like_bank(n_images: int, n_rows: int, planted: float = 0.30, seed_base: int = 1000):
+    bank, prev = [], None
+    for i in range(n_images):
+        prev = sift_like_image(i, n_rows, prev, planted, seed_base)
+        bank.append(prev)
+    return bank
+
+
+def orb_like_image(i: int, n_rows: int, prev: np.ndarray | None = None, planted: float = 0.30,
+                   flips: int = 20, seed_base: int = 5000) -> np.ndarray:
+    """ORB-like descriptors: uint8 [n_rows, 32] uniform bits; ``planted`` rows are copies of
+    rows of ``prev`` with ``flips`` random bit flips."""
+    rng = np.random.Generator(np.random.PCG64(seed_base + i))
+    d = rng.integers(0, 256, size=(n_rows, 32), dtype=np.uint8)
+    if prev is not None and prev.shape[0] > 0 and planted > 0:
+        k = int(n_rows * planted)
+        src = rng.integers(0, prev.shape[0], size=k)
+        c = prev[src].copy()
+        bit = rng.integers(0, 256, size=(k, flips))
+        for f in range(flips):
+            c[np.arange(k), bit[:, f] >> 3] ^= (1 << (bit[:, f] & 7)).astype(np.uint8)
+        d[:k] = c
+    return d
+
+
+def orb_like_bank(n_images: int, n_rows: int, planted: float = 0.30, flips: int = 20, seed_base: int = 5000):
+    bank, prev = [], None
+    for i in range(n_images):
+        prev = orb_like_image(i, n_rows, prev, planted, flips, seed_base)
+        bank.append(prev)
+    return bank
+
+
+def adversarial_sift(seed: int = 3):
+    """Small descriptor sets exercising ties, duplicates, zero rows and ragged sizes."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = rng.integers(0, 120, size=(257, 128), dtype=np.uint8)
+    dup = np.concatenate([base[:40], base[:40], base[10:20], np.zeros((3, 128), np.uint8), base[40:]])
+    sat = np.full((5, 128), 255, np.uint8)
+    return {
+        "base": base,
+        "dup": dup,                                  # exact ties at ranks 1 and 2
+        "zeros": np.zeros((9, 128), np.uint8),
+        "sat": np.concatenate([sat, np.zeros((2, 128), np.uint8), base[:7]]),  # max distance 128*255^2
+        "one": base[:1],
+        "two": base[:2],
+        "n127": base[:127],
+        "n129": base[:129],
+        "empty": np.zeros((0, 128), np.uint8),
+    }
