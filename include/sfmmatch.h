@@ -1,0 +1,149 @@
+/*
+ * sfmmatch.h — C ABI of the B200-native pairwise descriptor matcher (libsfmmatch.so).
+ *
+ * This is the drop-in boundary for the feature-matching stage of brunothg/sfm-mvs-pipeline.
+ * Every entry point names the reference interface it replaces (paths into the reference tree).
+ * No C++ / torch types cross this boundary: plain pointers, sizes and status codes.
+ *
+ * Status codes: 0 = ok, < 0 = error (sfm_last_error(ctx) gives the text).  No exception
+ * crosses the ABI; the C++ adapter turns a non-zero status into cv::Exception
+ * so the reference's catch-branch (UnorderedFeatureMatchingStrategy.cpp:66-72) still works.
+ * There is NO CPU fallback: every compute entry point fails with SFM_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef SFMMATCH_H
+#define SFMMATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFM_OK              0
+#define SFM_ERR_INVALID    -1   /* bad argument / shape mismatch (cv::batchDistance asserts) */
+#define SFM_ERR_CUDA       -2   /* CUDA runtime/driver error, or no usable device */
+#define SFM_ERR_CAPACITY   -3   /* caller buffer too small / train rows >= 2^18 (IMGIDX_ONE) */
+#define SFM_ERR_UNSUPPORTED -4  /* e.g. radius match, k > 2, cross_check with k != 1 semantics */
+#define SFM_ERR_STATE      -5   /* call order violated (e.g. match before bank upload) */
+
+/* cv::NormTypes values used by the reference (PhotogrammetrieCli.cpp:378, :387) */
+#define SFM_NORM_L2        4
+#define SFM_NORM_HAMMING   6
+/* cv::Mat depth codes of the descriptor matrices (CameraShot.h:39-42) */
+#define SFM_CV_8U          0
+#define SFM_CV_32F         5
+/* OpenCV's IMGIDX_ONE limit, surfaced by the reference as "max 262144" (PhotogrammetrieCli.cpp:430) */
+#define SFM_MAX_ROWS       (1 << 18)
+
+/* engine selector (tests / profiling): which hand-written kernel computes the distances */
+#define SFM_ENGINE_AUTO    0    /* tcgen05 for L2 on u8-valued data, popc for Hamming */
+#define SFM_ENGINE_TENSOR  1    /* force tcgen05/TMA/TMEM kernel (L2, and Hamming via bit-expanded u8) */
+#define SFM_ENGINE_SIMT    2    /* force CUDA-core kernels (dp4a L2 / popc Hamming / fp32 L2) */
+
+/* Byte-compatible with cv::DMatch {int queryIdx, trainIdx, imgIdx; float distance;}.
+ * left shot <-> queryIdx, right shot <-> trainIdx (Scene.h:47-51). */
+typedef struct sfm_dmatch {
+    int32_t queryIdx;
+    int32_t trainIdx;
+    int32_t imgIdx;
+    float   distance;
+} sfm_dmatch;
+
+/* Options of one matching run.  Defaults = the reference's behaviour:
+ * k=2 knnMatch + Lowe ratio 0.7 (UnorderedFeatureMatchingStrategy.cpp:51-59), cross-check off
+ * (BFMatcher::create(normType), PhotogrammetrieCli.cpp:378/:387), distinct off
+ * (PhotogrammetrieCli.cpp:112), min_match_count 0 here (SfM applies 20, PhotogrammetrieCli.cpp:95). */
+typedef struct sfm_opts {
+    int32_t norm;             /* SFM_NORM_L2 | SFM_NORM_HAMMING */
+    int32_t k;                /* 2 (ratio test) ; 1 = DescriptorMatcher::match() semantics, keep all */
+    double  ratio;            /* 0.7 */
+    int32_t cross_check;      /* 1: mutual-nearest-neighbour filter instead of the ratio test
+                                 (cv::BFMatcher(crossCheck=true) semantics) */
+    int32_t distinct;         /* 1: SfM.cpp:547-564 one-to-one trainIdx filter */
+    int32_t min_match_count;  /* pairs with fewer matches are dropped (SfM.cpp:566-570); 0 keeps all */
+    int32_t engine;           /* SFM_ENGINE_* */
+} sfm_opts;
+
+typedef struct sfm_ctx sfm_ctx;
+typedef struct sfm_result sfm_result;
+
+/* Fill *o with the reference defaults for `norm`. */
+void sfm_opts_default(sfm_opts *o, int32_t norm);
+
+/* Library / context ------------------------------------------------------------------------
+ * One context per GPU (one process per GPU under torchrun, or one context per device in a
+ * single C++ process).  Replaces: construction of the matcher object,
+ * PhotogrammetrieCli::configureFeatureMatcher (PhotogrammetrieCli.cpp:359-392). */
+int  sfm_ctx_create(sfm_ctx **out, int device);
+void sfm_ctx_destroy(sfm_ctx *ctx);
+const char *sfm_last_error(const sfm_ctx *ctx);      /* ctx may be NULL: last create error */
+int  sfm_device_sm_count(const sfm_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on — lets the caller
+ * bracket work with CUDA events. */
+void *sfm_ctx_stream(sfm_ctx *ctx);
+
+/* Descriptor bank -----------------------------------------------------------------------------
+ * Replaces: reading CameraShot::getFeatures().descriptors for every shot of the scene
+ * (UnorderedFeatureMatchingStrategy.cpp:51, CameraShot.h:39-42).  rows[i] points at image i's
+ * host cv::Mat data (n_rows[i] x cols, row stride step_bytes[i] >= cols*elemsize; step_bytes
+ * may be NULL for dense rows).  depth SFM_CV_32F with cols=128 (SIFT) or SFM_CV_8U (ORB: cols=32;
+ * SIFT already packed: cols=128).  Inputs are copied; the caller's buffers are not retained.
+ * CV_32F data that is integer-valued in 0..255 (what cv::SIFT emits) is packed to u8 on the
+ * device and matched exactly; other float data takes the fp32 path. */
+int sfm_bank_upload(sfm_ctx *ctx, int n_images, const void *const *rows, const int32_t *n_rows,
+                    int cols, const size_t *step_bytes, int cv_depth);
+/* Same, but the descriptors already live in device memory of this context's GPU (e.g. a replica
+ * received through ncclBroadcast): one dense buffer, image i occupying rows
+ * [row_offset[i], row_offset[i]+n_rows[i]) with row stride cols*elemsize. */
+int sfm_bank_upload_device(sfm_ctx *ctx, int n_images, const void *dev_rows, const int64_t *row_offset,
+                           const int32_t *n_rows, int cols, int cv_depth);
+int sfm_bank_info(const sfm_ctx *ctx, int *n_images, int *cols, int *is_u8_valued);
+
+/* Pair selection --------------------------------------------------------------------------------
+ * Replaces the matchPairs construction of the three strategies, chosen exactly like
+ * PhotogrammetrieCli::configureFeatureMatcherStrategy (PhotogrammetrieCli.cpp:320-340):
+ * feature_sequence >= 2 && feature_gridlength >= 1 -> Grid (GridFeatureMatchingStrategy.cpp:48-85),
+ * feature_sequence >= 2 -> Video (VideoFeatureMatchingStrategy.cpp:43-48), else Unordered
+ * (UnorderedFeatureMatchingStrategy.cpp:32-37).  Writes up to `capacity` pairs (left,right) into
+ * `pairs` and the full count into *n_pairs (call with capacity 0 to size the buffer). */
+int sfm_select_pairs(int n_shots, int feature_sequence, int feature_gridlength,
+                     int32_t *pairs, int64_t capacity, int64_t *n_pairs);
+
+/* The stage ----------------------------------------------------------------------------------------
+ * Replaces IFeatureMatchingStrategy::calculateShotMatches (IFeatureMatchingStrategy.h:45-46) as
+ * invoked from SfM::calculateShotMatches (SfM.cpp:545) plus that function's post-filters
+ * (SfM.cpp:547-570): for every pair (left,right) of the list, knnMatch(k=2) of left's descriptors
+ * against right's, Lowe ratio filter, optional distinct / min-match-count filters.
+ * Results come back in INPUT PAIR ORDER, each list ascending by queryIdx (what OpenCV emits). */
+int sfm_match_pairs(sfm_ctx *ctx, const int32_t *pairs /* n_pairs x 2 */, int64_t n_pairs,
+                    const sfm_opts *opts, sfm_result **out);
+/* Two-phase form used for device-side timing: enqueue runs every kernel on the context stream and
+ * leaves the compacted match lists in device memory; collect copies them to pinned host memory. */
+int sfm_match_pairs_enqueue(sfm_ctx *ctx, const int32_t *pairs, int64_t n_pairs, const sfm_opts *opts);
+int sfm_match_pairs_collect(sfm_ctx *ctx, sfm_result **out);
+
+int64_t           sfm_result_n_pairs(const sfm_result *r);
+const int64_t    *sfm_result_offsets(const sfm_result *r);   /* n_pairs + 1 entries */
+const sfm_dmatch *sfm_result_matches(const sfm_result *r);   /* offsets[n_pairs] entries */
+const uint8_t    *sfm_result_dropped(const sfm_result *r);   /* n_pairs flags: 1 = erased by min_match_count */
+void              sfm_result_free(sfm_result *r);
+/* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
+int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/* Operator level ---------------------------------------------------------------------------------
+ * Replaces cv::DescriptorMatcher::knnMatch(query, train, matches, k) (call sites
+ * UnorderedFeatureMatchingStrategy.cpp:51, VideoFeatureMatchingStrategy.cpp:62,
+ * GridFeatureMatchingStrategy.cpp:105) and ::match() (…:68, :79, :122) for one host query/train pair.
+ * Output has the shape of cv::batchDistance(..., K=k): nidx[nq*k] (-1 where fewer than k train rows)
+ * and dist[nq*k] (L2: sqrtf; Hamming: popcount as float), ascending distance, ties -> lowest trainIdx.
+ * Re-entrant per context (serialised internally). */
+int sfm_knn_match(sfm_ctx *ctx, const void *query, int nq, size_t q_step,
+                  const void *train, int nt, size_t t_step, int cols, int cv_depth,
+                  int norm, int k, int engine, int32_t *nidx, float *dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFMMATCH_H */

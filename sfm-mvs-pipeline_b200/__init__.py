@@ -1,0 +1,234 @@
+"""ctypes binding over libsfmmatch.so (the C ABI in include/sfmmatch.h).
+
+This module contains no compute: every call lands in the hand-written CUDA kernels through the
+C ABI.  It fails loudly (ImportError / SfmError) when the library is not built or no sm_100 GPU is
+usable — there is no CPU fallback.  Names mirror the reference's matching interface:
+``knn_match`` <-> cv::DescriptorMatcher::knnMatch (Unordered...cpp:51), ``match_pairs`` <->
+IFeatureMatchingStrategy::calculateShotMatches + SfM::calculateShotMatches' post filters
+(IFeatureMatchingStrategy.h:45-46, SfM.cpp:542-575), ``select_pairs`` <-> the three strategies'
+pair lists (PhotogrammetrieCli.cpp:320-340).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsfmmatch.so")
+
+NORM_L2, NORM_HAMMING = 4, 6
+CV_8U, CV_32F = 0, 5
+ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT = 0, 1, 2
+MAX_ROWS = 1 << 18
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5
+
+DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
+
+EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_error", "sfm_device_sm_count",
+           "sfm_ctx_stream", "sfm_bank_upload", "sfm_bank_upload_device", "sfm_bank_info", "sfm_select_pairs",
+           "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
+           "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
+           "sfm_knn_match"]
+
+
+class SfmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sfmmatch error {code}: {msg}")
+        self.code = code
+
+
+class Opts(C.Structure):
+    _fields_ = [("norm", C.c_int32), ("k", C.c_int32), ("ratio", C.c_double), ("cross_check", C.c_int32),
+                ("distinct", C.c_int32), ("min_match_count", C.c_int32), ("engine", C.c_int32)]
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is not built (run `make -C {HERE}` or __graft_entry__.build()); "
+                          "there is no fallback implementation")
+    lib = C.CDLL(LIB_PATH)
+    lib.sfm_last_error.restype = C.c_char_p
+    lib.sfm_ctx_stream.restype = C.c_void_p
+    lib.sfm_result_n_pairs.restype = C.c_int64
+    lib.sfm_result_offsets.restype = C.POINTER(C.c_int64)
+    lib.sfm_result_matches.restype = C.c_void_p
+    lib.sfm_result_dropped.restype = C.POINTER(C.c_uint8)
+    lib.sfm_result_free.restype = None
+    lib.sfm_ctx_destroy.restype = None
+    lib.sfm_opts_default.restype = None
+    return lib
+
+
+_lib = load_library()
+
+
+def select_pairs(n_shots: int, feature_sequence: int = 0, feature_gridlength: int = 0) -> np.ndarray:
+    n = C.c_int64(0)
+    rc = _lib.sfm_select_pairs(C.c_int(n_shots), C.c_int(feature_sequence), C.c_int(feature_gridlength), None,
+                               C.c_int64(0), C.byref(n))
+    if rc != OK:
+        raise SfmError(rc, "invalid pairing parameters")
+    out = np.zeros((n.value, 2), np.int32)
+    _lib.sfm_select_pairs(C.c_int(n_shots), C.c_int(feature_sequence), C.c_int(feature_gridlength),
+                          out.ctypes.data_as(C.c_void_p), C.c_int64(n.value), C.byref(n))
+    return out
+
+
+def _depth_of(a: np.ndarray) -> int:
+    if a.dtype == np.uint8:
+        return CV_8U
+    if a.dtype == np.float32:
+        return CV_32F
+    raise SfmError(ERR_INVALID, f"descriptor dtype {a.dtype} is neither CV_8U nor CV_32F")
+
+
+class MatchResult:
+    """Per-pair DMatch lists in input pair order (ShotMatches without the shot pointers)."""
+
+    def __init__(self, offsets, matches, dropped):
+        self.offsets, self.matches, self.dropped = offsets, matches, dropped
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, p):
+        if self.dropped[p]:
+            return None
+        return self.matches[self.offsets[p]:self.offsets[p + 1]]
+
+    def counts(self):
+        return np.diff(self.offsets)
+
+
+class Matcher:
+    """One context = one GPU.  Mirrors the role of the injected cv::Ptr<cv::DescriptorMatcher> plus the
+    strategy object of the reference (SfM.cpp:52-65)."""
+
+    def __init__(self, device: int = 0):
+        self._ctx = C.c_void_p()
+        rc = _lib.sfm_ctx_create(C.byref(self._ctx), C.c_int(device))
+        if rc != OK:
+            raise SfmError(rc, _lib.sfm_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if self._ctx:
+            _lib.sfm_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise SfmError(rc, _lib.sfm_last_error(self._ctx).decode())
+
+    @property
+    def sm_count(self):
+        return int(_lib.sfm_device_sm_count(self._ctx))
+
+    @property
+    def stream(self) -> int:
+        return int(_lib.sfm_ctx_stream(self._ctx) or 0)
+
+    def stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.sfm_last_stats(self._ctx, C.byref(a), C.byref(b), C.byref(c))
+        return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    # ---- bank
+    def upload_bank(self, descriptors):
+        """descriptors: list of 2-D numpy arrays (one per shot), all uint8 or all float32, same width;
+        rows may be strided (like a cv::Mat with step > cols*elemSize)."""
+        n = len(descriptors)
+        if n == 0:
+            self._check(_lib.sfm_bank_upload(self._ctx, 0, None, None, C.c_int(128), None, C.c_int(CV_8U)))
+            return
+        depth = _depth_of(descriptors[0])
+        cols = descriptors[0].shape[1]
+        keep = []
+        for d in descriptors:
+            if d.ndim != 2 or d.shape[1] != cols or _depth_of(d) != depth:
+                raise SfmError(ERR_INVALID, "all descriptor matrices must share dtype and width")
+            if d.strides[1] != d.itemsize:
+                d = np.ascontiguousarray(d)
+            keep.append(d)
+        ptrs = (C.c_void_p * n)(*[d.ctypes.data if d.shape[0] else None for d in keep])
+        nrows = (C.c_int32 * n)(*[d.shape[0] for d in keep])
+        steps = (C.c_size_t * n)(*[d.strides[0] if d.shape[0] > 1 else cols * d.itemsize for d in keep])
+        self._check(_lib.sfm_bank_upload(self._ctx, C.c_int(n), ptrs, nrows, C.c_int(cols), steps, C.c_int(depth)))
+
+    def upload_bank_device(self, dev_ptr: int, row_offset, n_rows, cols: int, depth: int):
+        n = len(n_rows)
+        ro = (C.c_int64 * n)(*[int(x) for x in row_offset])
+        nr = (C.c_int32 * n)(*[int(x) for x in n_rows])
+        self._check(_lib.sfm_bank_upload_device(self._ctx, C.c_int(n), C.c_void_p(dev_ptr), ro, nr, C.c_int(cols),
+                                                C.c_int(depth)))
+
+    def bank_info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _lib.sfm_bank_info(self._ctx, C.byref(a), C.byref(b), C.byref(c))
+        return {"n_images": a.value, "cols": b.value, "u8_valued": bool(c.value)}
+
+    # ---- the stage
+    def _opts(self, norm, k, ratio, cross_check, distinct, min_match_count, engine):
+        o = Opts()
+        _lib.sfm_opts_default(C.byref(o), C.c_int32(norm))
+        o.k, o.ratio, o.cross_check, o.distinct = k, ratio, int(cross_check), int(distinct)
+        o.min_match_count, o.engine = min_match_count, engine
+        return o
+
+    def enqueue(self, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False, min_match_count=0,
+                engine=ENGINE_AUTO):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        o = self._opts(norm, k, ratio, cross_check, distinct, min_match_count, engine)
+        self._check(_lib.sfm_match_pairs_enqueue(self._ctx, pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
+                                                 C.byref(o)))
+
+    def collect(self) -> MatchResult:
+        res = C.c_void_p()
+        self._check(_lib.sfm_match_pairs_collect(self._ctx, C.byref(res)))
+        try:
+            n = _lib.sfm_result_n_pairs(res)
+            offsets = np.ctypeslib.as_array(_lib.sfm_result_offsets(res), shape=(n + 1,)).copy()
+            total = int(offsets[n])
+            dropped = (np.ctypeslib.as_array(_lib.sfm_result_dropped(res), shape=(n,)).copy() if n else
+                       np.zeros(0, np.uint8))
+            if total:
+                buf = (C.c_char * (total * 16)).from_address(_lib.sfm_result_matches(res))
+                matches = np.frombuffer(buf, dtype=DMATCH_DTYPE, count=total).copy()
+            else:
+                matches = np.zeros(0, DMATCH_DTYPE)
+        finally:
+            _lib.sfm_result_free(res)
+        return MatchResult(offsets, matches, dropped)
+
+    def match_pairs(self, pairs, norm, **kw) -> MatchResult:
+        self.enqueue(pairs, norm, **kw)
+        return self.collect()
+
+    # ---- operator level
+    def knn_match(self, query: np.ndarray, train: np.ndarray, norm: int, k: int = 2, engine: int = ENGINE_AUTO):
+        """cv::batchDistance-shaped result: (nidx[nq,k] int32, dist[nq,k] float32)."""
+        dq, dt = _depth_of(query), _depth_of(train)
+        if dq != dt or query.ndim != 2 or train.ndim != 2 or query.shape[1] != train.shape[1]:
+            raise SfmError(ERR_INVALID, "type == src2.type() && src1.cols == src2.cols (cv::batchDistance assert)")
+        if query.strides[1] != query.itemsize:
+            query = np.ascontiguousarray(query)
+        if train.strides[1] != train.itemsize:
+            train = np.ascontiguousarray(train)
+        nq, nt, cols = query.shape[0], train.shape[0], query.shape[1]
+        nidx = np.full((nq, k), -1, np.int32)
+        dist = np.full((nq, k), np.inf, np.float32)
+        qs = query.strides[0] if nq > 1 else cols * query.itemsize
+        ts = train.strides[0] if nt > 1 else cols * train.itemsize
+        self._check(_lib.sfm_knn_match(self._ctx, C.c_void_p(query.ctypes.data if nq else None), C.c_int(nq),
+                                       C.c_size_t(qs), C.c_void_p(train.ctypes.data if nt else None), C.c_int(nt),
+                                       C.c_size_t(ts), C.c_int(cols), C.c_int(dq), C.c_int(norm), C.c_int(k),
+                                       C.c_int(engine), nidx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
+        return nidx, dist

@@ -1,0 +1,71 @@
+// kernels.h — host-side launcher prototypes of every hand-written kernel in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sfm {
+
+// ---- knn_simt.cu
+constexpr int kSimtRowsPerUnit = 128;
+constexpr int kF32RowsPerUnit = 32;
+cudaError_t launch_knn2_hamming_popc(const uint8_t* bank, const PairDesc* pairs, const int64_t* unit_prefix,
+                                     int n_pairs, int64_t n_units, Top2* out, cudaStream_t s);
+cudaError_t launch_knn2_l2_u8_dp4a(const uint8_t* bank, const int32_t* norm2, const PairDesc* pairs,
+                                   const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, cudaStream_t s);
+cudaError_t launch_knn2_l2_f32(const float* bank, int cols, const PairDesc* pairs, const int64_t* unit_prefix,
+                               int n_pairs, int64_t n_units, Top2* out, cudaStream_t s);
+
+// ---- knn_l2_tc.cu  (tcgen05 / TMA / TMEM)
+constexpr int kTcRowsPerUnit = 128;
+struct TcLaunchInfo { int grid; int smem_bytes; };
+// tmap: CUtensorMap (128 B, 64-B aligned, passed by value as __grid_constant__) over the u8 bank
+cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_host, const int32_t* ckey,
+                                 const int32_t* norm2, const PairDesc* pairs, const int64_t* unit_prefix,
+                                 int n_pairs, int64_t n_units, Top2* out, int sm_count, cudaStream_t s);
+
+// ---- post.cu
+cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols, uint8_t* dst,
+                                  int* not_integer_flag, cudaStream_t s);
+cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* row_valid_end /*per 256-row block*/,
+                               int32_t* norm2, int32_t* ckey, cudaStream_t s);
+struct FilterParams {
+    int norm;            // SFM_NORM_*
+    int k;               // 1 or 2
+    double ratio;
+    int cross_check;
+    int distinct;
+};
+// Everything the filter passes need.  Staging rows of pair p start at out_prefix[p] (multiple of 256);
+// per-train-row side arrays (reverse knn for cross-check, best-match counters for distinct) of pair p
+// start at t_prefix[p] (multiple of 256).
+struct FilterArgs {
+    const Top2* top2;
+    const Top2* rev;             // cross-check: knn of train rows against query rows (top-1 used)
+    const PairDesc* pairs;
+    const int64_t* out_prefix;   // n_pairs + 1
+    const int64_t* t_prefix;     // n_pairs + 1
+    int n_pairs;
+    int64_t staged_rows;         // out_prefix[n_pairs]
+    FilterParams fp;
+    int32_t* train_cnt;          // distinct: zeroed by the caller
+};
+// pass 1 (only with distinct): count how often each train row is the best match of a kept query row
+cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s);
+// pass 2: number of surviving matches per 256-row chunk
+cudaError_t launch_filter_count(const FilterArgs& a, int32_t* chunk_counts, cudaStream_t s);
+// scan: chunk counts -> chunk offsets; per-pair counts with min_match_count applied -> absolute pair
+// offsets continuing *running_total (device scalar, updated), dropped flags
+cudaError_t launch_scan_offsets(const int32_t* chunk_counts, int64_t n_chunks, const int64_t* out_prefix, int n_pairs,
+                                int min_match_count, int64_t* chunk_excl /*n_chunks+1*/, int64_t* pair_counts_tmp,
+                                int64_t* pair_offsets /*n_pairs*/, uint8_t* pair_dropped, int64_t* running_total,
+                                cudaStream_t s);
+// pass 3: ordered compaction into the DMatch output (ascending queryIdx inside every pair)
+cudaError_t launch_compact(const FilterArgs& a, const int64_t* chunk_excl, const int64_t* pair_offsets,
+                           const uint8_t* pair_dropped, DMatch* out, int64_t out_capacity, int* overflow_flag,
+                           cudaStream_t s);
+// raw knn result -> cv::batchDistance-shaped arrays (sfm_knn_match)
+cudaError_t launch_top2_to_arrays(const Top2* top2, int nq, int k, int norm, int32_t* nidx, float* dist, cudaStream_t s);
+
+}  // namespace sfm

@@ -1,0 +1,274 @@
+// knn_l2_tc.cu — SIFT (128-byte, u8-valued) squared-L2 knn(k=2) on the 5th-gen tensor cores.
+//
+// Replaces cv::batchDistance(NORM_L2, K=2) under BFMatcher::knnMatch for every pair the strategies issue
+// (UnorderedFeatureMatchingStrategy.cpp:51, VideoFeatureMatchingStrategy.cpp:62, GridFeatureMatchingStrategy.cpp:105).
+//
+// dist^2(a,b) = |a|^2 + |b|^2 - 2 a.b ; a.b is a dense u8 x u8 -> s32 contraction (K = 128) computed with
+// tcgen05.mma.kind::i8, operands staged in shared memory by TMA (128-byte swizzle, one swizzle atom per
+// descriptor row), accumulators in TMEM.  The per-row top-2 never leaves the SM: epilogue warps read the
+// accumulators with tcgen05.ld (one TMEM lane = one query row = one thread) and keep a running top-2 of
+//     key = (|b_j|^2 - 2 a.b_j) * 256 + (j mod 256)          = ckey_j - 512 * acc
+// a single IMAD per element from a per-train-row constant ckey_j that TMA-bulk-copies in with the tile.
+// Keys are unique inside a tile, so "ties -> lowest trainIdx"  is free; across tiles the
+// running state is a 64-bit (value, global column) key.  All arithmetic is integer: results are bit-exact.
+//
+// Persistent kernel, one CTA per SM, warp-specialised:
+//   warp 0      TMA producer   (A tile once per unit, B tile + ckeys per train tile, 4-stage ring)
+//   warp 1      MMA issuer     (4 x tcgen05.mma M128 N256 K32 per tile, 2 TMEM accumulator stages)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue group 0 (even tiles)   } thread = query row, TMEM lane quarter = warp % 4
+//   warps 8-11  epilogue group 1 (odd tiles)    }
+// unit = (pair, block of 128 query rows); units are dealt round-robin to CTAs so that concurrently running
+// CTAs stream the same train image out of L2.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sfm {
+
+namespace tc {
+constexpr int BM = 128, BN = 256, KB = 128;
+constexpr int kBStages = 4, kAStages = 2, kAccStages = 2, kCkSlots = 8;
+constexpr int kABytes = BM * KB, kBBytes = BN * KB, kCkBytes = BN * 4;
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+// shared memory carve-up (offsets from a 1024-byte aligned base)
+constexpr int offB = 0;
+constexpr int offA = offB + kBStages * kBBytes;
+constexpr int offCk = offA + kAStages * kABytes;
+constexpr int offMerge = offCk + kCkSlots * kCkBytes;            // [128][2] int64
+constexpr int offBar = offMerge + BM * 2 * 8;
+constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages + kCkSlots;
+constexpr int offTmemPtr = offBar + kNumBars * 8;
+constexpr int kSmemBytes = offTmemPtr + 16 + 1024;                // + alignment slack
+constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
+constexpr int64_t kEmptyKey = INT64_MAX;
+}  // namespace tc
+
+struct UnitInfo { PairDesc pd; int rb; int n_tiles; };
+
+__device__ __forceinline__ UnitInfo decode_unit(const PairDesc* __restrict__ pairs, const int64_t* __restrict__ unit_prefix,
+                                                int n_pairs, int64_t unit) {
+    UnitInfo u;
+    const int p = find_segment(unit_prefix, n_pairs, unit);
+    u.pd = pairs[p];
+    u.rb = static_cast<int>(unit - unit_prefix[p]);
+    u.n_tiles = (u.pd.nt + tc::BN - 1) / tc::BN;
+    return u;
+}
+
+// (m1, m2) <- two smallest of {m1, m2, k}, m1 <= m2
+__device__ __forceinline__ void top2_key(int32_t k, int32_t& m1, int32_t& m2) {
+    m2 = min(m2, max(m1, k));
+    m1 = min(m1, k);
+}
+__device__ __forceinline__ void top2_key64(int64_t k, int64_t& m1, int64_t& m2) {
+    m2 = min(m2, max(m1, k));
+    m1 = min(m1, k);
+}
+
+__global__ void __launch_bounds__(tc::kThreads, 1)
+knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const int32_t* __restrict__ ckey, const int32_t* __restrict__ norm2,
+                     const PairDesc* __restrict__ pairs, const int64_t* __restrict__ unit_prefix, int n_pairs,
+                     int64_t n_units, Top2* __restrict__ out) {
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + offBar;
+    auto b_full = [&](int i) { return bar0 + 8u * i; };
+    auto b_empty = [&](int i) { return bar0 + 8u * (kBStages + i); };
+    auto a_full = [&](int i) { return bar0 + 8u * (2 * kBStages + i); };
+    auto a_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + kAStages + i); };
+    auto acc_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + i); };
+    auto acc_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + kAccStages + i); };
+    auto ck_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + 2 * kAccStages + i); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + offTmemPtr);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 128); }
+        for (int i = 0; i < kCkSlots; ++i) mbar_init(ck_full(i), 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(base + offTmemPtr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        // the whole warp walks the schedule (keeps the warp converged for the final barrier); lane 0 issues
+        uint32_t tile_iter = 0, unit_iter = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitInfo u = decode_unit(pairs, unit_prefix, n_pairs, unit);
+            if (u.n_tiles == 0) continue;
+            const int as = unit_iter % kAStages;
+            mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(a_full(as), kABytes);
+                tma_load_2d(base + offA + as * kABytes, &tmap_a, 0, u.pd.q_row0 + u.rb * BM, a_full(as));
+            }
+            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+                const int st = tile_iter % kBStages;
+                mbar_wait(b_empty(st), ((tile_iter / kBStages) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(b_full(st), kBBytes);
+                    tma_load_2d(base + offB + st * kBBytes, &tmap_b, 0, u.pd.t_row0 + t * BN, b_full(st));
+                    // ckey ring: 8 slots, the producer is never more than kBStages + kAccStages = 6 tiles ahead
+                    // of the epilogue, so a slot is free again before it is reloaded
+                    const int cs = tile_iter % kCkSlots;
+                    mbar_arrive_expect_tx(ck_full(cs), kCkBytes);
+                    bulk_load_1d(base + offCk + cs * kCkBytes, ckey + u.pd.t_row0 + t * BN, kCkBytes, ck_full(cs));
+                }
+                __syncwarp();
+            }
+            ++unit_iter;
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer (lane 0 issues)
+        uint32_t tile_iter = 0, unit_iter = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitInfo u = decode_unit(pairs, unit_prefix, n_pairs, unit);
+            if (u.n_tiles == 0) continue;
+            const int as = unit_iter % kAStages;
+            mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
+            const uint64_t adesc = umma_desc_sw128(base + offA + as * kABytes);
+            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+                const int acc = tile_iter % kAccStages;
+                const int st = tile_iter % kBStages;
+                mbar_wait(acc_empty(acc), ((tile_iter / kAccStages) & 1) ^ 1);
+                mbar_wait(b_full(st), (tile_iter / kBStages) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t bdesc = umma_desc_sw128(base + offB + st * kBBytes);
+                    const uint32_t d = tmem_base + acc * BN;
+#pragma unroll
+                    for (int k = 0; k < KB / 32; ++k)      // K = 32 bytes per tcgen05.mma.kind::i8; +32 B = +2 encoded
+                        umma_i8(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                    umma_commit(b_empty(st));              // smem stage free once these MMAs retire
+                    umma_commit(acc_full(acc));            // accumulator ready for the epilogue
+                    if (t == u.n_tiles - 1) umma_commit(a_empty(as));
+                }
+                __syncwarp();
+            }
+            ++unit_iter;
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================================================================ epilogue: running top-2 per query row
+        const int group = (warp - kEpiWarp0) >> 2;         // 0: even tiles, 1: odd tiles
+        const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+        const int row_in_unit = quarter * 32 + lane;
+        int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
+        uint32_t tile_iter = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitInfo u = decode_unit(pairs, unit_prefix, n_pairs, unit);
+            int64_t r1 = kEmptyKey, r2 = kEmptyKey;
+            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+                if ((tile_iter & 1) != static_cast<uint32_t>(group)) continue;
+                const int acc = tile_iter % kAccStages;
+                const int cs = tile_iter % kCkSlots;
+                mbar_wait(ck_full(cs), (tile_iter / kCkSlots) & 1);
+                mbar_wait(acc_full(acc), (tile_iter / kAccStages) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+                const int4* ck4 = reinterpret_cast<const int4*>(base_ptr + offCk + cs * kCkBytes);
+                int32_t m1a = INT32_MAX, m2a = INT32_MAX, m1b = INT32_MAX, m2b = INT32_MAX;
+                uint32_t v[2][32];
+                tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t (&cur)[32] = v[c & 1];
+                    // make the loaded registers depend on the wait
+                    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                                 : "+r"(cur[0]), "+r"(cur[1]), "+r"(cur[2]), "+r"(cur[3]), "+r"(cur[4]), "+r"(cur[5]),
+                                   "+r"(cur[6]), "+r"(cur[7]), "+r"(cur[8]), "+r"(cur[9]), "+r"(cur[10]), "+r"(cur[11]),
+                                   "+r"(cur[12]), "+r"(cur[13]), "+r"(cur[14]), "+r"(cur[15]), "+r"(cur[16]),
+                                   "+r"(cur[17]), "+r"(cur[18]), "+r"(cur[19]), "+r"(cur[20]), "+r"(cur[21]),
+                                   "+r"(cur[22]), "+r"(cur[23]), "+r"(cur[24]), "+r"(cur[25]), "+r"(cur[26]),
+                                   "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
+                                 :: "memory");
+                    if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int4 ck = ck4[c * 8 + (j >> 2)];           // smem broadcast
+                        top2_key(ck.x - 512 * static_cast<int32_t>(cur[j]), m1a, m2a);
+                        top2_key(ck.y - 512 * static_cast<int32_t>(cur[j + 1]), m1b, m2b);
+                        top2_key(ck.z - 512 * static_cast<int32_t>(cur[j + 2]), m1a, m2a);
+                        top2_key(ck.w - 512 * static_cast<int32_t>(cur[j + 3]), m1b, m2b);
+                    }
+                }
+                // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
+                tc_fence_before();
+                mbar_arrive(acc_empty(acc));
+                // merge the two chains (keys unique inside a tile) and fold into the 64-bit running state
+                const int32_t t1 = min(m1a, m1b);
+                const int32_t t2 = min(max(m1a, m1b), min(m2a, m2b));
+                const int64_t colbase = static_cast<int64_t>(t) * BN;
+                const int64_t k1 = static_cast<int64_t>(t1 >> 8) * (1ll << 32) + (colbase + (t1 & 255));
+                const int64_t k2 = static_cast<int64_t>(t2 >> 8) * (1ll << 32) + (colbase + (t2 & 255));
+                top2_key64(k1, r1, r2);
+                top2_key64(k2, r1, r2);
+            }
+            // ---- unit end: combine the two groups, write the raw knn result of this query row
+            if (group == 1) { merge[row_in_unit * 2] = r1; merge[row_in_unit * 2 + 1] = r2; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (group == 0) {
+                top2_key64(merge[row_in_unit * 2], r1, r2);
+                top2_key64(merge[row_in_unit * 2 + 1], r1, r2);
+                const int row = u.rb * BM + row_in_unit;
+                if (row < u.pd.nq) {
+                    const int32_t na = norm2[u.pd.q_row0 + row];
+                    const int32_t v1 = static_cast<int32_t>(r1 >> 32), v2 = static_cast<int32_t>(r2 >> 32);
+                    const bool has1 = r1 != kEmptyKey && v1 < (kSentinelKey >> 8);
+                    const bool has2 = r2 != kEmptyKey && v2 < (kSentinelKey >> 8);
+                    Top2 o;
+                    o.i0 = has1 ? static_cast<int32_t>(r1 & 0xFFFFFFFF) : -1;
+                    o.i1 = has2 ? static_cast<int32_t>(r2 & 0xFFFFFFFF) : -1;
+                    o.d0 = has1 ? static_cast<float>(na + v1) : __int_as_float(0x7f800000);
+                    o.d1 = has2 ? static_cast<float>(na + v2) : __int_as_float(0x7f800000);
+                    out[u.pd.out_row0 + row] = o;
+                }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_host, const int32_t* ckey,
+                                 const int32_t* norm2, const PairDesc* pairs, const int64_t* unit_prefix,
+                                 int n_pairs, int64_t n_units, Top2* out, int sm_count, cudaStream_t s) {
+    if (n_units == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tc::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
+    const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
+    const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
+    knn2_l2_u8_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(*ta, *tb, ckey, norm2, pairs, unit_prefix, n_pairs,
+                                                                    n_units, out);
+    return cudaGetLastError();
+}
+
+}  // namespace sfm

@@ -1,0 +1,279 @@
+// post.cu — the small kernels around the knn kernels:
+//   pack_f32_to_u8   CV_32F integer-valued SIFT rows -> u8 bank rows (+ integer-valued check)
+//   norms_ckeys      |b|^2 per bank row and the packed per-column key constant of the tcgen05 epilogue
+//   filter_*         Lowe ratio test in double (UnorderedFeatureMatchingStrategy.cpp:55-65), match() k=1 mode
+//                    (…:66-72), cross-check (cv::BFMatcher crossCheck semantics), distinct (SfM.cpp:547-564)
+//   scan_offsets     per-pair counts, min-match-count drop (SfM.cpp:566-570), output offsets
+//   compact          ordered DMatch lists (ascending queryIdx, pair order)
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sfm {
+
+constexpr int kNormL2 = 4;
+
+// ------------------------------------------------------------------------------------------------ upload helpers
+__global__ void pack_f32_to_u8_kernel(const float* __restrict__ src, size_t stride, int n_rows, int cols,
+                                      uint8_t* __restrict__ dst, int* __restrict__ bad) {
+    const int vec_per_row = cols >> 2;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<int64_t>(n_rows) * vec_per_row) return;
+    const int r = static_cast<int>(i / vec_per_row), v = static_cast<int>(i - static_cast<int64_t>(r) * vec_per_row);
+    const float4 f = *reinterpret_cast<const float4*>(src + r * stride + 4 * v);
+    const float e[4] = {f.x, f.y, f.z, f.w};
+    uint32_t w = 0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float x = e[k];
+        ok = ok && (x >= 0.f) && (x <= 255.f) && (x == rintf(x));   // NaN fails x >= 0
+        w |= (static_cast<uint32_t>(ok ? static_cast<int>(x) : 0) & 0xFFu) << (8 * k);
+    }
+    if (!ok) atomicOr(bad, 1);
+    *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r) * cols + 4 * v) = w;
+}
+
+cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols, uint8_t* dst,
+                                  int* not_integer_flag, cudaStream_t s) {
+    const int64_t n = static_cast<int64_t>(n_rows) * (cols >> 2);
+    if (n == 0) return cudaSuccess;
+    pack_f32_to_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, src_stride_elems, n_rows, cols, dst,
+                                                                                  not_integer_flag);
+    return cudaGetLastError();
+}
+
+// one warp per 128-byte row
+__global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t padded_rows,
+                                   const int32_t* __restrict__ valid_in_block, int32_t* __restrict__ norm2,
+                                   int32_t* __restrict__ ckey) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= padded_rows) return;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(bank + row * 128 + 4 * lane);
+    uint32_t s = __dp4a(w, w, 0u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const int col = static_cast<int>(row & (kRowAlign - 1));
+        const bool valid = col < valid_in_block[row / kRowAlign];
+        norm2[row] = static_cast<int32_t>(s);
+        // key = (|b|^2 - 2ab) * 256 + col  ==  ckey - 512 * ab
+        ckey[row] = valid ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col)) : (kSentinelKey | col);
+    }
+}
+
+cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* valid_in_block,
+                               int32_t* norm2, int32_t* ckey, cudaStream_t s) {
+    if (padded_rows == 0) return cudaSuccess;
+    const int64_t threads = padded_rows * 32;
+    norms_ckeys_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(bank, padded_rows, valid_in_block,
+                                                                                     norm2, ckey);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ filters
+struct RowCtx { int p; int row; bool valid; PairDesc pd; Top2 t; };
+
+__device__ __forceinline__ RowCtx load_row(const FilterArgs& a, int64_t srow) {
+    RowCtx c;
+    c.p = find_segment(a.out_prefix, a.n_pairs, srow);
+    c.pd = a.pairs[c.p];
+    c.row = static_cast<int>(srow - a.out_prefix[c.p]);
+    c.valid = c.row < c.pd.nq;
+    if (c.valid) c.t = a.top2[srow];
+    return c;
+}
+
+__device__ __forceinline__ float final_distance(int norm, float d) {
+    // L2: DMatch.distance = float32(sqrt(float32(sum))) with IEEE rounding
+    return norm == kNormL2 ? __fsqrt_rn(d) : d;
+}
+
+// keep-decision before the distinct filter
+__device__ __forceinline__ bool keep_basic(const FilterArgs& a, const RowCtx& c, float& dist0) {
+    if (!c.valid || c.t.i0 < 0) return false;
+    dist0 = final_distance(a.fp.norm, c.t.d0);
+    if (a.fp.cross_check) {
+        // mutual nearest neighbour: NN(train row NN(q)) == q
+        const Top2 r = a.rev[a.t_prefix[c.p] + c.t.i0];
+        return r.i0 == c.row;
+    }
+    if (a.fp.k < 2 || c.t.i1 < 0) return true;       // match() semantics / single neighbour kept (:62-64)
+    const float dist1 = final_distance(a.fp.norm, c.t.d1);
+    // float < float * double(0.7): evaluated in double (UnorderedFeatureMatchingStrategy.cpp:55-59)
+    return static_cast<double>(dist0) < static_cast<double>(dist1) * a.fp.ratio;
+}
+
+__device__ __forceinline__ bool keep_final(const FilterArgs& a, const RowCtx& c, float& dist0) {
+    bool k = keep_basic(a, c, dist0);
+    if (k && a.fp.distinct) k = a.train_cnt[a.t_prefix[c.p] + c.t.i0] == 1;
+    return k;
+}
+
+__global__ void __launch_bounds__(256) filter_mark_kernel(FilterArgs a) {
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (srow >= a.staged_rows) return;
+    const RowCtx c = load_row(a, srow);
+    float d;
+    if (keep_basic(a, c, d)) atomicAdd(a.train_cnt + a.t_prefix[c.p] + c.t.i0, 1);
+}
+
+__global__ void __launch_bounds__(256) filter_count_kernel(FilterArgs a, int32_t* __restrict__ chunk_counts) {
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    bool k = false;
+    if (srow < a.staged_rows) {
+        const RowCtx c = load_row(a, srow);
+        float d;
+        k = keep_final(a, c, d);
+    }
+    const int n = __syncthreads_count(k);
+    if (threadIdx.x == 0) chunk_counts[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(256) compact_kernel(FilterArgs a, const int64_t* __restrict__ chunk_excl,
+                                                      const int64_t* __restrict__ pair_offsets,
+                                                      const uint8_t* __restrict__ pair_dropped, DMatch* __restrict__ out,
+                                                      int64_t capacity, int* __restrict__ overflow) {
+    __shared__ int warp_cnt[8];
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool k = false;
+    float d = 0.f;
+    RowCtx c;
+    c.p = 0; c.row = 0; c.valid = false;
+    if (srow < a.staged_rows) {
+        c = load_row(a, srow);
+        k = keep_final(a, c, d);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = __popc(bal & ((1u << lane) - 1));
+    for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+    if (!k) return;
+    // a chunk never straddles two pairs (staging rows of a pair start at a multiple of 256)
+    if (pair_dropped[c.p]) return;
+    const int64_t first_chunk = a.out_prefix[c.p] >> 8;
+    const int64_t pos = pair_offsets[c.p] + (chunk_excl[blockIdx.x] - chunk_excl[first_chunk]) + before;
+    if (pos >= capacity) { atomicOr(overflow, 1); return; }
+    DMatch m;
+    m.queryIdx = c.row; m.trainIdx = c.t.i0; m.imgIdx = 0; m.distance = d;
+    out[pos] = m;
+}
+
+static inline unsigned chunks_of(int64_t rows) { return static_cast<unsigned>((rows + 255) / 256); }
+
+cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    filter_mark_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_filter_count(const FilterArgs& a, int32_t* chunk_counts, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    filter_count_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a, chunk_counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_compact(const FilterArgs& a, const int64_t* chunk_excl, const int64_t* pair_offsets,
+                           const uint8_t* pair_dropped, DMatch* out, int64_t out_capacity, int* overflow_flag,
+                           cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    compact_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a, chunk_excl, pair_offsets, pair_dropped, out, out_capacity,
+                                                            overflow_flag);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ scan
+// Single-CTA exclusive scan over `n` values produced by `get(i)`, results through `put(i, excl)`; returns the
+// total to every thread.  n is at most a few hundred thousand (one value per 256 staged rows).
+template <class Get, class Put>
+__device__ int64_t block_exclusive_scan(int64_t n, Get get, Put put) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t total_s;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t per = (n + nthr - 1) / nthr;
+    const int64_t lo = min(n, per * tid), hi = min(n, lo + per);
+    int64_t sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += get(i);
+    int64_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = lane < (nthr >> 5) ? warp_sums[lane] : 0;
+        int64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sums[lane] = wi - w;                 // exclusive prefix of warp totals
+        if (lane == 31) total_s = wi;
+    }
+    __syncthreads();
+    int64_t run = warp_sums[warp] + (incl - sum);
+    for (int64_t i = lo; i < hi; ++i) { const int64_t v = get(i); put(i, run); run += v; }
+    __syncthreads();
+    return total_s;
+}
+
+__global__ void __launch_bounds__(1024) scan_offsets_kernel(const int32_t* __restrict__ chunk_counts, int64_t n_chunks,
+                                                            const int64_t* __restrict__ out_prefix, int n_pairs,
+                                                            int min_match_count, int64_t* __restrict__ chunk_excl,
+                                                            int64_t* __restrict__ pair_counts,
+                                                            int64_t* __restrict__ pair_offsets,
+                                                            uint8_t* __restrict__ pair_dropped,
+                                                            int64_t* __restrict__ running_total) {
+    const int64_t total = block_exclusive_scan(
+        n_chunks, [&](int64_t i) { return static_cast<int64_t>(chunk_counts[i]); },
+        [&](int64_t i, int64_t e) { chunk_excl[i] = e; });
+    if (threadIdx.x == 0) chunk_excl[n_chunks] = total;
+    __syncthreads();
+    for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+        const int64_t c = chunk_excl[out_prefix[p + 1] >> 8] - chunk_excl[out_prefix[p] >> 8];
+        const bool drop = c < min_match_count;
+        pair_dropped[p] = drop ? 1 : 0;
+        pair_counts[p] = drop ? 0 : c;
+    }
+    __syncthreads();
+    const int64_t base = *running_total;
+    const int64_t kept = block_exclusive_scan(
+        n_pairs, [&](int64_t i) { return pair_counts[i]; },
+        [&](int64_t i, int64_t e) { pair_offsets[i] = base + e; });
+    if (threadIdx.x == 0) *running_total = base + kept;
+}
+
+cudaError_t launch_scan_offsets(const int32_t* chunk_counts, int64_t n_chunks, const int64_t* out_prefix, int n_pairs,
+                                int min_match_count, int64_t* chunk_excl, int64_t* pair_counts_tmp, int64_t* pair_offsets,
+                                uint8_t* pair_dropped, int64_t* running_total, cudaStream_t s) {
+    if (n_pairs == 0) return cudaSuccess;
+    scan_offsets_kernel<<<1, 1024, 0, s>>>(chunk_counts, n_chunks, out_prefix, n_pairs, min_match_count, chunk_excl,
+                                           pair_counts_tmp, pair_offsets, pair_dropped, running_total);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ knnMatch arrays
+__global__ void top2_to_arrays_kernel(const Top2* __restrict__ top2, int nq, int k, int norm, int32_t* __restrict__ nidx,
+                                      float* __restrict__ dist) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nq) return;
+    const Top2 t = top2[r];
+    const float inf = __int_as_float(0x7f800000);
+    nidx[r * k] = t.i0;
+    dist[r * k] = t.i0 >= 0 ? final_distance(norm, t.d0) : inf;
+    if (k > 1) {
+        nidx[r * k + 1] = t.i1;
+        dist[r * k + 1] = t.i1 >= 0 ? final_distance(norm, t.d1) : inf;
+    }
+}
+
+cudaError_t launch_top2_to_arrays(const Top2* top2, int nq, int k, int norm, int32_t* nidx, float* dist, cudaStream_t s) {
+    if (nq == 0) return cudaSuccess;
+    top2_to_arrays_kernel<<<(nq + 255) / 256, 256, 0, s>>>(top2, nq, k, norm, nidx, dist);
+    return cudaGetLastError();
+}
+
+}  // namespace sfm

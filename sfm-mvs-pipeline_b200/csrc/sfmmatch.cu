@@ -1,0 +1,681 @@
+// sfmmatch.cu — implementation of the C ABI declared in include/sfmmatch.h.
+//
+// Host side of the matching stage: device bank management, batching of the pair list, kernel
+// sequencing on one CUDA stream, result marshalling.  No CPU compute fallback exists: every entry
+// point that computes distances launches the kernels of csrc/ or fails with SFM_ERR_CUDA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sfmmatch.h"
+#include "kernels.h"
+
+using namespace sfm;
+
+static_assert(sizeof(sfm_dmatch) == 16 && sizeof(DMatch) == 16, "DMatch must be byte-compatible with cv::DMatch");
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+inline int64_t pad_rows(int64_t n) { return (n + kRowAlign - 1) / kRowAlign * kRowAlign; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Device-resident descriptor bank.  Image i occupies padded rows [row0[i], row0[i] + pad(n_rows[i])).
+struct Bank {
+    int n_images = 0, cols = 0, depth = 0;
+    bool u8_valued = false;          // d_u8 holds the descriptors (ORB bytes, or u8-valued SIFT)
+    bool have_f32 = false;           // d_f32 holds float descriptors (non-integer data only)
+    std::vector<int32_t> n_rows;
+    std::vector<int64_t> row0;
+    int64_t padded_rows = 0;
+    DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid;
+    alignas(64) CUtensorMap tmap_a, tmap_b;
+    bool have_tmap = false;
+    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); }
+};
+
+struct RunState {                    // what collect() needs from the last enqueue
+    bool valid = false;
+    int64_t n_pairs = 0;
+    int64_t total_query_rows = 0;
+    std::vector<int32_t> pairs;      // kept for the automatic capacity retry
+    sfm_opts opts{};
+};
+
+}  // namespace
+
+struct sfm_result {
+    int64_t n_pairs = 0;
+    PinBuf offsets, matches, dropped;
+};
+
+struct sfm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::mutex mu;
+    EncodeTiledFn encode = nullptr;
+    Bank bank, scratch;
+    // workspace
+    DevBuf d_pairs, d_rev_pairs, d_unit_prefix, d_rev_unit_prefix, d_out_prefix, d_t_prefix;
+    DevBuf d_top2, d_rev, d_train_cnt, d_chunk_counts, d_chunk_excl, d_pair_counts, d_pair_offsets, d_dropped;
+    DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
+    DevBuf d_out, d_knn;
+    int64_t out_capacity = 0;
+    PinBuf h_meta, h_stage[2], h_scalars, h_knn;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaEvent_t meta_ev = nullptr;   // h_meta may be rewritten once this has fired
+    RunState run;
+    int64_t stat_launches = 0, stat_h2d = 0, stat_d2h = 0;
+    size_t staging_budget_rows = 0;
+};
+
+namespace {
+
+int fail(sfm_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU_TRY(ctx, expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(ctx, SFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+int make_tmaps(sfm_ctx* c, Bank& b) {
+    b.have_tmap = false;
+    if (!(b.u8_valued && b.cols == 128) || b.padded_rows == 0) return SFM_OK;
+    const cuuint64_t dims[2] = {128, static_cast<cuuint64_t>(b.padded_rows)};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box_a[2] = {128, kTcRowsPerUnit};
+    const cuuint32_t box_b[2] = {128, 256};
+    CUresult r = c->encode(&b.tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.d_u8.p, dims, strides, box_a, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(r));
+    r = c->encode(&b.tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.d_u8.p, dims, strides, box_b, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(r));
+    b.have_tmap = true;
+    return SFM_OK;
+}
+
+// Lay out the bank (row offsets), allocate, zero the padding.
+int bank_layout(sfm_ctx* c, Bank& b, int n_images, const int32_t* n_rows, int cols, int depth) {
+    if (n_images < 0 || cols <= 0) return fail(c, SFM_ERR_INVALID, "bank: bad n_images/cols");
+    if (depth != SFM_CV_8U && depth != SFM_CV_32F) return fail(c, SFM_ERR_INVALID, "bank: depth must be CV_8U or CV_32F");
+    if (depth == SFM_CV_8U && cols % 16 != 0) return fail(c, SFM_ERR_INVALID, "bank: CV_8U descriptors need cols % 16 == 0");
+    if (depth == SFM_CV_32F && cols % 4 != 0) return fail(c, SFM_ERR_INVALID, "bank: CV_32F descriptors need cols % 4 == 0");
+    b.n_images = n_images; b.cols = cols; b.depth = depth;
+    b.n_rows.assign(n_rows, n_rows + n_images);
+    b.row0.resize(n_images + 1);
+    int64_t r = 0;
+    for (int i = 0; i < n_images; ++i) {
+        if (n_rows[i] < 0) return fail(c, SFM_ERR_INVALID, "bank: negative row count");
+        if (n_rows[i] >= SFM_MAX_ROWS)
+            return fail(c, SFM_ERR_CAPACITY, "bank: image has >= 2^18 descriptors (OpenCV IMGIDX_ONE limit)");
+        b.row0[i] = r;
+        r += pad_rows(n_rows[i]);
+    }
+    b.row0[n_images] = r;
+    b.padded_rows = r;
+    if (r >= (int64_t(1) << 31)) return fail(c, SFM_ERR_CAPACITY, "bank: more than 2^31 padded rows");
+    return SFM_OK;
+}
+
+// After the raw descriptors are on the device (d_f32 for CV_32F, d_u8 for CV_8U): pack / norms / tensor maps.
+int bank_finish(sfm_ctx* c, Bank& b) {
+    cudaStream_t s = c->stream;
+    b.u8_valued = false; b.have_f32 = false;
+    if (b.depth == SFM_CV_32F) {
+        b.have_f32 = true;
+        if (b.cols == 128 && b.padded_rows > 0) {
+            CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
+            int* flag = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 12);
+            CU_TRY(c, cudaMemsetAsync(flag, 0, 4, s));
+            CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>(), 128, static_cast<int>(b.padded_rows), 128,
+                                            b.d_u8.as<uint8_t>(), flag, s));
+            c->stat_launches++;
+            int* h = c->h_scalars.as<int>();
+            CU_TRY(c, cudaMemcpyAsync(h, flag, 4, cudaMemcpyDeviceToHost, s));
+            CU_TRY(c, cudaStreamSynchronize(s));
+            if (*h == 0) { b.u8_valued = true; b.have_f32 = false; b.d_f32.release(); }
+        }
+    } else {
+        b.u8_valued = true;
+    }
+    if (b.u8_valued && b.cols == 128 && b.padded_rows > 0) {
+        // valid rows per 256-row block
+        const int64_t nblk = b.padded_rows / kRowAlign;
+        std::vector<int32_t> valid(nblk);
+        for (int i = 0; i < b.n_images; ++i) {
+            const int64_t b0 = b.row0[i] / kRowAlign, nb = pad_rows(b.n_rows[i]) / kRowAlign;
+            for (int64_t k = 0; k < nb; ++k)
+                valid[b0 + k] = static_cast<int32_t>(std::min<int64_t>(kRowAlign, std::max<int64_t>(0, b.n_rows[i] - k * kRowAlign)));
+        }
+        CU_TRY(c, b.d_valid.ensure(nblk * 4));
+        CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid.data(), nblk * 4, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
+        CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
+        CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>(), b.padded_rows, b.d_valid.as<int32_t>(), b.d_norm2.as<int32_t>(),
+                                     b.d_ckey.as<int32_t>(), s));
+        c->stat_launches++;
+        CU_TRY(c, cudaStreamSynchronize(s));      // `valid` is a pageable temporary
+    }
+    return make_tmaps(c, b);
+}
+
+int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                     const size_t* step_bytes, int depth) {
+    int rc = bank_layout(c, b, n_images, n_rows, cols, depth);
+    if (rc != SFM_OK) return rc;
+    cudaStream_t s = c->stream;
+    const size_t esz = depth == SFM_CV_32F ? 4 : 1;
+    const size_t row_bytes = static_cast<size_t>(cols) * esz;
+    DevBuf& dst = depth == SFM_CV_32F ? b.d_f32 : b.d_u8;
+    CU_TRY(c, dst.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * row_bytes)));
+    CU_TRY(c, cudaMemsetAsync(dst.p, 0, static_cast<size_t>(b.padded_rows) * row_bytes, s));
+    // stage through two pinned buffers so that the H2D copy of one chunk overlaps the host gather of the next
+    const size_t chunk = size_t(32) << 20;
+    for (int k = 0; k < 2; ++k) CU_TRY(c, c->h_stage[k].ensure(chunk));
+    int which = 0;
+    for (int i = 0; i < n_images; ++i) {
+        if (n_rows[i] == 0) continue;
+        if (!rows[i]) return fail(c, SFM_ERR_INVALID, "bank: null descriptor pointer for a non-empty image");
+        const size_t step = step_bytes ? step_bytes[i] : row_bytes;
+        if (step < row_bytes) return fail(c, SFM_ERR_INVALID, "bank: step smaller than a row");
+        const size_t rows_per_chunk = std::max<size_t>(1, chunk / row_bytes);
+        for (size_t r0 = 0; r0 < static_cast<size_t>(n_rows[i]); r0 += rows_per_chunk) {
+            const size_t nr = std::min(rows_per_chunk, static_cast<size_t>(n_rows[i]) - r0);
+            CU_TRY(c, cudaEventSynchronize(c->stage_ev[which]));
+            uint8_t* h = c->h_stage[which].as<uint8_t>();
+            const uint8_t* src = static_cast<const uint8_t*>(rows[i]) + r0 * step;
+            if (step == row_bytes) std::memcpy(h, src, nr * row_bytes);
+            else for (size_t r = 0; r < nr; ++r) std::memcpy(h + r * row_bytes, src + r * step, row_bytes);
+            CU_TRY(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst.p) + (static_cast<size_t>(b.row0[i]) + r0) * row_bytes, h,
+                                      nr * row_bytes, cudaMemcpyHostToDevice, s));
+            CU_TRY(c, cudaEventRecord(c->stage_ev[which], s));
+            c->stat_h2d += static_cast<int64_t>(nr * row_bytes);
+            which ^= 1;
+        }
+    }
+    return bank_finish(c, b);
+}
+
+// ------------------------------------------------------------------------------------------------ the stage
+enum class Engine { TC, DP4A, F32, POPC };
+
+int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out) {
+    if (norm == SFM_NORM_HAMMING) {
+        if (b.depth != SFM_CV_8U) return fail(c, SFM_ERR_INVALID, "NORM_HAMMING needs CV_8U descriptors");
+        if (b.cols != 32) return fail(c, SFM_ERR_UNSUPPORTED, "Hamming kernel is built for 256-bit (32-byte) descriptors");
+        if (requested == SFM_ENGINE_TENSOR) return fail(c, SFM_ERR_UNSUPPORTED, "tensor-core Hamming engine not built yet");
+        *out = Engine::POPC;
+        return SFM_OK;
+    }
+    if (norm != SFM_NORM_L2) return fail(c, SFM_ERR_UNSUPPORTED, "only NORM_L2 and NORM_HAMMING are supported");
+    if (b.u8_valued && b.cols == 128) {
+        *out = requested == SFM_ENGINE_SIMT ? Engine::DP4A : Engine::TC;
+        return SFM_OK;
+    }
+    if (!b.have_f32) return fail(c, SFM_ERR_UNSUPPORTED, "NORM_L2 on CV_8U data needs 128-byte descriptors");
+    if (requested == SFM_ENGINE_TENSOR) return fail(c, SFM_ERR_UNSUPPORTED, "tensor engine needs u8-valued 128-d descriptors");
+    if (b.cols > 512) return fail(c, SFM_ERR_UNSUPPORTED, "fp32 L2 kernel supports up to 512 columns");
+    *out = Engine::F32;
+    return SFM_OK;
+}
+
+int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, const int64_t* d_unit_prefix, int n_pairs,
+               int64_t n_units, Top2* out) {
+    cudaStream_t s = c->stream;
+    c->stat_launches++;
+    switch (eng) {
+        case Engine::TC:
+            CU_TRY(c, launch_knn2_l2_u8_tc(&b.tmap_a, &b.tmap_b, b.d_ckey.as<int32_t>(), b.d_norm2.as<int32_t>(), d_pairs,
+                                           d_unit_prefix, n_pairs, n_units, out, c->sm_count, s));
+            break;
+        case Engine::DP4A:
+            CU_TRY(c, launch_knn2_l2_u8_dp4a(b.d_u8.as<uint8_t>(), b.d_norm2.as<int32_t>(), d_pairs, d_unit_prefix, n_pairs,
+                                             n_units, out, s));
+            break;
+        case Engine::F32:
+            CU_TRY(c, launch_knn2_l2_f32(b.d_f32.as<float>(), b.cols, d_pairs, d_unit_prefix, n_pairs, n_units, out, s));
+            break;
+        case Engine::POPC:
+            CU_TRY(c, launch_knn2_hamming_popc(b.d_u8.as<uint8_t>(), d_pairs, d_unit_prefix, n_pairs, n_units, out, s));
+            break;
+    }
+    return SFM_OK;
+}
+
+int rows_per_unit(Engine e) { return e == Engine::F32 ? kF32RowsPerUnit : (e == Engine::TC ? kTcRowsPerUnit : kSimtRowsPerUnit); }
+
+int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o) {
+    Bank& b = c->bank;
+    if (b.n_images == 0 && n_pairs > 0) return fail(c, SFM_ERR_STATE, "match_pairs before bank upload");
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(c, SFM_ERR_INVALID, "bad pair list");
+    if (n_pairs >= (int64_t(1) << 31)) return fail(c, SFM_ERR_CAPACITY, "too many pairs");
+    if (o->k != 1 && o->k != 2) return fail(c, SFM_ERR_UNSUPPORTED, "k must be 1 or 2");
+    if (!(o->ratio >= 0.0)) return fail(c, SFM_ERR_INVALID, "ratio must be >= 0");
+    Engine eng;
+    int rc = pick_engine(c, b, o->norm, o->engine, &eng);
+    if (rc != SFM_OK) return rc;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int l = pairs[2 * p], r = pairs[2 * p + 1];
+        if (l < 0 || r < 0 || l >= b.n_images || r >= b.n_images) return fail(c, SFM_ERR_INVALID, "pair index out of range");
+    }
+    cudaStream_t s = c->stream;
+    const int rpu = rows_per_unit(eng);
+    const bool need_rev = o->cross_check != 0;
+    const bool need_cnt = o->distinct != 0;
+
+    // ---- split into batches bounded by the staging budget
+    struct Batch { int64_t p0, p1, staged_rows, t_rows, n_units, n_rev_units; };
+    std::vector<Batch> batches;
+    {
+        Batch cur{0, 0, 0, 0, 0, 0};
+        for (int64_t p = 0; p < n_pairs; ++p) {
+            const int64_t q = pad_rows(b.n_rows[pairs[2 * p]]), t = pad_rows(b.n_rows[pairs[2 * p + 1]]);
+            if (cur.p1 > cur.p0 && (cur.staged_rows + q > static_cast<int64_t>(c->staging_budget_rows) ||
+                                    cur.t_rows + t > static_cast<int64_t>(c->staging_budget_rows))) {
+                batches.push_back(cur);
+                cur = Batch{p, p, 0, 0, 0, 0};
+            }
+            cur.p1 = p + 1;
+            cur.staged_rows += q;
+            cur.t_rows += t;
+        }
+        if (cur.p1 > cur.p0) batches.push_back(cur);
+    }
+    const int64_t nb = static_cast<int64_t>(batches.size());
+
+    // ---- host metadata for the whole list, one H2D
+    //   PairDesc[n_pairs] | rev PairDesc[n_pairs] | unit_prefix[n_pairs+nb] | rev_unit_prefix[..] | out_prefix[..] | t_prefix[..]
+    const size_t npre = static_cast<size_t>(n_pairs + nb);
+    const size_t bytes_pd = sizeof(PairDesc) * static_cast<size_t>(n_pairs);
+    const size_t bytes_pre = sizeof(int64_t) * npre;
+    CU_TRY(c, cudaEventSynchronize(c->meta_ev));
+    CU_TRY(c, c->h_meta.ensure(std::max<size_t>(64, 2 * bytes_pd + 4 * bytes_pre)));
+    PairDesc* h_pd = c->h_meta.as<PairDesc>();
+    PairDesc* h_rpd = h_pd + n_pairs;
+    int64_t* h_unit = reinterpret_cast<int64_t*>(h_rpd + n_pairs);
+    int64_t* h_runit = h_unit + npre;
+    int64_t* h_out = h_runit + npre;
+    int64_t* h_tp = h_out + npre;
+    int64_t max_staged = 0, max_t = 0, max_chunks = 0, total_q = 0;
+    for (int64_t bi = 0; bi < nb; ++bi) {
+        Batch& B = batches[bi];
+        int64_t units = 0, runits = 0, orow = 0, trow = 0;
+        const int64_t base = B.p0 + bi;      // prefix arrays carry one extra entry per batch
+        for (int64_t p = B.p0; p < B.p1; ++p) {
+            const int l = pairs[2 * p], r = pairs[2 * p + 1];
+            PairDesc d;
+            d.q_row0 = static_cast<int32_t>(b.row0[l]); d.nq = b.n_rows[l];
+            d.t_row0 = static_cast<int32_t>(b.row0[r]); d.nt = b.n_rows[r];
+            d.out_row0 = orow;
+            h_pd[p] = d;
+            PairDesc rd;                      // roles swapped: train rows query the left image
+            rd.q_row0 = d.t_row0; rd.nq = d.nt; rd.t_row0 = d.q_row0; rd.nt = d.nq; rd.out_row0 = trow;
+            h_rpd[p] = rd;
+            const int64_t k = p - B.p0;
+            h_unit[base + k] = units; h_runit[base + k] = runits; h_out[base + k] = orow; h_tp[base + k] = trow;
+            units += (d.nq + rpu - 1) / rpu;
+            runits += (d.nt + rpu - 1) / rpu;
+            orow += pad_rows(d.nq);
+            trow += pad_rows(d.nt);
+            total_q += d.nq;
+        }
+        const int64_t k = B.p1 - B.p0;
+        h_unit[base + k] = units; h_runit[base + k] = runits; h_out[base + k] = orow; h_tp[base + k] = trow;
+        B.n_units = units; B.n_rev_units = runits; B.staged_rows = orow; B.t_rows = trow;
+        max_staged = std::max(max_staged, orow);
+        max_t = std::max(max_t, trow);
+        max_chunks = std::max(max_chunks, orow / 256);
+    }
+    CU_TRY(c, c->d_pairs.ensure(std::max<size_t>(64, 2 * bytes_pd + 4 * bytes_pre)));
+    if (n_pairs > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->d_pairs.p, c->h_meta.p, 2 * bytes_pd + 4 * bytes_pre, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, cudaEventRecord(c->meta_ev, s));
+        c->stat_h2d += static_cast<int64_t>(2 * bytes_pd + 4 * bytes_pre);
+    }
+    const PairDesc* d_pd = c->d_pairs.as<PairDesc>();
+    const PairDesc* d_rpd = d_pd + n_pairs;
+    const int64_t* d_unit = reinterpret_cast<const int64_t*>(d_rpd + n_pairs);
+    const int64_t* d_runit = d_unit + npre;
+    const int64_t* d_outp = d_runit + npre;
+    const int64_t* d_tp = d_outp + npre;
+
+    CU_TRY(c, c->d_top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
+    if (need_rev) CU_TRY(c, c->d_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
+    if (need_cnt) CU_TRY(c, c->d_train_cnt.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
+    CU_TRY(c, c->d_chunk_counts.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
+    CU_TRY(c, c->d_chunk_excl.ensure(static_cast<size_t>(max_chunks + 1) * 8));
+    CU_TRY(c, c->d_pair_counts.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
+    CU_TRY(c, c->d_pair_offsets.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
+    CU_TRY(c, c->d_dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs))));
+    // output capacity: grown on demand (collect() retries with the worst case if a run overflows)
+    if (c->out_capacity == 0) c->out_capacity = int64_t(1) << 22;
+    c->out_capacity = std::max<int64_t>(c->out_capacity, std::min<int64_t>(total_q, std::max<int64_t>(int64_t(1) << 22, total_q / 4)));
+    CU_TRY(c, c->d_out.ensure(static_cast<size_t>(c->out_capacity) * sizeof(DMatch)));
+    CU_TRY(c, cudaMemsetAsync(c->d_scalars.p, 0, 12, s));     // running_total, overflow
+    int64_t* d_total = c->d_scalars.as<int64_t>();
+    int* d_overflow = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 8);
+
+    FilterParams fp;
+    fp.norm = o->norm; fp.k = o->k; fp.ratio = o->ratio; fp.cross_check = o->cross_check; fp.distinct = o->distinct;
+    for (int64_t bi = 0; bi < nb; ++bi) {
+        const Batch& B = batches[bi];
+        const int np = static_cast<int>(B.p1 - B.p0);
+        const int64_t base = B.p0 + bi;
+        rc = launch_knn(c, b, eng, d_pd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>());
+        if (rc != SFM_OK) return rc;
+        if (need_rev) {
+            rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, c->d_rev.as<Top2>());
+            if (rc != SFM_OK) return rc;
+        }
+        FilterArgs a;
+        a.top2 = c->d_top2.as<Top2>(); a.rev = c->d_rev.as<Top2>(); a.pairs = d_pd + B.p0;
+        a.out_prefix = d_outp + base; a.t_prefix = d_tp + base; a.n_pairs = np; a.staged_rows = B.staged_rows;
+        a.fp = fp; a.train_cnt = c->d_train_cnt.as<int32_t>();
+        if (need_cnt) {
+            CU_TRY(c, cudaMemsetAsync(c->d_train_cnt.p, 0, static_cast<size_t>(B.t_rows) * 4, s));
+            CU_TRY(c, launch_filter_mark(a, s));
+            c->stat_launches++;
+        }
+        CU_TRY(c, launch_filter_count(a, c->d_chunk_counts.as<int32_t>(), s));
+        CU_TRY(c, launch_scan_offsets(c->d_chunk_counts.as<int32_t>(), B.staged_rows / 256, d_outp + base, np,
+                                      o->min_match_count, c->d_chunk_excl.as<int64_t>(), c->d_pair_counts.as<int64_t>(),
+                                      c->d_pair_offsets.as<int64_t>() + B.p0, c->d_dropped.as<uint8_t>() + B.p0, d_total, s));
+        CU_TRY(c, launch_compact(a, c->d_chunk_excl.as<int64_t>(), c->d_pair_offsets.as<int64_t>() + B.p0,
+                                 c->d_dropped.as<uint8_t>() + B.p0, c->d_out.as<DMatch>(), c->out_capacity, d_overflow, s));
+        c->stat_launches += 3;
+    }
+    c->run.valid = true;
+    c->run.n_pairs = n_pairs;
+    c->run.total_query_rows = total_q;
+    c->run.opts = *o;
+    if (c->run.pairs.data() != pairs) c->run.pairs.assign(pairs, pairs + 2 * n_pairs);
+    return SFM_OK;
+}
+
+int collect_impl(sfm_ctx* c, sfm_result** out) {
+    if (!c->run.valid) return fail(c, SFM_ERR_STATE, "collect without a preceding enqueue");
+    cudaStream_t s = c->stream;
+    const int64_t n = c->run.n_pairs;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int64_t* hs = c->h_scalars.as<int64_t>();
+        CU_TRY(c, cudaMemcpyAsync(hs, c->d_scalars.p, 16, cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaStreamSynchronize(s));
+        const int64_t total = hs[0];
+        const int overflow = reinterpret_cast<int*>(hs)[2];
+        if (overflow) {
+            if (attempt == 1) return fail(c, SFM_ERR_CAPACITY, "output capacity overflow after retry");
+            c->out_capacity = std::max<int64_t>(c->run.total_query_rows, 1);
+            std::vector<int32_t> keep;
+            keep.swap(c->run.pairs);
+            sfm_opts o = c->run.opts;
+            int rc = enqueue_impl(c, keep.data(), n, &o);
+            c->run.pairs.swap(keep);
+            if (rc != SFM_OK) return rc;
+            continue;
+        }
+        sfm_result* r = new sfm_result();
+        r->n_pairs = n;
+        CU_TRY(c, r->offsets.ensure(static_cast<size_t>(n + 1) * 8));
+        CU_TRY(c, r->dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n))));
+        CU_TRY(c, r->matches.ensure(std::max<size_t>(16, static_cast<size_t>(total) * sizeof(DMatch))));
+        if (n > 0) {
+            CU_TRY(c, cudaMemcpyAsync(r->offsets.p, c->d_pair_offsets.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, s));
+            CU_TRY(c, cudaMemcpyAsync(r->dropped.p, c->d_dropped.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, s));
+        }
+        if (total > 0)
+            CU_TRY(c, cudaMemcpyAsync(r->matches.p, c->d_out.p, static_cast<size_t>(total) * sizeof(DMatch), cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaStreamSynchronize(s));
+        r->offsets.as<int64_t>()[n] = total;
+        c->stat_d2h += 16 + n * 9 + total * static_cast<int64_t>(sizeof(DMatch));
+        *out = r;
+        return SFM_OK;
+    }
+    return fail(c, SFM_ERR_CAPACITY, "unreachable");
+}
+
+}  // namespace
+
+// ==================================================================================================== C ABI
+extern "C" {
+
+void sfm_opts_default(sfm_opts* o, int32_t norm) {
+    o->norm = norm; o->k = 2; o->ratio = 0.7; o->cross_check = 0; o->distinct = 0; o->min_match_count = 0;
+    o->engine = SFM_ENGINE_AUTO;
+}
+
+int sfm_ctx_create(sfm_ctx** out, int device) {
+    if (!out) return fail(nullptr, SFM_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SFM_ERR_CUDA, std::string("no CUDA device usable (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SFM_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, SFM_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SFM_ERR_CUDA, "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                               "; this library carries sm_100a code only");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, SFM_ERR_CUDA, cudaGetErrorString(e));
+    sfm_ctx* c = new sfm_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    auto bail = [&](const std::string& m) { g_create_error = m; sfm_ctx_destroy(c); return SFM_ERR_CUDA; };
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    for (int k = 0; k < 2; ++k)
+        if ((e = cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&c->meta_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) return bail("cuTensorMapEncodeTiled not available from the driver");
+    c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if ((e = c->d_scalars.ensure(64)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = c->h_scalars.ensure(64)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    size_t mb = 512;
+    if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
+    c->staging_budget_rows = (mb << 20) / sizeof(Top2);
+    *out = c;
+    return SFM_OK;
+}
+
+void sfm_ctx_destroy(sfm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->bank.release(); c->scratch.release();
+    DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
+                      &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
+                      &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn};
+    for (DevBuf* b : bufs) b->release();
+    c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
+    for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
+    if (c->meta_ev) cudaEventDestroy(c->meta_ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* sfm_last_error(const sfm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+int sfm_device_sm_count(const sfm_ctx* c) { return c ? c->sm_count : 0; }
+void* sfm_ctx_stream(sfm_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+
+int sfm_bank_upload(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                    const size_t* step_bytes, int cv_depth) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n_images > 0 && (!rows || !n_rows)) return fail(c, SFM_ERR_INVALID, "bank: null arrays");
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    return bank_upload_host(c, c->bank, n_images, rows, n_rows, cols, step_bytes, cv_depth);
+}
+
+int sfm_bank_upload_device(sfm_ctx* c, int n_images, const void* dev_rows, const int64_t* row_offset, const int32_t* n_rows,
+                           int cols, int cv_depth) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n_images > 0 && (!dev_rows || !n_rows || !row_offset)) return fail(c, SFM_ERR_INVALID, "bank: null arrays");
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    Bank& b = c->bank;
+    int rc = bank_layout(c, b, n_images, n_rows, cols, cv_depth);
+    if (rc != SFM_OK) return rc;
+    const size_t esz = cv_depth == SFM_CV_32F ? 4 : 1;
+    const size_t row_bytes = static_cast<size_t>(cols) * esz;
+    DevBuf& dst = cv_depth == SFM_CV_32F ? b.d_f32 : b.d_u8;
+    CU_TRY(c, dst.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * row_bytes)));
+    CU_TRY(c, cudaMemsetAsync(dst.p, 0, static_cast<size_t>(b.padded_rows) * row_bytes, c->stream));
+    for (int i = 0; i < n_images; ++i) {
+        if (n_rows[i] == 0) continue;
+        CU_TRY(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst.p) + static_cast<size_t>(b.row0[i]) * row_bytes,
+                                  static_cast<const uint8_t*>(dev_rows) + static_cast<size_t>(row_offset[i]) * row_bytes,
+                                  static_cast<size_t>(n_rows[i]) * row_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return bank_finish(c, b);
+}
+
+int sfm_bank_info(const sfm_ctx* c, int* n_images, int* cols, int* is_u8_valued) {
+    if (!c) return SFM_ERR_INVALID;
+    if (n_images) *n_images = c->bank.n_images;
+    if (cols) *cols = c->bank.cols;
+    if (is_u8_valued) *is_u8_valued = c->bank.u8_valued ? 1 : 0;
+    return SFM_OK;
+}
+
+int sfm_match_pairs_enqueue(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_opts* opts) {
+    if (!c || !opts) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    return enqueue_impl(c, pairs, n_pairs, opts);
+}
+
+int sfm_match_pairs_collect(sfm_ctx* c, sfm_result** out) {
+    if (!c || !out) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(c, cudaSetDevice(c->device));
+    return collect_impl(c, out);
+}
+
+int sfm_match_pairs(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_opts* opts, sfm_result** out) {
+    int rc = sfm_match_pairs_enqueue(c, pairs, n_pairs, opts);
+    if (rc != SFM_OK) return rc;
+    return sfm_match_pairs_collect(c, out);
+}
+
+int64_t sfm_result_n_pairs(const sfm_result* r) { return r ? r->n_pairs : 0; }
+const int64_t* sfm_result_offsets(const sfm_result* r) { return r ? r->offsets.as<int64_t>() : nullptr; }
+const sfm_dmatch* sfm_result_matches(const sfm_result* r) { return r ? r->matches.as<sfm_dmatch>() : nullptr; }
+const uint8_t* sfm_result_dropped(const sfm_result* r) { return r ? r->dropped.as<uint8_t>() : nullptr; }
+void sfm_result_free(sfm_result* r) {
+    if (!r) return;
+    r->offsets.release(); r->matches.release(); r->dropped.release();
+    delete r;
+}
+
+int sfm_last_stats(const sfm_ctx* c, int64_t* launches, int64_t* h2d, int64_t* d2h) {
+    if (!c) return SFM_ERR_INVALID;
+    if (launches) *launches = c->stat_launches;
+    if (h2d) *h2d = c->stat_h2d;
+    if (d2h) *d2h = c->stat_d2h;
+    return SFM_OK;
+}
+
+int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const void* train, int nt, size_t t_step, int cols,
+                  int cv_depth, int norm, int k, int engine, int32_t* nidx, float* dist) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (k != 1 && k != 2) return fail(c, SFM_ERR_UNSUPPORTED, "knnMatch: k must be 1 or 2");
+    if (nq < 0 || nt < 0 || cols <= 0) return fail(c, SFM_ERR_INVALID, "knnMatch: bad shape");
+    if (nq > 0 && (!nidx || !dist)) return fail(c, SFM_ERR_INVALID, "knnMatch: null output");
+    CU_TRY(c, cudaSetDevice(c->device));
+    Bank& b = c->scratch;
+    const void* rows[2] = {query, train};
+    const int32_t n_rows[2] = {nq, nt};
+    const size_t esz = cv_depth == SFM_CV_32F ? 4 : 1;
+    const size_t steps[2] = {q_step ? q_step : cols * esz, t_step ? t_step : cols * esz};
+    int rc = bank_upload_host(c, b, 2, rows, n_rows, cols, steps, cv_depth);
+    if (rc != SFM_OK) return rc;
+    if (nq == 0) return SFM_OK;
+    Engine eng;
+    rc = pick_engine(c, b, norm, engine, &eng);
+    if (rc != SFM_OK) return rc;
+    cudaStream_t s = c->stream;
+    const int rpu = rows_per_unit(eng);
+    struct Meta { PairDesc pd; int64_t unit_prefix[2]; } meta;
+    meta.pd.q_row0 = 0; meta.pd.nq = nq; meta.pd.t_row0 = static_cast<int32_t>(b.row0[1]); meta.pd.nt = nt; meta.pd.out_row0 = 0;
+    meta.unit_prefix[0] = 0; meta.unit_prefix[1] = (nq + rpu - 1) / rpu;
+    CU_TRY(c, c->d_pairs.ensure(sizeof(Meta)));
+    CU_TRY(c, cudaMemcpyAsync(c->d_pairs.p, &meta, sizeof(Meta), cudaMemcpyHostToDevice, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    CU_TRY(c, c->d_top2.ensure(static_cast<size_t>(pad_rows(nq)) * sizeof(Top2)));
+    const PairDesc* d_pd = c->d_pairs.as<PairDesc>();
+    const int64_t* d_unit = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, unit_prefix));
+    rc = launch_knn(c, b, eng, d_pd, d_unit, 1, meta.unit_prefix[1], c->d_top2.as<Top2>());
+    if (rc != SFM_OK) return rc;
+    const size_t out_bytes = static_cast<size_t>(nq) * k * 4;
+    CU_TRY(c, c->d_knn.ensure(2 * out_bytes));
+    int32_t* d_idx = c->d_knn.as<int32_t>();
+    float* d_dist = reinterpret_cast<float*>(c->d_knn.as<uint8_t>() + out_bytes);
+    CU_TRY(c, launch_top2_to_arrays(c->d_top2.as<Top2>(), nq, k, norm, d_idx, d_dist, s));
+    c->stat_launches++;
+    CU_TRY(c, c->h_knn.ensure(2 * out_bytes));
+    CU_TRY(c, cudaMemcpyAsync(c->h_knn.p, d_idx, 2 * out_bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    std::memcpy(nidx, c->h_knn.p, out_bytes);
+    std::memcpy(dist, c->h_knn.as<uint8_t>() + out_bytes, out_bytes);
+    c->stat_d2h += static_cast<int64_t>(2 * out_bytes);
+    c->run.valid = false;
+    return SFM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// sfm_match_cli — host driver of the matching stage with the reference's switch grammar
+// (-P<key>=<value> parameters, --<flag> flags; AppArgs.cpp:29-53) and switch names
+// (PhotogrammetrieCli.cpp:320-392, :95, :112, :422-460):
+//   -Pfeature-detector=SIFT|ORB  -Pfeature-matcher=BF|FLANN  -Pfeature-limit=N  -Pfeature-sequence=S
+//   -Pfeature-gridlength=L  -Pmatch-threshold=T  --distinct-matches  -Ploglevel=0..4
+// Feature extraction is outside this stage, so descriptors come from a file instead of -Pimage:
+//   -Pdescriptors=<bank.sfmd>   "SFMD" u32 version, u32 n_images, u32 cols, u32 depth(0=CV_8U,5=CV_32F),
+//                               then per image: u32 n_rows + n_rows*cols*elemsize bytes
+//   -Pout=<matches.bin>         u64 n_pairs, then per kept pair: i32 left, i32 right, u64 n, n x DMatch(16 B)
+//   -Pdevice=<gpu>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <string>
+
+#include "matching.h"
+
+using namespace sfmhost;
+
+struct Args {
+    std::multimap<std::string, std::string> kv;
+    void parse(int argc, char** argv) {
+        for (int i = 1; i < argc; ++i) {
+            std::string a = argv[i];
+            if (a.size() < 3 || a[0] != '-') { kv.insert({"", a}); continue; }
+            const auto eq = a.find('=');
+            const std::string type = a.substr(0, 2);
+            const std::string key = a.substr(2, eq == std::string::npos ? std::string::npos : eq - 2);
+            const std::string val = eq == std::string::npos ? "" : a.substr(eq + 1);
+            if (type == "-P") kv.insert({key, val});
+            else if (type == "--") kv.insert({key, "1"});
+        }
+    }
+    std::string get(const std::string& k, const std::string& def = "") const {
+        auto it = kv.find(k);            // first occurrence wins, like AppArgs::getArg
+        return it == kv.end() ? def : it->second;
+    }
+    bool flag(const std::string& k) const { return get(k, "0") == "1"; }
+};
+
+static void usage() {
+    std::puts("sfm_match_cli -Pdescriptors=<bank.sfmd> [-Pfeature-detector=SIFT|ORB] [-Pfeature-matcher=BF|FLANN]\n"
+              "              [-Pfeature-limit=10000] [-Pfeature-sequence=0] [-Pfeature-gridlength=0] [-Pmatch-threshold=20]\n"
+              "              [--distinct-matches] [-Pout=matches.bin] [-Pdevice=0] [-Ploglevel=2]");
+}
+
+int main(int argc, char** argv) {
+    Args args;
+    args.parse(argc, argv);
+    const std::string path = args.get("descriptors");
+    if (path.empty()) { usage(); return 0; }
+    try {
+        const int loglevel = std::stoi(args.get("loglevel", "2"));
+        const std::string det = args.get("feature-detector");
+        int limit = std::stoi(args.get("feature-limit", "10000"));
+        if (limit >= SFM_MAX_ROWS) throw std::invalid_argument("feature-limit must stay below 262144");
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw std::runtime_error("cannot open " + path);
+        char magic[4]; uint32_t hdr[4];
+        f.read(magic, 4); f.read(reinterpret_cast<char*>(hdr), 16);
+        if (!f || std::memcmp(magic, "SFMD", 4) != 0 || hdr[0] != 1) throw std::runtime_error("not an SFMD v1 file");
+        const uint32_t n_images = hdr[1], cols = hdr[2], depth = hdr[3];
+        const size_t esz = depth == SFM_CV_32F ? 4 : 1;
+        std::vector<std::vector<char>> storage(n_images);
+        Scene scene;
+        for (uint32_t i = 0; i < n_images; ++i) {
+            uint32_t n = 0;
+            f.read(reinterpret_cast<char*>(&n), 4);
+            storage[i].resize(static_cast<size_t>(n) * cols * esz);
+            f.read(storage[i].data(), static_cast<std::streamsize>(storage[i].size()));
+            if (!f) throw std::runtime_error("truncated SFMD file");
+            auto shot = std::make_shared<Shot>();
+            shot->imagePath = "image" + std::to_string(i);
+            // -Pfeature-limit bounds the rows per image (ORB::create(limit) / SIFT::create(limit,...)); 0 = unlimited
+            const uint32_t use = (limit > 0 && n > static_cast<uint32_t>(limit)) ? static_cast<uint32_t>(limit) : n;
+            shot->descriptors = DescriptorMat{storage[i].data(), static_cast<int>(use), static_cast<int>(cols), cols * esz,
+                                              static_cast<int>(depth)};
+            scene.shots.push_back(shot);
+        }
+        std::vector<std::string> warnings;
+        if (det != "ORB" && det != "SIFT" && !det.empty())
+            warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
+        auto matcher = configureFeatureMatcher(det, args.get("feature-matcher"), std::stoi(args.get("device", "0")), &warnings);
+        auto strategy = configureFeatureMatcherStrategy(std::stoi(args.get("feature-sequence", "0")),
+                                                        std::stoi(args.get("feature-gridlength", "0")), &warnings);
+        for (auto& w : warnings) std::fprintf(stderr, "[WARN] %s\n", w.c_str());
+        if (matcher->flannMode() && loglevel >= 2)
+            std::fprintf(stderr, "[INFO] feature-matcher=FLANN: served by the exact GPU matcher\n");
+        MatchingStage stage;
+        stage.setMatchingAlgorithm(matcher);
+        stage.setFeatureMatchingStrategy(strategy);
+        stage.setMinMatchCount(std::stoi(args.get("match-threshold", "20")));
+        stage.setUseDistinctFeatureMatchTest(args.flag("distinct-matches"));
+        const auto t0 = std::chrono::steady_clock::now();
+        const std::vector<ShotMatches> res = stage.calculateShotMatches(scene);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const size_t n_pairs = strategy->matchPairs(scene.shots.size()).size();
+        size_t total = 0;
+        for (auto& sm : res) total += sm.matches.size();
+        std::printf("pairs=%zu kept=%zu matches=%zu seconds=%.6f\n", n_pairs, res.size(), total, dt);
+        if (loglevel >= 3)
+            for (auto& sm : res)
+                std::printf("%s : %s -> %zu\n", sm.left->imagePath.c_str(), sm.right->imagePath.c_str(), sm.matches.size());
+        const std::string out = args.get("out");
+        if (!out.empty()) {
+            std::ofstream o(out, std::ios::binary);
+            const uint64_t np = res.size();
+            o.write(reinterpret_cast<const char*>(&np), 8);
+            for (auto& sm : res) {
+                int32_t l = -1, r = -1;
+                for (size_t i = 0; i < scene.shots.size(); ++i) {
+                    if (scene.shots[i] == sm.left) l = static_cast<int32_t>(i);
+                    if (scene.shots[i] == sm.right) r = static_cast<int32_t>(i);
+                }
+                const uint64_t n = sm.matches.size();
+                o.write(reinterpret_cast<const char*>(&l), 4);
+                o.write(reinterpret_cast<const char*>(&r), 4);
+                o.write(reinterpret_cast<const char*>(&n), 8);
+                o.write(reinterpret_cast<const char*>(sm.matches.data()), static_cast<std::streamsize>(n * sizeof(DMatch)));
+            }
+        }
+    } catch (const std::exception& e) {
+        // the reference prints the exception and returns 0 (main.cpp:26-34)
+        std::fprintf(stderr, "[ERROR] %s\n", e.what());
+        return 0;
+    }
+    return 0;
+}

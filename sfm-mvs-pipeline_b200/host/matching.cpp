@@ -1,0 +1,149 @@
+#include "matching.h"
+
+#include <cmath>
+
+namespace sfmhost {
+
+static void check(sfm_ctx* ctx, int rc) {
+    if (rc != SFM_OK) throw MatcherError(rc, sfm_last_error(ctx));
+}
+
+GpuDescriptorMatcher::GpuDescriptorMatcher(int normType, bool crossCheck, int device, bool flannMode)
+    : norm_(normType), crossCheck_(crossCheck), flann_(flannMode) {
+    if (normType != SFM_NORM_L2 && normType != SFM_NORM_HAMMING) throw std::invalid_argument("unsupported normType");
+    const int rc = sfm_ctx_create(&ctx_, device);
+    if (rc != SFM_OK) throw MatcherError(rc, sfm_last_error(nullptr));
+}
+
+GpuDescriptorMatcher::~GpuDescriptorMatcher() { sfm_ctx_destroy(ctx_); }
+
+void GpuDescriptorMatcher::knnMatch(const DescriptorMat& q, const DescriptorMat& t,
+                                    std::vector<std::vector<DMatch>>& matches, int k) const {
+    matches.clear();
+    // cv::batchDistance asserts type == src2.type() && src1.cols == src2.cols
+    if (q.depth != t.depth || q.cols != t.cols || q.cols == 0)
+        throw MatcherError(SFM_ERR_INVALID, "knnMatch: descriptor type/width mismatch");
+    if (crossCheck_ && k != 1) throw MatcherError(SFM_ERR_INVALID, "knnMatch: crossCheck requires k == 1");
+    if (k < 1) return;
+    const int kk = k > 2 ? -1 : k;
+    if (kk < 0) throw MatcherError(SFM_ERR_UNSUPPORTED, "knnMatch: k > 2 is not supported");
+    std::vector<int32_t> nidx(static_cast<std::size_t>(q.rows) * kk);
+    std::vector<float> dist(static_cast<std::size_t>(q.rows) * kk);
+    check(ctx_, sfm_knn_match(ctx_, q.data, q.rows, q.step, t.data, t.rows, t.step, q.cols, q.depth, norm_, kk,
+                              SFM_ENGINE_AUTO, nidx.data(), dist.data()));
+    std::vector<int32_t> rev;
+    if (crossCheck_ && t.rows > 0 && q.rows > 0) {
+        std::vector<float> rdist(t.rows);
+        rev.resize(t.rows);
+        check(ctx_, sfm_knn_match(ctx_, t.data, t.rows, t.step, q.data, q.rows, q.step, q.cols, q.depth, norm_, 1,
+                                  SFM_ENGINE_AUTO, rev.data(), rdist.data()));
+    }
+    matches.resize(q.rows);
+    for (int r = 0; r < q.rows; ++r)
+        for (int j = 0; j < kk; ++j) {
+            const int32_t ti = nidx[static_cast<std::size_t>(r) * kk + j];
+            if (ti < 0) break;
+            if (crossCheck_ && rev[ti] != r) break;      // rows without a mutual partner return an empty list
+            matches[r].push_back(DMatch{r, ti, 0, dist[static_cast<std::size_t>(r) * kk + j]});
+        }
+}
+
+void GpuDescriptorMatcher::match(const DescriptorMat& q, const DescriptorMat& t, std::vector<DMatch>& out) const {
+    std::vector<std::vector<DMatch>> knn;
+    knnMatch(q, t, knn, 1);
+    out.clear();
+    for (auto& m : knn)
+        if (!m.empty()) out.push_back(m[0]);
+}
+
+void IFeatureMatchingStrategy::calculateShotMatches(const Scene& scene, std::shared_ptr<GpuDescriptorMatcher>& matcher,
+                                                    std::vector<ShotMatches>& out) {
+    if (!matcher) throw std::invalid_argument("matcher must not be null");
+    const auto& shots = scene.getShots();
+    const PairList pl = matchPairs(shots.size());
+    dropped_.assign(pl.size(), 0);
+    if (shots.empty()) return;
+    sfm_ctx* ctx = matcher->context();
+    // one bank upload for the whole scene (replaces reading every shot's cv::Mat once per pair)
+    std::vector<const void*> rows(shots.size());
+    std::vector<int32_t> nrows(shots.size());
+    std::vector<std::size_t> steps(shots.size());
+    int cols = 0, depth = -1;
+    for (std::size_t i = 0; i < shots.size(); ++i) {
+        const DescriptorMat& d = shots[i]->descriptors;
+        if (!d.empty()) {
+            if (depth < 0) { depth = d.depth; cols = d.cols; }
+            else if (d.depth != depth || d.cols != cols) throw MatcherError(SFM_ERR_INVALID, "descriptor type/width mismatch");
+        }
+    }
+    if (depth < 0) { depth = SFM_CV_8U; cols = 128; }
+    const std::size_t esz = depth == SFM_CV_32F ? 4 : 1;
+    for (std::size_t i = 0; i < shots.size(); ++i) {
+        const DescriptorMat& d = shots[i]->descriptors;
+        rows[i] = d.empty() ? nullptr : d.data;
+        nrows[i] = d.empty() ? 0 : d.rows;
+        steps[i] = d.step ? d.step : static_cast<std::size_t>(cols) * esz;
+    }
+    check(ctx, sfm_bank_upload(ctx, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(), depth));
+    std::vector<int32_t> flat(pl.size() * 2);
+    for (std::size_t p = 0; p < pl.size(); ++p) { flat[2 * p] = pl[p].first; flat[2 * p + 1] = pl[p].second; }
+    sfm_opts o;
+    sfm_opts_default(&o, matcher->normType());
+    o.ratio = stage_.ratio;
+    o.cross_check = matcher->crossCheck() ? 1 : 0;
+    o.k = matcher->crossCheck() ? 1 : 2;
+    o.distinct = stage_.distinct ? 1 : 0;
+    o.min_match_count = stage_.minMatchCount;
+    sfm_result* res = nullptr;
+    check(ctx, sfm_match_pairs(ctx, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
+    const int64_t* off = sfm_result_offsets(res);
+    const sfm_dmatch* m = sfm_result_matches(res);
+    const uint8_t* dr = sfm_result_dropped(res);
+    for (std::size_t p = 0; p < pl.size(); ++p) {
+        dropped_[p] = dr[p];
+        ShotMatches sm;
+        sm.left = shots[pl[p].first];
+        sm.right = shots[pl[p].second];
+        sm.matches.assign(m + off[p], m + off[p + 1]);
+        out.push_back(std::move(sm));
+    }
+    sfm_result_free(res);
+}
+
+MatchingStage::MatchingStage()
+    : strategy_(std::make_shared<UnorderedFeatureMatchingStrategy>()) {}
+
+std::vector<ShotMatches> MatchingStage::calculateShotMatches(const Scene& scene) {
+    if (!matcher_) throw std::invalid_argument("Der Feature Matching Algorithmus darf nicht null sein.");
+    StageOptions so;
+    so.distinct = distinct_;
+    so.minMatchCount = minMatchCount_;
+    strategy_->setStageOptions(so);
+    std::vector<ShotMatches> all, kept;
+    strategy_->calculateShotMatches(scene, matcher_, all);
+    const auto& dropped = strategy_->lastDropped();
+    for (std::size_t p = 0; p < all.size(); ++p)
+        if (!dropped[p]) kept.push_back(std::move(all[p]));
+    return kept;
+}
+
+std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& det, const std::string& mat, int device,
+                                                              std::vector<std::string>* warnings) {
+    const bool flann = mat == "FLANN";
+    if (!flann && mat != "BF" && !mat.empty() && warnings)
+        warnings->push_back("Unbekannter Algorithmus fuer den Merkmalsvergleich: " + mat + ". Benutze BF.");
+    const int norm = det == "ORB" ? SFM_NORM_HAMMING : SFM_NORM_L2;      // anything else than ORB -> SIFT
+    return std::make_shared<GpuDescriptorMatcher>(norm, false, device, flann);
+}
+
+std::shared_ptr<IFeatureMatchingStrategy> configureFeatureMatcherStrategy(int seq, int grid, std::vector<std::string>* warnings) {
+    if (seq >= 2) {
+        if (grid >= 1) return std::make_shared<GridFeatureMatchingStrategy>(seq, grid);
+        return std::make_shared<VideoFeatureMatchingStrategy>(seq);
+    }
+    if (seq != 0 && warnings)
+        warnings->push_back("Ungueltige Sequenzlaenge: " + std::to_string(seq) + ". Benutze default (Ungeordnet).");
+    return std::make_shared<UnorderedFeatureMatchingStrategy>();
+}
+
+}  // namespace sfmhost

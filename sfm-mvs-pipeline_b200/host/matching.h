@@ -1,0 +1,173 @@
+// matching.h — C++ host side above the C ABI, mirroring the reference's matching-stage interface
+// (same names, argument meaning and error behaviour) without depending on OpenCV:
+//
+//   DescriptorMat                <-> cv::Mat Features::descriptors            (CameraShot.h:39-42)
+//   DMatch                       <-> cv::DMatch (byte-compatible)
+//   GpuDescriptorMatcher         <-> cv::Ptr<cv::DescriptorMatcher>           (SfM.h:78, knnMatch/match call sites
+//                                    UnorderedFeatureMatchingStrategy.cpp:51/:68)
+//   Shot / Scene / ShotMatches   <-> CameraShot / Scene / ShotMatches         (Scene.h:35-135)
+//   IFeatureMatchingStrategy + Unordered/Video/Grid strategies                (IFeatureMatchingStrategy.h:34-48 ...)
+//   MatchingStage                <-> SfM::calculateShotMatches + its setters  (SfM.cpp:542-575, :52-79)
+//
+// The strategies here do not loop over pairs calling knnMatch: they hand the whole pair list to
+// sfm_match_pairs (one bank upload, batched kernels), which is the throughput path.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sfmmatch.h"
+#include "pair_selector.h"
+
+namespace sfmhost {
+
+using DMatch = sfm_dmatch;
+
+struct DescriptorMat {          // subset of cv::Mat the stage touches
+    const void* data = nullptr;
+    int rows = 0, cols = 0;
+    std::size_t step = 0;       // bytes between rows (0 = dense)
+    int depth = SFM_CV_32F;     // SFM_CV_8U | SFM_CV_32F
+    bool empty() const { return rows == 0 || cols == 0; }
+};
+
+// Thrown where the reference would see cv::Exception out of OpenCV (caught at *Strategy.cpp:66).
+struct MatcherError : std::runtime_error {
+    int code;
+    MatcherError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+class GpuDescriptorMatcher {
+public:
+    // normType: SFM_NORM_L2 (BFMatcher::create(NORM_L2)) or SFM_NORM_HAMMING; crossCheck as in cv::BFMatcher.
+    // `flannMode` records that -Pfeature-matcher=FLANN was requested: the exact GPU matcher replaces it.
+    explicit GpuDescriptorMatcher(int normType = SFM_NORM_L2, bool crossCheck = false, int device = 0, bool flannMode = false);
+    ~GpuDescriptorMatcher();
+    GpuDescriptorMatcher(const GpuDescriptorMatcher&) = delete;
+    GpuDescriptorMatcher& operator=(const GpuDescriptorMatcher&) = delete;
+
+    // cv::DescriptorMatcher::knnMatch(query, train, matches, k): per query row up to k matches, ascending distance.
+    void knnMatch(const DescriptorMat& query, const DescriptorMat& train, std::vector<std::vector<DMatch>>& matches, int k) const;
+    // cv::DescriptorMatcher::match(query, train, matches): best match per query row (cross-check honoured).
+    void match(const DescriptorMat& query, const DescriptorMat& train, std::vector<DMatch>& matches) const;
+
+    int normType() const { return norm_; }
+    bool crossCheck() const { return crossCheck_; }
+    bool flannMode() const { return flann_; }
+    sfm_ctx* context() const { return ctx_; }
+
+private:
+    sfm_ctx* ctx_ = nullptr;
+    int norm_;
+    bool crossCheck_, flann_;
+};
+
+struct Shot {
+    std::string imagePath;
+    DescriptorMat descriptors;      // Features::descriptors
+};
+
+struct Scene {
+    std::vector<std::shared_ptr<Shot>> shots;
+    const std::vector<std::shared_ptr<Shot>>& getShots() const { return shots; }
+};
+
+struct ShotMatches {
+    std::shared_ptr<Shot> left, right;    // left -> queryIdx, right -> trainIdx
+    std::vector<DMatch> matches;
+    double homographyInlierRatio = -1;
+};
+
+struct StageOptions {               // what SfM::calculateShotMatches applies after the strategy
+    bool distinct = false;          // --distinct-matches (SfM.cpp:547-564)
+    int minMatchCount = 0;          // SfM.cpp:566-570 (0 = strategies alone, like the reference's strategy classes)
+    double ratio = 0.7;             // Lowe ratio (UnorderedFeatureMatchingStrategy.cpp:53)
+};
+
+class IFeatureMatchingStrategy {
+public:
+    virtual ~IFeatureMatchingStrategy() = default;
+    virtual PairList matchPairs(std::size_t nShots) const = 0;
+    // Same contract as the reference: appends one ShotMatches per pair.  Order = pair-list order (the reference's
+    // order depends on thread timing).
+    virtual void calculateShotMatches(const Scene& scene, std::shared_ptr<GpuDescriptorMatcher>& matcher,
+                                      std::vector<ShotMatches>& matches);
+    void setStageOptions(const StageOptions& o) { stage_ = o; }
+    const std::vector<uint8_t>& lastDropped() const { return dropped_; }
+
+protected:
+    StageOptions stage_;
+    std::vector<uint8_t> dropped_;
+};
+
+class UnorderedFeatureMatchingStrategy : public IFeatureMatchingStrategy {
+public:
+    PairList matchPairs(std::size_t n) const override { return unorderedPairs(n); }
+};
+
+class VideoFeatureMatchingStrategy : public IFeatureMatchingStrategy {
+public:
+    explicit VideoFeatureMatchingStrategy(int sequenceLength) { setSequenceLength(sequenceLength); }
+    void setSequenceLength(int s) {
+        if (s < 2) throw std::invalid_argument("Die Sequenzlaenge darf nicht kleiner als 2 sein.");
+        sequenceLength_ = s;
+    }
+    PairList matchPairs(std::size_t n) const override { return videoPairs(n, sequenceLength_); }
+private:
+    int sequenceLength_ = 2;
+};
+
+class GridFeatureMatchingStrategy : public IFeatureMatchingStrategy {
+public:
+    GridFeatureMatchingStrategy(int sequenceLength, int rowLength) { setSequenceLength(sequenceLength); setRowLength(rowLength); }
+    void setSequenceLength(int s) {
+        if (s < 2) throw std::invalid_argument("Die Sequenzlaenge darf nicht kleiner als 2 sein.");
+        sequenceLength_ = s;
+    }
+    void setRowLength(int r) {
+        if (r < 1) throw std::invalid_argument("Die Zeilenlaenge darf nicht kleiner als 1 sein.");
+        rowLength_ = r;
+    }
+    PairList matchPairs(std::size_t n) const override { return gridPairs(n, sequenceLength_, rowLength_); }
+private:
+    int sequenceLength_ = 2, rowLength_ = 1;
+};
+
+// SfM::calculateShotMatches: strategy + distinct filter + min-match-count drop.
+class MatchingStage {
+public:
+    MatchingStage();
+    void setMatchingAlgorithm(const std::shared_ptr<GpuDescriptorMatcher>& m) {
+        if (!m) throw std::invalid_argument("Der Feature Matching Algorithmus darf nicht null sein.");
+        matcher_ = m;
+    }
+    void setFeatureMatchingStrategy(const std::shared_ptr<IFeatureMatchingStrategy>& s) {
+        if (!s) throw std::invalid_argument("Die Feature Matching Strategie darf nicht null sein.");
+        strategy_ = s;
+    }
+    void setMinMatchCount(int n) {
+        if (n < 4) throw std::invalid_argument("Der minimale Match Count darf nicht < 4 sein.");
+        minMatchCount_ = n;
+    }
+    void setUseDistinctFeatureMatchTest(bool b) { distinct_ = b; }
+    // returns the surviving ShotMatches (pairs below minMatchCount erased), pair-list order
+    std::vector<ShotMatches> calculateShotMatches(const Scene& scene);
+
+private:
+    std::shared_ptr<GpuDescriptorMatcher> matcher_;
+    std::shared_ptr<IFeatureMatchingStrategy> strategy_;
+    int minMatchCount_ = 20;        // SfM.h default
+    bool distinct_ = false;
+};
+
+// PhotogrammetrieCli::configureFeatureMatcher / configureFeatureMatcherStrategy (PhotogrammetrieCli.cpp:320-392)
+std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& featureDetector,
+                                                              const std::string& featureMatcher, int device,
+                                                              std::vector<std::string>* warnings);
+std::shared_ptr<IFeatureMatchingStrategy> configureFeatureMatcherStrategy(int featureSequence, int featureGridLength,
+                                                                          std::vector<std::string>* warnings);
+
+}  // namespace sfmhost

@@ -1,0 +1,91 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol include/sfmmatch.h declares,
+its host-side logic (pair selection) equals the oracle, and compute entry points refuse to run without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sfmmatch.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(sfm):
+    lib = C.CDLL(sfm.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sfmmatch.h but not exported"
+    assert sorted(sfm.EXPORTS) == names
+
+
+def test_struct_layouts(sfm):
+    assert sfm.DMATCH_DTYPE.itemsize == 16 and sfm.DMATCH_DTYPE == orc.DMATCH_DTYPE   # == cv::DMatch
+    assert C.sizeof(sfm.Opts) == 32
+    o = sfm.Opts()
+    C.CDLL(sfm.LIB_PATH).sfm_opts_default(C.byref(o), C.c_int32(4))
+    assert (o.norm, o.k, o.ratio, o.cross_check, o.distinct, o.min_match_count, o.engine) == (4, 2, 0.7, 0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("n,seq,grid", [(0, 0, 0), (1, 0, 0), (7, 0, 0), (200, 0, 0), (3, 2, 0), (3, 3, 0), (50, 5, 0),
+                                        (1000, 3, 40), (1000, 2, 40), (1000, 4, 40), (20, 3, 5), (3, 2, 2), (3, 2, 3),
+                                        (3, 2, 1), (3, 3, 3), (17, 4, 4), (9, 1, 0), (9, -3, 2), (12, 2, 12), (12, 9, 5)])
+def test_select_pairs_equals_oracle(sfm, n, seq, grid):
+    got = sfm.select_pairs(n, seq, grid)
+    exp = orc.select_pairs(n, seq, grid)
+    assert got.tolist() == exp.tolist()
+
+
+def test_grid_known_answer_through_the_abi(sfm):
+    # GridFeatureMatchingStrategy.h:31-39
+    p = sfm.select_pairs(20, 3, 5)
+    assert sorted(int(b) + 1 for a, b in p if a == 0) == [2, 3, 6, 7, 11]
+
+
+def test_c_oracle_pair_lists_agree():
+    from oracle import oracle_c as oc
+    assert oc.pairs_grid(1000, 3, 40).tolist() == orc.pairs_grid(1000, 3, 40).tolist()
+    assert oc.pairs_video(50, 5).tolist() == orc.pairs_video(50, 5).tolist()
+    assert oc.pairs_unordered(30).tolist() == orc.pairs_unordered(30).tolist()
+
+
+def test_c_oracle_matches_numpy_oracle(insel_sift):
+    from oracle import oracle_c as oc
+    import workloads
+    idx, dist = oc.knn2(insel_sift["desc0"], insel_sift["desc1"], 4)
+    assert np.array_equal(idx, insel_sift["p01_nidx"])
+    assert np.array_equal(dist.view(np.uint32), insel_sift["p01_dist"].view(np.uint32))
+    ob = workloads.orb_like_bank(2, 500)
+    i1, d1 = oc.knn2(ob[0], ob[1], 6)
+    i2, d2 = orc.knn2_hamming(ob[0], ob[1])
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    bank = workloads.sift_like_bank(3, 400)
+    a = oc.match_pairs(bank, orc.pairs_unordered(3), 4)
+    b = orc.match_pairs(bank, orc.pairs_unordered(3), 4)
+    assert all(orc.dmatch_equal(x, y) for x, y in zip(a, b))
+
+
+def test_no_cpu_fallback_without_gpu(sfm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sfm.SfmError) as e:
+        sfm.Matcher(0)
+    assert e.value.code == sfm.ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "sfm-mvs-pipeline_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.lower(), f"{f} mentions the oracle: the product must not depend on it"

@@ -1,0 +1,271 @@
+"""GPU parity tests (run with -m gpu on the B200): the CUDA path through the C ABI against the oracle and the
+committed cv2 golden vectors.  Bit-exact for u8-valued SIFT and for ORB (indices AND distance bits); stated
+tolerance only for non-integer float descriptors."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import workloads
+from oracle import oracle_np as orc
+from oracle.oracle_np import NORM_HAMMING, NORM_L2
+
+pytestmark = pytest.mark.gpu
+PAIRS = ((0, 1), (0, 2), (1, 2))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def matcher(sfm):
+    m = sfm.Matcher(0)
+    yield m
+    m.close()
+
+
+def _same_knn(idx, dist, g_idx, g_dist):
+    assert np.array_equal(idx, g_idx), f"index mismatch at rows {np.nonzero((idx != g_idx).any(1))[0][:10]}"
+    assert np.array_equal(dist.view(np.uint32), g_dist.view(np.uint32))
+
+
+def _engines(sfm):
+    return [("tensor", sfm.ENGINE_TENSOR), ("simt", sfm.ENGINE_SIMT)]
+
+
+# ------------------------------------------------------------------ operator level: knnMatch
+@pytest.mark.parametrize("a,b", PAIRS)
+@pytest.mark.parametrize("eng", ["tensor", "simt"])
+@pytest.mark.parametrize("as_float", [True, False])
+def test_insel_sift_knn_bit_exact(sfm, matcher, insel_sift, a, b, eng, as_float):
+    q, t = insel_sift[f"desc{a}"], insel_sift[f"desc{b}"]
+    if as_float:      # the reference hands CV_32F integer-valued Mats
+        q, t = q.astype(np.float32), t.astype(np.float32)
+    idx, dist = matcher.knn_match(q, t, NORM_L2, 2, dict(_engines(sfm))[eng])
+    _same_knn(idx, dist, insel_sift[f"p{a}{b}_nidx"], insel_sift[f"p{a}{b}_dist"])
+
+
+@pytest.mark.parametrize("a,b", PAIRS)
+def test_insel_orb_knn_bit_exact(sfm, matcher, insel_orb, a, b):
+    idx, dist = matcher.knn_match(insel_orb[f"desc{a}"], insel_orb[f"desc{b}"], NORM_HAMMING, 2)
+    _same_knn(idx, dist, insel_orb[f"p{a}{b}_nidx"], insel_orb[f"p{a}{b}_dist"])
+
+
+@pytest.mark.parametrize("eng", ["tensor", "simt"])
+def test_adversarial_ties_and_ragged_sizes(sfm, matcher, synthetic_cv2, eng):
+    adv = workloads.adversarial_sift()
+    e = dict(_engines(sfm))[eng]
+    cases = {"dup_base": (adv["dup"], adv["base"]), "base_dup": (adv["base"], adv["dup"]),
+             "zeros_dup": (adv["zeros"], adv["dup"]), "sat_sat": (adv["sat"], adv["sat"]),
+             "base_two": (adv["base"], adv["two"]), "n127_n129": (adv["n127"], adv["n129"]),
+             "n129_n127": (adv["n129"], adv["n127"])}
+    for name, (q, t) in cases.items():
+        idx, dist = matcher.knn_match(q, t, NORM_L2, 2, e)
+        _same_knn(idx, dist, synthetic_cv2[f"{name}_nidx"], synthetic_cv2[f"{name}_dist"])
+    # one train row -> single neighbour, second slot -1 / inf
+    idx, dist = matcher.knn_match(adv["base"], adv["one"], NORM_L2, 2, e)
+    assert np.array_equal(idx[:, 0], synthetic_cv2["base_one_nidx"][:, 0]) and np.all(idx[:, 1] == -1)
+    assert np.array_equal(dist[:, 0].view(np.uint32), synthetic_cv2["base_one_dist"][:, 0].view(np.uint32))
+    # zero train rows -> N empty lists; zero query rows -> empty result
+    idx, dist = matcher.knn_match(adv["base"], adv["empty"], NORM_L2, 2, e)
+    assert np.all(idx == -1)
+    idx, dist = matcher.knn_match(adv["empty"], adv["base"], NORM_L2, 2, e)
+    assert idx.shape == (0, 2)
+    # k = 1 (DescriptorMatcher::match)
+    idx, dist = matcher.knn_match(adv["dup"], adv["base"], NORM_L2, 1, e)
+    assert np.array_equal(idx[:, 0], synthetic_cv2["dup_base_nidx"][:, 0])
+
+
+def test_hamming_ties_and_synthetic(sfm, matcher, synthetic_cv2):
+    ob = workloads.orb_like_bank(3, 900)
+    obd = np.concatenate([ob[1][:50], ob[1][:50], ob[1]])
+    for name, q, t in (("orb01", ob[0], ob[1]), ("orb12", ob[1], ob[2]), ("orb_dup", ob[0], obd),
+                       ("orb_one", ob[0], ob[1][:1])):
+        idx, dist = matcher.knn_match(q, t, NORM_HAMMING, 2)
+        g_idx, g_dist = synthetic_cv2[f"{name}_nidx"], synthetic_cv2[f"{name}_dist"]
+        if name == "orb_one":
+            assert np.array_equal(idx[:, 0], g_idx[:, 0]) and np.all(idx[:, 1] == -1)
+        else:
+            _same_knn(idx, dist, g_idx, g_dist)
+
+
+def test_error_behaviour_mirrors_opencv(sfm, matcher):
+    adv = workloads.adversarial_sift()
+    with pytest.raises(sfm.SfmError):       # width mismatch -> cv::error
+        matcher.knn_match(adv["base"], np.zeros((4, 64), np.uint8), NORM_L2)
+    with pytest.raises(sfm.SfmError):       # float descriptors with NORM_HAMMING -> cv::error
+        matcher.knn_match(adv["base"].astype(np.float32), adv["base"].astype(np.float32), NORM_HAMMING)
+    with pytest.raises(sfm.SfmError):       # k > 2 unsupported
+        matcher.knn_match(adv["base"], adv["base"], NORM_L2, 3)
+    with pytest.raises(sfm.SfmError) as e:  # >= 2^18 train rows (IMGIDX_ONE)
+        matcher.knn_match(adv["base"], np.zeros((1 << 18, 128), np.uint8), NORM_L2)
+    assert e.value.code == sfm.ERR_CAPACITY
+
+
+def test_float_descriptors_tolerance(sfm, matcher):
+    """Non-integer CV_32F data: fp32 path.  Tolerance (north_star): identical match indices except on
+    distance ties within 1e-5 relative; distances within 1e-5 relative."""
+    rng = np.random.default_rng(5)
+    q = rng.random((300, 128), dtype=np.float32) * 3
+    t = rng.random((411, 128), dtype=np.float32) * 3
+    idx, dist = matcher.knn_match(q, t, NORM_L2, 2)
+    eidx, edist = orc.knn2_l2(q, t)
+    assert np.allclose(dist, edist, rtol=1e-5)
+    diff = idx != eidx
+    if diff.any():      # only allowed where the two candidates are tied within tolerance
+        r, k = np.nonzero(diff)
+        d_alt = np.sqrt(((q[r] - t[idx[r, k]]) ** 2).sum(1))
+        assert np.allclose(d_alt, edist[r, k], rtol=1e-5)
+    # 64-wide float descriptors (SURF-like) also run
+    idx, dist = matcher.knn_match(q[:, :64].copy(), t[:, :64].copy(), NORM_L2, 2)
+    eidx, edist = orc.knn2_l2(q[:, :64], t[:, :64])
+    assert np.allclose(dist, edist, rtol=1e-5) and (idx == eidx).mean() > 0.999
+
+
+def test_strided_rows_like_cv_mat_step(sfm, matcher, insel_sift):
+    q = insel_sift["desc0"]
+    big = np.zeros((q.shape[0], 160), np.uint8)
+    big[:, :128] = q
+    idx, dist = matcher.knn_match(big[:, :128], insel_sift["desc1"], NORM_L2, 2)
+    _same_knn(idx, dist, insel_sift["p01_nidx"], insel_sift["p01_dist"])
+
+
+# ------------------------------------------------------------------ plugin level: match_pairs
+@pytest.mark.parametrize("eng", ["tensor", "simt"])
+def test_insel_sift_match_pairs_c1(sfm, matcher, insel_sift, eng):
+    """BASELINE config C1: insel SIFT, grid pairing (seq,row) in {(2,3),(3,3),(2,1)}."""
+    bank = [insel_sift[f"desc{i}"].astype(np.float32) for i in range(3)]
+    matcher.upload_bank(bank)
+    assert matcher.bank_info()["u8_valued"]
+    for seq, row in ((2, 3), (3, 3), (2, 1)):
+        pairs = sfm.select_pairs(3, seq, row)
+        res = matcher.match_pairs(pairs, NORM_L2, engine=dict(_engines(sfm))[eng])
+        for p, (a, b) in enumerate(pairs):
+            assert orc.dmatch_equal(res[p], insel_sift[f"p{a}{b}_good"])
+
+
+def test_insel_orb_match_pairs_c2(sfm, matcher, insel_orb):
+    """BASELINE config C2: insel ORB, sequence pairing seq in {2,3}, bit-exact."""
+    matcher.upload_bank([insel_orb[f"desc{i}"] for i in range(3)])
+    for seq in (2, 3):
+        pairs = sfm.select_pairs(3, seq, 0)
+        res = matcher.match_pairs(pairs, NORM_HAMMING)
+        for p, (a, b) in enumerate(pairs):
+            assert orc.dmatch_equal(res[p], insel_orb[f"p{a}{b}_good"])
+
+
+def test_synthetic_bank_all_pairs_vs_oracle(sfm, matcher):
+    bank = []
+    prev = None
+    for i, n in enumerate((700, 517, 300, 1024, 0, 1, 257)):    # ragged, empty and single-row images
+        prev_ok = prev if prev is not None and prev.shape[0] else None
+        d = workloads.sift_like_image(i, n, prev_ok)
+        bank.append(d)
+        prev = d
+    pairs = sfm.select_pairs(len(bank), 0, 0)
+    matcher.upload_bank(bank)
+    exp = orc.match_pairs(bank, pairs, NORM_L2)
+    for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+        res = matcher.match_pairs(pairs, NORM_L2, engine=eng)
+        assert len(res) == len(pairs)
+        for p in range(len(pairs)):
+            assert orc.dmatch_equal(res[p], exp[p]), (eng, pairs[p])
+    # post filters of SfM::calculateShotMatches
+    exp = orc.match_pairs(bank, pairs, NORM_L2, distinct=True, min_match_count=20)
+    res = matcher.match_pairs(pairs, NORM_L2, distinct=True, min_match_count=20)
+    for p in range(len(pairs)):
+        if exp[p] is None:
+            assert res[p] is None
+        else:
+            assert orc.dmatch_equal(res[p], exp[p])
+    # match() semantics (k = 1 keeps everything)
+    res = matcher.match_pairs(pairs[:3], NORM_L2, k=1)
+    for p in range(3):
+        idx, dist = orc.knn2_l2(bank[pairs[p][0]], bank[pairs[p][1]])
+        assert orc.dmatch_equal(res[p], orc.match_k1(idx, dist))
+
+
+def test_cross_check_vs_cv2_golden(sfm, matcher, insel_sift, synthetic_cv2):
+    matcher.upload_bank([insel_sift[f"desc{i}"] for i in range(3)])
+    res = matcher.match_pairs([[0, 1]], NORM_L2, k=1, cross_check=True)
+    assert orc.dmatch_equal(res[0], insel_sift["p01_cross"])
+    bank = workloads.sift_like_bank(3, 700)
+    matcher.upload_bank(bank)
+    res = matcher.match_pairs([[0, 1]], NORM_L2, k=1, cross_check=True)
+    assert orc.dmatch_equal(res[0], synthetic_cv2["syn01_cross"])
+    ob = workloads.orb_like_bank(3, 900)
+    matcher.upload_bank(ob)
+    res = matcher.match_pairs([[0, 1]], NORM_HAMMING, k=1, cross_check=True)
+    assert orc.dmatch_equal(res[0], synthetic_cv2["orb01_cross"])
+
+
+def test_batching_is_invisible(sfm):
+    """A tiny staging budget forces many batches; results must be byte-identical."""
+    bank = workloads.sift_like_bank(6, 600)
+    pairs = sfm.select_pairs(6, 0, 0)
+    out = []
+    for mb in ("1", "512"):
+        os.environ["SFM_STAGING_MB"] = mb
+        m = sfm.Matcher(0)
+        m.upload_bank(bank)
+        r = m.match_pairs(pairs, NORM_L2)
+        out.append((r.offsets.copy(), r.matches.copy()))
+        m.close()
+    os.environ.pop("SFM_STAGING_MB")
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1].tobytes() == out[1][1].tobytes()
+
+
+def test_full_size_pair_c3_shape(sfm, matcher):
+    """One 8192 x 8192 pair of the C3 workload, full oracle comparison, plus size-independent properties."""
+    a = workloads.sift_like_image(0, 8192)
+    b = workloads.sift_like_image(1, 8192, a)
+    idx, dist = matcher.knn_match(a, b, NORM_L2, 2, sfm.ENGINE_TENSOR)
+    eidx, edist = orc.knn2_l2(a, b)
+    _same_knn(idx, dist, eidx, edist)
+    assert np.all(dist[:, 0] <= dist[:, 1])                      # sortedness
+    sidx, sdist = matcher.knn_match(a, a, NORM_L2, 1, sfm.ENGINE_TENSOR)
+    # self-match: distance 0 at (the lowest index of) an identical row
+    assert np.all(sdist[:, 0] == 0) and np.all(sidx[:, 0] <= np.arange(8192))
+    matcher.upload_bank([a, b])
+    r1 = matcher.match_pairs([[0, 1]], NORM_L2, engine=sfm.ENGINE_TENSOR)
+    r2 = matcher.match_pairs([[0, 1]], NORM_L2, engine=sfm.ENGINE_SIMT)          # two independent kernels agree
+    assert r1.matches.tobytes() == r2.matches.tobytes()
+    assert orc.dmatch_equal(r1[0], orc.ratio_filter(eidx, edist))
+    r3 = matcher.match_pairs([[0, 1]], NORM_L2)                                   # idempotence
+    assert r1.matches.tobytes() == r3.matches.tobytes()
+
+
+def test_orb_30000_rows_properties(sfm, matcher):
+    """N = 30000 (run-orb-sequence.sh -Pfeature-limit=30000): sampled oracle rows + planted-match recovery."""
+    a = workloads.orb_like_image(0, 30000)
+    b = workloads.orb_like_image(1, 30000, a)
+    idx, dist = matcher.knn_match(b[:2048], a, NORM_HAMMING, 2)
+    eidx, edist = orc.knn2_hamming(b[:2048], a)
+    _same_knn(idx, dist, eidx, edist)
+    matcher.upload_bank([a, b])
+    r = matcher.match_pairs([[1, 0]], NORM_HAMMING)
+    got = r[0]
+    # planted copies (first 30 % of b, 20 bit flips) must survive the ratio test
+    assert (got["queryIdx"] < 9000).sum() >= 8900 and np.all(got["distance"][got["queryIdx"] < 9000] <= 20)
+
+
+def test_cli_keeps_reference_switches(sfm, insel_sift, tmp_path):
+    cli = os.path.join(ROOT, "sfm-mvs-pipeline_b200", "sfm_match_cli")
+    if not os.path.exists(cli):
+        pytest.skip("cli not built")
+    bank = [insel_sift[f"desc{i}"].astype(np.float32) for i in range(3)]
+    path = tmp_path / "bank.sfmd"
+    with open(path, "wb") as f:
+        f.write(b"SFMD" + np.array([1, 3, 128, 5], np.uint32).tobytes())
+        for d in bank:
+            f.write(np.uint32(d.shape[0]).tobytes() + d.tobytes())
+    out = tmp_path / "m.bin"
+    r = subprocess.run([cli, f"-Pdescriptors={path}", "-Pfeature-detector=SIFT", "-Pfeature-matcher=FLANN",
+                        "-Pfeature-sequence=2", "-Pfeature-gridlength=3", "-Pmatch-threshold=20", f"-Pout={out}"],
+                       capture_output=True, text=True, timeout=120)
+    assert "pairs=2 kept=2 matches=420" in r.stdout, r.stdout + r.stderr     # 205 + 215 (Appendix B)
+    raw = open(out, "rb").read()
+    assert np.frombuffer(raw[:8], np.uint64)[0] == 2
+    n0 = int(np.frombuffer(raw[16:24], np.uint64)[0])
+    m0 = np.frombuffer(raw[24:24 + 16 * n0], orc.DMATCH_DTYPE)
+    assert orc.dmatch_equal(m0, insel_sift["p01_good"])
