@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — image-pairs/s of the matching stage on BASELINE config C3
+(synthetic unordered all-pairs: 200 images x 8192 SIFT 128-d descriptors, 19 900 pairs).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU matcher
+
+A step = one pass of the hot path over the whole pair list.  `value` = pairs/s with the descriptor bank
+resident in HBM (device time, CUDA events on the library's stream, max over ranks); `e2e` = the same through
+the C-ABI with HOST buffers (pinned CV_32F descriptors uploaded and match lists copied back every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import workloads  # noqa: E402
+
+METRIC = "image-pairs/sec matched @8192 SIFT/img"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=200, help="images in the synthetic bank (C3: 200)")
+    ap.add_argument("--rows", type=int, default=8192, help="descriptors per image (C3: 8192)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    if a.images == 200 and a.rows == 8192:
+        return "C3 synthetic unordered all-pairs: 200 images x 8192 SIFT 128-d (19900 pairs)"
+    return f"synthetic unordered all-pairs: {a.images} images x {a.rows} SIFT 128-d ({a.images * (a.images - 1) // 2} pairs)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def make_pairs(sfm_or_none, n_images):
+    if sfm_or_none is not None:
+        return sfm_or_none.select_pairs(n_images, 0, 0)
+    from oracle import oracle_np as orc
+    return orc.pairs_unordered(n_images)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_baseline(bank_getter, pairs, sample_pairs, seed=7):
+    """cv2 (the OpenCV routines the reference's knnMatch resolves to) on a fixed random sample of the pair list."""
+    from oracle import cv2_ref
+    from oracle.oracle_np import NORM_L2
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sel = pairs[rng.choice(len(pairs), size=min(sample_pairs, len(pairs)), replace=False)]
+    imgs = sorted(set(sel.reshape(-1).tolist()))
+    bank = {i: bank_getter(i) for i in imgs}
+    cores = os.cpu_count() or 1
+    best = None
+    for topo in ("inner", "outer"):
+        dt, good = cv2_ref.time_pairs(bank, sel, NORM_L2, 0.7, topology=topo, threads=cores)
+        v = len(sel) / dt
+        if best is None or v > best[0]:
+            best = (v, topo, dt, good)
+    return {"value": best[0], "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{len(sel)} random pairs (seed {seed}) of the workload, cv2 {cv2_ref.cv2.__version__} "
+                      f"batchDistance(NORM_L2,K=2)+ratio 0.7 = the OpenCV routine the reference's knnMatch calls; "
+                      f"topology '{best[1]}' (best of pairs-serial/threads-inside and threads-over-pairs), {best[2]:.1f} s",
+            "good_matches_in_sample": int(best[3])}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cv2_ref
+    from oracle.oracle_np import NORM_L2
+    if not cv2_ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "cv2 not importable on this box"}))
+        return
+    pairs = make_pairs(None, a.images)
+    cache = {}
+
+    def get(i):
+        if i not in cache:
+            prev = get(i - 1) if i > 0 else None
+            cache[i] = workloads.sift_like_image(i, a.rows, prev)
+        return cache[i]
+
+    cores = os.cpu_count() or 1
+    rng = np.random.Generator(np.random.PCG64(7))
+    per_step = max(1, min(a.cpu_sample_pairs // 2, len(pairs)))
+    # cap the image range so that bank generation stays bounded
+    pool = pairs[(pairs[:, 1] < min(a.images, 24))]
+    steps = []
+    for s in range(a.warmup + a.steps):
+        steps.append(pool[rng.choice(len(pool), size=min(per_step, len(pool)), replace=False)])
+    bank = {i: get(i) for i in sorted(set(np.concatenate(steps).reshape(-1).tolist()))}
+    # pick the faster thread topology once (untimed)
+    t_in, _ = cv2_ref.time_pairs(bank, steps[0][:4], NORM_L2, 0.7, "inner", cores)
+    t_out, _ = cv2_ref.time_pairs(bank, steps[0][:max(4, min(cores, len(steps[0])))], NORM_L2, 0.7, "outer", cores)
+    topo = "inner" if t_in / 4 <= t_out / max(4, min(cores, len(steps[0]))) else "outer"
+    for s in range(a.warmup):
+        cv2_ref.time_pairs(bank, steps[s], NORM_L2, 0.7, topo, cores)
+    t0 = time.perf_counter()
+    n = 0
+    for s in range(a.warmup, a.warmup + a.steps):
+        cv2_ref.time_pairs(bank, steps[s], NORM_L2, 0.7, topo, cores)
+        n += len(steps[s])
+    dt = time.perf_counter() - t0
+    v = n / dt
+    sample = (f"each step = {per_step} random pairs of the workload (images 0..23), cv2 {cv2_ref.cv2.__version__} "
+              f"batchDistance+ratio on {cores} host threads, topology '{topo}'")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the matcher has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sfm = ge.load_package()
+    spec = __import__("importlib").util.spec_from_file_location("sfm_shard", os.path.join(ge.PKG_DIR, "shard.py"))
+    shard = __import__("importlib").util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+
+    n_img, n_rows = a.images, a.rows
+    pairs = make_pairs(sfm, n_img)
+    # ---- synthetic bank: rank 0 generates, NCCL broadcast gives every GPU its replica
+    bank_dev = torch.empty((n_img * n_rows, 128), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        host = np.concatenate(workloads.sift_like_bank(n_img, n_rows))
+        bank_dev.copy_(torch.from_numpy(host))
+    if world > 1:
+        shard.broadcast_bank(bank_dev, 0)
+    torch.cuda.synchronize()
+    m = sfm.Matcher(local_rank)
+    rows_per = [n_rows] * n_img
+    offs = [i * n_rows for i in range(n_img)]
+    m.upload_bank_device(bank_dev.data_ptr(), offs, rows_per, 128, sfm.CV_8U)
+    # host copy as the reference holds it: CV_32F integer-valued Mats, page-locked
+    host_f32 = torch.empty((n_img * n_rows, 128), dtype=torch.float32, pin_memory=True)
+    host_f32.copy_(bank_dev.to(torch.float32).cpu())
+    host_np = host_f32.numpy()
+    host_list = [host_np[i * n_rows:(i + 1) * n_rows] for i in range(n_img)]
+    del bank_dev
+
+    mine = shard.assign_pairs(pairs, rows_per, world)[rank]
+    my_pairs = np.ascontiguousarray(pairs[mine])
+    stream = torch.cuda.ExternalStream(m.stream, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        m.enqueue(my_pairs, sfm.NORM_L2)
+    m.set_profiling(True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    st0 = m.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    knn_ms = post_ms = 0.0
+    knn_launches = 0
+    e0.record(stream)
+    for _ in range(a.steps):
+        m.enqueue(my_pairs, sfm.NORM_L2)
+        pr = m.last_profile()            # waits for this step's last kernel: steps run back to back on the stream
+        knn_ms += pr["knn_ms"]; post_ms += pr["post_ms"]; knn_launches += pr["knn_launches"]
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = m.stats()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = torch.tensor([st1["kernel_launches"] - st0["kernel_launches"]], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(launches)
+    m.set_profiling(False)
+    result = m.collect()
+    value = len(pairs) * a.steps / (ms_total / 1e3)
+
+    # ---- end to end through the C ABI with host buffers
+    e2e_ms, h2d, d2h = [], 0, 0
+    total_matches = None
+    for _ in range(max(1, a.e2e_steps)):
+        barrier()
+        s0 = m.stats()
+        t0 = time.perf_counter()
+        m.upload_bank(host_list)                                   # pinned CV_32F -> device, packed to u8 on the GPU
+        res = m.match_pairs(my_pairs, sfm.NORM_L2)                 # kernels + D2H of the compacted lists
+        if world > 1:
+            g = shard.gather_matches(mine, res.counts(), res.matches, res.dropped, len(pairs), dev, 0)
+            if rank == 0:
+                total_matches = int(g[0][-1])
+        else:
+            total_matches = int(res.offsets[-1])
+        barrier()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        s1 = m.stats()
+        h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
+    t = torch.tensor([min(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = len(pairs) / (float(t.item()) / 1e3)
+
+    if rank == 0:
+        bf16_burst, bf16_sust, hbm, src = measured_peaks()
+        ops_per_step_rank = 2.0 * n_rows * n_rows * 128 * len(my_pairs)
+        achieved = ops_per_step_rank * a.steps / (knn_ms / 1e3) / 1e12 if knn_ms > 0 else None
+        peak_i8 = 2.0 * bf16_sust
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "knn_tc_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(a), "pairs": int(len(pairs)), "parallelism": f"pair-list x{world}",
+                       "l2": "inputs larger than L2 (bank 200 MiB + 512 MiB top-2 staging per batch vs 126 MB L2); no flush",
+                       "engine": "tcgen05 kind::i8 + fused top-2 epilogue", "matches_per_step": total_matches,
+                       "matches_device_run": int(result.offsets[-1])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": float(t.item()), "host_buffers": "pinned CV_32F descriptors, as the reference holds them"},
+            "gpu_launches": int(launches.item()),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_i8, "unit": "TFLOP/s",
+                         "frac": (achieved / peak_i8) if achieved else None, "traffic": traffic,
+                         "kernel": "knn2_l2_u8_tc_kernel", "launches": knn_launches,
+                         "avg_launch_ms": knn_ms / max(1, knn_launches),
+                         "algorithmic": "2*Nq*Nt*128 op per pair (SURVEY 8d) x pairs per launch",
+                         "peak_source": f"{src}: 2 x bf16_tflops_sustained ({bf16_sust}) for kind::i8",
+                         "frac_of_bf16_rate": (achieved / bf16_sust) if achieved else None,
+                         "knn_share_of_step": knn_ms / ms_total if ms_total else None},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                cache = {}
+
+                def get(i):
+                    if i not in cache:
+                        cache[i] = host_np[i * n_rows:(i + 1) * n_rows]
+                    return cache[i]
+                out["cpu_baseline"] = cpu_baseline(get, pairs, a.cpu_sample_pairs)
+            except Exception as ex:  # pragma: no cover
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
+                                       "sample": f"failed: {ex}"}
+        print(json.dumps(out))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

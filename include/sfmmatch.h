@@ -132,6 +132,11 @@ void              sfm_result_free(sfm_result *r);
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
+/* Per-kernel device timing of the last enqueue (CUDA events on the context stream around the knn kernel and
+ * around the filter/scan/compact kernels of every batch).  Measurement aid for bench.py's roofline block. */
+int sfm_set_profiling(sfm_ctx *ctx, int on);
+int sfm_last_profile(sfm_ctx *ctx, double *knn_ms, double *post_ms, int *knn_launches);
+
 /* Operator level ---------------------------------------------------------------------------------
  * Replaces cv::DescriptorMatcher::knnMatch(query, train, matches, k) (call sites
  * UnorderedFeatureMatchingStrategy.cpp:51, VideoFeatureMatchingStrategy.cpp:62,

@@ -108,6 +108,10 @@ struct sfm_ctx {
     cudaEvent_t meta_ev = nullptr;   // h_meta may be rewritten once this has fired
     RunState run;
     int64_t stat_launches = 0, stat_h2d = 0, stat_d2h = 0;
+    // optional per-kernel timing of the last enqueue (sfm_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;     // triples per batch: knn begin, knn end, post end
+    int prof_used = 0;
     size_t staging_budget_rows = 0;
 };
 
@@ -219,15 +223,27 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
     DevBuf& dst = depth == SFM_CV_32F ? b.d_f32 : b.d_u8;
     CU_TRY(c, dst.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * row_bytes)));
     CU_TRY(c, cudaMemsetAsync(dst.p, 0, static_cast<size_t>(b.padded_rows) * row_bytes, s));
-    // stage through two pinned buffers so that the H2D copy of one chunk overlaps the host gather of the next
+    // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are
+    // DMA'd directly; pageable ones are staged through two pinned buffers so that the H2D copy of one chunk
+    // overlaps the host gather of the next.
     const size_t chunk = size_t(32) << 20;
-    for (int k = 0; k < 2; ++k) CU_TRY(c, c->h_stage[k].ensure(chunk));
     int which = 0;
     for (int i = 0; i < n_images; ++i) {
         if (n_rows[i] == 0) continue;
         if (!rows[i]) return fail(c, SFM_ERR_INVALID, "bank: null descriptor pointer for a non-empty image");
         const size_t step = step_bytes ? step_bytes[i] : row_bytes;
         if (step < row_bytes) return fail(c, SFM_ERR_INVALID, "bank: step smaller than a row");
+        uint8_t* d_img = static_cast<uint8_t*>(dst.p) + static_cast<size_t>(b.row0[i]) * row_bytes;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, rows[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        if (pinned) {
+            CU_TRY(c, cudaMemcpy2DAsync(d_img, row_bytes, rows[i], step, row_bytes, static_cast<size_t>(n_rows[i]),
+                                        cudaMemcpyHostToDevice, s));
+            c->stat_h2d += static_cast<int64_t>(n_rows[i]) * static_cast<int64_t>(row_bytes);
+            continue;
+        }
+        for (int k = 0; k < 2; ++k) CU_TRY(c, c->h_stage[k].ensure(chunk));
         const size_t rows_per_chunk = std::max<size_t>(1, chunk / row_bytes);
         for (size_t r0 = 0; r0 < static_cast<size_t>(n_rows[i]); r0 += rows_per_chunk) {
             const size_t nr = std::min(rows_per_chunk, static_cast<size_t>(n_rows[i]) - r0);
@@ -236,8 +252,7 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
             const uint8_t* src = static_cast<const uint8_t*>(rows[i]) + r0 * step;
             if (step == row_bytes) std::memcpy(h, src, nr * row_bytes);
             else for (size_t r = 0; r < nr; ++r) std::memcpy(h + r * row_bytes, src + r * step, row_bytes);
-            CU_TRY(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst.p) + (static_cast<size_t>(b.row0[i]) + r0) * row_bytes, h,
-                                      nr * row_bytes, cudaMemcpyHostToDevice, s));
+            CU_TRY(c, cudaMemcpyAsync(d_img + r0 * row_bytes, h, nr * row_bytes, cudaMemcpyHostToDevice, s));
             CU_TRY(c, cudaEventRecord(c->stage_ev[which], s));
             c->stat_h2d += static_cast<int64_t>(nr * row_bytes);
             which ^= 1;
@@ -407,16 +422,26 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
 
     FilterParams fp;
     fp.norm = o->norm; fp.k = o->k; fp.ratio = o->ratio; fp.cross_check = o->cross_check; fp.distinct = o->distinct;
+    c->prof_used = 0;
+    if (c->profiling) {
+        while (static_cast<int64_t>(c->prof_ev.size()) < 3 * nb) {
+            cudaEvent_t ev;
+            CU_TRY(c, cudaEventCreate(&ev));
+            c->prof_ev.push_back(ev);
+        }
+    }
     for (int64_t bi = 0; bi < nb; ++bi) {
         const Batch& B = batches[bi];
         const int np = static_cast<int>(B.p1 - B.p0);
         const int64_t base = B.p0 + bi;
+        if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
         rc = launch_knn(c, b, eng, d_pd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>());
         if (rc != SFM_OK) return rc;
         if (need_rev) {
             rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, c->d_rev.as<Top2>());
             if (rc != SFM_OK) return rc;
         }
+        if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 1], s));
         FilterArgs a;
         a.top2 = c->d_top2.as<Top2>(); a.rev = c->d_rev.as<Top2>(); a.pairs = d_pd + B.p0;
         a.out_prefix = d_outp + base; a.t_prefix = d_tp + base; a.n_pairs = np; a.staged_rows = B.staged_rows;
@@ -433,6 +458,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
         CU_TRY(c, launch_compact(a, c->d_chunk_excl.as<int64_t>(), c->d_pair_offsets.as<int64_t>() + B.p0,
                                  c->d_dropped.as<uint8_t>() + B.p0, c->d_out.as<DMatch>(), c->out_capacity, d_overflow, s));
         c->stat_launches += 3;
+        if (c->profiling) { CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 2], s)); c->prof_used = static_cast<int>(3 * (bi + 1)); }
     }
     c->run.valid = true;
     c->run.n_pairs = n_pairs;
@@ -541,6 +567,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->meta_ev) cudaEventDestroy(c->meta_ev);
+    for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -627,6 +654,30 @@ int sfm_last_stats(const sfm_ctx* c, int64_t* launches, int64_t* h2d, int64_t* d
     if (launches) *launches = c->stat_launches;
     if (h2d) *h2d = c->stat_h2d;
     if (d2h) *d2h = c->stat_d2h;
+    return SFM_OK;
+}
+
+int sfm_set_profiling(sfm_ctx* c, int on) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->profiling = on != 0;
+    return SFM_OK;
+}
+
+int sfm_last_profile(sfm_ctx* c, double* knn_ms, double* post_ms, int* knn_launches) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    double k = 0, p = 0;
+    if (c->prof_used > 0) CU_TRY(c, cudaEventSynchronize(c->prof_ev[c->prof_used - 1]));
+    for (int i = 0; i + 3 <= c->prof_used; i += 3) {
+        float a = 0, b2 = 0;
+        CU_TRY(c, cudaEventElapsedTime(&a, c->prof_ev[i], c->prof_ev[i + 1]));
+        CU_TRY(c, cudaEventElapsedTime(&b2, c->prof_ev[i + 1], c->prof_ev[i + 2]));
+        k += a; p += b2;
+    }
+    if (knn_ms) *knn_ms = k;
+    if (post_ms) *post_ms = p;
+    if (knn_launches) *knn_launches = c->prof_used / 3 * (c->run.opts.cross_check ? 2 : 1);
     return SFM_OK;
 }
 

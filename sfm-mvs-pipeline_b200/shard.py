@@ -1,0 +1,96 @@
+"""Pair-list sharding across GPUs and gathering of match lists (one process per GPU, torch.distributed).
+
+The stage shards naturally: every image pair is independent (the reference already runs them as an OpenMP
+``parallel for`` over pairs, UnorderedFeatureMatchingStrategy.cpp:40).  Each rank holds a replica of the
+descriptor bank, takes a cost-balanced share of the pair list, and only the compacted match lists travel:
+NCCL (or gloo in the CPU tests) is used to broadcast the bank and to gather (counts, matches) on rank 0.
+No data-path collective runs while the kernels work.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def assign_pairs(pairs: np.ndarray, n_rows, world_size: int):
+    """Deal pairs to ranks by cost Nq*Nt: sort by cost (descending, stable) and deal round-robin in a
+    snake order, then restore ascending pair order inside each rank (keeps pairs that share the left image
+    adjacent, which keeps the train images L2-resident).  Equal-cost lists degenerate to a strided deal.
+    Returns a list of int64 index arrays (positions in ``pairs``), one per rank."""
+    pairs = np.asarray(pairs, np.int64).reshape(-1, 2)
+    n_rows = np.asarray(n_rows, np.int64)
+    if world_size <= 1 or len(pairs) == 0:
+        return [np.arange(len(pairs), dtype=np.int64)] + [np.zeros(0, np.int64) for _ in range(max(0, world_size - 1))]
+    cost = n_rows[pairs[:, 0]] * n_rows[pairs[:, 1]]
+    order = np.argsort(-cost, kind="stable")
+    k = np.arange(len(order))
+    rnd, pos = k // world_size, k % world_size
+    rank_of = np.where(rnd % 2 == 0, pos, world_size - 1 - pos)      # snake: 0..W-1, W-1..0, ...
+    out = []
+    for r in range(world_size):
+        out.append(np.sort(order[rank_of == r]).astype(np.int64))
+    return out
+
+
+def broadcast_bank(bank_tensor, src: int = 0, group=None):
+    """Broadcast the packed descriptor bank (a torch tensor, on the GPU under NCCL) from ``src``."""
+    import torch.distributed as dist
+    dist.broadcast(bank_tensor, src=src, group=group)
+    return bank_tensor
+
+
+def gather_matches(local_idx: np.ndarray, counts: np.ndarray, matches: np.ndarray, dropped: np.ndarray,
+                   n_pairs_total: int, device, dst: int = 0, group=None):
+    """Gather per-rank results on ``dst`` and reassemble them in global pair order.
+
+    local_idx : positions (in the global pair list) of this rank's pairs, ascending
+    counts    : matches per local pair;  matches: concatenated DMatch records (structured, 16 B)
+    Returns (offsets[n_pairs_total+1], matches, dropped) on ``dst`` and None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_local, n_match = int(len(local_idx)), int(len(matches))
+    sizes = torch.tensor([n_local, n_match], dtype=torch.int64, device=device)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    max_local, max_match = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    # one int32 payload per rank: [idx | counts | dropped | matches as 4 x int32]
+    width = 3 * max_local + 4 * max_match
+    payload = np.zeros(max(width, 1), np.int32)
+    payload[:n_local] = local_idx
+    payload[max_local:max_local + n_local] = counts
+    payload[2 * max_local:2 * max_local + n_local] = dropped
+    if n_match:
+        payload[3 * max_local:3 * max_local + 4 * n_match] = np.ascontiguousarray(matches).view(np.int32).reshape(-1)
+    t = torch.from_numpy(payload).to(device)
+    gathered = [torch.zeros_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    total_counts = np.zeros(n_pairs_total, np.int64)
+    total_dropped = np.zeros(n_pairs_total, np.uint8)
+    per_rank = []
+    for r in range(world):
+        buf = gathered[r].cpu().numpy()
+        nl, nm = int(all_sizes[r, 0]), int(all_sizes[r, 1])
+        idx = buf[:nl].astype(np.int64)
+        cnt = buf[max_local:max_local + nl].astype(np.int64)
+        total_counts[idx] = cnt
+        total_dropped[idx] = buf[2 * max_local:2 * max_local + nl].astype(np.uint8)
+        m = buf[3 * max_local:3 * max_local + 4 * nm].copy().view(_dmatch_dtype())
+        per_rank.append((idx, cnt, m))
+    offsets = np.zeros(n_pairs_total + 1, np.int64)
+    np.cumsum(total_counts, out=offsets[1:])
+    out = np.zeros(int(offsets[-1]), _dmatch_dtype())
+    for idx, cnt, m in per_rank:
+        src_off = np.zeros(len(cnt) + 1, np.int64)
+        np.cumsum(cnt, out=src_off[1:])
+        for k in range(len(idx)):
+            if cnt[k]:
+                out[offsets[idx[k]]:offsets[idx[k]] + cnt[k]] = m[src_off[k]:src_off[k + 1]]
+    return offsets, out, total_dropped
+
+
+def _dmatch_dtype():
+    return np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
