@@ -26,8 +26,9 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
                                  int n_pairs, int64_t n_units, Top2* out, int sm_count, cudaStream_t s);
 
 // ---- post.cu
-cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols, uint8_t* dst,
-                                  int* not_integer_flag, cudaStream_t s);
+cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols,
+                                  const int32_t* valid_in_block, uint8_t* dst, int* not_integer_flag, cudaStream_t s);
+cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, const int32_t* valid_in_block, cudaStream_t s);
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* row_valid_end /*per 256-row block*/,
                                int32_t* norm2, int32_t* ckey, cudaStream_t s);
 struct FilterParams {
@@ -51,6 +52,19 @@ struct FilterArgs {
     FilterParams fp;
     int32_t* train_cnt;          // distinct: zeroed by the caller
 };
+// tcgen05 path only: tighten the provisional second neighbour (see refine_second_kernel in post.cu)
+struct RefineArgs {
+    Top2* top2;
+    const PairDesc* pairs;
+    const int64_t* out_prefix;   // n_pairs + 1
+    int n_pairs;
+    int64_t staged_rows;
+    const uint8_t* bank;         // u8 bank, 128-byte rows
+    const int32_t* norm2;
+    int all_rows;                // 1: every row (raw knnMatch output), 0: only rows that can pass the ratio test
+    double ratio;
+};
+cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
 // pass 1 (only with distinct): count how often each train row is the best match of a kept query row
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s);
 // pass 2: number of surviving matches per 256-row chunk

@@ -11,6 +11,10 @@
 // a single IMAD per element from a per-train-row constant ckey_j that TMA-bulk-copies in with the tile.
 // Keys are unique inside a tile, so "ties -> lowest trainIdx"  is free; across tiles the
 // running state is a 64-bit (value, global column) key.  All arithmetic is integer: results are bit-exact.
+// To keep the epilogue at ~0.6 ALU op per element the kernel tracks the top-2 of 32-column CHUNK MINIMA
+// (VIMNMX3 trees): rank 1 is exact, rank 2 is the best element outside rank 1's chunk.  The true second
+// neighbour is min(that, second-best inside rank 1's chunk); refine_second_kernel recomputes those 31
+// distances with __dp4a, and only for rows whose provisional ratio test passes (a fraction of a percent).
 //
 // Persistent kernel, one CTA per SM, warp-specialised:
 //   warp 0      TMA producer   (A tile once per unit, B tile + ckeys per train tile, 4-stage ring)
@@ -186,7 +190,11 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
                 const int4* ck4 = reinterpret_cast<const int4*>(base_ptr + offCk + cs * kCkBytes);
-                int32_t m1a = INT32_MAX, m2a = INT32_MAX, m1b = INT32_MAX, m2b = INT32_MAX;
+                // Per 32-column chunk: 32 IMAD build the keys, a VIMNMX3 tree (16 ops) takes the chunk minimum,
+                // 3 more ops insert it into the running top-2 OF CHUNK MINIMA.  m1 is therefore the exact best
+                // element; m2 is the best element outside m1's chunk, an upper bound of the true second
+                // neighbour that refine_second_kernel (post.cu) tightens for the rows that need it.
+                int32_t m1 = INT32_MAX, m2 = INT32_MAX;
                 uint32_t v[2][32];
                 tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
@@ -202,21 +210,29 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                    "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
                                  :: "memory");
                     if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    int32_t k[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const int4 ck = ck4[c * 8 + (j >> 2)];           // smem broadcast
-                        top2_key(ck.x - 512 * static_cast<int32_t>(cur[j]), m1a, m2a);
-                        top2_key(ck.y - 512 * static_cast<int32_t>(cur[j + 1]), m1b, m2b);
-                        top2_key(ck.z - 512 * static_cast<int32_t>(cur[j + 2]), m1a, m2a);
-                        top2_key(ck.w - 512 * static_cast<int32_t>(cur[j + 3]), m1b, m2b);
+                        k[j] = ck.x - 512 * static_cast<int32_t>(cur[j]);
+                        k[j + 1] = ck.y - 512 * static_cast<int32_t>(cur[j + 1]);
+                        k[j + 2] = ck.z - 512 * static_cast<int32_t>(cur[j + 2]);
+                        k[j + 3] = ck.w - 512 * static_cast<int32_t>(cur[j + 3]);
                     }
+                    // balanced min3 tree: 32 -> 11 -> 4 -> 2 -> 1
+                    int32_t a[11];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) a[i] = __vimin3_s32(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+                    a[10] = min(k[30], k[31]);
+                    const int32_t b0 = __vimin3_s32(a[0], a[1], a[2]), b1 = __vimin3_s32(a[3], a[4], a[5]);
+                    const int32_t b2 = __vimin3_s32(a[6], a[7], a[8]), b3 = min(a[9], a[10]);
+                    const int32_t cm = min(__vimin3_s32(b0, b1, b2), b3);
+                    top2_key(cm, m1, m2);
                 }
                 // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
                 tc_fence_before();
                 mbar_arrive(acc_empty(acc));
-                // merge the two chains (keys unique inside a tile) and fold into the 64-bit running state
-                const int32_t t1 = min(m1a, m1b);
-                const int32_t t2 = min(max(m1a, m1b), min(m2a, m2b));
+                const int32_t t1 = m1, t2 = m2;
                 const int64_t colbase = static_cast<int64_t>(t) * BN;
                 const int64_t k1 = static_cast<int64_t>(t1 >> 8) * (1ll << 32) + (colbase + (t1 & 255));
                 const int64_t k2 = static_cast<int64_t>(t2 >> 8) * (1ll << 32) + (colbase + (t2 & 255));

@@ -5,6 +5,8 @@
 //                    (…:66-72), cross-check (cv::BFMatcher crossCheck semantics), distinct (SfM.cpp:547-564)
 //   scan_offsets     per-pair counts, min-match-count drop (SfM.cpp:566-570), output offsets
 //   compact          ordered DMatch lists (ascending queryIdx, pair order)
+#include <climits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -14,31 +16,51 @@ constexpr int kNormL2 = 4;
 
 // ------------------------------------------------------------------------------------------------ upload helpers
 __global__ void pack_f32_to_u8_kernel(const float* __restrict__ src, size_t stride, int n_rows, int cols,
-                                      uint8_t* __restrict__ dst, int* __restrict__ bad) {
+                                      const int32_t* __restrict__ valid_in_block, uint8_t* __restrict__ dst,
+                                      int* __restrict__ bad) {
     const int vec_per_row = cols >> 2;
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<int64_t>(n_rows) * vec_per_row) return;
     const int r = static_cast<int>(i / vec_per_row), v = static_cast<int>(i - static_cast<int64_t>(r) * vec_per_row);
-    const float4 f = *reinterpret_cast<const float4*>(src + r * stride + 4 * v);
-    const float e[4] = {f.x, f.y, f.z, f.w};
     uint32_t w = 0;
-    bool ok = true;
+    if ((r & (kRowAlign - 1)) < valid_in_block[r / kRowAlign]) {       // padding rows become zero descriptors
+        const float4 f = *reinterpret_cast<const float4*>(src + r * stride + 4 * v);
+        const float e[4] = {f.x, f.y, f.z, f.w};
+        bool ok = true;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float x = e[k];
-        ok = ok && (x >= 0.f) && (x <= 255.f) && (x == rintf(x));   // NaN fails x >= 0
-        w |= (static_cast<uint32_t>(ok ? static_cast<int>(x) : 0) & 0xFFu) << (8 * k);
+        for (int k = 0; k < 4; ++k) {
+            const float x = e[k];
+            ok = ok && (x >= 0.f) && (x <= 255.f) && (x == rintf(x));   // NaN fails x >= 0
+            w |= (static_cast<uint32_t>(ok ? static_cast<int>(x) : 0) & 0xFFu) << (8 * k);
+        }
+        if (!ok) atomicOr(bad, 1);
     }
-    if (!ok) atomicOr(bad, 1);
     *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r) * cols + 4 * v) = w;
 }
 
-cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols, uint8_t* dst,
-                                  int* not_integer_flag, cudaStream_t s) {
+cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols,
+                                  const int32_t* valid_in_block, uint8_t* dst, int* not_integer_flag, cudaStream_t s) {
     const int64_t n = static_cast<int64_t>(n_rows) * (cols >> 2);
     if (n == 0) return cudaSuccess;
-    pack_f32_to_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, src_stride_elems, n_rows, cols, dst,
-                                                                                  not_integer_flag);
+    pack_f32_to_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(src, src_stride_elems, n_rows, cols,
+                                                                                  valid_in_block, dst, not_integer_flag);
+    return cudaGetLastError();
+}
+
+// zero the padding rows of a bank (rows past each image's last descriptor, up to the 256-row boundary)
+__global__ void zero_padding_kernel(uint8_t* __restrict__ bank, int row_vecs /*16-byte units per row*/, int64_t padded_rows,
+                                    const int32_t* __restrict__ valid_in_block) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= padded_rows * row_vecs) return;
+    const int64_t r = i / row_vecs;
+    if ((r & (kRowAlign - 1)) >= valid_in_block[r / kRowAlign]) reinterpret_cast<uint4*>(bank)[i] = make_uint4(0, 0, 0, 0);
+}
+
+cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, const int32_t* valid_in_block, cudaStream_t s) {
+    const int64_t n = padded_rows * (row_bytes / 16);
+    if (n == 0) return cudaSuccess;
+    zero_padding_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(static_cast<uint8_t*>(bank), row_bytes / 16,
+                                                                                padded_rows, valid_in_block);
     return cudaGetLastError();
 }
 
@@ -161,8 +183,71 @@ __global__ void __launch_bounds__(256) compact_kernel(FilterArgs a, const int64_
     out[pos] = m;
 }
 
+// ------------------------------------------------------------------------------------------------ refine
+// The tcgen05 kernel reports rank 1 exactly and, as rank 2, the best train row OUTSIDE the 32-row chunk that
+// holds rank 1.  The true second neighbour is the smaller of that and the second-best row inside the chunk.
+// A row needs the recomputation only if it could still survive the ratio test: with the provisional
+// d1' >= d1(true), d0 >= ratio*d1' already implies rejection.  For every row that needs it one warp recomputes
+// the chunk: lane l takes train row chunk0 + l (128-byte row, 32 x __dp4a), then a warp min over the packed
+// (distance, index) keys.  Exact integer arithmetic, ties -> lowest trainIdx.
+__global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool need = false, changed = false;
+    Top2 t;
+    t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
+    int q_bank_row = 0, t_row0 = 0, nt = 0;
+    if (srow < a.staged_rows) {
+        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        const PairDesc pd = a.pairs[p];
+        const int row = static_cast<int>(srow - a.out_prefix[p]);
+        if (row < pd.nq) {
+            t = a.top2[srow];
+            q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
+            if (t.i0 >= 0) {
+                if (a.all_rows || t.i1 < 0) need = true;
+                else need = static_cast<double>(__fsqrt_rn(t.d0)) < static_cast<double>(__fsqrt_rn(t.d1)) * a.ratio;
+            }
+        }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
+        const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
+        const int ntr = __shfl_sync(0xffffffffu, nt, src);
+        const int best = __shfl_sync(0xffffffffu, t.i0, src);
+        const int j = (best & ~31) + lane;
+        const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
+        const uint4* tv = reinterpret_cast<const uint4*>(a.bank + (static_cast<size_t>(tr0) + j) * 128);
+        uint32_t dot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 x = __ldg(qv + i), y = __ldg(tv + i);
+            dot = __dp4a(x.x, y.x, dot); dot = __dp4a(x.y, y.y, dot);
+            dot = __dp4a(x.z, y.z, dot); dot = __dp4a(x.w, y.w, dot);
+        }
+        const int32_t d = a.norm2[qrow] + a.norm2[tr0 + j] - 2 * static_cast<int32_t>(dot);
+        long long key = (j < ntr && j != best) ? ((static_cast<long long>(d) << 32) | static_cast<unsigned>(j)) : LLONG_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+        if (lane == src && key != LLONG_MAX) {
+            const float cd = static_cast<float>(static_cast<int32_t>(key >> 32));
+            const int cj = static_cast<int>(key & 0xFFFFFFFFll);
+            if (t.i1 < 0 || cd < t.d1 || (cd == t.d1 && cj < t.i1)) { t.i1 = cj; t.d1 = cd; changed = true; }
+        }
+    }
+    if (changed) a.top2[srow] = t;
+}
+
 static inline unsigned chunks_of(int64_t rows) { return static_cast<unsigned>((rows + 255) / 256); }
 
+cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    refine_second_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
     filter_mark_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);

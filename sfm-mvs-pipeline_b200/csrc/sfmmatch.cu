@@ -87,6 +87,7 @@ struct RunState {                    // what collect() needs from the last enque
 struct sfm_result {
     int64_t n_pairs = 0;
     PinBuf offsets, matches, dropped;
+    sfm_ctx* owner = nullptr;
 };
 
 struct sfm_ctx {
@@ -103,9 +104,11 @@ struct sfm_ctx {
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
     int64_t out_capacity = 0;
-    PinBuf h_meta, h_stage[2], h_scalars, h_knn;
+    PinBuf h_meta, h_stage[2], h_scalars, h_knn, h_valid;
+    std::vector<sfm_result*> result_pool;   // recycled results (pinned buffers are expensive to allocate)
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t meta_ev = nullptr;   // h_meta may be rewritten once this has fired
+    cudaEvent_t valid_ev = nullptr;  // same for h_valid
     RunState run;
     int64_t stat_launches = 0, stat_h2d = 0, stat_d2h = 0;
     // optional per-kernel timing of the last enqueue (sfm_set_profiling)
@@ -175,40 +178,51 @@ int bank_layout(sfm_ctx* c, Bank& b, int n_images, const int32_t* n_rows, int co
 int bank_finish(sfm_ctx* c, Bank& b) {
     cudaStream_t s = c->stream;
     b.u8_valued = false; b.have_f32 = false;
+    if (b.padded_rows == 0) { b.u8_valued = b.depth == SFM_CV_8U; return make_tmaps(c, b); }
+    // valid rows per 256-row block (pinned temporary: no sync needed before it is reused, see meta_ev)
+    const int64_t nblk = b.padded_rows / kRowAlign;
+    CU_TRY(c, cudaEventSynchronize(c->valid_ev));
+    CU_TRY(c, c->h_valid.ensure(static_cast<size_t>(nblk) * 4));
+    int32_t* valid = c->h_valid.as<int32_t>();
+    for (int i = 0; i < b.n_images; ++i) {
+        const int64_t b0 = b.row0[i] / kRowAlign, nb = pad_rows(b.n_rows[i]) / kRowAlign;
+        for (int64_t k = 0; k < nb; ++k)
+            valid[b0 + k] = static_cast<int32_t>(std::min<int64_t>(kRowAlign, std::max<int64_t>(0, b.n_rows[i] - k * kRowAlign)));
+    }
+    CU_TRY(c, b.d_valid.ensure(static_cast<size_t>(nblk) * 4));
+    CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid, static_cast<size_t>(nblk) * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(c, cudaEventRecord(c->valid_ev, s));
+    const int32_t* d_valid = b.d_valid.as<int32_t>();
     if (b.depth == SFM_CV_32F) {
         b.have_f32 = true;
-        if (b.cols == 128 && b.padded_rows > 0) {
+        if (b.cols == 128) {
             CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
             int* flag = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 12);
             CU_TRY(c, cudaMemsetAsync(flag, 0, 4, s));
-            CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>(), 128, static_cast<int>(b.padded_rows), 128,
+            CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>(), 128, static_cast<int>(b.padded_rows), 128, d_valid,
                                             b.d_u8.as<uint8_t>(), flag, s));
             c->stat_launches++;
-            int* h = c->h_scalars.as<int>();
+            int* h = c->h_scalars.as<int>() + 8;
             CU_TRY(c, cudaMemcpyAsync(h, flag, 4, cudaMemcpyDeviceToHost, s));
             CU_TRY(c, cudaStreamSynchronize(s));
-            if (*h == 0) { b.u8_valued = true; b.have_f32 = false; b.d_f32.release(); }
+            // integer-valued (what cv::SIFT emits): match on the u8 copy; d_f32 stays allocated as upload staging
+            if (*h == 0) { b.u8_valued = true; b.have_f32 = false; }
+        }
+        if (b.have_f32) {
+            CU_TRY(c, launch_zero_padding(b.d_f32.p, b.cols * 4, b.padded_rows, d_valid, s));
+            c->stat_launches++;
         }
     } else {
         b.u8_valued = true;
+        CU_TRY(c, launch_zero_padding(b.d_u8.p, b.cols, b.padded_rows, d_valid, s));
+        c->stat_launches++;
     }
-    if (b.u8_valued && b.cols == 128 && b.padded_rows > 0) {
-        // valid rows per 256-row block
-        const int64_t nblk = b.padded_rows / kRowAlign;
-        std::vector<int32_t> valid(nblk);
-        for (int i = 0; i < b.n_images; ++i) {
-            const int64_t b0 = b.row0[i] / kRowAlign, nb = pad_rows(b.n_rows[i]) / kRowAlign;
-            for (int64_t k = 0; k < nb; ++k)
-                valid[b0 + k] = static_cast<int32_t>(std::min<int64_t>(kRowAlign, std::max<int64_t>(0, b.n_rows[i] - k * kRowAlign)));
-        }
-        CU_TRY(c, b.d_valid.ensure(nblk * 4));
-        CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid.data(), nblk * 4, cudaMemcpyHostToDevice, s));
+    if (b.u8_valued && b.cols == 128) {
         CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
         CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
-        CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>(), b.padded_rows, b.d_valid.as<int32_t>(), b.d_norm2.as<int32_t>(),
+        CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>(), b.padded_rows, d_valid, b.d_norm2.as<int32_t>(),
                                      b.d_ckey.as<int32_t>(), s));
         c->stat_launches++;
-        CU_TRY(c, cudaStreamSynchronize(s));      // `valid` is a pageable temporary
     }
     return make_tmaps(c, b);
 }
@@ -222,7 +236,6 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
     const size_t row_bytes = static_cast<size_t>(cols) * esz;
     DevBuf& dst = depth == SFM_CV_32F ? b.d_f32 : b.d_u8;
     CU_TRY(c, dst.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * row_bytes)));
-    CU_TRY(c, cudaMemsetAsync(dst.p, 0, static_cast<size_t>(b.padded_rows) * row_bytes, s));
     // Caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pinned tensors) are
     // DMA'd directly; pageable ones are staged through two pinned buffers so that the H2D copy of one chunk
     // overlaps the host gather of the next.
@@ -238,8 +251,11 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
         const bool pinned = cudaPointerGetAttributes(&attr, rows[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) cudaGetLastError();
         if (pinned) {
-            CU_TRY(c, cudaMemcpy2DAsync(d_img, row_bytes, rows[i], step, row_bytes, static_cast<size_t>(n_rows[i]),
-                                        cudaMemcpyHostToDevice, s));
+            if (step == row_bytes)
+                CU_TRY(c, cudaMemcpyAsync(d_img, rows[i], static_cast<size_t>(n_rows[i]) * row_bytes, cudaMemcpyHostToDevice, s));
+            else
+                CU_TRY(c, cudaMemcpy2DAsync(d_img, row_bytes, rows[i], step, row_bytes, static_cast<size_t>(n_rows[i]),
+                                            cudaMemcpyHostToDevice, s));
             c->stat_h2d += static_cast<int64_t>(n_rows[i]) * static_cast<int64_t>(row_bytes);
             continue;
         }
@@ -442,6 +458,14 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
             if (rc != SFM_OK) return rc;
         }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 1], s));
+        if (eng == Engine::TC && o->k == 2 && !need_rev) {
+            RefineArgs ra;
+            ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
+            ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
+            ra.all_rows = 0; ra.ratio = o->ratio;
+            CU_TRY(c, launch_refine_second(ra, s));
+            c->stat_launches++;
+        }
         FilterArgs a;
         a.top2 = c->d_top2.as<Top2>(); a.rev = c->d_rev.as<Top2>(); a.pairs = d_pd + B.p0;
         a.out_prefix = d_outp + base; a.t_prefix = d_tp + base; a.n_pairs = np; a.staged_rows = B.staged_rows;
@@ -489,7 +513,10 @@ int collect_impl(sfm_ctx* c, sfm_result** out) {
             if (rc != SFM_OK) return rc;
             continue;
         }
-        sfm_result* r = new sfm_result();
+        sfm_result* r;
+        if (!c->result_pool.empty()) { r = c->result_pool.back(); c->result_pool.pop_back(); }
+        else r = new sfm_result();
+        r->owner = c;
         r->n_pairs = n;
         CU_TRY(c, r->offsets.ensure(static_cast<size_t>(n + 1) * 8));
         CU_TRY(c, r->dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n))));
@@ -541,6 +568,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     for (int k = 0; k < 2; ++k)
         if ((e = cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&c->meta_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&c->valid_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -567,6 +595,9 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->meta_ev) cudaEventDestroy(c->meta_ev);
+    if (c->valid_ev) cudaEventDestroy(c->valid_ev);
+    for (sfm_result* r : c->result_pool) { r->offsets.release(); r->matches.release(); r->dropped.release(); delete r; }
+    c->h_valid.release();
     for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -600,7 +631,6 @@ int sfm_bank_upload_device(sfm_ctx* c, int n_images, const void* dev_rows, const
     const size_t row_bytes = static_cast<size_t>(cols) * esz;
     DevBuf& dst = cv_depth == SFM_CV_32F ? b.d_f32 : b.d_u8;
     CU_TRY(c, dst.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * row_bytes)));
-    CU_TRY(c, cudaMemsetAsync(dst.p, 0, static_cast<size_t>(b.padded_rows) * row_bytes, c->stream));
     for (int i = 0; i < n_images; ++i) {
         if (n_rows[i] == 0) continue;
         CU_TRY(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst.p) + static_cast<size_t>(b.row0[i]) * row_bytes,
@@ -645,6 +675,11 @@ const sfm_dmatch* sfm_result_matches(const sfm_result* r) { return r ? r->matche
 const uint8_t* sfm_result_dropped(const sfm_result* r) { return r ? r->dropped.as<uint8_t>() : nullptr; }
 void sfm_result_free(sfm_result* r) {
     if (!r) return;
+    sfm_ctx* c = r->owner;
+    if (c) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (c->result_pool.size() < 4) { c->result_pool.push_back(r); return; }
+    }
     r->offsets.release(); r->matches.release(); r->dropped.release();
     delete r;
 }
@@ -702,9 +737,10 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     if (rc != SFM_OK) return rc;
     cudaStream_t s = c->stream;
     const int rpu = rows_per_unit(eng);
-    struct Meta { PairDesc pd; int64_t unit_prefix[2]; } meta;
+    struct Meta { PairDesc pd; int64_t unit_prefix[2]; int64_t out_prefix[2]; } meta;
     meta.pd.q_row0 = 0; meta.pd.nq = nq; meta.pd.t_row0 = static_cast<int32_t>(b.row0[1]); meta.pd.nt = nt; meta.pd.out_row0 = 0;
     meta.unit_prefix[0] = 0; meta.unit_prefix[1] = (nq + rpu - 1) / rpu;
+    meta.out_prefix[0] = 0; meta.out_prefix[1] = pad_rows(nq);
     CU_TRY(c, c->d_pairs.ensure(sizeof(Meta)));
     CU_TRY(c, cudaMemcpyAsync(c->d_pairs.p, &meta, sizeof(Meta), cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaStreamSynchronize(s));
@@ -713,6 +749,15 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     const int64_t* d_unit = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, unit_prefix));
     rc = launch_knn(c, b, eng, d_pd, d_unit, 1, meta.unit_prefix[1], c->d_top2.as<Top2>());
     if (rc != SFM_OK) return rc;
+    if (eng == Engine::TC && k == 2) {
+        RefineArgs ra;
+        ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd;
+        ra.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
+        ra.n_pairs = 1; ra.staged_rows = pad_rows(nq); ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
+        ra.all_rows = 1; ra.ratio = 0.0;
+        CU_TRY(c, launch_refine_second(ra, s));
+        c->stat_launches++;
+    }
     const size_t out_bytes = static_cast<size_t>(nq) * k * 4;
     CU_TRY(c, c->d_knn.ensure(2 * out_bytes));
     int32_t* d_idx = c->d_knn.as<int32_t>();
