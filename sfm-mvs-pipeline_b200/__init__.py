@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libsfmmatch.so")
 
 NORM_L2, NORM_HAMMING = 4, 6
 CV_8U, CV_32F = 0, 5
-ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT = 0, 1, 2
+ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT, ENGINE_TENSOR_IMAD = 0, 1, 2, 3
 MAX_ROWS = 1 << 18
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5
 

@@ -12,6 +12,14 @@ constexpr int kRowAlign = 256;
 // (max real key = 128*255^2*256 + 255 = 0x7F0100FF), still < 2^31.
 constexpr int32_t kSentinelKey = 0x7FFFFF00;
 
+// Value-only tcgen05 kernel (knn_l2_tcv.cu): every bank row carries 32 signed "norm digits" e_k so that one extra
+// u8 x s8 K-step against the constant weight row W = {255 x12, 1 x4, 255 x12, 1 x4} adds  -(||b||^2 >> 1)  to the
+// accumulator:  sum_k W_k e_k = -(||b||^2 >> 1).  Usable iff every ||b||^2 <= kExtMaxNorm2 (SIFT: ~2.6e5).
+constexpr int kExtBytes = 32;
+constexpr int32_t kExtMaxNorm2 = 1500000;
+// padded (invalid) train rows get all digits = -128: D = 0 - kExtPadValue, below every valid D (>= -750000)
+constexpr int32_t kExtPadValue = 24 * 255 * 128 + 8 * 128;
+
 // One image pair of a batch, device-resident.  left <-> query, right <-> train (Scene.h:47-51).
 struct PairDesc {
     int32_t q_row0;     // first bank row of the query (left) image, multiple of kRowAlign
@@ -149,6 +157,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_u8(int m, int n) {
     return (2u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
+}
+// same with a signed B operand (A = u8, B = s8)
+__host__ __device__ constexpr uint32_t umma_idesc_u8s8(int m, int n) {
+    return umma_idesc_u8(m, n) | (1u << 10);
+}
+// UMMA shared-memory descriptor: K-major operand with 32-byte rows, 32-byte swizzle; 8-row groups 256 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(256 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(6) << 61;                              // SWIZZLE_32B
+    return d;
 }
 
 }  // namespace sfm

@@ -25,12 +25,17 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
                                  const int32_t* norm2, const PairDesc* pairs, const int64_t* unit_prefix,
                                  int n_pairs, int64_t n_units, Top2* out, int sm_count, cudaStream_t s);
 
+// ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
+cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
+                                  const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
+                                  Top2* out, int sm_count, cudaStream_t s);
+
 // ---- post.cu
 cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols,
                                   const int32_t* valid_in_block, uint8_t* dst, int* not_integer_flag, cudaStream_t s);
 cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, const int32_t* valid_in_block, cudaStream_t s);
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* row_valid_end /*per 256-row block*/,
-                               int32_t* norm2, int32_t* ckey, cudaStream_t s);
+                               int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, cudaStream_t s);
 struct FilterParams {
     int norm;            // SFM_NORM_*
     int k;               // 1 or 2
@@ -65,6 +70,8 @@ struct RefineArgs {
     double ratio;
 };
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
+// value-only tcgen05 path: (chunk, D) pairs -> exact Top2 for rows that can pass the ratio test (see post.cu)
+cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s);
 // pass 1 (only with distinct): count how often each train row is the best match of a kept query row
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s);
 // pass 2: number of surviving matches per 256-row chunk

@@ -1,0 +1,283 @@
+// knn_l2_tcv.cu — "value-only" variant of the tcgen05 SIFT kernel: the throughput path of sfm_match_pairs.
+//
+// Same contraction, pipeline and warp roles as knn_l2_tc.cu (TMA -> smem ring -> tcgen05.mma.kind::i8 -> TMEM ->
+// tcgen05.ld epilogue), but the per-train-row constant is folded into the MMA instead of the epilogue: every bank
+// row carries 32 signed norm digits e (see common.cuh) and a fifth K-step (A = constant weight rows, u8;
+// B = digits, s8) adds -(|b|^2 >> 1), so the accumulator holds
+//        D = a.b - (|b_j|^2 >> 1)          and        |a - b_j|^2 = |a|^2 - 2 D + (|b_j|^2 & 1).
+// A larger D is a closer row, strictly (the parity bit only orders rows with equal D).  The epilogue therefore
+// needs no per-column constant at all: per 32-column chunk a VIMNMX3 tree takes the maximum of the raw accumulators
+// (1/2 ALU op per element, no IMAD, no shared-memory loads) and the running state is the top-3 of CHUNK maxima,
+// kept as (D, chunk).  Output per query row: the two best chunks and their D values, plus an "ambiguous" flag when
+// the third-best chunk ties the second (then rows outside the two reported chunks could still matter).
+// refine_value_kernel (post.cu) turns this into the exact cv::batchDistance answer: rows whose ratio test cannot
+// pass even with the bounds  d0^2 >= |a|^2 - 2 D1,  d1^2 <= |a|^2 - 2 D2 + 1  are rejected outright (~99.7 % of C3's
+// rows); for the rest the two chunks (64 train rows) are recomputed exactly with __dp4a, ambiguous rows by brute
+// force over the whole train image.  Everything is integer arithmetic -> bit-exact (tests/test_gpu_parity.py).
+//
+// Precondition (checked on the host): every |b|^2 of the bank <= kExtMaxNorm2.  Otherwise knn_l2_tc.cu is used.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sfm {
+
+namespace tcv {
+constexpr int BM = 128, BN = 256, KB = 128;
+constexpr int kBStages = 4, kAStages = 2, kAccStages = 2;
+constexpr int kABytes = BM * KB, kBBytes = BN * KB, kEBytes = BN * kExtBytes, kAExtBytes = BM * kExtBytes;
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int offB = 0;
+constexpr int offE = offB + kBStages * kBBytes;                   // digit tiles, one per B stage
+constexpr int offA = offE + kBStages * kEBytes;
+constexpr int offAExt = offA + kAStages * kABytes;                // constant weight rows
+constexpr int offMerge = offAExt + kAExtBytes;                    // [128][3] int64
+constexpr int offBar = offMerge + BM * 3 * 8;
+constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages;
+constexpr int offTmemPtr = offBar + kNumBars * 8;
+constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
+constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
+constexpr uint32_t kIdescExt = umma_idesc_u8s8(BM, BN);
+constexpr int64_t kEmpty = INT64_MIN;
+}  // namespace tcv
+
+struct UnitInfoV { PairDesc pd; int rb; int n_tiles; };
+
+__device__ __forceinline__ UnitInfoV decode_unit_v(const PairDesc* __restrict__ pairs, const int64_t* __restrict__ unit_prefix,
+                                                   int n_pairs, int64_t unit) {
+    UnitInfoV u;
+    const int p = find_segment(unit_prefix, n_pairs, unit);
+    u.pd = pairs[p];
+    u.rb = static_cast<int>(unit - unit_prefix[p]);
+    u.n_tiles = (u.pd.nt + tcv::BN - 1) / tcv::BN;
+    return u;
+}
+
+// running top-3 (descending) insert
+__device__ __forceinline__ void top3_max(int32_t k, int32_t& m1, int32_t& m2, int32_t& m3) {
+    const int32_t t = min(m1, k);
+    m1 = max(m1, k);
+    const int32_t u = min(m2, t);
+    m2 = max(m2, t);
+    m3 = max(m3, u);
+}
+__device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, int64_t& m3) {
+    const int64_t t = min(m1, k);
+    m1 = max(m1, k);
+    const int64_t u = min(m2, t);
+    m2 = max(m2, t);
+    m3 = max(m3, u);
+}
+
+__global__ void __launch_bounds__(tcv::kThreads, 1)
+knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
+                      const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out) {
+    using namespace tcv;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + offBar;
+    auto b_full = [&](int i) { return bar0 + 8u * i; };
+    auto b_empty = [&](int i) { return bar0 + 8u * (kBStages + i); };
+    auto a_full = [&](int i) { return bar0 + 8u * (2 * kBStages + i); };
+    auto a_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + kAStages + i); };
+    auto acc_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + i); };
+    auto acc_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + kAccStages + i); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + offTmemPtr);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_e);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(base + offTmemPtr, 512);
+        tmem_relinquish();
+    }
+    // constant weight operand: 128 identical rows {255 x12, 1 x4, 255 x12, 1 x4}; both 16-byte halves of a row are
+    // equal, so the 32-byte swizzle (which only swaps halves) leaves the image unchanged
+    for (int i = threadIdx.x; i < kAExtBytes / 4; i += kThreads) {
+        const int word = i & 3;                                     // word inside a 16-byte half
+        reinterpret_cast<uint32_t*>(base_ptr + offAExt)[i] = word < 3 ? 0xFFFFFFFFu : 0x01010101u;
+    }
+    fence_proxy_async();                                            // generic-proxy writes -> visible to the MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        uint32_t tile_iter = 0, unit_iter = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
+            if (u.n_tiles == 0) continue;
+            const int as = unit_iter % kAStages;
+            mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(a_full(as), kABytes);
+                tma_load_2d(base + offA + as * kABytes, &tmap_a, 0, u.pd.q_row0 + u.rb * BM, a_full(as));
+            }
+            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+                const int st = tile_iter % kBStages;
+                mbar_wait(b_empty(st), ((tile_iter / kBStages) & 1) ^ 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(b_full(st), kBBytes + kEBytes);
+                    tma_load_2d(base + offB + st * kBBytes, &tmap_b, 0, u.pd.t_row0 + t * BN, b_full(st));
+                    tma_load_2d(base + offE + st * kEBytes, &tmap_e, 0, u.pd.t_row0 + t * BN, b_full(st));
+                }
+                __syncwarp();
+            }
+            ++unit_iter;
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer (lane 0 issues)
+        uint32_t tile_iter = 0, unit_iter = 0;
+        const uint64_t aext = umma_desc_sw32(base + offAExt);
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
+            if (u.n_tiles == 0) continue;
+            const int as = unit_iter % kAStages;
+            mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
+            const uint64_t adesc = umma_desc_sw128(base + offA + as * kABytes);
+            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+                const int acc = tile_iter % kAccStages;
+                const int st = tile_iter % kBStages;
+                mbar_wait(acc_empty(acc), ((tile_iter / kAccStages) & 1) ^ 1);
+                mbar_wait(b_full(st), (tile_iter / kBStages) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t bdesc = umma_desc_sw128(base + offB + st * kBBytes);
+                    const uint64_t edesc = umma_desc_sw32(base + offE + st * kEBytes);
+                    const uint32_t d = tmem_base + acc * BN;
+#pragma unroll
+                    for (int k = 0; k < KB / 32; ++k)
+                        umma_i8(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                    umma_i8(d, aext, edesc, kIdescExt, 1);          // += -(|b|^2 >> 1)
+                    umma_commit(b_empty(st));
+                    umma_commit(acc_full(acc));
+                    if (t == u.n_tiles - 1) umma_commit(a_empty(as));
+                }
+                __syncwarp();
+            }
+            ++unit_iter;
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================================================================ epilogue: top-3 of chunk maxima per query row
+        const int group = (warp - kEpiWarp0) >> 2;         // 0: even tiles, 1: odd tiles
+        const int quarter = warp & 3;
+        const int row_in_unit = quarter * 32 + lane;
+        int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
+        uint32_t tile_iter = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
+            int64_t r1 = kEmpty, r2 = kEmpty, r3 = kEmpty;
+            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+                if ((tile_iter & 1) != static_cast<uint32_t>(group)) continue;
+                const int acc = tile_iter % kAccStages;
+                mbar_wait(acc_full(acc), (tile_iter / kAccStages) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+                int32_t m1 = INT32_MIN, m2 = INT32_MIN, m3 = INT32_MIN;
+                uint32_t v[2][32];
+                tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t (&cur)[32] = v[c & 1];
+                    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                                 : "+r"(cur[0]), "+r"(cur[1]), "+r"(cur[2]), "+r"(cur[3]), "+r"(cur[4]), "+r"(cur[5]),
+                                   "+r"(cur[6]), "+r"(cur[7]), "+r"(cur[8]), "+r"(cur[9]), "+r"(cur[10]), "+r"(cur[11]),
+                                   "+r"(cur[12]), "+r"(cur[13]), "+r"(cur[14]), "+r"(cur[15]), "+r"(cur[16]),
+                                   "+r"(cur[17]), "+r"(cur[18]), "+r"(cur[19]), "+r"(cur[20]), "+r"(cur[21]),
+                                   "+r"(cur[22]), "+r"(cur[23]), "+r"(cur[24]), "+r"(cur[25]), "+r"(cur[26]),
+                                   "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
+                                 :: "memory");
+                    if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    // balanced max3 tree over the raw accumulators: 32 -> 11 -> 4 -> 1
+                    int32_t a[11];
+#pragma unroll
+                    for (int i = 0; i < 10; ++i)
+                        a[i] = __vimax3_s32(static_cast<int32_t>(cur[3 * i]), static_cast<int32_t>(cur[3 * i + 1]),
+                                            static_cast<int32_t>(cur[3 * i + 2]));
+                    a[10] = max(static_cast<int32_t>(cur[30]), static_cast<int32_t>(cur[31]));
+                    const int32_t b0 = __vimax3_s32(a[0], a[1], a[2]), b1 = __vimax3_s32(a[3], a[4], a[5]);
+                    const int32_t b2 = __vimax3_s32(a[6], a[7], a[8]), b3 = max(a[9], a[10]);
+                    const int32_t cmax = max(__vimax3_s32(b0, b1, b2), b3);
+                    // |D| < 2^21: 3 spare bits carry the chunk id; equal D -> the lower chunk wins
+                    top3_max(cmax * 8 + (7 - c), m1, m2, m3);
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty(acc));
+                // fold into the 64-bit running state: (D, -global chunk)
+                const int32_t tk[3] = {m1, m2, m3};
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int32_t gch = t * (BN / 32) + (7 - (tk[i] & 7));
+                    const int64_t k64 = static_cast<int64_t>(tk[i] >> 3) * (1ll << 32) + (0x7FFFFFFF - gch);
+                    top3_max64(k64, r1, r2, r3);
+                }
+            }
+            if (group == 1) { merge[row_in_unit * 3] = r1; merge[row_in_unit * 3 + 1] = r2; merge[row_in_unit * 3 + 2] = r3; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (group == 0) {
+                top3_max64(merge[row_in_unit * 3], r1, r2, r3);
+                top3_max64(merge[row_in_unit * 3 + 1], r1, r2, r3);
+                top3_max64(merge[row_in_unit * 3 + 2], r1, r2, r3);
+                const int row = u.rb * BM + row_in_unit;
+                if (row < u.pd.nq) {
+                    // a chunk whose maximum is the padding value holds no valid train row
+                    const int32_t v1 = static_cast<int32_t>(r1 >> 32), v2 = static_cast<int32_t>(r2 >> 32);
+                    const int32_t v3 = static_cast<int32_t>(r3 >> 32);
+                    const bool has1 = r1 != kEmpty && v1 > -kExtPadValue;
+                    const bool has2 = r2 != kEmpty && v2 > -kExtPadValue;
+                    const bool has3 = r3 != kEmpty && v3 > -kExtPadValue;
+                    Top2 o;
+                    o.i0 = has1 ? 0x7FFFFFFF - static_cast<int32_t>(r1 & 0xFFFFFFFF) : -1;      // chunk of the best D
+                    o.i1 = has2 ? 0x7FFFFFFF - static_cast<int32_t>(r2 & 0xFFFFFFFF) : -1;      // second chunk
+                    if (has2 && has3 && v3 == v2) o.i1 |= 0x40000000;                           // ambiguous
+                    o.d0 = __int_as_float(v1);
+                    o.d1 = __int_as_float(v2);
+                    out[u.pd.out_row0 + row] = o;
+                }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
+                                  const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
+                                  Top2* out, int sm_count, cudaStream_t s) {
+    if (n_units == 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tcv::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
+    const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
+    const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e_host);
+    const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
+    knn2_l2_u8_tcv_kernel<<<grid, tcv::kThreads, tcv::kSmemBytes, s>>>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units,
+                                                                       out);
+    return cudaGetLastError();
+}
+
+}  // namespace sfm

@@ -64,10 +64,11 @@ cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, 
     return cudaGetLastError();
 }
 
-// one warp per 128-byte row
+// one warp per 128-byte row: |b|^2, the packed column key of the IMAD epilogue, and the norm digits of the
+// value-only epilogue (see common.cuh)
 __global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t padded_rows,
                                    const int32_t* __restrict__ valid_in_block, int32_t* __restrict__ norm2,
-                                   int32_t* __restrict__ ckey) {
+                                   int32_t* __restrict__ ckey, int8_t* __restrict__ ext, int* __restrict__ max_norm2) {
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= padded_rows) return;
@@ -75,21 +76,31 @@ __global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t pad
     uint32_t s = __dp4a(w, w, 0u);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int col = static_cast<int>(row & (kRowAlign - 1));
+    const bool valid = col < valid_in_block[row / kRowAlign];
     if (lane == 0) {
-        const int col = static_cast<int>(row & (kRowAlign - 1));
-        const bool valid = col < valid_in_block[row / kRowAlign];
         norm2[row] = static_cast<int32_t>(s);
         // key = (|b|^2 - 2ab) * 256 + col  ==  ckey - 512 * ab
         ckey[row] = valid ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col)) : (kSentinelKey | col);
+        if (valid) atomicMax(max_norm2, static_cast<int>(s));
     }
+    // digit of lane p: weight 255 at positions with (p & 15) < 12, weight 1 otherwise
+    int digit = 128;
+    if (valid && s <= static_cast<uint32_t>(kExtMaxNorm2)) {
+        const int g = static_cast<int>(s >> 1), q = g / 255, r = g - q * 255;
+        const int sub = lane & 15, half = lane >> 4;
+        if (sub < 12) digit = min(128, max(0, q - 128 * (half * 12 + sub)));
+        else          digit = min(128, max(0, r - 128 * (half * 4 + sub - 12)));
+    }
+    ext[row * kExtBytes + lane] = static_cast<int8_t>(-digit);
 }
 
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* valid_in_block,
-                               int32_t* norm2, int32_t* ckey, cudaStream_t s) {
+                               int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, cudaStream_t s) {
     if (padded_rows == 0) return cudaSuccess;
     const int64_t threads = padded_rows * 32;
     norms_ckeys_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(bank, padded_rows, valid_in_block,
-                                                                                     norm2, ckey);
+                                                                                     norm2, ckey, ext, max_norm2);
     return cudaGetLastError();
 }
 
@@ -241,11 +252,108 @@ __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
     if (changed) a.top2[srow] = t;
 }
 
+// ------------------------------------------------------------------------------------------------ refine (value-only)
+// Input: per query row the two best 32-row train chunks by D = ab - (|b|^2 >> 1) and their D values, as written by
+// knn2_l2_u8_tcv_kernel (i0 = chunk1, i1 = chunk2 | ambiguous << 30, d0/d1 = D1/D2 as int bits).
+// Output: the exact Top2 {idx0, idx1, d0^2, d1^2} for rows that can still pass the ratio test, i0 = -1 for the rest.
+//   bounds: d0^2 >= |a|^2 - 2 D1 and d1^2 <= |a|^2 - 2 D2 + 1  (the parity bit of |b|^2 is in [0,1]); sqrtf and the
+//   double product are monotonic, so  sqrtf(lo0) >= ratio * sqrtf(hi1)  implies the real test fails.
+// One warp per row that needs work: lane = train row of the chunk, 32 x __dp4a, lexicographic (d^2, idx) keys.
+__device__ __forceinline__ void warp_chunk_candidates(const uint8_t* __restrict__ bank, const int32_t* __restrict__ norm2,
+                                                      const uint4 (&q)[8], int na, int tr0, int ntr, int chunk, int lane,
+                                                      long long& a1, long long& a2) {
+    const int j = chunk * 32 + lane;
+    const uint4* tv = reinterpret_cast<const uint4*>(bank + (static_cast<size_t>(tr0) + j) * 128);
+    uint32_t dot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 y = __ldg(tv + i);
+        dot = __dp4a(q[i].x, y.x, dot); dot = __dp4a(q[i].y, y.y, dot);
+        dot = __dp4a(q[i].z, y.z, dot); dot = __dp4a(q[i].w, y.w, dot);
+    }
+    if (j < ntr) {
+        const int32_t d = na + norm2[tr0 + j] - 2 * static_cast<int32_t>(dot);
+        const long long key = (static_cast<long long>(d) << 32) | static_cast<unsigned>(j);
+        a2 = min(a2, max(a1, key));
+        a1 = min(a1, key);
+    }
+}
+
+__global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool need = false, valid = false;
+    Top2 t;
+    t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
+    int q_bank_row = 0, t_row0 = 0, nt = 0;
+    if (srow < a.staged_rows) {
+        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        const PairDesc pd = a.pairs[p];
+        const int row = static_cast<int>(srow - a.out_prefix[p]);
+        if (row < pd.nq) {
+            valid = true;
+            t = a.top2[srow];
+            q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
+            if (t.i0 >= 0) {
+                if (a.all_rows || t.i1 < 0 || (t.i1 & 0x40000000)) need = true;
+                else {
+                    const int na = a.norm2[q_bank_row];
+                    const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na - 2 * __float_as_int(t.d0))));   // parity can make it -1
+                    const float hi1 = __fsqrt_rn(static_cast<float>(na - 2 * __float_as_int(t.d1) + 1));
+                    need = static_cast<double>(lo0) < static_cast<double>(hi1) * a.ratio;
+                }
+            }
+        }
+    }
+    const float inf = __int_as_float(0x7f800000);
+    Top2 o;
+    o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
+        const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
+        const int ntr = __shfl_sync(0xffffffffu, nt, src);
+        const int c1 = __shfl_sync(0xffffffffu, t.i0, src);
+        const int c2raw = __shfl_sync(0xffffffffu, t.i1, src);
+        const int na = a.norm2[qrow];
+        uint4 q[8];
+        const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
+        long long a1 = LLONG_MAX, a2 = LLONG_MAX;
+        if (c2raw >= 0 && (c2raw & 0x40000000)) {
+            // ambiguous: a third chunk ties the second one -> exact brute force over the whole train image
+            for (int c = 0; c * 32 < ntr; ++c) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c, lane, a1, a2);
+        } else {
+            warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c1, lane, a1, a2);
+            if (c2raw >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c2raw, lane, a1, a2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+            a2 = min(max(a1, b1), min(a2, b2));
+            a1 = min(a1, b1);
+        }
+        if (lane == src) {
+            if (a1 != LLONG_MAX) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(a1 >> 32)); }
+            if (a2 != LLONG_MAX) { o.i1 = static_cast<int>(a2 & 0xFFFFFFFFll); o.d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
+        }
+    }
+    if (valid) a.top2[srow] = o;        // rows that cannot pass keep i0 = -1 (rejected)
+}
+
 static inline unsigned chunks_of(int64_t rows) { return static_cast<unsigned>((rows + 255) / 256); }
 
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
     refine_second_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    refine_value_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s) {

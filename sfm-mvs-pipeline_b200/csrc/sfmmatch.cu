@@ -68,10 +68,11 @@ struct Bank {
     std::vector<int32_t> n_rows;
     std::vector<int64_t> row0;
     int64_t padded_rows = 0;
-    DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid;
-    alignas(64) CUtensorMap tmap_a, tmap_b;
+    DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid, d_ext;
+    alignas(64) CUtensorMap tmap_a, tmap_b, tmap_e;
+    bool ext_ok = false;             // every |b|^2 <= kExtMaxNorm2: the value-only tcgen05 kernel may be used
     bool have_tmap = false;
-    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); }
+    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); }
 };
 
 struct RunState {                    // what collect() needs from the last enqueue
@@ -147,6 +148,13 @@ int make_tmaps(sfm_ctx* c, Bank& b) {
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(r));
+    const cuuint64_t dims_e[2] = {kExtBytes, static_cast<cuuint64_t>(b.padded_rows)};
+    const cuuint64_t strides_e[1] = {kExtBytes};
+    const cuuint32_t box_e[2] = {kExtBytes, 256};
+    r = c->encode(&b.tmap_e, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.d_ext.p, dims_e, strides_e, box_e, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(E) failed: " + std::to_string(r));
     b.have_tmap = true;
     return SFM_OK;
 }
@@ -193,37 +201,43 @@ int bank_finish(sfm_ctx* c, Bank& b) {
     CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid, static_cast<size_t>(nblk) * 4, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaEventRecord(c->valid_ev, s));
     const int32_t* d_valid = b.d_valid.as<int32_t>();
+    int* flags = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 16);      // [0] not-integer, [1] max |b|^2
+    CU_TRY(c, cudaMemsetAsync(flags, 0, 8, s));
+    bool maybe_u8 = b.depth == SFM_CV_8U;
+    if (b.depth == SFM_CV_32F && b.cols == 128) {
+        CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
+        CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>(), 128, static_cast<int>(b.padded_rows), 128, d_valid,
+                                        b.d_u8.as<uint8_t>(), flags, s));
+        c->stat_launches++;
+        maybe_u8 = true;
+    } else if (b.depth == SFM_CV_8U) {
+        CU_TRY(c, launch_zero_padding(b.d_u8.p, b.cols, b.padded_rows, d_valid, s));
+        c->stat_launches++;
+    }
+    if (maybe_u8 && b.cols == 128) {
+        CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
+        CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
+        CU_TRY(c, b.d_ext.ensure(static_cast<size_t>(b.padded_rows) * kExtBytes));
+        CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>(), b.padded_rows, d_valid, b.d_norm2.as<int32_t>(),
+                                     b.d_ckey.as<int32_t>(), b.d_ext.as<int8_t>(), flags + 1, s));
+        c->stat_launches++;
+    }
+    int* h = c->h_scalars.as<int>() + 8;
+    CU_TRY(c, cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    b.ext_ok = false;
     if (b.depth == SFM_CV_32F) {
-        b.have_f32 = true;
-        if (b.cols == 128) {
-            CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
-            int* flag = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 12);
-            CU_TRY(c, cudaMemsetAsync(flag, 0, 4, s));
-            CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>(), 128, static_cast<int>(b.padded_rows), 128, d_valid,
-                                            b.d_u8.as<uint8_t>(), flag, s));
-            c->stat_launches++;
-            int* h = c->h_scalars.as<int>() + 8;
-            CU_TRY(c, cudaMemcpyAsync(h, flag, 4, cudaMemcpyDeviceToHost, s));
-            CU_TRY(c, cudaStreamSynchronize(s));
-            // integer-valued (what cv::SIFT emits): match on the u8 copy; d_f32 stays allocated as upload staging
-            if (*h == 0) { b.u8_valued = true; b.have_f32 = false; }
-        }
-        if (b.have_f32) {
+        // integer-valued (what cv::SIFT emits): match on the u8 copy; d_f32 stays allocated as upload staging
+        if (b.cols == 128 && h[0] == 0) { b.u8_valued = true; b.have_f32 = false; }
+        else {
+            b.have_f32 = true;
             CU_TRY(c, launch_zero_padding(b.d_f32.p, b.cols * 4, b.padded_rows, d_valid, s));
             c->stat_launches++;
         }
     } else {
         b.u8_valued = true;
-        CU_TRY(c, launch_zero_padding(b.d_u8.p, b.cols, b.padded_rows, d_valid, s));
-        c->stat_launches++;
     }
-    if (b.u8_valued && b.cols == 128) {
-        CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
-        CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
-        CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>(), b.padded_rows, d_valid, b.d_norm2.as<int32_t>(),
-                                     b.d_ckey.as<int32_t>(), s));
-        c->stat_launches++;
-    }
+    if (b.u8_valued && b.cols == 128) b.ext_ok = h[1] <= kExtMaxNorm2;
     return make_tmaps(c, b);
 }
 
@@ -278,13 +292,14 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
 }
 
 // ------------------------------------------------------------------------------------------------ the stage
-enum class Engine { TC, DP4A, F32, POPC };
+enum class Engine { TC, TCV, DP4A, F32, POPC };
 
 int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out) {
     if (norm == SFM_NORM_HAMMING) {
         if (b.depth != SFM_CV_8U) return fail(c, SFM_ERR_INVALID, "NORM_HAMMING needs CV_8U descriptors");
         if (b.cols != 32) return fail(c, SFM_ERR_UNSUPPORTED, "Hamming kernel is built for 256-bit (32-byte) descriptors");
-        if (requested == SFM_ENGINE_TENSOR) return fail(c, SFM_ERR_UNSUPPORTED, "tensor-core Hamming engine not built yet");
+        if (requested == SFM_ENGINE_TENSOR || requested == SFM_ENGINE_TENSOR_IMAD)
+            return fail(c, SFM_ERR_UNSUPPORTED, "tensor-core Hamming engine not built yet");
         *out = Engine::POPC;
         return SFM_OK;
     }
@@ -294,7 +309,8 @@ int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out)
         return SFM_OK;
     }
     if (!b.have_f32) return fail(c, SFM_ERR_UNSUPPORTED, "NORM_L2 on CV_8U data needs 128-byte descriptors");
-    if (requested == SFM_ENGINE_TENSOR) return fail(c, SFM_ERR_UNSUPPORTED, "tensor engine needs u8-valued 128-d descriptors");
+    if (requested == SFM_ENGINE_TENSOR || requested == SFM_ENGINE_TENSOR_IMAD)
+        return fail(c, SFM_ERR_UNSUPPORTED, "tensor engine needs u8-valued 128-d descriptors");
     if (b.cols > 512) return fail(c, SFM_ERR_UNSUPPORTED, "fp32 L2 kernel supports up to 512 columns");
     *out = Engine::F32;
     return SFM_OK;
@@ -308,6 +324,10 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
         case Engine::TC:
             CU_TRY(c, launch_knn2_l2_u8_tc(&b.tmap_a, &b.tmap_b, b.d_ckey.as<int32_t>(), b.d_norm2.as<int32_t>(), d_pairs,
                                            d_unit_prefix, n_pairs, n_units, out, c->sm_count, s));
+            break;
+        case Engine::TCV:
+            CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
+                                            c->sm_count, s));
             break;
         case Engine::DP4A:
             CU_TRY(c, launch_knn2_l2_u8_dp4a(b.d_u8.as<uint8_t>(), b.d_norm2.as<int32_t>(), d_pairs, d_unit_prefix, n_pairs,
@@ -323,7 +343,9 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
     return SFM_OK;
 }
 
-int rows_per_unit(Engine e) { return e == Engine::F32 ? kF32RowsPerUnit : (e == Engine::TC ? kTcRowsPerUnit : kSimtRowsPerUnit); }
+int rows_per_unit(Engine e) {
+    return e == Engine::F32 ? kF32RowsPerUnit : ((e == Engine::TC || e == Engine::TCV) ? kTcRowsPerUnit : kSimtRowsPerUnit);
+}
 
 int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o) {
     Bank& b = c->bank;
@@ -335,6 +357,8 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
     Engine eng;
     int rc = pick_engine(c, b, o->norm, o->engine, &eng);
     if (rc != SFM_OK) return rc;
+    // ratio-test runs on data with SIFT-sized norms take the value-only tcgen05 kernel (knn_l2_tcv.cu)
+    if (eng == Engine::TC && o->engine != SFM_ENGINE_TENSOR_IMAD && o->k == 2 && !o->cross_check && b.ext_ok) eng = Engine::TCV;
     for (int64_t p = 0; p < n_pairs; ++p) {
         const int l = pairs[2 * p], r = pairs[2 * p + 1];
         if (l < 0 || r < 0 || l >= b.n_images || r >= b.n_images) return fail(c, SFM_ERR_INVALID, "pair index out of range");
@@ -458,12 +482,13 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
             if (rc != SFM_OK) return rc;
         }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 1], s));
-        if (eng == Engine::TC && o->k == 2 && !need_rev) {
+        if ((eng == Engine::TC || eng == Engine::TCV) && o->k == 2 && !need_rev) {
             RefineArgs ra;
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
             ra.all_rows = 0; ra.ratio = o->ratio;
-            CU_TRY(c, launch_refine_second(ra, s));
+            if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
+            else CU_TRY(c, launch_refine_second(ra, s));
             c->stat_launches++;
         }
         FilterArgs a;

@@ -30,7 +30,8 @@ def _same_knn(idx, dist, g_idx, g_dist):
 
 
 def _engines(sfm):
-    return [("tensor", sfm.ENGINE_TENSOR), ("simt", sfm.ENGINE_SIMT)]
+    # "tensor" = tcgen05 (value-only kernel where allowed), "tensor_imad" = tcgen05 with the packed-key epilogue
+    return [("tensor", sfm.ENGINE_TENSOR), ("tensor_imad", sfm.ENGINE_TENSOR_IMAD), ("simt", sfm.ENGINE_SIMT)]
 
 
 # ------------------------------------------------------------------ operator level: knnMatch
@@ -131,7 +132,7 @@ def test_strided_rows_like_cv_mat_step(sfm, matcher, insel_sift):
 
 
 # ------------------------------------------------------------------ plugin level: match_pairs
-@pytest.mark.parametrize("eng", ["tensor", "simt"])
+@pytest.mark.parametrize("eng", ["tensor", "tensor_imad", "simt"])
 def test_insel_sift_match_pairs_c1(sfm, matcher, insel_sift, eng):
     """BASELINE config C1: insel SIFT, grid pairing (seq,row) in {(2,3),(3,3),(2,1)}."""
     bank = [insel_sift[f"desc{i}"].astype(np.float32) for i in range(3)]
@@ -165,7 +166,7 @@ def test_synthetic_bank_all_pairs_vs_oracle(sfm, matcher):
     pairs = sfm.select_pairs(len(bank), 0, 0)
     matcher.upload_bank(bank)
     exp = orc.match_pairs(bank, pairs, NORM_L2)
-    for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+    for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_TENSOR_IMAD, sfm.ENGINE_SIMT):
         res = matcher.match_pairs(pairs, NORM_L2, engine=eng)
         assert len(res) == len(pairs)
         for p in range(len(pairs)):
@@ -183,6 +184,42 @@ def test_synthetic_bank_all_pairs_vs_oracle(sfm, matcher):
     for p in range(3):
         idx, dist = orc.knn2_l2(bank[pairs[p][0]], bank[pairs[p][1]])
         assert orc.dmatch_equal(res[p], orc.match_k1(idx, dist))
+
+
+def test_value_only_kernel_ties_and_fallback(sfm, matcher):
+    """The value-only tcgen05 kernel orders rows by D = ab - (|b|^2 >> 1); exact ties in D (duplicated rows, zero
+    rows, several chunks with the same maximum) must be resolved exactly by the refine pass, and banks whose norms
+    exceed the digit range must fall back to the packed-key kernel.  Bit-exact against the oracle either way."""
+    adv = workloads.adversarial_sift()
+    rng = np.random.default_rng(11)
+    base = adv["base"]
+    # many chunks containing the same rows: every chunk maximum ties -> 'ambiguous' brute-force path
+    tiled = np.concatenate([base[:40]] * 12 + [np.zeros((5, 128), np.uint8)] + [base[:33]] * 3)
+    near = np.clip(base.astype(np.int32) + rng.integers(-1, 2, size=base.shape), 0, 255).astype(np.uint8)
+    bank = [base, tiled, near, adv["dup"], adv["zeros"], adv["one"], adv["two"], adv["n129"]]
+    pairs = sfm.select_pairs(len(bank), 0, 0)
+    pairs = np.concatenate([pairs, pairs[:, ::-1]])            # both directions
+    matcher.upload_bank(bank)
+    exp = orc.match_pairs(bank, pairs, NORM_L2, ratio=0.95)
+    for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_TENSOR_IMAD):
+        res = matcher.match_pairs(pairs, NORM_L2, ratio=0.95, engine=eng)
+        for p in range(len(pairs)):
+            assert orc.dmatch_equal(res[p], exp[p]), (eng, pairs[p].tolist())
+    # ratio 1.0 / 0.0 edge cases of the provisional bound
+    for ratio in (1.0, 0.0, 0.3):
+        exp = orc.match_pairs(bank, pairs[:10], NORM_L2, ratio=ratio)
+        res = matcher.match_pairs(pairs[:10], NORM_L2, ratio=ratio)
+        for p in range(10):
+            assert orc.dmatch_equal(res[p], exp[p]), (ratio, pairs[p].tolist())
+    # large norms (|b|^2 up to 128*255^2): digit range exceeded -> packed-key kernel, still exact
+    big = [rng.integers(0, 256, size=(300, 128), dtype=np.uint8), rng.integers(0, 256, size=(257, 128), dtype=np.uint8),
+           adv["sat"]]
+    bp = sfm.select_pairs(3, 0, 0)
+    matcher.upload_bank(big)
+    exp = orc.match_pairs(big, bp, NORM_L2, ratio=0.99)
+    res = matcher.match_pairs(bp, NORM_L2, ratio=0.99)
+    for p in range(len(bp)):
+        assert orc.dmatch_equal(res[p], exp[p])
 
 
 def test_cross_check_vs_cv2_golden(sfm, matcher, insel_sift, synthetic_cv2):
