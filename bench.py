@@ -294,7 +294,7 @@ def run_ours(a):
         achieved = ops_per_step_rank * a.steps / (knn_ms / 1e3) / 1e12 if knn_ms > 0 else None
         peak_i8 = 2.0 * bf16_sust
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "knn_tc_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "knn_tcv_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         out = {
@@ -303,7 +303,7 @@ def run_ours(a):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(a), "pairs": int(len(pairs)), "parallelism": f"pair-list x{world}",
                        "l2": "inputs larger than L2 (bank 200 MiB + 512 MiB top-2 staging per batch vs 126 MB L2); no flush",
-                       "engine": "tcgen05 kind::i8 + fused top-2 epilogue", "matches_per_step": total_matches,
+                       "engine": "tcgen05 kind::i8, value-only fused top-k epilogue (knn2_l2_u8_tcv_kernel) + exact refine", "matches_per_step": total_matches,
                        "matches_device_run": int(result.offsets[-1])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": float(t.item()), "host_buffers": "pinned CV_32F descriptors, as the reference holds them"},
@@ -311,7 +311,7 @@ def run_ours(a):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_i8, "unit": "TFLOP/s",
                          "frac": (achieved / peak_i8) if achieved else None, "traffic": traffic,
-                         "kernel": "knn2_l2_u8_tc_kernel", "launches": knn_launches,
+                         "kernel": "knn2_l2_u8_tcv_kernel", "launches": knn_launches,
                          "avg_launch_ms": knn_ms / max(1, knn_launches),
                          "algorithmic": "2*Nq*Nt*128 op per pair (SURVEY 8d) x pairs per launch",
                          "peak_source": f"{src}: 2 x bf16_tflops_sustained ({bf16_sust}) for kind::i8",

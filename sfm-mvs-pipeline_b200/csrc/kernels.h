@@ -28,7 +28,7 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
 // ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int sm_count, cudaStream_t s);
+                                  Top2* out, int sm_count, int groups, cudaStream_t s);
 
 // ---- post.cu
 cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols,

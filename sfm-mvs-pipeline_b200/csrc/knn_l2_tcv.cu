@@ -7,9 +7,10 @@
 //        D = a.b - (|b_j|^2 >> 1)          and        |a - b_j|^2 = |a|^2 - 2 D + (|b_j|^2 & 1).
 // A larger D is a closer row, strictly (the parity bit only orders rows with equal D).  The epilogue therefore
 // needs no per-column constant at all: per 32-column chunk a VIMNMX3 tree takes the maximum of the raw accumulators
-// (1/2 ALU op per element, no IMAD, no shared-memory loads) and the running state is the top-3 of CHUNK maxima,
-// kept as (D, chunk).  Output per query row: the two best chunks and their D values, plus an "ambiguous" flag when
-// the third-best chunk ties the second (then rows outside the two reported chunks could still matter).
+// (1/2 ALU op per element, no IMAD, no shared-memory loads) and the running state is the top-4 of CHUNK maxima,
+// kept as (D, chunk).  The two nearest rows always lie in chunks whose maximum is >= the second-best chunk maximum,
+// so the output per query row is: the two best chunks and their D values, a third chunk if it ties the second, and
+// an "ambiguous" flag if a fourth ties too (probability ~1e-7 per row: brute force in the refine pass).
 // refine_value_kernel (post.cu) turns this into the exact cv::batchDistance answer: rows whose ratio test cannot
 // pass even with the bounds  d0^2 >= |a|^2 - 2 D1,  d1^2 <= |a|^2 - 2 D2 + 1  are rejected outright (~99.7 % of C3's
 // rows); for the rest the two chunks (64 train rows) are recomputed exactly with __dp4a, ambiguous rows by brute
@@ -27,14 +28,16 @@ namespace tcv {
 constexpr int BM = 128, BN = 256, KB = 128;
 constexpr int kBStages = 4, kAStages = 2, kAccStages = 2;
 constexpr int kABytes = BM * KB, kBBytes = BN * KB, kEBytes = BN * kExtBytes, kAExtBytes = BM * kExtBytes;
-constexpr int kThreads = 384;
+
 constexpr int kEpiWarp0 = 4;
+constexpr int32_t kValueBias = kExtPadValue;                      // D + bias >= 0, < 2^22
+constexpr int kSeqBits = 9;                                       // chunks one epilogue warp visits per unit <= 512
 constexpr int offB = 0;
 constexpr int offE = offB + kBStages * kBBytes;                   // digit tiles, one per B stage
 constexpr int offA = offE + kBStages * kEBytes;
 constexpr int offAExt = offA + kAStages * kABytes;                // constant weight rows
-constexpr int offMerge = offAExt + kAExtBytes;                    // [128][3] int64
-constexpr int offBar = offMerge + BM * 3 * 8;
+constexpr int offMerge = offAExt + kAExtBytes;                    // [3 groups][128][4] int64
+constexpr int offBar = offMerge + 3 * BM * 4 * 8;
 constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages;
 constexpr int offTmemPtr = offBar + kNumBars * 8;
 constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
@@ -63,6 +66,25 @@ __device__ __forceinline__ void top3_max(int32_t k, int32_t& m1, int32_t& m2, in
     m2 = max(m2, t);
     m3 = max(m3, u);
 }
+// running top-4 (descending) insert, 7 ops
+__device__ __forceinline__ void top4_max(int32_t k, int32_t& m1, int32_t& m2, int32_t& m3, int32_t& m4) {
+    const int32_t t = min(m1, k);
+    m1 = max(m1, k);
+    const int32_t u = min(m2, t);
+    m2 = max(m2, t);
+    const int32_t w = min(m3, u);
+    m3 = max(m3, u);
+    m4 = max(m4, w);
+}
+__device__ __forceinline__ void top4_max64(int64_t k, int64_t& m1, int64_t& m2, int64_t& m3, int64_t& m4) {
+    const int64_t t = min(m1, k);
+    m1 = max(m1, k);
+    const int64_t u = min(m2, t);
+    m2 = max(m2, t);
+    const int64_t w = min(m3, u);
+    m3 = max(m3, u);
+    m4 = max(m4, w);
+}
 __device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, int64_t& m3) {
     const int64_t t = min(m1, k);
     m1 = max(m1, k);
@@ -71,11 +93,16 @@ __device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, 
     m3 = max(m3, u);
 }
 
-__global__ void __launch_bounds__(tcv::kThreads, 1)
+// kGroups epilogue groups of 4 warps: 2 = (tile parity), 4 = (tile parity) x (column half)
+template <int kGroups>
+__global__ void __launch_bounds__(128 + 128 * kGroups, 1)
 knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
                       const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out) {
     using namespace tcv;
+    constexpr int kThreads = 128 + 128 * kGroups;
+    constexpr int kHalves = kGroups / 2;                            // column splits of a tile
+    constexpr int kChunksPerVisit = BN / 32 / kHalves;              // 32-column chunks one warp reads per tile
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -98,7 +125,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 128); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 128 * kHalves); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -174,26 +201,32 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             ++unit_iter;
         }
     } else if (warp >= kEpiWarp0) {
-        // ================================================================ epilogue: top-3 of chunk maxima per query row
-        const int group = (warp - kEpiWarp0) >> 2;         // 0: even tiles, 1: odd tiles
+        // ================================================================ epilogue: top-4 of chunk maxima per query row
+        // 16 warps = 4 groups; group g works on the tiles of parity (g & 1) and on the column half (g >> 1), so four
+        // tcgen05.ld are in flight per SM sub-partition (the loads are latency- not bandwidth-limited).
+        // Running state for the WHOLE unit in 32-bit keys:  key = (D + bias) << 9 | (511 - seq), seq = running number
+        // of the chunk in this warp's visiting order (ascending train rows) -> equal D keeps the earlier chunk.
+        const int group = (warp - kEpiWarp0) >> 2;
+        const int parity = group & 1, half = group >> 1;
         const int quarter = warp & 3;
         const int row_in_unit = quarter * 32 + lane;
         int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
         uint32_t tile_iter = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
-            int64_t r1 = kEmpty, r2 = kEmpty, r3 = kEmpty;
+            int32_t m1 = -1, m2 = -1, m3 = -1, m4 = -1;
+            const int t_first = static_cast<int>((parity - tile_iter) & 1u);     // first tile of this unit we own
+            int seq = 0;
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
-                if ((tile_iter & 1) != static_cast<uint32_t>(group)) continue;
+                if ((tile_iter & 1) != static_cast<uint32_t>(parity)) continue;
                 const int acc = tile_iter % kAccStages;
                 mbar_wait(acc_full(acc), (tile_iter / kAccStages) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-                int32_t m1 = INT32_MIN, m2 = INT32_MIN, m3 = INT32_MIN;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / kHalves);
                 uint32_t v[2][32];
                 tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < kChunksPerVisit; ++c) {
                     uint32_t (&cur)[32] = v[c & 1];
                     asm volatile("tcgen05.wait::ld.sync.aligned;"
                                  : "+r"(cur[0]), "+r"(cur[1]), "+r"(cur[2]), "+r"(cur[3]), "+r"(cur[4]), "+r"(cur[5]),
@@ -203,7 +236,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                    "+r"(cur[22]), "+r"(cur[23]), "+r"(cur[24]), "+r"(cur[25]), "+r"(cur[26]),
                                    "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
                                  :: "memory");
-                    if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (c + 1 < kChunksPerVisit) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
                     // balanced max3 tree over the raw accumulators: 32 -> 11 -> 4 -> 1
                     int32_t a[11];
 #pragma unroll
@@ -214,44 +247,57 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     const int32_t b0 = __vimax3_s32(a[0], a[1], a[2]), b1 = __vimax3_s32(a[3], a[4], a[5]);
                     const int32_t b2 = __vimax3_s32(a[6], a[7], a[8]), b3 = max(a[9], a[10]);
                     const int32_t cmax = max(__vimax3_s32(b0, b1, b2), b3);
-                    // |D| < 2^21: 3 spare bits carry the chunk id; equal D -> the lower chunk wins
-                    top3_max(cmax * 8 + (7 - c), m1, m2, m3);
+                    top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - (seq + c)), m1, m2, m3, m4);
                 }
+                seq += kChunksPerVisit;
                 tc_fence_before();
                 mbar_arrive(acc_empty(acc));
-                // fold into the 64-bit running state: (D, -global chunk)
-                const int32_t tk[3] = {m1, m2, m3};
+            }
+            // ---- unit end: to (D + bias, -global chunk) 64-bit keys, merge the four groups, write the candidates
+            int64_t r[4];
+            {
+                const int32_t mk[4] = {m1, m2, m3, m4};
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int32_t gch = t * (BN / 32) + (7 - (tk[i] & 7));
-                    const int64_t k64 = static_cast<int64_t>(tk[i] >> 3) * (1ll << 32) + (0x7FFFFFFF - gch);
-                    top3_max64(k64, r1, r2, r3);
+                for (int i = 0; i < 4; ++i) {
+                    if (mk[i] < 0) { r[i] = kEmpty; continue; }
+                    const int sq = 511 - (mk[i] & 511);
+                    const int gch = (t_first + 2 * (sq / kChunksPerVisit)) * (BN / 32) + half * kChunksPerVisit + (sq % kChunksPerVisit);
+                    r[i] = static_cast<int64_t>(mk[i] >> kSeqBits) * (1ll << 32) + (0x7FFFFFFF - gch);
                 }
             }
-            if (group == 1) { merge[row_in_unit * 3] = r1; merge[row_in_unit * 3 + 1] = r2; merge[row_in_unit * 3 + 2] = r3; }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (group != 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) merge[((group - 1) * BM + row_in_unit) * 4 + i] = r[i];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * kGroups) : "memory");
             if (group == 0) {
-                top3_max64(merge[row_in_unit * 3], r1, r2, r3);
-                top3_max64(merge[row_in_unit * 3 + 1], r1, r2, r3);
-                top3_max64(merge[row_in_unit * 3 + 2], r1, r2, r3);
+                for (int g = 0; g < kGroups - 1; ++g)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) top4_max64(merge[(g * BM + row_in_unit) * 4 + i], r[0], r[1], r[2], r[3]);
                 const int row = u.rb * BM + row_in_unit;
                 if (row < u.pd.nq) {
-                    // a chunk whose maximum is the padding value holds no valid train row
-                    const int32_t v1 = static_cast<int32_t>(r1 >> 32), v2 = static_cast<int32_t>(r2 >> 32);
-                    const int32_t v3 = static_cast<int32_t>(r3 >> 32);
-                    const bool has1 = r1 != kEmpty && v1 > -kExtPadValue;
-                    const bool has2 = r2 != kEmpty && v2 > -kExtPadValue;
-                    const bool has3 = r3 != kEmpty && v3 > -kExtPadValue;
+                    // value part 0 (D == -bias) is a chunk of padding rows only
+                    int32_t vv[4], ch[4];
+                    bool has[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        vv[i] = static_cast<int32_t>(r[i] >> 32);
+                        ch[i] = 0x7FFFFFFF - static_cast<int32_t>(r[i] & 0xFFFFFFFF);
+                        has[i] = r[i] != kEmpty && vv[i] > 0;
+                    }
                     Top2 o;
-                    o.i0 = has1 ? 0x7FFFFFFF - static_cast<int32_t>(r1 & 0xFFFFFFFF) : -1;      // chunk of the best D
-                    o.i1 = has2 ? 0x7FFFFFFF - static_cast<int32_t>(r2 & 0xFFFFFFFF) : -1;      // second chunk
-                    if (has2 && has3 && v3 == v2) o.i1 |= 0x40000000;                           // ambiguous
-                    o.d0 = __int_as_float(v1);
-                    o.d1 = __int_as_float(v2);
+                    o.i0 = has[0] ? ch[0] : -1;                                          // chunk of the best D
+                    o.i1 = has[1] ? ch[1] : -1;                                          // second chunk
+                    if (has[1] && has[2] && vv[2] == vv[1]) {
+                        o.i0 |= (ch[2] + 1) << 16;                                       // a third chunk ties the second
+                        if (has[3] && vv[3] == vv[1]) o.i1 |= 0x40000000;                // and a fourth: ambiguous
+                    }
+                    o.d0 = __int_as_float(vv[0] - kValueBias);
+                    o.d1 = __int_as_float(vv[1] - kValueBias);
                     out[u.pd.out_row0 + row] = o;
                 }
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(128 * kGroups) : "memory");
         }
     }
 
@@ -260,24 +306,33 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
-                                  const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int sm_count, cudaStream_t s) {
-    if (n_units == 0) return cudaSuccess;
+template <int kGroups>
+static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
+                              const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int grid, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tcv::kSmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    knn2_l2_u8_tcv_kernel<kGroups><<<grid, 128 + 128 * kGroups, tcv::kSmemBytes, s>>>(ta, tb, te, pairs, unit_prefix, n_pairs,
+                                                                                      n_units, out);
+    return cudaGetLastError();
+}
+
+// groups: 2 or 4 epilogue groups.  The 32-bit running keys number at most 512 chunks per epilogue warp and unit:
+// train images up to 32768 rows with 2 groups, 65536 with 4.
+cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
+                                  const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
+                                  Top2* out, int sm_count, int groups, cudaStream_t s) {
+    if (n_units == 0) return cudaSuccess;
     const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
     const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e_host);
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
-    knn2_l2_u8_tcv_kernel<<<grid, tcv::kThreads, tcv::kSmemBytes, s>>>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units,
-                                                                       out);
-    return cudaGetLastError();
+    if (groups == 2) return launch_tcv<2>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
+    return launch_tcv<4>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
 }
 
 }  // namespace sfm

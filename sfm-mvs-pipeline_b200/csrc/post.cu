@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
 
 // ------------------------------------------------------------------------------------------------ refine (value-only)
 // Input: per query row the two best 32-row train chunks by D = ab - (|b|^2 >> 1) and their D values, as written by
-// knn2_l2_u8_tcv_kernel (i0 = chunk1, i1 = chunk2 | ambiguous << 30, d0/d1 = D1/D2 as int bits).
+// knn2_l2_u8_tcv_kernel (i0 = chunk1 | (chunk3 + 1) << 16, i1 = chunk2 | ambiguous << 30, d0/d1 = D1/D2 as int bits;
+// chunk3 is present when a third chunk's maximum ties the second, ambiguous when a fourth does too).
 // Output: the exact Top2 {idx0, idx1, d0^2, d1^2} for rows that can still pass the ratio test, i0 = -1 for the rest.
 //   bounds: d0^2 >= |a|^2 - 2 D1 and d1^2 <= |a|^2 - 2 D2 + 1  (the parity bit of |b|^2 is in [0,1]); sqrtf and the
 //   double product are monotonic, so  sqrtf(lo0) >= ratio * sqrtf(hi1)  implies the real test fails.
@@ -315,8 +316,9 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
         const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
         const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
         const int ntr = __shfl_sync(0xffffffffu, nt, src);
-        const int c1 = __shfl_sync(0xffffffffu, t.i0, src);
+        const int c1raw = __shfl_sync(0xffffffffu, t.i0, src);
         const int c2raw = __shfl_sync(0xffffffffu, t.i1, src);
+        const int c1 = c1raw & 0xFFFF, c3 = (c1raw >> 16) - 1;      // c3 >= 0: a third chunk ties the second
         const int na = a.norm2[qrow];
         uint4 q[8];
         const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
         } else {
             warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c1, lane, a1, a2);
             if (c2raw >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c2raw, lane, a1, a2);
+            if (c3 >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c3, lane, a1, a2);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
