@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--images", type=int, default=200, help="images in the synthetic bank (C3: 200)")
     ap.add_argument("--rows", type=int, default=8192, help="descriptors per image (C3: 8192)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-pairs", type=int, default=24)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

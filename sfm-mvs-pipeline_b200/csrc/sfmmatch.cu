@@ -399,23 +399,31 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
     const int64_t nb = static_cast<int64_t>(batches.size());
 
     // ---- host metadata for the whole list, one H2D
-    //   PairDesc[n_pairs] | rev PairDesc[n_pairs] | unit_prefix[n_pairs+nb] | rev_unit_prefix[..] | out_prefix[..] | t_prefix[..]
+    //   PairDesc[n] (input order: filters) | PairDesc[n] (processing order: knn) | rev PairDesc[n] (processing order)
+    //   | unit_prefix[n+nb] | rev_unit_prefix[..] | out_prefix[..] | t_prefix[..]
+    // Processing order: inside a batch the pairs are walked in 8 x 8 image blocks, so that the ~16 descriptor
+    // sets a block touches stay L2-resident (the input order of an all-pairs list re-reads every train image
+    // from HBM for every pair).  Results still land at the staging rows of the INPUT order.
     const size_t npre = static_cast<size_t>(n_pairs + nb);
     const size_t bytes_pd = sizeof(PairDesc) * static_cast<size_t>(n_pairs);
     const size_t bytes_pre = sizeof(int64_t) * npre;
+    const size_t bytes_meta = 3 * bytes_pd + 4 * bytes_pre;
     CU_TRY(c, cudaEventSynchronize(c->meta_ev));
-    CU_TRY(c, c->h_meta.ensure(std::max<size_t>(64, 2 * bytes_pd + 4 * bytes_pre)));
+    CU_TRY(c, c->h_meta.ensure(std::max<size_t>(64, bytes_meta)));
     PairDesc* h_pd = c->h_meta.as<PairDesc>();
-    PairDesc* h_rpd = h_pd + n_pairs;
+    PairDesc* h_ppd = h_pd + n_pairs;
+    PairDesc* h_rpd = h_ppd + n_pairs;
     int64_t* h_unit = reinterpret_cast<int64_t*>(h_rpd + n_pairs);
     int64_t* h_runit = h_unit + npre;
     int64_t* h_out = h_runit + npre;
     int64_t* h_tp = h_out + npre;
     int64_t max_staged = 0, max_t = 0, max_chunks = 0, total_q = 0;
+    std::vector<int64_t> order;
     for (int64_t bi = 0; bi < nb; ++bi) {
         Batch& B = batches[bi];
-        int64_t units = 0, runits = 0, orow = 0, trow = 0;
+        int64_t orow = 0, trow = 0;
         const int64_t base = B.p0 + bi;      // prefix arrays carry one extra entry per batch
+        const int64_t np = B.p1 - B.p0;
         for (int64_t p = B.p0; p < B.p1; ++p) {
             const int l = pairs[2 * p], r = pairs[2 * p + 1];
             PairDesc d;
@@ -423,32 +431,46 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
             d.t_row0 = static_cast<int32_t>(b.row0[r]); d.nt = b.n_rows[r];
             d.out_row0 = orow;
             h_pd[p] = d;
-            PairDesc rd;                      // roles swapped: train rows query the left image
-            rd.q_row0 = d.t_row0; rd.nq = d.nt; rd.t_row0 = d.q_row0; rd.nt = d.nq; rd.out_row0 = trow;
-            h_rpd[p] = rd;
             const int64_t k = p - B.p0;
-            h_unit[base + k] = units; h_runit[base + k] = runits; h_out[base + k] = orow; h_tp[base + k] = trow;
-            units += (d.nq + rpu - 1) / rpu;
-            runits += (d.nt + rpu - 1) / rpu;
+            h_out[base + k] = orow; h_tp[base + k] = trow;
             orow += pad_rows(d.nq);
             trow += pad_rows(d.nt);
             total_q += d.nq;
         }
-        const int64_t k = B.p1 - B.p0;
-        h_unit[base + k] = units; h_runit[base + k] = runits; h_out[base + k] = orow; h_tp[base + k] = trow;
+        h_out[base + np] = orow; h_tp[base + np] = trow;
+        order.resize(np);
+        for (int64_t k = 0; k < np; ++k) order[k] = B.p0 + k;
+        std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+            const int lx = pairs[2 * x] >> 3, rx = pairs[2 * x + 1] >> 3, ly = pairs[2 * y] >> 3, ry = pairs[2 * y + 1] >> 3;
+            return lx != ly ? lx < ly : rx < ry;
+        });
+        int64_t units = 0, runits = 0;
+        for (int64_t k = 0; k < np; ++k) {
+            const PairDesc& d = h_pd[order[k]];
+            h_ppd[B.p0 + k] = d;
+            PairDesc rd;                      // roles swapped: train rows query the left image
+            rd.q_row0 = d.t_row0; rd.nq = d.nt; rd.t_row0 = d.q_row0; rd.nt = d.nq;
+            rd.out_row0 = h_tp[base + (order[k] - B.p0)];
+            h_rpd[B.p0 + k] = rd;
+            h_unit[base + k] = units; h_runit[base + k] = runits;
+            units += (d.nq + rpu - 1) / rpu;
+            runits += (d.nt + rpu - 1) / rpu;
+        }
+        h_unit[base + np] = units; h_runit[base + np] = runits;
         B.n_units = units; B.n_rev_units = runits; B.staged_rows = orow; B.t_rows = trow;
         max_staged = std::max(max_staged, orow);
         max_t = std::max(max_t, trow);
         max_chunks = std::max(max_chunks, orow / 256);
     }
-    CU_TRY(c, c->d_pairs.ensure(std::max<size_t>(64, 2 * bytes_pd + 4 * bytes_pre)));
+    CU_TRY(c, c->d_pairs.ensure(std::max<size_t>(64, bytes_meta)));
     if (n_pairs > 0) {
-        CU_TRY(c, cudaMemcpyAsync(c->d_pairs.p, c->h_meta.p, 2 * bytes_pd + 4 * bytes_pre, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, cudaMemcpyAsync(c->d_pairs.p, c->h_meta.p, bytes_meta, cudaMemcpyHostToDevice, s));
         CU_TRY(c, cudaEventRecord(c->meta_ev, s));
-        c->stat_h2d += static_cast<int64_t>(2 * bytes_pd + 4 * bytes_pre);
+        c->stat_h2d += static_cast<int64_t>(bytes_meta);
     }
     const PairDesc* d_pd = c->d_pairs.as<PairDesc>();
-    const PairDesc* d_rpd = d_pd + n_pairs;
+    const PairDesc* d_ppd = d_pd + n_pairs;
+    const PairDesc* d_rpd = d_ppd + n_pairs;
     const int64_t* d_unit = reinterpret_cast<const int64_t*>(d_rpd + n_pairs);
     const int64_t* d_runit = d_unit + npre;
     const int64_t* d_outp = d_runit + npre;
@@ -485,7 +507,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
         const int np = static_cast<int>(B.p1 - B.p0);
         const int64_t base = B.p0 + bi;
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
-        rc = launch_knn(c, b, eng, d_pd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>());
+        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>());
         if (rc != SFM_OK) return rc;
         if (need_rev) {
             rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, c->d_rev.as<Top2>());
