@@ -102,6 +102,10 @@ int sfm_bank_upload(sfm_ctx *ctx, int n_images, const void *const *rows, const i
 int sfm_bank_upload_device(sfm_ctx *ctx, int n_images, const void *dev_rows, const int64_t *row_offset,
                            const int32_t *n_rows, int cols, int cv_depth);
 int sfm_bank_info(const sfm_ctx *ctx, int *n_images, int *cols, int *is_u8_valued);
+/* Device address of image `image`'s packed u8 rows inside the resident bank (valid until the next upload).  Lets a
+ * multi-GPU host upload 1/N of the images per GPU and all-gather the packed bank over NVLink instead of sending the
+ * whole CV_32F scene through every GPU's PCIe link. */
+int sfm_bank_device_ptr(const sfm_ctx *ctx, int image, const void **dev_rows, int32_t *n_rows);
 
 /* Pair selection --------------------------------------------------------------------------------
  * Replaces the matchPairs construction of the three strategies, chosen exactly like

@@ -30,7 +30,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_ctx_stream", "sfm_bank_upload", "sfm_bank_upload_device", "sfm_bank_info", "sfm_select_pairs",
            "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
-           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile"]
+           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr"]
 
 
 class SfmError(RuntimeError):
@@ -177,6 +177,11 @@ class Matcher:
         nr = (C.c_int32 * n)(*[int(x) for x in n_rows])
         self._check(_lib.sfm_bank_upload_device(self._ctx, C.c_int(n), C.c_void_p(dev_ptr), ro, nr, C.c_int(cols),
                                                 C.c_int(depth)))
+
+    def bank_device_ptr(self, image: int):
+        p, n = C.c_void_p(), C.c_int32()
+        self._check(_lib.sfm_bank_device_ptr(self._ctx, C.c_int(image), C.byref(p), C.byref(n)))
+        return int(p.value or 0), n.value
 
     def bank_info(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -698,6 +698,15 @@ int sfm_bank_upload_device(sfm_ctx* c, int n_images, const void* dev_rows, const
     return bank_finish(c, b);
 }
 
+int sfm_bank_device_ptr(const sfm_ctx* c, int image, const void** dev_rows, int32_t* n_rows) {
+    if (!c || !dev_rows) return SFM_ERR_INVALID;
+    const Bank& b = c->bank;
+    if (image < 0 || image >= b.n_images || !b.u8_valued) return SFM_ERR_STATE;
+    *dev_rows = b.d_u8.as<uint8_t>() + static_cast<size_t>(b.row0[image]) * b.cols;
+    if (n_rows) *n_rows = b.n_rows[image];
+    return SFM_OK;
+}
+
 int sfm_bank_info(const sfm_ctx* c, int* n_images, int* cols, int* is_u8_valued) {
     if (!c) return SFM_ERR_INVALID;
     if (n_images) *n_images = c->bank.n_images;
