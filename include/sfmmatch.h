@@ -38,8 +38,8 @@ extern "C" {
 #define SFM_MAX_ROWS       (1 << 18)
 
 /* engine selector (tests / profiling): which hand-written kernel computes the distances */
-#define SFM_ENGINE_AUTO    0    /* tcgen05 for L2 on u8-valued data, popc for Hamming */
-#define SFM_ENGINE_TENSOR  1    /* force tcgen05/TMA/TMEM kernel (L2, and Hamming via bit-expanded u8) */
+#define SFM_ENGINE_AUTO    0    /* tcgen05 kernels (L2 on u8-valued 128-d data; Hamming on 256-bit descriptors) */
+#define SFM_ENGINE_TENSOR  1    /* force tcgen05/TMA/TMEM kernels (Hamming: bits expanded to u8, K = 256, exact) */
 #define SFM_ENGINE_SIMT    2    /* force CUDA-core kernels (dp4a L2 / popc Hamming / fp32 L2) */
 #define SFM_ENGINE_TENSOR_IMAD 3 /* force the tcgen05 kernel with the packed-key (IMAD) epilogue even where the
                                    value-only tcgen05 kernel would be chosen */

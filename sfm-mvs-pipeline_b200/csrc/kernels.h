@@ -23,7 +23,7 @@ struct TcLaunchInfo { int grid; int smem_bytes; };
 // tmap: CUtensorMap (128 B, 64-B aligned, passed by value as __grid_constant__) over the u8 bank
 cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_host, const int32_t* ckey,
                                  const int32_t* norm2, const PairDesc* pairs, const int64_t* unit_prefix,
-                                 int n_pairs, int64_t n_units, Top2* out, int sm_count, cudaStream_t s);
+                                 int n_pairs, int64_t n_units, Top2* out, int sm_count, int slabs, cudaStream_t s);
 
 // ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
@@ -33,6 +33,8 @@ cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_ho
 // ---- post.cu
 cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols,
                                   const int32_t* valid_in_block, uint8_t* dst, int* not_integer_flag, cudaStream_t s);
+cudaError_t launch_expand_bits(const uint8_t* bank32, int64_t padded_rows, const int32_t* valid_in_block, uint8_t* bits,
+                               int32_t* norm2, int32_t* ckey, cudaStream_t s);
 cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, const int32_t* valid_in_block, cudaStream_t s);
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* row_valid_end /*per 256-row block*/,
                                int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, cudaStream_t s);
@@ -68,6 +70,7 @@ struct RefineArgs {
     const int32_t* norm2;
     int all_rows;                // 1: every row (raw knnMatch output), 0: only rows that can pass the ratio test
     double ratio;
+    int hamming;                 // bank = 32-byte ORB rows, distances by __popc (no sqrt in the provisional test)
 };
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
 // value-only tcgen05 path: (chunk, D) pairs -> exact Top2 for rows that can pass the ratio test (see post.cu)

@@ -32,22 +32,29 @@
 namespace sfm {
 
 namespace tc {
-constexpr int BM = 128, BN = 256, KB = 128;
-constexpr int kBStages = 4, kAStages = 2, kAccStages = 2, kCkSlots = 8;
-constexpr int kABytes = BM * KB, kBBytes = BN * KB, kCkBytes = BN * 4;
+constexpr int BM = 128, BN = 256;
+constexpr int kAStages = 2, kAccStages = 2, kCkSlots = 8;
+constexpr int kCkBytes = BN * 4;
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
-// shared memory carve-up (offsets from a 1024-byte aligned base)
-constexpr int offB = 0;
-constexpr int offA = offB + kBStages * kBBytes;
-constexpr int offCk = offA + kAStages * kABytes;
-constexpr int offMerge = offCk + kCkSlots * kCkBytes;            // [128][2] int64
-constexpr int offBar = offMerge + BM * 2 * 8;
-constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages + kCkSlots;
-constexpr int offTmemPtr = offBar + kNumBars * 8;
-constexpr int kSmemBytes = offTmemPtr + 16 + 1024;                // + alignment slack
 constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
 constexpr int64_t kEmptyKey = INT64_MAX;
+// kSlabs = number of 128-byte K slabs of a descriptor row: 1 = SIFT (128 x u8), 2 = ORB bits expanded to 256 x u8
+// (Hamming(a,b) = |a| + |b| - 2 a.b is the same contraction).  Shared memory carve-up from a 1024-byte aligned base.
+template <int kSlabs>
+struct Cfg {
+    static constexpr int KB = 128 * kSlabs;
+    static constexpr int kBStages = kSlabs == 1 ? 4 : 2;
+    static constexpr int kABytes = BM * KB, kBBytes = BN * KB;
+    static constexpr int offB = 0;
+    static constexpr int offA = offB + kBStages * kBBytes;
+    static constexpr int offCk = offA + kAStages * kABytes;
+    static constexpr int offMerge = offCk + kCkSlots * kCkBytes;            // [128][2] int64
+    static constexpr int offBar = offMerge + BM * 2 * 8;
+    static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages + kCkSlots;
+    static constexpr int offTmemPtr = offBar + kNumBars * 8;
+    static constexpr int kSmemBytes = offTmemPtr + 16 + 1024;               // + alignment slack
+};
 }  // namespace tc
 
 struct UnitInfo { PairDesc pd; int rb; int n_tiles; };
@@ -72,12 +79,17 @@ __device__ __forceinline__ void top2_key64(int64_t k, int64_t& m1, int64_t& m2) 
     m1 = min(m1, k);
 }
 
+template <int kSlabs>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const int32_t* __restrict__ ckey, const int32_t* __restrict__ norm2,
                      const PairDesc* __restrict__ pairs, const int64_t* __restrict__ unit_prefix, int n_pairs,
                      int64_t n_units, Top2* __restrict__ out) {
     using namespace tc;
+    using C = Cfg<kSlabs>;
+    constexpr int kBStages = C::kBStages, kABytes = C::kABytes, kBBytes = C::kBBytes;
+    constexpr int offA = C::offA, offB = C::offB, offCk = C::offCk, offMerge = C::offMerge, offBar = C::offBar;
+    constexpr int offTmemPtr = C::offTmemPtr;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -124,14 +136,20 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
             if (lane == 0) {
                 mbar_arrive_expect_tx(a_full(as), kABytes);
-                tma_load_2d(base + offA + as * kABytes, &tmap_a, 0, u.pd.q_row0 + u.rb * BM, a_full(as));
+#pragma unroll
+                for (int sl = 0; sl < kSlabs; ++sl)      // one 128-byte-wide box per K slab
+                    tma_load_2d(base + offA + as * kABytes + sl * (BM * 128), &tmap_a, sl * 128, u.pd.q_row0 + u.rb * BM,
+                                a_full(as));
             }
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
                 const int st = tile_iter % kBStages;
                 mbar_wait(b_empty(st), ((tile_iter / kBStages) & 1) ^ 1);
                 if (lane == 0) {
                     mbar_arrive_expect_tx(b_full(st), kBBytes);
-                    tma_load_2d(base + offB + st * kBBytes, &tmap_b, 0, u.pd.t_row0 + t * BN, b_full(st));
+#pragma unroll
+                    for (int sl = 0; sl < kSlabs; ++sl)
+                        tma_load_2d(base + offB + st * kBBytes + sl * (BN * 128), &tmap_b, sl * 128, u.pd.t_row0 + t * BN,
+                                    b_full(st));
                     // ckey ring: 8 slots, the producer is never more than kBStages + kAccStages = 6 tiles ahead
                     // of the epilogue, so a slot is free again before it is reloaded
                     const int cs = tile_iter % kCkSlots;
@@ -150,7 +168,7 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
-            const uint64_t adesc = umma_desc_sw128(base + offA + as * kABytes);
+            const uint32_t a_smem = base + offA + as * kABytes;
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
                 const int acc = tile_iter % kAccStages;
                 const int st = tile_iter % kBStages;
@@ -158,11 +176,16 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 mbar_wait(b_full(st), (tile_iter / kBStages) & 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint64_t bdesc = umma_desc_sw128(base + offB + st * kBBytes);
+                    const uint32_t b_smem = base + offB + st * kBBytes;
                     const uint32_t d = tmem_base + acc * BN;
 #pragma unroll
-                    for (int k = 0; k < KB / 32; ++k)      // K = 32 bytes per tcgen05.mma.kind::i8; +32 B = +2 encoded
-                        umma_i8(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
+                    for (int sl = 0; sl < kSlabs; ++sl) {
+                        const uint64_t adesc = umma_desc_sw128(a_smem + sl * (BM * 128));
+                        const uint64_t bdesc = umma_desc_sw128(b_smem + sl * (BN * 128));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)        // K = 32 bytes per tcgen05.mma.kind::i8; +32 B = +2 encoded
+                            umma_i8(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, (sl | k) > 0);
+                    }
                     umma_commit(b_empty(st));              // smem stage free once these MMAs retire
                     umma_commit(acc_full(acc));            // accumulator ready for the epilogue
                     if (t == u.n_tiles - 1) umma_commit(a_empty(as));
@@ -268,23 +291,32 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_host, const int32_t* ckey,
-                                 const int32_t* norm2, const PairDesc* pairs, const int64_t* unit_prefix,
-                                 int n_pairs, int64_t n_units, Top2* out, int sm_count, cudaStream_t s) {
-    if (n_units == 0) return cudaSuccess;
+template <int kSlabs>
+static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const int32_t* ckey, const int32_t* norm2,
+                             const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out,
+                             int grid, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             tc::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tc_kernel<kSlabs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             tc::Cfg<kSlabs>::kSmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    knn2_l2_u8_tc_kernel<kSlabs><<<grid, tc::kThreads, tc::Cfg<kSlabs>::kSmemBytes, s>>>(ta, tb, ckey, norm2, pairs, unit_prefix,
+                                                                                        n_pairs, n_units, out);
+    return cudaGetLastError();
+}
+
+// slabs: 1 = 128-byte rows (SIFT), 2 = 256-byte rows (ORB bits expanded to bytes)
+cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_host, const int32_t* ckey,
+                                 const int32_t* norm2, const PairDesc* pairs, const int64_t* unit_prefix,
+                                 int n_pairs, int64_t n_units, Top2* out, int sm_count, int slabs, cudaStream_t s) {
+    if (n_units == 0) return cudaSuccess;
     const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
-    knn2_l2_u8_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(*ta, *tb, ckey, norm2, pairs, unit_prefix, n_pairs,
-                                                                    n_units, out);
-    return cudaGetLastError();
+    if (slabs == 2) return launch_tc<2>(*ta, *tb, ckey, norm2, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
+    return launch_tc<1>(*ta, *tb, ckey, norm2, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
 }
 
 }  // namespace sfm

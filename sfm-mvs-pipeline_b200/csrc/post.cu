@@ -104,6 +104,39 @@ cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const i
     return cudaGetLastError();
 }
 
+// ORB: expand every descriptor bit to one byte (256-byte rows for the tcgen05 kernel: Hamming(a,b) = |a| + |b| - 2 a.b
+// over 0/1 bytes), popcount as the "squared norm", packed column key.  One warp per 32-byte row.
+__global__ void expand_bits_kernel(const uint8_t* __restrict__ bank32, int64_t padded_rows,
+                                   const int32_t* __restrict__ valid_in_block, uint8_t* __restrict__ bits,
+                                   int32_t* __restrict__ norm2, int32_t* __restrict__ ckey) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= padded_rows) return;
+    const uint32_t byte = bank32[row * 32 + lane];
+    uint2 o;
+    o.x = (byte & 1u) | ((byte & 2u) << 7) | ((byte & 4u) << 14) | ((byte & 8u) << 21);
+    o.y = ((byte >> 4) & 1u) | (((byte >> 4) & 2u) << 7) | (((byte >> 4) & 4u) << 14) | (((byte >> 4) & 8u) << 21);
+    *reinterpret_cast<uint2*>(bits + row * 256 + lane * 8) = o;
+    uint32_t s = __popc(byte);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        const int col = static_cast<int>(row & (kRowAlign - 1));
+        const bool valid = col < valid_in_block[row / kRowAlign];
+        norm2[row] = static_cast<int32_t>(s);
+        ckey[row] = valid ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col)) : (kSentinelKey | col);
+    }
+}
+
+cudaError_t launch_expand_bits(const uint8_t* bank32, int64_t padded_rows, const int32_t* valid_in_block, uint8_t* bits,
+                               int32_t* norm2, int32_t* ckey, cudaStream_t s) {
+    if (padded_rows == 0) return cudaSuccess;
+    const int64_t threads = padded_rows * 32;
+    expand_bits_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(bank32, padded_rows, valid_in_block, bits,
+                                                                                     norm2, ckey);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ filters
 struct RowCtx { int p; int row; bool valid; PairDesc pd; Top2 t; };
 
@@ -201,6 +234,7 @@ __global__ void __launch_bounds__(256) compact_kernel(FilterArgs a, const int64_
 // d1' >= d1(true), d0 >= ratio*d1' already implies rejection.  For every row that needs it one warp recomputes
 // the chunk: lane l takes train row chunk0 + l (128-byte row, 32 x __dp4a), then a warp min over the packed
 // (distance, index) keys.  Exact integer arithmetic, ties -> lowest trainIdx.
+template <bool kHamming>
 __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
     const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -217,7 +251,10 @@ __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
             q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
             if (t.i0 >= 0) {
                 if (a.all_rows || t.i1 < 0) need = true;
-                else need = static_cast<double>(__fsqrt_rn(t.d0)) < static_cast<double>(__fsqrt_rn(t.d1)) * a.ratio;
+                else {
+                    const float x0 = kHamming ? t.d0 : __fsqrt_rn(t.d0), x1 = kHamming ? t.d1 : __fsqrt_rn(t.d1);
+                    need = static_cast<double>(x0) < static_cast<double>(x1) * a.ratio;
+                }
             }
         }
     }
@@ -230,16 +267,26 @@ __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
         const int ntr = __shfl_sync(0xffffffffu, nt, src);
         const int best = __shfl_sync(0xffffffffu, t.i0, src);
         const int j = (best & ~31) + lane;
-        const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
-        const uint4* tv = reinterpret_cast<const uint4*>(a.bank + (static_cast<size_t>(tr0) + j) * 128);
-        uint32_t dot = 0;
+        int32_t d;
+        if (kHamming) {
+            // 32-byte ORB rows: the distance itself, 8 x __popc
+            const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 32);
+            const uint4* tv = reinterpret_cast<const uint4*>(a.bank + (static_cast<size_t>(tr0) + j) * 32);
+            const uint4 x0 = __ldg(qv), x1 = __ldg(qv + 1), y0 = __ldg(tv), y1 = __ldg(tv + 1);
+            d = __popc(x0.x ^ y0.x) + __popc(x0.y ^ y0.y) + __popc(x0.z ^ y0.z) + __popc(x0.w ^ y0.w) +
+                __popc(x1.x ^ y1.x) + __popc(x1.y ^ y1.y) + __popc(x1.z ^ y1.z) + __popc(x1.w ^ y1.w);
+        } else {
+            const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
+            const uint4* tv = reinterpret_cast<const uint4*>(a.bank + (static_cast<size_t>(tr0) + j) * 128);
+            uint32_t dot = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint4 x = __ldg(qv + i), y = __ldg(tv + i);
-            dot = __dp4a(x.x, y.x, dot); dot = __dp4a(x.y, y.y, dot);
-            dot = __dp4a(x.z, y.z, dot); dot = __dp4a(x.w, y.w, dot);
+            for (int i = 0; i < 8; ++i) {
+                const uint4 x = __ldg(qv + i), y = __ldg(tv + i);
+                dot = __dp4a(x.x, y.x, dot); dot = __dp4a(x.y, y.y, dot);
+                dot = __dp4a(x.z, y.z, dot); dot = __dp4a(x.w, y.w, dot);
+            }
+            d = a.norm2[qrow] + a.norm2[tr0 + j] - 2 * static_cast<int32_t>(dot);
         }
-        const int32_t d = a.norm2[qrow] + a.norm2[tr0 + j] - 2 * static_cast<int32_t>(dot);
         long long key = (j < ntr && j != best) ? ((static_cast<long long>(d) << 32) | static_cast<unsigned>(j)) : LLONG_MAX;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
@@ -351,7 +398,8 @@ static inline unsigned chunks_of(int64_t rows) { return static_cast<unsigned>((r
 
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
-    refine_second_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
+    if (a.hamming) refine_second_kernel<true><<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
+    else refine_second_kernel<false><<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s) {

@@ -68,11 +68,11 @@ struct Bank {
     std::vector<int32_t> n_rows;
     std::vector<int64_t> row0;
     int64_t padded_rows = 0;
-    DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid, d_ext;
+    DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid, d_ext, d_bits;     // d_bits: ORB bits expanded to bytes (256 B rows)
     alignas(64) CUtensorMap tmap_a, tmap_b, tmap_e;
     bool ext_ok = false;             // every |b|^2 <= kExtMaxNorm2: the value-only tcgen05 kernel may be used
     bool have_tmap = false;
-    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); }
+    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release(); }
 };
 
 struct RunState {                    // what collect() needs from the last enqueue
@@ -136,7 +136,26 @@ int fail(sfm_ctx* c, int code, const std::string& msg) {
 
 int make_tmaps(sfm_ctx* c, Bank& b) {
     b.have_tmap = false;
-    if (!(b.u8_valued && b.cols == 128) || b.padded_rows == 0) return SFM_OK;
+    if (b.padded_rows == 0) return SFM_OK;
+    if (b.depth == SFM_CV_8U && b.cols == 32) {
+        // ORB: tensor maps over the bit-expanded copy, 256-byte rows, one 128-byte-wide box per K slab
+        const cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(b.padded_rows)};
+        const cuuint64_t strides[1] = {256};
+        const cuuint32_t estr[2] = {1, 1};
+        const cuuint32_t box_a[2] = {128, kTcRowsPerUnit};
+        const cuuint32_t box_b[2] = {128, 256};
+        CUresult r = c->encode(&b.tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.d_bits.p, dims, strides, box_a, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = c->encode(&b.tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.d_bits.p, dims, strides, box_b, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(ORB bits) failed: " + std::to_string(r));
+        b.have_tmap = true;
+        return SFM_OK;
+    }
+    if (!(b.u8_valued && b.cols == 128)) return SFM_OK;
     const cuuint64_t dims[2] = {128, static_cast<cuuint64_t>(b.padded_rows)};
     const cuuint64_t strides[1] = {128};
     const cuuint32_t estr[2] = {1, 1};
@@ -215,6 +234,14 @@ int bank_finish(sfm_ctx* c, Bank& b) {
     } else if (b.depth == SFM_CV_8U) {
         CU_TRY(c, launch_zero_padding(b.d_u8.p, b.cols, b.padded_rows, d_valid, s));
         c->stat_launches++;
+        if (b.cols == 32) {
+            CU_TRY(c, b.d_bits.ensure(static_cast<size_t>(b.padded_rows) * 256));
+            CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
+            CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
+            CU_TRY(c, launch_expand_bits(b.d_u8.as<uint8_t>(), b.padded_rows, d_valid, b.d_bits.as<uint8_t>(),
+                                         b.d_norm2.as<int32_t>(), b.d_ckey.as<int32_t>(), s));
+            c->stat_launches++;
+        }
     }
     if (maybe_u8 && b.cols == 128) {
         CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
@@ -300,9 +327,8 @@ int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out)
     if (norm == SFM_NORM_HAMMING) {
         if (b.depth != SFM_CV_8U) return fail(c, SFM_ERR_INVALID, "NORM_HAMMING needs CV_8U descriptors");
         if (b.cols != 32) return fail(c, SFM_ERR_UNSUPPORTED, "Hamming kernel is built for 256-bit (32-byte) descriptors");
-        if (requested == SFM_ENGINE_TENSOR || requested == SFM_ENGINE_TENSOR_IMAD)
-            return fail(c, SFM_ERR_UNSUPPORTED, "tensor-core Hamming engine not built yet");
-        *out = Engine::POPC;
+        // tensor engine: bits expanded to bytes, same tcgen05 kernel with K = 256 (exact); SIMT: the __popc kernel
+        *out = requested == SFM_ENGINE_SIMT ? Engine::POPC : Engine::TC;
         return SFM_OK;
     }
     if (norm != SFM_NORM_L2) return fail(c, SFM_ERR_UNSUPPORTED, "only NORM_L2 and NORM_HAMMING are supported");
@@ -325,7 +351,7 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
     switch (eng) {
         case Engine::TC:
             CU_TRY(c, launch_knn2_l2_u8_tc(&b.tmap_a, &b.tmap_b, b.d_ckey.as<int32_t>(), b.d_norm2.as<int32_t>(), d_pairs,
-                                           d_unit_prefix, n_pairs, n_units, out, c->sm_count, s));
+                                           d_unit_prefix, n_pairs, n_units, out, c->sm_count, b.cols == 32 ? 2 : 1, s));
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
@@ -518,7 +544,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
             RefineArgs ra;
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
-            ra.all_rows = 0; ra.ratio = o->ratio;
+            ra.all_rows = 0; ra.ratio = o->ratio; ra.hamming = o->norm == SFM_NORM_HAMMING;
             if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
             else CU_TRY(c, launch_refine_second(ra, s));
             c->stat_launches++;
@@ -821,7 +847,7 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
         ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd;
         ra.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
         ra.n_pairs = 1; ra.staged_rows = pad_rows(nq); ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
-        ra.all_rows = 1; ra.ratio = 0.0;
+        ra.all_rows = 1; ra.ratio = 0.0; ra.hamming = norm == SFM_NORM_HAMMING;
         CU_TRY(c, launch_refine_second(ra, s));
         c->stat_launches++;
     }

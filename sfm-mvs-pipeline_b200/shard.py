@@ -84,11 +84,13 @@ def gather_matches(local_idx: np.ndarray, counts: np.ndarray, matches: np.ndarra
     np.cumsum(total_counts, out=offsets[1:])
     out = np.zeros(int(offsets[-1]), _dmatch_dtype())
     for idx, cnt, m in per_rank:
+        if len(m) == 0:
+            continue
         src_off = np.zeros(len(cnt) + 1, np.int64)
         np.cumsum(cnt, out=src_off[1:])
-        for k in range(len(idx)):
-            if cnt[k]:
-                out[offsets[idx[k]]:offsets[idx[k]] + cnt[k]] = m[src_off[k]:src_off[k + 1]]
+        # destination of every record: start of its pair in the global list + position inside the pair
+        dst = np.repeat(offsets[idx] - src_off[:-1], cnt) + np.arange(len(m), dtype=np.int64)
+        out[dst] = m
     return offsets, out, total_dropped
 
 

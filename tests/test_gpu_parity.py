@@ -47,8 +47,9 @@ def test_insel_sift_knn_bit_exact(sfm, matcher, insel_sift, a, b, eng, as_float)
 
 
 @pytest.mark.parametrize("a,b", PAIRS)
-def test_insel_orb_knn_bit_exact(sfm, matcher, insel_orb, a, b):
-    idx, dist = matcher.knn_match(insel_orb[f"desc{a}"], insel_orb[f"desc{b}"], NORM_HAMMING, 2)
+@pytest.mark.parametrize("eng", ["tensor", "simt"])     # tcgen05 on bit-expanded rows / the __popc kernel
+def test_insel_orb_knn_bit_exact(sfm, matcher, insel_orb, a, b, eng):
+    idx, dist = matcher.knn_match(insel_orb[f"desc{a}"], insel_orb[f"desc{b}"], NORM_HAMMING, 2, dict(_engines(sfm))[eng])
     _same_knn(idx, dist, insel_orb[f"p{a}{b}_nidx"], insel_orb[f"p{a}{b}_dist"])
 
 
@@ -82,12 +83,22 @@ def test_hamming_ties_and_synthetic(sfm, matcher, synthetic_cv2):
     obd = np.concatenate([ob[1][:50], ob[1][:50], ob[1]])
     for name, q, t in (("orb01", ob[0], ob[1]), ("orb12", ob[1], ob[2]), ("orb_dup", ob[0], obd),
                        ("orb_one", ob[0], ob[1][:1])):
-        idx, dist = matcher.knn_match(q, t, NORM_HAMMING, 2)
-        g_idx, g_dist = synthetic_cv2[f"{name}_nidx"], synthetic_cv2[f"{name}_dist"]
-        if name == "orb_one":
-            assert np.array_equal(idx[:, 0], g_idx[:, 0]) and np.all(idx[:, 1] == -1)
-        else:
-            _same_knn(idx, dist, g_idx, g_dist)
+        for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+            idx, dist = matcher.knn_match(q, t, NORM_HAMMING, 2, eng)
+            g_idx, g_dist = synthetic_cv2[f"{name}_nidx"], synthetic_cv2[f"{name}_dist"]
+            if name == "orb_one":
+                assert np.array_equal(idx[:, 0], g_idx[:, 0]) and np.all(idx[:, 1] == -1)
+            else:
+                _same_knn(idx, dist, g_idx, g_dist)
+    # all-zero / all-one descriptors and ragged sizes
+    z = np.zeros((70, 32), np.uint8)
+    o = np.full((45, 32), 255, np.uint8)
+    mix = np.concatenate([z[:3], ob[0][:200], o[:2], ob[0][:50]])
+    for q, t in ((mix, ob[1][:257]), (ob[1][:129], mix), (z, o), (mix, mix)):
+        e_idx, e_dist = orc.knn2_hamming(q, t)
+        for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+            idx, dist = matcher.knn_match(q, t, NORM_HAMMING, 2, eng)
+            _same_knn(idx, dist, e_idx, e_dist)
 
 
 def test_error_behaviour_mirrors_opencv(sfm, matcher):
@@ -150,9 +161,10 @@ def test_insel_orb_match_pairs_c2(sfm, matcher, insel_orb):
     matcher.upload_bank([insel_orb[f"desc{i}"] for i in range(3)])
     for seq in (2, 3):
         pairs = sfm.select_pairs(3, seq, 0)
-        res = matcher.match_pairs(pairs, NORM_HAMMING)
-        for p, (a, b) in enumerate(pairs):
-            assert orc.dmatch_equal(res[p], insel_orb[f"p{a}{b}_good"])
+        for eng in (sfm.ENGINE_AUTO, sfm.ENGINE_SIMT):
+            res = matcher.match_pairs(pairs, NORM_HAMMING, engine=eng)
+            for p, (a, b) in enumerate(pairs):
+                assert orc.dmatch_equal(res[p], insel_orb[f"p{a}{b}_good"])
 
 
 def test_synthetic_bank_all_pairs_vs_oracle(sfm, matcher):
@@ -232,8 +244,9 @@ def test_cross_check_vs_cv2_golden(sfm, matcher, insel_sift, synthetic_cv2):
     assert orc.dmatch_equal(res[0], synthetic_cv2["syn01_cross"])
     ob = workloads.orb_like_bank(3, 900)
     matcher.upload_bank(ob)
-    res = matcher.match_pairs([[0, 1]], NORM_HAMMING, k=1, cross_check=True)
-    assert orc.dmatch_equal(res[0], synthetic_cv2["orb01_cross"])
+    for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+        res = matcher.match_pairs([[0, 1]], NORM_HAMMING, k=1, cross_check=True, engine=eng)
+        assert orc.dmatch_equal(res[0], synthetic_cv2["orb01_cross"])
 
 
 def test_batching_is_invisible(sfm):
@@ -276,11 +289,14 @@ def test_orb_30000_rows_properties(sfm, matcher):
     """N = 30000 (run-orb-sequence.sh -Pfeature-limit=30000): sampled oracle rows + planted-match recovery."""
     a = workloads.orb_like_image(0, 30000)
     b = workloads.orb_like_image(1, 30000, a)
-    idx, dist = matcher.knn_match(b[:2048], a, NORM_HAMMING, 2)
     eidx, edist = orc.knn2_hamming(b[:2048], a)
-    _same_knn(idx, dist, eidx, edist)
+    for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+        idx, dist = matcher.knn_match(b[:2048], a, NORM_HAMMING, 2, eng)
+        _same_knn(idx, dist, eidx, edist)
     matcher.upload_bank([a, b])
     r = matcher.match_pairs([[1, 0]], NORM_HAMMING)
+    r_simt = matcher.match_pairs([[1, 0]], NORM_HAMMING, engine=sfm.ENGINE_SIMT)
+    assert r.matches.tobytes() == r_simt.matches.tobytes()        # tcgen05 and __popc kernels agree on all 30000 rows
     got = r[0]
     # planted copies (first 30 % of b, 20 bit flips) must survive the ratio test
     assert (got["queryIdx"] < 9000).sum() >= 8900 and np.all(got["distance"][got["queryIdx"] < 9000] <= 20)

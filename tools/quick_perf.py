@@ -30,8 +30,10 @@ for name, eng in (("tensor", sfm.ENGINE_TENSOR), ("simt", sfm.ENGINE_SIMT)):
 ob = workloads.orb_like_bank(4, 30000)
 m.upload_bank(ob)
 op = sfm.select_pairs(4, 2, 0)
-for rep in range(2):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream); m.enqueue(op, sfm.NORM_HAMMING); e1.record(stream); e1.synchronize()
-    ms = e0.elapsed_time(e1); r = m.collect()
-    print(f"orb popc rep{rep}: {ms:.3f} ms for {len(op)} pairs (30000x30000) -> {len(op)/ms*1e3:.1f} pairs/s matches={int(r.offsets[-1])}")
+for name, eng in (("tensor", sfm.ENGINE_TENSOR), ("popc", sfm.ENGINE_SIMT)):
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); m.enqueue(op, sfm.NORM_HAMMING, engine=eng); e1.record(stream); e1.synchronize()
+        ms = e0.elapsed_time(e1); r = m.collect()
+        print(f"orb {name} rep{rep}: {ms:.3f} ms for {len(op)} pairs (30000x30000) -> {len(op)/ms*1e3:.1f} pairs/s "
+              f"matches={int(r.offsets[-1])}")
