@@ -1,0 +1,57 @@
+"""Worker for tests/test_multi_gpu.py (launched with torch.distributed.run, one rank per GPU): replicate the bank
+over NCCL, shard the pair list, gather on rank 0 and compare byte-for-byte with rank 0's own single-GPU run."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+import workloads  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    sfm = ge.load_package()
+    spec = importlib.util.spec_from_file_location("sfm_shard", os.path.join(ge.PKG_DIR, "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    sizes = [1500, 1024, 777, 2048, 300, 1300, 0, 640]
+    total = sum(sizes)
+    bank_dev = torch.zeros((max(total, 1), 128), dtype=torch.uint8, device=dev)
+    if rank == 0:
+        bank, prev = [], None
+        for i, n in enumerate(sizes):
+            d = workloads.sift_like_image(i, n, prev if prev is not None and len(prev) else None)
+            bank.append(d)
+            prev = d
+        bank_dev.copy_(torch.from_numpy(np.concatenate(bank)))
+    shard.broadcast_bank(bank_dev, 0)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).tolist()
+    m = sfm.Matcher(local)
+    m.upload_bank_device(bank_dev.data_ptr(), offs, sizes, 128, sfm.CV_8U)
+    pairs = sfm.select_pairs(len(sizes), 0, 0)
+    mine = shard.assign_pairs(pairs, sizes, world)[rank]
+    res = m.match_pairs(pairs[mine], sfm.NORM_L2, min_match_count=20)
+    g = shard.gather_matches(mine, res.counts(), res.matches, res.dropped, len(pairs), dev, 0)
+    ok = True
+    if rank == 0:
+        full = m.match_pairs(pairs, sfm.NORM_L2, min_match_count=20)
+        ok = (np.array_equal(g[0], full.offsets) and g[1].tobytes() == full.matches.tobytes()
+              and np.array_equal(g[2], full.dropped))
+        print("MGPU_IDENTICAL" if ok else "MGPU_MISMATCH", int(full.offsets[-1]), flush=True)
+    m.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
