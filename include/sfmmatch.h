@@ -134,7 +134,7 @@ int64_t           sfm_result_n_pairs(const sfm_result *r);
 const int64_t    *sfm_result_offsets(const sfm_result *r);   /* n_pairs + 1 entries */
 const sfm_dmatch *sfm_result_matches(const sfm_result *r);   /* offsets[n_pairs] entries */
 const uint8_t    *sfm_result_dropped(const sfm_result *r);   /* n_pairs flags: 1 = erased by min_match_count */
-void              sfm_result_free(sfm_result *r);
+void              sfm_result_free(sfm_result *r);       /* call before sfm_ctx_destroy of the producing context */
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 

@@ -295,13 +295,10 @@ template <int kSlabs>
 static cudaError_t launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const int32_t* ckey, const int32_t* norm2,
                              const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out,
                              int grid, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tc_kernel<kSlabs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // per launch: the attribute is per device, and one process may drive several GPUs
+    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tc_kernel<kSlabs>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tc::Cfg<kSlabs>::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (e != cudaSuccess) return e;
     knn2_l2_u8_tc_kernel<kSlabs><<<grid, tc::kThreads, tc::Cfg<kSlabs>::kSmemBytes, s>>>(ta, tb, ckey, norm2, pairs, unit_prefix,
                                                                                         n_pairs, n_units, out);
     return cudaGetLastError();

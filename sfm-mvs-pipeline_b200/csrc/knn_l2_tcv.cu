@@ -309,13 +309,10 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 template <int kGroups>
 static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
                               const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int grid, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // per launch: the attribute is per device, and one process may drive several GPUs
+    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              tcv::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (e != cudaSuccess) return e;
     knn2_l2_u8_tcv_kernel<kGroups><<<grid, 128 + 128 * kGroups, tcv::kSmemBytes, s>>>(ta, tb, te, pairs, unit_prefix, n_pairs,
                                                                                       n_units, out);
     return cudaGetLastError();
