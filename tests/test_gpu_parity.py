@@ -322,3 +322,43 @@ def test_cli_keeps_reference_switches(sfm, insel_sift, tmp_path):
     n0 = int(np.frombuffer(raw[16:24], np.uint64)[0])
     m0 = np.frombuffer(raw[24:24 + 16 * n0], orc.DMATCH_DTYPE)
     assert orc.dmatch_equal(m0, insel_sift["p01_good"])
+
+
+def test_randomised_ragged_banks_all_engines(sfm, matcher):
+    """Fuzz: random image sizes (0 .. ~2500 rows, around every tile/chunk boundary), random pair lists, every engine,
+    against the C restatement of the oracle (threads over pairs).  Bit-exact."""
+    from oracle import oracle_c as oc
+    rng = np.random.default_rng(2024)
+    edge = [0, 1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 513, 1023, 1025]
+    for trial in range(4):
+        n_img = 7
+        sizes = [int(rng.choice(edge)) if rng.random() < 0.5 else int(rng.integers(0, 2500)) for _ in range(n_img)]
+        bank, prev = [], None
+        for i, n in enumerate(sizes):
+            d = workloads.sift_like_image(100 * trial + i, n, prev if prev is not None and len(prev) else None)
+            bank.append(d)
+            prev = d
+        pairs = sfm.select_pairs(n_img, 0, 0)
+        pairs = pairs[rng.permutation(len(pairs))]
+        pairs = np.concatenate([pairs, pairs[:5, ::-1]])
+        ne = [p for p in pairs if sizes[p[0]] > 0 and sizes[p[1]] > 0]
+        exp = dict(zip(map(tuple, ne), oc.match_pairs(bank, np.array(ne), 4, 0.8))) if ne else {}
+        matcher.upload_bank(bank)
+        for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_TENSOR_IMAD, sfm.ENGINE_SIMT):
+            res = matcher.match_pairs(pairs, NORM_L2, ratio=0.8, engine=eng)
+            for k, p in enumerate(map(tuple, pairs)):
+                want = exp.get(p, np.zeros(0, orc.DMATCH_DTYPE))
+                assert orc.dmatch_equal(res[k], want), (trial, eng, p, sizes)
+        # ORB-like with the same ragged sizes, both Hamming engines
+        ob, prev = [], None
+        for i, n in enumerate(sizes):
+            d = workloads.orb_like_image(100 * trial + i, n, prev if prev is not None and len(prev) else None)
+            ob.append(d)
+            prev = d
+        exp = dict(zip(map(tuple, ne), oc.match_pairs(ob, np.array(ne), 6, 0.8))) if ne else {}
+        matcher.upload_bank(ob)
+        for eng in (sfm.ENGINE_TENSOR, sfm.ENGINE_SIMT):
+            res = matcher.match_pairs(pairs, NORM_HAMMING, ratio=0.8, engine=eng)
+            for k, p in enumerate(map(tuple, pairs)):
+                want = exp.get(p, np.zeros(0, orc.DMATCH_DTYPE))
+                assert orc.dmatch_equal(res[k], want), (trial, eng, p, sizes)
