@@ -165,7 +165,7 @@ def run_reference(a):
     from oracle import cv2_ref
     from oracle.oracle_np import NORM_L2
     if not cv2_ref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "cv2 not importable on this box"}))
+        _emit(json.dumps({"impl": "reference", "unavailable": "cv2 not importable on this box"}))
         return
     pairs = make_pairs(None, a.images, a.seq, a.grid)
     cache = {}
@@ -200,7 +200,7 @@ def run_reference(a):
     v = n / dt
     sample = (f"each step = {per_step} random pairs of the workload (images 0..23), cv2 {cv2_ref.cv2.__version__} "
               f"batchDistance+ratio on {cores} host threads, topology '{topo}'")
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -250,7 +250,8 @@ def run_ours(a):
     host_list = [host_np[i * n_rows:(i + 1) * n_rows] for i in range(n_img)]
     del bank_dev
 
-    mine = shard.assign_pairs(pairs, rows_per, world)[rank]
+    all_mine = shard.assign_pairs(pairs, rows_per, world)
+    mine = all_mine[rank]
     my_pairs = np.ascontiguousarray(pairs[mine])
     stream = torch.cuda.ExternalStream(m.stream, device=dev)
 
@@ -303,6 +304,7 @@ def run_ours(a):
         s0 = m.stats()
         ps0 = packer.stats() if world > 1 else None
         t0 = time.perf_counter()
+        tr = [t0]
         if world == 1:
             m.upload_bank(host_list)                               # pinned CV_32F -> device, packed to u8 on the GPU
         else:
@@ -311,19 +313,27 @@ def run_ours(a):
             lo, hi = rank * n_img // world, (rank + 1) * n_img // world
             packer.upload_bank(host_list[lo:hi])
             ptr, _ = packer.bank_device_ptr(0)
-            part = _as_cuda_u8(ptr, (hi - lo) * n_rows * 128, dev)
+            part = shard.cuda_view(ptr, (hi - lo) * n_rows * 128, dev)
             parts = [gathered[r * n_img // world * n_rows * 128:(r + 1) * n_img // world * n_rows * 128] for r in range(world)]
             dist.all_gather(parts, part)
+            tr.append(time.perf_counter())
             m.upload_bank_device(gathered.data_ptr(), offs, rows_per, 128, sfm.CV_8U)
-        res = m.match_pairs(my_pairs, sfm.NORM_L2)                 # kernels + D2H of the compacted lists
-        if world > 1:
-            g = shard.gather_matches(mine, res.counts(), res.matches, res.dropped, len(pairs), dev, 0)
+        tr.append(time.perf_counter())
+        if world == 1:
+            res = m.match_pairs(my_pairs, sfm.NORM_L2)             # kernels + D2H of the compacted lists
+            total_matches = int(res.offsets[-1])
+            tr.append(time.perf_counter())
+        else:
+            m.enqueue(my_pairs, sfm.NORM_L2)                       # kernels; lists stay on the GPU ...
+            tr.append(time.perf_counter())
+            g = shard.gather_matches_device(m, mine, all_mine, len(pairs), dev, 0)   # ... NCCL gather, one D2H on rank 0
             if rank == 0:
                 total_matches = int(g[0][-1])
-        else:
-            total_matches = int(res.offsets[-1])
+        tr.append(time.perf_counter())
         barrier()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        if os.environ.get("SFM_BENCH_TRACE") and rank == 0:
+            print("e2e phases ms:", [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(tr[:-1], tr[1:])], file=sys.stderr)
         s1 = m.stats()
         h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
         if world > 1:
@@ -380,13 +390,22 @@ def run_ours(a):
             except Exception as ex:  # pragma: no cover
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                        "sample": f"failed: {ex}"}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     m.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; fd 1 is pointed at stderr for the rest of the run so that native
+    libraries (NCCL's version banner, ...) cannot pollute it."""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = apply_workload(parse())
     if args.impl == "reference":
         run_reference(args)

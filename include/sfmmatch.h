@@ -129,6 +129,12 @@ int sfm_match_pairs(sfm_ctx *ctx, const int32_t *pairs /* n_pairs x 2 */, int64_
  * leaves the compacted match lists in device memory; collect copies them to pinned host memory. */
 int sfm_match_pairs_enqueue(sfm_ctx *ctx, const int32_t *pairs, int64_t n_pairs, const sfm_opts *opts);
 int sfm_match_pairs_collect(sfm_ctx *ctx, sfm_result **out);
+/* Device-resident view of the last enqueue's result (valid until the next enqueue/upload on this context), for a
+ * multi-GPU host that gathers match lists GPU-to-GPU (ncclGather / torch.distributed) instead of through host memory:
+ * d_matches = total_matches sfm_dmatch records, d_pair_offsets = n_pairs int64 start offsets, d_dropped = n_pairs bytes.
+ * Waits for the enqueued kernels. */
+int sfm_match_pairs_device_view(sfm_ctx *ctx, const void **d_matches, const void **d_pair_offsets,
+                                const void **d_dropped, int64_t *n_pairs, int64_t *total_matches);
 
 int64_t           sfm_result_n_pairs(const sfm_result *r);
 const int64_t    *sfm_result_offsets(const sfm_result *r);   /* n_pairs + 1 entries */

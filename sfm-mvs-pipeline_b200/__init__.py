@@ -30,7 +30,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_ctx_stream", "sfm_bank_upload", "sfm_bank_upload_device", "sfm_bank_info", "sfm_select_pairs",
            "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
-           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr"]
+           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view"]
 
 
 class SfmError(RuntimeError):
@@ -220,6 +220,13 @@ class Matcher:
         finally:
             _lib.sfm_result_free(res)
         return MatchResult(offsets, matches, dropped)
+
+    def device_view(self):
+        """(d_matches_ptr, d_pair_offsets_ptr, d_dropped_ptr, n_pairs, total_matches) of the last enqueue."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, t = C.c_int64(), C.c_int64()
+        self._check(_lib.sfm_match_pairs_device_view(self._ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(n), C.byref(t)))
+        return int(a.value or 0), int(b.value or 0), int(c.value or 0), n.value, t.value
 
     def match_pairs(self, pairs, norm, **kw) -> MatchResult:
         self.enqueue(pairs, norm, **kw)

@@ -715,7 +715,13 @@ int sfm_bank_upload_device(sfm_ctx* c, int n_images, const void* dev_rows, const
     const size_t row_bytes = static_cast<size_t>(cols) * esz;
     DevBuf& dst = cv_depth == SFM_CV_32F ? b.d_f32 : b.d_u8;
     CU_TRY(c, dst.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * row_bytes)));
-    for (int i = 0; i < n_images; ++i) {
+    bool same_layout = true;          // source already laid out like the padded bank: one copy instead of n_images
+    for (int i = 0; i < n_images && same_layout; ++i) same_layout = row_offset[i] == b.row0[i];
+    if (same_layout && n_images > 0 && b.padded_rows > 0) {
+        const int64_t last = b.row0[n_images - 1] + n_rows[n_images - 1];
+        CU_TRY(c, cudaMemcpyAsync(dst.p, dev_rows, static_cast<size_t>(last) * row_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    for (int i = 0; i < n_images && !same_layout; ++i) {
         if (n_rows[i] == 0) continue;
         CU_TRY(c, cudaMemcpyAsync(static_cast<uint8_t*>(dst.p) + static_cast<size_t>(b.row0[i]) * row_bytes,
                                   static_cast<const uint8_t*>(dev_rows) + static_cast<size_t>(row_offset[i]) * row_bytes,
@@ -747,6 +753,25 @@ int sfm_match_pairs_enqueue(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, c
     CU_TRY(c, cudaSetDevice(c->device));
     c->run.valid = false;
     return enqueue_impl(c, pairs, n_pairs, opts);
+}
+
+int sfm_match_pairs_device_view(sfm_ctx* c, const void** d_matches, const void** d_pair_offsets, const void** d_dropped,
+                                int64_t* n_pairs, int64_t* total_matches) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->run.valid) return fail(c, SFM_ERR_STATE, "device view without a preceding enqueue");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int64_t* hs = c->h_scalars.as<int64_t>();
+    CU_TRY(c, cudaMemcpyAsync(hs, c->d_scalars.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stat_d2h += 16;
+    if (reinterpret_cast<int*>(hs)[2]) return fail(c, SFM_ERR_CAPACITY, "output capacity overflow: use sfm_match_pairs_collect (it retries)");
+    if (d_matches) *d_matches = c->d_out.p;
+    if (d_pair_offsets) *d_pair_offsets = c->d_pair_offsets.p;
+    if (d_dropped) *d_dropped = c->d_dropped.p;
+    if (n_pairs) *n_pairs = c->run.n_pairs;
+    if (total_matches) *total_matches = hs[0];
+    return SFM_OK;
 }
 
 int sfm_match_pairs_collect(sfm_ctx* c, sfm_result** out) {

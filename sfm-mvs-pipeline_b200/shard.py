@@ -94,5 +94,68 @@ def gather_matches(local_idx: np.ndarray, counts: np.ndarray, matches: np.ndarra
     return offsets, out, total_dropped
 
 
+def cuda_view(ptr: int, nbytes: int, device, dtype=None):
+    """torch view (no copy) of library-owned device memory."""
+    import torch
+
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (max(nbytes, 0),), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    t = torch.as_tensor(h, device=device) if nbytes > 0 else torch.zeros(0, dtype=torch.uint8, device=device)
+    return t if dtype is None else t.view(dtype)
+
+
+def gather_matches_device(matcher, local_idx, all_local_idx, n_pairs_total: int, device, dst: int = 0, group=None):
+    """GPU-to-GPU gather of the last enqueue's match lists (NCCL): per-rank device views from the library
+    (sfm_match_pairs_device_view) -> dist.gather of padded int32 payloads -> reassembly in global pair order on the
+    destination GPU -> ONE device-to-host copy on ``dst``.  ``all_local_idx`` = assign_pairs(...) for every rank
+    (known everywhere, so only the match totals need an all_gather).
+    Returns (offsets, matches, dropped) as numpy arrays on ``dst`` and None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    pm, po, pd, n_local, n_match = matcher.device_view()
+    tot = torch.tensor([n_match], dtype=torch.int64, device=device)
+    all_tot = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(all_tot, tot, group=group)
+    all_tot = torch.cat(all_tot).cpu().numpy()
+    max_local = max(len(x) for x in all_local_idx)
+    max_match = int(all_tot.max())
+    off = cuda_view(po, n_local * 8, device, torch.int64)
+    counts = torch.diff(off, append=tot).to(torch.int32)
+    dropped = cuda_view(pd, n_local, device).to(torch.int32)
+    m32 = cuda_view(pm, n_match * 16, device, torch.int32)
+    payload = torch.zeros(max(2 * max_local + 4 * max_match, 1), dtype=torch.int32, device=device)
+    payload[:n_local] = counts
+    payload[max_local:max_local + n_local] = dropped
+    payload[2 * max_local:2 * max_local + 4 * n_match] = m32
+    gathered = [torch.zeros_like(payload) for _ in range(world)] if rank == dst else None
+    dist.gather(payload, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    total_counts = torch.zeros(n_pairs_total, dtype=torch.int64, device=device)
+    total_dropped = torch.zeros(n_pairs_total, dtype=torch.uint8, device=device)
+    idx_dev = [torch.from_numpy(np.asarray(x, np.int64)).to(device) for x in all_local_idx]
+    for r in range(world):
+        nl = len(all_local_idx[r])
+        total_counts[idx_dev[r]] = gathered[r][:nl].to(torch.int64)
+        total_dropped[idx_dev[r]] = gathered[r][max_local:max_local + nl].to(torch.uint8)
+    offsets = torch.zeros(n_pairs_total + 1, dtype=torch.int64, device=device)
+    offsets[1:] = torch.cumsum(total_counts, 0)
+    out = torch.zeros((int(all_tot.sum()), 4), dtype=torch.int32, device=device)
+    for r in range(world):
+        nl, nm = len(all_local_idx[r]), int(all_tot[r])
+        if nm == 0:
+            continue
+        cnt = gathered[r][:nl].to(torch.int64)
+        src_off = torch.cumsum(cnt, 0) - cnt
+        dst_idx = torch.repeat_interleave(offsets[idx_dev[r]] - src_off, cnt) + torch.arange(nm, device=device)
+        out[dst_idx] = gathered[r][2 * max_local:2 * max_local + 4 * nm].view(nm, 4)
+    matches = out.cpu().numpy().view(_dmatch_dtype()).reshape(-1)
+    return offsets.cpu().numpy(), matches, total_dropped.cpu().numpy()
+
+
 def _dmatch_dtype():
     return np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])

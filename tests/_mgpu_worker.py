@@ -41,11 +41,17 @@ def main():
     mine = shard.assign_pairs(pairs, sizes, world)[rank]
     res = m.match_pairs(pairs[mine], sfm.NORM_L2, min_match_count=20)
     g = shard.gather_matches(mine, res.counts(), res.matches, res.dropped, len(pairs), dev, 0)
+    # the GPU-to-GPU gather of the device-resident result must give the same answer
+    all_mine = shard.assign_pairs(pairs, sizes, world)
+    m.enqueue(pairs[mine], sfm.NORM_L2, min_match_count=20)
+    g2 = shard.gather_matches_device(m, mine, all_mine, len(pairs), dev, 0)
     ok = True
     if rank == 0:
         full = m.match_pairs(pairs, sfm.NORM_L2, min_match_count=20)
         ok = (np.array_equal(g[0], full.offsets) and g[1].tobytes() == full.matches.tobytes()
               and np.array_equal(g[2], full.dropped))
+        ok = ok and (np.array_equal(g2[0], full.offsets) and g2[1].tobytes() == full.matches.tobytes()
+                     and np.array_equal(g2[2], full.dropped))
         print("MGPU_IDENTICAL" if ok else "MGPU_MISMATCH", int(full.offsets[-1]), flush=True)
     m.close()
     dist.barrier()
