@@ -306,7 +306,7 @@ def run_ours(a):
         t0 = time.perf_counter()
         tr = [t0]
         if world == 1:
-            m.upload_bank(host_list)                               # pinned CV_32F -> device, packed to u8 on the GPU
+            pass                                                   # upload is part of the fused call below
         else:
             # every rank uploads + packs 1/N of the scene over its own PCIe link, NCCL all-gathers the packed
             # u8 bank over NVLink, the library adopts the replica (sfm_bank_upload_device)
@@ -320,7 +320,9 @@ def run_ours(a):
             m.upload_bank_device(gathered.data_ptr(), offs, rows_per, 128, sfm.CV_8U)
         tr.append(time.perf_counter())
         if world == 1:
-            res = m.match_pairs(my_pairs, sfm.NORM_L2)             # kernels + D2H of the compacted lists
+            # sfm_match_pairs_from_host: pinned CV_32F descriptors -> device (packed to u8 on the GPU, group by group,
+            # overlapped with the matching of resident pairs) -> kernels -> D2H of the compacted lists
+            res = m.match_pairs_from_host(host_list, my_pairs, sfm.NORM_L2)
             total_matches = int(res.offsets[-1])
             tr.append(time.perf_counter())
         else:

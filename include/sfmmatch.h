@@ -136,6 +136,14 @@ int sfm_match_pairs_collect(sfm_ctx *ctx, sfm_result **out);
 int sfm_match_pairs_device_view(sfm_ctx *ctx, const void **d_matches, const void **d_pair_offsets,
                                 const void **d_dropped, int64_t *n_pairs, int64_t *total_matches);
 
+/* sfm_bank_upload + sfm_match_pairs as ONE call = the whole of IFeatureMatchingStrategy::calculateShotMatches
+ * (descriptors of every shot in host memory in, per-pair DMatch lists out).  When the descriptor matrices are
+ * page-locked and 128 columns wide, the upload of image groups overlaps the matching of the pairs that are already
+ * resident; results are identical to the two-call form (input pair order).  The bank stays resident afterwards. */
+int sfm_match_pairs_from_host(sfm_ctx *ctx, int n_images, const void *const *rows, const int32_t *n_rows, int cols,
+                              const size_t *step_bytes, int cv_depth, const int32_t *pairs, int64_t n_pairs,
+                              const sfm_opts *opts, sfm_result **out);
+
 int64_t           sfm_result_n_pairs(const sfm_result *r);
 const int64_t    *sfm_result_offsets(const sfm_result *r);   /* n_pairs + 1 entries */
 const sfm_dmatch *sfm_result_matches(const sfm_result *r);   /* offsets[n_pairs] entries */

@@ -30,7 +30,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_ctx_stream", "sfm_bank_upload", "sfm_bank_upload_device", "sfm_bank_info", "sfm_select_pairs",
            "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
-           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view"]
+           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view", "sfm_match_pairs_from_host"]
 
 
 class SfmError(RuntimeError):
@@ -203,9 +203,40 @@ class Matcher:
         self._check(_lib.sfm_match_pairs_enqueue(self._ctx, pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
                                                  C.byref(o)))
 
+    def _bank_args(self, descriptors):
+        n = len(descriptors)
+        depth = _depth_of(descriptors[0])
+        cols = descriptors[0].shape[1]
+        keep = []
+        for d in descriptors:
+            if d.ndim != 2 or d.shape[1] != cols or _depth_of(d) != depth:
+                raise SfmError(ERR_INVALID, "all descriptor matrices must share dtype and width")
+            if d.strides[1] != d.itemsize:
+                d = np.ascontiguousarray(d)
+            keep.append(d)
+        ptrs = (C.c_void_p * n)(*[d.ctypes.data if d.shape[0] else None for d in keep])
+        nrows = (C.c_int32 * n)(*[d.shape[0] for d in keep])
+        steps = (C.c_size_t * n)(*[d.strides[0] if d.shape[0] > 1 else cols * d.itemsize for d in keep])
+        return keep, ptrs, nrows, steps, cols, depth
+
+    def match_pairs_from_host(self, descriptors, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False,
+                              min_match_count=0, engine=ENGINE_AUTO) -> MatchResult:
+        """Upload + match + collect in one call (pipelined when the arrays are page-locked, 128 wide)."""
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        keep, ptrs, nrows, steps, cols, depth = self._bank_args(descriptors)
+        o = self._opts(norm, k, ratio, cross_check, distinct, min_match_count, engine)
+        res = C.c_void_p()
+        self._check(_lib.sfm_match_pairs_from_host(self._ctx, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps,
+                                                   C.c_int(depth), pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
+                                                   C.byref(o), C.byref(res)))
+        return self._wrap_result(res)
+
     def collect(self) -> MatchResult:
         res = C.c_void_p()
         self._check(_lib.sfm_match_pairs_collect(self._ctx, C.byref(res)))
+        return self._wrap_result(res)
+
+    def _wrap_result(self, res) -> MatchResult:
         try:
             n = _lib.sfm_result_n_pairs(res)
             offsets = np.ctypeslib.as_array(_lib.sfm_result_offsets(res), shape=(n + 1,)).copy()

@@ -89,6 +89,10 @@ cudaError_t launch_scan_offsets(const int32_t* chunk_counts, int64_t n_chunks, c
 cudaError_t launch_compact(const FilterArgs& a, const int64_t* chunk_excl, const int64_t* pair_offsets,
                            const uint8_t* pair_dropped, DMatch* out, int64_t out_capacity, int* overflow_flag,
                            cudaStream_t s);
+// schedule order -> input pair order (pipelined host path)
+cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
+                           const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,
+                           uint8_t* drop_in, cudaStream_t s);
 // raw knn result -> cv::batchDistance-shaped arrays (sfm_knn_match)
 cudaError_t launch_top2_to_arrays(const Top2* top2, int nq, int k, int norm, int32_t* nidx, float* dist, cudaStream_t s);
 

@@ -499,6 +499,44 @@ cudaError_t launch_scan_offsets(const int32_t* chunk_counts, int64_t n_chunks, c
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ reorder
+// The pipelined host path schedules pairs by availability of their images, so the compacted lists come out in
+// schedule order; these three passes bring them back to INPUT pair order (order[k] = input index of scheduled pair k).
+__global__ void reorder_counts_kernel(const int64_t* __restrict__ off_s, const int64_t* __restrict__ total,
+                                      const int64_t* __restrict__ order, int64_t n, int64_t* __restrict__ cnt_in) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t end = k + 1 < n ? off_s[k + 1] : *total;
+    cnt_in[order[k]] = end - off_s[k];
+}
+__global__ void __launch_bounds__(1024) reorder_scan_kernel(const int64_t* __restrict__ cnt_in, int64_t n,
+                                                            int64_t* __restrict__ off_in) {
+    block_exclusive_scan(n, [&](int64_t i) { return cnt_in[i]; }, [&](int64_t i, int64_t e) { off_in[i] = e; });
+}
+__global__ void reorder_copy_kernel(const DMatch* __restrict__ src, const int64_t* __restrict__ off_s,
+                                    const int64_t* __restrict__ total, const int64_t* __restrict__ order,
+                                    const int64_t* __restrict__ off_in, const uint8_t* __restrict__ drop_s, int64_t n,
+                                    DMatch* __restrict__ dst, uint8_t* __restrict__ drop_in) {
+    const int64_t k = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;   // one warp per pair
+    const int lane = threadIdx.x & 31;
+    if (k >= n) return;
+    const int64_t p = order[k];
+    const int64_t s0 = off_s[k], cnt = (k + 1 < n ? off_s[k + 1] : *total) - s0, d0 = off_in[p];
+    for (int64_t i = lane; i < cnt; i += 32) dst[d0 + i] = src[s0 + i];
+    if (lane == 0) drop_in[p] = drop_s[k];
+}
+
+cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
+                           const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,
+                           uint8_t* drop_in, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    reorder_counts_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(off_s, total, order, n, cnt_tmp);
+    reorder_scan_kernel<<<1, 1024, 0, s>>>(cnt_tmp, n, off_in);
+    reorder_copy_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, s>>>(src, off_s, total, order, off_in, drop_s,
+                                                                                    n, dst, drop_in);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ knnMatch arrays
 __global__ void top2_to_arrays_kernel(const Top2* __restrict__ top2, int nq, int k, int norm, int32_t* __restrict__ nidx,
                                       float* __restrict__ dist) {

@@ -104,6 +104,9 @@ struct sfm_ctx {
     DevBuf d_top2, d_rev, d_train_cnt, d_chunk_counts, d_chunk_excl, d_pair_counts, d_pair_offsets, d_dropped;
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
+    DevBuf d_out2, d_pair_offsets2, d_dropped2, d_order, d_cnt_tmp;   // reorder targets of the pipelined host path
+    cudaStream_t copy_stream = nullptr;                               // uploads of the pipelined host path
+    std::vector<cudaEvent_t> group_ev;                                // image group g is resident + packed
     int64_t out_capacity = 0;
     PinBuf h_meta, h_stage[2], h_scalars, h_knn, h_valid;
     std::vector<sfm_result*> result_pool;   // recycled results (pinned buffers are expensive to allocate)
@@ -375,8 +378,27 @@ int rows_per_unit(Engine e) {
     return e == Engine::F32 ? kF32RowsPerUnit : ((e == Engine::TC || e == Engine::TCV) ? kTcRowsPerUnit : kSimtRowsPerUnit);
 }
 
-int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o) {
+// Optional processing schedule of enqueue_impl (pipelined host path): order[k] = input index of the k-th scheduled
+// pair, avail[k] = index of the event (non-decreasing in k) the batch containing k has to wait for.
+struct Schedule {
+    const int64_t* order = nullptr;
+    const int* avail = nullptr;
+    const cudaEvent_t* events = nullptr;
+};
+
+int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm_opts* o, const Schedule* sched = nullptr) {
     Bank& b = c->bank;
+    const int32_t* pairs = pairs_in;
+    std::vector<int32_t> scheduled;
+    if (sched && sched->order && n_pairs > 0) {
+        if (!pairs_in) return fail(c, SFM_ERR_INVALID, "bad pair list");
+        scheduled.resize(2 * n_pairs);
+        for (int64_t k = 0; k < n_pairs; ++k) {
+            scheduled[2 * k] = pairs_in[2 * sched->order[k]];
+            scheduled[2 * k + 1] = pairs_in[2 * sched->order[k] + 1];
+        }
+        pairs = scheduled.data();           // from here on "pair p" means schedule position p
+    }
     if (b.n_images == 0 && n_pairs > 0) return fail(c, SFM_ERR_STATE, "match_pairs before bank upload");
     if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(c, SFM_ERR_INVALID, "bad pair list");
     if (n_pairs >= (int64_t(1) << 31)) return fail(c, SFM_ERR_CAPACITY, "too many pairs");
@@ -411,7 +433,8 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
         Batch cur{0, 0, 0, 0, 0, 0};
         for (int64_t p = 0; p < n_pairs; ++p) {
             const int64_t q = pad_rows(b.n_rows[pairs[2 * p]]), t = pad_rows(b.n_rows[pairs[2 * p + 1]]);
-            if (cur.p1 > cur.p0 && (cur.staged_rows + q > static_cast<int64_t>(c->staging_budget_rows) ||
+            const bool avail_break = sched && sched->avail && p > 0 && sched->avail[p] != sched->avail[p - 1];
+            if (cur.p1 > cur.p0 && (avail_break || cur.staged_rows + q > static_cast<int64_t>(c->staging_budget_rows) ||
                                     cur.t_rows + t > static_cast<int64_t>(c->staging_budget_rows))) {
                 batches.push_back(cur);
                 cur = Batch{p, p, 0, 0, 0, 0};
@@ -532,6 +555,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
         const Batch& B = batches[bi];
         const int np = static_cast<int>(B.p1 - B.p0);
         const int64_t base = B.p0 + bi;
+        if (sched && sched->avail && sched->events) CU_TRY(c, cudaStreamWaitEvent(s, sched->events[sched->avail[B.p0]], 0));
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
         rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>());
         if (rc != SFM_OK) return rc;
@@ -567,6 +591,24 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_op
         c->stat_launches += 3;
         if (c->profiling) { CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 2], s)); c->prof_used = static_cast<int>(3 * (bi + 1)); }
     }
+    if (sched && sched->order && n_pairs > 0) {
+        // schedule order -> input order (swap the buffers so that collect / device_view see input order)
+        CU_TRY(c, c->d_order.ensure(static_cast<size_t>(n_pairs) * 8));
+        CU_TRY(c, cudaMemcpyAsync(c->d_order.p, sched->order, static_cast<size_t>(n_pairs) * 8, cudaMemcpyHostToDevice, s));
+        CU_TRY(c, c->d_cnt_tmp.ensure(static_cast<size_t>(n_pairs) * 8));
+        CU_TRY(c, c->d_pair_offsets2.ensure(static_cast<size_t>(n_pairs) * 8));
+        CU_TRY(c, c->d_dropped2.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs))));
+        CU_TRY(c, c->d_out2.ensure(static_cast<size_t>(c->out_capacity) * sizeof(DMatch)));
+        CU_TRY(c, launch_reorder(c->d_out.as<DMatch>(), c->d_pair_offsets.as<int64_t>(), d_total, c->d_order.as<int64_t>(),
+                                 c->d_dropped.as<uint8_t>(), n_pairs, c->d_cnt_tmp.as<int64_t>(),
+                                 c->d_pair_offsets2.as<int64_t>(), c->d_out2.as<DMatch>(), c->d_dropped2.as<uint8_t>(), s));
+        c->stat_launches += 3;
+        CU_TRY(c, cudaStreamSynchronize(s));          // sched->order is caller-owned host memory
+        std::swap(c->d_out, c->d_out2);
+        std::swap(c->d_pair_offsets, c->d_pair_offsets2);
+        std::swap(c->d_dropped, c->d_dropped2);
+    }
+    pairs = pairs_in;
     c->run.valid = true;
     c->run.n_pairs = n_pairs;
     c->run.total_query_rows = total_q;
@@ -619,6 +661,147 @@ int collect_impl(sfm_ctx* c, sfm_result** out) {
     return fail(c, SFM_ERR_CAPACITY, "unreachable");
 }
 
+// ------------------------------------------------------------------------------------------------ pipelined host path
+// sfm_match_pairs_from_host: upload + match + collect as one call.  With page-locked 128-column descriptors the images
+// are uploaded in groups on a copy stream (H2D, pack to u8, norms/keys/digits per group, one event per group) while the
+// compute stream already matches the pairs whose two images are resident; pairs are scheduled by availability and the
+// lists are brought back to input order at the end.  Bank properties (integer-valued, norm range) are assumed and
+// verified after the fact; if the assumption fails the call falls back to the sequential path.
+int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                   const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
+                   sfm_result** out) {
+    auto sequential = [&]() -> int {
+        int rc = bank_upload_host(c, c->bank, n_images, rows, n_rows, cols, step_bytes, depth);
+        if (rc != SFM_OK) return rc;
+        rc = enqueue_impl(c, pairs, n_pairs, o);
+        if (rc != SFM_OK) return rc;
+        return collect_impl(c, out);
+    };
+    bool pipelined = cols == 128 && (depth == SFM_CV_32F || depth == SFM_CV_8U) && o->norm == SFM_NORM_L2 && o->k == 2 &&
+                     !o->cross_check && (o->engine == SFM_ENGINE_AUTO || o->engine == SFM_ENGINE_TENSOR) &&
+                     n_images >= 16 && n_pairs > 0 && pairs && rows && n_rows;
+    const size_t esz = depth == SFM_CV_32F ? 4 : 1;
+    const size_t row_bytes = static_cast<size_t>(cols) * esz;
+    for (int i = 0; pipelined && i < n_images; ++i) {
+        if (n_rows[i] < 0 || n_rows[i] > 32768) { pipelined = false; break; }
+        if (n_rows[i] == 0) continue;
+        cudaPointerAttributes attr;
+        if (!rows[i] || cudaPointerGetAttributes(&attr, rows[i]) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            pipelined = false;
+        }
+        if (step_bytes && step_bytes[i] < row_bytes) pipelined = false;
+    }
+    for (int64_t p = 0; pipelined && p < n_pairs; ++p) {
+        const int l = pairs[2 * p], r = pairs[2 * p + 1];
+        if (l < 0 || r < 0 || l >= n_images || r >= n_images) pipelined = false;       // let the sequential path report it
+    }
+    if (!pipelined) return sequential();
+
+    Bank& b = c->bank;
+    int rc = bank_layout(c, b, n_images, n_rows, cols, depth);
+    if (rc != SFM_OK) return rc;
+    if (b.padded_rows == 0) return sequential();
+    cudaStream_t cs = c->copy_stream, s = c->stream;
+    CU_TRY(c, cudaStreamSynchronize(s));                  // earlier work may still read the buffers we are about to refill
+    // ---- buffers + valid table
+    const int64_t nblk = b.padded_rows / kRowAlign;
+    CU_TRY(c, cudaEventSynchronize(c->valid_ev));
+    CU_TRY(c, c->h_valid.ensure(static_cast<size_t>(nblk) * 4));
+    int32_t* valid = c->h_valid.as<int32_t>();
+    for (int i = 0; i < n_images; ++i) {
+        const int64_t b0 = b.row0[i] / kRowAlign, nbk = pad_rows(b.n_rows[i]) / kRowAlign;
+        for (int64_t k = 0; k < nbk; ++k)
+            valid[b0 + k] = static_cast<int32_t>(std::min<int64_t>(kRowAlign, std::max<int64_t>(0, b.n_rows[i] - k * kRowAlign)));
+    }
+    CU_TRY(c, b.d_valid.ensure(static_cast<size_t>(nblk) * 4));
+    CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
+    if (depth == SFM_CV_32F) CU_TRY(c, b.d_f32.ensure(static_cast<size_t>(b.padded_rows) * 512));
+    CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
+    CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
+    CU_TRY(c, b.d_ext.ensure(static_cast<size_t>(b.padded_rows) * kExtBytes));
+    CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid, static_cast<size_t>(nblk) * 4, cudaMemcpyHostToDevice, cs));
+    CU_TRY(c, cudaEventRecord(c->valid_ev, cs));
+    int* flags = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 16);
+    CU_TRY(c, cudaMemsetAsync(flags, 0, 8, cs));
+    // optimistic bank properties (verified below)
+    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true;
+    rc = make_tmaps(c, b);
+    if (rc != SFM_OK) return rc;
+    // ---- image groups of roughly equal size
+    const int n_groups = std::min(8, n_images / 2);
+    std::vector<int> group_of(n_images);
+    std::vector<int> group_end(n_groups);
+    {
+        int g = 0;
+        for (int i = 0; i < n_images; ++i) {
+            group_of[i] = g;
+            group_end[g] = i + 1;
+            if (b.row0[i + 1] * n_groups >= b.padded_rows * (g + 1) && g + 1 < n_groups && i + 1 < n_images) ++g;
+        }
+        for (int k = g + 1; k < n_groups; ++k) group_end[k] = n_images;
+    }
+    while (static_cast<int>(c->group_ev.size()) < n_groups) {
+        cudaEvent_t ev;
+        CU_TRY(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->group_ev.push_back(ev);
+    }
+    const int32_t* d_valid = b.d_valid.as<int32_t>();
+    int first = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int last = group_end[g];
+        const int64_t r0 = b.row0[first], r1 = b.row0[last];
+        uint8_t* dst = static_cast<uint8_t*>(depth == SFM_CV_32F ? b.d_f32.p : b.d_u8.p);
+        for (int i = first; i < last; ++i) {
+            if (n_rows[i] == 0) continue;
+            const size_t step = step_bytes ? step_bytes[i] : row_bytes;
+            uint8_t* d_img = dst + static_cast<size_t>(b.row0[i]) * row_bytes;
+            if (step == row_bytes)
+                CU_TRY(c, cudaMemcpyAsync(d_img, rows[i], static_cast<size_t>(n_rows[i]) * row_bytes, cudaMemcpyHostToDevice, cs));
+            else
+                CU_TRY(c, cudaMemcpy2DAsync(d_img, row_bytes, rows[i], step, row_bytes, static_cast<size_t>(n_rows[i]),
+                                            cudaMemcpyHostToDevice, cs));
+            c->stat_h2d += static_cast<int64_t>(n_rows[i]) * static_cast<int64_t>(row_bytes);
+        }
+        if (r1 > r0) {
+            if (depth == SFM_CV_32F)
+                CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>() + r0 * 128, 128, static_cast<int>(r1 - r0), 128,
+                                                d_valid + r0 / kRowAlign, b.d_u8.as<uint8_t>() + r0 * 128, flags, cs));
+            else
+                CU_TRY(c, launch_zero_padding(b.d_u8.as<uint8_t>() + r0 * 128, 128, r1 - r0, d_valid + r0 / kRowAlign, cs));
+            CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>() + r0 * 128, r1 - r0, d_valid + r0 / kRowAlign,
+                                         b.d_norm2.as<int32_t>() + r0, b.d_ckey.as<int32_t>() + r0,
+                                         b.d_ext.as<int8_t>() + r0 * kExtBytes, flags + 1, cs));
+            c->stat_launches += 2;
+        }
+        CU_TRY(c, cudaEventRecord(c->group_ev[g], cs));
+        first = last;
+    }
+    int* h = c->h_scalars.as<int>() + 8;
+    CU_TRY(c, cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, cs));
+    // ---- schedule pairs by the group that completes them
+    std::vector<int64_t> order(n_pairs);
+    std::vector<int> avail_in(n_pairs), avail(n_pairs);
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        order[p] = p;
+        avail_in[p] = std::max(group_of[pairs[2 * p]], group_of[pairs[2 * p + 1]]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return avail_in[x] < avail_in[y]; });
+    for (int64_t k = 0; k < n_pairs; ++k) avail[k] = avail_in[order[k]];
+    Schedule sc;
+    sc.order = order.data(); sc.avail = avail.data(); sc.events = c->group_ev.data();
+    rc = enqueue_impl(c, pairs, n_pairs, o, &sc);
+    CU_TRY(c, cudaStreamSynchronize(cs));
+    if (rc != SFM_OK) return rc;
+    if (h[0] != 0 || h[1] > kExtMaxNorm2) {
+        // not integer-valued, or norms beyond the digit range: the optimistic run is void -> sequential path
+        CU_TRY(c, cudaStreamSynchronize(s));
+        c->run.valid = false;
+        return sequential();
+    }
+    return collect_impl(c, out);
+}
+
 }  // namespace
 
 // ==================================================================================================== C ABI
@@ -648,6 +831,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     c->sm_count = prop.multiProcessorCount;
     auto bail = [&](const std::string& m) { g_create_error = m; sfm_ctx_destroy(c); return SFM_ERR_CUDA; };
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     for (int k = 0; k < 2; ++k)
         if ((e = cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&c->meta_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
@@ -674,7 +858,8 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     c->bank.release(); c->scratch.release();
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
                       &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
-                      &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn};
+                      &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
+                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp};
     for (DevBuf* b : bufs) b->release();
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
@@ -683,6 +868,8 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     for (sfm_result* r : c->result_pool) { r->offsets.release(); r->matches.release(); r->dropped.release(); delete r; }
     c->h_valid.release();
     for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->group_ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -785,6 +972,17 @@ int sfm_match_pairs(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm
     int rc = sfm_match_pairs_enqueue(c, pairs, n_pairs, opts);
     if (rc != SFM_OK) return rc;
     return sfm_match_pairs_collect(c, out);
+}
+
+int sfm_match_pairs_from_host(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                              const size_t* step_bytes, int cv_depth, const int32_t* pairs, int64_t n_pairs,
+                              const sfm_opts* opts, sfm_result** out) {
+    if (!c || !opts || !out) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (n_images > 0 && (!rows || !n_rows)) return fail(c, SFM_ERR_INVALID, "bank: null arrays");
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    return from_host_impl(c, n_images, rows, n_rows, cols, step_bytes, cv_depth, pairs, n_pairs, opts, out);
 }
 
 int64_t sfm_result_n_pairs(const sfm_result* r) { return r ? r->n_pairs : 0; }

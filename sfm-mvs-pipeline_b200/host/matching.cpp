@@ -84,7 +84,6 @@ void IFeatureMatchingStrategy::calculateShotMatches(const Scene& scene, std::sha
         nrows[i] = d.empty() ? 0 : d.rows;
         steps[i] = d.step ? d.step : static_cast<std::size_t>(cols) * esz;
     }
-    check(ctx, sfm_bank_upload(ctx, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(), depth));
     std::vector<int32_t> flat(pl.size() * 2);
     for (std::size_t p = 0; p < pl.size(); ++p) { flat[2 * p] = pl[p].first; flat[2 * p + 1] = pl[p].second; }
     sfm_opts o;
@@ -95,7 +94,9 @@ void IFeatureMatchingStrategy::calculateShotMatches(const Scene& scene, std::sha
     o.distinct = stage_.distinct ? 1 : 0;
     o.min_match_count = stage_.minMatchCount;
     sfm_result* res = nullptr;
-    check(ctx, sfm_match_pairs(ctx, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
+    // one call for the whole scene: bank upload (pipelined with the matching when the Mats are page-locked) + all pairs
+    check(ctx, sfm_match_pairs_from_host(ctx, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(),
+                                         depth, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
     const int64_t* off = sfm_result_offsets(res);
     const sfm_dmatch* m = sfm_result_matches(res);
     const uint8_t* dr = sfm_result_dropped(res);

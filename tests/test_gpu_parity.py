@@ -362,3 +362,41 @@ def test_randomised_ragged_banks_all_engines(sfm, matcher):
             for k, p in enumerate(map(tuple, pairs)):
                 want = exp.get(p, np.zeros(0, orc.DMATCH_DTYPE))
                 assert orc.dmatch_equal(res[k], want), (trial, eng, p, sizes)
+
+
+def test_pipelined_from_host_equals_two_call_form(sfm, matcher):
+    """sfm_match_pairs_from_host (upload of image groups overlapped with matching, pairs scheduled by availability,
+    lists re-ordered on the device) must return byte-identical results to sfm_bank_upload + sfm_match_pairs."""
+    import torch
+    rng = np.random.default_rng(5)
+    sizes = [int(x) for x in rng.integers(0, 900, size=21)] + [0, 1, 257]
+    bank, prev = [], None
+    for i, n in enumerate(sizes):
+        d = workloads.sift_like_image(i, n, prev if prev is not None and len(prev) else None)
+        bank.append(d)
+        prev = d
+    pairs = sfm.select_pairs(len(bank), 0, 0)
+    pairs = pairs[rng.permutation(len(pairs))]
+    matcher.upload_bank(bank)
+    ref = matcher.match_pairs(pairs, NORM_L2, min_match_count=3)
+    for dtype in (np.float32, np.uint8):
+        pinned = [torch.from_numpy(b.astype(dtype)).pin_memory() for b in bank]
+        arrs = [p.numpy() for p in pinned]
+        got = matcher.match_pairs_from_host(arrs, pairs, NORM_L2, min_match_count=3)          # pipelined path
+        assert np.array_equal(got.offsets, ref.offsets) and got.matches.tobytes() == ref.matches.tobytes()
+        assert np.array_equal(got.dropped, ref.dropped)
+        again = matcher.match_pairs(pairs, NORM_L2, min_match_count=3)                        # the bank stays resident
+        assert again.matches.tobytes() == ref.matches.tobytes()
+    got = matcher.match_pairs_from_host([b.astype(np.float32) for b in bank], pairs, NORM_L2, min_match_count=3)
+    assert got.matches.tobytes() == ref.matches.tobytes()                                    # pageable -> sequential path
+    # optimistic assumption violated (non-integer floats / huge norms): falls back, still equals the two-call result
+    fl = [torch.from_numpy((b.astype(np.float32) * 0.37)).pin_memory() for b in bank]
+    matcher.upload_bank([f.numpy() for f in fl])
+    ref2 = matcher.match_pairs(pairs[:40], NORM_L2)
+    got2 = matcher.match_pairs_from_host([f.numpy() for f in fl], pairs[:40], NORM_L2)
+    assert got2.matches.tobytes() == ref2.matches.tobytes()
+    big = [torch.from_numpy(rng.integers(0, 256, size=(max(n, 1), 128), dtype=np.uint8)).pin_memory() for n in sizes]
+    matcher.upload_bank([x.numpy() for x in big])
+    ref3 = matcher.match_pairs(pairs[:40], NORM_L2, ratio=0.95)
+    got3 = matcher.match_pairs_from_host([x.numpy() for x in big], pairs[:40], NORM_L2, ratio=0.95)
+    assert got3.matches.tobytes() == ref3.matches.tobytes()
