@@ -151,6 +151,9 @@ const uint8_t    *sfm_result_dropped(const sfm_result *r);   /* n_pairs flags: 1
 void              sfm_result_free(sfm_result *r);       /* call before sfm_ctx_destroy of the producing context */
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* Non-integer CV_32F descriptors (3xTF32 tcgen05 candidate search + exact fp32 re-rank): how many query rows the
+ * last run re-ranked in fp32 and how many of those failed the exactness certificate and were brute-forced. */
+int sfm_last_float_stats(sfm_ctx *ctx, int64_t *rows_reranked, int64_t *rows_brute_forced);
 
 /* Per-kernel device timing of the last enqueue (CUDA events on the context stream around the knn kernel and
  * around the filter/scan/compact kernels of every batch).  Measurement aid for bench.py's roofline block. */

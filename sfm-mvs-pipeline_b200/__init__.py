@@ -30,7 +30,8 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_ctx_stream", "sfm_bank_upload", "sfm_bank_upload_device", "sfm_bank_info", "sfm_select_pairs",
            "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
-           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view", "sfm_match_pairs_from_host"]
+           "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view", "sfm_match_pairs_from_host",
+           "sfm_last_float_stats"]
 
 
 class SfmError(RuntimeError):
@@ -140,6 +141,12 @@ class Matcher:
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.sfm_last_stats(self._ctx, C.byref(a), C.byref(b), C.byref(c))
         return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+    def float_stats(self):
+        """Non-integer CV_32F runs: rows re-ranked in fp32 / rows that failed the certificate (brute-forced)."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(_lib.sfm_last_float_stats(self._ctx, C.byref(a), C.byref(b)))
+        return {"rows_reranked": a.value, "rows_brute_forced": b.value}
 
     def set_profiling(self, on: bool):
         self._check(_lib.sfm_set_profiling(self._ctx, C.c_int(1 if on else 0)))

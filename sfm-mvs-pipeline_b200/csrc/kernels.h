@@ -30,6 +30,11 @@ cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_ho
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
                                   Top2* out, int sm_count, int groups, cudaStream_t s);
 
+// ---- knn_l2_tf32.cu  (tcgen05 kind::tf32, 3xTF32 candidate search for non-integer float descriptors)
+cudaError_t launch_knn2_l2_f32_tc3(const void* tmaps /* 5 CUtensorMap: hi_a, lo_a, hi_b, lo_b, ext */, const PairDesc* pairs,
+                                   const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, float* aux,
+                                   int sm_count, cudaStream_t s);
+
 // ---- post.cu
 cudaError_t launch_pack_f32_to_u8(const float* src, size_t src_stride_elems, int n_rows, int cols,
                                   const int32_t* valid_in_block, uint8_t* dst, int* not_integer_flag, cudaStream_t s);
@@ -89,6 +94,25 @@ cudaError_t launch_scan_offsets(const int32_t* chunk_counts, int64_t n_chunks, c
 cudaError_t launch_compact(const FilterArgs& a, const int64_t* chunk_excl, const int64_t* pair_offsets,
                            const uint8_t* pair_dropped, DMatch* out, int64_t out_capacity, int* overflow_flag,
                            cudaStream_t s);
+// float path: hi/lo split + norms + norm K-step rows; exact fp32 re-rank with certificate
+cudaError_t launch_f32_split(const float* bank, int64_t padded_rows, const int32_t* valid_in_block, float* hi, float* lo,
+                             float* fnorm2, float* ext, int* max_norm_bits, cudaStream_t s);
+struct RefineF32Args {
+    Top2* top2;
+    const float* aux;            // fifth-best chunk maximum per staged row
+    const PairDesc* pairs;
+    const int64_t* out_prefix;
+    int n_pairs;
+    int64_t staged_rows;
+    const float* bank;           // fp32 bank, 128 floats per row
+    const float* fnorm2;
+    float nb_max;                // largest |b|^2 of the bank (error bound)
+    int all_rows;
+    unsigned long long* stats;   // [0] rows re-ranked, [1] rows brute-forced (certificate failed)
+    int swap_roles;              // cross-check pass: train rows query the left image (rows laid out by t_prefix)
+    double ratio;
+};
+cudaError_t launch_refine_f32(const RefineF32Args& a, cudaStream_t s);
 // schedule order -> input pair order (pipelined host path)
 cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
                            const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,

@@ -499,6 +499,164 @@ cudaError_t launch_scan_offsets(const int32_t* chunk_counts, int64_t n_chunks, c
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ float (3xTF32) path
+// Split every fp32 bank row into hi = tf32(x) and lo = x - hi, its squared norm, and the three tf32-exact pieces of
+// -|b|^2/2 that the norm K step of knn2_l2_f32_tc3_kernel multiplies with {1,1,1}.  One warp per 128-float row.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void f32_split_kernel(const float* __restrict__ bank, int64_t padded_rows,
+                                 const int32_t* __restrict__ valid_in_block, float* __restrict__ hi, float* __restrict__ lo,
+                                 float* __restrict__ fnorm2, float* __restrict__ ext, int* __restrict__ max_norm_bits) {
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= padded_rows) return;
+    const float4 x = reinterpret_cast<const float4*>(bank + row * 128)[lane];
+    float4 h, l;
+    h.x = tf32_trunc(x.x); h.y = tf32_trunc(x.y); h.z = tf32_trunc(x.z); h.w = tf32_trunc(x.w);
+    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+    reinterpret_cast<float4*>(hi + row * 128)[lane] = h;
+    reinterpret_cast<float4*>(lo + row * 128)[lane] = l;
+    float s = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const bool valid = static_cast<int>(row & (kRowAlign - 1)) < valid_in_block[row / kRowAlign];
+        fnorm2[row] = s;
+        const float g = valid ? 0.5f * s : 1e30f;                 // padded rows: D~ = -1e30, never a candidate
+        const float g0 = tf32_trunc(g), g1 = tf32_trunc(g - g0), g2 = tf32_trunc(g - g0 - g1);
+        float4* e = reinterpret_cast<float4*>(ext + row * 8);
+        e[0] = make_float4(-g0, -g1, -g2, 0.f);
+        e[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && s >= 0.f) atomicMax(max_norm_bits, __float_as_int(s));   // non-negative floats order like ints
+    }
+}
+
+cudaError_t launch_f32_split(const float* bank, int64_t padded_rows, const int32_t* valid_in_block, float* hi, float* lo,
+                             float* fnorm2, float* ext, int* max_norm_bits, cudaStream_t s) {
+    if (padded_rows == 0) return cudaSuccess;
+    const int64_t threads = padded_rows * 32;
+    f32_split_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(bank, padded_rows, valid_in_block, hi, lo,
+                                                                                   fnorm2, ext, max_norm_bits);
+    return cudaGetLastError();
+}
+
+// Exact fp32 re-rank + certificate for the 3xTF32 candidate kernel.  Input per query row: up to four candidate
+// chunks (i0 = c0 | c1 << 16, i1 = c2 | c3 << 16, 0xFFFF = none), v0 = d0, v1 = d1 (best / second-best chunk maximum
+// of D~ = a.b - |b|^2/2) and aux = v4 (fifth-best chunk maximum: an upper bound of D~ for every row outside the four
+// chunks).  |D~ - D| <= eps(row).  Output: exact Top2 (d^2 = sum (a-b)^2 in fp32), i0 = -1 for rows rejected by the
+// provisional ratio test.
+__device__ __forceinline__ void warp_chunk_candidates_f32(const float* __restrict__ bank, const float4 (&q)[32], int tr0,
+                                                          int ntr, int chunk, int lane, unsigned long long& a1,
+                                                          unsigned long long& a2) {
+    const int j = chunk * 32 + lane;
+    if (j < ntr) {
+        const float4* tv = reinterpret_cast<const float4*>(bank + (static_cast<size_t>(tr0) + j) * 128);
+        float d = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const float4 y = __ldg(tv + i);
+            const float e0 = q[i].x - y.x, e1 = q[i].y - y.y, e2 = q[i].z - y.z, e3 = q[i].w - y.w;
+            d = fmaf(e0, e0, d); d = fmaf(e1, e1, d); d = fmaf(e2, e2, d); d = fmaf(e3, e3, d);
+        }
+        if (d == d) {                                               // NaN never becomes a neighbour
+            const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(d)) << 32) | static_cast<unsigned>(j);
+            a2 = min(a2, max(a1, key));
+            a1 = min(a1, key);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) refine_f32_kernel(RefineF32Args a) {
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool need = false, valid = false;
+    Top2 t;
+    t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
+    float v4 = 0.f, eps = 0.f, na = 0.f;
+    int q_bank_row = 0, t_row0 = 0, nt = 0;
+    if (srow < a.staged_rows) {
+        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        PairDesc pd = a.pairs[p];
+        if (a.swap_roles) {
+            const PairDesc f = pd;
+            pd.q_row0 = f.t_row0; pd.nq = f.nt; pd.t_row0 = f.q_row0; pd.nt = f.nq;
+        }
+        const int row = static_cast<int>(srow - a.out_prefix[p]);
+        if (row < pd.nq) {
+            valid = true;
+            t = a.top2[srow];
+            v4 = a.aux[srow];
+            q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
+            na = a.fnorm2[q_bank_row];
+            // 3xTF32 + fp32 accumulation + fp32 norms: |D~ - D| well below 2^-13 of the magnitudes involved
+            eps = 1.220703125e-4f * (sqrtf(na * a.nb_max) + na + a.nb_max);
+            if ((t.i0 & 0xFFFF) != 0xFFFF) {
+                if (a.all_rows || (t.i0 >> 16) == 0xFFFF) need = true;        // fewer than two chunks known: look inside
+                else {
+                    const float lo0 = fmaxf(0.f, na - 2.f * (t.d0 + eps)), hi1 = fmaxf(0.f, na - 2.f * (t.d1 - eps));
+                    need = static_cast<double>(__fsqrt_rn(lo0)) * (1.0 - 1e-6) < static_cast<double>(__fsqrt_rn(hi1)) * a.ratio;
+                }
+            }
+        }
+    }
+    const float inf = __int_as_float(0x7f800000);
+    Top2 o;
+    o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (lane == 0 && mask) atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
+        const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
+        const int ntr = __shfl_sync(0xffffffffu, nt, src);
+        const int i0 = __shfl_sync(0xffffffffu, t.i0, src), i1 = __shfl_sync(0xffffffffu, t.i1, src);
+        const float rv4 = __shfl_sync(0xffffffffu, v4, src), reps = __shfl_sync(0xffffffffu, eps, src);
+        const float rna = __shfl_sync(0xffffffffu, na, src);
+        float4 q[32];
+        const float4* qv = reinterpret_cast<const float4*>(a.bank + static_cast<size_t>(qrow) * 128);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) q[i] = __ldg(qv + i);
+        const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
+        unsigned long long a1 = ~0ull, a2 = ~0ull;
+        for (int k = 0; k < 4; ++k)
+            if (cand[k] != 0xFFFF) warp_chunk_candidates_f32(a.bank, q, tr0, ntr, cand[k], lane, a1, a2);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+            a2 = min(max(a1, b1), min(a2, b2));
+            a1 = min(a1, b1);
+        }
+        // certificate: rows outside the candidate chunks have D~ <= v4, i.e. d^2 >= |a|^2 - 2 (v4 + eps)
+        const bool all_chunks_known = cand[3] == 0xFFFF || rv4 == __int_as_float(0xff800000);
+        const float lb_other = rna - 2.f * (rv4 + reps);
+        const bool certified = all_chunks_known ||
+                               (a2 != ~0ull && __uint_as_float(static_cast<unsigned>(a2 >> 32)) * (1.f + 1e-6f) < lb_other);
+        if (!certified) {                                           // exact brute force over the whole train image
+            if (lane == 0) atomicAdd(a.stats + 1, 1ull);
+            a1 = ~0ull; a2 = ~0ull;
+            for (int c = 0; c * 32 < ntr; ++c) warp_chunk_candidates_f32(a.bank, q, tr0, ntr, c, lane, a1, a2);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+                a2 = min(max(a1, b1), min(a2, b2));
+                a1 = min(a1, b1);
+            }
+        }
+        if (lane == src) {
+            if (a1 != ~0ull) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFull); o.d0 = __uint_as_float(static_cast<unsigned>(a1 >> 32)); }
+            if (a2 != ~0ull) { o.i1 = static_cast<int>(a2 & 0xFFFFFFFFull); o.d1 = __uint_as_float(static_cast<unsigned>(a2 >> 32)); }
+        }
+    }
+    if (valid) a.top2[srow] = o;
+}
+
+cudaError_t launch_refine_f32(const RefineF32Args& a, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    refine_f32_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ reorder
 // The pipelined host path schedules pairs by availability of their images, so the compacted lists come out in
 // schedule order; these three passes bring them back to INPUT pair order (order[k] = input index of scheduled pair k).

@@ -71,8 +71,14 @@ struct Bank {
     DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid, d_ext, d_bits;     // d_bits: ORB bits expanded to bytes (256 B rows)
     alignas(64) CUtensorMap tmap_a, tmap_b, tmap_e;
     bool ext_ok = false;             // every |b|^2 <= kExtMaxNorm2: the value-only tcgen05 kernel may be used
+    // non-integer float descriptors, 128 wide: hi/lo split for the 3xTF32 tcgen05 kernel
+    DevBuf d_fhi, d_flo, d_fnorm, d_fext;
+    alignas(64) CUtensorMap tmaps_f[5];   // hi (A box), lo (A box), hi (B box), lo (B box), norm rows
+    bool f_tc_ok = false;
+    float f_nb_max = 0.f;
     bool have_tmap = false;
-    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release(); }
+    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release();
+                     d_fhi.release(); d_flo.release(); d_fnorm.release(); d_fext.release(); }
 };
 
 struct RunState {                    // what collect() needs from the last enqueue
@@ -104,6 +110,7 @@ struct sfm_ctx {
     DevBuf d_top2, d_rev, d_train_cnt, d_chunk_counts, d_chunk_excl, d_pair_counts, d_pair_offsets, d_dropped;
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
+    DevBuf d_aux, d_aux_rev;         // 3xTF32 path: fifth-best chunk maximum per staged row
     DevBuf d_out2, d_pair_offsets2, d_dropped2, d_order, d_cnt_tmp;   // reorder targets of the pipelined host path
     cudaStream_t copy_stream = nullptr;                               // uploads of the pipelined host path
     std::vector<cudaEvent_t> group_ev;                                // image group g is resident + packed
@@ -136,6 +143,31 @@ int fail(sfm_ctx* c, int code, const std::string& msg) {
         if (_e != cudaSuccess)                                                                       \
             return fail(ctx, SFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
     } while (0)
+
+int make_tmaps_f32(sfm_ctx* c, Bank& b) {
+    b.f_tc_ok = false;
+    if (b.padded_rows == 0) return SFM_OK;
+    const cuuint64_t dims[2] = {512, static_cast<cuuint64_t>(b.padded_rows)};      // 128 floats = 512 bytes per row
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box[2] = {128, 128};                                          // one 128-byte K slab x 128 rows
+    void* src[4] = {b.d_fhi.p, b.d_flo.p, b.d_fhi.p, b.d_flo.p};
+    for (int i = 0; i < 4; ++i) {
+        CUresult r = c->encode(&b.tmaps_f[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, src[i], dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(f32 hi/lo) failed: " + std::to_string(r));
+    }
+    const cuuint64_t dims_e[2] = {32, static_cast<cuuint64_t>(b.padded_rows)};
+    const cuuint64_t strides_e[1] = {32};
+    const cuuint32_t box_e[2] = {32, 128};
+    CUresult r = c->encode(&b.tmaps_f[4], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.d_fext.p, dims_e, strides_e, box_e, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, SFM_ERR_CUDA, "cuTensorMapEncodeTiled(f32 norm rows) failed: " + std::to_string(r));
+    b.f_tc_ok = true;
+    return SFM_OK;
+}
 
 int make_tmaps(sfm_ctx* c, Bank& b) {
     b.have_tmap = false;
@@ -265,6 +297,24 @@ int bank_finish(sfm_ctx* c, Bank& b) {
             b.have_f32 = true;
             CU_TRY(c, launch_zero_padding(b.d_f32.p, b.cols * 4, b.padded_rows, d_valid, s));
             c->stat_launches++;
+            b.f_tc_ok = false;
+            if (b.cols == 128) {
+                // hi/lo split, norms and norm rows for the 3xTF32 tcgen05 kernel
+                const size_t fb = static_cast<size_t>(b.padded_rows) * 512;
+                CU_TRY(c, b.d_fhi.ensure(fb));
+                CU_TRY(c, b.d_flo.ensure(fb));
+                CU_TRY(c, b.d_fnorm.ensure(b.padded_rows * 4));
+                CU_TRY(c, b.d_fext.ensure(static_cast<size_t>(b.padded_rows) * 32));
+                CU_TRY(c, cudaMemsetAsync(flags, 0, 8, s));
+                CU_TRY(c, launch_f32_split(b.d_f32.as<float>(), b.padded_rows, d_valid, b.d_fhi.as<float>(), b.d_flo.as<float>(),
+                                           b.d_fnorm.as<float>(), b.d_fext.as<float>(), flags + 1, s));
+                c->stat_launches++;
+                CU_TRY(c, cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, s));
+                CU_TRY(c, cudaStreamSynchronize(s));
+                std::memcpy(&b.f_nb_max, &h[1], 4);
+                int rcf = make_tmaps_f32(c, b);
+                if (rcf != SFM_OK) return rcf;
+            }
         }
     } else {
         b.u8_valued = true;
@@ -324,7 +374,7 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
 }
 
 // ------------------------------------------------------------------------------------------------ the stage
-enum class Engine { TC, TCV, DP4A, F32, POPC };
+enum class Engine { TC, TCV, TF32, DP4A, F32, POPC };
 
 int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out) {
     if (norm == SFM_NORM_HAMMING) {
@@ -340,15 +390,18 @@ int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out)
         return SFM_OK;
     }
     if (!b.have_f32) return fail(c, SFM_ERR_UNSUPPORTED, "NORM_L2 on CV_8U data needs 128-byte descriptors");
+    // non-integer float descriptors: 3xTF32 tcgen05 candidate search + exact fp32 re-rank (128 columns), or the
+    // CUDA-core fp32 kernel (any width up to 512, and SFM_ENGINE_SIMT)
+    if (b.f_tc_ok && requested != SFM_ENGINE_SIMT) { *out = Engine::TF32; return SFM_OK; }
     if (requested == SFM_ENGINE_TENSOR || requested == SFM_ENGINE_TENSOR_IMAD)
-        return fail(c, SFM_ERR_UNSUPPORTED, "tensor engine needs u8-valued 128-d descriptors");
+        return fail(c, SFM_ERR_UNSUPPORTED, "tensor engine needs 128-column descriptors");
     if (b.cols > 512) return fail(c, SFM_ERR_UNSUPPORTED, "fp32 L2 kernel supports up to 512 columns");
     *out = Engine::F32;
     return SFM_OK;
 }
 
 int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, const int64_t* d_unit_prefix, int n_pairs,
-               int64_t n_units, Top2* out) {
+               int64_t n_units, Top2* out, float* aux = nullptr) {
     cudaStream_t s = c->stream;
     c->stat_launches++;
     switch (eng) {
@@ -359,6 +412,9 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
                                             c->sm_count, c->tcv_groups_run, s));
+            break;
+        case Engine::TF32:
+            CU_TRY(c, launch_knn2_l2_f32_tc3(b.tmaps_f, d_pairs, d_unit_prefix, n_pairs, n_units, out, aux, c->sm_count, s));
             break;
         case Engine::DP4A:
             CU_TRY(c, launch_knn2_l2_u8_dp4a(b.d_u8.as<uint8_t>(), b.d_norm2.as<int32_t>(), d_pairs, d_unit_prefix, n_pairs,
@@ -375,7 +431,8 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
 }
 
 int rows_per_unit(Engine e) {
-    return e == Engine::F32 ? kF32RowsPerUnit : ((e == Engine::TC || e == Engine::TCV) ? kTcRowsPerUnit : kSimtRowsPerUnit);
+    return e == Engine::F32 ? kF32RowsPerUnit
+                            : ((e == Engine::TC || e == Engine::TCV || e == Engine::TF32) ? kTcRowsPerUnit : kSimtRowsPerUnit);
 }
 
 // Optional processing schedule of enqueue_impl (pipelined host path): order[k] = input index of the k-th scheduled
@@ -527,6 +584,11 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
 
     CU_TRY(c, c->d_top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
     if (need_rev) CU_TRY(c, c->d_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
+    if (eng == Engine::TF32) {
+        CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
+        CU_TRY(c, c->d_aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+        if (need_rev) CU_TRY(c, c->d_aux_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
+    }
     if (need_cnt) CU_TRY(c, c->d_train_cnt.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
     CU_TRY(c, c->d_chunk_counts.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
     CU_TRY(c, c->d_chunk_excl.ensure(static_cast<size_t>(max_chunks + 1) * 8));
@@ -557,13 +619,29 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         const int64_t base = B.p0 + bi;
         if (sched && sched->avail && sched->events) CU_TRY(c, cudaStreamWaitEvent(s, sched->events[sched->avail[B.p0]], 0));
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
-        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>());
+        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>(), c->d_aux.as<float>());
         if (rc != SFM_OK) return rc;
         if (need_rev) {
-            rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, c->d_rev.as<Top2>());
+            rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, c->d_rev.as<Top2>(), c->d_aux_rev.as<float>());
             if (rc != SFM_OK) return rc;
         }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 1], s));
+        if (eng == Engine::TF32) {
+            // candidates -> exact fp32 top-2 (+ certificate); everything downstream sees ordinary Top2 rows
+            RefineF32Args fa;
+            fa.top2 = c->d_top2.as<Top2>(); fa.aux = c->d_aux.as<float>(); fa.pairs = d_pd + B.p0; fa.out_prefix = d_outp + base;
+            fa.n_pairs = np; fa.staged_rows = B.staged_rows; fa.bank = b.d_f32.as<float>(); fa.fnorm2 = b.d_fnorm.as<float>();
+            fa.nb_max = b.f_nb_max; fa.all_rows = (o->k == 1 || need_rev) ? 1 : 0; fa.swap_roles = 0; fa.ratio = o->ratio;
+            fa.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
+            CU_TRY(c, launch_refine_f32(fa, s));
+            c->stat_launches++;
+            if (need_rev) {
+                fa.top2 = c->d_rev.as<Top2>(); fa.aux = c->d_aux_rev.as<float>(); fa.swap_roles = 1;
+                fa.out_prefix = d_tp + base; fa.staged_rows = B.t_rows; fa.all_rows = 1;
+                CU_TRY(c, launch_refine_f32(fa, s));
+                c->stat_launches++;
+            }
+        }
         if ((eng == Engine::TC || eng == Engine::TCV) && o->k == 2 && !need_rev) {
             RefineArgs ra;
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
@@ -859,7 +937,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
                       &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
                       &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
-                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp};
+                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev};
     for (DevBuf* b : bufs) b->release();
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
@@ -1008,6 +1086,18 @@ int sfm_last_stats(const sfm_ctx* c, int64_t* launches, int64_t* h2d, int64_t* d
     return SFM_OK;
 }
 
+int sfm_last_float_stats(sfm_ctx* c, int64_t* rows_reranked, int64_t* rows_brute_forced) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(c, cudaSetDevice(c->device));
+    int64_t h[2];
+    CU_TRY(c, cudaMemcpyAsync(h, c->d_scalars.as<uint8_t>() + 32, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (rows_reranked) *rows_reranked = h[0];
+    if (rows_brute_forced) *rows_brute_forced = h[1];
+    return SFM_OK;
+}
+
 int sfm_set_profiling(sfm_ctx* c, int on) {
     if (!c) return SFM_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1063,8 +1153,22 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     CU_TRY(c, c->d_top2.ensure(static_cast<size_t>(pad_rows(nq)) * sizeof(Top2)));
     const PairDesc* d_pd = c->d_pairs.as<PairDesc>();
     const int64_t* d_unit = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, unit_prefix));
-    rc = launch_knn(c, b, eng, d_pd, d_unit, 1, meta.unit_prefix[1], c->d_top2.as<Top2>());
+    if (eng == Engine::TF32) {
+        CU_TRY(c, c->d_aux.ensure(static_cast<size_t>(pad_rows(nq)) * 4));
+        CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
+    }
+    rc = launch_knn(c, b, eng, d_pd, d_unit, 1, meta.unit_prefix[1], c->d_top2.as<Top2>(), c->d_aux.as<float>());
     if (rc != SFM_OK) return rc;
+    if (eng == Engine::TF32) {
+        RefineF32Args fa;
+        fa.top2 = c->d_top2.as<Top2>(); fa.aux = c->d_aux.as<float>(); fa.pairs = d_pd;
+        fa.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
+        fa.n_pairs = 1; fa.staged_rows = pad_rows(nq); fa.bank = b.d_f32.as<float>(); fa.fnorm2 = b.d_fnorm.as<float>();
+        fa.nb_max = b.f_nb_max; fa.all_rows = 1; fa.swap_roles = 0; fa.ratio = 0.0;
+        fa.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
+        CU_TRY(c, launch_refine_f32(fa, s));
+        c->stat_launches++;
+    }
     if (eng == Engine::TC && k == 2) {
         RefineArgs ra;
         ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd;
