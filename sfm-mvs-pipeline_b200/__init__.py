@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsfmmatch.so")
+LIB_PATH = os.environ.get("SFMMATCH_LIB") or os.path.join(HERE, "libsfmmatch.so")   # override: kernel experiments
 
 NORM_L2, NORM_HAMMING = 4, 6
 CV_8U, CV_32F = 0, 5

@@ -28,7 +28,7 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
 // ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int sm_count, int groups, cudaStream_t s);
+                                  Top2* out, int sm_count, int layout, int tile_rows, cudaStream_t s);
 
 // ---- knn_l2_tf32.cu  (tcgen05 kind::tf32, 3xTF32 candidate search for non-integer float descriptors)
 cudaError_t launch_knn2_l2_f32_tc3(const void* tmaps /* 5 CUtensorMap: hi_a, lo_a, hi_b, lo_b, ext */, const PairDesc* pairs,

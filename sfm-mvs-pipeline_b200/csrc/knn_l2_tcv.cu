@@ -25,36 +25,49 @@
 namespace sfm {
 
 namespace tcv {
-constexpr int BM = 128, BN = 256, KB = 128;
-constexpr int kBStages = 4, kAStages = 2, kAccStages = 2;
-constexpr int kABytes = BM * KB, kBBytes = BN * KB, kEBytes = BN * kExtBytes, kAExtBytes = BM * kExtBytes;
-
+constexpr int BM = 128, KB = 128;
+constexpr int kAStages = 2;
+constexpr int kABytes = BM * KB, kAExtBytes = BM * kExtBytes;
 constexpr int kEpiWarp0 = 4;
 constexpr int32_t kValueBias = kExtPadValue;                      // D + bias >= 0, < 2^22
 constexpr int kSeqBits = 9;                                       // chunks one epilogue warp visits per unit <= 512
-constexpr int offB = 0;
-constexpr int offE = offB + kBStages * kBBytes;                   // digit tiles, one per B stage
-constexpr int offA = offE + kBStages * kEBytes;
-constexpr int offAExt = offA + kAStages * kABytes;                // constant weight rows
-constexpr int offMerge = offAExt + kAExtBytes;                    // [3 groups][128][4] int64
-constexpr int offBar = offMerge + 3 * BM * 4 * 8;
-constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages;
-constexpr int offTmemPtr = offBar + kNumBars * 8;
-constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
-constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
-constexpr uint32_t kIdescExt = umma_idesc_u8s8(BM, BN);
 constexpr int64_t kEmpty = INT64_MIN;
+
+// Tile width BN = train rows per MMA tile; the 512 TMEM columns hold 512 / BN accumulator stages.  BN = 256 is the one
+// in use: tools/microbench2.cu measured tcgen05.mma.kind::i8 M128 x N256 x K32 at exactly 128 cycles (8192 MAC/clk/SM)
+// and N128 at 64, but every MMA costs its ISSUING thread 50-100 cycles (descriptor moves to uniform registers, the elect
+// loop, the instruction), so 128-row tiles (twice the instructions per train row) were 1.6x slower (profiles/
+// r1_tcv_issue_analysis.txt).
+template <int BN_>
+struct Cfg {
+    static constexpr int BN = BN_;
+    static constexpr int kAccStages = 512 / BN;
+    static constexpr int kBStages = 1024 / BN;                     // 128 KB of train rows in flight either way
+    static constexpr int kBBytes = BN * KB, kEBytes = BN * kExtBytes;
+    static constexpr int offB = 0;
+    static constexpr int offE = offB + kBStages * kBBytes;         // digit tiles, one per B stage
+    static constexpr int offA = offE + kBStages * kEBytes;
+    static constexpr int offAExt = offA + kAStages * kABytes;      // constant weight rows
+    static constexpr int offMerge = offAExt + kAExtBytes;          // [3 groups][128][4] int64
+    static constexpr int offBar = offMerge + 3 * BM * 4 * 8;
+    static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages;
+    static constexpr int offTmemPtr = offBar + kNumBars * 8;
+    static constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
+    static constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
+    static constexpr uint32_t kIdescExt = umma_idesc_u8s8(BM, BN);
+};
 }  // namespace tcv
 
 struct UnitInfoV { PairDesc pd; int rb; int n_tiles; };
 
+template <int BN>
 __device__ __forceinline__ UnitInfoV decode_unit_v(const PairDesc* __restrict__ pairs, const int64_t* __restrict__ unit_prefix,
                                                    int n_pairs, int64_t unit) {
     UnitInfoV u;
     const int p = find_segment(unit_prefix, n_pairs, unit);
     u.pd = pairs[p];
     u.rb = static_cast<int>(unit - unit_prefix[p]);
-    u.n_tiles = (u.pd.nt + tcv::BN - 1) / tcv::BN;
+    u.n_tiles = (u.pd.nt + BN - 1) / BN;
     return u;
 }
 
@@ -93,15 +106,23 @@ __device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, 
     m3 = max(m3, u);
 }
 
-// kGroups epilogue groups of 4 warps: 2 = (tile parity), 4 = (tile parity) x (column half)
-template <int kGroups>
-__global__ void __launch_bounds__(128 + 128 * kGroups, 1)
+// kParity x kHalves epilogue groups of 4 warps: a group owns the tiles of one parity (kParity = 2) or every tile
+// (kParity = 1), and one of kHalves column ranges of the tile.  With two accumulator stages the MMA of tile t+2 waits for
+// the complete epilogue of tile t, so the latency of ONE tile's epilogue has to stay below the MMA time of a tile:
+// splitting the columns of every tile over the groups (1 x 2) halves that latency, alternating tiles (2 x 1) does not.
+template <int kParity, int kHalves, int kBN>
+__global__ void __launch_bounds__(128 + 128 * kParity * kHalves, 1)
 knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
                       const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out) {
     using namespace tcv;
+    using C = Cfg<kBN>;
+    constexpr int BN = C::BN, kAccStages = C::kAccStages, kBStages = C::kBStages, kBBytes = C::kBBytes, kEBytes = C::kEBytes;
+    constexpr int offB = C::offB, offE = C::offE, offA = C::offA, offAExt = C::offAExt, offMerge = C::offMerge;
+    constexpr int offBar = C::offBar, offTmemPtr = C::offTmemPtr;
+    constexpr uint32_t kIdesc = C::kIdesc, kIdescExt = C::kIdescExt;
+    constexpr int kGroups = kParity * kHalves;
     constexpr int kThreads = 128 + 128 * kGroups;
-    constexpr int kHalves = kGroups / 2;                            // column splits of a tile
     constexpr int kChunksPerVisit = BN / 32 / kHalves;              // 32-column chunks one warp reads per tile
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -124,8 +145,8 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 128 * kHalves); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 2); }   // two MMA warps release A
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4 * kHalves); }   // one arrival per reading warp
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -148,7 +169,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         // ================================================================ TMA producer
         uint32_t tile_iter = 0, unit_iter = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
@@ -168,21 +189,38 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             ++unit_iter;
         }
-    } else if (warp == 1) {
-        // ================================================================ MMA issuer (lane 0 issues)
-        uint32_t tile_iter = 0, unit_iter = 0;
+    } else if (warp == 1 || warp == 3) {
+        // ================================================================ MMA issuers (lane 0 issues)
+        // One tcgen05.mma costs the issuing thread 50-100 cycles (descriptor moves to uniform registers, the elect loop,
+        // the instruction itself) and a satisfied mbarrier wait ~60: measured 770 cycles of issue-side work per tile with
+        // NOTHING else running, against 640 cycles of tensor-pipe work.  So two warps issue: warp 1 the even tiles
+        // (accumulator stage 0), warp 3 the odd tiles (stage 1).  Each warp's tcgen05.commit covers its own MMAs, hence
+        // both arrive on a_empty (count 2) after their last tile of a unit.
+        const uint32_t my_par = static_cast<uint32_t>(warp >> 1);
+        uint32_t tile0 = 0, unit_iter = 0;                          // tile0: running tile number at the start of the unit
         const uint64_t aext = umma_desc_sw32(base + offAExt);
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
             const uint64_t adesc = umma_desc_sw128(base + offA + as * kABytes);
-            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+            const int first = static_cast<int>((my_par - tile0) & 1u);            // my first tile of this unit
+            const int last = first < u.n_tiles ? first + 2 * ((u.n_tiles - 1 - first) / 2) : -1;
+            if (last < 0 && lane == 0) mbar_arrive(a_empty(as));                       // no tile of this unit is mine
+            for (int t = first; t < u.n_tiles; t += 2) {
+                const uint32_t tile_iter = tile0 + t;
                 const int acc = tile_iter % kAccStages;
                 const int st = tile_iter % kBStages;
-                mbar_wait(acc_empty(acc), ((tile_iter / kAccStages) & 1) ^ 1);
-                mbar_wait(b_full(st), (tile_iter / kBStages) & 1);
+                {
+                    // both polls in flight at once (a satisfied try_wait still costs ~60 cycles); the train tile has
+                    // normally landed long before the epilogue hands the accumulator stage back
+                    const uint32_t par_b = (tile_iter / kBStages) & 1, par_acc = ((tile_iter / kAccStages) & 1) ^ 1;
+                    bool ok_b = mbar_try_wait(b_full(st), par_b);
+                    bool ok_acc = mbar_try_wait(acc_empty(acc), par_acc);
+                    while (!ok_b) ok_b = mbar_try_wait(b_full(st), par_b);
+                    while (!ok_acc) ok_acc = mbar_try_wait(acc_empty(acc), par_acc);
+                }
                 tc_fence_after();
                 if (lane == 0) {
                     const uint64_t bdesc = umma_desc_sw128(base + offB + st * kBBytes);
@@ -192,12 +230,15 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     for (int k = 0; k < KB / 32; ++k)
                         umma_i8(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
                     umma_i8(d, aext, edesc, kIdescExt, 1);          // += -(|b|^2 >> 1)
+                    // two commits (B stage -> producer, accumulator -> epilogue): one shared mbarrier for both waiters
+                    // measured 4 % slower
                     umma_commit(b_empty(st));
                     umma_commit(acc_full(acc));
-                    if (t == u.n_tiles - 1) umma_commit(a_empty(as));
+                    if (t == last) umma_commit(a_empty(as));
                 }
                 __syncwarp();
             }
+            tile0 += u.n_tiles;
             ++unit_iter;
         }
     } else if (warp >= kEpiWarp0) {
@@ -207,18 +248,18 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         // Running state for the WHOLE unit in 32-bit keys:  key = (D + bias) << 9 | (511 - seq), seq = running number
         // of the chunk in this warp's visiting order (ascending train rows) -> equal D keeps the earlier chunk.
         const int group = (warp - kEpiWarp0) >> 2;
-        const int parity = group & 1, half = group >> 1;
+        const int parity = group % kParity, half = group / kParity;
         const int quarter = warp & 3;
         const int row_in_unit = quarter * 32 + lane;
         int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
         uint32_t tile_iter = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v(pairs, unit_prefix, n_pairs, unit);
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
             int32_t m1 = -1, m2 = -1, m3 = -1, m4 = -1;
-            const int t_first = static_cast<int>((parity - tile_iter) & 1u);     // first tile of this unit we own
+            const int t_first = kParity == 2 ? static_cast<int>((parity - tile_iter) & 1u) : 0;   // first tile of this unit we own
             int seq = 0;
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
-                if ((tile_iter & 1) != static_cast<uint32_t>(parity)) continue;
+                if (kParity == 2 && (tile_iter & 1) != static_cast<uint32_t>(parity)) continue;
                 const int acc = tile_iter % kAccStages;
                 mbar_wait(acc_full(acc), (tile_iter / kAccStages) & 1);
                 tc_fence_after();
@@ -237,6 +278,13 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                    "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
                                  :: "memory");
                     if (c + 1 < kChunksPerVisit) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    else {
+                        // last chunk is in registers (tcgen05.wait::ld is warp-wide): hand the stage back now, ONE arrival
+                        // per warp (128 per-thread arrivals on one mbarrier serialise in shared memory)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(acc));
+                    }
                     // balanced max3 tree over the raw accumulators: 32 -> 11 -> 4 -> 1
                     int32_t a[11];
 #pragma unroll
@@ -250,8 +298,6 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - (seq + c)), m1, m2, m3, m4);
                 }
                 seq += kChunksPerVisit;
-                tc_fence_before();
-                mbar_arrive(acc_empty(acc));
             }
             // ---- unit end: to (D + bias, -global chunk) 64-bit keys, merge the four groups, write the candidates
             int64_t r[4];
@@ -261,7 +307,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 for (int i = 0; i < 4; ++i) {
                     if (mk[i] < 0) { r[i] = kEmpty; continue; }
                     const int sq = 511 - (mk[i] & 511);
-                    const int gch = (t_first + 2 * (sq / kChunksPerVisit)) * (BN / 32) + half * kChunksPerVisit + (sq % kChunksPerVisit);
+                    const int gch = (t_first + kParity * (sq / kChunksPerVisit)) * (BN / 32) + half * kChunksPerVisit + (sq % kChunksPerVisit);
                     r[i] = static_cast<int64_t>(mk[i] >> kSeqBits) * (1ll << 32) + (0x7FFFFFFF - gch);
                 }
             }
@@ -306,30 +352,36 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int kGroups>
+template <int kParity, int kHalves, int kBN>
 static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
                               const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int grid, cudaStream_t s) {
     // per launch: the attribute is per device, and one process may drive several GPUs
-    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             tcv::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, tcv::Cfg<kBN>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    knn2_l2_u8_tcv_kernel<kGroups><<<grid, 128 + 128 * kGroups, tcv::kSmemBytes, s>>>(ta, tb, te, pairs, unit_prefix, n_pairs,
-                                                                                      n_units, out);
+    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
+        ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out);
     return cudaGetLastError();
 }
 
-// groups: 2 or 4 epilogue groups.  The 32-bit running keys number at most 512 chunks per epilogue warp and unit:
-// train images up to 32768 rows with 2 groups, 65536 with 4.
+// layout: epilogue organisation = 10 * kParity + kHalves: 12 (8 warps, column halves of every tile; fastest), 14 (16
+// warps, column quarters of every tile), 21 (8 warps, alternate tiles).  The 32-bit running keys number at most 512 chunks per epilogue warp and unit: train
+// images up to 32768 rows with two groups (12, 21), 65536 with four (14).  tile_rows: 128 (four TMEM accumulator stages; tmap_b /
+// tmap_e must have 128-row boxes) or 256 (two stages, 256-row boxes).
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int sm_count, int groups, cudaStream_t s) {
+                                  Top2* out, int sm_count, int layout, int tile_rows, cudaStream_t s) {
     if (n_units == 0) return cudaSuccess;
     const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
     const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e_host);
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
-    if (groups == 2) return launch_tcv<2>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
-    return launch_tcv<4>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
+#define SFM_TCV_CASE(P, H, T)                                                                                          \
+    if (layout == 10 * P + H && tile_rows == T)                                                                        \
+        return launch_tcv<P, H, T>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
+    SFM_TCV_CASE(1, 2, 256) SFM_TCV_CASE(1, 4, 256) SFM_TCV_CASE(2, 1, 256)
+#undef SFM_TCV_CASE
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace sfm

@@ -127,8 +127,9 @@ struct sfm_ctx {
     std::vector<cudaEvent_t> prof_ev;     // triples per batch: knn begin, knn end, post end
     int prof_used = 0;
     size_t staging_budget_rows = 0;
-    int tcv_groups_run = 2;
-    int tcv_groups = 0;              // epilogue groups of the value-only kernel: 0 = auto, SFM_TCV_GROUPS = 2 | 4 forces
+    int tcv_layout_run = 12;
+    int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
+                                     // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
 };
 
 namespace {
@@ -411,7 +412,7 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            c->sm_count, c->tcv_groups_run, s));
+                                            c->sm_count, c->tcv_layout_run, 256, s));
             break;
         case Engine::TF32:
             CU_TRY(c, launch_knn2_l2_f32_tc3(b.tmaps_f, d_pairs, d_unit_prefix, n_pairs, n_units, out, aux, c->sm_count, s));
@@ -469,10 +470,10 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
     if (eng == Engine::TC && o->engine != SFM_ENGINE_TENSOR_IMAD && o->k == 2 && !o->cross_check && b.ext_ok) {
         int32_t max_rows = 0;
         for (int32_t n : b.n_rows) max_rows = std::max(max_rows, n);
-        // 2 epilogue groups (8 warps) measured fastest; their 32-bit keys cover train images up to 32768 rows,
-        // 4 groups up to 65536
-        c->tcv_groups_run = c->tcv_groups ? c->tcv_groups : (max_rows <= 32768 ? 2 : 4);
-        if (max_rows <= (c->tcv_groups_run == 2 ? 32768 : 65536)) eng = Engine::TCV;
+        // 2 epilogue groups (8 warps, layout 12) measured fastest; their 32-bit keys cover train images up to 32768
+        // rows, 4 groups (layout 14) up to 65536
+        c->tcv_layout_run = c->tcv_layout ? c->tcv_layout : (max_rows <= 32768 ? 12 : 14);
+        if (max_rows <= (c->tcv_layout_run == 14 ? 65536 : 32768)) eng = Engine::TCV;
     }
     for (int64_t p = 0; p < n_pairs; ++p) {
         const int l = pairs[2 * p], r = pairs[2 * p + 1];
@@ -924,7 +925,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     size_t mb = 512;
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
-    if (const char* env = std::getenv("SFM_TCV_GROUPS")) { const int g = std::atoi(env); if (g == 2 || g == 4) c->tcv_groups = g; }
+    if (const char* env = std::getenv("SFM_TCV_LAYOUT")) { const int g = std::atoi(env); if (g == 12 || g == 14 || g == 21 || g == 22) c->tcv_layout = g; }
     *out = c;
     return SFM_OK;
 }

@@ -234,6 +234,36 @@ def test_value_only_kernel_ties_and_fallback(sfm, matcher):
         assert orc.dmatch_equal(res[p], exp[p])
 
 
+@pytest.mark.parametrize("layout", [12, 14, 21])
+def test_value_only_kernel_epilogue_layouts(sfm, layout, monkeypatch):
+    """Every epilogue organisation of the value-only kernel (SFM_TCV_LAYOUT: column halves / column quarters of every
+    tile, alternate tiles) and the two MMA-issuing warps give the oracle's lists bit for bit, including units with a
+    single train tile (one issuing warp has nothing to do), odd tile counts and > 32768-row train images (layout 14)."""
+    monkeypatch.setenv("SFM_TCV_LAYOUT", str(layout))
+    m = sfm.Matcher(0)
+    try:
+        sizes = [700, 256, 1, 130, 2049, 513, 300]               # 1, 2, 3, 9 train tiles; units of 1..17 query blocks
+        bank = workloads.sift_like_bank(len(sizes), 2100)
+        bank = [b[:n] for b, n in zip(bank, sizes)]
+        pairs = sfm.select_pairs(len(bank), 0, 0)
+        pairs = np.concatenate([pairs, pairs[:, ::-1]])
+        m.upload_bank(bank)
+        exp = orc.match_pairs(bank, pairs, NORM_L2, ratio=0.8)
+        res = m.match_pairs(pairs, NORM_L2, ratio=0.8)
+        for p in range(len(pairs)):
+            assert orc.dmatch_equal(res[p], exp[p]), (layout, pairs[p].tolist())
+        if layout == 14:                                         # 40 000-row train image: 157 tiles, 4 epilogue groups
+            big = workloads.sift_like_image(1, 40000, bank[0])
+            q = workloads.sift_like_image(2, 600, big)
+            m.upload_bank([q, big])
+            exp = orc.match_pairs([q, big], [[0, 1], [1, 0]], NORM_L2)
+            res = m.match_pairs([[0, 1], [1, 0]], NORM_L2)
+            assert orc.dmatch_equal(res[0], exp[0]) and orc.dmatch_equal(res[1], exp[1])
+            assert len(res[0]) > 100
+    finally:
+        m.close()
+
+
 def test_cross_check_vs_cv2_golden(sfm, matcher, insel_sift, synthetic_cv2):
     matcher.upload_bank([insel_sift[f"desc{i}"] for i in range(3)])
     res = matcher.match_pairs([[0, 1]], NORM_L2, k=1, cross_check=True)

@@ -1,0 +1,28 @@
+"""A/B of the value-only kernel's configurations: kernel-only time (sfm_set_profiling) on an all-pairs workload.
+usage: SFM_TCV_LAYOUT=12|21|22 SFM_TCV_TILE=128|256 python tools/tcv_ab.py [images] [rows]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import __graft_entry__ as ge
+import workloads
+
+sfm = ge.load_package()
+n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+n_rows = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+m = sfm.Matcher(0)
+m.upload_bank(workloads.sift_like_bank(n_img, n_rows))
+pairs = sfm.select_pairs(n_img, 0, 0)
+m.set_profiling(True)
+best = None
+for rep in range(int(os.environ.get('REPS', '5'))):
+    m.enqueue(pairs, sfm.NORM_L2)
+    pr = m.last_profile()
+    r = m.collect()
+    if rep and (best is None or pr["knn_ms"] < best[0]):
+        best = (pr["knn_ms"], pr["post_ms"], int(r.offsets[-1]))
+ops = 2.0 * n_rows * n_rows * 128 * len(pairs)
+import subprocess
+clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+print(f"[{clk}] layout={os.environ.get('SFM_TCV_LAYOUT','auto')} tile={os.environ.get('SFM_TCV_TILE','auto')}: knn {best[0]:.3f} ms "
+      f"post {best[1]:.3f} ms -> {len(pairs)/best[0]*1e3:.0f} pairs/s kernel-only, {ops/best[0]/1e9:.0f} TOP/s, matches={best[2]}")
