@@ -18,10 +18,12 @@
 //
 // Persistent kernel, one CTA per SM, warp-specialised:
 //   warp 0      TMA producer   (A tile once per unit, B tile + ckeys per train tile, 4-stage ring)
-//   warp 1      MMA issuer     (4 x tcgen05.mma M128 N256 K32 per tile, 2 TMEM accumulator stages)
+//   warps 1, 3  MMA issuers    (4 x tcgen05.mma M128 N256 K32 per K slab and tile; warp 1 issues the even tiles into
+//                               TMEM accumulator stage 0, warp 3 the odd tiles into stage 1 — one thread cannot issue
+//                               fast enough, see profiles/r1_tcv_issue_analysis.txt)
 //   warp 2      TMEM allocator
-//   warps 4-7   epilogue group 0 (even tiles)   } thread = query row, TMEM lane quarter = warp % 4
-//   warps 8-11  epilogue group 1 (odd tiles)    }
+//   warps 4-7   epilogue group 0 (columns   0..127 of every tile) } thread = query row, TMEM lane quarter = warp % 4
+//   warps 8-11  epilogue group 1 (columns 128..255 of every tile) }
 // unit = (pair, block of 128 query rows); units are dealt round-robin to CTAs so that concurrently running
 // CTAs stream the same train image out of L2.
 #include <cuda.h>
@@ -111,8 +113,8 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 128); }
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 2); }    // both MMA warps release A
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 8); }  // one arrival per epilogue warp
         for (int i = 0; i < kCkSlots; ++i) mbar_init(ck_full(i), 1);
         fence_barrier_init();
     }
@@ -160,20 +162,30 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             }
             ++unit_iter;
         }
-    } else if (warp == 1) {
-        // ================================================================ MMA issuer (lane 0 issues)
-        uint32_t tile_iter = 0, unit_iter = 0;
+    } else if (warp == 1 || warp == 3) {
+        // ================================================================ MMA issuers (lane 0 issues)
+        const uint32_t my_par = static_cast<uint32_t>(warp >> 1);       // warp 1: even tiles, warp 3: odd tiles
+        uint32_t tile0 = 0, unit_iter = 0;                              // tile0: running tile number at the start of the unit
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const UnitInfo u = decode_unit(pairs, unit_prefix, n_pairs, unit);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
             const uint32_t a_smem = base + offA + as * kABytes;
-            for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
+            const int first = static_cast<int>((my_par - tile0) & 1u);  // my first tile of this unit
+            const int last = first < u.n_tiles ? first + 2 * ((u.n_tiles - 1 - first) / 2) : -1;
+            if (last < 0 && lane == 0) mbar_arrive(a_empty(as));        // no tile of this unit is mine
+            for (int t = first; t < u.n_tiles; t += 2) {
+                const uint32_t tile_iter = tile0 + t;
                 const int acc = tile_iter % kAccStages;
                 const int st = tile_iter % kBStages;
-                mbar_wait(acc_empty(acc), ((tile_iter / kAccStages) & 1) ^ 1);
-                mbar_wait(b_full(st), (tile_iter / kBStages) & 1);
+                {
+                    const uint32_t par_b = (tile_iter / kBStages) & 1, par_acc = ((tile_iter / kAccStages) & 1) ^ 1;
+                    bool ok_b = mbar_try_wait(b_full(st), par_b);
+                    bool ok_acc = mbar_try_wait(acc_empty(acc), par_acc);
+                    while (!ok_b) ok_b = mbar_try_wait(b_full(st), par_b);
+                    while (!ok_acc) ok_acc = mbar_try_wait(acc_empty(acc), par_acc);
+                }
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t b_smem = base + offB + st * kBBytes;
@@ -188,15 +200,16 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     }
                     umma_commit(b_empty(st));              // smem stage free once these MMAs retire
                     umma_commit(acc_full(acc));            // accumulator ready for the epilogue
-                    if (t == u.n_tiles - 1) umma_commit(a_empty(as));
+                    if (t == last) umma_commit(a_empty(as));
                 }
                 __syncwarp();
             }
+            tile0 += u.n_tiles;
             ++unit_iter;
         }
     } else if (warp >= kEpiWarp0) {
         // ================================================================ epilogue: running top-2 per query row
-        const int group = (warp - kEpiWarp0) >> 2;         // 0: even tiles, 1: odd tiles
+        const int group = (warp - kEpiWarp0) >> 2;         // column half of every tile
         const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
         const int row_in_unit = quarter * 32 + lane;
         int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
@@ -205,14 +218,13 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const UnitInfo u = decode_unit(pairs, unit_prefix, n_pairs, unit);
             int64_t r1 = kEmptyKey, r2 = kEmptyKey;
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
-                if ((tile_iter & 1) != static_cast<uint32_t>(group)) continue;
                 const int acc = tile_iter % kAccStages;
                 const int cs = tile_iter % kCkSlots;
                 mbar_wait(ck_full(cs), (tile_iter / kCkSlots) & 1);
                 mbar_wait(acc_full(acc), (tile_iter / kAccStages) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-                const int4* ck4 = reinterpret_cast<const int4*>(base_ptr + offCk + cs * kCkBytes);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + group * (BN / 2);
+                const int4* ck4 = reinterpret_cast<const int4*>(base_ptr + offCk + cs * kCkBytes) + group * (BN / 8);
                 // Per 32-column chunk: 32 IMAD build the keys, a VIMNMX3 tree (16 ops) takes the chunk minimum,
                 // 3 more ops insert it into the running top-2 OF CHUNK MINIMA.  m1 is therefore the exact best
                 // element; m2 is the best element outside m1's chunk, an upper bound of the true second
@@ -221,7 +233,7 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 uint32_t v[2][32];
                 tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = 0; c < BN / 64; ++c) {
                     uint32_t (&cur)[32] = v[c & 1];
                     // make the loaded registers depend on the wait
                     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -232,7 +244,13 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                    "+r"(cur[22]), "+r"(cur[23]), "+r"(cur[24]), "+r"(cur[25]), "+r"(cur[26]),
                                    "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
                                  :: "memory");
-                    if (c + 1 < BN / 32) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (c + 1 < BN / 64) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    else {
+                        // the last chunk is in registers (tcgen05.wait::ld is warp-wide): hand the stage back now
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(acc));
+                    }
                     int32_t k[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -252,9 +270,6 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     const int32_t cm = min(__vimin3_s32(b0, b1, b2), b3);
                     top2_key(cm, m1, m2);
                 }
-                // all TMEM reads of this accumulator stage are complete: hand it back to the MMA warp
-                tc_fence_before();
-                mbar_arrive(acc_empty(acc));
                 const int32_t t1 = m1, t2 = m2;
                 const int64_t colbase = static_cast<int64_t>(t) * BN;
                 const int64_t k1 = static_cast<int64_t>(t1 >> 8) * (1ll << 32) + (colbase + (t1 & 255));
