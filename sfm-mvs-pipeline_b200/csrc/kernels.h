@@ -28,7 +28,7 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
 // ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int sm_count, int layout, int tile_rows, cudaStream_t s);
+                                  Top2* out, int32_t* aux, int sm_count, int layout, int tile_rows, int issuers, cudaStream_t s);
 
 // ---- knn_l2_tf32.cu  (tcgen05 kind::tf32, 3xTF32 candidate search for non-integer float descriptors)
 cudaError_t launch_knn2_l2_f32_tc3(const void* tmaps /* 5 CUtensorMap: hi_a, lo_a, hi_b, lo_b, ext */, const PairDesc* pairs,
@@ -42,7 +42,9 @@ cudaError_t launch_expand_bits(const uint8_t* bank32, int64_t padded_rows, const
                                int32_t* norm2, int32_t* ckey, cudaStream_t s);
 cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, const int32_t* valid_in_block, cudaStream_t s);
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* row_valid_end /*per 256-row block*/,
-                               int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, cudaStream_t s);
+                               int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2 /* [0] max, [1] min over valid rows */,
+                               int32_t* blk_min, int32_t* blk_max /* |b|^2 range per 256-row block, pre-initialised */,
+                               cudaStream_t s);
 struct FilterParams {
     int norm;            // SFM_NORM_*
     int k;               // 1 or 2
@@ -76,10 +78,17 @@ struct RefineArgs {
     int all_rows;                // 1: every row (raw knnMatch output), 0: only rows that can pass the ratio test
     double ratio;
     int hamming;                 // bank = 32-byte ORB rows, distances by __popc (no sqrt in the provisional test)
+    // norm-less value-only path (refine_dot): fifth-best chunk maximum per staged row, |b|^2 range per 256-row bank block
+    const int32_t* aux;
+    const int32_t* blk_min;
+    const int32_t* blk_max;
+    unsigned long long* stats;   // [0] rows re-ranked, [1] rows brute-forced
 };
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
 // value-only tcgen05 path: (chunk, D) pairs -> exact Top2 for rows that can pass the ratio test (see post.cu)
 cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s);
+// norm-less value-only path: four candidate chunks + bounds -> exact best match and a decided ratio test (see post.cu)
+cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s);
 // pass 1 (only with distinct): count how often each train row is the best match of a kept query row
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s);
 // pass 2: number of surviving matches per 256-row chunk

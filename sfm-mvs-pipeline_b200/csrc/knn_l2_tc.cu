@@ -136,7 +136,7 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(a_full(as), kABytes);
 #pragma unroll
                 for (int sl = 0; sl < kSlabs; ++sl)      // one 128-byte-wide box per K slab
@@ -146,7 +146,7 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
                 const int st = tile_iter % kBStages;
                 mbar_wait(b_empty(st), ((tile_iter / kBStages) & 1) ^ 1);
-                if (lane == 0) {
+                if (elect_one()) {
                     mbar_arrive_expect_tx(b_full(st), kBBytes);
 #pragma unroll
                     for (int sl = 0; sl < kSlabs; ++sl)
@@ -187,7 +187,7 @@ knn2_l2_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     while (!ok_acc) ok_acc = mbar_try_wait(acc_empty(acc), par_acc);
                 }
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t b_smem = base + offB + st * kBBytes;
                     const uint32_t d = tmem_base + acc * BN;
 #pragma unroll

@@ -48,8 +48,8 @@ struct Cfg {
     static constexpr int offE = offB + kBStages * kBBytes;         // digit tiles, one per B stage
     static constexpr int offA = offE + kBStages * kEBytes;
     static constexpr int offAExt = offA + kAStages * kABytes;      // constant weight rows
-    static constexpr int offMerge = offAExt + kAExtBytes;          // [3 groups][128][4] int64
-    static constexpr int offBar = offMerge + 3 * BM * 4 * 8;
+    static constexpr int offMerge = offAExt + kAExtBytes;          // [3 groups][128][5] int64
+    static constexpr int offBar = offMerge + 3 * BM * 5 * 8;
     static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages;
     static constexpr int offTmemPtr = offBar + kNumBars * 8;
     static constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
@@ -89,6 +89,29 @@ __device__ __forceinline__ void top4_max(int32_t k, int32_t& m1, int32_t& m2, in
     m3 = max(m3, u);
     m4 = max(m4, w);
 }
+// running top-5 (descending) insert, 9 ops
+__device__ __forceinline__ void top5_max(int32_t k, int32_t& m1, int32_t& m2, int32_t& m3, int32_t& m4, int32_t& m5) {
+    const int32_t t = min(m1, k);
+    m1 = max(m1, k);
+    const int32_t u = min(m2, t);
+    m2 = max(m2, t);
+    const int32_t w = min(m3, u);
+    m3 = max(m3, u);
+    const int32_t x = min(m4, w);
+    m4 = max(m4, w);
+    m5 = max(m5, x);
+}
+__device__ __forceinline__ void top5_max64(int64_t k, int64_t& m1, int64_t& m2, int64_t& m3, int64_t& m4, int64_t& m5) {
+    const int64_t t = min(m1, k);
+    m1 = max(m1, k);
+    const int64_t u = min(m2, t);
+    m2 = max(m2, t);
+    const int64_t w = min(m3, u);
+    m3 = max(m3, u);
+    const int64_t x = min(m4, w);
+    m4 = max(m4, w);
+    m5 = max(m5, x);
+}
 __device__ __forceinline__ void top4_max64(int64_t k, int64_t& m1, int64_t& m2, int64_t& m3, int64_t& m4) {
     const int64_t t = min(m1, k);
     m1 = max(m1, k);
@@ -110,11 +133,19 @@ __device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, 
 // (kParity = 1), and one of kHalves column ranges of the tile.  With two accumulator stages the MMA of tile t+2 waits for
 // the complete epilogue of tile t, so the latency of ONE tile's epilogue has to stay below the MMA time of a tile:
 // splitting the columns of every tile over the groups (1 x 2) halves that latency, alternating tiles (2 x 1) does not.
-template <int kParity, int kHalves, int kBN>
+//
+// kNorm = true : the accumulator carries the norm term (fifth K-step), output = best chunks by D = ab - (|b|^2 >> 1).
+// kNorm = false: "norm-less" variant for banks whose |b|^2 vary little (SIFT: ~1 %): four K-steps only (-20 % tensor
+//                work and energy, no digit tiles), the epilogue ranks chunks by the raw dot product a.b and reports the
+//                four best chunks, V1, V2 and the fifth-best chunk maximum V5; refine_dot_kernel (post.cu) turns that
+//                into the exact answer with the train image's norm range: d^2 >= |a|^2 + min|b|^2 - 2 V for every row
+//                whose chunk maximum is V (see there).  Same exactness guarantee, everything integer.
+template <int kParity, int kHalves, int kBN, bool kNorm>
 __global__ void __launch_bounds__(128 + 128 * kParity * kHalves, 1)
 knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
-                      const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out) {
+                      const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out,
+                      int32_t* __restrict__ aux, int n_issuers) {
     using namespace tcv;
     using C = Cfg<kBN>;
     constexpr int BN = C::BN, kAccStages = C::kAccStages, kBStages = C::kBStages, kBBytes = C::kBBytes, kEBytes = C::kEBytes;
@@ -145,7 +176,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 2); }   // two MMA warps release A
+        for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), n_issuers); }   // every MMA warp releases A
         for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4 * kHalves); }   // one arrival per reading warp
         fence_barrier_init();
     }
@@ -173,29 +204,31 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(a_full(as), kABytes);
                 tma_load_2d(base + offA + as * kABytes, &tmap_a, 0, u.pd.q_row0 + u.rb * BM, a_full(as));
             }
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
                 const int st = tile_iter % kBStages;
                 mbar_wait(b_empty(st), ((tile_iter / kBStages) & 1) ^ 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(b_full(st), kBBytes + kEBytes);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(b_full(st), kBBytes + (kNorm ? kEBytes : 0));
                     tma_load_2d(base + offB + st * kBBytes, &tmap_b, 0, u.pd.t_row0 + t * BN, b_full(st));
-                    tma_load_2d(base + offE + st * kEBytes, &tmap_e, 0, u.pd.t_row0 + t * BN, b_full(st));
+                    if (kNorm) tma_load_2d(base + offE + st * kEBytes, &tmap_e, 0, u.pd.t_row0 + t * BN, b_full(st));
                 }
                 __syncwarp();
             }
             ++unit_iter;
         }
-    } else if (warp == 1 || warp == 3) {
-        // ================================================================ MMA issuers (lane 0 issues)
-        // One tcgen05.mma costs the issuing thread 50-100 cycles (descriptor moves to uniform registers, the elect loop,
-        // the instruction itself) and a satisfied mbarrier wait ~60: measured 770 cycles of issue-side work per tile with
-        // NOTHING else running, against 640 cycles of tensor-pipe work.  So two warps issue: warp 1 the even tiles
-        // (accumulator stage 0), warp 3 the odd tiles (stage 1).  Each warp's tcgen05.commit covers its own MMAs, hence
-        // both arrive on a_empty (count 2) after their last tile of a unit.
+    } else if (warp == 1 || (warp == 3 && n_issuers == 2)) {
+        // ================================================================ MMA issuers (one elected lane issues)
+        // The issue side is a serial chain per tile: two mbarrier polls (~60 cycles each even when satisfied), 5 tcgen05.mma
+        // and 2-3 tcgen05.commit at >= 48 cycles per instruction.  Guarded by `lane == 0`, ptxas wrapped every one of them
+        // in an elect / R2UR.BROADCAST / BRA.U.ANY loop (~75 cycles each; measured 770 cycles of issue work per tile against
+        // 640 cycles of tensor-pipe work); guarded by elect.sync they are straight-line UTCIMMA / UTCBAR.  Two warps issue
+        // (n_issuers = 2): warp 1 the even tiles (accumulator stage 0), warp 3 the odd tiles (stage 1), so the polls of
+        // one tile overlap the issue of the other.  Each warp's tcgen05.commit covers its own MMAs, hence every issuing
+        // warp arrives on a_empty after its last tile of a unit.
         const uint32_t my_par = static_cast<uint32_t>(warp >> 1);
         uint32_t tile0 = 0, unit_iter = 0;                          // tile0: running tile number at the start of the unit
         const uint64_t aext = umma_desc_sw32(base + offAExt);
@@ -205,10 +238,10 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const int as = unit_iter % kAStages;
             mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
             const uint64_t adesc = umma_desc_sw128(base + offA + as * kABytes);
-            const int first = static_cast<int>((my_par - tile0) & 1u);            // my first tile of this unit
-            const int last = first < u.n_tiles ? first + 2 * ((u.n_tiles - 1 - first) / 2) : -1;
+            const int first = n_issuers == 2 ? static_cast<int>((my_par - tile0) & 1u) : 0;   // my first tile of this unit
+            const int last = first < u.n_tiles ? first + n_issuers * ((u.n_tiles - 1 - first) / n_issuers) : -1;
             if (last < 0 && lane == 0) mbar_arrive(a_empty(as));                       // no tile of this unit is mine
-            for (int t = first; t < u.n_tiles; t += 2) {
+            for (int t = first; t < u.n_tiles; t += n_issuers) {
                 const uint32_t tile_iter = tile0 + t;
                 const int acc = tile_iter % kAccStages;
                 const int st = tile_iter % kBStages;
@@ -222,14 +255,14 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     while (!ok_acc) ok_acc = mbar_try_wait(acc_empty(acc), par_acc);
                 }
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint64_t bdesc = umma_desc_sw128(base + offB + st * kBBytes);
                     const uint64_t edesc = umma_desc_sw32(base + offE + st * kEBytes);
                     const uint32_t d = tmem_base + acc * BN;
 #pragma unroll
                     for (int k = 0; k < KB / 32; ++k)
                         umma_i8(d, adesc + 2 * k, bdesc + 2 * k, kIdesc, k > 0);
-                    umma_i8(d, aext, edesc, kIdescExt, 1);          // += -(|b|^2 >> 1)
+                    if (kNorm) umma_i8(d, aext, edesc, kIdescExt, 1);          // += -(|b|^2 >> 1)
                     // two commits (B stage -> producer, accumulator -> epilogue): one shared mbarrier for both waiters
                     // measured 4 % slower
                     umma_commit(b_empty(st));
@@ -255,7 +288,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t tile_iter = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
-            int32_t m1 = -1, m2 = -1, m3 = -1, m4 = -1;
+            int32_t m1 = -1, m2 = -1, m3 = -1, m4 = -1, m5 = -1;        // m5: fifth-best chunk key (kNorm = false only)
             const int t_first = kParity == 2 ? static_cast<int>((parity - tile_iter) & 1u) : 0;   // first tile of this unit we own
             int seq = 0;
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
@@ -295,16 +328,18 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     const int32_t b0 = __vimax3_s32(a[0], a[1], a[2]), b1 = __vimax3_s32(a[3], a[4], a[5]);
                     const int32_t b2 = __vimax3_s32(a[6], a[7], a[8]), b3 = max(a[9], a[10]);
                     const int32_t cmax = max(__vimax3_s32(b0, b1, b2), b3);
-                    top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - (seq + c)), m1, m2, m3, m4);
+                    if (kNorm) top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - (seq + c)), m1, m2, m3, m4);
+                    else top5_max(cmax * (1 << kSeqBits) + (511 - (seq + c)), m1, m2, m3, m4, m5);   // 0 <= a.b < 2^22
                 }
                 seq += kChunksPerVisit;
             }
-            // ---- unit end: to (D + bias, -global chunk) 64-bit keys, merge the four groups, write the candidates
-            int64_t r[4];
+            // ---- unit end: to (D + bias, -global chunk) 64-bit keys, merge the groups, write the candidates
+            constexpr int kKeys = kNorm ? 4 : 5;                    // the fifth key only carries a value
+            int64_t r[5];
             {
-                const int32_t mk[4] = {m1, m2, m3, m4};
+                const int32_t mk[5] = {m1, m2, m3, m4, m5};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < kKeys; ++i) {
                     if (mk[i] < 0) { r[i] = kEmpty; continue; }
                     const int sq = 511 - (mk[i] & 511);
                     const int gch = (t_first + kParity * (sq / kChunksPerVisit)) * (BN / 32) + half * kChunksPerVisit + (sq % kChunksPerVisit);
@@ -313,33 +348,48 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             if (group != 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) merge[((group - 1) * BM + row_in_unit) * 4 + i] = r[i];
+                for (int i = 0; i < kKeys; ++i) merge[((group - 1) * BM + row_in_unit) * 5 + i] = r[i];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(128 * kGroups) : "memory");
             if (group == 0) {
                 for (int g = 0; g < kGroups - 1; ++g)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) top4_max64(merge[(g * BM + row_in_unit) * 4 + i], r[0], r[1], r[2], r[3]);
+                    for (int i = 0; i < kKeys; ++i) {
+                        const int64_t k = merge[(g * BM + row_in_unit) * 5 + i];
+                        if (kNorm) top4_max64(k, r[0], r[1], r[2], r[3]);
+                        else top5_max64(k, r[0], r[1], r[2], r[3], r[4]);
+                    }
                 const int row = u.rb * BM + row_in_unit;
                 if (row < u.pd.nq) {
-                    // value part 0 (D == -bias) is a chunk of padding rows only
-                    int32_t vv[4], ch[4];
-                    bool has[4];
+                    int32_t vv[5], ch[5];
+                    bool has[5];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < kKeys; ++i) {
                         vv[i] = static_cast<int32_t>(r[i] >> 32);
                         ch[i] = 0x7FFFFFFF - static_cast<int32_t>(r[i] & 0xFFFFFFFF);
+                        // value part 0: kNorm: D == -bias, a chunk of padding rows only; norm-less: a.b == 0, padding rows or
+                        // rows orthogonal to the query (the refine pass treats everything outside the candidates as a.b <= V5)
                         has[i] = r[i] != kEmpty && vv[i] > 0;
                     }
                     Top2 o;
-                    o.i0 = has[0] ? ch[0] : -1;                                          // chunk of the best D
-                    o.i1 = has[1] ? ch[1] : -1;                                          // second chunk
-                    if (has[1] && has[2] && vv[2] == vv[1]) {
-                        o.i0 |= (ch[2] + 1) << 16;                                       // a third chunk ties the second
-                        if (has[3] && vv[3] == vv[1]) o.i1 |= 0x40000000;                // and a fourth: ambiguous
+                    if (kNorm) {
+                        o.i0 = has[0] ? ch[0] : -1;                                          // chunk of the best D
+                        o.i1 = has[1] ? ch[1] : -1;                                          // second chunk
+                        if (has[1] && has[2] && vv[2] == vv[1]) {
+                            o.i0 |= (ch[2] + 1) << 16;                                       // a third chunk ties the second
+                            if (has[3] && vv[3] == vv[1]) o.i1 |= 0x40000000;                // and a fourth: ambiguous
+                        }
+                        o.d0 = __int_as_float(vv[0] - kValueBias);
+                        o.d1 = __int_as_float(vv[1] - kValueBias);
+                    } else {
+                        // four candidate chunks (0xFFFF = none; only chunks with a positive maximum, i.e. with a real row),
+                        // V1, V2 and V5 >= 0 = an upper bound of a.b for every train row outside those chunks
+                        o.i0 = (has[0] ? ch[0] : 0xFFFF) | (has[1] ? ch[1] : 0xFFFF) << 16;
+                        o.i1 = (has[2] ? ch[2] : 0xFFFF) | (has[3] ? ch[3] : 0xFFFF) << 16;
+                        o.d0 = __int_as_float(has[0] ? vv[0] : -1);
+                        o.d1 = __int_as_float(has[1] ? vv[1] : -1);
+                        aux[u.pd.out_row0 + row] = has[4] ? vv[4] : 0;
                     }
-                    o.d0 = __int_as_float(vv[0] - kValueBias);
-                    o.d1 = __int_as_float(vv[1] - kValueBias);
                     out[u.pd.out_row0 + row] = o;
                 }
             }
@@ -352,15 +402,16 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int kParity, int kHalves, int kBN>
+template <int kParity, int kHalves, int kBN, bool kNorm>
 static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
-                              const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int grid, cudaStream_t s) {
+                              const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int32_t* aux, int grid,
+                              int issuers, cudaStream_t s) {
     // per launch: the attribute is per device, and one process may drive several GPUs
-    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN>,
+    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, tcv::Cfg<kBN>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
-        ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out);
+    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
+        ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out, aux, issuers);
     return cudaGetLastError();
 }
 
@@ -370,7 +421,8 @@ static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, cons
 // tmap_e must have 128-row boxes) or 256 (two stages, 256-row boxes).
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int sm_count, int layout, int tile_rows, cudaStream_t s) {
+                                  Top2* out, int32_t* aux /* non-null selects the norm-less variant */, int sm_count, int layout,
+                                  int tile_rows, int issuers, cudaStream_t s) {
     if (n_units == 0) return cudaSuccess;
     const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
@@ -378,7 +430,8 @@ cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_ho
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
 #define SFM_TCV_CASE(P, H, T)                                                                                          \
     if (layout == 10 * P + H && tile_rows == T)                                                                        \
-        return launch_tcv<P, H, T>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, grid, s);
+        return aux ? launch_tcv<P, H, T, false>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s) \
+                   : launch_tcv<P, H, T, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s);
     SFM_TCV_CASE(1, 2, 256) SFM_TCV_CASE(1, 4, 256) SFM_TCV_CASE(2, 1, 256)
 #undef SFM_TCV_CASE
     return cudaErrorInvalidValue;

@@ -115,7 +115,7 @@ knn2_l2_f32_tc3_kernel(const __grid_constant__ CUtensorMap tmap_hi_a, const __gr
             const UnitInfoF u = decode_unit_f(pairs, unit_prefix, n_pairs, unit);
             if (u.n_tiles == 0) continue;
             mbar_wait(a_empty, (unit_iter & 1) ^ 1);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(a_full, kABytes);
                 const int row = u.pd.q_row0 + u.rb * BM;
 #pragma unroll
@@ -129,7 +129,7 @@ knn2_l2_f32_tc3_kernel(const __grid_constant__ CUtensorMap tmap_hi_a, const __gr
                 for (int sl = 0; sl < kSlabs; ++sl, ++slab_iter) {
                     const int st = slab_iter % kBStages;
                     mbar_wait(b_empty(st), ((slab_iter / kBStages) & 1) ^ 1);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(b_full(st), kBStageBytes + (sl == 0 ? kEBytes : 0));
                         tma_load_2d(base + offB + st * kBStageBytes, &tmap_hi_b, sl * 128, row, b_full(st));
                         tma_load_2d(base + offB + st * kBStageBytes + kSlabBytesB, &tmap_lo_b, sl * 128, row, b_full(st));
@@ -158,7 +158,7 @@ knn2_l2_f32_tc3_kernel(const __grid_constant__ CUtensorMap tmap_hi_a, const __gr
                     const int st = slab_iter % kBStages;
                     mbar_wait(b_full(st), (slab_iter / kBStages) & 1);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint64_t a_hi = umma_desc_sw128(base + offA + sl * kSlabBytesA);
                         const uint64_t a_lo = umma_desc_sw128(base + offA + (kSlabs + sl) * kSlabBytesA);
                         const uint64_t b_hi = umma_desc_sw128(base + offB + st * kBStageBytes);

@@ -68,7 +68,8 @@ cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, 
 // value-only epilogue (see common.cuh)
 __global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t padded_rows,
                                    const int32_t* __restrict__ valid_in_block, int32_t* __restrict__ norm2,
-                                   int32_t* __restrict__ ckey, int8_t* __restrict__ ext, int* __restrict__ max_norm2) {
+                                   int32_t* __restrict__ ckey, int8_t* __restrict__ ext, int* __restrict__ max_norm2,
+                                   int32_t* __restrict__ blk_min, int32_t* __restrict__ blk_max) {
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= padded_rows) return;
@@ -82,7 +83,12 @@ __global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t pad
         norm2[row] = static_cast<int32_t>(s);
         // key = (|b|^2 - 2ab) * 256 + col  ==  ckey - 512 * ab
         ckey[row] = valid ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col)) : (kSentinelKey | col);
-        if (valid) atomicMax(max_norm2, static_cast<int>(s));
+        if (valid) {
+            atomicMax(max_norm2, static_cast<int>(s));
+            atomicMin(max_norm2 + 1, static_cast<int>(s));
+            atomicMin(blk_min + row / kRowAlign, static_cast<int>(s));      // |b|^2 range of the block: bounds of the
+            atomicMax(blk_max + row / kRowAlign, static_cast<int>(s));      // norm-less path (refine_dot_kernel)
+        }
     }
     // digit of lane p: weight 255 at positions with (p & 15) < 12, weight 1 otherwise
     int digit = 128;
@@ -96,11 +102,12 @@ __global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t pad
 }
 
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* valid_in_block,
-                               int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, cudaStream_t s) {
+                               int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, int32_t* blk_min, int32_t* blk_max,
+                               cudaStream_t s) {
     if (padded_rows == 0) return cudaSuccess;
     const int64_t threads = padded_rows * 32;
     norms_ckeys_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(bank, padded_rows, valid_in_block,
-                                                                                     norm2, ckey, ext, max_norm2);
+                                                                                     norm2, ckey, ext, max_norm2, blk_min, blk_max);
     return cudaGetLastError();
 }
 
@@ -392,6 +399,159 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
         }
     }
     if (valid) a.top2[srow] = o;        // rows that cannot pass keep i0 = -1 (rejected)
+}
+
+// ------------------------------------------------------------------------------------------------ refine (norm-less)
+// Input per query row, from knn2_l2_u8_tcv_kernel<.., kNorm = false>: up to four candidate chunks (i0 = c0 | c1 << 16,
+// i1 = c2 | c3 << 16, 0xFFFF = none; only chunks whose maximum is > 0, so every candidate chunk holds a real row) ranked
+// by chunk maximum of the raw dot product, V1 = d0, V2 = d1 (int bits, -1 = none) and aux = V5 >= 0, an upper bound of
+// a.b for every train row outside the candidate chunks (zero-padding rows and orthogonal rows have a.b = 0).
+// With N- <= |b|^2 <= N+ over the train image (per-block ranges from norms_ckeys_kernel):
+//     every train row                   : d^2 >= |a|^2 + N- - 2 V1
+//     the best rows of chunks 1 and 2   : d^2 <= |a|^2 + N+ - 2 V2          (two different rows)
+//     every row outside the four chunks : d^2 >= |a|^2 + N- - 2 V5  =: lbo
+// (1) rows with sqrtf(|a|^2 + N- - 2 V1) >= ratio * sqrtf(|a|^2 + N+ - 2 V2) cannot pass the ratio test: rejected.
+// (2) the others recompute their <= 128 candidate rows exactly (__dp4a) -> (e0, j0), (e1, j1), exact within the chunks.
+//     e0 < lbo certifies (e0, j0) as THE nearest neighbour (ties resolve to the lowest index inside the chunks; a tie
+//     with an outside row is excluded by the strict '<').  The second neighbour's d1^2 lies in [min(e1, lbo), e1]; the
+//     ratio test  sqrtf(e0) < ratio * sqrtf(d1^2)  is monotone in d1^2, so it is decided if both ends agree, and the
+//     reported (d0, idx0) never depends on d1.  In that case d1 is written as the end that was used (keep_basic re-runs
+//     the same comparison); the lists equal cv::BFMatcher + ratio test bit for bit.
+// (3) anything else (not certified, or the two ends disagree) is brute-forced over the whole train image.
+__global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
+    __shared__ int s_min[8], s_max[8];
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // the 256 staged rows of a CTA belong to one pair: the train image's |b|^2 range, once per CTA
+    int nbmin = INT_MAX, nbmax = 0;
+    {
+        const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 256;
+        const int p = find_segment(a.out_prefix, a.n_pairs, r0 < a.staged_rows ? r0 : a.staged_rows - 1);
+        const PairDesc pd = a.pairs[p];
+        const int b0 = pd.t_row0 / kRowAlign, nb = (pd.nt + kRowAlign - 1) / kRowAlign;
+        for (int b = threadIdx.x; b < nb; b += 256) { nbmin = min(nbmin, a.blk_min[b0 + b]); nbmax = max(nbmax, a.blk_max[b0 + b]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nbmin = min(nbmin, __shfl_xor_sync(0xffffffffu, nbmin, o));
+            nbmax = max(nbmax, __shfl_xor_sync(0xffffffffu, nbmax, o));
+        }
+        if (lane == 0) { s_min[wid] = nbmin; s_max[wid] = nbmax; }
+        __syncthreads();
+        nbmin = s_min[0]; nbmax = s_max[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { nbmin = min(nbmin, s_min[w]); nbmax = max(nbmax, s_max[w]); }
+    }
+    bool need = false, valid = false;
+    Top2 t;
+    t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
+    int v5 = -1, na = 0, q_bank_row = 0, t_row0 = 0, nt = 0;
+    if (srow < a.staged_rows) {
+        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        const PairDesc pd = a.pairs[p];
+        const int row = static_cast<int>(srow - a.out_prefix[p]);
+        if (row < pd.nq && pd.nt > 0) {
+            valid = true;
+            t = a.top2[srow];
+            v5 = a.aux[srow];
+            q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
+            na = a.norm2[q_bank_row];
+            const int V1 = __float_as_int(t.d0), V2 = __float_as_int(t.d1);
+            if (a.all_rows || V2 <= 0) need = true;                           // fewer than two chunks with a real maximum
+            else {
+                const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na + nbmin - 2 * V1)));
+                const float hi1 = __fsqrt_rn(static_cast<float>(max(0, na + nbmax - 2 * V2)));
+                need = static_cast<double>(lo0) < static_cast<double>(hi1) * a.ratio;
+            }
+        } else if (row < pd.nq) {
+            valid = true;                                                     // empty train image: no neighbours
+        }
+    }
+    const float inf = __int_as_float(0x7f800000);
+    Top2 o;
+    o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
+    unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (lane == 0 && mask) atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
+        const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
+        const int ntr = __shfl_sync(0xffffffffu, nt, src);
+        const int i0 = __shfl_sync(0xffffffffu, t.i0, src), i1 = __shfl_sync(0xffffffffu, t.i1, src);
+        const int rv5 = __shfl_sync(0xffffffffu, v5, src);
+        const int rna = __shfl_sync(0xffffffffu, na, src);
+        uint4 q[8];
+        const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
+        const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
+        long long a1 = LLONG_MAX, a2 = LLONG_MAX;
+        int covered = 0;                                                // real train rows inside the candidate chunks
+        for (int k = 0; k < 4; ++k)
+            if (cand[k] != 0xFFFF) {
+                warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[k], lane, a1, a2);
+                covered += max(0, min(32, ntr - 32 * cand[k]));
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+            a2 = min(max(a1, b1), min(a2, b2));
+            a1 = min(a1, b1);
+        }
+        // decide (all lanes hold the same a1, a2)
+        bool done = false;
+        float out_d1 = inf;
+        int out_i1 = -1;
+        const bool outside = covered < ntr;                             // train rows exist outside the candidate chunks
+        const long long lbo = outside ? static_cast<long long>(rna) + nbmin - 2ll * rv5 : LLONG_MAX;
+        if (a1 != LLONG_MAX) {
+            const long long e0 = a1 >> 32;
+            if (!outside) {                                             // the chunks cover the whole train image: exact
+                done = true;
+                if (a2 != LLONG_MAX) { out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll); out_d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
+            } else if (e0 < lbo && !a.all_rows) {
+                const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
+                const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
+                const long long lb1 = min(e1, lbo);                     // <= true d1^2 <= e1 (e1 = none: only the bound)
+                const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb1)))) * a.ratio;
+                if (e1 == LLONG_MAX) {
+                    // a second neighbour exists outside the chunks (outside == true): only 'pass at the lower end' decides
+                    if (pass_lo) { done = true; out_i1 = ntr; out_d1 = static_cast<float>(static_cast<int32_t>(lb1)); }
+                } else {
+                    const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)))) * a.ratio;
+                    if (pass_lo == pass_hi) {
+                        done = true;
+                        out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll);
+                        out_d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lb1 : e1));
+                    }
+                }
+            }
+        }
+        if (!done) {                                                    // exact brute force over the whole train image
+            if (lane == 0) atomicAdd(a.stats + 1, 1ull);
+            a1 = LLONG_MAX; a2 = LLONG_MAX;
+            for (int c = 0; c * 32 < ntr; ++c) warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, c, lane, a1, a2);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+                a2 = min(max(a1, b1), min(a2, b2));
+                a1 = min(a1, b1);
+            }
+            out_i1 = -1; out_d1 = inf;
+            if (a2 != LLONG_MAX) { out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll); out_d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
+        }
+        if (lane == src) {
+            if (a1 != LLONG_MAX) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(a1 >> 32)); }
+            o.i1 = out_i1; o.d1 = out_d1;
+        }
+    }
+    if (valid) a.top2[srow] = o;        // rows that cannot pass keep i0 = -1 (rejected)
+}
+
+cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    refine_dot_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
 }
 
 static inline unsigned chunks_of(int64_t rows) { return static_cast<unsigned>((rows + 255) / 256); }

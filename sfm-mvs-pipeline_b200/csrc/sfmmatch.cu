@@ -68,6 +68,8 @@ struct Bank {
     std::vector<int32_t> n_rows;
     std::vector<int64_t> row0;
     int64_t padded_rows = 0;
+    DevBuf d_blkmin, d_blkmax;       // |b|^2 range per 256-row block (norm-less value-only path)
+    int32_t nb_min = 0, nb_max = 0;  // |b|^2 range over the valid rows of the bank
     DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid, d_ext, d_bits;     // d_bits: ORB bits expanded to bytes (256 B rows)
     alignas(64) CUtensorMap tmap_a, tmap_b, tmap_e;
     bool ext_ok = false;             // every |b|^2 <= kExtMaxNorm2: the value-only tcgen05 kernel may be used
@@ -77,7 +79,7 @@ struct Bank {
     bool f_tc_ok = false;
     float f_nb_max = 0.f;
     bool have_tmap = false;
-    void release() { d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release();
+    void release() { d_blkmin.release(); d_blkmax.release(); d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release();
                      d_fhi.release(); d_flo.release(); d_fnorm.release(); d_fext.release(); }
 };
 
@@ -128,6 +130,8 @@ struct sfm_ctx {
     int prof_used = 0;
     size_t staging_budget_rows = 0;
     int tcv_layout_run = 12;
+    int tcv_normless = 1;            // norm-less variant of the value-only kernel: SFM_TCV_NORMLESS = 0 never | 1 auto | 2 always
+    int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
 };
@@ -258,8 +262,9 @@ int bank_finish(sfm_ctx* c, Bank& b) {
     CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid, static_cast<size_t>(nblk) * 4, cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaEventRecord(c->valid_ev, s));
     const int32_t* d_valid = b.d_valid.as<int32_t>();
-    int* flags = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 16);      // [0] not-integer, [1] max |b|^2
+    int* flags = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 16);      // [0] not-integer, [1] max |b|^2, [2] min |b|^2
     CU_TRY(c, cudaMemsetAsync(flags, 0, 8, s));
+    CU_TRY(c, cudaMemsetAsync(flags + 2, 0x7f, 4, s));
     bool maybe_u8 = b.depth == SFM_CV_8U;
     if (b.depth == SFM_CV_32F && b.cols == 128) {
         CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
@@ -283,12 +288,18 @@ int bank_finish(sfm_ctx* c, Bank& b) {
         CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
         CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
         CU_TRY(c, b.d_ext.ensure(static_cast<size_t>(b.padded_rows) * kExtBytes));
+        const size_t nblk_b = static_cast<size_t>(b.padded_rows / kRowAlign) * 4;
+        CU_TRY(c, b.d_blkmin.ensure(nblk_b));
+        CU_TRY(c, b.d_blkmax.ensure(nblk_b));
+        CU_TRY(c, cudaMemsetAsync(b.d_blkmin.p, 0x7f, nblk_b, s));
+        CU_TRY(c, cudaMemsetAsync(b.d_blkmax.p, 0, nblk_b, s));
         CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>(), b.padded_rows, d_valid, b.d_norm2.as<int32_t>(),
-                                     b.d_ckey.as<int32_t>(), b.d_ext.as<int8_t>(), flags + 1, s));
+                                     b.d_ckey.as<int32_t>(), b.d_ext.as<int8_t>(), flags + 1, b.d_blkmin.as<int32_t>(),
+                                     b.d_blkmax.as<int32_t>(), s));
         c->stat_launches++;
     }
     int* h = c->h_scalars.as<int>() + 8;
-    CU_TRY(c, cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaMemcpyAsync(h, flags, 12, cudaMemcpyDeviceToHost, s));
     CU_TRY(c, cudaStreamSynchronize(s));
     b.ext_ok = false;
     if (b.depth == SFM_CV_32F) {
@@ -320,7 +331,7 @@ int bank_finish(sfm_ctx* c, Bank& b) {
     } else {
         b.u8_valued = true;
     }
-    if (b.u8_valued && b.cols == 128) b.ext_ok = h[1] <= kExtMaxNorm2;
+    if (b.u8_valued && b.cols == 128) { b.ext_ok = h[1] <= kExtMaxNorm2; b.nb_max = h[1]; b.nb_min = std::min(h[2], h[1]); }
     return make_tmaps(c, b);
 }
 
@@ -375,7 +386,7 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
 }
 
 // ------------------------------------------------------------------------------------------------ the stage
-enum class Engine { TC, TCV, TF32, DP4A, F32, POPC };
+enum class Engine { TC, TCV, TCN, TF32, DP4A, F32, POPC };
 
 int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out) {
     if (norm == SFM_NORM_HAMMING) {
@@ -412,7 +423,11 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            c->sm_count, c->tcv_layout_run, 256, s));
+                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, s));
+            break;
+        case Engine::TCN:
+            CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
+                                            reinterpret_cast<int32_t*>(aux), c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, s));
             break;
         case Engine::TF32:
             CU_TRY(c, launch_knn2_l2_f32_tc3(b.tmaps_f, d_pairs, d_unit_prefix, n_pairs, n_units, out, aux, c->sm_count, s));
@@ -433,7 +448,7 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
 
 int rows_per_unit(Engine e) {
     return e == Engine::F32 ? kF32RowsPerUnit
-                            : ((e == Engine::TC || e == Engine::TCV || e == Engine::TF32) ? kTcRowsPerUnit : kSimtRowsPerUnit);
+                            : ((e == Engine::TC || e == Engine::TCV || e == Engine::TCN || e == Engine::TF32) ? kTcRowsPerUnit : kSimtRowsPerUnit);
 }
 
 // Optional processing schedule of enqueue_impl (pipelined host path): order[k] = input index of the k-th scheduled
@@ -473,7 +488,13 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         // 2 epilogue groups (8 warps, layout 12) measured fastest; their 32-bit keys cover train images up to 32768
         // rows, 4 groups (layout 14) up to 65536
         c->tcv_layout_run = c->tcv_layout ? c->tcv_layout : (max_rows <= 32768 ? 12 : 14);
-        if (max_rows <= (c->tcv_layout_run == 14 ? 65536 : 32768)) eng = Engine::TCV;
+        if (max_rows <= (c->tcv_layout_run == 14 ? 65536 : 32768)) {
+            eng = Engine::TCV;
+            // norms within 1/16 of each other (SIFT: ~1 %): the norm-less variant, one K-step less per tile; its bounds
+            // lose their grip when norms vary a lot, the exactness does not depend on the choice
+            if (c->tcv_normless == 2 || (c->tcv_normless == 1 && static_cast<int64_t>(b.nb_max - b.nb_min) * 16 <= b.nb_max))
+                eng = Engine::TCN;
+        }
     }
     for (int64_t p = 0; p < n_pairs; ++p) {
         const int l = pairs[2 * p], r = pairs[2 * p + 1];
@@ -585,7 +606,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
 
     CU_TRY(c, c->d_top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
     if (need_rev) CU_TRY(c, c->d_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
-    if (eng == Engine::TF32) {
+    if (eng == Engine::TF32 || eng == Engine::TCN) {
         CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
         CU_TRY(c, c->d_aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
         if (need_rev) CU_TRY(c, c->d_aux_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
@@ -643,12 +664,15 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
                 c->stat_launches++;
             }
         }
-        if ((eng == Engine::TC || eng == Engine::TCV) && o->k == 2 && !need_rev) {
-            RefineArgs ra;
+        if ((eng == Engine::TC || eng == Engine::TCV || eng == Engine::TCN) && o->k == 2 && !need_rev) {
+            RefineArgs ra{};
+            ra.aux = c->d_aux.as<int32_t>(); ra.blk_min = b.d_blkmin.as<int32_t>(); ra.blk_max = b.d_blkmax.as<int32_t>();
+            ra.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
             ra.all_rows = 0; ra.ratio = o->ratio; ra.hamming = o->norm == SFM_NORM_HAMMING;
-            if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
+            if (eng == Engine::TCN) CU_TRY(c, launch_refine_dot(ra, s));
+            else if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
             else CU_TRY(c, launch_refine_second(ra, s));
             c->stat_launches++;
         }
@@ -803,8 +827,14 @@ int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int3
     CU_TRY(c, cudaEventRecord(c->valid_ev, cs));
     int* flags = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 16);
     CU_TRY(c, cudaMemsetAsync(flags, 0, 8, cs));
-    // optimistic bank properties (verified below)
-    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true;
+    CU_TRY(c, cudaMemsetAsync(flags + 2, 0x7f, 4, cs));
+    const size_t nblk_b = static_cast<size_t>(nblk) * 4;
+    CU_TRY(c, b.d_blkmin.ensure(nblk_b));
+    CU_TRY(c, b.d_blkmax.ensure(nblk_b));
+    CU_TRY(c, cudaMemsetAsync(b.d_blkmin.p, 0x7f, nblk_b, cs));
+    CU_TRY(c, cudaMemsetAsync(b.d_blkmax.p, 0, nblk_b, cs));
+    // optimistic bank properties (verified below): integer-valued SIFT-like rows whose norms vary little
+    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true; b.nb_min = b.nb_max = 1;
     rc = make_tmaps(c, b);
     if (rc != SFM_OK) return rc;
     // ---- image groups of roughly equal size
@@ -850,14 +880,15 @@ int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int3
                 CU_TRY(c, launch_zero_padding(b.d_u8.as<uint8_t>() + r0 * 128, 128, r1 - r0, d_valid + r0 / kRowAlign, cs));
             CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>() + r0 * 128, r1 - r0, d_valid + r0 / kRowAlign,
                                          b.d_norm2.as<int32_t>() + r0, b.d_ckey.as<int32_t>() + r0,
-                                         b.d_ext.as<int8_t>() + r0 * kExtBytes, flags + 1, cs));
+                                         b.d_ext.as<int8_t>() + r0 * kExtBytes, flags + 1,
+                                         b.d_blkmin.as<int32_t>() + r0 / kRowAlign, b.d_blkmax.as<int32_t>() + r0 / kRowAlign, cs));
             c->stat_launches += 2;
         }
         CU_TRY(c, cudaEventRecord(c->group_ev[g], cs));
         first = last;
     }
     int* h = c->h_scalars.as<int>() + 8;
-    CU_TRY(c, cudaMemcpyAsync(h, flags, 8, cudaMemcpyDeviceToHost, cs));
+    CU_TRY(c, cudaMemcpyAsync(h, flags, 12, cudaMemcpyDeviceToHost, cs));
     // ---- schedule pairs by the group that completes them
     std::vector<int64_t> order(n_pairs);
     std::vector<int> avail_in(n_pairs), avail(n_pairs);
@@ -872,6 +903,7 @@ int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int3
     rc = enqueue_impl(c, pairs, n_pairs, o, &sc);
     CU_TRY(c, cudaStreamSynchronize(cs));
     if (rc != SFM_OK) return rc;
+    b.nb_max = h[1]; b.nb_min = std::min(h[2], h[1]);
     if (h[0] != 0 || h[1] > kExtMaxNorm2) {
         // not integer-valued, or norms beyond the digit range: the optimistic run is void -> sequential path
         CU_TRY(c, cudaStreamSynchronize(s));
@@ -925,6 +957,8 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     size_t mb = 512;
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
+    if (const char* env = std::getenv("SFM_TCV_NORMLESS")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_normless = t; }
+    if (const char* env = std::getenv("SFM_TCV_ISSUERS")) { const int t = std::atoi(env); if (t == 1 || t == 2) c->tcv_issuers = t; }
     if (const char* env = std::getenv("SFM_TCV_LAYOUT")) { const int g = std::atoi(env); if (g == 12 || g == 14 || g == 21 || g == 22) c->tcv_layout = g; }
     *out = c;
     return SFM_OK;
@@ -1171,7 +1205,7 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
         c->stat_launches++;
     }
     if (eng == Engine::TC && k == 2) {
-        RefineArgs ra;
+        RefineArgs ra{};
         ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd;
         ra.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
         ra.n_pairs = 1; ra.staged_rows = pad_rows(nq); ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();

@@ -217,6 +217,22 @@ def test_value_only_kernel_ties_and_fallback(sfm, matcher):
         res = matcher.match_pairs(pairs, NORM_L2, ratio=0.95, engine=eng)
         for p in range(len(pairs)):
             assert orc.dmatch_equal(res[p], exp[p]), (eng, pairs[p].tolist())
+    # the norm-less variant forced onto this bank (zero rows, duplicates, one-row images: its bounds are useless here,
+    # its certificate / brute-force fallback must still give the exact lists)
+    import os
+    os.environ["SFM_TCV_NORMLESS"] = "2"
+    try:
+        m2 = sfm.Matcher(0)
+        m2.upload_bank(bank)
+        for ratio in (0.95, 0.7, 1.0, 0.0):
+            exp_r = exp if ratio == 0.95 else orc.match_pairs(bank, pairs, NORM_L2, ratio=ratio)
+            res = m2.match_pairs(pairs, NORM_L2, ratio=ratio)
+            for p in range(len(pairs)):
+                assert orc.dmatch_equal(res[p], exp_r[p]), ("normless", ratio, pairs[p].tolist())
+        assert m2.float_stats()["rows_reranked"] > 0
+        m2.close()
+    finally:
+        del os.environ["SFM_TCV_NORMLESS"]
     # ratio 1.0 / 0.0 edge cases of the provisional bound
     for ratio in (1.0, 0.0, 0.3):
         exp = orc.match_pairs(bank, pairs[:10], NORM_L2, ratio=ratio)
@@ -234,12 +250,15 @@ def test_value_only_kernel_ties_and_fallback(sfm, matcher):
         assert orc.dmatch_equal(res[p], exp[p])
 
 
-@pytest.mark.parametrize("layout", [12, 14, 21])
-def test_value_only_kernel_epilogue_layouts(sfm, layout, monkeypatch):
+@pytest.mark.parametrize("layout,issuers,normless", [(12, 2, 1), (12, 2, 0), (12, 1, 1), (14, 2, 1), (14, 2, 0), (21, 2, 1),
+                                                     (21, 1, 0)])
+def test_value_only_kernel_epilogue_layouts(sfm, layout, issuers, normless, monkeypatch):
     """Every epilogue organisation of the value-only kernel (SFM_TCV_LAYOUT: column halves / column quarters of every
     tile, alternate tiles) and the two MMA-issuing warps give the oracle's lists bit for bit, including units with a
     single train tile (one issuing warp has nothing to do), odd tile counts and > 32768-row train images (layout 14)."""
     monkeypatch.setenv("SFM_TCV_LAYOUT", str(layout))
+    monkeypatch.setenv("SFM_TCV_ISSUERS", str(issuers))
+    monkeypatch.setenv("SFM_TCV_NORMLESS", str(normless))
     m = sfm.Matcher(0)
     try:
         sizes = [700, 256, 1, 130, 2049, 513, 300]               # 1, 2, 3, 9 train tiles; units of 1..17 query blocks

@@ -126,16 +126,16 @@ static void run(const char* name, Params p, const uint8_t* gsrc, long long* d_cy
 // Tight issue loop: compile-time N / K-steps / accumulator pattern, nothing but tcgen05.mma in the loop.
 //   kIndep = 1: one accumulator per tile (dependent chain of kK MMAs);  2: two tiles interleaved (A k0, B k0, A k1, ...)
 template <int kN, int kK, int kIndep>
-__global__ void __launch_bounds__(640, 1) k_tight(int tiles, long long* cyc, int ld_warps, int ld_iters, int alu, uint32_t* sink) {
+__global__ void __launch_bounds__(640, 1) k_tight(int tiles, long long* cyc, int ld_warps, int ld_iters, int alu, uint32_t* sink, int commits, int ext) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t offA = 0, offB = 16384, offBar = 16384 + 32768, offT = offBar + 64;
-    const uint32_t bar_mma = base + offBar;
+    const uint32_t bar_mma = base + offBar, bar_c1 = base + offBar + 8, bar_c2 = base + offBar + 16;
     volatile uint32_t* tptr = reinterpret_cast<volatile uint32_t*>(bp + offT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(bp)[i] = i * 2654435761u;
-    if (warp == 1 && lane == 0) { mbar_init(bar_mma, 1); fence_barrier_init(); }
+    if (warp == 1 && lane == 0) { mbar_init(bar_mma, 1); mbar_init(bar_c1, 1); mbar_init(bar_c2, 1); fence_barrier_init(); }
     if (warp == 2) { tmem_alloc(base + offT, 512); tmem_relinquish(); }
     fence_proxy_async();
     tc_fence_before();
@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(640, 1) k_tight(int tiles, long long* cyc, int
                 for (int j = 0; j < kIndep; ++j)
                     umma_i8(d0 + j * (kN % 256), ad + 2 * (k & 3), bd + 2 * (k & 3), idesc, k > 0 ? 1u : 0u);
             }
+            if (ext) umma_i8(d0, umma_desc_sw32(base + offA), umma_desc_sw32(base + offB), umma_idesc_u8s8(128, kN), 1u);
+            if (commits > 0) umma_commit(bar_c1);
+            if (commits > 1) umma_commit(bar_c2);
         }
         umma_commit(bar_mma);
         mbar_wait(bar_mma, 0);
@@ -202,11 +205,12 @@ __global__ void __launch_bounds__(640, 1) k_tight(int tiles, long long* cyc, int
 }
 
 template <int kN, int kK, int kIndep>
-static void run_tight(long long* d_cyc, int ld_warps = 0, int alu = 0, uint32_t* d_sink = nullptr) {
+static void run_tight(long long* d_cyc, int ld_warps = 0, int alu = 0, uint32_t* d_sink = nullptr, int commits = 0, int ext = 0) {
     const int grid = 148, smem = 16384 + 32768 + 1024 + 2048, tiles = 8192;
     cudaFuncSetAttribute(k_tight<kN, kK, kIndep>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int ld_iters = ld_warps ? tiles * 2 : 0;   // 4 chunks x half the columns per iteration = one tile per 2 iterations per group
-    k_tight<kN, kK, kIndep><<<grid, 128 + 32 * ld_warps, smem>>>(tiles, d_cyc, ld_warps, ld_iters, alu, d_sink);
+    k_tight<kN, kK, kIndep><<<grid, 128 + 32 * ld_warps, smem>>>(tiles, d_cyc, ld_warps, ld_iters, alu, d_sink, commits, ext);
+    if (commits || ext) printf("[commits/tile=%d ext-mma=%d] ", commits, ext);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[296];
     cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
@@ -227,6 +231,10 @@ int main() {
     cudaMalloc(&d_cyc, 148 * 4 * 8);
     cudaMemset(d_cyc, 0, 148 * 4 * 8);
     cudaMalloc(&d_sink, 4096);
+    for (int cm : {0, 1, 2}) run_tight<256, 5, 1>(d_cyc, 0, 0, d_sink, cm, 0);
+    for (int cm : {0, 2}) run_tight<256, 4, 1>(d_cyc, 0, 0, d_sink, cm, 1);
+    run_tight<256, 4, 1>(d_cyc, 8, 1, d_sink, 2, 1);
+    for (int cm : {0, 2}) run_tight<128, 4, 1>(d_cyc, 0, 0, d_sink, cm, 1);
     for (int w : {4, 8, 16}) for (int alu : {0, 1}) run_tight<256, 5, 1>(d_cyc, w, alu, d_sink);
     for (int w : {8}) for (int alu : {0, 1}) run_tight<256, 4, 1>(d_cyc, w, alu, d_sink);
     run_tight<64, 4, 1>(d_cyc); run_tight<64, 4, 2>(d_cyc); run_tight<64, 16, 1>(d_cyc);

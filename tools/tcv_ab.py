@@ -11,7 +11,15 @@ sfm = ge.load_package()
 n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 n_rows = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 m = sfm.Matcher(0)
-m.upload_bank(workloads.sift_like_bank(n_img, n_rows))
+bank = workloads.sift_like_bank(n_img, n_rows)
+if os.environ.get("RENORM"):      # cv::SIFT-like norms (every row rescaled to |b| = 512 and re-rounded: ~1 % spread of |b|^2)
+    out = []
+    for b in bank:
+        f = b.astype(np.float32)
+        f *= 512.0 / np.maximum(np.linalg.norm(f, axis=1, keepdims=True), 1e-9)
+        out.append(np.clip(np.rint(f), 0, 255).astype(np.uint8))
+    bank = out
+m.upload_bank(bank)
 pairs = sfm.select_pairs(n_img, 0, 0)
 m.set_profiling(True)
 best = None
@@ -25,4 +33,4 @@ ops = 2.0 * n_rows * n_rows * 128 * len(pairs)
 import subprocess
 clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
 print(f"[{clk}] layout={os.environ.get('SFM_TCV_LAYOUT','auto')} tile={os.environ.get('SFM_TCV_TILE','auto')}: knn {best[0]:.3f} ms "
-      f"post {best[1]:.3f} ms -> {len(pairs)/best[0]*1e3:.0f} pairs/s kernel-only, {ops/best[0]/1e9:.0f} TOP/s, matches={best[2]}")
+      f"stats={m.float_stats()} post {best[1]:.3f} ms -> {len(pairs)/best[0]*1e3:.0f} pairs/s kernel-only, {ops/best[0]/1e9:.0f} TOP/s, matches={best[2]}")
