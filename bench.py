@@ -316,6 +316,7 @@ def run_ours(a):
             part = shard.cuda_view(ptr, (hi - lo) * n_rows * 128, dev)
             parts = [gathered[r * n_img // world * n_rows * 128:(r + 1) * n_img // world * n_rows * 128] for r in range(world)]
             dist.all_gather(parts, part)
+            stream.wait_stream(torch.cuda.current_stream(dev))     # the library's stream reads `gathered` next
             tr.append(time.perf_counter())
             m.upload_bank_device(gathered.data_ptr(), offs, rows_per, 128, sfm.CV_8U)
         tr.append(time.perf_counter())
@@ -341,6 +342,7 @@ def run_ours(a):
         if world > 1:
             ps1 = packer.stats()
             h2d += ps1["h2d_bytes"] - ps0["h2d_bytes"]
+            d2h += shard.LAST_D2H_BYTES if rank == 0 else 8       # rank 0: the gathered lists; others: their match total
     t = torch.tensor([min(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -106,55 +106,86 @@ def cuda_view(ptr: int, nbytes: int, device, dtype=None):
     return t if dtype is None else t.view(dtype)
 
 
+_PINNED = {}
+LAST_D2H_BYTES = 0        # bytes of the last gather_matches_device's device-to-host copies (bench.py's e2e accounting)
+
+
+def _pinned(name, shape, dtype):
+    """Reusable page-locked host buffer (device-to-host copies into pageable memory run at a fraction of PCIe speed)."""
+    import torch
+    n = int(np.prod(shape))
+    buf = _PINNED.get(name)
+    if buf is None or buf.dtype != dtype or buf.numel() < n:
+        buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+        _PINNED[name] = buf
+    return buf[:n].view(*shape)
+
+
 def gather_matches_device(matcher, local_idx, all_local_idx, n_pairs_total: int, device, dst: int = 0, group=None):
     """GPU-to-GPU gather of the last enqueue's match lists (NCCL): per-rank device views from the library
     (sfm_match_pairs_device_view) -> dist.gather of padded int32 payloads -> reassembly in global pair order on the
-    destination GPU -> ONE device-to-host copy on ``dst``.  ``all_local_idx`` = assign_pairs(...) for every rank
-    (known everywhere, so only the match totals need an all_gather).
-    Returns (offsets, matches, dropped) as numpy arrays on ``dst`` and None elsewhere."""
+    destination GPU (one scatter for all ranks) -> ONE device-to-host copy into pinned memory on ``dst``.
+    ``all_local_idx`` = assign_pairs(...) for every rank (known everywhere, so only the match totals need an all_gather).
+    Returns (offsets, matches, dropped) on ``dst`` — numpy views of reusable page-locked buffers, valid until the next
+    call — and None elsewhere."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     pm, po, pd, n_local, n_match = matcher.device_view()
+    lib_stream = torch.cuda.ExternalStream(matcher.stream, device=device)
+    torch.cuda.current_stream(device).wait_stream(lib_stream)          # the views below are written on the library stream
     tot = torch.tensor([n_match], dtype=torch.int64, device=device)
-    all_tot = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_tot, tot, group=group)
-    all_tot = torch.cat(all_tot).cpu().numpy()
+    all_tot_t = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_tot_t, tot, group=group)
+    all_tot = all_tot_t.cpu().numpy()
     max_local = max(len(x) for x in all_local_idx)
     max_match = int(all_tot.max())
+    width = max(2 * max_local + 4 * max_match, 1)
     off = cuda_view(po, n_local * 8, device, torch.int64)
-    counts = torch.diff(off, append=tot).to(torch.int32)
-    dropped = cuda_view(pd, n_local, device).to(torch.int32)
-    m32 = cuda_view(pm, n_match * 16, device, torch.int32)
-    payload = torch.zeros(max(2 * max_local + 4 * max_match, 1), dtype=torch.int32, device=device)
-    payload[:n_local] = counts
-    payload[max_local:max_local + n_local] = dropped
-    payload[2 * max_local:2 * max_local + 4 * n_match] = m32
-    gathered = [torch.zeros_like(payload) for _ in range(world)] if rank == dst else None
-    dist.gather(payload, gathered, dst=dst, group=group)
+    payload = torch.empty(width, dtype=torch.int32, device=device)
+    payload[:n_local] = torch.diff(off, append=tot)
+    payload[max_local:max_local + n_local] = cuda_view(pd, n_local, device)
+    payload[2 * max_local:2 * max_local + 4 * n_match] = cuda_view(pm, n_match * 16, device, torch.int32)
+    gathered = torch.empty((world, width), dtype=torch.int32, device=device) if rank == dst else None
+    dist.gather(payload, list(gathered.unbind(0)) if rank == dst else None, dst=dst, group=group)
     if rank != dst:
         return None
-    total_counts = torch.zeros(n_pairs_total, dtype=torch.int64, device=device)
-    total_dropped = torch.zeros(n_pairs_total, dtype=torch.uint8, device=device)
-    idx_dev = [torch.from_numpy(np.asarray(x, np.int64)).to(device) for x in all_local_idx]
-    for r in range(world):
-        nl = len(all_local_idx[r])
-        total_counts[idx_dev[r]] = gathered[r][:nl].to(torch.int64)
-        total_dropped[idx_dev[r]] = gathered[r][max_local:max_local + nl].to(torch.uint8)
+    # global pair index of every (rank, local position), padded positions point at a dummy slot
+    key = ("idx", world, n_pairs_total, max_local)
+    if _PINNED.get("idx_key") != key:
+        idx = np.full((world, max_local), n_pairs_total, np.int64)
+        for r in range(world):
+            idx[r, :len(all_local_idx[r])] = all_local_idx[r]
+        _PINNED["idx_key"], _PINNED["idx_dev"] = key, torch.from_numpy(idx).to(device)
+    idx_dev = _PINNED["idx_dev"]
+    cnt = gathered[:, :max_local].to(torch.int64)                       # [world, max_local], 0 in padded positions
+    total_counts = torch.zeros(n_pairs_total + 1, dtype=torch.int64, device=device)
+    total_counts[idx_dev.reshape(-1)] = cnt.reshape(-1)
+    total_dropped = torch.zeros(n_pairs_total + 1, dtype=torch.uint8, device=device)
+    total_dropped[idx_dev.reshape(-1)] = gathered[:, max_local:2 * max_local].reshape(-1).to(torch.uint8)
     offsets = torch.zeros(n_pairs_total + 1, dtype=torch.int64, device=device)
-    offsets[1:] = torch.cumsum(total_counts, 0)
-    out = torch.zeros((int(all_tot.sum()), 4), dtype=torch.int32, device=device)
-    for r in range(world):
-        nl, nm = len(all_local_idx[r]), int(all_tot[r])
-        if nm == 0:
-            continue
-        cnt = gathered[r][:nl].to(torch.int64)
-        src_off = torch.cumsum(cnt, 0) - cnt
-        dst_idx = torch.repeat_interleave(offsets[idx_dev[r]] - src_off, cnt) + torch.arange(nm, device=device)
-        out[dst_idx] = gathered[r][2 * max_local:2 * max_local + 4 * nm].view(nm, 4)
-    matches = out.cpu().numpy().view(_dmatch_dtype()).reshape(-1)
-    return offsets.cpu().numpy(), matches, total_dropped.cpu().numpy()
+    offsets[1:] = torch.cumsum(total_counts[:n_pairs_total], 0)
+    # destination of every gathered record: start of its pair in the global list + position inside the pair
+    src_off = torch.cumsum(cnt, 1) - cnt                                # start of each local pair in its rank's records
+    n_all = int(all_tot.sum())
+    shift = (offsets[idx_dev.clamp(max=n_pairs_total - 1)] - src_off).reshape(-1)      # per (rank, local pair)
+    rec_rank_pos = torch.repeat_interleave(torch.arange(world * max_local, device=device), cnt.reshape(-1), output_size=n_all)
+    within = torch.cat([torch.arange(int(all_tot[r]), device=device) for r in range(world)]) if n_all else torch.zeros(0, dtype=torch.int64, device=device)
+    dst_idx = shift[rec_rank_pos] + within
+    recs = torch.cat([gathered[r, 2 * max_local:2 * max_local + 4 * int(all_tot[r])] for r in range(world)]).view(n_all, 4)
+    out = torch.empty((n_all, 4), dtype=torch.int32, device=device)
+    out[dst_idx] = recs
+    h_out = _pinned("matches", (n_all, 4), torch.int32)
+    h_off = _pinned("offsets", (n_pairs_total + 1,), torch.int64)
+    h_drop = _pinned("dropped", (n_pairs_total,), torch.uint8)
+    h_out.copy_(out, non_blocking=True)
+    h_off.copy_(offsets, non_blocking=True)
+    h_drop.copy_(total_dropped[:n_pairs_total], non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    global LAST_D2H_BYTES
+    LAST_D2H_BYTES = int(h_out.numel() * 4 + h_off.numel() * 8 + h_drop.numel() + all_tot_t.numel() * 8)
+    return h_off.numpy(), h_out.numpy().view(_dmatch_dtype()).reshape(-1), h_drop.numpy()
 
 
 def _dmatch_dtype():
