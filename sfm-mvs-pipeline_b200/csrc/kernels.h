@@ -28,7 +28,8 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
 // ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
-                                  Top2* out, int32_t* aux, int sm_count, int layout, int tile_rows, int issuers, cudaStream_t s);
+                                  Top2* out, int32_t* aux, int sm_count, int layout, int tile_rows, int issuers, int chunk_rows,
+                                  cudaStream_t s);
 
 // ---- knn_l2_tf32.cu  (tcgen05 kind::tf32, 3xTF32 candidate search for non-integer float descriptors)
 cudaError_t launch_knn2_l2_f32_tc3(const void* tmaps /* 5 CUtensorMap: hi_a, lo_a, hi_b, lo_b, ext */, const PairDesc* pairs,
@@ -83,6 +84,7 @@ struct RefineArgs {
     const int32_t* blk_min;
     const int32_t* blk_max;
     unsigned long long* stats;   // [0] rows re-ranked, [1] rows brute-forced
+    int chunk_rows;              // train rows per candidate chunk of the value-only kernels (32 or 64)
 };
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
 // value-only tcgen05 path: (chunk, D) pairs -> exact Top2 for rows that can pass the ratio test (see post.cu)

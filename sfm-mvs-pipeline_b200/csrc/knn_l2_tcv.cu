@@ -140,7 +140,10 @@ __device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, 
 //                four best chunks, V1, V2 and the fifth-best chunk maximum V5; refine_dot_kernel (post.cu) turns that
 //                into the exact answer with the train image's norm range: d^2 >= |a|^2 + min|b|^2 - 2 V for every row
 //                whose chunk maximum is V (see there).  Same exactness guarantee, everything integer.
-template <int kParity, int kHalves, int kBN, bool kNorm>
+// kCC = columns (train rows) per chunk: 32 or 64.  The epilogue is ALU-bound (ncu: ALU pipe 67 %, 0.85 instructions per
+// accumulator element with 32-column chunks); the per-chunk bookkeeping (key, top-4/5 insert) halves with 64-column chunks,
+// the refine pass then recomputes 64 train rows per candidate chunk.
+template <int kParity, int kHalves, int kBN, bool kNorm, int kCC>
 __global__ void __launch_bounds__(128 + 128 * kParity * kHalves, 1)
 knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
@@ -154,7 +157,10 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr uint32_t kIdesc = C::kIdesc, kIdescExt = C::kIdescExt;
     constexpr int kGroups = kParity * kHalves;
     constexpr int kThreads = 128 + 128 * kGroups;
-    constexpr int kChunksPerVisit = BN / 32 / kHalves;              // 32-column chunks one warp reads per tile
+    constexpr int kLoadsPerVisit = BN / 32 / kHalves;               // 32-column tcgen05.ld one warp issues per tile
+    constexpr int kChunksPerVisit = BN / kCC / kHalves;             // chunks one warp reads per tile
+    static_assert(kCC == 32 || kCC == 64, "chunk = one or two 32-column loads");
+    static_assert(kChunksPerVisit >= 1, "a warp reads at least one whole chunk per tile");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -299,8 +305,9 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / kHalves);
                 uint32_t v[2][32];
                 tmem_ld_32x32(taddr, v[0]);
+                int32_t cm_even = 0;
 #pragma unroll
-                for (int c = 0; c < kChunksPerVisit; ++c) {
+                for (int c = 0; c < kLoadsPerVisit; ++c) {
                     uint32_t (&cur)[32] = v[c & 1];
                     asm volatile("tcgen05.wait::ld.sync.aligned;"
                                  : "+r"(cur[0]), "+r"(cur[1]), "+r"(cur[2]), "+r"(cur[3]), "+r"(cur[4]), "+r"(cur[5]),
@@ -310,7 +317,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                                    "+r"(cur[22]), "+r"(cur[23]), "+r"(cur[24]), "+r"(cur[25]), "+r"(cur[26]),
                                    "+r"(cur[27]), "+r"(cur[28]), "+r"(cur[29]), "+r"(cur[30]), "+r"(cur[31])
                                  :: "memory");
-                    if (c + 1 < kChunksPerVisit) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (c + 1 < kLoadsPerVisit) tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
                     else {
                         // last chunk is in registers (tcgen05.wait::ld is warp-wide): hand the stage back now, ONE arrival
                         // per warp (128 per-thread arrivals on one mbarrier serialise in shared memory)
@@ -327,9 +334,12 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     a[10] = max(static_cast<int32_t>(cur[30]), static_cast<int32_t>(cur[31]));
                     const int32_t b0 = __vimax3_s32(a[0], a[1], a[2]), b1 = __vimax3_s32(a[3], a[4], a[5]);
                     const int32_t b2 = __vimax3_s32(a[6], a[7], a[8]), b3 = max(a[9], a[10]);
-                    const int32_t cmax = max(__vimax3_s32(b0, b1, b2), b3);
-                    if (kNorm) top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - (seq + c)), m1, m2, m3, m4);
-                    else top5_max(cmax * (1 << kSeqBits) + (511 - (seq + c)), m1, m2, m3, m4, m5);   // 0 <= a.b < 2^22
+                    int32_t cmax = max(__vimax3_s32(b0, b1, b2), b3);
+                    if (kCC == 64 && (c & 1) == 0) { cm_even = cmax; continue; }       // first half of a 64-column chunk
+                    if (kCC == 64) cmax = max(cmax, cm_even);
+                    const int cs = seq + (kCC == 64 ? c / 2 : c);
+                    if (kNorm) top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - cs), m1, m2, m3, m4);
+                    else top5_max(cmax * (1 << kSeqBits) + (511 - cs), m1, m2, m3, m4, m5);   // 0 <= a.b < 2^22
                 }
                 seq += kChunksPerVisit;
             }
@@ -342,7 +352,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 for (int i = 0; i < kKeys; ++i) {
                     if (mk[i] < 0) { r[i] = kEmpty; continue; }
                     const int sq = 511 - (mk[i] & 511);
-                    const int gch = (t_first + kParity * (sq / kChunksPerVisit)) * (BN / 32) + half * kChunksPerVisit + (sq % kChunksPerVisit);
+                    const int gch = (t_first + kParity * (sq / kChunksPerVisit)) * (BN / kCC) + half * kChunksPerVisit + (sq % kChunksPerVisit);
                     r[i] = static_cast<int64_t>(mk[i] >> kSeqBits) * (1ll << 32) + (0x7FFFFFFF - gch);
                 }
             }
@@ -402,15 +412,15 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int kParity, int kHalves, int kBN, bool kNorm>
+template <int kParity, int kHalves, int kBN, bool kNorm, int kCC>
 static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
                               const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int32_t* aux, int grid,
                               int issuers, cudaStream_t s) {
     // per launch: the attribute is per device, and one process may drive several GPUs
-    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm>,
+    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, tcv::Cfg<kBN>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
+    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
         ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out, aux, issuers);
     return cudaGetLastError();
 }
@@ -422,16 +432,20 @@ static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, cons
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
                                   Top2* out, int32_t* aux /* non-null selects the norm-less variant */, int sm_count, int layout,
-                                  int tile_rows, int issuers, cudaStream_t s) {
+                                  int tile_rows, int issuers, int chunk_rows, cudaStream_t s) {
     if (n_units == 0) return cudaSuccess;
     const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
     const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e_host);
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
 #define SFM_TCV_CASE(P, H, T)                                                                                          \
-    if (layout == 10 * P + H && tile_rows == T)                                                                        \
-        return aux ? launch_tcv<P, H, T, false>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s) \
-                   : launch_tcv<P, H, T, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s);
+    if (layout == 10 * P + H && tile_rows == T) {                                                                      \
+        if (chunk_rows == 64)                                                                                          \
+            return aux ? launch_tcv<P, H, T, false, 64>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s) \
+                       : launch_tcv<P, H, T, true, 64>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s); \
+        return aux ? launch_tcv<P, H, T, false, 32>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s) \
+                   : launch_tcv<P, H, T, true, 32>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s); \
+    }
     SFM_TCV_CASE(1, 2, 256) SFM_TCV_CASE(1, 4, 256) SFM_TCV_CASE(2, 1, 256)
 #undef SFM_TCV_CASE
     return cudaErrorInvalidValue;

@@ -383,9 +383,12 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
             // ambiguous: a third chunk ties the second one -> exact brute force over the whole train image
             for (int c = 0; c * 32 < ntr; ++c) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c, lane, a1, a2);
         } else {
-            warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c1, lane, a1, a2);
-            if (c2raw >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c2raw, lane, a1, a2);
-            if (c3 >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c3, lane, a1, a2);
+            const int sub = a.chunk_rows / 32;                      // a candidate chunk = sub groups of 32 train rows
+            for (int k = 0; k < sub; ++k) {
+                warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c1 * sub + k, lane, a1, a2);
+                if (c2raw >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c2raw * sub + k, lane, a1, a2);
+                if (c3 >= 0) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c3 * sub + k, lane, a1, a2);
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -487,10 +490,12 @@ __global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
         const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
         long long a1 = LLONG_MAX, a2 = LLONG_MAX;
         int covered = 0;                                                // real train rows inside the candidate chunks
+        const int sub = a.chunk_rows / 32;                          // a candidate chunk = sub groups of 32 train rows
         for (int k = 0; k < 4; ++k)
             if (cand[k] != 0xFFFF) {
-                warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[k], lane, a1, a2);
-                covered += max(0, min(32, ntr - 32 * cand[k]));
+                for (int h = 0; h < sub; ++h)
+                    warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[k] * sub + h, lane, a1, a2);
+                covered += max(0, min(a.chunk_rows, ntr - a.chunk_rows * cand[k]));
             }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {

@@ -131,6 +131,7 @@ struct sfm_ctx {
     size_t staging_budget_rows = 0;
     int tcv_layout_run = 12;
     int tcv_normless = 1;            // norm-less variant of the value-only kernel: SFM_TCV_NORMLESS = 0 never | 1 auto | 2 always
+    int tcv_chunk = 64;              // train rows per candidate chunk of the value-only kernel (SFM_TCV_CHUNK = 32 | 64)
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
@@ -423,11 +424,12 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, s));
+                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk, s));
             break;
         case Engine::TCN:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            reinterpret_cast<int32_t*>(aux), c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, s));
+                                            reinterpret_cast<int32_t*>(aux), c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers,
+                                            c->tcv_chunk, s));
             break;
         case Engine::TF32:
             CU_TRY(c, launch_knn2_l2_f32_tc3(b.tmaps_f, d_pairs, d_unit_prefix, n_pairs, n_units, out, aux, c->sm_count, s));
@@ -668,6 +670,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             RefineArgs ra{};
             ra.aux = c->d_aux.as<int32_t>(); ra.blk_min = b.d_blkmin.as<int32_t>(); ra.blk_max = b.d_blkmax.as<int32_t>();
             ra.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
+            ra.chunk_rows = c->tcv_chunk;
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
             ra.all_rows = 0; ra.ratio = o->ratio; ra.hamming = o->norm == SFM_NORM_HAMMING;
@@ -833,8 +836,10 @@ int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int3
     CU_TRY(c, b.d_blkmax.ensure(nblk_b));
     CU_TRY(c, cudaMemsetAsync(b.d_blkmin.p, 0x7f, nblk_b, cs));
     CU_TRY(c, cudaMemsetAsync(b.d_blkmax.p, 0, nblk_b, cs));
-    // optimistic bank properties (verified below): integer-valued SIFT-like rows whose norms vary little
-    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true; b.nb_min = b.nb_max = 1;
+    // optimistic bank properties (verified below): integer-valued SIFT-sized rows.  The norm spread is unknown until the
+    // data has arrived, so the pipelined run uses the kernel with the norm K-step (nb_min = 0 keeps the norm-less
+    // variant off)
+    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true; b.nb_min = 0; b.nb_max = 1;
     rc = make_tmaps(c, b);
     if (rc != SFM_OK) return rc;
     // ---- image groups of roughly equal size
@@ -958,6 +963,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
     if (const char* env = std::getenv("SFM_TCV_NORMLESS")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_normless = t; }
+    if (const char* env = std::getenv("SFM_TCV_CHUNK")) { const int t = std::atoi(env); if (t == 32 || t == 64) c->tcv_chunk = t; }
     if (const char* env = std::getenv("SFM_TCV_ISSUERS")) { const int t = std::atoi(env); if (t == 1 || t == 2) c->tcv_issuers = t; }
     if (const char* env = std::getenv("SFM_TCV_LAYOUT")) { const int g = std::atoi(env); if (g == 12 || g == 14 || g == 21 || g == 22) c->tcv_layout = g; }
     *out = c;

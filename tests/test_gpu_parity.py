@@ -250,15 +250,16 @@ def test_value_only_kernel_ties_and_fallback(sfm, matcher):
         assert orc.dmatch_equal(res[p], exp[p])
 
 
-@pytest.mark.parametrize("layout,issuers,normless", [(12, 2, 1), (12, 2, 0), (12, 1, 1), (14, 2, 1), (14, 2, 0), (21, 2, 1),
-                                                     (21, 1, 0)])
-def test_value_only_kernel_epilogue_layouts(sfm, layout, issuers, normless, monkeypatch):
+@pytest.mark.parametrize("layout,issuers,normless,chunk", [(12, 2, 1, 64), (12, 2, 0, 64), (12, 2, 0, 32), (12, 1, 1, 32),
+                                                           (14, 2, 1, 64), (14, 2, 0, 32), (21, 2, 1, 32), (21, 1, 0, 64)])
+def test_value_only_kernel_epilogue_layouts(sfm, layout, issuers, normless, chunk, monkeypatch):
     """Every epilogue organisation of the value-only kernel (SFM_TCV_LAYOUT: column halves / column quarters of every
     tile, alternate tiles) and the two MMA-issuing warps give the oracle's lists bit for bit, including units with a
     single train tile (one issuing warp has nothing to do), odd tile counts and > 32768-row train images (layout 14)."""
     monkeypatch.setenv("SFM_TCV_LAYOUT", str(layout))
     monkeypatch.setenv("SFM_TCV_ISSUERS", str(issuers))
     monkeypatch.setenv("SFM_TCV_NORMLESS", str(normless))
+    monkeypatch.setenv("SFM_TCV_CHUNK", str(chunk))
     m = sfm.Matcher(0)
     try:
         sizes = [700, 256, 1, 130, 2049, 513, 300]               # 1, 2, 3, 9 train tiles; units of 1..17 query blocks
