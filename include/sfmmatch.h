@@ -149,6 +149,26 @@ const int64_t    *sfm_result_offsets(const sfm_result *r);   /* n_pairs + 1 entr
 const sfm_dmatch *sfm_result_matches(const sfm_result *r);   /* offsets[n_pairs] entries */
 const uint8_t    *sfm_result_dropped(const sfm_result *r);   /* n_pairs flags: 1 = erased by min_match_count */
 void              sfm_result_free(sfm_result *r);       /* call before sfm_ctx_destroy of the producing context */
+/* Homography stage -------------------------------------------------------------------------
+ * Replaces SfM::calculateHomography (SfM.cpp:599-637): per ShotMatches of the last sfm_match_pairs* run,
+ * cv::findHomography(left points, right points, cv::RANSAC, threshold, mask) -> inlier count / match count.
+ * The match lists never leave the GPU for this.
+ *
+ * sfm_keypoints_upload: KeyPoint.pt of every descriptor row of the bank (same images, same row counts; call after the
+ * bank upload).  pts[i] points at the first (x, y) float pair of image i, step_bytes[i] = distance between consecutive
+ * points (8 for a packed float2 array, sizeof(cv::KeyPoint) = 28 for &keypoints[0].pt of a std::vector<cv::KeyPoint>;
+ * NULL = 8).
+ * sfm_homography_inlier_ratios: thresholds in pixels, one value or one per pair (SfM.cpp:617-620 derives it from
+ * ransacReprojectionMatchingThreshold and the image sizes); max_iters = cv::findHomography's maxIters (2000): the
+ * number of 4-point hypotheses evaluated per pair (OpenCV stops earlier when its confidence criterion is met; this is
+ * its upper bound).  ratios[p] = inliers / matches, or -1 for pairs with < 4 matches or dropped by min_match_count
+ * (the reference leaves ShotMatches::homographyInlierRatio at -1 there).  inliers / best_hypothesis may be NULL.
+ * Randomised like the reference: same seed -> same result; parity with cv::findHomography is statistical (tests). */
+int sfm_keypoints_upload(sfm_ctx *ctx, int n_images, const void *const *pts, const int32_t *n_rows,
+                         const size_t *step_bytes);
+int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t n_thresholds, int max_iters,
+                                 uint64_t seed, double *ratios, int32_t *inliers, int32_t *best_hypothesis);
+
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* Non-integer CV_32F descriptors (3xTF32 tcgen05 candidate search + exact fp32 re-rank): how many query rows the

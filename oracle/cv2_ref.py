@@ -118,3 +118,13 @@ def time_pairs(bank, pairs, norm, ratio=0.7, topology="inner", threads=None):
         dt = time.perf_counter() - t0
         cv2.setNumThreads(threads)
     return dt, good
+
+
+def find_homography_inliers(pts_left: np.ndarray, pts_right: np.ndarray, threshold: float = 3.0):
+    """cv::findHomography(left, right, cv::RANSAC, threshold, mask) as SfM::calculateHomography calls it
+    (SfM.cpp:622-625, default maxIters 2000 / confidence 0.995) -> (inlier count, mask); (0, None) if no model."""
+    H, mask = cv2.findHomography(np.ascontiguousarray(pts_left, np.float32), np.ascontiguousarray(pts_right, np.float32),
+                                 cv2.RANSAC, float(threshold))
+    if H is None or mask is None:
+        return 0, None
+    return int(np.count_nonzero(mask)), mask.reshape(-1).astype(bool)

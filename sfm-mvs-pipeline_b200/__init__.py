@@ -31,7 +31,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
            "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view", "sfm_match_pairs_from_host",
-           "sfm_last_float_stats"]
+           "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios"]
 
 
 class SfmError(RuntimeError):
@@ -269,6 +269,37 @@ class Matcher:
     def match_pairs(self, pairs, norm, **kw) -> MatchResult:
         self.enqueue(pairs, norm, **kw)
         return self.collect()
+
+    # ---- homography stage (SfM::calculateHomography, SfM.cpp:599-637)
+    def upload_keypoints(self, keypoints):
+        """keypoints: one float32 [n_rows, 2] array (KeyPoint.pt) per shot of the bank; rows may be strided
+        (e.g. a view into packed cv::KeyPoint records, step 28)."""
+        n = len(keypoints)
+        keep = []
+        for k in keypoints:
+            k = np.asarray(k)
+            if k.dtype != np.float32 or k.ndim != 2 or k.shape[1] != 2:
+                raise SfmError(ERR_INVALID, "keypoints must be float32 [n, 2]")
+            if k.shape[0] and k.strides[1] != 4:
+                k = np.ascontiguousarray(k)
+            keep.append(k)
+        ptrs = (C.c_void_p * n)(*[k.ctypes.data if k.shape[0] else None for k in keep])
+        nrows = (C.c_int32 * n)(*[k.shape[0] for k in keep])
+        steps = (C.c_size_t * n)(*[k.strides[0] if k.shape[0] > 1 else 8 for k in keep])
+        self._check(_lib.sfm_keypoints_upload(self._ctx, C.c_int(n), ptrs, nrows, steps))
+
+    def homography_inlier_ratios(self, threshold=3.0, max_iters=2000, seed=0):
+        """Per pair of the last match_pairs run: (ratio, inlier count, winning hypothesis); ratio = -1 where the
+        reference attempts no homography (< 4 matches, dropped pairs).  threshold: pixels, scalar or one per pair."""
+        a, b, c, n, t = self.device_view()
+        thr = np.ascontiguousarray(np.atleast_1d(np.asarray(threshold, np.float64)))
+        ratios = np.zeros(n, np.float64)
+        inl = np.zeros(n, np.int32)
+        hyp = np.zeros(n, np.int32)
+        self._check(_lib.sfm_homography_inlier_ratios(self._ctx, thr.ctypes.data_as(C.c_void_p), C.c_int64(len(thr)),
+                                                      C.c_int(max_iters), C.c_uint64(seed), ratios.ctypes.data_as(C.c_void_p),
+                                                      inl.ctypes.data_as(C.c_void_p), hyp.ctypes.data_as(C.c_void_p)))
+        return ratios, inl, hyp
 
     # ---- operator level
     def knn_match(self, query: np.ndarray, train: np.ndarray, norm: int, k: int = 2, engine: int = ENGINE_AUTO):

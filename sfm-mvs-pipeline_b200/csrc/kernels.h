@@ -124,6 +124,23 @@ struct RefineF32Args {
     double ratio;
 };
 cudaError_t launch_refine_f32(const RefineF32Args& a, cudaStream_t s);
+// ---- homography.cu: SfM::calculateHomography (SfM.cpp:599-637) on the device-resident match lists
+struct HomographyArgs {
+    const float2* keypoints;     // KeyPoint.pt of every bank row (same row numbering as the descriptor bank)
+    const int64_t* row0;         // [2 * n_pairs]: first bank row of the left / right image of every pair
+    const DMatch* matches;       // compacted lists of the last run, input pair order
+    const int64_t* pair_offsets; // [n_pairs] start of every list
+    const int64_t* total;        // end of the last list
+    const uint8_t* dropped;      // pairs removed by min_match_count (may be null)
+    int n_pairs;
+    const double* thresholds;    // reprojection threshold in pixels: one value, or one per pair
+    int n_thresholds;
+    int max_iters;               // hypotheses per pair (cv::findHomography default maxIters = 2000)
+    uint64_t seed;
+    int32_t* inliers;            // out: size of the best consensus set, -1 = no homography (< 4 matches / dropped)
+    int32_t* best_hyp;           // out: hypothesis number that produced it (may be null)
+};
+cudaError_t launch_homography_ransac(const HomographyArgs& a, cudaStream_t s);
 // schedule order -> input pair order (pipelined host path)
 cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
                            const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,

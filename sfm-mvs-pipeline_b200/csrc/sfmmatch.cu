@@ -68,6 +68,8 @@ struct Bank {
     std::vector<int32_t> n_rows;
     std::vector<int64_t> row0;
     int64_t padded_rows = 0;
+    DevBuf d_kp;                     // KeyPoint.pt (float2) per bank row, sfm_keypoints_upload
+    bool have_kp = false;
     DevBuf d_blkmin, d_blkmax;       // |b|^2 range per 256-row block (norm-less value-only path)
     int32_t nb_min = 0, nb_max = 0;  // |b|^2 range over the valid rows of the bank
     DevBuf d_u8, d_f32, d_norm2, d_ckey, d_valid, d_ext, d_bits;     // d_bits: ORB bits expanded to bytes (256 B rows)
@@ -79,7 +81,7 @@ struct Bank {
     bool f_tc_ok = false;
     float f_nb_max = 0.f;
     bool have_tmap = false;
-    void release() { d_blkmin.release(); d_blkmax.release(); d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release();
+    void release() { d_kp.release(); d_blkmin.release(); d_blkmax.release(); d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release();
                      d_fhi.release(); d_flo.release(); d_fnorm.release(); d_fext.release(); }
 };
 
@@ -112,6 +114,7 @@ struct sfm_ctx {
     DevBuf d_top2, d_rev, d_train_cnt, d_chunk_counts, d_chunk_excl, d_pair_counts, d_pair_offsets, d_dropped;
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
+    DevBuf d_hom;                    // homography stage: row0[2n] int64 | thresholds | inliers | best hypothesis
     DevBuf d_aux, d_aux_rev;         // 3xTF32 path: fifth-best chunk maximum per staged row
     DevBuf d_out2, d_pair_offsets2, d_dropped2, d_order, d_cnt_tmp;   // reorder targets of the pipelined host path
     cudaStream_t copy_stream = nullptr;                               // uploads of the pipelined host path
@@ -227,7 +230,7 @@ int bank_layout(sfm_ctx* c, Bank& b, int n_images, const int32_t* n_rows, int co
     if (depth != SFM_CV_8U && depth != SFM_CV_32F) return fail(c, SFM_ERR_INVALID, "bank: depth must be CV_8U or CV_32F");
     if (depth == SFM_CV_8U && cols % 16 != 0) return fail(c, SFM_ERR_INVALID, "bank: CV_8U descriptors need cols % 16 == 0");
     if (depth == SFM_CV_32F && cols % 4 != 0) return fail(c, SFM_ERR_INVALID, "bank: CV_32F descriptors need cols % 4 == 0");
-    b.n_images = n_images; b.cols = cols; b.depth = depth;
+    b.n_images = n_images; b.cols = cols; b.depth = depth; b.have_kp = false;
     b.n_rows.assign(n_rows, n_rows + n_images);
     b.row0.resize(n_images + 1);
     int64_t r = 0;
@@ -978,7 +981,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
                       &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
                       &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
-                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev};
+                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom};
     for (DevBuf* b : bufs) b->release();
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
@@ -1136,6 +1139,94 @@ int sfm_last_float_stats(sfm_ctx* c, int64_t* rows_reranked, int64_t* rows_brute
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (rows_reranked) *rows_reranked = h[0];
     if (rows_brute_forced) *rows_brute_forced = h[1];
+    return SFM_OK;
+}
+
+// ---- SfM::calculateHomography (SfM.cpp:599-637) on the device-resident match lists
+int sfm_keypoints_upload(sfm_ctx* c, int n_images, const void* const* pts, const int32_t* n_rows, const size_t* step_bytes) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    Bank& b = c->bank;
+    if (n_images != b.n_images) return fail(c, SFM_ERR_STATE, "keypoints: image count differs from the descriptor bank");
+    if (n_images > 0 && (!pts || !n_rows)) return fail(c, SFM_ERR_INVALID, "keypoints: null arrays");
+    for (int i = 0; i < n_images; ++i)
+        if (n_rows[i] != b.n_rows[i]) return fail(c, SFM_ERR_INVALID, "keypoints: row count differs from the descriptor bank");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, b.d_kp.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * 8)));
+    for (int i = 0; i < n_images; ++i) {
+        if (n_rows[i] == 0) continue;
+        if (!pts[i]) return fail(c, SFM_ERR_INVALID, "keypoints: null image pointer");
+        const size_t step = step_bytes && step_bytes[i] ? step_bytes[i] : 8;       // sizeof(cv::KeyPoint) = 28 for a KeyPoint vector
+        if (step < 8) return fail(c, SFM_ERR_INVALID, "keypoints: step < 8 bytes");
+        CU_TRY(c, cudaMemcpy2DAsync(b.d_kp.as<uint8_t>() + static_cast<size_t>(b.row0[i]) * 8, 8, pts[i], step, 8,
+                                    static_cast<size_t>(n_rows[i]), cudaMemcpyHostToDevice, c->stream));
+        c->stat_h2d += static_cast<int64_t>(n_rows[i]) * 8;
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));       // the caller's buffers may go away
+    b.have_kp = true;
+    return SFM_OK;
+}
+
+int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n_thresholds, int max_iters, uint64_t seed,
+                                 double* ratios, int32_t* inliers, int32_t* best_hypothesis) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->run.valid) return fail(c, SFM_ERR_STATE, "homography without a preceding match_pairs run");
+    if (!c->bank.have_kp) return fail(c, SFM_ERR_STATE, "homography before sfm_keypoints_upload");
+    const int64_t n = c->run.n_pairs;
+    if (!thresholds || (n_thresholds != 1 && n_thresholds != n)) return fail(c, SFM_ERR_INVALID, "homography: one threshold, or one per pair");
+    if (max_iters <= 0) return fail(c, SFM_ERR_INVALID, "homography: max_iters must be positive");
+    for (int64_t i = 0; i < n_thresholds; ++i)
+        if (!(thresholds[i] > 0.0)) return fail(c, SFM_ERR_INVALID, "homography: threshold must be > 0 pixels");
+    if (n == 0) return SFM_OK;
+    if (!ratios) return fail(c, SFM_ERR_INVALID, "homography: null output");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const Bank& b = c->bank;
+    // layout of d_hom / the host staging vector: row0[2n] int64 | thresholds[nt] double | offsets copy [n+1] int64 (host only)
+    const size_t off_thr = static_cast<size_t>(2 * n) * 8, off_inl = off_thr + static_cast<size_t>(n_thresholds) * 8;
+    const size_t off_hyp = off_inl + static_cast<size_t>(n) * 4, bytes = off_hyp + static_cast<size_t>(n) * 4;
+    CU_TRY(c, c->d_hom.ensure(bytes));
+    std::vector<uint8_t> h(off_inl);
+    int64_t* h_row0 = reinterpret_cast<int64_t*>(h.data());
+    for (int64_t p = 0; p < n; ++p) {
+        h_row0[2 * p] = b.row0[c->run.pairs[2 * p]];
+        h_row0[2 * p + 1] = b.row0[c->run.pairs[2 * p + 1]];
+    }
+    std::memcpy(h.data() + off_thr, thresholds, static_cast<size_t>(n_thresholds) * 8);
+    CU_TRY(c, cudaMemcpyAsync(c->d_hom.p, h.data(), off_inl, cudaMemcpyHostToDevice, s));
+    c->stat_h2d += static_cast<int64_t>(off_inl);
+    HomographyArgs a;
+    a.keypoints = b.d_kp.as<float2>();
+    a.row0 = c->d_hom.as<int64_t>();
+    a.matches = c->d_out.as<DMatch>();
+    a.pair_offsets = c->d_pair_offsets.as<int64_t>();
+    a.total = c->d_scalars.as<int64_t>();
+    a.dropped = c->d_dropped.as<uint8_t>();
+    a.n_pairs = static_cast<int>(n);
+    a.thresholds = reinterpret_cast<const double*>(c->d_hom.as<uint8_t>() + off_thr);
+    a.n_thresholds = static_cast<int>(n_thresholds);
+    a.max_iters = max_iters;
+    a.seed = seed;
+    a.inliers = reinterpret_cast<int32_t*>(c->d_hom.as<uint8_t>() + off_inl);
+    a.best_hyp = reinterpret_cast<int32_t*>(c->d_hom.as<uint8_t>() + off_hyp);
+    CU_TRY(c, launch_homography_ransac(a, s));
+    c->stat_launches++;
+    std::vector<int32_t> h_out(static_cast<size_t>(2 * n));
+    std::vector<int64_t> h_off(static_cast<size_t>(n + 1));
+    CU_TRY(c, cudaMemcpyAsync(h_out.data(), a.inliers, static_cast<size_t>(2 * n) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaMemcpyAsync(h_off.data(), c->d_pair_offsets.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaMemcpyAsync(&h_off[n], c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaStreamSynchronize(s));
+    c->stat_d2h += static_cast<int64_t>(2 * n) * 4 + (n + 1) * 8;
+    for (int64_t p = 0; p < n; ++p) {
+        const int32_t k = h_out[p];
+        const int64_t m = h_off[p + 1] - h_off[p];
+        // inlierCount / matches.size(); pairs without a homography keep ShotMatches' initial -1 (Scene.h:56)
+        ratios[p] = k < 0 ? -1.0 : static_cast<double>(k) / static_cast<double>(m);
+        if (inliers) inliers[p] = k;
+        if (best_hypothesis) best_hypothesis[p] = h_out[n + p];
+    }
     return SFM_OK;
 }
 
