@@ -9,8 +9,8 @@
 //
 // Here: one CTA per pair, one thread per hypothesis (max_iters hypotheses, OpenCV's default 2000 = the upper bound of its
 // adaptive loop), all threads walk the pair's matches together (shared-memory broadcast).  Minimal sets come from a
-// counter-based generator (splitmix64 of seed, pair, hypothesis, draw) so that the numpy restatement (oracle/
-// homography_np.py) reproduces every hypothesis; degenerate sets are rejected like cv::HomographyEstimatorCallback::
+// counter-based generator (splitmix64 of seed, pair, hypothesis, draw) so that the numpy restatement used by the
+// tests reproduces every hypothesis; degenerate sets are rejected like cv::HomographyEstimatorCallback::
 // checkSubset (collinear triples, orientation of the four triples must agree between the two images).  The 4-point model is
 // the closed form  H = S_dst * adj(S_src)  with S = unit-square-to-quadrilateral map (Heckbert), in double; the error is the
 // forward transfer error in the right image, compared with thr^2 exactly as computeError / findInliers do.
