@@ -159,15 +159,27 @@ void              sfm_result_free(sfm_result *r);       /* call before sfm_ctx_d
  * points (8 for a packed float2 array, sizeof(cv::KeyPoint) = 28 for &keypoints[0].pt of a std::vector<cv::KeyPoint>;
  * NULL = 8).
  * sfm_homography_inlier_ratios: thresholds in pixels, one value or one per pair (SfM.cpp:617-620 derives it from
- * ransacReprojectionMatchingThreshold and the image sizes); max_iters = cv::findHomography's maxIters (2000): the
- * number of 4-point hypotheses evaluated per pair (OpenCV stops earlier when its confidence criterion is met; this is
- * its upper bound).  ratios[p] = inliers / matches, or -1 for pairs with < 4 matches or dropped by min_match_count
- * (the reference leaves ShotMatches::homographyInlierRatio at -1 there).  inliers / best_hypothesis may be NULL.
- * Randomised like the reference: same seed -> same result; parity with cv::findHomography is statistical (tests). */
+ * ransacReprojectionMatchingThreshold and the image sizes).  opts (NULL = defaults): max_iters / confidence =
+ * cv::findHomography's maxIters (2000) and confidence (0.995), i.e. the budget of 4-point hypotheses per pair and the
+ * early-stopping rule of OpenCV's RANSAC loop, replayed on the device (confidence >= 1: every hypothesis counts);
+ * refine = 1: like cv::findHomography, re-estimate the model on the consensus set (normalised least squares) and
+ * report the matches within the threshold of THAT model; seed: same seed -> same result.
+ * ratios[p] = inliers / matches, or -1 for pairs with < 4 matches or dropped by min_match_count (the reference leaves
+ * ShotMatches::homographyInlierRatio at -1 there); exactly 4 matches -> 1 (OpenCV runs no RANSAC on four points).
+ * inliers / ransac_inliers (consensus size of the best minimal model) / best_hypothesis may be NULL.
+ * Parity with cv::findHomography is statistical (different random minimal sets): tolerance in tests/test_homography.py. */
+typedef struct sfm_homography_opts {
+    int32_t  max_iters;
+    int32_t  refine;
+    double   confidence;
+    uint64_t seed;
+} sfm_homography_opts;
+void sfm_homography_opts_default(sfm_homography_opts *o);
 int sfm_keypoints_upload(sfm_ctx *ctx, int n_images, const void *const *pts, const int32_t *n_rows,
                          const size_t *step_bytes);
-int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t n_thresholds, int max_iters,
-                                 uint64_t seed, double *ratios, int32_t *inliers, int32_t *best_hypothesis);
+int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t n_thresholds,
+                                 const sfm_homography_opts *opts, double *ratios, int32_t *inliers,
+                                 int32_t *ransac_inliers, int32_t *best_hypothesis);
 
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);

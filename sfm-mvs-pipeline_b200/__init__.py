@@ -31,13 +31,18 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_match_pairs", "sfm_match_pairs_enqueue", "sfm_match_pairs_collect", "sfm_result_n_pairs",
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
            "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view", "sfm_match_pairs_from_host",
-           "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios"]
+           "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios",
+           "sfm_homography_opts_default"]
 
 
 class SfmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"sfmmatch error {code}: {msg}")
         self.code = code
+
+
+class HomographyOpts(C.Structure):
+    _fields_ = [("max_iters", C.c_int32), ("refine", C.c_int32), ("confidence", C.c_double), ("seed", C.c_uint64)]
 
 
 class Opts(C.Structure):
@@ -59,6 +64,7 @@ def load_library():
     lib.sfm_result_free.restype = None
     lib.sfm_ctx_destroy.restype = None
     lib.sfm_opts_default.restype = None
+    lib.sfm_homography_opts_default.restype = None
     return lib
 
 
@@ -288,18 +294,20 @@ class Matcher:
         steps = (C.c_size_t * n)(*[k.strides[0] if k.shape[0] > 1 else 8 for k in keep])
         self._check(_lib.sfm_keypoints_upload(self._ctx, C.c_int(n), ptrs, nrows, steps))
 
-    def homography_inlier_ratios(self, threshold=3.0, max_iters=2000, seed=0):
-        """Per pair of the last match_pairs run: (ratio, inlier count, winning hypothesis); ratio = -1 where the
+    def homography_inlier_ratios(self, threshold=3.0, max_iters=2000, seed=0, confidence=0.995, refine=True):
+        """Per pair of the last match_pairs run: dict(ratio, inliers, ransac_inliers, hypothesis); ratio = -1 where the
         reference attempts no homography (< 4 matches, dropped pairs).  threshold: pixels, scalar or one per pair."""
         a, b, c, n, t = self.device_view()
         thr = np.ascontiguousarray(np.atleast_1d(np.asarray(threshold, np.float64)))
+        o = HomographyOpts()
+        _lib.sfm_homography_opts_default(C.byref(o))
+        o.max_iters, o.refine, o.confidence, o.seed = max_iters, int(bool(refine)), confidence, seed
         ratios = np.zeros(n, np.float64)
-        inl = np.zeros(n, np.int32)
-        hyp = np.zeros(n, np.int32)
-        self._check(_lib.sfm_homography_inlier_ratios(self._ctx, thr.ctypes.data_as(C.c_void_p), C.c_int64(len(thr)),
-                                                      C.c_int(max_iters), C.c_uint64(seed), ratios.ctypes.data_as(C.c_void_p),
-                                                      inl.ctypes.data_as(C.c_void_p), hyp.ctypes.data_as(C.c_void_p)))
-        return ratios, inl, hyp
+        inl, rinl, hyp = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(_lib.sfm_homography_inlier_ratios(self._ctx, thr.ctypes.data_as(C.c_void_p), C.c_int64(len(thr)), C.byref(o),
+                                                      ratios.ctypes.data_as(C.c_void_p), inl.ctypes.data_as(C.c_void_p),
+                                                      rinl.ctypes.data_as(C.c_void_p), hyp.ctypes.data_as(C.c_void_p)))
+        return {"ratio": ratios, "inliers": inl, "ransac_inliers": rinl, "hypothesis": hyp}
 
     # ---- operator level
     def knn_match(self, query: np.ndarray, train: np.ndarray, norm: int, k: int = 2, engine: int = ENGINE_AUTO):

@@ -135,9 +135,12 @@ struct HomographyArgs {
     int n_pairs;
     const double* thresholds;    // reprojection threshold in pixels: one value, or one per pair
     int n_thresholds;
-    int max_iters;               // hypotheses per pair (cv::findHomography default maxIters = 2000)
+    int max_iters;               // hypotheses per pair (cv::findHomography default maxIters = 2000), <= 16384
+    double confidence;           // cv::findHomography default 0.995; >= 1 evaluates every hypothesis
     uint64_t seed;
-    int32_t* inliers;            // out: size of the best consensus set, -1 = no homography (< 4 matches / dropped)
+    int refine;                  // 1: least-squares re-estimation on the consensus set, mask of the refined model (cv::findHomography)
+    int32_t* inliers;            // out: inlier count cv::findHomography's mask would hold, -1 = no homography (< 4 matches / dropped)
+    int32_t* ransac_inliers;     // out: consensus size of the best minimal model (may be null)
     int32_t* best_hyp;           // out: hypothesis number that produced it (may be null)
 };
 cudaError_t launch_homography_ransac(const HomographyArgs& a, cudaStream_t s);

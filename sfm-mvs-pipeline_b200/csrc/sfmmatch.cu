@@ -1167,15 +1167,27 @@ int sfm_keypoints_upload(sfm_ctx* c, int n_images, const void* const* pts, const
     return SFM_OK;
 }
 
-int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n_thresholds, int max_iters, uint64_t seed,
-                                 double* ratios, int32_t* inliers, int32_t* best_hypothesis) {
+void sfm_homography_opts_default(sfm_homography_opts* o) {
+    if (!o) return;
+    o->max_iters = 2000;       // cv::findHomography defaults (calib3d.hpp), as SfM.cpp:622-625 leaves them
+    o->confidence = 0.995;
+    o->refine = 1;
+    o->seed = 0;
+}
+
+int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n_thresholds, const sfm_homography_opts* opts,
+                                 double* ratios, int32_t* inliers, int32_t* ransac_inliers, int32_t* best_hypothesis) {
     if (!c) return SFM_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
+    sfm_homography_opts o;
+    sfm_homography_opts_default(&o);
+    if (opts) o = *opts;
     if (!c->run.valid) return fail(c, SFM_ERR_STATE, "homography without a preceding match_pairs run");
     if (!c->bank.have_kp) return fail(c, SFM_ERR_STATE, "homography before sfm_keypoints_upload");
     const int64_t n = c->run.n_pairs;
     if (!thresholds || (n_thresholds != 1 && n_thresholds != n)) return fail(c, SFM_ERR_INVALID, "homography: one threshold, or one per pair");
-    if (max_iters <= 0) return fail(c, SFM_ERR_INVALID, "homography: max_iters must be positive");
+    if (o.max_iters <= 0 || o.max_iters > 16384) return fail(c, SFM_ERR_INVALID, "homography: max_iters must be in 1..16384");
+    if (!(o.confidence > 0.0)) return fail(c, SFM_ERR_INVALID, "homography: confidence must be > 0");
     for (int64_t i = 0; i < n_thresholds; ++i)
         if (!(thresholds[i] > 0.0)) return fail(c, SFM_ERR_INVALID, "homography: threshold must be > 0 pixels");
     if (n == 0) return SFM_OK;
@@ -1183,19 +1195,19 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     const Bank& b = c->bank;
-    // layout of d_hom / the host staging vector: row0[2n] int64 | thresholds[nt] double | offsets copy [n+1] int64 (host only)
-    const size_t off_thr = static_cast<size_t>(2 * n) * 8, off_inl = off_thr + static_cast<size_t>(n_thresholds) * 8;
-    const size_t off_hyp = off_inl + static_cast<size_t>(n) * 4, bytes = off_hyp + static_cast<size_t>(n) * 4;
+    // d_hom: row0[2n] int64 | thresholds[nt] double | inliers[n] | ransac inliers[n] | best hypothesis[n] (int32)
+    const size_t off_thr = static_cast<size_t>(2 * n) * 8, off_out = off_thr + static_cast<size_t>(n_thresholds) * 8;
+    const size_t bytes = off_out + static_cast<size_t>(3 * n) * 4;
     CU_TRY(c, c->d_hom.ensure(bytes));
-    std::vector<uint8_t> h(off_inl);
+    std::vector<uint8_t> h(off_out);
     int64_t* h_row0 = reinterpret_cast<int64_t*>(h.data());
     for (int64_t p = 0; p < n; ++p) {
         h_row0[2 * p] = b.row0[c->run.pairs[2 * p]];
         h_row0[2 * p + 1] = b.row0[c->run.pairs[2 * p + 1]];
     }
     std::memcpy(h.data() + off_thr, thresholds, static_cast<size_t>(n_thresholds) * 8);
-    CU_TRY(c, cudaMemcpyAsync(c->d_hom.p, h.data(), off_inl, cudaMemcpyHostToDevice, s));
-    c->stat_h2d += static_cast<int64_t>(off_inl);
+    CU_TRY(c, cudaMemcpyAsync(c->d_hom.p, h.data(), off_out, cudaMemcpyHostToDevice, s));
+    c->stat_h2d += static_cast<int64_t>(off_out);
     HomographyArgs a;
     a.keypoints = b.d_kp.as<float2>();
     a.row0 = c->d_hom.as<int64_t>();
@@ -1206,26 +1218,30 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
     a.n_pairs = static_cast<int>(n);
     a.thresholds = reinterpret_cast<const double*>(c->d_hom.as<uint8_t>() + off_thr);
     a.n_thresholds = static_cast<int>(n_thresholds);
-    a.max_iters = max_iters;
-    a.seed = seed;
-    a.inliers = reinterpret_cast<int32_t*>(c->d_hom.as<uint8_t>() + off_inl);
-    a.best_hyp = reinterpret_cast<int32_t*>(c->d_hom.as<uint8_t>() + off_hyp);
+    a.max_iters = o.max_iters;
+    a.confidence = o.confidence;
+    a.refine = o.refine ? 1 : 0;
+    a.seed = o.seed;
+    a.inliers = reinterpret_cast<int32_t*>(c->d_hom.as<uint8_t>() + off_out);
+    a.ransac_inliers = a.inliers + n;
+    a.best_hyp = a.inliers + 2 * n;
     CU_TRY(c, launch_homography_ransac(a, s));
     c->stat_launches++;
-    std::vector<int32_t> h_out(static_cast<size_t>(2 * n));
+    std::vector<int32_t> h_out(static_cast<size_t>(3 * n));
     std::vector<int64_t> h_off(static_cast<size_t>(n + 1));
-    CU_TRY(c, cudaMemcpyAsync(h_out.data(), a.inliers, static_cast<size_t>(2 * n) * 4, cudaMemcpyDeviceToHost, s));
+    CU_TRY(c, cudaMemcpyAsync(h_out.data(), a.inliers, static_cast<size_t>(3 * n) * 4, cudaMemcpyDeviceToHost, s));
     CU_TRY(c, cudaMemcpyAsync(h_off.data(), c->d_pair_offsets.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(c, cudaMemcpyAsync(&h_off[n], c->d_scalars.p, 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(c, cudaStreamSynchronize(s));
-    c->stat_d2h += static_cast<int64_t>(2 * n) * 4 + (n + 1) * 8;
+    c->stat_d2h += static_cast<int64_t>(3 * n) * 4 + (n + 1) * 8;
     for (int64_t p = 0; p < n; ++p) {
         const int32_t k = h_out[p];
         const int64_t m = h_off[p + 1] - h_off[p];
         // inlierCount / matches.size(); pairs without a homography keep ShotMatches' initial -1 (Scene.h:56)
         ratios[p] = k < 0 ? -1.0 : static_cast<double>(k) / static_cast<double>(m);
         if (inliers) inliers[p] = k;
-        if (best_hypothesis) best_hypothesis[p] = h_out[n + p];
+        if (ransac_inliers) ransac_inliers[p] = h_out[n + p];
+        if (best_hypothesis) best_hypothesis[p] = h_out[2 * n + p];
     }
     return SFM_OK;
 }

@@ -5,9 +5,10 @@ numbers (tests/golden/insel_homography.npz).  GPU tests (-m gpu): csrc/homograph
 restatement (same hypotheses -> same inlier counts) and against the cv2 golden numbers.
 
 Stated tolerance against cv::findHomography (different random minimal sets, so no bit parity): the inlier RATIO agrees
-within 0.05 absolute on every fixture.  cv::findHomography stops as soon as its confidence criterion (0.995) is met,
-this stage always evaluates the full budget of 2000 minimal sets, so its consensus set is typically the same size or a few
-matches larger (insel SIFT 0-2: 158 vs 153 of 163; all other fixtures differ by <= 7 of thousands)."""
+within 0.03 absolute on every fixture, for every seed tried.  Both run the same procedure — RANSAC over 4-point models
+with OpenCV's early-stopping rule, least-squares re-estimation on the consensus set, mask of the re-estimated model —
+and the re-estimation makes the final count nearly independent of which good minimal set was drawn (insel ORB 0-1:
+6076..6087 over six seeds vs cv2's 6074 of 6170)."""
 import os
 
 import numpy as np
@@ -18,7 +19,7 @@ from oracle import oracle_np as orc
 from oracle.oracle_np import NORM_HAMMING, NORM_L2
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RATIO_TOL = 0.05
+RATIO_TOL = 0.03
 PAIRS = ((0, 1), (0, 2), (1, 2))
 
 
@@ -31,9 +32,10 @@ def test_oracle_vs_cv2_synthetic(hom):
     for k in range(5):
         p1, p2 = hom[f"syn{k}_p1"], hom[f"syn{k}_p2"]
         pts = np.concatenate([p1, p2], 1)
-        cnt, hyp, mask = hn.ransac_inliers(pts, 3.0, pair=k, seed=7)
         cv = int(hom[f"syn{k}_count"])
-        assert abs(cnt - cv) / len(pts) <= RATIO_TOL, (k, cnt, cv)
+        for seed in (7, 8, 9):
+            cnt, hyp, mask = hn.ransac_inliers(pts, 3.0, pair=k, seed=seed)
+            assert abs(cnt - cv) / len(pts) <= RATIO_TOL, (k, seed, cnt, cv)
         # the consensus set contains (almost) only planted inliers
         planted = hom[f"syn{k}_planted"]
         assert (mask & ~planted).sum() <= max(2, 0.02 * len(pts))
@@ -45,9 +47,14 @@ def test_oracle_vs_cv2_insel(hom, insel_sift, insel_orb):
         for a, b in PAIRS:
             good = gold[f"p{a}{b}_good"]
             pts = hn.aligned_points(hom[f"{tag}_kp{a}"], hom[f"{tag}_kp{b}"], good)
-            cnt, _, _ = hn.ransac_inliers(pts, 3.0, pair=0, seed=1)
             cv = int(hom[f"{tag}_h{a}{b}_count"])
-            assert abs(cnt - cv) / len(good) <= RATIO_TOL, (tag, a, b, cnt, cv)
+            for seed in (1, 2, 3):
+                cnt, _, _ = hn.ransac_inliers(pts, 3.0, pair=0, seed=seed)
+                assert abs(cnt - cv) / len(good) <= RATIO_TOL, (tag, a, b, seed, cnt, cv)
+            # without the re-estimation the count is the consensus of one minimal model: never larger than the exhaustive one
+            c_min = hn.ransac_inliers(pts, 3.0, pair=0, seed=1, refine=False)[0]
+            c_all = hn.ransac_inliers(pts, 3.0, pair=0, seed=1, refine=False, confidence=1.0)[0]
+            assert 4 <= c_min <= c_all <= len(good)
 
 
 def test_oracle_degenerate_inputs():
@@ -57,6 +64,7 @@ def test_oracle_degenerate_inputs():
     assert hn.ransac_inliers(same, 3.0, 0)[0] == 0
     line = np.stack([np.arange(20), np.arange(20), np.arange(20), np.arange(20)], 1).astype(np.float32)
     assert hn.ransac_inliers(line, 3.0, 0)[0] == 0
+    assert hn.ransac_inliers(np.random.default_rng(0).uniform(0, 99, (4, 4)).astype(np.float32), 3.0, 0)[0] == 4   # exactly 4: no RANSAC
     # generator: indices in range and distinct
     idx, ok = hn.minimal_sets(3, 5, 500, 7)
     assert ok.all() and idx.min() >= 0 and idx.max() < 7
@@ -82,18 +90,20 @@ def test_gpu_insel_pairs(sfm, matcher, hom, insel_sift, insel_orb, tag, norm):
     matcher.upload_bank(bank)
     matcher.upload_keypoints(kps)
     res = matcher.match_pairs(pairs, norm)
-    ratios, inl, hyp = matcher.homography_inlier_ratios(3.0, 2000, seed=11)
-    for p, (a, b) in enumerate(PAIRS):
-        good = gold[f"p{a}{b}_good"]
-        assert orc.dmatch_equal(res[p], good)
-        # the restatement of the same algorithm: identical count and winning hypothesis
-        pts = hn.aligned_points(kps[a], kps[b], good)
-        cnt, h, _ = hn.ransac_inliers(pts, 3.0, pair=p, seed=11)
-        assert (int(inl[p]), int(hyp[p])) == (cnt, h)
-        assert ratios[p] == cnt / len(good)
-        # cv::findHomography golden number
-        cv = int(hom[f"{tag}_h{a}{b}_count"])
-        assert abs(ratios[p] - cv / len(good)) <= RATIO_TOL, (tag, a, b, int(inl[p]), cv)
+    for seed, refine, conf in ((11, True, 0.995), (12, True, 0.995), (11, False, 0.995), (11, False, 1.0)):
+        r = matcher.homography_inlier_ratios(3.0, 2000, seed=seed, refine=refine, confidence=conf)
+        for p, (a, b) in enumerate(PAIRS):
+            good = gold[f"p{a}{b}_good"]
+            assert orc.dmatch_equal(res[p], good)
+            # the restatement of the same algorithm: identical counts and winning hypothesis
+            pts = hn.aligned_points(kps[a], kps[b], good)
+            cnt, h, _, rcnt = hn.ransac_inliers(pts, 3.0, pair=p, seed=seed, refine=refine, confidence=conf, details=True)
+            assert (int(r["ransac_inliers"][p]), int(r["hypothesis"][p])) == (rcnt, h)
+            assert int(r["inliers"][p]) == cnt
+            assert r["ratio"][p] == cnt / len(good)
+            if refine:      # cv::findHomography golden number
+                cv = int(hom[f"{tag}_h{a}{b}_count"])
+                assert abs(r["ratio"][p] - cv / len(good)) <= RATIO_TOL, (tag, a, b, int(r["inliers"][p]), cv)
 
 
 @pytest.mark.gpu
@@ -112,7 +122,8 @@ def test_gpu_keypoint_stride_thresholds_and_skips(sfm, matcher, hom, insel_sift)
     matcher.upload_keypoints([r[:, :2] for r in recs])
     res = matcher.match_pairs(pairs, NORM_L2, min_match_count=180)    # drops pair (0, 2) (163 matches)
     thr = np.array([3.0, 3.0, 1.0, 3.0])
-    ratios, inl, hyp = matcher.homography_inlier_ratios(thr, 500, seed=5)
+    r = matcher.homography_inlier_ratios(thr, 500, seed=5)
+    ratios, inl, hyp = r["ratio"], r["inliers"], r["hypothesis"]
     assert ratios[1] == -1.0 and inl[1] == -1                          # fewer than 4 matches
     assert ratios[3] == -1.0 and res[3] is None                        # dropped by min_match_count
     for p in (0, 2):
@@ -147,7 +158,8 @@ def test_gpu_synthetic_planted_homographies(sfm, matcher, hom):
     matcher.upload_bank(bank)
     matcher.upload_keypoints(kps)
     res = matcher.match_pairs(pairs, NORM_L2)
-    ratios, inl, hyp = matcher.homography_inlier_ratios(3.0, 2000, seed=3)
+    r = matcher.homography_inlier_ratios(3.0, 2000, seed=3)
+    ratios, inl, hyp = r["ratio"], r["inliers"], r["hypothesis"]
     for j, k in enumerate(ks):
         m = res[j]
         n = len(hom[f"syn{k}_p1"])

@@ -29,6 +29,30 @@ def sift_like_image(i: int, n_rows: int, prev: np.ndarray | None = None, planted
     return d
 
 
+def sift_like_keypoints(n_images: int, n_rows: int, planted: float = 0.30, seed_base: int = 1000, width: float = 4000.0,
+                        height: float = 3000.0, noise: float = 0.7):
+    """KeyPoint.pt arrays (float32 [n_rows, 2]) consistent with sift_like_bank: the planted rows of image i sit where a
+    random homography maps the keypoints of their source rows in image i-1 (+ Gaussian noise in pixels), every other
+    row is uniform in the image.  Replays sift_like_image's generator to recover the source rows."""
+    kps, prev_kp = [], None
+    for i in range(n_images):
+        rng = np.random.Generator(np.random.PCG64(seed_base + i))
+        rng.gamma(0.6, size=(n_rows, 128))                                    # same stream position as sift_like_image
+        krng = np.random.Generator(np.random.PCG64(seed_base + 500000 + i))
+        kp = np.stack([krng.uniform(0, width, n_rows), krng.uniform(0, height, n_rows)], 1)
+        if prev_kp is not None and planted > 0:
+            k = int(n_rows * planted)
+            src = rng.integers(0, prev_kp.shape[0], size=k)
+            H = np.array([[1 + krng.normal(0, 0.02), krng.normal(0, 0.02), krng.normal(0, 40)],
+                          [krng.normal(0, 0.02), 1 + krng.normal(0, 0.02), krng.normal(0, 40)],
+                          [krng.normal(0, 3e-6), krng.normal(0, 3e-6), 1.0]])
+            q = np.c_[prev_kp[src], np.ones(k)] @ H.T
+            kp[:k] = q[:, :2] / q[:, 2:3] + krng.normal(0, noise, (k, 2))
+        prev_kp = kp
+        kps.append(kp.astype(np.float32))
+    return kps
+
+
 def sift_like_bank(n_images: int, n_rows: int, planted: float = 0.30, seed_base: int = 1000):
     bank, prev = [], None
     for i in range(n_images):
