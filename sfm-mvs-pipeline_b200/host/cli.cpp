@@ -6,6 +6,9 @@
 // Feature extraction is outside this stage, so descriptors come from a file instead of -Pimage:
 //   -Pdescriptors=<bank.sfmd>   "SFMD" u32 version, u32 n_images, u32 cols, u32 depth(0=CV_8U,5=CV_32F),
 //                               then per image: u32 n_rows + n_rows*cols*elemsize bytes
+//   -Pkeypoints=<bank.sfmk>     optional, enables the homography stage (SfM::calculateHomography): "SFMK" u32 version, u32 n_images,
+//                               then per image: u32 n_rows, u32 width, u32 height, n_rows x (float x, float y)
+//   -Pransac-matching-threshold=0.006   as PhotogrammetrieCli.cpp:98-99 (< 0: pixels, > 0: fraction of the image size)
 //   -Pout=<matches.bin>         u64 n_pairs, then per kept pair: i32 left, i32 right, u64 n, n x DMatch(16 B)
 //   -Pdevice=<gpu>
 #include <chrono>
@@ -43,7 +46,8 @@ struct Args {
 static void usage() {
     std::puts("sfm_match_cli -Pdescriptors=<bank.sfmd> [-Pfeature-detector=SIFT|ORB] [-Pfeature-matcher=BF|FLANN]\n"
               "              [-Pfeature-limit=10000] [-Pfeature-sequence=0] [-Pfeature-gridlength=0] [-Pmatch-threshold=20]\n"
-              "              [--distinct-matches] [-Pout=matches.bin] [-Pdevice=0] [-Ploglevel=2]");
+              "              [--distinct-matches] [-Pkeypoints=<bank.sfmk>] [-Pransac-matching-threshold=0.006]\n"
+              "              [-Pout=matches.bin] [-Pdevice=0] [-Ploglevel=2]");
 }
 
 int main(int argc, char** argv) {
@@ -79,6 +83,27 @@ int main(int argc, char** argv) {
                                               static_cast<int>(depth)};
             scene.shots.push_back(shot);
         }
+        const std::string kpath = args.get("keypoints");
+        std::vector<std::vector<float>> kstorage(n_images);
+        if (!kpath.empty()) {
+            std::ifstream kf(kpath, std::ios::binary);
+            if (!kf) throw std::runtime_error("cannot open " + kpath);
+            char kmagic[4]; uint32_t khdr[2];
+            kf.read(kmagic, 4); kf.read(reinterpret_cast<char*>(khdr), 8);
+            if (!kf || std::memcmp(kmagic, "SFMK", 4) != 0 || khdr[0] != 1 || khdr[1] != n_images)
+                throw std::runtime_error("not an SFMK v1 file for this descriptor bank");
+            for (uint32_t i = 0; i < n_images; ++i) {
+                uint32_t meta[3];
+                kf.read(reinterpret_cast<char*>(meta), 12);
+                kstorage[i].resize(static_cast<size_t>(meta[0]) * 2);
+                kf.read(reinterpret_cast<char*>(kstorage[i].data()), static_cast<std::streamsize>(kstorage[i].size() * 4));
+                if (!kf || static_cast<int>(meta[0]) < scene.shots[i]->descriptors.rows) throw std::runtime_error("truncated SFMK file");
+                scene.shots[i]->keypointPts = kstorage[i].data();
+                scene.shots[i]->keypointStep = 8;
+                scene.shots[i]->imageWidth = static_cast<int>(meta[1]);
+                scene.shots[i]->imageHeight = static_cast<int>(meta[2]);
+            }
+        }
         std::vector<std::string> warnings;
         if (det != "ORB" && det != "SIFT" && !det.empty())
             warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
@@ -93,16 +118,19 @@ int main(int argc, char** argv) {
         stage.setFeatureMatchingStrategy(strategy);
         stage.setMinMatchCount(std::stoi(args.get("match-threshold", "20")));
         stage.setUseDistinctFeatureMatchTest(args.flag("distinct-matches"));
+        stage.setRansacReprojectionMatchingThreshold(std::stod(args.get("ransac-matching-threshold", "0.006")));
         const auto t0 = std::chrono::steady_clock::now();
-        const std::vector<ShotMatches> res = stage.calculateShotMatches(scene);
+        std::vector<ShotMatches> res = stage.calculateShotMatches(scene);
+        if (!kpath.empty()) stage.calculateHomography(res);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         const size_t n_pairs = strategy->matchPairs(scene.shots.size()).size();
         size_t total = 0;
         for (auto& sm : res) total += sm.matches.size();
         std::printf("pairs=%zu kept=%zu matches=%zu seconds=%.6f\n", n_pairs, res.size(), total, dt);
-        if (loglevel >= 3)
+        if (loglevel >= 3 || !kpath.empty())
             for (auto& sm : res)
-                std::printf("%s : %s -> %zu\n", sm.left->imagePath.c_str(), sm.right->imagePath.c_str(), sm.matches.size());
+                std::printf("%s : %s -> %zu homographyInlierRatio: %.6f\n", sm.left->imagePath.c_str(), sm.right->imagePath.c_str(),
+                            sm.matches.size(), sm.homographyInlierRatio);
         const std::string out = args.get("out");
         if (!out.empty()) {
             std::ofstream o(out, std::ios::binary);

@@ -1,5 +1,7 @@
 #include "matching.h"
 
+#include <algorithm>
+
 #include <cmath>
 
 namespace sfmhost {
@@ -123,9 +125,45 @@ std::vector<ShotMatches> MatchingStage::calculateShotMatches(const Scene& scene)
     std::vector<ShotMatches> all, kept;
     strategy_->calculateShotMatches(scene, matcher_, all);
     const auto& dropped = strategy_->lastDropped();
+    keptPair_.clear();
+    lastShots_ = scene.getShots();
+    lastPairs_ = strategy_->matchPairs(lastShots_.size());
     for (std::size_t p = 0; p < all.size(); ++p)
-        if (!dropped[p]) kept.push_back(std::move(all[p]));
+        if (!dropped[p]) { kept.push_back(std::move(all[p])); keptPair_.push_back(p); }
     return kept;
+}
+
+void MatchingStage::calculateHomography(std::vector<ShotMatches>& shotMatches) {
+    if (!matcher_) throw std::invalid_argument("Der Feature Matching Algorithmus darf nicht null sein.");
+    if (shotMatches.size() != keptPair_.size())
+        throw std::invalid_argument("calculateHomography expects the ShotMatches of the last calculateShotMatches");
+    if (lastPairs_.empty()) return;
+    sfm_ctx* ctx = matcher_->context();
+    const std::size_t n = lastShots_.size();
+    std::vector<const void*> pts(n);
+    std::vector<int32_t> nrows(n);
+    std::vector<std::size_t> steps(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        const Shot& s = *lastShots_[i];
+        nrows[i] = s.descriptors.empty() ? 0 : s.descriptors.rows;
+        if (nrows[i] > 0 && !s.keypointPts) throw std::invalid_argument("calculateHomography: shot without keypoints");
+        pts[i] = s.keypointPts;
+        steps[i] = s.keypointStep ? s.keypointStep : 8;
+    }
+    check(ctx, sfm_keypoints_upload(ctx, static_cast<int>(n), pts.data(), nrows.data(), steps.data()));
+    // SfM.cpp:615-620 (the reference takes rightSize.height twice; mirrored)
+    std::vector<double> thr(lastPairs_.size());
+    for (std::size_t p = 0; p < lastPairs_.size(); ++p) {
+        const Shot& l = *lastShots_[lastPairs_[p].first];
+        const Shot& r = *lastShots_[lastPairs_[p].second];
+        const double t = ransacReprojectionMatchingThreshold_;
+        thr[p] = t < 0 ? -t : std::max(std::max(l.imageWidth, l.imageHeight), r.imageHeight) * t;
+        if (!(thr[p] > 0)) throw std::invalid_argument("calculateHomography: image sizes are needed for a relative threshold");
+    }
+    std::vector<double> ratios(lastPairs_.size());
+    check(ctx, sfm_homography_inlier_ratios(ctx, thr.data(), static_cast<int64_t>(thr.size()), nullptr, ratios.data(), nullptr,
+                                            nullptr, nullptr));
+    for (std::size_t k = 0; k < shotMatches.size(); ++k) shotMatches[k].homographyInlierRatio = ratios[keptPair_[k]];
 }
 
 std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& det, const std::string& mat, int device,

@@ -7,7 +7,8 @@
 //                                    UnorderedFeatureMatchingStrategy.cpp:51/:68)
 //   Shot / Scene / ShotMatches   <-> CameraShot / Scene / ShotMatches         (Scene.h:35-135)
 //   IFeatureMatchingStrategy + Unordered/Video/Grid strategies                (IFeatureMatchingStrategy.h:34-48 ...)
-//   MatchingStage                <-> SfM::calculateShotMatches + its setters  (SfM.cpp:542-575, :52-79)
+//   MatchingStage                <-> SfM::calculateShotMatches + its setters  (SfM.cpp:542-575, :52-79) and
+//                                    SfM::calculateHomography                 (SfM.cpp:599-637)
 //
 // The strategies here do not loop over pairs calling knnMatch: they hand the whole pair list to
 // sfm_match_pairs (one bank upload, batched kernels), which is the throughput path.
@@ -68,6 +69,12 @@ private:
 struct Shot {
     std::string imagePath;
     DescriptorMat descriptors;      // Features::descriptors
+    // Features::keypoints (CameraShot.h:39-42): pointer to the first KeyPoint.pt (two floats) and the distance in bytes
+    // between consecutive points (sizeof(cv::KeyPoint) = 28 for a std::vector<cv::KeyPoint>, 8 for packed float pairs);
+    // one point per descriptor row.  Needed by MatchingStage::calculateHomography only.
+    const float* keypointPts = nullptr;
+    std::size_t keypointStep = 0;
+    int imageWidth = 0, imageHeight = 0;    // CameraShot::getImageSize()
 };
 
 struct Scene {
@@ -153,14 +160,27 @@ public:
         minMatchCount_ = n;
     }
     void setUseDistinctFeatureMatchTest(bool b) { distinct_ = b; }
+    // SfM::setRansacReprojectionMatchingThreshold (SfM.cpp:108-115): < 0 = pixels, > 0 = fraction of the image size
+    void setRansacReprojectionMatchingThreshold(double t) {
+        if (t == 0) throw std::invalid_argument("Der RANSAC Schwellwert darf nicht 0 sein.");
+        ransacReprojectionMatchingThreshold_ = t;
+    }
     // returns the surviving ShotMatches (pairs below minMatchCount erased), pair-list order
     std::vector<ShotMatches> calculateShotMatches(const Scene& scene);
+    // SfM::calculateHomography (SfM.cpp:599-637) for the ShotMatches returned by the last calculateShotMatches: sets
+    // homographyInlierRatio from the match lists that are still resident on the GPU (pairs with < 4 matches keep -1).
+    // Every shot needs keypointPts and an image size.
+    void calculateHomography(std::vector<ShotMatches>& shotMatches);
 
 private:
     std::shared_ptr<GpuDescriptorMatcher> matcher_;
     std::shared_ptr<IFeatureMatchingStrategy> strategy_;
     int minMatchCount_ = 20;        // SfM.h default
     bool distinct_ = false;
+    double ransacReprojectionMatchingThreshold_ = -3.0;      // SfM.h:50
+    std::vector<std::size_t> keptPair_;                      // pair-list position of every ShotMatches returned last
+    std::vector<std::shared_ptr<Shot>> lastShots_;
+    PairList lastPairs_;
 };
 
 // PhotogrammetrieCli::configureFeatureMatcher / configureFeatureMatcherStrategy (PhotogrammetrieCli.cpp:320-392)

@@ -168,3 +168,40 @@ def test_gpu_synthetic_planted_homographies(sfm, matcher, hom):
         cnt, h, mask = hn.ransac_inliers(pts, 3.0, pair=j, seed=3)
         assert (int(inl[j]), int(hyp[j])) == (cnt, h), (k, int(inl[j]), cnt)
         assert abs(ratios[j] - int(hom[f"syn{k}_count"]) / n) <= RATIO_TOL
+
+
+@pytest.mark.gpu
+def test_gpu_host_mirror_cli_homography(sfm, hom, insel_sift, tmp_path):
+    """C++ host mirror (MatchingStage::calculateHomography) through the CLI with the reference's switch spelling
+    (-Pransac-matching-threshold, PhotogrammetrieCli.cpp:98-99; relative threshold = max(image side) * t)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "sfm-mvs-pipeline_b200", "sfm_match_cli")
+    if not os.path.exists(cli):
+        pytest.skip("cli not built")
+    bank = [insel_sift[f"desc{i}"].astype(np.float32) for i in range(3)]
+    path, kpath = tmp_path / "bank.sfmd", tmp_path / "bank.sfmk"
+    with open(path, "wb") as f:
+        f.write(b"SFMD" + np.array([1, 3, 128, 5], np.uint32).tobytes())
+        for d in bank:
+            f.write(np.uint32(d.shape[0]).tobytes() + d.tobytes())
+    with open(kpath, "wb") as f:
+        f.write(b"SFMK" + np.array([1, 3], np.uint32).tobytes())
+        for i in range(3):
+            k = hom[f"sift_kp{i}"]
+            w, h = hom["sift_sizes"][i]
+            f.write(np.array([len(k), w, h], np.uint32).tobytes() + np.ascontiguousarray(k, np.float32).tobytes())
+    r = subprocess.run([cli, f"-Pdescriptors={path}", f"-Pkeypoints={kpath}", "-Pfeature-detector=SIFT",
+                        "-Pmatch-threshold=20", "-Pransac-matching-threshold=0.006"], capture_output=True, text=True, timeout=120)
+    assert "pairs=3 kept=3 matches=583" in r.stdout, r.stdout + r.stderr          # 205 + 163 + 215
+    ratios = [float(line.rsplit(" ", 1)[1]) for line in r.stdout.splitlines() if "homographyInlierRatio" in line]
+    assert len(ratios) == 3
+    thr = 720 * 0.006                                                              # insel images are 720 x 405
+    for (a, b), got in zip(PAIRS, ratios):
+        good = insel_sift[f"p{a}{b}_good"]
+        pts = hn.aligned_points(hom[f"sift_kp{a}"], hom[f"sift_kp{b}"], good)
+        from oracle import cv2_ref
+        if cv2_ref.available():
+            cv, _ = cv2_ref.find_homography_inliers(pts[:, :2], pts[:, 2:], thr)
+            assert abs(got - cv / len(good)) <= RATIO_TOL
+        assert 0.5 < got <= 1.0
