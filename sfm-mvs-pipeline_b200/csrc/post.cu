@@ -66,48 +66,65 @@ cudaError_t launch_zero_padding(void* bank, int row_bytes, int64_t padded_rows, 
 
 // one warp per 128-byte row: |b|^2, the packed column key of the IMAD epilogue, and the norm digits of the
 // value-only epilogue (see common.cuh)
-__global__ void norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t padded_rows,
+constexpr int kNormRowsPerWarp = 8;              // 8 warps x 8 rows = 64 rows per CTA: one global atomic pair per CTA
+__global__ void __launch_bounds__(256) norms_ckeys_kernel(const uint8_t* __restrict__ bank, int64_t padded_rows,
                                    const int32_t* __restrict__ valid_in_block, int32_t* __restrict__ norm2,
                                    int32_t* __restrict__ ckey, int8_t* __restrict__ ext, int* __restrict__ max_norm2,
                                    int32_t* __restrict__ blk_min, int32_t* __restrict__ blk_max) {
-    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= padded_rows) return;
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(bank + row * 128 + 4 * lane);
-    uint32_t s = __dp4a(w, w, 0u);
+    __shared__ int s_max, s_min;
+    if (threadIdx.x == 0) { s_max = 0; s_min = INT_MAX; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row_base = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * kNormRowsPerWarp;
+    int w_max = 0, w_min = INT_MAX;                  // over this warp's valid rows (lane 0)
+    for (int r = 0; r < kNormRowsPerWarp; ++r) {
+        const int64_t row = row_base + r;
+        if (row >= padded_rows) break;
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(bank + row * 128 + 4 * lane);
+        uint32_t s = __dp4a(w, w, 0u);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const int col = static_cast<int>(row & (kRowAlign - 1));
-    const bool valid = col < valid_in_block[row / kRowAlign];
-    if (lane == 0) {
-        norm2[row] = static_cast<int32_t>(s);
-        // key = (|b|^2 - 2ab) * 256 + col  ==  ckey - 512 * ab
-        ckey[row] = valid ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col)) : (kSentinelKey | col);
-        if (valid) {
-            atomicMax(max_norm2, static_cast<int>(s));
-            atomicMin(max_norm2 + 1, static_cast<int>(s));
-            atomicMin(blk_min + row / kRowAlign, static_cast<int>(s));      // |b|^2 range of the block: bounds of the
-            atomicMax(blk_max + row / kRowAlign, static_cast<int>(s));      // norm-less path (refine_dot_kernel)
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const int col = static_cast<int>(row & (kRowAlign - 1));
+        const bool valid = col < valid_in_block[row / kRowAlign];
+        if (lane == 0) {
+            norm2[row] = static_cast<int32_t>(s);
+            // key = (|b|^2 - 2ab) * 256 + col  ==  ckey - 512 * ab
+            ckey[row] = valid ? static_cast<int32_t>((s << 8) | static_cast<uint32_t>(col)) : (kSentinelKey | col);
+            if (valid) { w_max = max(w_max, static_cast<int>(s)); w_min = min(w_min, static_cast<int>(s)); }
         }
+        // digit of lane p: weight 255 at positions with (p & 15) < 12, weight 1 otherwise
+        int digit = 128;
+        if (valid && s <= static_cast<uint32_t>(kExtMaxNorm2)) {
+            const int g = static_cast<int>(s >> 1), q = g / 255, rr = g - q * 255;
+            const int sub = lane & 15, half = lane >> 4;
+            if (sub < 12) digit = min(128, max(0, q - 128 * (half * 12 + sub)));
+            else          digit = min(128, max(0, rr - 128 * (half * 4 + sub - 12)));
+        }
+        ext[row * kExtBytes + lane] = static_cast<int8_t>(-digit);
     }
-    // digit of lane p: weight 255 at positions with (p & 15) < 12, weight 1 otherwise
-    int digit = 128;
-    if (valid && s <= static_cast<uint32_t>(kExtMaxNorm2)) {
-        const int g = static_cast<int>(s >> 1), q = g / 255, r = g - q * 255;
-        const int sub = lane & 15, half = lane >> 4;
-        if (sub < 12) digit = min(128, max(0, q - 128 * (half * 12 + sub)));
-        else          digit = min(128, max(0, r - 128 * (half * 4 + sub - 12)));
+    // |b|^2 ranges: the 8 rows of a warp lie in one 256-row block (row_base is a multiple of 8), so one atomic pair per
+    // warp on the block range (bounds of the norm-less path, refine_dot_kernel) and one per CTA on the bank range --
+    // a per-row atomic on ONE address cost 1.7 ms on the C3 bank
+    if (lane == 0 && w_min != INT_MAX) {
+        atomicMin(blk_min + row_base / kRowAlign, w_min);
+        atomicMax(blk_max + row_base / kRowAlign, w_max);
+        atomicMax(&s_max, w_max);
+        atomicMin(&s_min, w_min);
     }
-    ext[row * kExtBytes + lane] = static_cast<int8_t>(-digit);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_min != INT_MAX) {
+        atomicMax(max_norm2, s_max);
+        atomicMin(max_norm2 + 1, s_min);
+    }
 }
 
 cudaError_t launch_norms_ckeys(const uint8_t* bank, int64_t padded_rows, const int32_t* valid_in_block,
                                int32_t* norm2, int32_t* ckey, int8_t* ext, int* max_norm2, int32_t* blk_min, int32_t* blk_max,
                                cudaStream_t s) {
     if (padded_rows == 0) return cudaSuccess;
-    const int64_t threads = padded_rows * 32;
-    norms_ckeys_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, s>>>(bank, padded_rows, valid_in_block,
-                                                                                     norm2, ckey, ext, max_norm2, blk_min, blk_max);
+    const int64_t rows_per_cta = 8 * kNormRowsPerWarp;
+    norms_ckeys_kernel<<<static_cast<unsigned>((padded_rows + rows_per_cta - 1) / rows_per_cta), 256, 0, s>>>(
+        bank, padded_rows, valid_in_block, norm2, ckey, ext, max_norm2, blk_min, blk_max);
     return cudaGetLastError();
 }
 
@@ -672,9 +689,12 @@ __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__
 __global__ void f32_split_kernel(const float* __restrict__ bank, int64_t padded_rows,
                                  const int32_t* __restrict__ valid_in_block, float* __restrict__ hi, float* __restrict__ lo,
                                  float* __restrict__ fnorm2, float* __restrict__ ext, int* __restrict__ max_norm_bits) {
+    __shared__ int s_max;                                         // largest |b|^2 of the CTA's rows (float bits)
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
     const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (row >= padded_rows) return;
+    if (row < padded_rows) {
     const float4 x = reinterpret_cast<const float4*>(bank + row * 128)[lane];
     float4 h, l;
     h.x = tf32_trunc(x.x); h.y = tf32_trunc(x.y); h.z = tf32_trunc(x.z); h.w = tf32_trunc(x.w);
@@ -692,8 +712,11 @@ __global__ void f32_split_kernel(const float* __restrict__ bank, int64_t padded_
         float4* e = reinterpret_cast<float4*>(ext + row * 8);
         e[0] = make_float4(-g0, -g1, -g2, 0.f);
         e[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && s >= 0.f) atomicMax(max_norm_bits, __float_as_int(s));   // non-negative floats order like ints
+        if (valid && s >= 0.f) atomicMax(&s_max, __float_as_int(s));          // non-negative floats order like ints
     }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max > 0) atomicMax(max_norm_bits, s_max);      // one global atomic per CTA, not per row
 }
 
 cudaError_t launch_f32_split(const float* bank, int64_t padded_rows, const int32_t* valid_in_block, float* hi, float* lo,
