@@ -291,6 +291,7 @@ def run_ours(a):
         dist.all_reduce(launches)
     m.set_profiling(False)
     result = m.collect()
+    refine_stats = m.float_stats()
     value = len(pairs) * a.steps / (ms_total / 1e3)
 
     # ---- end to end through the C ABI with host buffers
@@ -328,6 +329,8 @@ def run_ours(a):
             tr.append(time.perf_counter())
         else:
             m.enqueue(my_pairs, sfm.NORM_L2)                       # kernels; lists stay on the GPU ...
+            if os.environ.get("SFM_BENCH_TRACE"):
+                stream.synchronize()                               # trace only: separate the kernels from the gather
             tr.append(time.perf_counter())
             g = shard.gather_matches_device(m, mine, all_mine, len(pairs), dev, 0)   # ... NCCL gather, one D2H on rank 0
             if rank == 0:
@@ -366,8 +369,10 @@ def run_ours(a):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(a), "pairs": int(len(pairs)), "parallelism": f"pair-list x{world}",
                        "l2": "inputs larger than L2 (bank 200 MiB + 512 MiB top-2 staging per batch vs 126 MB L2); no flush",
-                       "engine": "tcgen05 kind::i8, value-only fused top-k epilogue (knn2_l2_u8_tcv_kernel) + exact refine", "matches_per_step": total_matches,
-                       "matches_device_run": int(result.offsets[-1])},
+                       "engine": "tcgen05 kind::i8, value-only fused top-k epilogue (knn2_l2_u8_tcv_kernel, norm-less variant: 4 K-steps) + exact refine", "matches_per_step": total_matches,
+                       "matches_device_run": int(result.offsets[-1]),
+                       "refine": {"rows_reranked_exactly": refine_stats["rows_reranked"], "rows_brute_forced": refine_stats["rows_brute_forced"],
+                                  "query_rows": int(n_rows) * int(len(my_pairs))}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": float(t.item()), "host_buffers": "pinned CV_32F descriptors, as the reference holds them",
                     "bytes_are": "summed over ranks (every rank uploads 1/N of the scene; NCCL all-gathers the packed bank)"},

@@ -66,6 +66,7 @@ struct FilterArgs {
     int64_t staged_rows;         // out_prefix[n_pairs]
     FilterParams fp;
     int32_t* train_cnt;          // distinct: zeroed by the caller
+    const int32_t* blk_pair;     // pair of every 256-row staging block (launch_block_pairs), or null: binary search
 };
 // tcgen05 path only: tighten the provisional second neighbour (see refine_second_kernel in post.cu)
 struct RefineArgs {
@@ -85,7 +86,14 @@ struct RefineArgs {
     const int32_t* blk_max;
     unsigned long long* stats;   // [0] rows re-ranked, [1] rows brute-forced
     int chunk_rows;              // train rows per candidate chunk of the value-only kernels (32 or 64)
+    // refine_dot: rows whose answer needs the whole train image are queued here and finished by brute_force_rows_kernel
+    // (one CTA per row) instead of stalling the warp that found them
+    int32_t* bf_list;            // staged row numbers, capacity = staged_rows
+    int* bf_count;
+    const int32_t* blk_pair;     // as in FilterArgs
 };
+// pair index of every 256-row staging block: one binary search per block instead of one per thread and post kernel
+cudaError_t launch_block_pairs(const int64_t* out_prefix, int n_pairs, int64_t n_blocks, int32_t* blk_pair, cudaStream_t s);
 cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
 // value-only tcgen05 path: (chunk, D) pairs -> exact Top2 for rows that can pass the ratio test (see post.cu)
 cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s);
@@ -118,6 +126,7 @@ struct RefineF32Args {
     const float* bank;           // fp32 bank, 128 floats per row
     const float* fnorm2;
     float nb_max;                // largest |b|^2 of the bank (error bound)
+    const int32_t* blk_pair;     // as in FilterArgs (staging blocks of THIS pass), or null
     int all_rows;
     unsigned long long* stats;   // [0] rows re-ranked, [1] rows brute-forced (certificate failed)
     int swap_roles;              // cross-check pass: train rows query the left image (rows laid out by t_prefix)

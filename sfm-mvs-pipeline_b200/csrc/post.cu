@@ -162,11 +162,29 @@ cudaError_t launch_expand_bits(const uint8_t* bank32, int64_t padded_rows, const
 }
 
 // ------------------------------------------------------------------------------------------------ filters
+// pair of a staging row: 256-row staging blocks never straddle pairs, so a per-block table replaces the binary search
+__device__ __forceinline__ int pair_of_row(const int32_t* __restrict__ blk_pair, const int64_t* __restrict__ out_prefix,
+                                           int n_pairs, int64_t srow) {
+    return blk_pair ? __ldg(blk_pair + (srow >> 8)) : find_segment(out_prefix, n_pairs, srow);
+}
+
+__global__ void block_pairs_kernel(const int64_t* __restrict__ out_prefix, int n_pairs, int64_t n_blocks,
+                                   int32_t* __restrict__ blk_pair) {
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b < n_blocks) blk_pair[b] = find_segment(out_prefix, n_pairs, b * 256);
+}
+
+cudaError_t launch_block_pairs(const int64_t* out_prefix, int n_pairs, int64_t n_blocks, int32_t* blk_pair, cudaStream_t s) {
+    if (n_blocks == 0) return cudaSuccess;
+    block_pairs_kernel<<<static_cast<unsigned>((n_blocks + 255) / 256), 256, 0, s>>>(out_prefix, n_pairs, n_blocks, blk_pair);
+    return cudaGetLastError();
+}
+
 struct RowCtx { int p; int row; bool valid; PairDesc pd; Top2 t; };
 
 __device__ __forceinline__ RowCtx load_row(const FilterArgs& a, int64_t srow) {
     RowCtx c;
-    c.p = find_segment(a.out_prefix, a.n_pairs, srow);
+    c.p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
     c.pd = a.pairs[c.p];
     c.row = static_cast<int>(srow - a.out_prefix[c.p]);
     c.valid = c.row < c.pd.nq;
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
     t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
     int q_bank_row = 0, t_row0 = 0, nt = 0;
     if (srow < a.staged_rows) {
-        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
         const PairDesc pd = a.pairs[p];
         const int row = static_cast<int>(srow - a.out_prefix[p]);
         if (row < pd.nq) {
@@ -351,6 +369,41 @@ __device__ __forceinline__ void warp_chunk_candidates(const uint8_t* __restrict_
     }
 }
 
+// exact top-2 over the WHOLE train image for one query row, one warp: four 32-row groups per step so that their loads
+// are in flight together (a warp that has to brute-force a row is the tail of the refine kernels)
+__device__ __forceinline__ void warp_brute_force(const uint8_t* __restrict__ bank, const int32_t* __restrict__ norm2,
+                                                 const uint4 (&q)[8], int na, int tr0, int ntr, int lane, long long& a1,
+                                                 long long& a2) {
+    const int groups = (ntr + 31) / 32;
+    int c = 0;
+    for (; c + 4 <= groups; c += 4) {
+        uint32_t dot[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint4 y[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                y[g] = __ldg(reinterpret_cast<const uint4*>(bank + (static_cast<size_t>(tr0) + (c + g) * 32 + lane) * 128) + i);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                dot[g] = __dp4a(q[i].x, y[g].x, dot[g]); dot[g] = __dp4a(q[i].y, y[g].y, dot[g]);
+                dot[g] = __dp4a(q[i].z, y[g].z, dot[g]); dot[g] = __dp4a(q[i].w, y[g].w, dot[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int j = (c + g) * 32 + lane;
+            if (j < ntr) {
+                const int32_t d = na + norm2[tr0 + j] - 2 * static_cast<int32_t>(dot[g]);
+                const long long key = (static_cast<long long>(d) << 32) | static_cast<unsigned>(j);
+                a2 = min(a2, max(a1, key));
+                a1 = min(a1, key);
+            }
+        }
+    }
+    for (; c < groups; ++c) warp_chunk_candidates(bank, norm2, q, na, tr0, ntr, c, lane, a1, a2);
+}
+
 __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
     const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -359,7 +412,7 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
     t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
     int q_bank_row = 0, t_row0 = 0, nt = 0;
     if (srow < a.staged_rows) {
-        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
         const PairDesc pd = a.pairs[p];
         const int row = static_cast<int>(srow - a.out_prefix[p]);
         if (row < pd.nq) {
@@ -398,7 +451,7 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
         long long a1 = LLONG_MAX, a2 = LLONG_MAX;
         if (c2raw >= 0 && (c2raw & 0x40000000)) {
             // ambiguous: a third chunk ties the second one -> exact brute force over the whole train image
-            for (int c = 0; c * 32 < ntr; ++c) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c, lane, a1, a2);
+            warp_brute_force(a.bank, a.norm2, q, na, tr0, ntr, lane, a1, a2);
         } else {
             const int sub = a.chunk_rows / 32;                      // a candidate chunk = sub groups of 32 train rows
             for (int k = 0; k < sub; ++k) {
@@ -431,23 +484,27 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
 //     the best rows of chunks 1 and 2   : d^2 <= |a|^2 + N+ - 2 V2          (two different rows)
 //     every row outside the four chunks : d^2 >= |a|^2 + N- - 2 V5  =: lbo
 // (1) rows with sqrtf(|a|^2 + N- - 2 V1) >= ratio * sqrtf(|a|^2 + N+ - 2 V2) cannot pass the ratio test: rejected.
-// (2) the others recompute their <= 128 candidate rows exactly (__dp4a) -> (e0, j0), (e1, j1), exact within the chunks.
+// (2a) the others first recompute the best chunk alone (stage A in the kernel): a planted match is certified against
+//     lb2 = |a|^2 + N- - 2 V2 and its ratio test decided from d1^2 in [min(e1', lb2), min(e1', |a|^2 + N+ - 2 V2)].
+// (2) what is left recomputes all candidate rows exactly (__dp4a) -> (e0, j0), (e1, j1), exact within the chunks.
 //     e0 < lbo certifies (e0, j0) as THE nearest neighbour (ties resolve to the lowest index inside the chunks; a tie
 //     with an outside row is excluded by the strict '<').  The second neighbour's d1^2 lies in [min(e1, lbo), e1]; the
 //     ratio test  sqrtf(e0) < ratio * sqrtf(d1^2)  is monotone in d1^2, so it is decided if both ends agree, and the
 //     reported (d0, idx0) never depends on d1.  In that case d1 is written as the end that was used (keep_basic re-runs
 //     the same comparison); the lists equal cv::BFMatcher + ratio test bit for bit.
 // (3) anything else (not certified, or the two ends disagree) is brute-forced over the whole train image.
-__global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
+__global__ void __launch_bounds__(256, 3) refine_dot_kernel(RefineArgs a) {
     __shared__ int s_min[8], s_max[8];
     const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // the 256 staged rows of a CTA belong to one pair: the train image's |b|^2 range, once per CTA
+    // the 256 staged rows of a CTA belong to ONE pair (pairs start at multiples of 256 staged rows): one segment search
+    // and one |b|^2 range of the train image per CTA
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 256;
+    const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, r0 < a.staged_rows ? r0 : a.staged_rows - 1);
+    const PairDesc pd = a.pairs[p];
+    const int64_t pair_row0 = a.out_prefix[p];
     int nbmin = INT_MAX, nbmax = 0;
     {
-        const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 256;
-        const int p = find_segment(a.out_prefix, a.n_pairs, r0 < a.staged_rows ? r0 : a.staged_rows - 1);
-        const PairDesc pd = a.pairs[p];
         const int b0 = pd.t_row0 / kRowAlign, nb = (pd.nt + kRowAlign - 1) / kRowAlign;
         for (int b = threadIdx.x; b < nb; b += 256) { nbmin = min(nbmin, a.blk_min[b0 + b]); nbmax = max(nbmax, a.blk_max[b0 + b]); }
 #pragma unroll
@@ -464,16 +521,15 @@ __global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
     bool need = false, valid = false;
     Top2 t;
     t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
-    int v5 = -1, na = 0, q_bank_row = 0, t_row0 = 0, nt = 0;
+    int v5 = -1, na = 0, q_bank_row = 0;
+    const int t_row0 = pd.t_row0, nt = pd.nt;
     if (srow < a.staged_rows) {
-        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
-        const PairDesc pd = a.pairs[p];
-        const int row = static_cast<int>(srow - a.out_prefix[p]);
+        const int row = static_cast<int>(srow - pair_row0);
         if (row < pd.nq && pd.nt > 0) {
             valid = true;
             t = a.top2[srow];
             v5 = a.aux[srow];
-            q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
+            q_bank_row = pd.q_row0 + row;
             na = a.norm2[q_bank_row];
             const int V1 = __float_as_int(t.d0), V2 = __float_as_int(t.d1);
             if (a.all_rows || V2 <= 0) need = true;                           // fewer than two chunks with a real maximum
@@ -495,8 +551,7 @@ __global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1;
         const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
-        const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
-        const int ntr = __shfl_sync(0xffffffffu, nt, src);
+        const int tr0 = t_row0, ntr = nt;
         const int i0 = __shfl_sync(0xffffffffu, t.i0, src), i1 = __shfl_sync(0xffffffffu, t.i1, src);
         const int rv5 = __shfl_sync(0xffffffffu, v5, src);
         const int rna = __shfl_sync(0xffffffffu, na, src);
@@ -505,9 +560,48 @@ __global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
         const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
-        long long a1 = LLONG_MAX, a2 = LLONG_MAX;
-        int covered = 0;                                                // real train rows inside the candidate chunks
+        const int rV2 = __float_as_int(__shfl_sync(0xffffffffu, t.d1, src));
         const int sub = a.chunk_rows / 32;                          // a candidate chunk = sub groups of 32 train rows
+        long long a1 = LLONG_MAX, a2 = LLONG_MAX;
+        // ---- stage A: the best chunk alone.  Every row outside it has a.b <= V2, i.e. d^2 >= |a|^2 + N- - 2 V2 =: lb2,
+        // and chunk 2 holds a real row with d^2 <= |a|^2 + N+ - 2 V2 =: ub2.  A planted match has e0 far below lb2: the
+        // nearest neighbour is certified and d1^2 lies in [min(e1', lb2), min(e1', ub2)] (e1' = second best inside the
+        // chunk) -- if the ratio test agrees at both ends the row is finished after 32-64 exact distances.
+        if (!a.all_rows && cand[0] != 0xFFFF && rV2 > 0) {
+            for (int h = 0; h < sub; ++h)
+                warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[0] * sub + h, lane, a1, a2);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+                a2 = min(max(a1, b1), min(a2, b2));
+                a1 = min(a1, b1);
+            }
+            if (a1 != LLONG_MAX) {
+                const long long e0 = a1 >> 32;
+                const long long lb2 = static_cast<long long>(rna) + nbmin - 2ll * rV2;
+                const long long ub2 = static_cast<long long>(rna) + nbmax - 2ll * rV2;
+                if (e0 < lb2) {
+                    const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
+                    const long long lo1 = min(e1, lb2), hi1 = min(e1, ub2);
+                    const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
+                    const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lo1)))) * a.ratio;
+                    const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(hi1)))) * a.ratio;
+                    if (pass_lo == pass_hi) {
+                        if (lane == src) {
+                            o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(e0));
+                            // the second neighbour itself is not reported by the ratio-filtered stage: any index >= 0 marks
+                            // "a second neighbour exists", d1 = the end of the interval that was tested
+                            o.i1 = a2 != LLONG_MAX ? static_cast<int>(a2 & 0xFFFFFFFFll) : ntr;
+                            o.d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lo1 : hi1));
+                        }
+                        continue;
+                    }
+                }
+            }
+            a1 = LLONG_MAX; a2 = LLONG_MAX;
+        }
+        // ---- stage B: all candidate chunks
+        int covered = 0;                                                // real train rows inside the candidate chunks
         for (int k = 0; k < 4; ++k)
             if (cand[k] != 0xFFFF) {
                 for (int h = 0; h < sub; ++h)
@@ -549,20 +643,26 @@ __global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
                 }
             }
         }
-        if (!done) {                                                    // exact brute force over the whole train image
-            if (lane == 0) atomicAdd(a.stats + 1, 1ull);
-            a1 = LLONG_MAX; a2 = LLONG_MAX;
-            for (int c = 0; c * 32 < ntr; ++c) warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, c, lane, a1, a2);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
-                a2 = min(max(a1, b1), min(a2, b2));
-                a1 = min(a1, b1);
-            }
-            out_i1 = -1; out_d1 = inf;
-            if (a2 != LLONG_MAX) { out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll); out_d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
+        // not certified, but perhaps certainly failing: the true d0^2 is >= min(e0, lbo) and the true d1^2 is <= e1 (the
+        // second best candidate is a real row), so  sqrtf(min(e0, lbo)) >= ratio * sqrtf(e1)  means the ratio test fails
+        // whatever lies outside the candidates -- the usual case of a row without a planted match
+        bool rejected = false;
+        if (!done && !a.all_rows && a1 != LLONG_MAX && a2 != LLONG_MAX && outside) {
+            const long long lb0 = max(0ll, min(a1 >> 32, lbo)), e1 = a2 >> 32;
+            const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb0)));
+            const float s1 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)));
+            if (!(static_cast<double>(s0) < static_cast<double>(s1) * a.ratio)) { done = true; rejected = true; }
         }
-        if (lane == src) {
+        if (!done) {
+            // exact brute force over the whole train image: queued for brute_force_rows_kernel (a whole CTA per row)
+            if (lane == 0) {
+                atomicAdd(a.stats + 1, 1ull);
+                const int64_t row_of_src = static_cast<int64_t>(blockIdx.x) * 256 + (threadIdx.x & ~31) + src;
+                a.bf_list[atomicAdd(a.bf_count, 1)] = static_cast<int32_t>(row_of_src);
+            }
+            rejected = true;                                            // placeholder until that kernel writes the row
+        }
+        if (lane == src && !rejected) {
             if (a1 != LLONG_MAX) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(a1 >> 32)); }
             o.i1 = out_i1; o.d1 = out_d1;
         }
@@ -570,9 +670,63 @@ __global__ void __launch_bounds__(256) refine_dot_kernel(RefineArgs a) {
     if (valid) a.top2[srow] = o;        // rows that cannot pass keep i0 = -1 (rejected)
 }
 
+// Rows queued by refine_dot_kernel: exact top-2 over the whole train image, one CTA per row (8 warps take every eighth
+// group of 4 x 32 train rows), lexicographic (d^2, idx) keys, block reduction through shared memory.
+__global__ void __launch_bounds__(256) brute_force_rows_kernel(RefineArgs a) {
+    __shared__ long long s_k[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = *a.bf_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int64_t srow = a.bf_list[i];
+        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
+        const PairDesc pd = a.pairs[p];
+        const int qrow = pd.q_row0 + static_cast<int>(srow - a.out_prefix[p]);
+        const int na = a.norm2[qrow];
+        uint4 q[8];
+        const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = __ldg(qv + k);
+        long long a1 = LLONG_MAX, a2 = LLONG_MAX;
+        // warp w takes train rows [w * 128 + 1024 * m, +128): a sub-range view of the image for warp_brute_force
+        for (int r0 = warp * 128; r0 < pd.nt; r0 += 1024) {
+            long long b1 = LLONG_MAX, b2 = LLONG_MAX;
+            warp_brute_force(a.bank, a.norm2, q, na, pd.t_row0 + r0, min(128, pd.nt - r0), lane, b1, b2);
+            // indices are relative to r0: rebase, then merge
+            if (b1 != LLONG_MAX) b1 += r0;
+            if (b2 != LLONG_MAX) b2 += r0;
+            a2 = min(max(a1, b1), min(a2, b2));
+            a1 = min(a1, b1);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+            a2 = min(max(a1, b1), min(a2, b2));
+            a1 = min(a1, b1);
+        }
+        __syncthreads();                                  // previous row's s_k has been read
+        if (lane == 0) { s_k[2 * warp] = a1; s_k[2 * warp + 1] = a2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long m1 = LLONG_MAX, m2 = LLONG_MAX;
+            for (int w = 0; w < 8; ++w) {
+                const long long b1 = s_k[2 * w], b2 = s_k[2 * w + 1];
+                m2 = min(max(m1, b1), min(m2, b2));
+                m1 = min(m1, b1);
+            }
+            const float inf = __int_as_float(0x7f800000);
+            Top2 o;
+            o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
+            if (m1 != LLONG_MAX) { o.i0 = static_cast<int>(m1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(m1 >> 32)); }
+            if (m2 != LLONG_MAX) { o.i1 = static_cast<int>(m2 & 0xFFFFFFFFll); o.d1 = static_cast<float>(static_cast<int32_t>(m2 >> 32)); }
+            a.top2[srow] = o;
+        }
+    }
+}
+
 cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
     refine_dot_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
+    brute_force_rows_kernel<<<592, 256, 0, s>>>(a);          // persistent over the queue (usually a few dozen rows)
     return cudaGetLastError();
 }
 
@@ -763,7 +917,7 @@ __global__ void __launch_bounds__(256) refine_f32_kernel(RefineF32Args a) {
     float v4 = 0.f, eps = 0.f, na = 0.f;
     int q_bank_row = 0, t_row0 = 0, nt = 0;
     if (srow < a.staged_rows) {
-        const int p = find_segment(a.out_prefix, a.n_pairs, srow);
+        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
         PairDesc pd = a.pairs[p];
         if (a.swap_roles) {
             const PairDesc f = pd;

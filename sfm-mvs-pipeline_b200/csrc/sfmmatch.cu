@@ -114,6 +114,8 @@ struct sfm_ctx {
     DevBuf d_top2, d_rev, d_train_cnt, d_chunk_counts, d_chunk_excl, d_pair_counts, d_pair_offsets, d_dropped;
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
+    DevBuf d_blk_pair;               // pair index of every 256-row staging block of the current batch
+    DevBuf d_bf;                     // norm-less path: queue of staged rows that need the whole train image
     DevBuf d_hom;                    // homography stage: row0[2n] int64 | thresholds | inliers | best hypothesis
     DevBuf d_aux, d_aux_rev;         // 3xTF32 path: fifth-best chunk maximum per staged row
     DevBuf d_out2, d_pair_offsets2, d_dropped2, d_order, d_cnt_tmp;   // reorder targets of the pipelined host path
@@ -133,6 +135,9 @@ struct sfm_ctx {
     int prof_used = 0;
     size_t staging_budget_rows = 0;
     int tcv_layout_run = 12;
+    int tcv_spread_div = 2;          // norm-less variant allowed when (max - min |b|^2) * div <= max (SFM_TCV_SPREAD_DIV):
+                                     // measured a win at the 36 % spread of the 200-image SURVEY 8d bank, cv::SIFT has ~1 %
+    int32_t prev_nb_min = 0, prev_nb_max = 1;   // |b|^2 range of the previous bank of this context (pipelined path)
     int tcv_normless = 1;            // norm-less variant of the value-only kernel: SFM_TCV_NORMLESS = 0 never | 1 auto | 2 always
     int tcv_chunk = 64;              // train rows per candidate chunk of the value-only kernel (SFM_TCV_CHUNK = 32 | 64)
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
@@ -335,7 +340,10 @@ int bank_finish(sfm_ctx* c, Bank& b) {
     } else {
         b.u8_valued = true;
     }
-    if (b.u8_valued && b.cols == 128) { b.ext_ok = h[1] <= kExtMaxNorm2; b.nb_max = h[1]; b.nb_min = std::min(h[2], h[1]); }
+    if (b.u8_valued && b.cols == 128) {
+        b.ext_ok = h[1] <= kExtMaxNorm2; b.nb_max = h[1]; b.nb_min = std::min(h[2], h[1]);
+        if (&b == &c->bank) { c->prev_nb_min = b.nb_min; c->prev_nb_max = b.nb_max; }
+    }
     return make_tmaps(c, b);
 }
 
@@ -495,9 +503,9 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         c->tcv_layout_run = c->tcv_layout ? c->tcv_layout : (max_rows <= 32768 ? 12 : 14);
         if (max_rows <= (c->tcv_layout_run == 14 ? 65536 : 32768)) {
             eng = Engine::TCV;
-            // norms within 1/16 of each other (SIFT: ~1 %): the norm-less variant, one K-step less per tile; its bounds
-            // lose their grip when norms vary a lot, the exactness does not depend on the choice
-            if (c->tcv_normless == 2 || (c->tcv_normless == 1 && static_cast<int64_t>(b.nb_max - b.nb_min) * 16 <= b.nb_max))
+            // norms within 1/2 of each other (cv::SIFT: ~1 %, the SURVEY 8d recipe: 20-36 %): the norm-less variant, one K-step
+            // less per tile; its bounds lose their grip when norms vary a lot, the exactness does not depend on the choice
+            if (c->tcv_normless == 2 || (c->tcv_normless == 1 && static_cast<int64_t>(b.nb_max - b.nb_min) * c->tcv_spread_div <= b.nb_max))
                 eng = Engine::TCN;
         }
     }
@@ -611,6 +619,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
 
     CU_TRY(c, c->d_top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
     if (need_rev) CU_TRY(c, c->d_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
+    if (eng == Engine::TCN) CU_TRY(c, c->d_bf.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
     if (eng == Engine::TF32 || eng == Engine::TCN) {
         CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
         CU_TRY(c, c->d_aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
@@ -618,6 +627,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
     }
     if (need_cnt) CU_TRY(c, c->d_train_cnt.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
     CU_TRY(c, c->d_chunk_counts.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
+    CU_TRY(c, c->d_blk_pair.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
     CU_TRY(c, c->d_chunk_excl.ensure(static_cast<size_t>(max_chunks + 1) * 8));
     CU_TRY(c, c->d_pair_counts.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
     CU_TRY(c, c->d_pair_offsets.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
@@ -645,6 +655,8 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         const int np = static_cast<int>(B.p1 - B.p0);
         const int64_t base = B.p0 + bi;
         if (sched && sched->avail && sched->events) CU_TRY(c, cudaStreamWaitEvent(s, sched->events[sched->avail[B.p0]], 0));
+        CU_TRY(c, launch_block_pairs(d_outp + base, np, B.staged_rows / 256, c->d_blk_pair.as<int32_t>(), s));
+        c->stat_launches++;
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
         rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>(), c->d_aux.as<float>());
         if (rc != SFM_OK) return rc;
@@ -656,6 +668,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         if (eng == Engine::TF32) {
             // candidates -> exact fp32 top-2 (+ certificate); everything downstream sees ordinary Top2 rows
             RefineF32Args fa;
+            fa.blk_pair = c->d_blk_pair.as<int32_t>();
             fa.top2 = c->d_top2.as<Top2>(); fa.aux = c->d_aux.as<float>(); fa.pairs = d_pd + B.p0; fa.out_prefix = d_outp + base;
             fa.n_pairs = np; fa.staged_rows = B.staged_rows; fa.bank = b.d_f32.as<float>(); fa.fnorm2 = b.d_fnorm.as<float>();
             fa.nb_max = b.f_nb_max; fa.all_rows = (o->k == 1 || need_rev) ? 1 : 0; fa.swap_roles = 0; fa.ratio = o->ratio;
@@ -663,7 +676,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             CU_TRY(c, launch_refine_f32(fa, s));
             c->stat_launches++;
             if (need_rev) {
-                fa.top2 = c->d_rev.as<Top2>(); fa.aux = c->d_aux_rev.as<float>(); fa.swap_roles = 1;
+                fa.top2 = c->d_rev.as<Top2>(); fa.aux = c->d_aux_rev.as<float>(); fa.swap_roles = 1; fa.blk_pair = nullptr;
                 fa.out_prefix = d_tp + base; fa.staged_rows = B.t_rows; fa.all_rows = 1;
                 CU_TRY(c, launch_refine_f32(fa, s));
                 c->stat_launches++;
@@ -673,11 +686,16 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             RefineArgs ra{};
             ra.aux = c->d_aux.as<int32_t>(); ra.blk_min = b.d_blkmin.as<int32_t>(); ra.blk_max = b.d_blkmax.as<int32_t>();
             ra.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
-            ra.chunk_rows = c->tcv_chunk;
+            ra.chunk_rows = c->tcv_chunk; ra.blk_pair = c->d_blk_pair.as<int32_t>();
+            ra.bf_list = c->d_bf.as<int32_t>(); ra.bf_count = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 48);
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
             ra.all_rows = 0; ra.ratio = o->ratio; ra.hamming = o->norm == SFM_NORM_HAMMING;
-            if (eng == Engine::TCN) CU_TRY(c, launch_refine_dot(ra, s));
+            if (eng == Engine::TCN) {
+                CU_TRY(c, cudaMemsetAsync(ra.bf_count, 0, 4, s));
+                CU_TRY(c, launch_refine_dot(ra, s));
+                c->stat_launches++;
+            }
             else if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
             else CU_TRY(c, launch_refine_second(ra, s));
             c->stat_launches++;
@@ -685,7 +703,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         FilterArgs a;
         a.top2 = c->d_top2.as<Top2>(); a.rev = c->d_rev.as<Top2>(); a.pairs = d_pd + B.p0;
         a.out_prefix = d_outp + base; a.t_prefix = d_tp + base; a.n_pairs = np; a.staged_rows = B.staged_rows;
-        a.fp = fp; a.train_cnt = c->d_train_cnt.as<int32_t>();
+        a.fp = fp; a.train_cnt = c->d_train_cnt.as<int32_t>(); a.blk_pair = c->d_blk_pair.as<int32_t>();
         if (need_cnt) {
             CU_TRY(c, cudaMemsetAsync(c->d_train_cnt.p, 0, static_cast<size_t>(B.t_rows) * 4, s));
             CU_TRY(c, launch_filter_mark(a, s));
@@ -840,9 +858,9 @@ int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int3
     CU_TRY(c, cudaMemsetAsync(b.d_blkmin.p, 0x7f, nblk_b, cs));
     CU_TRY(c, cudaMemsetAsync(b.d_blkmax.p, 0, nblk_b, cs));
     // optimistic bank properties (verified below): integer-valued SIFT-sized rows.  The norm spread is unknown until the
-    // data has arrived, so the pipelined run uses the kernel with the norm K-step (nb_min = 0 keeps the norm-less
-    // variant off)
-    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true; b.nb_min = 0; b.nb_max = 1;
+    // data has arrived: assume that of the previous bank of this context (the first call gets the kernel with the norm
+    // K-step); a wrong guess only costs time in the refine pass, never exactness
+    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true; b.nb_min = c->prev_nb_min; b.nb_max = c->prev_nb_max;
     rc = make_tmaps(c, b);
     if (rc != SFM_OK) return rc;
     // ---- image groups of roughly equal size
@@ -912,6 +930,7 @@ int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int3
     CU_TRY(c, cudaStreamSynchronize(cs));
     if (rc != SFM_OK) return rc;
     b.nb_max = h[1]; b.nb_min = std::min(h[2], h[1]);
+    c->prev_nb_min = b.nb_min; c->prev_nb_max = b.nb_max;
     if (h[0] != 0 || h[1] > kExtMaxNorm2) {
         // not integer-valued, or norms beyond the digit range: the optimistic run is void -> sequential path
         CU_TRY(c, cudaStreamSynchronize(s));
@@ -965,6 +984,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     size_t mb = 512;
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
+    if (const char* env = std::getenv("SFM_TCV_SPREAD_DIV")) { const int t = std::atoi(env); if (t >= 1) c->tcv_spread_div = t; }
     if (const char* env = std::getenv("SFM_TCV_NORMLESS")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_normless = t; }
     if (const char* env = std::getenv("SFM_TCV_CHUNK")) { const int t = std::atoi(env); if (t == 32 || t == 64) c->tcv_chunk = t; }
     if (const char* env = std::getenv("SFM_TCV_ISSUERS")) { const int t = std::atoi(env); if (t == 1 || t == 2) c->tcv_issuers = t; }
@@ -981,7 +1001,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
                       &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
                       &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
-                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom};
+                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom, &c->d_bf, &c->d_blk_pair};
     for (DevBuf* b : bufs) b->release();
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
@@ -1309,6 +1329,7 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     if (rc != SFM_OK) return rc;
     if (eng == Engine::TF32) {
         RefineF32Args fa;
+        fa.blk_pair = nullptr;
         fa.top2 = c->d_top2.as<Top2>(); fa.aux = c->d_aux.as<float>(); fa.pairs = d_pd;
         fa.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
         fa.n_pairs = 1; fa.staged_rows = pad_rows(nq); fa.bank = b.d_f32.as<float>(); fa.fnorm2 = b.d_fnorm.as<float>();
