@@ -90,6 +90,9 @@ struct RefineArgs {
     // (one CTA per row) instead of stalling the warp that found them
     int32_t* bf_list;            // staged row numbers, capacity = staged_rows
     int* bf_count;
+    int32_t* need_list;          // refine_dot pass 1 -> pass 2: staged rows that survived the quick reject (capacity = staged_rows)
+    int* need_count;
+    int32_t* pair_nb;            // [2 * n_pairs] |b|^2 range of the train image of every pair of the batch
     const int32_t* blk_pair;     // as in FilterArgs
 };
 // pair index of every 256-row staging block: one binary search per block instead of one per thread and post kernel

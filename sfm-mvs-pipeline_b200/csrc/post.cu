@@ -493,184 +493,204 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
 //     reported (d0, idx0) never depends on d1.  In that case d1 is written as the end that was used (keep_basic re-runs
 //     the same comparison); the lists equal cv::BFMatcher + ratio test bit for bit.
 // (3) anything else (not certified, or the two ends disagree) is brute-forced over the whole train image.
-__global__ void __launch_bounds__(256, 3) refine_dot_kernel(RefineArgs a) {
-    __shared__ int s_min[8], s_max[8];
-    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // the 256 staged rows of a CTA belong to ONE pair (pairs start at multiples of 256 staged rows): one segment search
-    // and one |b|^2 range of the train image per CTA
-    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 256;
-    const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, r0 < a.staged_rows ? r0 : a.staged_rows - 1);
-    const PairDesc pd = a.pairs[p];
-    const int64_t pair_row0 = a.out_prefix[p];
-    int nbmin = INT_MAX, nbmax = 0;
-    {
-        const int b0 = pd.t_row0 / kRowAlign, nb = (pd.nt + kRowAlign - 1) / kRowAlign;
-        for (int b = threadIdx.x; b < nb; b += 256) { nbmin = min(nbmin, a.blk_min[b0 + b]); nbmax = max(nbmax, a.blk_max[b0 + b]); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            nbmin = min(nbmin, __shfl_xor_sync(0xffffffffu, nbmin, o));
-            nbmax = max(nbmax, __shfl_xor_sync(0xffffffffu, nbmax, o));
-        }
-        if (lane == 0) { s_min[wid] = nbmin; s_max[wid] = nbmax; }
-        __syncthreads();
-        nbmin = s_min[0]; nbmax = s_max[0];
-#pragma unroll
-        for (int w = 1; w < 8; ++w) { nbmin = min(nbmin, s_min[w]); nbmax = max(nbmax, s_max[w]); }
-    }
-    bool need = false, valid = false;
-    Top2 t;
-    t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
-    int v5 = -1, na = 0, q_bank_row = 0;
-    const int t_row0 = pd.t_row0, nt = pd.nt;
-    if (srow < a.staged_rows) {
-        const int row = static_cast<int>(srow - pair_row0);
-        if (row < pd.nq && pd.nt > 0) {
-            valid = true;
-            t = a.top2[srow];
-            v5 = a.aux[srow];
-            q_bank_row = pd.q_row0 + row;
-            na = a.norm2[q_bank_row];
-            const int V1 = __float_as_int(t.d0), V2 = __float_as_int(t.d1);
-            if (a.all_rows || V2 <= 0) need = true;                           // fewer than two chunks with a real maximum
-            else {
-                const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na + nbmin - 2 * V1)));
-                const float hi1 = __fsqrt_rn(static_cast<float>(max(0, na + nbmax - 2 * V2)));
-                need = static_cast<double>(lo0) < static_cast<double>(hi1) * a.ratio;
-            }
-        } else if (row < pd.nq) {
-            valid = true;                                                     // empty train image: no neighbours
-        }
-    }
+// one warp, one query row that survived the quick reject: stages (2a), (2b), (3) of the comment above.  All arguments are
+// warp-uniform; lane 0 writes the row (or queues it for brute_force_rows_kernel).
+__device__ __forceinline__ void refine_dot_row(const RefineArgs& a, int64_t srow, int lane, const Top2 t, int rv5, int rna,
+                                               int qrow, int tr0, int ntr, int nbmin, int nbmax) {
     const float inf = __int_as_float(0x7f800000);
-    Top2 o;
-    o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
-    unsigned mask = __ballot_sync(0xffffffffu, need);
-    if (lane == 0 && mask) atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
-        const int tr0 = t_row0, ntr = nt;
-        const int i0 = __shfl_sync(0xffffffffu, t.i0, src), i1 = __shfl_sync(0xffffffffu, t.i1, src);
-        const int rv5 = __shfl_sync(0xffffffffu, v5, src);
-        const int rna = __shfl_sync(0xffffffffu, na, src);
-        uint4 q[8];
-        const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
+    const int i0 = t.i0, i1 = t.i1;
+    uint4 q[8];
+    const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
-        const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
-        const int rV2 = __float_as_int(__shfl_sync(0xffffffffu, t.d1, src));
-        const int sub = a.chunk_rows / 32;                          // a candidate chunk = sub groups of 32 train rows
-        long long a1 = LLONG_MAX, a2 = LLONG_MAX;
-        // ---- stage A: the best chunk alone.  Every row outside it has a.b <= V2, i.e. d^2 >= |a|^2 + N- - 2 V2 =: lb2,
-        // and chunk 2 holds a real row with d^2 <= |a|^2 + N+ - 2 V2 =: ub2.  A planted match has e0 far below lb2: the
-        // nearest neighbour is certified and d1^2 lies in [min(e1', lb2), min(e1', ub2)] (e1' = second best inside the
-        // chunk) -- if the ratio test agrees at both ends the row is finished after 32-64 exact distances.
-        if (!a.all_rows && cand[0] != 0xFFFF && rV2 > 0) {
-            for (int h = 0; h < sub; ++h)
-                warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[0] * sub + h, lane, a1, a2);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
-                a2 = min(max(a1, b1), min(a2, b2));
-                a1 = min(a1, b1);
-            }
-            if (a1 != LLONG_MAX) {
-                const long long e0 = a1 >> 32;
-                const long long lb2 = static_cast<long long>(rna) + nbmin - 2ll * rV2;
-                const long long ub2 = static_cast<long long>(rna) + nbmax - 2ll * rV2;
-                if (e0 < lb2) {
-                    const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
-                    const long long lo1 = min(e1, lb2), hi1 = min(e1, ub2);
-                    const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
-                    const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lo1)))) * a.ratio;
-                    const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(hi1)))) * a.ratio;
-                    if (pass_lo == pass_hi) {
-                        if (lane == src) {
-                            o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(e0));
-                            // the second neighbour itself is not reported by the ratio-filtered stage: any index >= 0 marks
-                            // "a second neighbour exists", d1 = the end of the interval that was tested
-                            o.i1 = a2 != LLONG_MAX ? static_cast<int>(a2 & 0xFFFFFFFFll) : ntr;
-                            o.d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lo1 : hi1));
-                        }
-                        continue;
-                    }
-                }
-            }
-            a1 = LLONG_MAX; a2 = LLONG_MAX;
-        }
-        // ---- stage B: all candidate chunks
-        int covered = 0;                                                // real train rows inside the candidate chunks
-        for (int k = 0; k < 4; ++k)
-            if (cand[k] != 0xFFFF) {
-                for (int h = 0; h < sub; ++h)
-                    warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[k] * sub + h, lane, a1, a2);
-                covered += max(0, min(a.chunk_rows, ntr - a.chunk_rows * cand[k]));
-            }
+    for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
+    const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
+    const int rV2 = __float_as_int(t.d1);
+    const int sub = a.chunk_rows / 32;                          // a candidate chunk = sub groups of 32 train rows
+    long long a1 = LLONG_MAX, a2 = LLONG_MAX;
+    // ---- stage A: the best chunk alone.  Every row outside it has a.b <= V2, i.e. d^2 >= |a|^2 + N- - 2 V2 =: lb2,
+    // and chunk 2 holds a real row with d^2 <= |a|^2 + N+ - 2 V2 =: ub2.  A planted match has e0 far below lb2: the
+    // nearest neighbour is certified and d1^2 lies in [min(e1', lb2), min(e1', ub2)] (e1' = second best inside the
+    // chunk) -- if the ratio test agrees at both ends the row is finished after 32-64 exact distances.
+    if (!a.all_rows && cand[0] != 0xFFFF && rV2 > 0) {
+        for (int h = 0; h < sub; ++h)
+            warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[0] * sub + h, lane, a1, a2);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
             a2 = min(max(a1, b1), min(a2, b2));
             a1 = min(a1, b1);
         }
-        // decide (all lanes hold the same a1, a2)
-        bool done = false;
-        float out_d1 = inf;
-        int out_i1 = -1;
-        const bool outside = covered < ntr;                             // train rows exist outside the candidate chunks
-        const long long lbo = outside ? static_cast<long long>(rna) + nbmin - 2ll * rv5 : LLONG_MAX;
         if (a1 != LLONG_MAX) {
             const long long e0 = a1 >> 32;
-            if (!outside) {                                             // the chunks cover the whole train image: exact
-                done = true;
-                if (a2 != LLONG_MAX) { out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll); out_d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
-            } else if (e0 < lbo && !a.all_rows) {
-                const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
+            const long long lb2 = static_cast<long long>(rna) + nbmin - 2ll * rV2;
+            const long long ub2 = static_cast<long long>(rna) + nbmax - 2ll * rV2;
+            if (e0 < lb2) {
                 const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
-                const long long lb1 = min(e1, lbo);                     // <= true d1^2 <= e1 (e1 = none: only the bound)
-                const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb1)))) * a.ratio;
-                if (e1 == LLONG_MAX) {
-                    // a second neighbour exists outside the chunks (outside == true): only 'pass at the lower end' decides
-                    if (pass_lo) { done = true; out_i1 = ntr; out_d1 = static_cast<float>(static_cast<int32_t>(lb1)); }
-                } else {
-                    const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)))) * a.ratio;
-                    if (pass_lo == pass_hi) {
-                        done = true;
-                        out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll);
-                        out_d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lb1 : e1));
+                const long long lo1 = min(e1, lb2), hi1 = min(e1, ub2);
+                const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
+                const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lo1)))) * a.ratio;
+                const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(hi1)))) * a.ratio;
+                if (pass_lo == pass_hi) {
+                    if (lane == 0) {
+                        Top2 o;
+                        o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(e0));
+                        // the second neighbour itself is not reported by the ratio-filtered stage: any index >= 0 marks
+                        // "a second neighbour exists", d1 = the end of the interval that was tested
+                        o.i1 = a2 != LLONG_MAX ? static_cast<int>(a2 & 0xFFFFFFFFll) : ntr;
+                        o.d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lo1 : hi1));
+                        a.top2[srow] = o;
                     }
+                    return;
                 }
             }
         }
-        // not certified, but perhaps certainly failing: the true d0^2 is >= min(e0, lbo) and the true d1^2 is <= e1 (the
-        // second best candidate is a real row), so  sqrtf(min(e0, lbo)) >= ratio * sqrtf(e1)  means the ratio test fails
-        // whatever lies outside the candidates -- the usual case of a row without a planted match
-        bool rejected = false;
-        if (!done && !a.all_rows && a1 != LLONG_MAX && a2 != LLONG_MAX && outside) {
-            const long long lb0 = max(0ll, min(a1 >> 32, lbo)), e1 = a2 >> 32;
-            const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb0)));
-            const float s1 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)));
-            if (!(static_cast<double>(s0) < static_cast<double>(s1) * a.ratio)) { done = true; rejected = true; }
+        a1 = LLONG_MAX; a2 = LLONG_MAX;
+    }
+    // ---- stage B: all candidate chunks
+    int covered = 0;                                                // real train rows inside the candidate chunks
+    for (int k = 0; k < 4; ++k)
+        if (cand[k] != 0xFFFF) {
+            for (int h = 0; h < sub; ++h)
+                warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[k] * sub + h, lane, a1, a2);
+            covered += max(0, min(a.chunk_rows, ntr - a.chunk_rows * cand[k]));
         }
-        if (!done) {
-            // exact brute force over the whole train image: queued for brute_force_rows_kernel (a whole CTA per row)
-            if (lane == 0) {
-                atomicAdd(a.stats + 1, 1ull);
-                const int64_t row_of_src = static_cast<int64_t>(blockIdx.x) * 256 + (threadIdx.x & ~31) + src;
-                a.bf_list[atomicAdd(a.bf_count, 1)] = static_cast<int32_t>(row_of_src);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+        a2 = min(max(a1, b1), min(a2, b2));
+        a1 = min(a1, b1);
+    }
+    // decide (all lanes hold the same a1, a2)
+    bool done = false;
+    float out_d1 = inf;
+    int out_i1 = -1;
+    const bool outside = covered < ntr;                             // train rows exist outside the candidate chunks
+    const long long lbo = outside ? static_cast<long long>(rna) + nbmin - 2ll * rv5 : LLONG_MAX;
+    if (a1 != LLONG_MAX) {
+        const long long e0 = a1 >> 32;
+        if (!outside) {                                             // the chunks cover the whole train image: exact
+            done = true;
+            if (a2 != LLONG_MAX) { out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll); out_d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
+        } else if (e0 < lbo && !a.all_rows) {
+            const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
+            const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
+            const long long lb1 = min(e1, lbo);                     // <= true d1^2 <= e1 (e1 = none: only the bound)
+            const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb1)))) * a.ratio;
+            if (e1 == LLONG_MAX) {
+                // a second neighbour exists outside the chunks (outside == true): only 'pass at the lower end' decides
+                if (pass_lo) { done = true; out_i1 = ntr; out_d1 = static_cast<float>(static_cast<int32_t>(lb1)); }
+            } else {
+                const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)))) * a.ratio;
+                if (pass_lo == pass_hi) {
+                    done = true;
+                    out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll);
+                    out_d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lb1 : e1));
+                }
             }
-            rejected = true;                                            // placeholder until that kernel writes the row
         }
-        if (lane == src && !rejected) {
+    }
+    // not certified, but perhaps certainly failing: the true d0^2 is >= min(e0, lbo) and the true d1^2 is <= e1 (the
+    // second best candidate is a real row), so  sqrtf(min(e0, lbo)) >= ratio * sqrtf(e1)  means the ratio test fails
+    // whatever lies outside the candidates -- the usual case of a row without a planted match
+    bool rejected = false;
+    if (!done && !a.all_rows && a1 != LLONG_MAX && a2 != LLONG_MAX && outside) {
+        const long long lb0 = max(0ll, min(a1 >> 32, lbo)), e1 = a2 >> 32;
+        const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb0)));
+        const float s1 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)));
+        if (!(static_cast<double>(s0) < static_cast<double>(s1) * a.ratio)) { done = true; rejected = true; }
+    }
+    if (!done) {
+        // exact brute force over the whole train image: queued for brute_force_rows_kernel (a whole CTA per row)
+        if (lane == 0) {
+            atomicAdd(a.stats + 1, 1ull);
+            a.bf_list[atomicAdd(a.bf_count, 1)] = static_cast<int32_t>(srow);
+        }
+        rejected = true;                                            // placeholder until that kernel writes the row
+    }
+    if (lane == 0) {
+        Top2 o;
+        o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
+        if (!rejected) {
             if (a1 != LLONG_MAX) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(a1 >> 32)); }
             o.i1 = out_i1; o.d1 = out_d1;
         }
+        a.top2[srow] = o;
     }
-    if (valid) a.top2[srow] = o;        // rows that cannot pass keep i0 = -1 (rejected)
 }
 
-// Rows queued by refine_dot_kernel: exact top-2 over the whole train image, one CTA per row (8 warps take every eighth
+// |b|^2 range of the train image of every pair of the batch (from the per-256-row-block ranges): one warp per pair
+__global__ void pair_norm_range_kernel(RefineArgs a) {
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= a.n_pairs) return;
+    const PairDesc pd = a.pairs[p];
+    const int b0 = pd.t_row0 / kRowAlign, nb = (pd.nt + kRowAlign - 1) / kRowAlign;
+    int mn = INT_MAX, mx = 0;
+    for (int b = lane; b < nb; b += 32) { mn = min(mn, a.blk_min[b0 + b]); mx = max(mx, a.blk_max[b0 + b]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if (lane == 0) { a.pair_nb[2 * p] = mn; a.pair_nb[2 * p + 1] = mx; }
+}
+
+// pass 1, one thread per staged row at memory speed: quick reject (1); rows that survive go to need_list (their candidate
+// record stays in top2 for pass 2), all others get their final 'no match' record
+__global__ void __launch_bounds__(256) refine_dot_select_kernel(RefineArgs a) {
+    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool need = false, valid = false;
+    if (srow < a.staged_rows) {
+        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
+        const PairDesc pd = a.pairs[p];
+        const int row = static_cast<int>(srow - a.out_prefix[p]);
+        if (row < pd.nq) {
+            valid = true;
+            if (pd.nt > 0) {
+                const Top2 t = a.top2[srow];
+                const int na = a.norm2[pd.q_row0 + row];
+                const int nbmin = a.pair_nb[2 * p], nbmax = a.pair_nb[2 * p + 1];
+                const int V1 = __float_as_int(t.d0), V2 = __float_as_int(t.d1);
+                if (a.all_rows || V2 <= 0) need = true;                       // fewer than two chunks with a real maximum
+                else {
+                    const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na + nbmin - 2 * V1)));
+                    const float hi1 = __fsqrt_rn(static_cast<float>(max(0, na + nbmax - 2 * V2)));
+                    need = static_cast<double>(lo0) < static_cast<double>(hi1) * a.ratio;
+                }
+            }
+        }
+    }
+    if (valid && !need) {
+        Top2 o;
+        o.i0 = -1; o.i1 = -1; o.d0 = __int_as_float(0x7f800000); o.d1 = o.d0;
+        a.top2[srow] = o;                                                     // cannot pass (or empty train image)
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (mask) {
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(a.need_count, __popc(mask));
+            atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) a.need_list[base + __popc(mask & ((1u << lane) - 1))] = static_cast<int32_t>(srow);
+    }
+}
+
+// pass 2: one warp per surviving row (persistent grid over need_list)
+__global__ void __launch_bounds__(256, 3) refine_dot_rows_kernel(RefineArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int n = *a.need_count;
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const int64_t srow = a.need_list[i];
+        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
+        const PairDesc pd = a.pairs[p];
+        const int qrow = pd.q_row0 + static_cast<int>(srow - a.out_prefix[p]);
+        refine_dot_row(a, srow, lane, a.top2[srow], a.aux[srow], a.norm2[qrow], qrow, pd.t_row0, pd.nt, a.pair_nb[2 * p],
+                       a.pair_nb[2 * p + 1]);
+    }
+}
+
+// Rows queued by refine_dot_row: exact top-2 over the whole train image, one CTA per row (8 warps take every eighth
 // group of 4 x 32 train rows), lexicographic (d^2, idx) keys, block reduction through shared memory.
 __global__ void __launch_bounds__(256) brute_force_rows_kernel(RefineArgs a) {
     __shared__ long long s_k[16];
@@ -725,7 +745,9 @@ __global__ void __launch_bounds__(256) brute_force_rows_kernel(RefineArgs a) {
 
 cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
-    refine_dot_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
+    pair_norm_range_kernel<<<static_cast<unsigned>((a.n_pairs + 7) / 8), 256, 0, s>>>(a);
+    refine_dot_select_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
+    refine_dot_rows_kernel<<<148 * 6, 256, 0, s>>>(a);       // persistent over the rows that survived the quick reject
     brute_force_rows_kernel<<<592, 256, 0, s>>>(a);          // persistent over the queue (usually a few dozen rows)
     return cudaGetLastError();
 }

@@ -115,6 +115,7 @@ struct sfm_ctx {
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
     DevBuf d_blk_pair;               // pair index of every 256-row staging block of the current batch
+    DevBuf d_need, d_pair_nb;        // norm-less path: rows that survived the quick reject; train-image norm range per pair
     DevBuf d_bf;                     // norm-less path: queue of staged rows that need the whole train image
     DevBuf d_hom;                    // homography stage: row0[2n] int64 | thresholds | inliers | best hypothesis
     DevBuf d_aux, d_aux_rev;         // 3xTF32 path: fifth-best chunk maximum per staged row
@@ -619,7 +620,11 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
 
     CU_TRY(c, c->d_top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
     if (need_rev) CU_TRY(c, c->d_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
-    if (eng == Engine::TCN) CU_TRY(c, c->d_bf.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+    if (eng == Engine::TCN) {
+        CU_TRY(c, c->d_bf.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+        CU_TRY(c, c->d_need.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+        CU_TRY(c, c->d_pair_nb.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
+    }
     if (eng == Engine::TF32 || eng == Engine::TCN) {
         CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
         CU_TRY(c, c->d_aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
@@ -688,13 +693,14 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             ra.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
             ra.chunk_rows = c->tcv_chunk; ra.blk_pair = c->d_blk_pair.as<int32_t>();
             ra.bf_list = c->d_bf.as<int32_t>(); ra.bf_count = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 48);
+            ra.need_list = c->d_need.as<int32_t>(); ra.need_count = ra.bf_count + 1; ra.pair_nb = c->d_pair_nb.as<int32_t>();
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
             ra.all_rows = 0; ra.ratio = o->ratio; ra.hamming = o->norm == SFM_NORM_HAMMING;
             if (eng == Engine::TCN) {
-                CU_TRY(c, cudaMemsetAsync(ra.bf_count, 0, 4, s));
+                CU_TRY(c, cudaMemsetAsync(ra.bf_count, 0, 8, s));          // brute-force queue + need list counters
                 CU_TRY(c, launch_refine_dot(ra, s));
-                c->stat_launches++;
+                c->stat_launches += 3;                                      // 4 kernels
             }
             else if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
             else CU_TRY(c, launch_refine_second(ra, s));
@@ -1001,7 +1007,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
                       &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
                       &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
-                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom, &c->d_bf, &c->d_blk_pair};
+                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom, &c->d_bf, &c->d_blk_pair, &c->d_need, &c->d_pair_nb};
     for (DevBuf* b : bufs) b->release();
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
