@@ -144,6 +144,7 @@ def gather_matches_device(matcher, local_idx, all_local_idx, n_pairs_total: int,
     width = max(2 * max_local + 4 * max_match, 1)
     off = cuda_view(po, n_local * 8, device, torch.int64)
     payload = torch.empty(width, dtype=torch.int32, device=device)
+    payload[:2 * max_local].zero_()                # ranks with fewer pairs than max_local: padded counts must be 0
     payload[:n_local] = torch.diff(off, append=tot)
     payload[max_local:max_local + n_local] = cuda_view(pd, n_local, device)
     payload[2 * max_local:2 * max_local + 4 * n_match] = cuda_view(pm, n_match * 16, device, torch.int32)

@@ -37,7 +37,7 @@ def main():
     offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).tolist()
     m = sfm.Matcher(local)
     m.upload_bank_device(bank_dev.data_ptr(), offs, sizes, 128, sfm.CV_8U)
-    pairs = sfm.select_pairs(len(sizes), 0, 0)
+    pairs = sfm.select_pairs(len(sizes), 0, 0)[:-1]      # 27 pairs: ranks get unequal shares (padding in the gather)
     mine = shard.assign_pairs(pairs, sizes, world)[rank]
     res = m.match_pairs(pairs[mine], sfm.NORM_L2, min_match_count=20)
     g = shard.gather_matches(mine, res.counts(), res.matches, res.dropped, len(pairs), dev, 0)
