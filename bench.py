@@ -369,7 +369,7 @@ def run_ours(a):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(a), "pairs": int(len(pairs)), "parallelism": f"pair-list x{world}",
                        "l2": "inputs larger than L2 (bank 200 MiB + 512 MiB top-2 staging per batch vs 126 MB L2); no flush",
-                       "engine": "tcgen05 kind::i8, value-only fused top-k epilogue (knn2_l2_u8_tcv_kernel, norm-less variant: 4 K-steps) + exact refine", "matches_per_step": total_matches,
+                       "engine": "tcgen05 kind::i8, value-only fused top-k epilogue (knn2_l2_u8_tcv_kernel; the library picks the norm-less 4-K-step variant with 64-row chunks when few rows need exact re-ranking, the 5-K-step variant with 32-row chunks otherwise) + exact refine", "matches_per_step": total_matches,
                        "matches_device_run": int(result.offsets[-1]),
                        "refine": {"rows_reranked_exactly": refine_stats["rows_reranked"], "rows_brute_forced": refine_stats["rows_brute_forced"],
                                   "query_rows": int(n_rows) * int(len(my_pairs))}},

@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
     Top2 o;
     o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
     unsigned mask = __ballot_sync(0xffffffffu, need);
+    if (lane == 0 && mask && a.stats) atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));   // feedback for the host
     while (mask) {
         const int src = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -675,18 +676,37 @@ __global__ void __launch_bounds__(256) refine_dot_select_kernel(RefineArgs a) {
     }
 }
 
-// pass 2: one warp per surviving row (persistent grid over need_list)
-__global__ void __launch_bounds__(256, 3) refine_dot_rows_kernel(RefineArgs a) {
+// pass 2: one warp per surviving row (persistent grid over need_list).  The row's metadata is a chain of five dependent
+// loads (list -> block table -> pair -> candidates / norm / bounds): it is fetched one row ahead of the row being refined.
+struct DotRowMeta { int64_t srow; Top2 t; int v5, na, qrow, tr0, nt, nbmin, nbmax; };
+__device__ __forceinline__ DotRowMeta load_dot_row(const RefineArgs& a, int i) {
+    DotRowMeta m;
+    m.srow = a.need_list[i];
+    const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, m.srow);
+    const PairDesc pd = a.pairs[p];
+    m.qrow = pd.q_row0 + static_cast<int>(m.srow - a.out_prefix[p]);
+    m.t = a.top2[m.srow];
+    m.v5 = a.aux[m.srow];
+    m.na = a.norm2[m.qrow];
+    m.tr0 = pd.t_row0; m.nt = pd.nt;
+    m.nbmin = a.pair_nb[2 * p]; m.nbmax = a.pair_nb[2 * p + 1];
+    return m;
+}
+
+__global__ void __launch_bounds__(256, 4) refine_dot_rows_kernel(RefineArgs a) {
     const int lane = threadIdx.x & 31;
     const int n = *a.need_count;
     const int warps = gridDim.x * (blockDim.x >> 5);
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
-        const int64_t srow = a.need_list[i];
-        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
-        const PairDesc pd = a.pairs[p];
-        const int qrow = pd.q_row0 + static_cast<int>(srow - a.out_prefix[p]);
-        refine_dot_row(a, srow, lane, a.top2[srow], a.aux[srow], a.norm2[qrow], qrow, pd.t_row0, pd.nt, a.pair_nb[2 * p],
-                       a.pair_nb[2 * p + 1]);
+    int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    DotRowMeta cur = load_dot_row(a, i);
+    while (true) {
+        const int ni = i + warps;
+        DotRowMeta nxt = cur;
+        if (ni < n) nxt = load_dot_row(a, ni);
+        refine_dot_row(a, cur.srow, lane, cur.t, cur.v5, cur.na, cur.qrow, cur.tr0, cur.nt, cur.nbmin, cur.nbmax);
+        if (ni >= n) break;
+        cur = nxt; i = ni;
     }
 }
 
@@ -747,7 +767,7 @@ cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
     pair_norm_range_kernel<<<static_cast<unsigned>((a.n_pairs + 7) / 8), 256, 0, s>>>(a);
     refine_dot_select_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
-    refine_dot_rows_kernel<<<148 * 6, 256, 0, s>>>(a);       // persistent over the rows that survived the quick reject
+    refine_dot_rows_kernel<<<148 * 8, 256, 0, s>>>(a);       // persistent over the rows that survived the quick reject
     brute_force_rows_kernel<<<592, 256, 0, s>>>(a);          // persistent over the queue (usually a few dozen rows)
     return cudaGetLastError();
 }

@@ -140,7 +140,16 @@ struct sfm_ctx {
                                      // measured a win at the 36 % spread of the 200-image SURVEY 8d bank, cv::SIFT has ~1 %
     int32_t prev_nb_min = 0, prev_nb_max = 1;   // |b|^2 range of the previous bank of this context (pipelined path)
     int tcv_normless = 1;            // norm-less variant of the value-only kernel: SFM_TCV_NORMLESS = 0 never | 1 auto | 2 always
-    int tcv_chunk = 64;              // train rows per candidate chunk of the value-only kernel (SFM_TCV_CHUNK = 32 | 64)
+    int tcv_chunk = 0;               // train rows per candidate chunk of the value-only kernels: 0 = adaptive, SFM_TCV_CHUNK = 32 | 64
+    int tcv_chunk_run = 64;
+    // adaptive choice between (norm-less kernel, 64-row chunks) and (kernel with the norm K-step, 32-row chunks): the share
+    // of query rows the previous run had to re-rank exactly.  Sparse matches (C3: 0.5 %) favour the first, dense matches
+    // (C4 grid neighbours: 7 %) the second, whose refine pass reads a quarter of the train rows per re-ranked row.
+    bool dense_matches = false;
+    bool tune_pending = false;
+    int64_t tune_rows = 0;
+    PinBuf h_tune;
+    cudaEvent_t tune_ev = nullptr;
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
@@ -436,12 +445,12 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk, s));
+                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk_run, s));
             break;
         case Engine::TCN:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
                                             reinterpret_cast<int32_t*>(aux), c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers,
-                                            c->tcv_chunk, s));
+                                            c->tcv_chunk_run, s));
             break;
         case Engine::TF32:
             CU_TRY(c, launch_knn2_l2_f32_tc3(b.tmaps_f, d_pairs, d_unit_prefix, n_pairs, n_units, out, aux, c->sm_count, s));
@@ -504,9 +513,18 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         c->tcv_layout_run = c->tcv_layout ? c->tcv_layout : (max_rows <= 32768 ? 12 : 14);
         if (max_rows <= (c->tcv_layout_run == 14 ? 65536 : 32768)) {
             eng = Engine::TCV;
+            // feedback of the previous run (copied to pinned memory behind its kernels; never waited for)
+            if (c->tune_pending && cudaEventQuery(c->tune_ev) == cudaSuccess) {
+                const double frac = c->tune_rows > 0 ? static_cast<double>(c->h_tune.as<unsigned long long>()[0]) / static_cast<double>(c->tune_rows) : 0.0;
+                if (frac > 0.02) c->dense_matches = true;
+                else if (frac < 0.01) c->dense_matches = false;
+                c->tune_pending = false;
+            }
+            c->tcv_chunk_run = c->tcv_chunk ? c->tcv_chunk : (c->dense_matches ? 32 : 64);
             // norms within 1/2 of each other (cv::SIFT: ~1 %, the SURVEY 8d recipe: 20-36 %): the norm-less variant, one K-step
             // less per tile; its bounds lose their grip when norms vary a lot, the exactness does not depend on the choice
-            if (c->tcv_normless == 2 || (c->tcv_normless == 1 && static_cast<int64_t>(b.nb_max - b.nb_min) * c->tcv_spread_div <= b.nb_max))
+            if (c->tcv_normless == 2 || (c->tcv_normless == 1 && !c->dense_matches &&
+                                         static_cast<int64_t>(b.nb_max - b.nb_min) * c->tcv_spread_div <= b.nb_max))
                 eng = Engine::TCN;
         }
     }
@@ -625,6 +643,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         CU_TRY(c, c->d_need.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
         CU_TRY(c, c->d_pair_nb.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
     }
+    if (eng == Engine::TCV) CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
     if (eng == Engine::TF32 || eng == Engine::TCN) {
         CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
         CU_TRY(c, c->d_aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
@@ -691,7 +710,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             RefineArgs ra{};
             ra.aux = c->d_aux.as<int32_t>(); ra.blk_min = b.d_blkmin.as<int32_t>(); ra.blk_max = b.d_blkmax.as<int32_t>();
             ra.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
-            ra.chunk_rows = c->tcv_chunk; ra.blk_pair = c->d_blk_pair.as<int32_t>();
+            ra.chunk_rows = c->tcv_chunk_run; ra.blk_pair = c->d_blk_pair.as<int32_t>();
             ra.bf_list = c->d_bf.as<int32_t>(); ra.bf_count = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 48);
             ra.need_list = c->d_need.as<int32_t>(); ra.need_count = ra.bf_count + 1; ra.pair_nb = c->d_pair_nb.as<int32_t>();
             ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
@@ -740,6 +759,12 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         std::swap(c->d_out, c->d_out2);
         std::swap(c->d_pair_offsets, c->d_pair_offsets2);
         std::swap(c->d_dropped, c->d_dropped2);
+    }
+    if ((eng == Engine::TCV || eng == Engine::TCN) && total_q > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->h_tune.p, c->d_scalars.as<uint8_t>() + 32, 16, cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaEventRecord(c->tune_ev, s));
+        c->tune_pending = true;
+        c->tune_rows = total_q;
     }
     pairs = pairs_in;
     c->run.valid = true;
@@ -980,6 +1005,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
         if ((e = cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&c->meta_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&c->valid_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaEventCreateWithFlags(&c->tune_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -987,6 +1013,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     c->encode = reinterpret_cast<EncodeTiledFn>(fn);
     if ((e = c->d_scalars.ensure(64)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = c->h_scalars.ensure(64)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = c->h_tune.ensure(64)) != cudaSuccess) return bail(cudaGetErrorString(e));
     size_t mb = 512;
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
@@ -1013,6 +1040,8 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->meta_ev) cudaEventDestroy(c->meta_ev);
     if (c->valid_ev) cudaEventDestroy(c->valid_ev);
+    if (c->tune_ev) cudaEventDestroy(c->tune_ev);
+    c->h_tune.release();
     for (sfm_result* r : c->result_pool) { r->offsets.release(); r->matches.release(); r->dropped.release(); delete r; }
     c->h_valid.release();
     for (cudaEvent_t ev : c->prof_ev) cudaEventDestroy(ev);

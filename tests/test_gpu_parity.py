@@ -284,6 +284,25 @@ def test_value_only_kernel_epilogue_layouts(sfm, layout, issuers, normless, chun
         m.close()
 
 
+def test_adaptive_variant_switch_keeps_results(sfm):
+    """The library switches between (norm-less kernel, 64-row chunks) and (norm K-step, 32-row chunks) from the share of
+    rows the previous run re-ranked; dense and sparse pair lists alternate here and every run equals the oracle."""
+    m = sfm.Matcher(0)
+    try:
+        bank = workloads.sift_like_bank(6, 1500)
+        dense = np.array([(0, 1), (1, 2), (2, 3), (3, 4), (4, 5)], np.int32)       # 30 % planted matches per pair
+        sparse = np.array([(0, 5), (5, 0), (1, 5), (0, 4)], np.int32)              # (almost) none
+        m.upload_bank(bank)
+        exp = {"dense": orc.match_pairs(bank, dense, NORM_L2), "sparse": orc.match_pairs(bank, sparse, NORM_L2)}
+        for name, pl in (("dense", dense), ("dense", dense), ("sparse", sparse), ("sparse", sparse), ("dense", dense),
+                         ("sparse", sparse), ("dense", dense)):
+            res = m.match_pairs(pl, NORM_L2)
+            for p in range(len(pl)):
+                assert orc.dmatch_equal(res[p], exp[name][p]), (name, pl[p].tolist())
+    finally:
+        m.close()
+
+
 def test_cross_check_vs_cv2_golden(sfm, matcher, insel_sift, synthetic_cv2):
     matcher.upload_bank([insel_sift[f"desc{i}"] for i in range(3)])
     res = matcher.match_pairs([[0, 1]], NORM_L2, k=1, cross_check=True)
