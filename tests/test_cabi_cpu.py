@@ -33,6 +33,13 @@ def test_struct_layouts(sfm):
     o = sfm.Opts()
     C.CDLL(sfm.LIB_PATH).sfm_opts_default(C.byref(o), C.c_int32(4))
     assert (o.norm, o.k, o.ratio, o.cross_check, o.distinct, o.min_match_count, o.engine) == (4, 2, 0.7, 0, 0, 0, 0)
+    # homography stage: cv::findHomography's defaults (maxIters 2000, confidence 0.995), refinement on
+    assert C.sizeof(sfm.HomographyOpts) == 24
+    h = sfm.HomographyOpts()
+    lib = C.CDLL(sfm.LIB_PATH)
+    lib.sfm_homography_opts_default.restype = None
+    lib.sfm_homography_opts_default(C.byref(h))
+    assert (h.max_iters, h.refine, h.confidence, h.seed) == (2000, 1, 0.995, 0)
 
 
 @pytest.mark.parametrize("n,seq,grid", [(0, 0, 0), (1, 0, 0), (7, 0, 0), (200, 0, 0), (3, 2, 0), (3, 3, 0), (50, 5, 0),
