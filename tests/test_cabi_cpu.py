@@ -96,3 +96,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle: the product must not depend on it"
+
+
+def test_host_match_index_equals_linear_scans():
+    """SURVEY §8f rank 4: hash indices over the ShotMatches (host/match_index.h) answer Scene::addShotMatches,
+    find3d2dMatches and mergePointcloudElement3d2d's lookups exactly like the reference's linear scans (restated in
+    host/test_match_index.cpp; random scenes with duplicated points, both orientations, -0 and NaN coordinates)."""
+    import subprocess
+    pkg = os.path.join(ROOT, "sfm-mvs-pipeline_b200")
+    subprocess.check_call(["make", "-s", "-C", pkg, "test_match_index"])
+    for seed in (1, 2, 3):
+        out = subprocess.run([os.path.join(pkg, "test_match_index"), str(seed)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and out.stdout.startswith("OK "), out.stdout + out.stderr
+        assert int(out.stdout.split()[1]) > 10000
