@@ -174,7 +174,15 @@ __global__ void __launch_bounds__(kHomThreads) homography_ransac_kernel(Homograp
     const double thr = a.n_thresholds > 1 ? a.thresholds[p] : a.thresholds[0];
     const double thr2 = thr * thr;
 
-    // ---- stage 1: consensus size of every hypothesis (a warp reads the same point: shared-memory broadcast)
+    // ---- stages 1 + 2 in rounds of 256 hypotheses: consensus sizes (a warp reads the same point: shared-memory broadcast),
+    // then one thread continues the replay of RANSACPointSetRegistrator::run over the new sizes in hypothesis order -- a better
+    // model shrinks the budget through RANSACUpdateNumIters(confidence, outlier ratio, 4, niters), rejected minimal sets do
+    // not count as iterations.  The loop ends as soon as the replay has consumed its budget: a pair with 99 % inliers is done
+    // after the first round (OpenCV: after ~3 iterations) instead of after all max_iters hypotheses.
+    __shared__ double s_niters;
+    __shared__ int s_iter, s_stop;
+    if (threadIdx.x == 0) { s_best[0] = 0; s_best[1] = -1; s_niters = static_cast<double>(a.max_iters); s_iter = 0; s_stop = 0; }
+    __syncthreads();
     for (int h0 = 0; h0 < a.max_iters; h0 += kHomThreads) {
         const int h = h0 + threadIdx.x;
         double H[9];
@@ -187,37 +195,39 @@ __global__ void __launch_bounds__(kHomThreads) homography_ransac_kernel(Homograp
             }
         }
         if (h < a.max_iters) s_cnt[h] = ok ? count : -1;           // -1: minimal set rejected (redrawn by OpenCV)
-    }
-    __syncthreads();
-    // ---- stage 2: RANSACPointSetRegistrator::run replayed over the hypotheses in order
-    if (threadIdx.x == 0) {
-        int best = 0, best_h = -1;
-        double niters = static_cast<double>(a.max_iters);
-        int iter = 0;
-        for (int h = 0; h < a.max_iters && iter < niters; ++h) {
-            const int cnt = s_cnt[h];
-            if (cnt < 0) continue;
-            if (cnt > max(best, 3)) {                               // goodCount > max(maxGoodCount, modelPoints - 1)
-                best = cnt; best_h = h;
-                // RANSACUpdateNumIters(confidence, (count - goodCount) / count, 4, niters)
-                const double ep = static_cast<double>(M - cnt) / static_cast<double>(M);
-                const double num = fmax(1.0 - a.confidence, 2.2250738585072014e-308);
-                const double q = 1.0 - ep;
-                const double denom = 1.0 - q * q * q * q;
-                if (denom < 2.2250738585072014e-308) niters = 0.0;
-                else {
-                    const double ln = log(num), ld = log(denom);
-                    niters = (ld >= 0.0 || -ln >= niters * (-ld)) ? niters : rint(ln / ld);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int best = s_best[0], best_h = s_best[1], iter = s_iter;
+            double niters = s_niters;
+            const int h_end = min(a.max_iters, h0 + kHomThreads);
+            int hh = h0;
+            for (; hh < h_end && iter < niters; ++hh) {
+                const int cnt = s_cnt[hh];
+                if (cnt < 0) continue;
+                if (cnt > max(best, 3)) {                           // goodCount > max(maxGoodCount, modelPoints - 1)
+                    best = cnt; best_h = hh;
+                    const double ep = static_cast<double>(M - cnt) / static_cast<double>(M);
+                    const double num = fmax(1.0 - a.confidence, 2.2250738585072014e-308);
+                    const double q = 1.0 - ep;
+                    const double denom = 1.0 - q * q * q * q;
+                    if (denom < 2.2250738585072014e-308) niters = 0.0;
+                    else {
+                        const double ln = log(num), ld = log(denom);
+                        niters = (ld >= 0.0 || -ln >= niters * (-ld)) ? niters : rint(ln / ld);
+                    }
                 }
+                ++iter;
             }
-            ++iter;
+            s_best[0] = best; s_best[1] = best_h; s_iter = iter; s_niters = niters;
+            s_stop = !(iter < niters) ? 1 : 0;                      // budget consumed: later hypotheses are never drawn
         }
-        s_best[0] = best; s_best[1] = best_h;
-        if (best_h >= 0) {
-            double H[9];
-            minimal_model(best_h, H);
-            for (int i = 0; i < 9; ++i) s_H[i] = H[i];
-        }
+        __syncthreads();
+        if (s_stop) break;
+    }
+    if (threadIdx.x == 0 && s_best[1] >= 0) {
+        double H[9];
+        minimal_model(s_best[1], H);
+        for (int i = 0; i < 9; ++i) s_H[i] = H[i];
     }
     __syncthreads();
     const int ransac_count = s_best[0], best_h = s_best[1];
