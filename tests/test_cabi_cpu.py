@@ -109,3 +109,24 @@ def test_host_match_index_equals_linear_scans():
         out = subprocess.run([os.path.join(pkg, "test_match_index"), str(seed)], capture_output=True, text=True, timeout=120)
         assert out.returncode == 0 and out.stdout.startswith("OK "), out.stdout + out.stderr
         assert int(out.stdout.split()[1]) > 10000
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU matcher through cv2) prints ONE JSON line with the contract's keys;
+    small shape so that the CPU suite stays fast."""
+    import json
+    import subprocess
+    import sys
+    from oracle import cv2_ref
+    if not cv2_ref.available():
+        pytest.skip("cv2 not importable")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--images", "6", "--rows", "512",
+                          "--steps", "2", "--warmup", "1", "--cpu-sample-pairs", "8"], capture_output=True, text=True, timeout=300)
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout + out.stderr
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
