@@ -121,3 +121,55 @@ def match_pair_normless(q: np.ndarray, t: np.ndarray, ratio: float = 0.7, chunk:
         if keep and e0 is not None:
             out.append((r, e0[1], 0, float(_f32sqrt(e0[0]))))
     return np.array(out, DMATCH_DTYPE) if out else np.zeros(0, DMATCH_DTYPE)
+
+
+def match_pair_value(q: np.ndarray, t: np.ndarray, ratio: float = 0.7, chunk: int = 64, stats: dict | None = None):
+    """Same for the variant WITH the norm K-step (knn2_l2_u8_tcv_kernel<kNorm = true> + refine_value_kernel): chunks are
+    ranked by D = a.b - (|b|^2 >> 1) (|a-b|^2 = |a|^2 - 2 D + (|b|^2 & 1)); the kernel reports the two best chunks, a third
+    if its maximum ties the second, and 'ambiguous' if a fourth ties too (-> brute force)."""
+    nq, nt = q.shape[0], t.shape[0]
+    out = []
+    if nq == 0 or nt == 0:
+        return np.zeros(0, DMATCH_DTYPE)
+    q64, t64 = q.astype(np.int64), t.astype(np.int64)
+    na_all, nb = (q64 * q64).sum(1), (t64 * t64).sum(1)
+    ab_all = q64 @ t64.T
+    pad = (-nt) % 256
+    n_chunks = (nt + pad) // chunk
+    st = stats if stats is not None else {}
+    for k in ("rejected", "chunks", "brute"):
+        st.setdefault(k, 0)
+    NEG = -(1 << 40)                                      # padded rows: below every valid D
+    for r in range(nq):
+        na = int(na_all[r])
+        D = np.concatenate([ab_all[r] - (nb >> 1), np.full(pad, NEG, np.int64)])
+        cmax = D.reshape(n_chunks, chunk).max(1)
+        order = [c for c in sorted(range(n_chunks), key=lambda c: (-int(cmax[c]), c)) if cmax[c] > NEG]
+        d2 = na + nb - 2 * ab_all[r]
+
+        def top2_in(rows):
+            keys = sorted((int(d2[j]), int(j)) for j in rows if j < nt)
+            return (keys[0] if keys else None), (keys[1] if len(keys) > 1 else None)
+
+        if not order:
+            continue
+        c1 = order[0]
+        c2 = order[1] if len(order) > 1 else None
+        c3 = order[2] if len(order) > 2 and cmax[order[2]] == cmax[order[1]] else None
+        ambiguous = c3 is not None and len(order) > 3 and cmax[order[3]] == cmax[order[1]]
+        if c2 is not None and not ambiguous:
+            lo0 = max(0, na - 2 * int(cmax[c1]))
+            hi1 = na - 2 * int(cmax[c2]) + 1
+            if not _ratio_pass(lo0, hi1, ratio):
+                st["rejected"] += 1
+                continue
+        if ambiguous:
+            st["brute"] += 1
+            e0, e1 = top2_in(range(nt))
+        else:
+            st["chunks"] += 1
+            rows = [j for c in (c1, c2, c3) if c is not None for j in range(c * chunk, c * chunk + chunk)]
+            e0, e1 = top2_in(rows)
+        if e0 is not None and (e1 is None or _ratio_pass(e0[0], e1[0], ratio)):
+            out.append((r, e0[1], 0, float(_f32sqrt(e0[0]))))
+    return np.array(out, DMATCH_DTYPE) if out else np.zeros(0, DMATCH_DTYPE)

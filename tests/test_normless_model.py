@@ -11,9 +11,11 @@ from oracle.oracle_np import NORM_L2
 
 
 def _check(q, t, ratio, chunk, stats):
-    got = nm.match_pair_normless(q, t, ratio, chunk, stats)
     exp = orc.match_pairs([q, t], [[0, 1]], NORM_L2, ratio=ratio)[0]
-    assert orc.dmatch_equal(got, exp), (q.shape, t.shape, ratio, chunk)
+    got = nm.match_pair_normless(q, t, ratio, chunk, stats)
+    assert orc.dmatch_equal(got, exp), ("norm-less", q.shape, t.shape, ratio, chunk)
+    got = nm.match_pair_value(q, t, ratio, chunk, stats.setdefault("value", {}))
+    assert orc.dmatch_equal(got, exp), ("norm K-step", q.shape, t.shape, ratio, chunk)
 
 
 @pytest.mark.parametrize("chunk", [32, 64])
@@ -35,13 +37,15 @@ def test_adversarial_and_wide_norm_spread(chunk):
     rng = np.random.default_rng(5)
     rnd = rng.integers(0, 256, size=(300, 128), dtype=np.uint8)
     sparse = (rng.random((257, 128)) < 0.03).astype(np.uint8) * rng.integers(1, 255, size=(257, 128), dtype=np.uint8)
-    sets = [adv["base"], adv["dup"], adv["zeros"], adv["sat"], adv["one"], adv["two"], adv["n129"], rnd, sparse]
+    tiled = np.concatenate([adv["base"][:40]] * 14)              # every chunk holds the same rows: chunk maxima tie
+    sets = [adv["base"], adv["dup"], adv["zeros"], adv["sat"], adv["one"], adv["two"], adv["n129"], rnd, sparse, tiled]
     for i, q in enumerate(sets):
         for j, t in enumerate(sets):
             if i != j:
                 for ratio in (0.7, 1.0):
                     _check(q[:120], t, ratio, chunk, stats)
     assert stats["brute"] > 0 and stats["stage_b"] > 0 and stats["proved_fail"] > 0
+    assert stats["value"]["brute"] > 0 and stats["value"]["chunks"] > 0              # tied chunk maxima -> 'ambiguous' path
 
 
 def test_random_small_images_fuzz():
