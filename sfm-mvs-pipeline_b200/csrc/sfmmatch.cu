@@ -5,6 +5,7 @@
 // point that computes distances launches the kernels of csrc/ or fails with SFM_ERR_CUDA.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges show up in nsys / `ncu --nvtx`, no cost without a tool attached
 
 #include <algorithm>
 #include <cstdio>
@@ -83,6 +84,14 @@ struct Bank {
     bool have_tmap = false;
     void release() { d_kp.release(); d_blkmin.release(); d_blkmax.release(); d_u8.release(); d_f32.release(); d_norm2.release(); d_ckey.release(); d_valid.release(); d_ext.release(); d_bits.release();
                      d_fhi.release(); d_flo.release(); d_fnorm.release(); d_fext.release(); }
+};
+
+// NVTX range for the phases of the stage (bank upload, enqueue, collect, knnMatch, homography)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 struct RunState {                    // what collect() needs from the last enqueue
@@ -264,6 +273,7 @@ int bank_layout(sfm_ctx* c, Bank& b, int n_images, const int32_t* n_rows, int co
 
 // After the raw descriptors are on the device (d_f32 for CV_32F, d_u8 for CV_8U): pack / norms / tensor maps.
 int bank_finish(sfm_ctx* c, Bank& b) {
+    NvtxRange nvtx_range("sfm:bank_finish (pack, norms, tensor maps)");
     cudaStream_t s = c->stream;
     b.u8_valued = false; b.have_f32 = false;
     if (b.padded_rows == 0) { b.u8_valued = b.depth == SFM_CV_8U; return make_tmaps(c, b); }
@@ -483,6 +493,7 @@ struct Schedule {
 };
 
 int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm_opts* o, const Schedule* sched = nullptr) {
+    NvtxRange nvtx_range("sfm:match_pairs_enqueue");
     Bank& b = c->bank;
     const int32_t* pairs = pairs_in;
     std::vector<int32_t> scheduled;
@@ -776,6 +787,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
 }
 
 int collect_impl(sfm_ctx* c, sfm_result** out) {
+    NvtxRange nvtx_range("sfm:match_pairs_collect");
     if (!c->run.valid) return fail(c, SFM_ERR_STATE, "collect without a preceding enqueue");
     cudaStream_t s = c->stream;
     const int64_t n = c->run.n_pairs;
@@ -1237,6 +1249,7 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
     sfm_homography_opts o;
     sfm_homography_opts_default(&o);
     if (opts) o = *opts;
+    NvtxRange nvtx_range("sfm:homography_inlier_ratios");
     if (!c->run.valid) return fail(c, SFM_ERR_STATE, "homography without a preceding match_pairs run");
     if (!c->bank.have_kp) return fail(c, SFM_ERR_STATE, "homography before sfm_keypoints_upload");
     const int64_t n = c->run.n_pairs;
@@ -1329,6 +1342,7 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
                   int cv_depth, int norm, int k, int engine, int32_t* nidx, float* dist) {
     if (!c) return SFM_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
+    NvtxRange nvtx_range("sfm:knn_match");
     if (k != 1 && k != 2) return fail(c, SFM_ERR_UNSUPPORTED, "knnMatch: k must be 1 or 2");
     if (nq < 0 || nt < 0 || cols <= 0) return fail(c, SFM_ERR_INVALID, "knnMatch: bad shape");
     if (nq > 0 && (!nidx || !dist)) return fail(c, SFM_ERR_INVALID, "knnMatch: null output");
