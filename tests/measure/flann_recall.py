@@ -2,7 +2,7 @@
 checks=100, index built inside every knnMatch call as the reference does) against the exact GPU result on a fixed
 random sample of pairs: time, top-1 recall, recall/precision of the ratio-test survivors."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as ge

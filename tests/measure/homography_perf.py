@@ -1,10 +1,10 @@
 """Homography stage on the C3 workload (200 x 8192 SIFT-like, 19 900 pairs): device time of
 sfm_homography_inlier_ratios on the device-resident match lists vs cv2.findHomography (the routine
 SfM::calculateHomography calls) on a sample of the same pairs, all host threads over pairs like the reference's
-`#pragma omp parallel for` (SfM.cpp:603).  usage: python tools/homography_perf.py [images] [rows] [cpu_sample_pairs]"""
+`#pragma omp parallel for` (SfM.cpp:603).  usage: python tests/measure/homography_perf.py [images] [rows] [cpu_sample_pairs]"""
 import json, os, sys, time
 from concurrent.futures import ThreadPoolExecutor
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

@@ -1,6 +1,6 @@
 """Small end-to-end case for compute-sanitizer (memcheck): every engine once, ragged sizes."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import __graft_entry__ as ge
