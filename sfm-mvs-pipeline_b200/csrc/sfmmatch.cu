@@ -813,16 +813,21 @@ int collect_impl(sfm_ctx* c, sfm_result** out) {
         else r = new sfm_result();
         r->owner = c;
         r->n_pairs = n;
-        CU_TRY(c, r->offsets.ensure(static_cast<size_t>(n + 1) * 8));
-        CU_TRY(c, r->dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n))));
-        CU_TRY(c, r->matches.ensure(std::max<size_t>(16, static_cast<size_t>(total) * sizeof(DMatch))));
-        if (n > 0) {
-            CU_TRY(c, cudaMemcpyAsync(r->offsets.p, c->d_pair_offsets.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, s));
-            CU_TRY(c, cudaMemcpyAsync(r->dropped.p, c->d_dropped.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, s));
-        }
-        if (total > 0)
-            CU_TRY(c, cudaMemcpyAsync(r->matches.p, c->d_out.p, static_cast<size_t>(total) * sizeof(DMatch), cudaMemcpyDeviceToHost, s));
-        CU_TRY(c, cudaStreamSynchronize(s));
+        auto fill = [&]() -> int {
+            CU_TRY(c, r->offsets.ensure(static_cast<size_t>(n + 1) * 8));
+            CU_TRY(c, r->dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n))));
+            CU_TRY(c, r->matches.ensure(std::max<size_t>(16, static_cast<size_t>(total) * sizeof(DMatch))));
+            if (n > 0) {
+                CU_TRY(c, cudaMemcpyAsync(r->offsets.p, c->d_pair_offsets.p, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, s));
+                CU_TRY(c, cudaMemcpyAsync(r->dropped.p, c->d_dropped.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, s));
+            }
+            if (total > 0)
+                CU_TRY(c, cudaMemcpyAsync(r->matches.p, c->d_out.p, static_cast<size_t>(total) * sizeof(DMatch), cudaMemcpyDeviceToHost, s));
+            CU_TRY(c, cudaStreamSynchronize(s));
+            return SFM_OK;
+        };
+        const int rc_fill = fill();
+        if (rc_fill != SFM_OK) { c->result_pool.push_back(r); return rc_fill; }      // keep the result object for the next run
         r->offsets.as<int64_t>()[n] = total;
         c->stat_d2h += 16 + n * 9 + total * static_cast<int64_t>(sizeof(DMatch));
         *out = r;

@@ -1,0 +1,79 @@
+"""The numpy restatement of cv::SIFT (oracle/sift_np.py) against golden vectors written by cv2 4.13.0
+(tests/golden/make_golden_sift.py): the reference's own photograph with the reference's detector settings
+(PhotogrammetrieCli.cpp:345-354: SIFT::create(0, 3, 0.09); SfM.cpp:584-588: detect() then compute()), and a synthetic image."""
+import os
+
+import numpy as np
+import pytest
+
+import workloads
+from oracle import sift_np as S
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _sift_compare as sc  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sift_extract.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def test_fast_atan2_known_answers():
+    # quadrant handling of cv::fastAtan2 (degrees, [0, 360)), accuracy of the 7th-order polynomial ~0.01 degrees
+    y = np.array([0, 1, 1, 0, -1, -1, 1e-3, 5], np.float32)
+    x = np.array([1, 1, 0, -1, -1, 1, -7, 5], np.float32)
+    exp = np.degrees(np.arctan2(y.astype(np.float64), x.astype(np.float64))) % 360
+    got = S.fast_atan2_deg(y, x)
+    assert np.abs(got - exp).max() < 0.02
+    assert S.fast_atan2_deg(np.float32(0), np.float32(0)) == 0
+
+
+def test_pyramid_shapes_and_sigmas():
+    # buildGaussianPyramid: sigma of level i relative to level i - 1; octave count of a 2x upsampled 405 x 720 image
+    sig = S.level_sigmas(3, 1.6)
+    assert len(sig) == 6 and abs(sig[1] - 1.2262735) < 1e-6 and abs(sig[3] - 1.9465878) < 1e-6
+    assert S.n_octaves_for((810, 1440)) == 9
+    base = S.create_initial_image(np.zeros((40, 64), np.uint8) + 7)
+    assert base.shape == (80, 128) and np.allclose(base, 7, atol=1e-4)
+    pyr = S.build_gaussian_pyramid(base, 3)
+    assert [p.shape for p in pyr[::6]] == [(80, 128), (40, 64), (20, 32)]
+
+
+def test_synthetic_image_is_reproducible(gold):
+    syn = workloads.synthetic_photo(0, 240, 320)
+    probe = [int(syn.astype(np.int64).sum()), int((syn.astype(np.int64) * np.arange(320)).sum())]
+    assert probe == gold["syn0_sha_probe"].tolist()
+
+
+def test_insel_photo_reference_settings(gold):
+    kp, desc = S.detect_and_compute(gold["insel1_gray"], contrast_threshold=0.09)
+    r = sc.assert_close(gold["insel1_kp_009"], gold["insel1_desc_009"], kp, desc, "insel 0.09")
+    assert r["n_a"] == 320 and r["matched"] >= 318
+    # removeDuplicatedSorted leaves the list ordered by x: same order as cv2 wherever both sides hold the keypoint
+    assert np.all(np.diff(kp["x"]) >= 0)
+
+
+@pytest.mark.parametrize("tag,ct", [("009", 0.09), ("004", 0.04)])
+def test_synthetic_photo(gold, tag, ct):
+    syn = workloads.synthetic_photo(0, 240, 320)
+    kp, desc = S.detect_and_compute(syn, contrast_threshold=ct)
+    sc.assert_close(gold[f"syn0_kp_{tag}"], gold[f"syn0_desc_{tag}"], kp, desc, f"synthetic {ct}")
+
+
+def test_edge_cases():
+    # flat image: no keypoints, empty descriptor matrix; tiny image: the border of 5 pixels leaves nothing to test
+    kp, desc = S.detect_and_compute(np.full((64, 64), 100, np.uint8))
+    assert len(kp) == 0 and desc.shape == (0, 128)
+    kp, desc = S.detect_and_compute(np.arange(36, dtype=np.uint8).reshape(6, 6) * 7)
+    assert len(kp) == 0
+    # one Gaussian blob: one keypoint at its centre, size ~ 2 * sigma of the blob * sqrt(2)
+    yy, xx = np.mgrid[0:96, 0:96]
+    blob = (200 * np.exp(-((xx - 40.3) ** 2 + (yy - 52.6) ** 2) / (2 * 6.0 ** 2))).astype(np.uint8)
+    kp, desc = S.detect_and_compute(blob)
+    assert len(kp) >= 1
+    k = kp[np.argmax(kp["response"])]
+    assert abs(k["x"] - 40.3) < 0.5 and abs(k["y"] - 52.6) < 0.5 and 10 < k["size"] < 24
+    assert desc.shape == (len(kp), 128) and desc.max() <= 255 and np.array_equal(desc, np.rint(desc))

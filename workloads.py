@@ -103,3 +103,31 @@ def adversarial_sift(seed: int = 3):
         "n129": base[:129],
         "empty": np.zeros((0, 128), np.uint8),
     }
+
+
+def synthetic_photo(seed: int = 0, height: int = 480, width: int = 640) -> np.ndarray:
+    """Synthetic grey image with structure at many scales (blobs, edges, fine texture): the input of the feature
+    extraction stage (SfM::extractFeatures) when no photographs are at hand.  uint8, deterministic in `seed`."""
+    rng = np.random.default_rng(77000 + seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    img = np.zeros((height, width), np.float32)
+    n_blobs = max(40, height * width // 160)
+    cx = rng.uniform(0, width, n_blobs).astype(np.float32)
+    cy = rng.uniform(0, height, n_blobs).astype(np.float32)
+    sg = np.exp(rng.uniform(np.log(1.2), np.log(12.0), n_blobs) - rng.exponential(0.0, n_blobs)).astype(np.float32)
+    am = rng.uniform(-1.0, 1.0, n_blobs).astype(np.float32)
+    for k in range(n_blobs):
+        r = int(4 * sg[k]) + 1
+        x0, x1 = max(0, int(cx[k]) - r), min(width, int(cx[k]) + r + 1)
+        y0, y1 = max(0, int(cy[k]) - r), min(height, int(cy[k]) + r + 1)
+        if x0 >= x1 or y0 >= y1:
+            continue
+        d2 = (xx[y0:y1, x0:x1] - cx[k]) ** 2 + (yy[y0:y1, x0:x1] - cy[k]) ** 2
+        img[y0:y1, x0:x1] += am[k] * np.exp(-d2 / (2 * sg[k] * sg[k]))
+    for _ in range(6):                                                    # a few straight edges
+        a = rng.uniform(0, np.pi)
+        off = rng.uniform(0.2, 0.8)
+        img += rng.uniform(-0.5, 0.5) * ((np.cos(a) * xx / width + np.sin(a) * yy / height) > off)
+    img += 0.05 * rng.standard_normal((height, width)).astype(np.float32)  # fine texture
+    img = 128.0 + 56.0 * (img - img.mean(dtype=np.float64)) / max(float(img.std(dtype=np.float64)), 1e-6)
+    return np.rint(np.clip(img, 0.0, 255.0)).astype(np.uint8)
