@@ -181,6 +181,44 @@ int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t
                                  const sfm_homography_opts *opts, double *ratios, int32_t *inliers,
                                  int32_t *ransac_inliers, int32_t *best_hypothesis);
 
+/* Feature extraction stage -----------------------------------------------------------------------
+ * Replaces the body of SfM::extractFeatures' loop (SfM.cpp:584-590),
+ *     featureDetector->detect(image, keypoints); descriptorExtractor->compute(image, keypoints, descriptors);
+ * for the detector PhotogrammetrieCli.cpp:345-354 configures, cv::SIFT::create(0, 3, 0.09): Gaussian / DoG pyramid,
+ * scale-space extrema, sub-pixel refinement, orientation histograms, removeDuplicatedSorted and the 4 x 4 x 8
+ * descriptors, all on the device (csrc/sift.cu).  Keypoints come back in cv::SIFT's order (sorted by x, y, ...), in
+ * input-image coordinates; descriptors are the u8 values cv::SIFT stores in its CV_32F rows.
+ *
+ * The extracted images accumulate in the context (image 0, 1, ... in call order) and stay device-resident;
+ * sfm_bank_from_features turns them into the descriptor bank AND the keypoint table of the matching / homography
+ * stages without a host round trip (it replaces sfm_bank_upload + sfm_keypoints_upload);
+ * sfm_features_download copies one image's keypoints / descriptors to the host (Shot::setFeatures needs them for the
+ * later pipeline stages).  Parity with cv::SIFT is a tolerance (float arithmetic with data-dependent decisions):
+ * tests/_sift_compare.py states it.  nfeatures (retainBest) is not implemented: the reference passes 0 (= keep all).
+ * max_keypoints bounds the per-image lists (0 = 262143, the matcher's per-image limit); more -> SFM_ERR_CAPACITY. */
+typedef struct sfm_keypoint {      /* cv::KeyPoint without class_id */
+    float   x, y, size, angle, response;
+    int32_t octave;
+} sfm_keypoint;
+typedef struct sfm_sift_opts {
+    int32_t n_octave_layers;       /* cv::SIFT::create arguments; defaults 3, 0.04, 10, 1.6 */
+    int32_t max_keypoints;
+    double  contrast_threshold;
+    double  edge_threshold;
+    double  sigma;
+} sfm_sift_opts;
+void sfm_sift_opts_default(sfm_sift_opts *o);
+int sfm_features_clear(sfm_ctx *ctx);
+int sfm_features_extract_sift(sfm_ctx *ctx, const uint8_t *gray, int rows, int cols, size_t step_bytes,
+                              const sfm_sift_opts *opts, int32_t *n_keypoints);
+int sfm_features_count(const sfm_ctx *ctx, int *n_images);
+int sfm_features_download(sfm_ctx *ctx, int image, int32_t *n_keypoints, sfm_keypoint *keypoints, uint8_t *descriptors);
+int sfm_bank_from_features(sfm_ctx *ctx);
+/* Measurement / test aids: [0] DoG extrema, [1] keypoints before removeDuplicatedSorted, [2] keypoints of the last
+ * extraction; one level of its Gaussian pyramid (out may be NULL to query the size). */
+int sfm_features_last_counts(const sfm_ctx *ctx, int32_t counts[3]);
+int sfm_features_pyramid_level(sfm_ctx *ctx, int octave, int level, float *out, int32_t *width, int32_t *height);
+
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* Non-integer CV_32F descriptors (3xTF32 tcgen05 candidate search + exact fp32 re-rank): how many query rows the

@@ -32,7 +32,12 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_result_offsets", "sfm_result_matches", "sfm_result_dropped", "sfm_result_free", "sfm_last_stats",
            "sfm_knn_match", "sfm_set_profiling", "sfm_last_profile", "sfm_bank_device_ptr", "sfm_match_pairs_device_view", "sfm_match_pairs_from_host",
            "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios",
-           "sfm_homography_opts_default"]
+           "sfm_homography_opts_default", "sfm_sift_opts_default", "sfm_features_clear", "sfm_features_extract_sift",
+           "sfm_features_count", "sfm_features_download", "sfm_bank_from_features", "sfm_features_last_counts",
+           "sfm_features_pyramid_level"]
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4")])          # sfm_keypoint = cv::KeyPoint without class_id
 
 
 class SfmError(RuntimeError):
@@ -43,6 +48,11 @@ class SfmError(RuntimeError):
 
 class HomographyOpts(C.Structure):
     _fields_ = [("max_iters", C.c_int32), ("refine", C.c_int32), ("confidence", C.c_double), ("seed", C.c_uint64)]
+
+
+class SiftOpts(C.Structure):
+    _fields_ = [("n_octave_layers", C.c_int32), ("max_keypoints", C.c_int32), ("contrast_threshold", C.c_double),
+                ("edge_threshold", C.c_double), ("sigma", C.c_double)]
 
 
 class Opts(C.Structure):
@@ -308,6 +318,63 @@ class Matcher:
                                                       ratios.ctypes.data_as(C.c_void_p), inl.ctypes.data_as(C.c_void_p),
                                                       rinl.ctypes.data_as(C.c_void_p), hyp.ctypes.data_as(C.c_void_p)))
         return {"ratio": ratios, "inliers": inl, "ransac_inliers": rinl, "hypothesis": hyp}
+
+    # ---- feature extraction stage (SfM::extractFeatures, SfM.cpp:577-597, cv::SIFT)
+    def features_clear(self):
+        self._check(_lib.sfm_features_clear(self._ctx))
+
+    def extract_sift(self, gray: np.ndarray, contrast_threshold: float = 0.04, n_octave_layers: int = 3,
+                     edge_threshold: float = 10.0, sigma: float = 1.6, max_keypoints: int = 0) -> int:
+        """detect() + compute() of cv::SIFT::create(0, n_octave_layers, contrast_threshold, edge_threshold, sigma) on one grey
+        uint8 image; the result is appended to the context's device-resident feature set.  Returns the keypoint count."""
+        gray = np.asarray(gray)
+        if gray.dtype != np.uint8 or gray.ndim != 2:
+            raise SfmError(ERR_INVALID, "extract_sift needs a 2-D uint8 (grey) image")
+        if gray.size and gray.strides[1] != 1:
+            gray = np.ascontiguousarray(gray)
+        o = SiftOpts()
+        _lib.sfm_sift_opts_default(C.byref(o))
+        o.n_octave_layers, o.max_keypoints = n_octave_layers, max_keypoints
+        o.contrast_threshold, o.edge_threshold, o.sigma = contrast_threshold, edge_threshold, sigma
+        n = C.c_int32(0)
+        step = gray.strides[0] if gray.shape[0] > 1 else gray.shape[1]
+        self._check(_lib.sfm_features_extract_sift(self._ctx, C.c_void_p(gray.ctypes.data if gray.size else None),
+                                                   C.c_int(gray.shape[0]), C.c_int(gray.shape[1]), C.c_size_t(step), C.byref(o),
+                                                   C.byref(n)))
+        return n.value
+
+    def features_count(self) -> int:
+        n = C.c_int(0)
+        self._check(_lib.sfm_features_count(self._ctx, C.byref(n)))
+        return n.value
+
+    def features_download(self, image: int):
+        """(keypoints [n] KEYPOINT_DTYPE, descriptors [n, 128] uint8) of one extracted image."""
+        n = C.c_int32(0)
+        self._check(_lib.sfm_features_download(self._ctx, C.c_int(image), C.byref(n), None, None))
+        kps = np.zeros(n.value, KEYPOINT_DTYPE)
+        desc = np.zeros((n.value, 128), np.uint8)
+        if n.value:
+            self._check(_lib.sfm_features_download(self._ctx, C.c_int(image), C.byref(n), kps.ctypes.data_as(C.c_void_p),
+                                                   desc.ctypes.data_as(C.c_void_p)))
+        return kps, desc
+
+    def bank_from_features(self):
+        """The extracted images become the descriptor bank and the keypoint table (device to device)."""
+        self._check(_lib.sfm_bank_from_features(self._ctx))
+
+    def features_last_counts(self):
+        c = (C.c_int32 * 3)()
+        self._check(_lib.sfm_features_last_counts(self._ctx, c))
+        return {"extrema": c[0], "keypoints_raw": c[1], "keypoints": c[2]}
+
+    def pyramid_level(self, octave: int, level: int) -> np.ndarray:
+        w, h = C.c_int32(0), C.c_int32(0)
+        self._check(_lib.sfm_features_pyramid_level(self._ctx, C.c_int(octave), C.c_int(level), None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.float32)
+        self._check(_lib.sfm_features_pyramid_level(self._ctx, C.c_int(octave), C.c_int(level), out.ctypes.data_as(C.c_void_p),
+                                                    C.byref(w), C.byref(h)))
+        return out
 
     # ---- operator level
     def knn_match(self, query: np.ndarray, train: np.ndarray, norm: int, k: int = 2, engine: int = ENGINE_AUTO):

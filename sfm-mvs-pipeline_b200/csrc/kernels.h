@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "common.cuh"
 
 namespace sfm {
@@ -156,6 +158,25 @@ struct HomographyArgs {
     int32_t* best_hyp;           // out: hypothesis number that produced it (may be null)
 };
 cudaError_t launch_homography_ransac(const HomographyArgs& a, cudaStream_t s);
+// ---- sift.cu: feature extraction, SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:345-354)
+struct SiftParams {
+    int n_layers;                // nOctaveLayers
+    double contrast_threshold, edge_threshold, sigma;
+};
+constexpr int kSiftMaxOctaves = 16;
+struct SiftWorkspace;            // device buffers of the stage: grey image, pyramid, candidate / keypoint lists, descriptors
+SiftWorkspace* sift_workspace_create();
+void sift_workspace_destroy(SiftWorkspace* w);
+// One grey image (host memory) -> keypoints (sorted, deduplicated, input-image coordinates) and 128-byte descriptors in the
+// workspace's device buffers.  Synchronises the stream once at the end (the keypoint count is needed on the host).
+// counts_out: [0] DoG extrema, [1] keypoints before removeDuplicatedSorted, [2] keypoints.
+cudaError_t sift_extract(SiftWorkspace* w, const uint8_t* gray, int rows, int cols, size_t step, const SiftParams& prm,
+                         int max_keypoints, cudaStream_t s, int* n_keypoints, int* n_launches, int counts_out[3], std::string* err);
+const void* sift_keypoints_device_raw(const SiftWorkspace* w);       // sift::Keypoint[n] = sfm_keypoint[n]
+const uint8_t* sift_descriptors_device(const SiftWorkspace* w);      // n x 128
+// test hook: geometry of the pyramid of the last extraction (float offsets of level 0 of every octave) and its base pointer
+int sift_pyramid_geometry(const SiftWorkspace* w, int* n_layers, int* widths, int* heights, int64_t* offsets, const float** base);
+cudaError_t launch_keypoint_xy(const void* keypoints, int n, float2* xy, cudaStream_t s);
 // schedule order -> input pair order (pipelined host path)
 cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
                            const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,

@@ -37,6 +37,22 @@ struct DevBuf {
         if (e == cudaSuccess) cap = bytes;
         return e;
     }
+    // growth that keeps the first `used` bytes (feature store: images are appended one by one)
+    cudaError_t ensure_keep(size_t bytes, size_t used, cudaStream_t s) {
+        if (bytes <= cap) return cudaSuccess;
+        const size_t want = std::max(bytes, cap + cap / 2);
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) return e;
+        if (p && used) {
+            e = cudaMemcpyAsync(q, p, used, cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { cudaFree(q); return e; }
+        }
+        if (p) cudaFree(p);
+        p = q; cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return static_cast<T*>(p); }
 };
@@ -159,6 +175,11 @@ struct sfm_ctx {
     int64_t tune_rows = 0;
     PinBuf h_tune;
     cudaEvent_t tune_ev = nullptr;
+    // feature extraction stage (sift.cu): images extracted so far, device-resident
+    SiftWorkspace* sift = nullptr;
+    DevBuf feat_kp, feat_desc;       // sfm_keypoint[total], u8[total][128]
+    std::vector<int64_t> feat_off{0};
+    int feat_counts[3] = {0, 0, 0};
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
@@ -1053,6 +1074,8 @@ void sfm_ctx_destroy(sfm_ctx* c) {
                       &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
                       &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom, &c->d_bf, &c->d_blk_pair, &c->d_need, &c->d_pair_nb};
     for (DevBuf* b : bufs) b->release();
+    c->feat_kp.release(); c->feat_desc.release();
+    sift_workspace_destroy(c->sift);
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->meta_ev) cudaEventDestroy(c->meta_ev);
@@ -1316,6 +1339,143 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
         if (ransac_inliers) ransac_inliers[p] = h_out[n + p];
         if (best_hypothesis) best_hypothesis[p] = h_out[2 * n + p];
     }
+    return SFM_OK;
+}
+
+// ---- SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:345-354) on the device
+static_assert(sizeof(sfm_keypoint) == 24, "sfm_keypoint layout (= sift::Keypoint of csrc/sift_core.cuh)");
+
+void sfm_sift_opts_default(sfm_sift_opts* o) {
+    if (!o) return;
+    o->n_octave_layers = 3;          // cv::SIFT::create defaults (features2d.hpp); the reference CLI passes (0, 3, 0.09)
+    o->max_keypoints = 0;            // 0: the matcher's per-image limit
+    o->contrast_threshold = 0.04;
+    o->edge_threshold = 10.0;
+    o->sigma = 1.6;
+}
+
+int sfm_features_clear(sfm_ctx* c) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->feat_off.assign(1, 0);
+    return SFM_OK;
+}
+
+int sfm_features_extract_sift(sfm_ctx* c, const uint8_t* gray, int rows, int cols, size_t step_bytes, const sfm_sift_opts* opts,
+                              int32_t* n_keypoints) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    NvtxRange nvtx_range("sfm:features_extract_sift");
+    sfm_sift_opts o;
+    sfm_sift_opts_default(&o);
+    if (opts) o = *opts;
+    if (!gray || rows <= 0 || cols <= 0) return fail(c, SFM_ERR_INVALID, "extract: empty image");
+    if (step_bytes == 0) step_bytes = static_cast<size_t>(cols);
+    if (step_bytes < static_cast<size_t>(cols)) return fail(c, SFM_ERR_INVALID, "extract: step smaller than a row");
+    if (rows > 32768 || cols > 32768) return fail(c, SFM_ERR_CAPACITY, "extract: image side above 32768 pixels");
+    if (o.n_octave_layers < 1 || o.n_octave_layers > 8) return fail(c, SFM_ERR_UNSUPPORTED, "extract: nOctaveLayers must be in 1..8");
+    if (!(o.sigma > 0.0) || !(o.contrast_threshold >= 0.0) || !(o.edge_threshold > 0.0))
+        return fail(c, SFM_ERR_INVALID, "extract: sigma / thresholds out of range");
+    int max_kp = o.max_keypoints > 0 ? o.max_keypoints : SFM_MAX_ROWS - 1;
+    if (max_kp >= SFM_MAX_ROWS) max_kp = SFM_MAX_ROWS - 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (!c->sift) c->sift = sift_workspace_create();
+    SiftParams prm;
+    prm.n_layers = o.n_octave_layers; prm.contrast_threshold = o.contrast_threshold; prm.edge_threshold = o.edge_threshold;
+    prm.sigma = o.sigma;
+    int n = 0, launches = 0;
+    std::string err;
+    cudaError_t e = sift_extract(c->sift, gray, rows, cols, step_bytes, prm, max_kp, c->stream, &n, &launches, c->feat_counts, &err);
+    if (e != cudaSuccess)
+        return fail(c, e == cudaErrorMemoryAllocation && !err.empty() && err.find("capacity") != std::string::npos ? SFM_ERR_CAPACITY : SFM_ERR_CUDA,
+                    err.empty() ? cudaGetErrorString(e) : err);
+    c->stat_launches += launches;
+    c->stat_h2d += static_cast<int64_t>(rows) * cols;
+    const int64_t used = c->feat_off.back();
+    CU_TRY(c, c->feat_kp.ensure_keep(static_cast<size_t>(used + n) * sizeof(sfm_keypoint) + 16, static_cast<size_t>(used) * sizeof(sfm_keypoint), c->stream));
+    CU_TRY(c, c->feat_desc.ensure_keep(static_cast<size_t>(used + n) * 128 + 16, static_cast<size_t>(used) * 128, c->stream));
+    if (n > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->feat_kp.as<sfm_keypoint>() + used, sift_keypoints_device_raw(c->sift), static_cast<size_t>(n) * sizeof(sfm_keypoint),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(c->feat_desc.as<uint8_t>() + used * 128, sift_descriptors_device(c->sift), static_cast<size_t>(n) * 128,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->feat_off.push_back(used + n);
+    if (n_keypoints) *n_keypoints = n;
+    return SFM_OK;
+}
+
+int sfm_features_count(const sfm_ctx* c, int* n_images) {
+    if (!c || !n_images) return SFM_ERR_INVALID;
+    *n_images = static_cast<int>(c->feat_off.size()) - 1;
+    return SFM_OK;
+}
+
+int sfm_features_last_counts(const sfm_ctx* c, int32_t counts[3]) {
+    if (!c || !counts) return SFM_ERR_INVALID;
+    for (int k = 0; k < 3; ++k) counts[k] = c->feat_counts[k];
+    return SFM_OK;
+}
+
+int sfm_features_download(sfm_ctx* c, int image, int32_t* n_keypoints, sfm_keypoint* kps, uint8_t* desc) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (image < 0 || image + 1 >= static_cast<int>(c->feat_off.size())) return fail(c, SFM_ERR_INVALID, "features: image index out of range");
+    const int64_t r0 = c->feat_off[image], n = c->feat_off[image + 1] - r0;
+    if (n_keypoints) *n_keypoints = static_cast<int32_t>(n);
+    if (n == 0 || (!kps && !desc)) return SFM_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (kps) CU_TRY(c, cudaMemcpyAsync(kps, c->feat_kp.as<sfm_keypoint>() + r0, static_cast<size_t>(n) * sizeof(sfm_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    if (desc) CU_TRY(c, cudaMemcpyAsync(desc, c->feat_desc.as<uint8_t>() + r0 * 128, static_cast<size_t>(n) * 128, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stat_d2h += n * ((kps ? 24 : 0) + (desc ? 128 : 0));
+    return SFM_OK;
+}
+
+int sfm_features_pyramid_level(sfm_ctx* c, int octave, int level, float* out, int32_t* width, int32_t* height) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->sift) return fail(c, SFM_ERR_STATE, "features: no extraction has run");
+    int widths[kSiftMaxOctaves], heights[kSiftMaxOctaves], n_layers = 0;
+    int64_t offs[kSiftMaxOctaves];
+    const float* base = nullptr;
+    const int n_oct = sift_pyramid_geometry(c->sift, &n_layers, widths, heights, offs, &base);
+    if (octave < 0 || octave >= n_oct || level < 0 || level >= n_layers + 3) return fail(c, SFM_ERR_INVALID, "features: no such pyramid level");
+    if (width) *width = widths[octave];
+    if (height) *height = heights[octave];
+    if (!out) return SFM_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t plane = static_cast<size_t>(widths[octave]) * heights[octave];
+    CU_TRY(c, cudaMemcpyAsync(out, base + offs[octave] + level * plane, plane * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return SFM_OK;
+}
+
+int sfm_bank_from_features(sfm_ctx* c) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    NvtxRange nvtx_range("sfm:bank_from_features");
+    const int n_images = static_cast<int>(c->feat_off.size()) - 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    std::vector<int32_t> n_rows(std::max(n_images, 1));
+    for (int i = 0; i < n_images; ++i) n_rows[i] = static_cast<int32_t>(c->feat_off[i + 1] - c->feat_off[i]);
+    Bank& b = c->bank;
+    int rc = bank_layout(c, b, n_images, n_rows.data(), 128, SFM_CV_8U);
+    if (rc != SFM_OK) return rc;
+    CU_TRY(c, b.d_u8.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * 128)));
+    CU_TRY(c, b.d_kp.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * 8)));
+    for (int i = 0; i < n_images; ++i) {
+        if (n_rows[i] == 0) continue;
+        CU_TRY(c, cudaMemcpyAsync(b.d_u8.as<uint8_t>() + static_cast<size_t>(b.row0[i]) * 128,
+                                  c->feat_desc.as<uint8_t>() + c->feat_off[i] * 128, static_cast<size_t>(n_rows[i]) * 128,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, launch_keypoint_xy(c->feat_kp.as<sfm_keypoint>() + c->feat_off[i], n_rows[i], b.d_kp.as<float2>() + b.row0[i], c->stream));
+        c->stat_launches++;
+    }
+    rc = bank_finish(c, b);
+    if (rc != SFM_OK) return rc;
+    b.have_kp = true;
     return SFM_OK;
 }
 

@@ -1,0 +1,428 @@
+// sift.cu — feature extraction on the device: SfM::extractFeatures (SfM.cpp:577-597) with the
+// detector of PhotogrammetrieCli.cpp:345-354, cv::SIFT.  One grey image in, sorted + deduplicated keypoints and their
+// 128-byte descriptors out, both device-resident so that the descriptor bank of the matching stage is filled without a
+// host round trip (sfm_bank_from_features).
+//
+// Kernels (all HBM / L2 bound, fp32, compiled with --fmad=false so that the pyramid is reproducible to the bit):
+//   upsample2x_kernel        u8 grey -> float, 2x INTER_LINEAR (createInitialImage)
+//   gauss_blur_kernel        separable Gaussian, BORDER_REFLECT_101, both passes fused through shared memory:
+//                            every pyramid level is read once and written once
+//   downsample_kernel        octave base = every second pixel of level [nOctaveLayers] of the previous octave
+//   extrema_kernel           26-neighbour extrema of the DoG (differences taken on the fly) -> candidate list
+//   refine_orient_kernel     adjustLocalExtrema + calcOrientationHist per candidate -> keypoint list
+//   rank_kernel / scatter_kernel / dedupe_kernel   KeyPointsFilter::removeDuplicatedSorted + firstOctave correction
+//   descriptor_kernel        calcSIFTDescriptor per keypoint -> u8 rows
+// The per-keypoint arithmetic is sift_core.cuh (shared with the host test harness); one thread walks one keypoint in
+// OpenCV's sample order, which keeps the float accumulation order of the histograms — and with it every borderline
+// decision — identical to the serial algorithm.
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "sift_core.cuh"
+
+namespace sfm {
+
+using namespace sift;
+static_assert(kSiftMaxOctaves == kMaxOctaves && sizeof(Keypoint) == 24, "sift_core.cuh / kernels.h disagree");
+
+namespace {
+
+struct BlurWeights {
+    int radius;
+    float w[2 * kMaxBlurRadius + 1];
+};
+
+__device__ __forceinline__ int reflect101(int p, int n) {      // cv::borderInterpolate(p, n, BORDER_REFLECT_101)
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint8_t* __restrict__ src, int w, int h, size_t step,
+                                                         float* __restrict__ dst) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= 2 * w || y >= 2 * h) return;
+    // sample position (d + 0.5) / 2 - 0.5: even d -> (k - 1, 0.75), odd d -> (k, 0.25); clamped taps have weight 0
+    int x0 = (x & 1) ? (x >> 1) : (x >> 1) - 1;
+    float fx = (x & 1) ? 0.25f : 0.75f;
+    if (x0 < 0) { x0 = 0; fx = 0.f; }
+    if (x0 >= w - 1) { x0 = w - 1; fx = 0.f; }
+    const int x1 = min(x0 + 1, w - 1);
+    int y0 = (y & 1) ? (y >> 1) : (y >> 1) - 1;
+    float fy = (y & 1) ? 0.25f : 0.75f;
+    if (y0 < 0) { y0 = 0; fy = 0.f; }
+    if (y0 >= h - 1) { y0 = h - 1; fy = 0.f; }
+    const int y1 = min(y0 + 1, h - 1);
+    const uint8_t* r0 = src + static_cast<size_t>(y0) * step;
+    const uint8_t* r1 = src + static_cast<size_t>(y1) * step;
+    const float a = static_cast<float>(r0[x0]) * (1.f - fx) + static_cast<float>(r0[x1]) * fx;
+    const float b = static_cast<float>(r1[x0]) * (1.f - fx) + static_cast<float>(r1[x1]) * fx;
+    dst[static_cast<size_t>(y) * (2 * w) + x] = a * (1.f - fy) + b * fy;
+}
+
+constexpr int kBlurTW = 64, kBlurTH = 32;
+
+__global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict__ src, float* __restrict__ dst, int w, int h,
+                                                         const BlurWeights k) {
+    extern __shared__ float sm[];
+    const int R = k.radius;
+    const int IW = kBlurTW + 2 * R, IH = kBlurTH + 2 * R;
+    float* in = sm;                  // IH x IW source tile with halo
+    float* mid = sm + IH * IW;       // IH x kBlurTW, filtered along x
+    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < IH * IW; idx += 256) {
+        const int iy = idx / IW, ix = idx - iy * IW;
+        const int gy = reflect101(y0 - R + iy, h), gx = reflect101(x0 - R + ix, w);
+        in[idx] = src[static_cast<size_t>(gy) * w + gx];
+    }
+    __syncthreads();
+    const int taps = 2 * R + 1;
+    for (int idx = tid; idx < IH * kBlurTW; idx += 256) {
+        const int iy = idx / kBlurTW, ix = idx - iy * kBlurTW;
+        const float* p = in + iy * IW + ix;
+        float acc = 0.f;
+        for (int t = 0; t < taps; ++t) acc += k.w[t] * p[t];
+        mid[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kBlurTH * kBlurTW; idx += 256) {
+        const int oy = idx / kBlurTW, ox = idx - oy * kBlurTW;
+        if (y0 + oy >= h || x0 + ox >= w) continue;
+        const float* p = mid + oy * kBlurTW + ox;
+        float acc = 0.f;
+        for (int t = 0; t < taps; ++t) acc += k.w[t] * p[t * kBlurTW];
+        dst[static_cast<size_t>(y0 + oy) * w + x0 + ox] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) downsample_kernel(const float* __restrict__ src, int sw, float* __restrict__ dst, int dw,
+                                                         int dh) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x < dw && y < dh) dst[static_cast<size_t>(y) * dw + x] = src[static_cast<size_t>(2 * y) * sw + 2 * x];
+}
+
+__global__ void __launch_bounds__(256) extrema_kernel(const PyramidView P, int o, float threshold, Candidate* __restrict__ cand,
+                                                      int* __restrict__ count, int capacity) {
+    const int c = blockIdx.x * 32 + threadIdx.x + kImgBorder, r = blockIdx.y * 8 + threadIdx.y + kImgBorder;
+    const int i = blockIdx.z + 1;
+    if (r >= P.h[o] - kImgBorder || c >= P.w[o] - kImgBorder) return;
+    if (!is_extremum(P, o, i, r, c, threshold)) return;
+    const int k = atomicAdd(count, 1);
+    if (k < capacity) cand[k] = Candidate{o, i, r, c};
+}
+
+__global__ void __launch_bounds__(128) refine_orient_kernel(const PyramidView P, const Candidate* __restrict__ cand,
+                                                            const int* __restrict__ n_cand, int cand_capacity, float contrast,
+                                                            float edge, float sigma, Keypoint* __restrict__ kps,
+                                                            int* __restrict__ n_kps, int kp_capacity) {
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    const int n = min(*n_cand, cand_capacity);
+    if (k >= n) return;
+    const Candidate cd = cand[k];
+    int layer = cd.layer, r = cd.r, c = cd.c;
+    Keypoint kp;
+    if (!adjust_local_extrema(P, cd.octave, layer, r, c, contrast, edge, sigma, kp)) return;
+    const float scl_octv = kp.size * 0.5f / (1 << cd.octave);
+    float angles[kOriBins];
+    const int m = orientation_peaks(P, cd.octave, layer, r, c, cv_round(4.5f * scl_octv), 1.5f * scl_octv, angles);
+    for (int a = 0; a < m; ++a) {
+        kp.angle = angles[a];
+        const int idx = atomicAdd(n_kps, 1);
+        if (idx < kp_capacity) kps[idx] = kp;
+    }
+}
+
+// position of every keypoint in KeyPoint12_LessThan order (ties between identical keypoints: list position)
+__global__ void __launch_bounds__(256) rank_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
+                                                   int* __restrict__ rank) {
+    __shared__ Keypoint tile[256];
+    const int n = min(*n_kps, capacity);
+    if (static_cast<int>(blockIdx.x) * 256 >= n) return;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    Keypoint me{};
+    if (i < n) me = kps[i];
+    int cnt = 0;
+    for (int base = 0; base < n; base += 256) {
+        if (base + static_cast<int>(threadIdx.x) < n) tile[threadIdx.x] = kps[base + threadIdx.x];
+        __syncthreads();
+        const int m = min(256, n - base);
+        if (i < n)
+            for (int j = 0; j < m; ++j) {
+                const Keypoint other = tile[j];
+                if (keypoint_less(other, me) || (!keypoint_less(me, other) && base + j < i)) ++cnt;
+            }
+        __syncthreads();
+    }
+    if (i < n) rank[i] = cnt;
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
+                                                      const int* __restrict__ rank, Keypoint* __restrict__ sorted) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < min(*n_kps, capacity)) sorted[rank[i]] = kps[i];
+}
+
+// keep the first of every run of equal (x, y, size, angle); coordinates back to the input image (firstOctave = -1)
+__global__ void __launch_bounds__(1024) dedupe_kernel(const Keypoint* __restrict__ sorted, const int* __restrict__ n_kps,
+                                                      int capacity, Keypoint* __restrict__ out, int* __restrict__ n_out) {
+    __shared__ int warp_sum[32];
+    __shared__ int running;
+    const int n = min(*n_kps, capacity);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        Keypoint kp{};
+        bool keep = false;
+        if (i < n) {
+            kp = sorted[i];
+            keep = i == 0 || !keypoint_duplicate(sorted[i - 1], kp);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_sum[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int wv = 0; wv < 32; ++wv) {
+            const int s = warp_sum[wv];
+            if (wv < warp) before += s;
+            total += s;
+        }
+        if (keep) {
+            const int pos = running + before + __popc(bal & ((1u << lane) - 1u));
+            kp.octave = (kp.octave & ~255) | ((kp.octave - 1) & 255);
+            kp.x *= 0.5f;
+            kp.y *= 0.5f;
+            kp.size *= 0.5f;
+            out[pos] = kp;
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = running;
+}
+
+constexpr int kDescThreads = 64;
+
+__global__ void __launch_bounds__(kDescThreads) descriptor_kernel(const PyramidView P, const Keypoint* __restrict__ kps,
+                                                                  const int* __restrict__ n_kps, int capacity,
+                                                                  uint8_t* __restrict__ desc) {
+    extern __shared__ float hist[];          // kDescHistLen x kDescThreads, thread t owns column t
+    const int i = blockIdx.x * kDescThreads + threadIdx.x;
+    if (i >= min(*n_kps, capacity)) return;
+    const Keypoint kp = kps[i];
+    int octave, layer;
+    float scale;
+    unpack_octave(kp.octave, octave, layer, scale);
+    const int o = octave + 1;                // firstOctave = -1
+    float angle = 360.f - kp.angle;
+    if (fabsf(angle - 360.f) < 1.1920929e-07f) angle = 0.f;
+    const float size = kp.size * scale;
+    sift_descriptor(P.level(o, layer), P.w[o], P.h[o], kp.x * scale, kp.y * scale, angle, size * 0.5f, hist + threadIdx.x,
+                    kDescThreads, desc + static_cast<size_t>(i) * kDescLen);
+}
+
+__global__ void __launch_bounds__(256) keypoint_xy_kernel(const Keypoint* __restrict__ kps, int n, float2* __restrict__ xy) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) xy[i] = make_float2(kps[i].x, kps[i].y);
+}
+
+BlurWeights make_weights(double sigma) {
+    // cv::GaussianBlur(src, dst, Size(), sigma) on CV_32F: ksize = cvRound(sigma * 4 * 2 + 1) | 1, exp kernel normalised in double
+    BlurWeights k{};
+    const int ksize = static_cast<int>(std::lrint(sigma * 8 + 1)) | 1;
+    k.radius = (ksize - 1) / 2;
+    if (k.radius > kMaxBlurRadius) { k.radius = -1; return k; }
+    std::vector<double> v(ksize);
+    double sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - k.radius;
+        v[i] = std::exp(-(x * x) / (2.0 * sigma * sigma));
+        sum += v[i];
+    }
+    for (int i = 0; i < ksize; ++i) k.w[i] = static_cast<float>(v[i] / sum);
+    return k;
+}
+
+template <class T>
+cudaError_t grow(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), need * sizeof(T));
+    if (e == cudaSuccess) cap = need;
+    return e;
+}
+
+}  // namespace
+
+struct SiftWorkspace {
+    uint8_t* d_gray = nullptr;   size_t gray_cap = 0;
+    float* d_up = nullptr;       size_t up_cap = 0;        // upsampled grey image before the first blur
+    float* d_pyr = nullptr;      size_t pyr_cap = 0;
+    Candidate* d_cand = nullptr; size_t cand_cap = 0;
+    Keypoint* d_kp_raw = nullptr; Keypoint* d_kp_sorted = nullptr; Keypoint* d_kp = nullptr; size_t kp_cap = 0, kp_cap2 = 0, kp_cap3 = 0;
+    int* d_rank = nullptr;       size_t rank_cap = 0;
+    uint8_t* d_desc = nullptr;   size_t desc_cap = 0;
+    int* d_counts = nullptr;     // [0] candidates, [1] raw keypoints, [2] final keypoints
+    int* h_counts = nullptr;     // pinned
+    PyramidView view{};
+    bool smem_set = false;
+};
+
+SiftWorkspace* sift_workspace_create() { return new SiftWorkspace(); }
+
+void sift_workspace_destroy(SiftWorkspace* w) {
+    if (!w) return;
+    cudaFree(w->d_gray); cudaFree(w->d_up); cudaFree(w->d_pyr); cudaFree(w->d_cand); cudaFree(w->d_kp_raw);
+    cudaFree(w->d_kp_sorted); cudaFree(w->d_kp); cudaFree(w->d_rank); cudaFree(w->d_desc); cudaFree(w->d_counts);
+    if (w->h_counts) cudaFreeHost(w->h_counts);
+    delete w;
+}
+
+const void* sift_keypoints_device_raw(const SiftWorkspace* w) { return w->d_kp; }
+const uint8_t* sift_descriptors_device(const SiftWorkspace* w) { return w->d_desc; }
+int sift_pyramid_geometry(const SiftWorkspace* w, int* n_layers, int* widths, int* heights, int64_t* offsets, const float** base) {
+    const PyramidView& P = w->view;
+    if (n_layers) *n_layers = P.n_layers;
+    for (int o = 0; o < P.n_octaves; ++o) {
+        if (widths) widths[o] = P.w[o];
+        if (heights) heights[o] = P.h[o];
+        if (offsets) offsets[o] = P.off[o];
+    }
+    if (base) *base = P.base;
+    return P.n_octaves;
+}
+
+#define SIFT_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) { if (err) *err = std::string(#expr) + ": " + cudaGetErrorString(_e); return _e; } \
+    } while (0)
+
+cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int cols, size_t step, const SiftParams& prm,
+                         int max_keypoints, cudaStream_t s, int* n_keypoints, int* n_launches, int counts_out[3], std::string* err) {
+    *n_keypoints = 0;
+    if (counts_out) counts_out[0] = counts_out[1] = counts_out[2] = 0;
+    int launches = 0;
+    // ---- geometry: doubled base image, octave count of SIFT_Impl::detectAndCompute (firstOctave = -1)
+    const int bw = 2 * cols, bh = 2 * rows;
+    const int n_oct = static_cast<int>(std::lrint(std::log(static_cast<double>(std::min(bw, bh))) / std::log(2.0) - 2)) + 1;
+    if (n_oct < 1) return cudaSuccess;                                     // image too small for a single octave
+    if (n_oct > kMaxOctaves) { if (err) *err = "image too large: more than 16 octaves"; return cudaErrorInvalidValue; }
+    const int L = prm.n_layers, levels = L + 3;
+    PyramidView& P = ws->view;
+    P.n_octaves = n_oct; P.n_layers = L;
+    int64_t total = 0;
+    for (int o = 0; o < n_oct; ++o) {
+        P.w[o] = o == 0 ? bw : P.w[o - 1] / 2;
+        P.h[o] = o == 0 ? bh : P.h[o - 1] / 2;
+        if (P.w[o] < 1 || P.h[o] < 1) { P.n_octaves = o; break; }
+        P.off[o] = total;
+        total += static_cast<int64_t>(levels) * P.w[o] * P.h[o];
+    }
+    const int n_octaves = P.n_octaves;
+    SIFT_TRY(grow(ws->d_gray, ws->gray_cap, static_cast<size_t>(rows) * cols));
+    SIFT_TRY(grow(ws->d_up, ws->up_cap, static_cast<size_t>(bw) * bh));
+    SIFT_TRY(grow(ws->d_pyr, ws->pyr_cap, static_cast<size_t>(total)));
+    P.base = ws->d_pyr;
+    const size_t cand_capacity = std::max<size_t>(1 << 16, static_cast<size_t>(max_keypoints) * 4);
+    SIFT_TRY(grow(ws->d_cand, ws->cand_cap, cand_capacity));
+    SIFT_TRY(grow(ws->d_kp_raw, ws->kp_cap, static_cast<size_t>(max_keypoints)));
+    SIFT_TRY(grow(ws->d_kp_sorted, ws->kp_cap2, static_cast<size_t>(max_keypoints)));
+    SIFT_TRY(grow(ws->d_kp, ws->kp_cap3, static_cast<size_t>(max_keypoints)));
+    SIFT_TRY(grow(ws->d_rank, ws->rank_cap, static_cast<size_t>(max_keypoints)));
+    SIFT_TRY(grow(ws->d_desc, ws->desc_cap, static_cast<size_t>(max_keypoints) * kDescLen));
+    if (!ws->d_counts) SIFT_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->d_counts), 16));
+    if (!ws->h_counts) SIFT_TRY(cudaMallocHost(reinterpret_cast<void**>(&ws->h_counts), 16));
+    if (!ws->smem_set) {
+        SIFT_TRY(cudaFuncSetAttribute(gauss_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SIFT_TRY(cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kDescHistLen * kDescThreads * static_cast<int>(sizeof(float))));
+        ws->smem_set = true;
+    }
+    SIFT_TRY(cudaMemsetAsync(ws->d_counts, 0, 16, s));
+    // ---- grey image to the device, doubled, first blur (createInitialImage)
+    SIFT_TRY(cudaMemcpy2DAsync(ws->d_gray, cols, gray, step, cols, rows, cudaMemcpyHostToDevice, s));
+    const dim3 blk(32, 8);
+    upsample2x_kernel<<<dim3((bw + 31) / 32, (bh + 7) / 8), blk, 0, s>>>(ws->d_gray, cols, rows, cols, ws->d_up);
+    ++launches;
+    auto blur = [&](const float* src, float* dst, int w, int h, double sigma) -> cudaError_t {
+        const BlurWeights k = make_weights(sigma);
+        if (k.radius < 0) { if (err) *err = "Gaussian kernel radius above 32 (sigma / nOctaveLayers out of the supported range)"; return cudaErrorInvalidValue; }
+        const size_t smem = (static_cast<size_t>(kBlurTH + 2 * k.radius) * (kBlurTW + 2 * k.radius) +
+                             static_cast<size_t>(kBlurTH + 2 * k.radius) * kBlurTW) * sizeof(float);
+        gauss_blur_kernel<<<dim3((w + kBlurTW - 1) / kBlurTW, (h + kBlurTH - 1) / kBlurTH), 256, smem, s>>>(src, dst, w, h, k);
+        ++launches;
+        return cudaGetLastError();
+    };
+    const float sigma_f = prm.sigma;
+    const float sig_diff = sqrtf(std::max(sigma_f * sigma_f - 0.5f * 0.5f * 4, 0.01f));
+    SIFT_TRY(blur(ws->d_up, ws->d_pyr + P.off[0], bw, bh, static_cast<double>(sig_diff)));
+    // ---- buildGaussianPyramid
+    std::vector<double> sig(levels);
+    sig[0] = prm.sigma;
+    const double kfac = std::pow(2.0, 1.0 / L);
+    for (int i = 1; i < levels; ++i) {
+        const double sig_prev = std::pow(kfac, static_cast<double>(i - 1)) * prm.sigma;
+        const double sig_total = sig_prev * kfac;
+        sig[i] = std::sqrt(sig_total * sig_total - sig_prev * sig_prev);
+    }
+    for (int o = 0; o < n_octaves; ++o) {
+        const int w = P.w[o], h = P.h[o];
+        const size_t plane = static_cast<size_t>(w) * h;
+        float* lv0 = ws->d_pyr + P.off[o];
+        if (o > 0) {
+            const float* src = ws->d_pyr + P.off[o - 1] + static_cast<size_t>(L) * P.w[o - 1] * P.h[o - 1];
+            downsample_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, s>>>(src, P.w[o - 1], lv0, w, h);
+            ++launches;
+        }
+        for (int i = 1; i < levels; ++i) SIFT_TRY(blur(lv0 + (i - 1) * plane, lv0 + i * plane, w, h, sig[i]));
+    }
+    // ---- findScaleSpaceExtrema
+    const float threshold = static_cast<float>(static_cast<int>(std::floor(0.5 * prm.contrast_threshold / L * 255)));
+    for (int o = 0; o < n_octaves; ++o) {
+        const int iw = P.w[o] - 2 * kImgBorder, ih = P.h[o] - 2 * kImgBorder;
+        if (iw <= 0 || ih <= 0) continue;
+        extrema_kernel<<<dim3((iw + 31) / 32, (ih + 7) / 8, L), blk, 0, s>>>(P, o, threshold, ws->d_cand, ws->d_counts,
+                                                                              static_cast<int>(cand_capacity));
+        ++launches;
+    }
+    refine_orient_kernel<<<static_cast<unsigned>((cand_capacity + 127) / 128), 128, 0, s>>>(
+        P, ws->d_cand, ws->d_counts, static_cast<int>(cand_capacity), static_cast<float>(prm.contrast_threshold),
+        static_cast<float>(prm.edge_threshold), static_cast<float>(prm.sigma), ws->d_kp_raw, ws->d_counts + 1, max_keypoints);
+    // ---- removeDuplicatedSorted + firstOctave correction
+    const unsigned kp_blocks = static_cast<unsigned>((max_keypoints + 255) / 256);
+    rank_kernel<<<kp_blocks, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank);
+    scatter_kernel<<<kp_blocks, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank, ws->d_kp_sorted);
+    dedupe_kernel<<<1, 1024, 0, s>>>(ws->d_kp_sorted, ws->d_counts + 1, max_keypoints, ws->d_kp, ws->d_counts + 2);
+    // ---- calcDescriptors
+    descriptor_kernel<<<static_cast<unsigned>((max_keypoints + kDescThreads - 1) / kDescThreads), kDescThreads,
+                        kDescHistLen * kDescThreads * sizeof(float), s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
+    launches += 5;
+    SIFT_TRY(cudaGetLastError());
+    SIFT_TRY(cudaMemcpyAsync(ws->h_counts, ws->d_counts, 12, cudaMemcpyDeviceToHost, s));
+    SIFT_TRY(cudaStreamSynchronize(s));
+    if (counts_out) { counts_out[0] = ws->h_counts[0]; counts_out[1] = ws->h_counts[1]; counts_out[2] = ws->h_counts[2]; }
+    if (ws->h_counts[0] > static_cast<int>(cand_capacity) || ws->h_counts[1] > max_keypoints) {
+        if (err) *err = "feature extraction: more candidates / keypoints than the capacity (" + std::to_string(ws->h_counts[0]) + " / " +
+                        std::to_string(ws->h_counts[1]) + "): raise max_keypoints";
+        return cudaErrorMemoryAllocation;
+    }
+    *n_keypoints = ws->h_counts[2];
+    if (n_launches) *n_launches = launches;
+    return cudaSuccess;
+}
+
+cudaError_t launch_keypoint_xy(const void* keypoints, int n, float2* xy, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    keypoint_xy_kernel<<<(n + 255) / 256, 256, 0, s>>>(static_cast<const Keypoint*>(keypoints), n, xy);
+    return cudaGetLastError();
+}
+
+}  // namespace sfm

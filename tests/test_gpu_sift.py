@@ -1,0 +1,134 @@
+"""Feature extraction on the device (csrc/sift.cu through the C ABI) against the numpy restatement of cv::SIFT and
+against cv2's golden vectors (SfM::extractFeatures, SfM.cpp:577-597).
+
+Parity bar: the Gaussian pyramid is float arithmetic in a fixed order -> compared to the restatement at 1e-4 absolute
+(values 0..255); keypoints / descriptors under the tolerance of tests/_sift_compare.py (borderline float decisions)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import workloads
+from oracle import oracle_np as orc
+from oracle import sift_np as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import _sift_compare as sc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m(sfm):
+    mt = sfm.Matcher(0)
+    yield mt
+    mt.close()
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(HERE, "golden", "sift_extract.npz"))
+
+
+def test_pyramid_equals_restatement(m):
+    img = workloads.synthetic_photo(0, 240, 320)
+    m.features_clear()
+    m.extract_sift(img)
+    base = S.create_initial_image(img)
+    n_oct = S.n_octaves_for(base.shape)
+    gpyr = S.build_gaussian_pyramid(base, n_oct)
+    for o in range(n_oct):
+        for i in (0, 3, 5):
+            got = m.pyramid_level(o, i)
+            exp = gpyr[o * 6 + i]
+            assert got.shape == exp.shape, (o, i)
+            assert np.abs(got - exp).max() < 1e-4, (o, i, float(np.abs(got - exp).max()))
+
+
+@pytest.mark.parametrize("shape,ct", [((240, 320), 0.04), ((240, 320), 0.09), ((101, 67), 0.04), ((64, 513), 0.04)])
+def test_keypoints_and_descriptors_equal_restatement(m, shape, ct):
+    img = workloads.synthetic_photo(3, *shape)
+    m.features_clear()
+    n = m.extract_sift(img, contrast_threshold=ct)
+    kp, desc = m.features_download(0)
+    assert n == len(kp)
+    kp_o, desc_o = S.detect_and_compute(img, contrast_threshold=ct)
+    r = sc.assert_close(kp_o, desc_o.astype(np.uint8), kp, desc, f"{shape} {ct}")
+    assert abs(r["n_a"] - r["n_b"]) <= max(2, r["n_a"] // 100)
+    assert np.all(np.diff(kp["x"]) >= 0)          # removeDuplicatedSorted order
+
+
+def test_reference_photo_against_cv2_golden(m, gold):
+    m.features_clear()
+    m.extract_sift(gold["insel1_gray"], contrast_threshold=0.09)          # PhotogrammetrieCli.cpp:345-354
+    kp, desc = m.features_download(0)
+    r = sc.assert_close(gold["insel1_kp_009"], gold["insel1_desc_009"], kp, desc, "insel vs cv2")
+    assert r["n_b"] in range(316, 325)
+    syn = workloads.synthetic_photo(0, 240, 320)
+    m.extract_sift(syn)
+    kp, desc = m.features_download(1)
+    sc.assert_close(gold["syn0_kp_004"], gold["syn0_desc_004"], kp, desc, "synthetic vs cv2")
+
+
+def test_edge_cases(m, sfm):
+    m.features_clear()
+    assert m.extract_sift(np.full((64, 64), 100, np.uint8)) == 0
+    assert m.extract_sift(np.arange(36, dtype=np.uint8).reshape(6, 6) * 7) == 0
+    assert m.extract_sift(np.zeros((1, 40), np.uint8)) == 0
+    assert m.features_count() == 3
+    kp, desc = m.features_download(1)
+    assert len(kp) == 0 and desc.shape == (0, 128)
+    # strided input (a column window of a wider image) equals the contiguous copy
+    wide = workloads.synthetic_photo(5, 120, 400)
+    m.features_clear()
+    m.extract_sift(wide[:, 40:300])
+    m.extract_sift(np.ascontiguousarray(wide[:, 40:300]))
+    a, b = m.features_download(0), m.features_download(1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and len(a[0]) > 20
+    with pytest.raises(sfm.SfmError) as e:
+        m.extract_sift(wide.astype(np.float32))
+    assert e.value.code == sfm.ERR_INVALID
+    with pytest.raises(sfm.SfmError) as e:
+        m.extract_sift(wide, n_octave_layers=9)
+    assert e.value.code == sfm.ERR_UNSUPPORTED
+    with pytest.raises(sfm.SfmError) as e:
+        m.extract_sift(wide, max_keypoints=10)
+    assert e.value.code == sfm.ERR_CAPACITY
+    with pytest.raises(sfm.SfmError):
+        m.features_download(7)
+
+
+def test_run_to_run_identical(m):
+    img = workloads.synthetic_photo(7, 200, 300)
+    m.features_clear()
+    m.extract_sift(img)
+    m.extract_sift(img)
+    a, b = m.features_download(0), m.features_download(1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_extracted_features_feed_the_matching_stage(m, sfm):
+    """extract -> bank_from_features -> match_pairs -> homography, nothing uploaded by the host in between."""
+    a = workloads.synthetic_photo(11, 240, 320)
+    b = np.roll(a, (3, 5), axis=(0, 1))                    # the same scene shifted by (5, 3) pixels
+    m.features_clear()
+    m.extract_sift(a)
+    m.extract_sift(b)
+    m.extract_sift(np.full((32, 32), 9, np.uint8))          # a shot without features
+    m.bank_from_features()
+    feats = [m.features_download(i) for i in range(3)]
+    pairs = sfm.select_pairs(3, 0, 0)
+    res = m.match_pairs(pairs, sfm.NORM_L2)
+    exp = orc.match_pairs([f[1] for f in feats], pairs, orc.NORM_L2)
+    for p in range(len(pairs)):
+        assert orc.dmatch_equal(res[p], exp[p]), pairs[p]
+    assert len(res[0]) > 50 and len(res[1]) == 0 and len(res[2]) == 0
+    # the matches of the shifted pair agree with the shift, and the homography stage sees the keypoints
+    ka, kb = feats[0][0], feats[1][0]
+    dx = kb["x"][res[0]["trainIdx"]] - ka["x"][res[0]["queryIdx"]]
+    dy = kb["y"][res[0]["trainIdx"]] - ka["y"][res[0]["queryIdx"]]
+    assert np.median(np.abs(dx - 5)) < 0.1 and np.median(np.abs(dy - 3)) < 0.1
+    h = m.homography_inlier_ratios(3.0, seed=1)
+    assert h["ratio"][0] > 0.8 and h["ratio"][1] == -1
