@@ -171,7 +171,8 @@ void sift_workspace_destroy(SiftWorkspace* w);
 // workspace's device buffers.  Synchronises the stream once at the end (the keypoint count is needed on the host).
 // counts_out: [0] DoG extrema, [1] keypoints before removeDuplicatedSorted, [2] keypoints.
 cudaError_t sift_extract(SiftWorkspace* w, const uint8_t* gray, int rows, int cols, size_t step, const SiftParams& prm,
-                         int max_keypoints, cudaStream_t s, int* n_keypoints, int* n_launches, int counts_out[3], std::string* err);
+                         int max_keypoints, int sm_count, cudaStream_t s, int* n_keypoints, int* n_launches, int counts_out[3],
+                         std::string* err);
 const void* sift_keypoints_device_raw(const SiftWorkspace* w);       // sift::Keypoint[n] = sfm_keypoint[n]
 const uint8_t* sift_descriptors_device(const SiftWorkspace* w);      // n x 128
 // test hook: geometry of the pyramid of the last extraction (float offsets of level 0 of every octave) and its base pointer

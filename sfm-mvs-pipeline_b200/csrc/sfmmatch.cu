@@ -1385,7 +1385,7 @@ int sfm_features_extract_sift(sfm_ctx* c, const uint8_t* gray, int rows, int col
     prm.sigma = o.sigma;
     int n = 0, launches = 0;
     std::string err;
-    cudaError_t e = sift_extract(c->sift, gray, rows, cols, step_bytes, prm, max_kp, c->stream, &n, &launches, c->feat_counts, &err);
+    cudaError_t e = sift_extract(c->sift, gray, rows, cols, step_bytes, prm, max_kp, c->sm_count, c->stream, &n, &launches, c->feat_counts, &err);
     if (e != cudaSuccess)
         return fail(c, e == cudaErrorMemoryAllocation && !err.empty() && err.find("capacity") != std::string::npos ? SFM_ERR_CAPACITY : SFM_ERR_CUDA,
                     err.empty() ? cudaGetErrorString(e) : err);

@@ -115,24 +115,65 @@ __global__ void __launch_bounds__(256) extrema_kernel(const PyramidView P, int o
     if (k < capacity) cand[k] = Candidate{o, i, r, c};
 }
 
-__global__ void __launch_bounds__(128) refine_orient_kernel(const PyramidView P, const Candidate* __restrict__ cand,
-                                                            const int* __restrict__ n_cand, int cand_capacity, float contrast,
-                                                            float edge, float sigma, Keypoint* __restrict__ kps,
-                                                            int* __restrict__ n_kps, int kp_capacity) {
-    const int k = blockIdx.x * 128 + threadIdx.x;
+// One warp per candidate (grid-stride).  Lane 0 runs adjustLocalExtrema; the orientation histogram is filled by all 32
+// lanes, 32 consecutive samples per step, and the contributions to one bin are added in sample order (lanes that hit
+// the same bin take turns by their rank among those lanes): the float sums equal the serial loop's bit for bit.
+constexpr int kRefineWarps = 4;
+__global__ void __launch_bounds__(kRefineWarps * 32) refine_orient_kernel(const PyramidView P, const Candidate* __restrict__ cand,
+                                                                         const int* __restrict__ n_cand, int cand_capacity,
+                                                                         float contrast, float edge, float sigma,
+                                                                         Keypoint* __restrict__ kps, int* __restrict__ n_kps,
+                                                                         int kp_capacity) {
+    __shared__ float hist_s[kRefineWarps][kOriBins];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* hist = hist_s[warp];
     const int n = min(*n_cand, cand_capacity);
-    if (k >= n) return;
-    const Candidate cd = cand[k];
-    int layer = cd.layer, r = cd.r, c = cd.c;
-    Keypoint kp;
-    if (!adjust_local_extrema(P, cd.octave, layer, r, c, contrast, edge, sigma, kp)) return;
-    const float scl_octv = kp.size * 0.5f / (1 << cd.octave);
-    float angles[kOriBins];
-    const int m = orientation_peaks(P, cd.octave, layer, r, c, cv_round(4.5f * scl_octv), 1.5f * scl_octv, angles);
-    for (int a = 0; a < m; ++a) {
-        kp.angle = angles[a];
-        const int idx = atomicAdd(n_kps, 1);
-        if (idx < kp_capacity) kps[idx] = kp;
+    const int stride = gridDim.x * kRefineWarps;
+    for (int k = blockIdx.x * kRefineWarps + warp; k < n; k += stride) {
+        const Candidate cd = cand[k];
+        int layer = cd.layer, r = cd.r, c = cd.c;
+        Keypoint kp{};
+        int ok = 0;
+        if (lane == 0) ok = adjust_local_extrema(P, cd.octave, layer, r, c, contrast, edge, sigma, kp) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) continue;
+        layer = __shfl_sync(0xffffffffu, layer, 0);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        const float size = __shfl_sync(0xffffffffu, kp.size, 0);
+        const float scl_octv = size * 0.5f / (1 << cd.octave);
+        const int radius = cv_round(4.5f * scl_octv);
+        const float osigma = 1.5f * scl_octv;
+        const float expf_scale = -1.f / (2.f * osigma * osigma);
+        const float* img = P.level(cd.octave, layer);
+        const int cols = P.w[cd.octave], rows = P.h[cd.octave];
+        for (int b = lane; b < kOriBins; b += 32) hist[b] = 0.f;
+        __syncwarp();
+        const int total = (2 * radius + 1) * (2 * radius + 1);
+        for (int g0 = 0; g0 < total; g0 += 32) {
+            const int g = g0 + lane;
+            int bin = 0;
+            float val = 0.f;
+            const bool valid = g < total && orientation_sample(img, cols, rows, r, c, radius, expf_scale, g, bin, val);
+            const unsigned peers = __match_any_sync(0xffffffffu, valid ? bin : 64 + lane);
+            const int rank = valid ? __popc(peers & ((1u << lane) - 1u)) : -1;
+            const int rounds = __reduce_max_sync(0xffffffffu, rank) + 1;
+            for (int t = 0; t < rounds; ++t) {
+                if (rank == t) hist[bin] += val;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            float temphist[kOriBins], angles[kOriBins];
+            for (int b = 0; b < kOriBins; ++b) temphist[b] = hist[b];
+            const int m = orientation_finish(temphist, angles);
+            for (int a = 0; a < m; ++a) {
+                kp.angle = angles[a];
+                const int idx = atomicAdd(n_kps, 1);
+                if (idx < kp_capacity) kps[idx] = kp;
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -141,29 +182,30 @@ __global__ void __launch_bounds__(256) rank_kernel(const Keypoint* __restrict__ 
                                                    int* __restrict__ rank) {
     __shared__ Keypoint tile[256];
     const int n = min(*n_kps, capacity);
-    if (static_cast<int>(blockIdx.x) * 256 >= n) return;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    Keypoint me{};
-    if (i < n) me = kps[i];
-    int cnt = 0;
-    for (int base = 0; base < n; base += 256) {
-        if (base + static_cast<int>(threadIdx.x) < n) tile[threadIdx.x] = kps[base + threadIdx.x];
-        __syncthreads();
-        const int m = min(256, n - base);
-        if (i < n)
-            for (int j = 0; j < m; ++j) {
-                const Keypoint other = tile[j];
-                if (keypoint_less(other, me) || (!keypoint_less(me, other) && base + j < i)) ++cnt;
-            }
-        __syncthreads();
+    for (int i0 = blockIdx.x * 256; i0 < n; i0 += gridDim.x * 256) {
+        const int i = i0 + threadIdx.x;
+        Keypoint me{};
+        if (i < n) me = kps[i];
+        int cnt = 0;
+        for (int base = 0; base < n; base += 256) {
+            if (base + static_cast<int>(threadIdx.x) < n) tile[threadIdx.x] = kps[base + threadIdx.x];
+            __syncthreads();
+            const int m = min(256, n - base);
+            if (i < n)
+                for (int j = 0; j < m; ++j) {
+                    const Keypoint other = tile[j];
+                    if (keypoint_less(other, me) || (!keypoint_less(me, other) && base + j < i)) ++cnt;
+                }
+            __syncthreads();
+        }
+        if (i < n) rank[i] = cnt;
     }
-    if (i < n) rank[i] = cnt;
 }
 
 __global__ void __launch_bounds__(256) scatter_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
                                                       const int* __restrict__ rank, Keypoint* __restrict__ sorted) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < min(*n_kps, capacity)) sorted[rank[i]] = kps[i];
+    const int n = min(*n_kps, capacity);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) sorted[rank[i]] = kps[i];
 }
 
 // keep the first of every run of equal (x, y, size, angle); coordinates back to the input image (firstOctave = -1)
@@ -207,24 +249,73 @@ __global__ void __launch_bounds__(1024) dedupe_kernel(const Keypoint* __restrict
     if (tid == 0) *n_out = running;
 }
 
-constexpr int kDescThreads = 64;
-
-__global__ void __launch_bounds__(kDescThreads) descriptor_kernel(const PyramidView P, const Keypoint* __restrict__ kps,
-                                                                  const int* __restrict__ n_kps, int capacity,
-                                                                  uint8_t* __restrict__ desc) {
-    extern __shared__ float hist[];          // kDescHistLen x kDescThreads, thread t owns column t
-    const int i = blockIdx.x * kDescThreads + threadIdx.x;
-    if (i >= min(*n_kps, capacity)) return;
-    const Keypoint kp = kps[i];
-    int octave, layer;
-    float scale;
-    unpack_octave(kp.octave, octave, layer, scale);
-    const int o = octave + 1;                // firstOctave = -1
-    float angle = 360.f - kp.angle;
-    if (fabsf(angle - 360.f) < 1.1920929e-07f) angle = 0.f;
-    const float size = kp.size * scale;
-    sift_descriptor(P.level(o, layer), P.w[o], P.h[o], kp.x * scale, kp.y * scale, angle, size * 0.5f, hist + threadIdx.x,
-                    kDescThreads, desc + static_cast<size_t>(i) * kDescLen);
+// One warp per keypoint (grid-stride).  The 32 lanes compute the votes of 32 consecutive samples of the window (row by
+// row, OpenCV's k order) and park them in shared memory; the histogram is then updated sample by sample, the eight
+// votes of a sample (eight distinct bins) by eight lanes at once: every bin receives its contributions in the serial
+// order.  The norms are summed by one lane in element order; clipping and quantisation are element-wise.
+constexpr int kDescWarps = 4;
+struct DescScratch {
+    float hist[kDescHistLen];
+    float votes[32][9];          // padded: lane-major writes and sample-major reads both conflict-free
+    int base[32];
+};
+__global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const PyramidView P, const Keypoint* __restrict__ kps,
+                                                                    const int* __restrict__ n_kps, int capacity,
+                                                                    uint8_t* __restrict__ desc) {
+    __shared__ DescScratch scratch[kDescWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DescScratch& S = scratch[warp];
+    const int n = min(*n_kps, capacity);
+    const int stride = gridDim.x * kDescWarps;
+    const int my_off = descriptor_vote_offset(lane & 7);
+    for (int i = blockIdx.x * kDescWarps + warp; i < n; i += stride) {
+        const Keypoint kp = kps[i];
+        int octave, layer;
+        float scale;
+        unpack_octave(kp.octave, octave, layer, scale);
+        const int o = octave + 1;                // firstOctave = -1
+        float angle = 360.f - kp.angle;
+        if (fabsf(angle - 360.f) < 1.1920929e-07f) angle = 0.f;
+        const float* img = P.level(o, layer);
+        const int cols = P.w[o], rows = P.h[o];
+        const DescFrame F = descriptor_frame(cols, rows, kp.x * scale, kp.y * scale, angle, kp.size * scale * 0.5f);
+        for (int b = lane; b < kDescHistLen; b += 32) S.hist[b] = 0.f;
+        __syncwarp();
+        const int side = 2 * F.radius + 1, total = side * side;
+        for (int g0 = 0; g0 < total; g0 += 32) {
+            const int g = g0 + lane;
+            int idx = 0;
+            float v[8];
+            const bool valid = g < total && descriptor_sample(img, cols, rows, F, g / side - F.radius, g % side - F.radius, idx, v);
+            unsigned mask = __ballot_sync(0xffffffffu, valid);
+            if (mask == 0) continue;
+            if (valid) {
+                S.base[lane] = idx;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) S.votes[lane][k] = v[k];
+            }
+            __syncwarp();
+            while (mask) {
+                const int l = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (lane < 8) S.hist[S.base[l] + my_off] += S.votes[l][lane];
+                __syncwarp();
+            }
+        }
+        float thr = 0.f;
+        if (lane == 0) thr = descriptor_fold_and_threshold(S.hist, 1);
+        thr = __shfl_sync(0xffffffffu, thr, 0);
+        float f = 0.f;
+        if (lane == 0) f = descriptor_clip_and_scale(S.hist, 1, thr);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        __syncwarp();
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            packed |= static_cast<uint32_t>(descriptor_quantise(S.hist[descriptor_element_index(lane * 4 + k)], f)) << (8 * k);
+        reinterpret_cast<uint32_t*>(desc + static_cast<size_t>(i) * kDescLen)[lane] = packed;
+        __syncwarp();
+    }
 }
 
 __global__ void __launch_bounds__(256) keypoint_xy_kernel(const Keypoint* __restrict__ kps, int n, float2* __restrict__ xy) {
@@ -306,7 +397,7 @@ int sift_pyramid_geometry(const SiftWorkspace* w, int* n_layers, int* widths, in
     } while (0)
 
 cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int cols, size_t step, const SiftParams& prm,
-                         int max_keypoints, cudaStream_t s, int* n_keypoints, int* n_launches, int counts_out[3], std::string* err) {
+                         int max_keypoints, int sm_count, cudaStream_t s, int* n_keypoints, int* n_launches, int counts_out[3], std::string* err) {
     *n_keypoints = 0;
     if (counts_out) counts_out[0] = counts_out[1] = counts_out[2] = 0;
     int launches = 0;
@@ -342,8 +433,6 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
     if (!ws->h_counts) SIFT_TRY(cudaMallocHost(reinterpret_cast<void**>(&ws->h_counts), 16));
     if (!ws->smem_set) {
         SIFT_TRY(cudaFuncSetAttribute(gauss_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        SIFT_TRY(cudaFuncSetAttribute(descriptor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kDescHistLen * kDescThreads * static_cast<int>(sizeof(float))));
         ws->smem_set = true;
     }
     SIFT_TRY(cudaMemsetAsync(ws->d_counts, 0, 16, s));
@@ -393,17 +482,16 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
                                                                               static_cast<int>(cand_capacity));
         ++launches;
     }
-    refine_orient_kernel<<<static_cast<unsigned>((cand_capacity + 127) / 128), 128, 0, s>>>(
+    const unsigned persistent = static_cast<unsigned>(sm_count > 0 ? sm_count : 148) * 8;
+    refine_orient_kernel<<<persistent, kRefineWarps * 32, 0, s>>>(
         P, ws->d_cand, ws->d_counts, static_cast<int>(cand_capacity), static_cast<float>(prm.contrast_threshold),
         static_cast<float>(prm.edge_threshold), static_cast<float>(prm.sigma), ws->d_kp_raw, ws->d_counts + 1, max_keypoints);
     // ---- removeDuplicatedSorted + firstOctave correction
-    const unsigned kp_blocks = static_cast<unsigned>((max_keypoints + 255) / 256);
-    rank_kernel<<<kp_blocks, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank);
-    scatter_kernel<<<kp_blocks, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank, ws->d_kp_sorted);
+    rank_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank);
+    scatter_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank, ws->d_kp_sorted);
     dedupe_kernel<<<1, 1024, 0, s>>>(ws->d_kp_sorted, ws->d_counts + 1, max_keypoints, ws->d_kp, ws->d_counts + 2);
     // ---- calcDescriptors
-    descriptor_kernel<<<static_cast<unsigned>((max_keypoints + kDescThreads - 1) / kDescThreads), kDescThreads,
-                        kDescHistLen * kDescThreads * sizeof(float), s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
+    descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
     launches += 5;
     SIFT_TRY(cudaGetLastError());
     SIFT_TRY(cudaMemcpyAsync(ws->h_counts, ws->d_counts, 12, cudaMemcpyDeviceToHost, s));

@@ -177,33 +177,31 @@ SIFT_HD bool adjust_local_extrema(const PyramidView& P, int octv, int& layer, in
     return true;
 }
 
-// calcOrientationHist + the peak search of findScaleSpaceExtremaT::process: angles[] receives the orientation of every
-// histogram peak >= 0.8 * maximum (degrees, OpenCV's 360 - bin convention); returns their number (<= kOriBins)
-SIFT_HD int orientation_peaks(const PyramidView& P, int octv, int layer, int pr, int pc, int radius, float sigma, float* angles) {
+// calcOrientationHist, one sample: g enumerates the (2 radius + 1)^2 window row by row (OpenCV's k order once the samples
+// outside the image are skipped); false = outside the image
+SIFT_HD bool orientation_sample(const float* img, int cols, int rows, int pr, int pc, int radius, float expf_scale, int g,
+                                int& bin, float& val) {
+    const int side = 2 * radius + 1;
+    const int i = g / side - radius, j = g % side - radius;
+    const int y = pr + i, x = pc + j;
+    if (y <= 0 || y >= rows - 1 || x <= 0 || x >= cols - 1) return false;
+    const float* p = img + static_cast<int64_t>(y) * cols + x;
+    const float dx = p[1] - p[-1];
+    const float dy = p[-cols] - p[cols];
+    const float w = expf(static_cast<float>(i * i + j * j) * expf_scale);
+    const float ori = fast_atan2_deg(dy, dx);
+    const float mag = sqrtf(dx * dx + dy * dy);
+    bin = cv_round((kOriBins / 360.f) * ori);
+    if (bin >= kOriBins) bin -= kOriBins;
+    if (bin < 0) bin += kOriBins;
+    val = w * mag;
+    return true;
+}
+
+// [1 4 6 4 1] / 16 smoothing of the raw histogram + the peak search of findScaleSpaceExtremaT::process: angles[] receives
+// the orientation of every peak >= 0.8 * maximum (degrees, OpenCV's 360 - bin convention); returns their number
+SIFT_HD int orientation_finish(const float* temphist, float* angles) {
     const int n = kOriBins;
-    const float* img = P.level(octv, layer);
-    const int cols = P.w[octv], rows = P.h[octv];
-    const float expf_scale = -1.f / (2.f * sigma * sigma);
-    float temphist[kOriBins];
-    for (int k = 0; k < n; ++k) temphist[k] = 0.f;
-    for (int i = -radius; i <= radius; ++i) {
-        const int y = pr + i;
-        if (y <= 0 || y >= rows - 1) continue;
-        for (int j = -radius; j <= radius; ++j) {
-            const int x = pc + j;
-            if (x <= 0 || x >= cols - 1) continue;
-            const float* p = img + static_cast<int64_t>(y) * cols + x;
-            const float dx = p[1] - p[-1];
-            const float dy = p[-cols] - p[cols];
-            const float w = expf(static_cast<float>(i * i + j * j) * expf_scale);
-            const float ori = fast_atan2_deg(dy, dx);
-            const float mag = sqrtf(dx * dx + dy * dy);
-            int bin = cv_round((n / 360.f) * ori);
-            if (bin >= n) bin -= n;
-            if (bin < 0) bin += n;
-            temphist[bin] += w * mag;
-        }
-    }
     float hist[kOriBins];
     float maxval = 0.f;
     for (int k = 0; k < n; ++k) {
@@ -225,6 +223,22 @@ SIFT_HD int orientation_peaks(const PyramidView& P, int octv, int layer, int pr,
         }
     }
     return count;
+}
+
+// the serial form (host harness; the kernel walks the same samples with one warp, see sift.cu)
+SIFT_HD int orientation_peaks(const PyramidView& P, int octv, int layer, int pr, int pc, int radius, float sigma, float* angles) {
+    const float* img = P.level(octv, layer);
+    const int cols = P.w[octv], rows = P.h[octv];
+    const float expf_scale = -1.f / (2.f * sigma * sigma);
+    float temphist[kOriBins];
+    for (int k = 0; k < kOriBins; ++k) temphist[k] = 0.f;
+    const int total = (2 * radius + 1) * (2 * radius + 1);
+    for (int g = 0; g < total; ++g) {
+        int bin;
+        float val;
+        if (orientation_sample(img, cols, rows, pr, pc, radius, expf_scale, g, bin, val)) temphist[bin] += val;
+    }
+    return orientation_finish(temphist, angles);
 }
 
 // KeyPoint12_LessThan of KeyPointsFilter::removeDuplicatedSorted (keypoint.cpp); class_id is -1 everywhere
@@ -249,62 +263,81 @@ SIFT_HD void unpack_octave(int32_t field, int& octave, int& layer, float& scale)
     scale = octave >= 0 ? 1.f / (1 << octave) : static_cast<float>(1 << -octave);
 }
 
-// calcSIFTDescriptor: 4 x 4 x 8 gradient histogram around (ptx, pty) of one pyramid level, rotated by `ori` degrees, window
-// scale `scl`; hist = kDescHistLen floats of scratch with element stride hstride; dst = 128 bytes (saturate_cast<uchar>)
-SIFT_HD void sift_descriptor(const float* img, int cols, int rows, float ptx, float pty, float ori, float scl, float* hist,
-                             int hstride, uint8_t* dst) {
+// calcSIFTDescriptor, split into the per-keypoint frame, the votes of one sample and the final normalisation
+struct DescFrame {
+    int px, py, radius;
+    float cos_t, sin_t, ori, exp_scale, bins_per_rad;
+};
+
+SIFT_HD DescFrame descriptor_frame(int cols, int rows, float ptx, float pty, float ori, float scl) {
     const int d = kDescWidth, n = kDescBins;
-    const int px = cv_round(ptx), py = cv_round(pty);
-    float cos_t = cosf(ori * static_cast<float>(3.14159265358979323846 / 180));
-    float sin_t = sinf(ori * static_cast<float>(3.14159265358979323846 / 180));
-    const float bins_per_rad = n / 360.f;
-    const float exp_scale = -1.f / (d * d * 0.5f);
+    DescFrame F;
+    F.px = cv_round(ptx);
+    F.py = cv_round(pty);
+    F.ori = ori;
+    F.cos_t = cosf(ori * static_cast<float>(3.14159265358979323846 / 180));
+    F.sin_t = sinf(ori * static_cast<float>(3.14159265358979323846 / 180));
+    F.bins_per_rad = n / 360.f;
+    F.exp_scale = -1.f / (d * d * 0.5f);
     const float hist_width = 3.f * scl;                                    // SIFT_DESCR_SCL_FCTR
     int radius = cv_round(hist_width * 1.4142135623730951f * (d + 1) * 0.5f);
     const int diag = static_cast<int>(sqrt(static_cast<double>(cols) * cols + static_cast<double>(rows) * rows));
-    radius = radius < diag ? radius : diag;
-    cos_t /= hist_width;
-    sin_t /= hist_width;
-    for (int k = 0; k < kDescHistLen; ++k) hist[k * hstride] = 0.f;
-    for (int i = -radius; i <= radius; ++i)
-        for (int j = -radius; j <= radius; ++j) {
-            const float c_rot = j * cos_t - i * sin_t;
-            const float r_rot = j * sin_t + i * cos_t;
-            float rbin = r_rot + d / 2 - 0.5f;
-            float cbin = c_rot + d / 2 - 0.5f;
-            const int r = py + i, c = px + j;
-            if (!(rbin > -1 && rbin < d && cbin > -1 && cbin < d && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) continue;
-            const float* p = img + static_cast<int64_t>(r) * cols + c;
-            const float dx = p[1] - p[-1];
-            const float dy = p[-cols] - p[cols];
-            const float w = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
-            const float angle = fast_atan2_deg(dy, dx);
-            const float mag = sqrtf(dx * dx + dy * dy) * w;
-            float obin = (angle - ori) * bins_per_rad;
-            const int r0 = static_cast<int>(floorf(rbin)), c0 = static_cast<int>(floorf(cbin));
-            int o0 = static_cast<int>(floorf(obin));
-            rbin -= r0; cbin -= c0; obin -= o0;
-            if (o0 < 0) o0 += n;
-            if (o0 >= n) o0 -= n;
-            const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
-            const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
-            const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
-            const float v_rco111 = v_rc11 * obin, v_rco110 = v_rc11 - v_rco111;
-            const float v_rco101 = v_rc10 * obin, v_rco100 = v_rc10 - v_rco101;
-            const float v_rco011 = v_rc01 * obin, v_rco010 = v_rc01 - v_rco011;
-            const float v_rco001 = v_rc00 * obin, v_rco000 = v_rc00 - v_rco001;
-            const int idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
-            hist[idx * hstride] += v_rco000;
-            hist[(idx + 1) * hstride] += v_rco001;
-            hist[(idx + (n + 2)) * hstride] += v_rco010;
-            hist[(idx + (n + 3)) * hstride] += v_rco011;
-            hist[(idx + (d + 2) * (n + 2)) * hstride] += v_rco100;
-            hist[(idx + (d + 2) * (n + 2) + 1) * hstride] += v_rco101;
-            hist[(idx + (d + 3) * (n + 2)) * hstride] += v_rco110;
-            hist[(idx + (d + 3) * (n + 2) + 1) * hstride] += v_rco111;
-        }
-    // circular orientation bins, then hysteresis threshold + scaling.  The 128 raw values stay in the scratch histogram
-    // (slots idx .. idx + 7 of every cell), read in OpenCV's order.
+    F.radius = radius < diag ? radius : diag;
+    F.cos_t /= hist_width;
+    F.sin_t /= hist_width;
+    return F;
+}
+
+// offsets of the eight trilinear votes of a sample from its base histogram index, in OpenCV's update order
+SIFT_HD int descriptor_vote_offset(int v) {
+    const int d = kDescWidth, n = kDescBins;
+    return ((v >> 2) & 1) * (d + 2) * (n + 2) + ((v >> 1) & 1) * (n + 2) + (v & 1);
+}
+
+// sample (i, j) of the window: false = outside the rotated 4 x 4 grid or the image; else base index + eight votes
+SIFT_HD bool descriptor_sample(const float* img, int cols, int rows, const DescFrame& F, int i, int j, int& idx, float v[8]) {
+    const int d = kDescWidth, n = kDescBins;
+    const float c_rot = j * F.cos_t - i * F.sin_t;
+    const float r_rot = j * F.sin_t + i * F.cos_t;
+    float rbin = r_rot + d / 2 - 0.5f;
+    float cbin = c_rot + d / 2 - 0.5f;
+    const int r = F.py + i, c = F.px + j;
+    if (!(rbin > -1 && rbin < d && cbin > -1 && cbin < d && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) return false;
+    const float* p = img + static_cast<int64_t>(r) * cols + c;
+    const float dx = p[1] - p[-1];
+    const float dy = p[-cols] - p[cols];
+    const float w = expf((c_rot * c_rot + r_rot * r_rot) * F.exp_scale);
+    const float angle = fast_atan2_deg(dy, dx);
+    const float mag = sqrtf(dx * dx + dy * dy) * w;
+    float obin = (angle - F.ori) * F.bins_per_rad;
+    const int r0 = static_cast<int>(floorf(rbin)), c0 = static_cast<int>(floorf(cbin));
+    int o0 = static_cast<int>(floorf(obin));
+    rbin -= r0; cbin -= c0; obin -= o0;
+    if (o0 < 0) o0 += n;
+    if (o0 >= n) o0 -= n;
+    const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+    const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11;
+    const float v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+    const float v_rco111 = v_rc11 * obin, v_rco110 = v_rc11 - v_rco111;
+    const float v_rco101 = v_rc10 * obin, v_rco100 = v_rc10 - v_rco101;
+    const float v_rco011 = v_rc01 * obin, v_rco010 = v_rc01 - v_rco011;
+    const float v_rco001 = v_rc00 * obin, v_rco000 = v_rc00 - v_rco001;
+    idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
+    v[0] = v_rco000; v[1] = v_rco001; v[2] = v_rco010; v[3] = v_rco011;
+    v[4] = v_rco100; v[5] = v_rco101; v[6] = v_rco110; v[7] = v_rco111;
+    return true;
+}
+
+// histogram index of descriptor element e = (i * 4 + j) * 8 + k
+SIFT_HD int descriptor_element_index(int e) {
+    const int d = kDescWidth, n = kDescBins;
+    const int k = e % n, j = (e / n) % d, i = e / (n * d);
+    return ((i + 1) * (d + 2) + (j + 1)) * (n + 2) + k;
+}
+
+// circular orientation bins folded in; returns the clipping threshold 0.2 * |raw| (sums in OpenCV's element order)
+SIFT_HD float descriptor_fold_and_threshold(float* hist, int hstride) {
+    const int d = kDescWidth, n = kDescBins;
     float nrm2 = 0.f;
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < d; ++j) {
@@ -313,28 +346,42 @@ SIFT_HD void sift_descriptor(const float* img, int cols, int rows, float ptx, fl
             hist[(idx + 1) * hstride] += hist[(idx + n + 1) * hstride];
             for (int k = 0; k < n; ++k) { const float v = hist[(idx + k) * hstride]; nrm2 += v * v; }
         }
-    const float thr = sqrtf(nrm2) * 0.2f;                                  // SIFT_DESCR_MAG_THR
-    nrm2 = 0.f;
-    for (int i = 0; i < d; ++i)
-        for (int j = 0; j < d; ++j) {
-            const int idx = ((i + 1) * (d + 2) + (j + 1)) * (n + 2);
-            for (int k = 0; k < n; ++k) {
-                float v = hist[(idx + k) * hstride];
-                v = v < thr ? v : thr;
-                hist[(idx + k) * hstride] = v;
-                nrm2 += v * v;
-            }
-        }
+    return sqrtf(nrm2) * 0.2f;                                             // SIFT_DESCR_MAG_THR
+}
+// clipped values written back; returns the scale factor 512 / max(|clipped|, FLT_EPSILON)
+SIFT_HD float descriptor_clip_and_scale(float* hist, int hstride, float thr) {
+    float nrm2 = 0.f;
+    for (int e = 0; e < kDescLen; ++e) {
+        const int idx = descriptor_element_index(e);
+        float v = hist[idx * hstride];
+        v = v < thr ? v : thr;
+        hist[idx * hstride] = v;
+        nrm2 += v * v;
+    }
     const float s = sqrtf(nrm2);
-    const float f = 512.f / (s > 1.1920929e-07f ? s : 1.1920929e-07f);      // SIFT_INT_DESCR_FCTR / max(norm, FLT_EPSILON)
-    for (int i = 0; i < d; ++i)
-        for (int j = 0; j < d; ++j) {
-            const int idx = ((i + 1) * (d + 2) + (j + 1)) * (n + 2);
-            for (int k = 0; k < n; ++k) {
-                const float v = rintf(hist[(idx + k) * hstride] * f);
-                dst[(i * d + j) * n + k] = static_cast<uint8_t>(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
-            }
+    return 512.f / (s > 1.1920929e-07f ? s : 1.1920929e-07f);             // SIFT_INT_DESCR_FCTR
+}
+SIFT_HD uint8_t descriptor_quantise(float v, float f) {                   // saturate_cast<uchar>(v * f)
+    const float q = rintf(v * f);
+    return static_cast<uint8_t>(q < 0.f ? 0.f : (q > 255.f ? 255.f : q));
+}
+
+// the serial form (host harness; the kernel walks the same samples with one warp, see sift.cu): hist = kDescHistLen floats
+// of scratch with element stride hstride; dst = 128 bytes
+SIFT_HD void sift_descriptor(const float* img, int cols, int rows, float ptx, float pty, float ori, float scl, float* hist,
+                             int hstride, uint8_t* dst) {
+    const DescFrame F = descriptor_frame(cols, rows, ptx, pty, ori, scl);
+    for (int k = 0; k < kDescHistLen; ++k) hist[k * hstride] = 0.f;
+    for (int i = -F.radius; i <= F.radius; ++i)
+        for (int j = -F.radius; j <= F.radius; ++j) {
+            int idx;
+            float v[8];
+            if (!descriptor_sample(img, cols, rows, F, i, j, idx, v)) continue;
+            for (int k = 0; k < 8; ++k) hist[(idx + descriptor_vote_offset(k)) * hstride] += v[k];
         }
+    const float thr = descriptor_fold_and_threshold(hist, hstride);
+    const float f = descriptor_clip_and_scale(hist, hstride, thr);
+    for (int e = 0; e < kDescLen; ++e) dst[e] = descriptor_quantise(hist[descriptor_element_index(e) * hstride], f);
 }
 
 }  // namespace sift
