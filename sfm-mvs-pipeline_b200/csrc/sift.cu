@@ -10,7 +10,7 @@
 //   downsample_kernel        octave base = every second pixel of level [nOctaveLayers] of the previous octave
 //   extrema_kernel           26-neighbour extrema of the DoG (differences taken on the fly) -> candidate list
 //   refine_orient_kernel     adjustLocalExtrema + calcOrientationHist per candidate -> keypoint list
-//   rank_kernel / scatter_kernel / dedupe_kernel   KeyPointsFilter::removeDuplicatedSorted + firstOctave correction
+//   bucket_* / scatter_kernel / dedupe_kernel      KeyPointsFilter::removeDuplicatedSorted + firstOctave correction
 //   descriptor_kernel        calcSIFTDescriptor per keypoint -> u8 rows
 // The per-keypoint arithmetic is sift_core.cuh (shared with the host test harness); one thread walks one keypoint in
 // OpenCV's sample order, which keeps the float accumulation order of the histograms — and with it every borderline
@@ -64,38 +64,69 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint8_t* __restri
 }
 
 constexpr int kBlurTW = 64, kBlurTH = 32;
+constexpr int kBlurMidStride = kBlurTW + 1;      // odd strides: a warp walking down a column of the tile hits 32 banks
+__host__ __device__ inline int blur_in_stride(int radius) { return (kBlurTW + 2 * radius) | 1; }
+
+// eight consecutive outputs along the filter direction per thread: a sliding window of eight inputs in registers, one
+// shared-memory load per tap.  Every output is still  ((0 + w0 x0) + w1 x1) + ...  in tap order, multiply and add rounded
+// separately (--fmad=false): the same floats as the one-output-at-a-time form.
+__device__ __forceinline__ void blur_eight_outputs(const float* __restrict__ p, int stride, int taps, const BlurWeights& k,
+                                                   float acc[8]) {
+    float win[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) { acc[o] = 0.f; win[o] = p[o * stride]; }
+    for (int t8 = 0; t8 < taps; t8 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (t8 + u < taps) {
+                const float wt = k.w[t8 + u];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] += wt * win[(o + u) & 7];
+                win[u] = p[(t8 + u + 8) * stride];
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict__ src, float* __restrict__ dst, int w, int h,
                                                          const BlurWeights k) {
     extern __shared__ float sm[];
     const int R = k.radius;
     const int IW = kBlurTW + 2 * R, IH = kBlurTH + 2 * R;
-    float* in = sm;                  // IH x IW source tile with halo
-    float* mid = sm + IH * IW;       // IH x kBlurTW, filtered along x
+    const int IS = blur_in_stride(R);
+    float* in = sm;                  // IH x IW source tile with halo (row stride IS), 8 floats of slack behind it
+    float* mid = sm + IH * IS + 8;   // IH x kBlurTW, filtered along x (row stride kBlurMidStride), 8 rows of slack behind it
     const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
     const int tid = threadIdx.x;
     for (int idx = tid; idx < IH * IW; idx += 256) {
         const int iy = idx / IW, ix = idx - iy * IW;
         const int gy = reflect101(y0 - R + iy, h), gx = reflect101(x0 - R + ix, w);
-        in[idx] = src[static_cast<size_t>(gy) * w + gx];
+        in[iy * IS + ix] = src[static_cast<size_t>(gy) * w + gx];
     }
     __syncthreads();
     const int taps = 2 * R + 1;
-    for (int idx = tid; idx < IH * kBlurTW; idx += 256) {
-        const int iy = idx / kBlurTW, ix = idx - iy * kBlurTW;
-        const float* p = in + iy * IW + ix;
-        float acc = 0.f;
-        for (int t = 0; t < taps; ++t) acc += k.w[t] * p[t];
-        mid[idx] = acc;
+    // along x: unit = (eight outputs, one tile row); consecutive lanes take consecutive rows
+    for (int unit = tid; unit < IH * (kBlurTW / 8); unit += 256) {
+        const int iy = unit % IH, ix0 = (unit / IH) * 8;
+        const float* p = in + iy * IS + ix0;
+        float acc[8];
+        blur_eight_outputs(p, 1, taps, k, acc);
+        float* q = mid + iy * kBlurMidStride + ix0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) q[o] = acc[o];
     }
     __syncthreads();
-    for (int idx = tid; idx < kBlurTH * kBlurTW; idx += 256) {
-        const int oy = idx / kBlurTW, ox = idx - oy * kBlurTW;
-        if (y0 + oy >= h || x0 + ox >= w) continue;
-        const float* p = mid + oy * kBlurTW + ox;
-        float acc = 0.f;
-        for (int t = 0; t < taps; ++t) acc += k.w[t] * p[t * kBlurTW];
-        dst[static_cast<size_t>(y0 + oy) * w + x0 + ox] = acc;
+    // along y: unit = (eight output rows, one column); consecutive lanes take consecutive columns
+    {
+        const int ox = tid % kBlurTW, oy0 = (tid / kBlurTW) * 8;
+        const float* p = mid + oy0 * kBlurMidStride + ox;
+        float acc[8];
+        blur_eight_outputs(p, kBlurMidStride, taps, k, acc);
+        if (x0 + ox < w) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                if (y0 + oy0 + o < h) dst[static_cast<size_t>(y0 + oy0 + o) * w + x0 + ox] = acc[o];
+        }
     }
 }
 
@@ -177,28 +208,75 @@ __global__ void __launch_bounds__(kRefineWarps * 32) refine_orient_kernel(const 
     }
 }
 
-// position of every keypoint in KeyPoint12_LessThan order (ties between identical keypoints: list position)
-__global__ void __launch_bounds__(256) rank_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
-                                                   int* __restrict__ rank) {
-    __shared__ Keypoint tile[256];
+// Position of every keypoint in KeyPoint12_LessThan order (ties between identical keypoints: list position).  The primary
+// key is x: keypoints are grouped by floor(x) (counting sort), every keypoint below a bucket precedes every keypoint in
+// it, and only the few members of one bucket are compared field by field.
+__device__ __forceinline__ int x_bucket(const Keypoint& k, int n_buckets) {
+    const int b = static_cast<int>(k.x);
+    return b < 0 ? 0 : (b >= n_buckets ? n_buckets - 1 : b);
+}
+__global__ void __launch_bounds__(256) bucket_count_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
+                                                           int n_buckets, int* __restrict__ count) {
     const int n = min(*n_kps, capacity);
-    for (int i0 = blockIdx.x * 256; i0 < n; i0 += gridDim.x * 256) {
-        const int i = i0 + threadIdx.x;
-        Keypoint me{};
-        if (i < n) me = kps[i];
-        int cnt = 0;
-        for (int base = 0; base < n; base += 256) {
-            if (base + static_cast<int>(threadIdx.x) < n) tile[threadIdx.x] = kps[base + threadIdx.x];
-            __syncthreads();
-            const int m = min(256, n - base);
-            if (i < n)
-                for (int j = 0; j < m; ++j) {
-                    const Keypoint other = tile[j];
-                    if (keypoint_less(other, me) || (!keypoint_less(me, other) && base + j < i)) ++cnt;
-                }
-            __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) atomicAdd(count + x_bucket(kps[i], n_buckets), 1);
+}
+// exclusive scan of the bucket sizes -> start[0 .. n_buckets]; cursor = copy of start for the fill pass
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const int* __restrict__ count, int n_buckets, int* __restrict__ start,
+                                                           int* __restrict__ cursor) {
+    __shared__ int warp_sum[32];
+    __shared__ int running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n_buckets; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n_buckets ? count[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
-        if (i < n) rank[i] = cnt;
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int wv = 0; wv < 32; ++wv) {
+            const int sv = warp_sum[wv];
+            if (wv < warp) before += sv;
+            total += sv;
+        }
+        if (i < n_buckets) {
+            const int excl = running + before + incl - v;
+            start[i] = excl;
+            cursor[i] = excl;
+        }
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) start[n_buckets] = running;
+}
+__global__ void __launch_bounds__(256) bucket_fill_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
+                                                          int n_buckets, int* __restrict__ cursor, int* __restrict__ grouped) {
+    const int n = min(*n_kps, capacity);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        grouped[atomicAdd(cursor + x_bucket(kps[i], n_buckets), 1)] = i;
+}
+__global__ void __launch_bounds__(256) bucket_rank_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
+                                                          int n_buckets, const int* __restrict__ start, const int* __restrict__ grouped,
+                                                          int* __restrict__ rank) {
+    const int n = min(*n_kps, capacity);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const Keypoint me = kps[i];
+        const int b = x_bucket(me, n_buckets);
+        const int p0 = start[b], p1 = start[b + 1];
+        int cnt = 0;
+        for (int p = p0; p < p1; ++p) {
+            const int j = grouped[p];
+            const Keypoint other = kps[j];
+            if (keypoint_less(other, me) || (!keypoint_less(me, other) && j < i)) ++cnt;
+        }
+        rank[i] = p0 + cnt;
     }
 }
 
@@ -359,6 +437,8 @@ struct SiftWorkspace {
     Candidate* d_cand = nullptr; size_t cand_cap = 0;
     Keypoint* d_kp_raw = nullptr; Keypoint* d_kp_sorted = nullptr; Keypoint* d_kp = nullptr; size_t kp_cap = 0, kp_cap2 = 0, kp_cap3 = 0;
     int* d_rank = nullptr;       size_t rank_cap = 0;
+    int* d_grouped = nullptr;    size_t grouped_cap = 0;
+    int* d_bucket = nullptr;     size_t bucket_cap = 0;   // count [nb + 1] | start [nb + 1] | cursor [nb + 1]
     uint8_t* d_desc = nullptr;   size_t desc_cap = 0;
     int* d_counts = nullptr;     // [0] candidates, [1] raw keypoints, [2] final keypoints
     int* h_counts = nullptr;     // pinned
@@ -371,7 +451,7 @@ SiftWorkspace* sift_workspace_create() { return new SiftWorkspace(); }
 void sift_workspace_destroy(SiftWorkspace* w) {
     if (!w) return;
     cudaFree(w->d_gray); cudaFree(w->d_up); cudaFree(w->d_pyr); cudaFree(w->d_cand); cudaFree(w->d_kp_raw);
-    cudaFree(w->d_kp_sorted); cudaFree(w->d_kp); cudaFree(w->d_rank); cudaFree(w->d_desc); cudaFree(w->d_counts);
+    cudaFree(w->d_kp_sorted); cudaFree(w->d_kp); cudaFree(w->d_rank); cudaFree(w->d_grouped); cudaFree(w->d_bucket); cudaFree(w->d_desc); cudaFree(w->d_counts);
     if (w->h_counts) cudaFreeHost(w->h_counts);
     delete w;
 }
@@ -428,6 +508,9 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
     SIFT_TRY(grow(ws->d_kp_sorted, ws->kp_cap2, static_cast<size_t>(max_keypoints)));
     SIFT_TRY(grow(ws->d_kp, ws->kp_cap3, static_cast<size_t>(max_keypoints)));
     SIFT_TRY(grow(ws->d_rank, ws->rank_cap, static_cast<size_t>(max_keypoints)));
+    SIFT_TRY(grow(ws->d_grouped, ws->grouped_cap, static_cast<size_t>(max_keypoints)));
+    const int n_buckets = bw + 1;                 // floor(x) of a keypoint in base-image coordinates
+    SIFT_TRY(grow(ws->d_bucket, ws->bucket_cap, 3 * static_cast<size_t>(n_buckets + 1)));
     SIFT_TRY(grow(ws->d_desc, ws->desc_cap, static_cast<size_t>(max_keypoints) * kDescLen));
     if (!ws->d_counts) SIFT_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->d_counts), 16));
     if (!ws->h_counts) SIFT_TRY(cudaMallocHost(reinterpret_cast<void**>(&ws->h_counts), 16));
@@ -444,8 +527,8 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
     auto blur = [&](const float* src, float* dst, int w, int h, double sigma) -> cudaError_t {
         const BlurWeights k = make_weights(sigma);
         if (k.radius < 0) { if (err) *err = "Gaussian kernel radius above 32 (sigma / nOctaveLayers out of the supported range)"; return cudaErrorInvalidValue; }
-        const size_t smem = (static_cast<size_t>(kBlurTH + 2 * k.radius) * (kBlurTW + 2 * k.radius) +
-                             static_cast<size_t>(kBlurTH + 2 * k.radius) * kBlurTW) * sizeof(float);
+        const size_t ih = static_cast<size_t>(kBlurTH + 2 * k.radius);
+        const size_t smem = (ih * blur_in_stride(k.radius) + 8 + (ih + 8) * kBlurMidStride) * sizeof(float);
         gauss_blur_kernel<<<dim3((w + kBlurTW - 1) / kBlurTW, (h + kBlurTH - 1) / kBlurTH), 256, smem, s>>>(src, dst, w, h, k);
         ++launches;
         return cudaGetLastError();
@@ -487,12 +570,20 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
         P, ws->d_cand, ws->d_counts, static_cast<int>(cand_capacity), static_cast<float>(prm.contrast_threshold),
         static_cast<float>(prm.edge_threshold), static_cast<float>(prm.sigma), ws->d_kp_raw, ws->d_counts + 1, max_keypoints);
     // ---- removeDuplicatedSorted + firstOctave correction
-    rank_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank);
+    int* b_count = ws->d_bucket;
+    int* b_start = ws->d_bucket + (n_buckets + 1);
+    int* b_cursor = ws->d_bucket + 2 * (n_buckets + 1);
+    SIFT_TRY(cudaMemsetAsync(b_count, 0, static_cast<size_t>(n_buckets + 1) * sizeof(int), s));
+    bucket_count_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, n_buckets, b_count);
+    bucket_scan_kernel<<<1, 1024, 0, s>>>(b_count, n_buckets, b_start, b_cursor);
+    bucket_fill_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, n_buckets, b_cursor, ws->d_grouped);
+    bucket_rank_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, n_buckets, b_start, ws->d_grouped,
+                                                  ws->d_rank);
     scatter_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank, ws->d_kp_sorted);
     dedupe_kernel<<<1, 1024, 0, s>>>(ws->d_kp_sorted, ws->d_counts + 1, max_keypoints, ws->d_kp, ws->d_counts + 2);
     // ---- calcDescriptors
     descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
-    launches += 5;
+    launches += 8;
     SIFT_TRY(cudaGetLastError());
     SIFT_TRY(cudaMemcpyAsync(ws->h_counts, ws->d_counts, 12, cudaMemcpyDeviceToHost, s));
     SIFT_TRY(cudaStreamSynchronize(s));
