@@ -184,9 +184,9 @@ int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t
 /* Feature extraction stage -----------------------------------------------------------------------
  * Replaces the body of SfM::extractFeatures' loop (SfM.cpp:584-590),
  *     featureDetector->detect(image, keypoints); descriptorExtractor->compute(image, keypoints, descriptors);
- * for the detector PhotogrammetrieCli.cpp:345-354 configures, cv::SIFT::create(0, 3, 0.09): Gaussian / DoG pyramid,
- * scale-space extrema, sub-pixel refinement, orientation histograms, removeDuplicatedSorted and the 4 x 4 x 8
- * descriptors, all on the device (csrc/sift.cu).  Keypoints come back in cv::SIFT's order (sorted by x, y, ...), in
+ * for the detector PhotogrammetrieCli.cpp:342-357 configures, cv::SIFT::create(featureLimit, 3, 0.09): Gaussian / DoG
+ * pyramid, scale-space extrema, sub-pixel refinement, orientation histograms, removeDuplicatedSorted, retainBest and
+ * the 4 x 4 x 8 descriptors, all on the device (csrc/sift.cu).  Keypoints come back in cv::SIFT's order (sorted by x, y, ...), in
  * input-image coordinates; descriptors are the u8 values cv::SIFT stores in its CV_32F rows.
  *
  * The extracted images accumulate in the context (image 0, 1, ... in call order) and stay device-resident;
@@ -194,7 +194,8 @@ int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t
  * stages without a host round trip (it replaces sfm_bank_upload + sfm_keypoints_upload);
  * sfm_features_download copies one image's keypoints / descriptors to the host (Shot::setFeatures needs them for the
  * later pipeline stages).  Parity with cv::SIFT is a tolerance (float arithmetic with data-dependent decisions):
- * tests/_sift_compare.py states it.  nfeatures (retainBest) is not implemented: the reference passes 0 (= keep all).
+ * tests/_sift_compare.py states it.  With n_features > 0 the survivors of retainBest keep the sorted order (OpenCV
+ * leaves them in the order std::nth_element produced; the set is the same).
  * max_keypoints bounds the per-image lists (0 = 262143, the matcher's per-image limit); more -> SFM_ERR_CAPACITY. */
 typedef struct sfm_keypoint {      /* cv::KeyPoint without class_id */
     float   x, y, size, angle, response;
@@ -206,6 +207,9 @@ typedef struct sfm_sift_opts {
     double  contrast_threshold;
     double  edge_threshold;
     double  sigma;
+    int32_t n_features;            /* cv::SIFT::create's nfeatures: 0 = keep all (default); the reference passes its
+                                      feature-limit (default 10000, PhotogrammetrieCli.cpp:345,355) */
+    int32_t reserved;
 } sfm_sift_opts;
 void sfm_sift_opts_default(sfm_sift_opts *o);
 int sfm_features_clear(sfm_ctx *ctx);

@@ -2,7 +2,8 @@
 
 Scope: SURVEY.md 8(f) rank 3, `SfM::extractFeatures` (reference SfM.cpp:577-597):
     featureDetector->detect(image, keypoints); descriptorExtractor->compute(image, keypoints, descriptors)
-with the detector `cv::SIFT::create(0, 3, 0.09)` that PhotogrammetrieCli.cpp:345-354 configures.  The algorithm lives
+with the detector `cv::SIFT::create(featureLimit, 3, 0.09)` that PhotogrammetrieCli.cpp:342-357 configures
+(feature-limit defaults to 10000: retainBest keeps the strongest responses).  The algorithm lives
 in a third-party dependency that is absent from /root/reference: OpenCV (the reference links the system OpenCV 4.x;
 the build container carries cv2 4.13.0, which is what this restatement is pinned against —
 tests/golden/make_golden_sift.py writes cv2's keypoints / descriptors for the reference's own image
@@ -17,6 +18,7 @@ algorithm of modules/features2d/src/sift.dispatch.cpp + sift.simd.hpp (float pip
                            adjustLocalExtrema (<= 5 Newton steps, contrast and edge tests), calcOrientationHist
                            (36 bins, [1 4 6 4 1] / 16 smoothing, peaks >= 0.8 max, parabolic bin interpolation)
     removeDuplicatedSorted sort by (x, y, -size, angle, -response, -octave), drop equal (x, y, size, angle)
+    retainBest             nfeatures > 0: keep responses >= the nfeatures-th largest
     calcSIFTDescriptor     4 x 4 x 8 histogram, trilinear votes, 0.2 clipping, * 512, saturate to u8
 
 Everything is computed in float32 in OpenCV's operation order where that is observable; the remaining differences
@@ -342,7 +344,17 @@ def remove_duplicated_sorted(kps):
     return k[np.concatenate([[True], ~same])]
 
 
-def detect(gray, n_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma=1.6, return_pyramid=False):
+def retain_best(kps, n_points):
+    """KeyPointsFilter::retainBest (keypoint.cpp): keep every keypoint whose response is >= the n_points-th largest response
+    (ties at the boundary stay).  OpenCV leaves the survivors in the order std::nth_element / std::partition produce; the
+    SET is what is defined, and it is returned here in the order of the input list."""
+    if n_points <= 0 or len(kps) <= n_points:
+        return kps
+    boundary = np.sort(kps["response"])[::-1][n_points - 1]
+    return kps[kps["response"] >= boundary]
+
+
+def detect(gray, n_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma=1.6, return_pyramid=False, nfeatures=0):
     """cv::SIFT::detect = detectAndCompute without descriptors (sift.dispatch.cpp SIFT_Impl::detectAndCompute, firstOctave = -1)."""
     base = create_initial_image(gray, sigma, True)
     n_oct = n_octaves_for(base.shape, -1)
@@ -350,6 +362,7 @@ def detect(gray, n_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma
     dog = build_dog_pyramid(gpyr, n_oct, n_layers)
     kps = find_scale_space_extrema(gpyr, dog, n_oct, n_layers, contrast_threshold, edge_threshold, sigma)
     kps = remove_duplicated_sorted(kps)
+    kps = retain_best(kps, nfeatures)
     # firstOctave < 0: back to the coordinates of the input image
     oc = kps["octave"]
     kps["octave"] = (oc & ~255) | ((oc - 1) & 255)
@@ -464,7 +477,7 @@ def compute(gray, kps, n_layers=3, sigma=1.6, gpyr=None):
     return out
 
 
-def detect_and_compute(gray, n_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma=1.6):
+def detect_and_compute(gray, n_layers=3, contrast_threshold=0.04, edge_threshold=10.0, sigma=1.6, nfeatures=0):
     """detect() then compute() as SfM::extractFeatures calls them (SfM.cpp:584-588)."""
-    kps = detect(gray, n_layers, contrast_threshold, edge_threshold, sigma)
+    kps = detect(gray, n_layers, contrast_threshold, edge_threshold, sigma, nfeatures=nfeatures)
     return kps, compute(gray, kps, n_layers, sigma)

@@ -52,7 +52,7 @@ class HomographyOpts(C.Structure):
 
 class SiftOpts(C.Structure):
     _fields_ = [("n_octave_layers", C.c_int32), ("max_keypoints", C.c_int32), ("contrast_threshold", C.c_double),
-                ("edge_threshold", C.c_double), ("sigma", C.c_double)]
+                ("edge_threshold", C.c_double), ("sigma", C.c_double), ("n_features", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Opts(C.Structure):
@@ -324,8 +324,8 @@ class Matcher:
         self._check(_lib.sfm_features_clear(self._ctx))
 
     def extract_sift(self, gray: np.ndarray, contrast_threshold: float = 0.04, n_octave_layers: int = 3,
-                     edge_threshold: float = 10.0, sigma: float = 1.6, max_keypoints: int = 0) -> int:
-        """detect() + compute() of cv::SIFT::create(0, n_octave_layers, contrast_threshold, edge_threshold, sigma) on one grey
+                     edge_threshold: float = 10.0, sigma: float = 1.6, max_keypoints: int = 0, n_features: int = 0) -> int:
+        """detect() + compute() of cv::SIFT::create(n_features, n_octave_layers, contrast_threshold, edge_threshold, sigma) on one grey
         uint8 image; the result is appended to the context's device-resident feature set.  Returns the keypoint count."""
         gray = np.asarray(gray)
         if gray.dtype != np.uint8 or gray.ndim != 2:
@@ -334,7 +334,7 @@ class Matcher:
             gray = np.ascontiguousarray(gray)
         o = SiftOpts()
         _lib.sfm_sift_opts_default(C.byref(o))
-        o.n_octave_layers, o.max_keypoints = n_octave_layers, max_keypoints
+        o.n_octave_layers, o.max_keypoints, o.n_features = n_octave_layers, max_keypoints, n_features
         o.contrast_threshold, o.edge_threshold, o.sigma = contrast_threshold, edge_threshold, sigma
         n = C.c_int32(0)
         step = gray.strides[0] if gray.shape[0] > 1 else gray.shape[1]

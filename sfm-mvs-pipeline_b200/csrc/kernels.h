@@ -161,6 +161,7 @@ cudaError_t launch_homography_ransac(const HomographyArgs& a, cudaStream_t s);
 // ---- sift.cu: feature extraction, SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:345-354)
 struct SiftParams {
     int n_layers;                // nOctaveLayers
+    int n_features;              // nfeatures (retainBest), 0 = all
     double contrast_threshold, edge_threshold, sigma;
 };
 constexpr int kSiftMaxOctaves = 16;

@@ -1344,11 +1344,14 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
 
 // ---- SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:345-354) on the device
 static_assert(sizeof(sfm_keypoint) == 24, "sfm_keypoint layout (= sift::Keypoint of csrc/sift_core.cuh)");
+static_assert(sizeof(sfm_sift_opts) == 40, "sfm_sift_opts layout");
 
 void sfm_sift_opts_default(sfm_sift_opts* o) {
     if (!o) return;
     o->n_octave_layers = 3;          // cv::SIFT::create defaults (features2d.hpp); the reference CLI passes (0, 3, 0.09)
     o->max_keypoints = 0;            // 0: the matcher's per-image limit
+    o->n_features = 0;               // cv::SIFT::create(nfeatures = 0): keep all; the reference passes its feature-limit
+    o->reserved = 0;
     o->contrast_threshold = 0.04;
     o->edge_threshold = 10.0;
     o->sigma = 1.6;
@@ -1381,7 +1384,7 @@ int sfm_features_extract_sift(sfm_ctx* c, const uint8_t* gray, int rows, int col
     CU_TRY(c, cudaSetDevice(c->device));
     if (!c->sift) c->sift = sift_workspace_create();
     SiftParams prm;
-    prm.n_layers = o.n_octave_layers; prm.contrast_threshold = o.contrast_threshold; prm.edge_threshold = o.edge_threshold;
+    prm.n_layers = o.n_octave_layers; prm.n_features = o.n_features > 0 ? o.n_features : 0; prm.contrast_threshold = o.contrast_threshold; prm.edge_threshold = o.edge_threshold;
     prm.sigma = o.sigma;
     int n = 0, launches = 0;
     std::string err;

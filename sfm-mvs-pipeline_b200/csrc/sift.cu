@@ -11,6 +11,7 @@
 //   extrema_kernel           26-neighbour extrema of the DoG (differences taken on the fly) -> candidate list
 //   refine_orient_kernel     adjustLocalExtrema + calcOrientationHist per candidate -> keypoint list
 //   bucket_* / scatter_kernel / dedupe_kernel      KeyPointsFilter::removeDuplicatedSorted + firstOctave correction
+//   retain_best_kernel       KeyPointsFilter::retainBest (nfeatures = the reference's feature-limit)
 //   descriptor_kernel        calcSIFTDescriptor per keypoint -> u8 rows
 // The per-keypoint arithmetic is sift_core.cuh (shared with the host test harness); one thread walks one keypoint in
 // OpenCV's sample order, which keeps the float accumulation order of the histograms — and with it every borderline
@@ -327,6 +328,74 @@ __global__ void __launch_bounds__(1024) dedupe_kernel(const Keypoint* __restrict
     if (tid == 0) *n_out = running;
 }
 
+// KeyPointsFilter::retainBest (nfeatures > 0): keep every keypoint whose response is >= the n_features-th largest one
+// (boundary ties stay), in place and in the order of the list.  One CTA: radix select over the bit pattern of the
+// responses (non-negative floats order like their bits; 11 + 11 + 10 bits), then an ordered compaction.
+__global__ void __launch_bounds__(1024) retain_best_kernel(Keypoint* __restrict__ kps, int* __restrict__ n_io, int capacity,
+                                                           int n_features) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned sel_prefix;
+    __shared__ int sel_remaining;
+    __shared__ int warp_sum[32];
+    __shared__ int running;
+    const int n = min(*n_io, capacity);
+    if (n_features <= 0 || n <= n_features) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned prefix = 0, prefix_mask = 0;
+    int remaining = n_features;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const int nb = pass == 2 ? 1024 : 2048;
+        for (int b = tid; b < nb; b += 1024) hist[b] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 1024) {
+            const unsigned bits = __float_as_uint(kps[i].response);
+            if ((bits & prefix_mask) == prefix) atomicAdd(&hist[(bits >> shift) & (nb - 1)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int rem = remaining, b = nb - 1;
+            for (; b > 0; --b) {
+                if (hist[b] >= static_cast<unsigned>(rem)) break;
+                rem -= static_cast<int>(hist[b]);
+            }
+            sel_prefix = prefix | (static_cast<unsigned>(b) << shift);
+            sel_remaining = rem;
+        }
+        __syncthreads();
+        prefix = sel_prefix;
+        remaining = sel_remaining;
+        prefix_mask |= static_cast<unsigned>(nb - 1) << shift;
+        __syncthreads();
+    }
+    const unsigned threshold = prefix;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        Keypoint kp{};
+        bool keep = false;
+        if (i < n) {
+            kp = kps[i];
+            keep = __float_as_uint(kp.response) >= threshold;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_sum[warp] = __popc(bal);
+        __syncthreads();                                   // every element of this chunk has been read
+        int before = 0, total = 0;
+        for (int wv = 0; wv < 32; ++wv) {
+            const int sv = warp_sum[wv];
+            if (wv < warp) before += sv;
+            total += sv;
+        }
+        if (keep) kps[running + before + __popc(bal & ((1u << lane) - 1u))] = kp;      // position <= i
+        __syncthreads();
+        if (tid == 0) running += total;
+        __syncthreads();
+    }
+    if (tid == 0) *n_io = running;
+}
+
 // One warp per keypoint (grid-stride).  The 32 lanes compute the votes of 32 consecutive samples of the window (row by
 // row, OpenCV's k order) and park them in shared memory; the histogram is then updated sample by sample, the eight
 // votes of a sample (eight distinct bins) by eight lanes at once: every bin receives its contributions in the serial
@@ -581,6 +650,10 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
                                                   ws->d_rank);
     scatter_kernel<<<persistent, 256, 0, s>>>(ws->d_kp_raw, ws->d_counts + 1, max_keypoints, ws->d_rank, ws->d_kp_sorted);
     dedupe_kernel<<<1, 1024, 0, s>>>(ws->d_kp_sorted, ws->d_counts + 1, max_keypoints, ws->d_kp, ws->d_counts + 2);
+    if (prm.n_features > 0) {
+        retain_best_kernel<<<1, 1024, 0, s>>>(ws->d_kp, ws->d_counts + 2, max_keypoints, prm.n_features);
+        ++launches;
+    }
     // ---- calcDescriptors
     descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
     launches += 8;

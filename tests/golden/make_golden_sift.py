@@ -6,7 +6,8 @@ Writes tests/golden/sift_extract.npz with, for the reference's own photograph im
 Shot::loadImage + cv::SIFT see it) and for workloads.synthetic_photo(0, 240, 320):
     the grey image (insel only; the synthetic one is regenerated from its seed),
     cv2's keypoints after detect() and descriptors after compute(), called separately like the reference does,
-    with the detector of PhotogrammetrieCli.cpp:345-354, cv::SIFT::create(0, 3, 0.09), and with OpenCV's defaults.
+    with the detector of PhotogrammetrieCli.cpp:342-357, cv::SIFT::create(featureLimit, 3, 0.09) (limit not reached, and a
+    limit of 100 that is), and with OpenCV's defaults.
 Nothing here comes from the numpy restatement (oracle/sift_np.py): the tests pin the restatement — and through it the
 CUDA path — against these arrays on a box where /root/reference does not exist.
 """
@@ -23,8 +24,8 @@ import workloads  # noqa: E402
 KP_FIELDS = ("x", "y", "size", "angle", "response", "octave")
 
 
-def extract(img, contrast):
-    det = cv2.SIFT_create(0, 3, contrast)
+def extract(img, contrast, nfeatures=0):
+    det = cv2.SIFT_create(nfeatures, 3, contrast)
     kp = det.detect(img, None)
     kp, desc = det.compute(img, kp)
     arr = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in kp],
@@ -38,6 +39,8 @@ def main():
     insel = cv2.imread("/root/reference/images/insel/1.jpg", cv2.IMREAD_GRAYSCALE)
     out["insel1_gray"] = insel
     out["insel1_kp_009"], out["insel1_desc_009"] = extract(insel, 0.09)
+    # the reference passes its feature-limit as nfeatures (default 10000): retainBest, exercised here with a small limit
+    out["insel1_kp_009_n100"], out["insel1_desc_009_n100"] = extract(insel, 0.09, 100)
     syn = workloads.synthetic_photo(0, 240, 320)
     out["syn0_sha_probe"] = np.array([int(syn.astype(np.int64).sum()), int((syn.astype(np.int64) * np.arange(320)).sum())])
     out["syn0_kp_004"], out["syn0_desc_004"] = extract(syn, 0.04)

@@ -72,6 +72,22 @@ def test_reference_photo_against_cv2_golden(m, gold):
     sc.assert_close(gold["syn0_kp_004"], gold["syn0_desc_004"], kp, desc, "synthetic vs cv2")
 
 
+def test_feature_limit(m, gold):
+    """cv::SIFT::create(featureLimit, 3, 0.09) (PhotogrammetrieCli.cpp:345,355): retainBest keeps the strongest responses."""
+    m.features_clear()
+    n = m.extract_sift(gold["insel1_gray"], contrast_threshold=0.09, n_features=100)
+    kp, desc = m.features_download(0)
+    assert n == 101 and np.all(np.diff(kp["x"]) >= 0)
+    sc.assert_close(gold["insel1_kp_009_n100"], gold["insel1_desc_009_n100"], kp, desc, "insel limit 100 vs cv2")
+    img = workloads.synthetic_photo(3, 240, 320)
+    for limit in (1, 37, 150, 100000):
+        m.extract_sift(img, n_features=limit)
+        kp, desc = m.features_download(m.features_count() - 1)
+        kp_o, desc_o = S.detect_and_compute(img, nfeatures=limit)
+        assert abs(len(kp) - len(kp_o)) <= 2 and len(kp) >= min(limit, len(kp_o) - 2)
+        sc.assert_close(kp_o, desc_o.astype(np.uint8), kp, desc, f"limit {limit}")
+
+
 def test_edge_cases(m, sfm):
     m.features_clear()
     assert m.extract_sift(np.full((64, 64), 100, np.uint8)) == 0

@@ -56,6 +56,18 @@ def test_insel_photo_reference_settings(gold):
     assert np.all(np.diff(kp["x"]) >= 0)
 
 
+def test_feature_limit_retain_best(gold):
+    # cv::SIFT::create(featureLimit, 3, 0.09): the 100 strongest responses, ties at the boundary kept (101 here)
+    kp, desc = S.detect_and_compute(gold["insel1_gray"], contrast_threshold=0.09, nfeatures=100)
+    assert len(gold["insel1_kp_009_n100"]) == 101
+    r = sc.assert_close(gold["insel1_kp_009_n100"], gold["insel1_desc_009_n100"], kp, desc, "insel 0.09 limit 100")
+    assert r["n_b"] == 101 and r["matched"] >= 100
+    k = S.KEYPOINT_DTYPE
+    few = np.array([(0, 0, 1, 0, r_, 0) for r_ in (0.5, 0.1, 0.5, 0.3, 0.3)], k)
+    assert np.allclose(S.retain_best(few, 3)["response"], [0.5, 0.5, 0.3, 0.3]) and len(S.retain_best(few, 0)) == 5
+    assert len(S.retain_best(few, 7)) == 5 and np.allclose(S.retain_best(few, 1)["response"], [0.5, 0.5])
+
+
 @pytest.mark.parametrize("tag,ct", [("009", 0.09), ("004", 0.04)])
 def test_synthetic_photo(gold, tag, ct):
     syn = workloads.synthetic_photo(0, 240, 320)
