@@ -36,7 +36,8 @@ def main():
     sfm = ge.load_package()
     m = sfm.Matcher(0)
     threads = len(os.sched_getaffinity(0))
-    for shape in ((1200, 1600), (3000, 4000)):
+    shapes = ((1200, 1600), (3000, 4000)) if os.environ.get("SIFT_PERF_BIG") else ((1200, 1600),)
+    for shape in shapes:
         base = [workloads.synthetic_photo(s, *shape) for s in range(2)]
         images = [base[i % 2] if i < 2 else np.ascontiguousarray(np.roll(base[i % 2], 17 * i, axis=1)) for i in range(n_images)]
         m.features_clear()
