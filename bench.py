@@ -40,8 +40,10 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-pairs", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"],
-                    help="c3 (default, the metric's config) | c4 big-grid 1000x4096 grid(40,3) | c5 big-unordered 500x16384")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "extract"],
+                    help="c3 (default, the metric's config) | c4 big-grid 1000x4096 grid(40,3) | c5 big-unordered 500x16384 | "
+                         "extract: the stage before matching (SfM::extractFeatures, cv::SIFT), a secondary line with its own metric")
+    ap.add_argument("--photo", default="1200x1600", help="extract workload: image size HEIGHTxWIDTH")
     return ap.parse_args()
 
 
@@ -405,6 +407,139 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- extract workload
+# Secondary line for the widened row SURVEY 8f rank 3 (SfM::extractFeatures, SfM.cpp:577-597; detector
+# PhotogrammetrieCli.cpp:342-357).  NOT the north-star metric: its own metric / unit, same JSON contract.
+EXTRACT_METRIC = "images/sec SIFT detect+compute (cv::SIFT(feature-limit 10000, 3, 0.09))"
+
+
+def _extract_images(a):
+    h, w = (int(v) for v in a.photo.lower().split("x"))
+    n = a.images if a.images != 200 else 16
+    base = [workloads.synthetic_photo(s, h, w) for s in range(min(n, 4))]
+    imgs = [base[i] if i < len(base) else np.ascontiguousarray(np.roll(base[i % len(base)], 13 * i, axis=1)) for i in range(n)]
+    return imgs, f"{n} synthetic photographs {w}x{h} (workloads.synthetic_photo)"
+
+
+def _cv2_extract_rate(imgs, threads):
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+    cv2.setNumThreads(1)                       # one image per thread, like the reference's OpenMP loop (SfM.cpp:582)
+
+    def one(img):
+        det = cv2.SIFT_create(10000, 3, 0.09)
+        kp = det.detect(img, None)
+        kp, d = det.compute(img, kp)
+        return len(kp)
+    t = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        counts = list(ex.map(one, imgs))
+    return len(imgs) / (time.perf_counter() - t), counts
+
+
+def run_extract_reference(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    imgs, name = _extract_images(a)
+    threads = len(os.sched_getaffinity(0))
+    for _ in range(a.warmup):
+        _cv2_extract_rate(imgs[:2], threads)
+    t0 = time.perf_counter()
+    rates = [_cv2_extract_rate(imgs, threads)[0] for _ in range(a.steps)]
+    dt = time.perf_counter() - t0
+    v = len(imgs) * a.steps / dt
+    import cv2
+    sample = f"each step = all {len(imgs)} images, cv2 {cv2.__version__} SIFT detect + compute, one image per thread"
+    _emit(json.dumps({"impl": "reference", "metric": EXTRACT_METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+                      "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": name, "sample": sample},
+                      "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "reference", "sample": sample},
+                      "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "steps_images_per_s": [round(r, 2) for r in rates]}))
+
+
+def run_extract_ours(a):
+    import torch
+    if a.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload extract is a single-GPU line (images are independent: replicas only)")
+    import __graft_entry__ as ge
+    sfm = ge.load_package()
+    m = sfm.Matcher(0)
+    imgs, name = _extract_images(a)
+    imgs = [torch.from_numpy(i).pin_memory().numpy() for i in imgs]         # page-locked host images
+    torch.cuda.set_device(0)
+    stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", 0))
+    opts = dict(contrast_threshold=0.09, n_features=10000)
+
+    def step(download):
+        m.features_clear()
+        prof = {"pyramid_ms": 0.0, "total_ms": 0.0, "pyramid_bytes": 0.0}
+        n_kp = 0
+        for im in imgs:
+            n_kp += m.extract_sift(im, **opts)
+            p = m.features_last_profile()
+            for k in prof:
+                prof[k] += p[k]
+        d2h = 0
+        if download:
+            for i in range(len(imgs)):
+                kp, desc = m.features_download(i)
+                d2h += kp.nbytes + desc.nbytes
+            m.bank_from_features()
+        return n_kp, prof, d2h
+    for _ in range(max(a.warmup, 3)):
+        step(True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = m.stats()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    profs = []
+    for _ in range(a.steps):
+        n_kp, prof, _ = step(False)
+        profs.append(prof)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    launches = m.stats()["kernel_launches"] - l0
+    ms = ev0.elapsed_time(ev1) / a.steps
+    # end to end: grey images in host memory -> keypoints + descriptors back on the host AND adopted as the matcher's bank
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        _, _, d2h = step(True)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / a.e2e_steps
+    clocks = sampler.stop()
+    _, _, hbm, src = measured_peaks()
+    pyr_ms = float(np.mean([p["pyramid_ms"] for p in profs]))
+    tot_ms = float(np.mean([p["total_ms"] for p in profs]))
+    pyr_bytes = float(np.mean([p["pyramid_bytes"] for p in profs]))
+    line = {"metric": EXTRACT_METRIC, "value": len(imgs) / (ms * 1e-3), "unit": "images/s", "n_gpus": 1, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "keypoints_per_step": int(n_kp), "l2_policy": "pyramid of one image (246 MB at 1600x1200) exceeds L2",
+                       "value_includes": "H2D of each grey image (the ABI takes host images); device time on the library stream",
+                       "note": "secondary line (SURVEY 8f rank 3), not the north-star metric"},
+            "e2e": {"value": len(imgs) / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(sum(i.nbytes for i in imgs)),
+                    "d2h_bytes_per_step": int(d2h), "includes": "features downloaded to the host + sfm_bank_from_features"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "Gaussian pyramid (upsample + blur + downsample launches of one step)",
+                         "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else None, "peak": hbm, "peak_source": src,
+                         "unit": "GB/s", "frac": (pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm) if pyr_ms > 0 else None, "traffic": None,
+                         "pyramid_ms_per_step": pyr_ms, "device_ms_per_step": tot_ms, "share_of_step": pyr_ms / tot_ms if tot_ms else None},
+            "clocks": clocks}
+    if not a.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        rate, counts = _cv2_extract_rate(imgs[:max(2, min(len(imgs), threads))], threads)
+        import cv2
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "reference",
+                                "sample": f"{max(2, min(len(imgs), threads))} images of the workload, cv2 {cv2.__version__} SIFT, one image per thread",
+                                "keypoints_per_image": int(np.mean(counts))}
+    _emit(json.dumps(line))
+    m.close()
+
+
 def _emit(line):
     """The ONE JSON line goes to the real stdout; fd 1 is pointed at stderr for the rest of the run so that native
     libraries (NCCL's version banner, ...) cannot pollute it."""
@@ -416,7 +551,9 @@ if __name__ == "__main__":
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     args = apply_workload(parse())
-    if args.impl == "reference":
+    if args.workload == "extract":
+        (run_extract_reference if args.impl == "reference" else run_extract_ours)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -222,6 +222,9 @@ int sfm_bank_from_features(sfm_ctx *ctx);
  * extraction; one level of its Gaussian pyramid (out may be NULL to query the size). */
 int sfm_features_last_counts(const sfm_ctx *ctx, int32_t counts[3]);
 int sfm_features_pyramid_level(sfm_ctx *ctx, int octave, int level, float *out, int32_t *width, int32_t *height);
+/* Device time of the last extraction (CUDA events on the context stream): Gaussian pyramid construction and the whole
+ * image (ms), and the algorithmic HBM bytes of the pyramid (8 B per pixel and level) — bench.py's roofline block. */
+int sfm_features_last_profile(const sfm_ctx *ctx, double *pyramid_ms, double *total_ms, double *pyramid_bytes);
 
 /* Counters of the last enqueue: kernels launched / bytes moved, for bench.py's gpu_launches etc. */
 int sfm_last_stats(const sfm_ctx *ctx, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes);

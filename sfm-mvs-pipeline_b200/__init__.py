@@ -34,7 +34,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios",
            "sfm_homography_opts_default", "sfm_sift_opts_default", "sfm_features_clear", "sfm_features_extract_sift",
            "sfm_features_count", "sfm_features_download", "sfm_bank_from_features", "sfm_features_last_counts",
-           "sfm_features_pyramid_level"]
+           "sfm_features_pyramid_level", "sfm_features_last_profile"]
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4")])          # sfm_keypoint = cv::KeyPoint without class_id
@@ -367,6 +367,11 @@ class Matcher:
         c = (C.c_int32 * 3)()
         self._check(_lib.sfm_features_last_counts(self._ctx, c))
         return {"extrema": c[0], "keypoints_raw": c[1], "keypoints": c[2]}
+
+    def features_last_profile(self):
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(_lib.sfm_features_last_profile(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
+        return {"pyramid_ms": a.value, "total_ms": b.value, "pyramid_bytes": c.value}
 
     def pyramid_level(self, octave: int, level: int) -> np.ndarray:
         w, h = C.c_int32(0), C.c_int32(0)

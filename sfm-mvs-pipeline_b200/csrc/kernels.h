@@ -176,6 +176,8 @@ cudaError_t sift_extract(SiftWorkspace* w, const uint8_t* gray, int rows, int co
                          std::string* err);
 const void* sift_keypoints_device_raw(const SiftWorkspace* w);       // sift::Keypoint[n] = sfm_keypoint[n]
 const uint8_t* sift_descriptors_device(const SiftWorkspace* w);      // n x 128
+// device time of the last extraction (CUDA events on the stream): pyramid construction / whole image; algorithmic HBM bytes of the pyramid
+void sift_last_profile(const SiftWorkspace* w, double* pyramid_ms, double* total_ms, double* pyramid_bytes);
 // test hook: geometry of the pyramid of the last extraction (float offsets of level 0 of every octave) and its base pointer
 int sift_pyramid_geometry(const SiftWorkspace* w, int* n_layers, int* widths, int* heights, int64_t* offsets, const float** base);
 cudaError_t launch_keypoint_xy(const void* keypoints, int n, float2* xy, cudaStream_t s);

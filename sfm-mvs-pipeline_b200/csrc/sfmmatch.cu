@@ -1420,6 +1420,13 @@ int sfm_features_last_counts(const sfm_ctx* c, int32_t counts[3]) {
     return SFM_OK;
 }
 
+int sfm_features_last_profile(const sfm_ctx* c, double* pyramid_ms, double* total_ms, double* pyramid_bytes) {
+    if (!c) return SFM_ERR_INVALID;
+    if (!c->sift) { if (pyramid_ms) *pyramid_ms = 0; if (total_ms) *total_ms = 0; if (pyramid_bytes) *pyramid_bytes = 0; return SFM_OK; }
+    sift_last_profile(c->sift, pyramid_ms, total_ms, pyramid_bytes);
+    return SFM_OK;
+}
+
 int sfm_features_download(sfm_ctx* c, int image, int32_t* n_keypoints, sfm_keypoint* kps, uint8_t* desc) {
     if (!c) return SFM_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);

@@ -513,6 +513,8 @@ struct SiftWorkspace {
     int* h_counts = nullptr;     // pinned
     PyramidView view{};
     bool smem_set = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};      // start | pyramid built | descriptors written
+    float pyramid_ms = 0.f, total_ms = 0.f;
 };
 
 SiftWorkspace* sift_workspace_create() { return new SiftWorkspace(); }
@@ -522,11 +524,23 @@ void sift_workspace_destroy(SiftWorkspace* w) {
     cudaFree(w->d_gray); cudaFree(w->d_up); cudaFree(w->d_pyr); cudaFree(w->d_cand); cudaFree(w->d_kp_raw);
     cudaFree(w->d_kp_sorted); cudaFree(w->d_kp); cudaFree(w->d_rank); cudaFree(w->d_grouped); cudaFree(w->d_bucket); cudaFree(w->d_desc); cudaFree(w->d_counts);
     if (w->h_counts) cudaFreeHost(w->h_counts);
+    for (cudaEvent_t e : w->ev) if (e) cudaEventDestroy(e);
     delete w;
 }
 
 const void* sift_keypoints_device_raw(const SiftWorkspace* w) { return w->d_kp; }
 const uint8_t* sift_descriptors_device(const SiftWorkspace* w) { return w->d_desc; }
+void sift_last_profile(const SiftWorkspace* w, double* pyramid_ms, double* total_ms, double* pyramid_bytes) {
+    if (pyramid_ms) *pyramid_ms = w->pyramid_ms;
+    if (total_ms) *total_ms = w->total_ms;
+    // algorithmic HBM traffic of the pyramid: the u8 image in, every level written once and (all but the last of an octave) read once
+    if (pyramid_bytes) {
+        const PyramidView& P = w->view;
+        double b = 0;
+        for (int o = 0; o < P.n_octaves; ++o) b += 8.0 * (P.n_layers + 3) * static_cast<double>(P.w[o]) * P.h[o];
+        *pyramid_bytes = b + (P.n_octaves ? 0.25 * P.w[0] * P.h[0] : 0.0);
+    }
+}
 int sift_pyramid_geometry(const SiftWorkspace* w, int* n_layers, int* widths, int* heights, int64_t* offsets, const float** base) {
     const PyramidView& P = w->view;
     if (n_layers) *n_layers = P.n_layers;
@@ -587,7 +601,9 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
         SIFT_TRY(cudaFuncSetAttribute(gauss_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         ws->smem_set = true;
     }
+    for (cudaEvent_t& e : ws->ev) if (!e) SIFT_TRY(cudaEventCreate(&e));
     SIFT_TRY(cudaMemsetAsync(ws->d_counts, 0, 16, s));
+    SIFT_TRY(cudaEventRecord(ws->ev[0], s));
     // ---- grey image to the device, doubled, first blur (createInitialImage)
     SIFT_TRY(cudaMemcpy2DAsync(ws->d_gray, cols, gray, step, cols, rows, cudaMemcpyHostToDevice, s));
     const dim3 blk(32, 8);
@@ -625,6 +641,7 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
         }
         for (int i = 1; i < levels; ++i) SIFT_TRY(blur(lv0 + (i - 1) * plane, lv0 + i * plane, w, h, sig[i]));
     }
+    SIFT_TRY(cudaEventRecord(ws->ev[1], s));
     // ---- findScaleSpaceExtrema
     const float threshold = static_cast<float>(static_cast<int>(std::floor(0.5 * prm.contrast_threshold / L * 255)));
     for (int o = 0; o < n_octaves; ++o) {
@@ -658,8 +675,11 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
     descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
     launches += 8;
     SIFT_TRY(cudaGetLastError());
+    SIFT_TRY(cudaEventRecord(ws->ev[2], s));
     SIFT_TRY(cudaMemcpyAsync(ws->h_counts, ws->d_counts, 12, cudaMemcpyDeviceToHost, s));
     SIFT_TRY(cudaStreamSynchronize(s));
+    SIFT_TRY(cudaEventElapsedTime(&ws->pyramid_ms, ws->ev[0], ws->ev[1]));
+    SIFT_TRY(cudaEventElapsedTime(&ws->total_ms, ws->ev[0], ws->ev[2]));
     if (counts_out) { counts_out[0] = ws->h_counts[0]; counts_out[1] = ws->h_counts[1]; counts_out[2] = ws->h_counts[2]; }
     if (ws->h_counts[0] > static_cast<int>(cand_capacity) || ws->h_counts[1] > max_keypoints) {
         if (err) *err = "feature extraction: more candidates / keypoints than the capacity (" + std::to_string(ws->h_counts[0]) + " / " +

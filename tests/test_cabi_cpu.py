@@ -130,3 +130,23 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["vs_baseline"] is None
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_bench_extract_reference_arm_contract():
+    """The secondary bench line of the feature-extraction stage: `bench.py --workload extract --impl reference` (cv2's SIFT on
+    the host threads) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    from oracle import cv2_ref
+    if not cv2_ref.available():
+        pytest.skip("cv2 not importable")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "extract", "--impl", "reference", "--images", "3",
+                          "--photo", "120x160", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout + out.stderr
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0 and "SIFT" in d["metric"]
