@@ -3,7 +3,11 @@
 // (PhotogrammetrieCli.cpp:320-392, :95, :112, :422-460):
 //   -Pfeature-detector=SIFT|ORB  -Pfeature-matcher=BF|FLANN  -Pfeature-limit=N  -Pfeature-sequence=S
 //   -Pfeature-gridlength=L  -Pmatch-threshold=T  --distinct-matches  -Ploglevel=0..4
-// Feature extraction is outside this stage, so descriptors come from a file instead of -Pimage:
+// Input, either of
+//   -Pimage=<shot.pgm> (repeated, one per shot; binary PGM "P5", 8 bit): SfM::extractFeatures runs on the device
+//                               (cv::SIFT::create(feature-limit, 3, 0.09), PhotogrammetrieCli.cpp:342-357), the descriptors and
+//                               keypoints stay there for the matching and homography stages
+// or descriptors computed elsewhere:
 //   -Pdescriptors=<bank.sfmd>   "SFMD" u32 version, u32 n_images, u32 cols, u32 depth(0=CV_8U,5=CV_32F),
 //                               then per image: u32 n_rows + n_rows*cols*elemsize bytes
 //   -Pkeypoints=<bank.sfmk>     optional, enables the homography stage (SfM::calculateHomography): "SFMK" u32 version, u32 n_images,
@@ -11,6 +15,7 @@
 //   -Pransac-matching-threshold=0.006   as PhotogrammetrieCli.cpp:98-99 (< 0: pixels, > 0: fraction of the image size)
 //   -Pout=<matches.bin>         u64 n_pairs, then per kept pair: i32 left, i32 right, u64 n, n x DMatch(16 B)
 //   -Pdevice=<gpu>
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -41,25 +46,111 @@ struct Args {
         return it == kv.end() ? def : it->second;
     }
     bool flag(const std::string& k) const { return get(k, "0") == "1"; }
+    std::vector<std::string> all(const std::string& k) const {
+        std::vector<std::string> v;
+        auto r = kv.equal_range(k);
+        for (auto it = r.first; it != r.second; ++it) v.push_back(it->second);
+        return v;
+    }
 };
 
+// binary PGM (P5, maxval <= 255): what Shot::loadImage + the grey conversion of cv::SIFT hand to the detector
+static void readPgm(const std::string& path, std::vector<uint8_t>& pixels, int& width, int& height) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    auto token = [&]() {
+        std::string t;
+        int ch;
+        while ((ch = f.get()) != EOF) {
+            if (ch == '#') { while ((ch = f.get()) != EOF && ch != '\n') {} continue; }
+            if (std::isspace(ch)) { if (!t.empty()) break; continue; }
+            t.push_back(static_cast<char>(ch));
+        }
+        return t;
+    };
+    if (token() != "P5") throw std::runtime_error(path + ": not a binary PGM (P5)");
+    width = std::stoi(token());
+    height = std::stoi(token());
+    const int maxval = std::stoi(token());
+    if (width <= 0 || height <= 0 || maxval <= 0 || maxval > 255) throw std::runtime_error(path + ": unsupported PGM header");
+    pixels.resize(static_cast<size_t>(width) * height);
+    f.read(reinterpret_cast<char*>(pixels.data()), static_cast<std::streamsize>(pixels.size()));
+    if (!f) throw std::runtime_error(path + ": truncated PGM");
+}
+
 static void usage() {
-    std::puts("sfm_match_cli -Pdescriptors=<bank.sfmd> [-Pfeature-detector=SIFT|ORB] [-Pfeature-matcher=BF|FLANN]\n"
+    std::puts("sfm_match_cli (-Pimage=<shot.pgm> ... | -Pdescriptors=<bank.sfmd>) [-Pfeature-detector=SIFT|ORB] [-Pfeature-matcher=BF|FLANN]\n"
               "              [-Pfeature-limit=10000] [-Pfeature-sequence=0] [-Pfeature-gridlength=0] [-Pmatch-threshold=20]\n"
               "              [--distinct-matches] [-Pkeypoints=<bank.sfmk>] [-Pransac-matching-threshold=0.006]\n"
               "              [-Pout=matches.bin] [-Pdevice=0] [-Ploglevel=2]");
+}
+
+static void report(const std::vector<ShotMatches>& res, size_t n_pairs, double dt, bool ratios) {
+    size_t total = 0;
+    for (auto& sm : res) total += sm.matches.size();
+    std::printf("pairs=%zu kept=%zu matches=%zu seconds=%.6f\n", n_pairs, res.size(), total, dt);
+    if (ratios)
+        for (auto& sm : res)
+            std::printf("%s : %s -> %zu homographyInlierRatio: %.6f\n", sm.left->imagePath.c_str(), sm.right->imagePath.c_str(),
+                        sm.matches.size(), sm.homographyInlierRatio);
+}
+
+// -Pimage=...: extractFeatures -> calculateShotMatches -> calculateHomography, all on the device (SfM.cpp:152-156 order)
+static int runFromImages(const Args& args, const std::vector<std::string>& paths, const std::string& det, int limit, int loglevel) {
+    if (det == "ORB") throw std::invalid_argument("-Pimage with feature-detector=ORB: ORB extraction is not built on the device");
+    std::vector<std::vector<uint8_t>> pixels(paths.size());
+    std::vector<GrayImage> images(paths.size());
+    Scene scene;
+    for (size_t i = 0; i < paths.size(); ++i) {
+        int w = 0, h = 0;
+        readPgm(paths[i], pixels[i], w, h);
+        images[i] = GrayImage{pixels[i].data(), h, w, static_cast<size_t>(w)};
+        auto shot = std::make_shared<Shot>();
+        shot->imagePath = paths[i];
+        scene.shots.push_back(shot);
+    }
+    std::vector<std::string> warnings;
+    if (det != "SIFT" && !det.empty()) warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
+    auto matcher = configureFeatureMatcher("SIFT", args.get("feature-matcher"), std::stoi(args.get("device", "0")), &warnings);
+    auto strategy = configureFeatureMatcherStrategy(std::stoi(args.get("feature-sequence", "0")),
+                                                    std::stoi(args.get("feature-gridlength", "0")), &warnings);
+    for (auto& w : warnings) std::fprintf(stderr, "[WARN] %s\n", w.c_str());
+    GpuSiftFeatureDetector detector(matcher, limit, 3, 0.09);         // cv::SIFT::create(featureLimit, 3, 0.09)
+    std::vector<Features> features;
+    const auto t0 = std::chrono::steady_clock::now();
+    detector.extractFeatures(images, scene, features);
+    const double t_extract = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    size_t n_kp = 0;
+    for (auto& f : features) n_kp += f.keypoints.size();
+    std::printf("images=%zu keypoints=%zu extract_seconds=%.6f\n", paths.size(), n_kp, t_extract);
+    if (loglevel >= 3)
+        for (size_t i = 0; i < paths.size(); ++i) std::printf("%s : %zu Merkmale\n", paths[i].c_str(), features[i].keypoints.size());
+    MatchingStage stage;
+    stage.setMatchingAlgorithm(matcher);
+    stage.setFeatureMatchingStrategy(strategy);
+    stage.setMinMatchCount(std::stoi(args.get("match-threshold", "20")));
+    stage.setUseDistinctFeatureMatchTest(args.flag("distinct-matches"));
+    stage.setRansacReprojectionMatchingThreshold(std::stod(args.get("ransac-matching-threshold", "0.006")));
+    const auto t1 = std::chrono::steady_clock::now();
+    std::vector<ShotMatches> res = stage.calculateShotMatches(scene);
+    stage.calculateHomography(res);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    report(res, strategy->matchPairs(scene.shots.size()).size(), dt, true);
+    return 0;
 }
 
 int main(int argc, char** argv) {
     Args args;
     args.parse(argc, argv);
     const std::string path = args.get("descriptors");
-    if (path.empty()) { usage(); return 0; }
+    const std::vector<std::string> imagePaths = args.all("image");
+    if (path.empty() && imagePaths.empty()) { usage(); return 0; }
     try {
         const int loglevel = std::stoi(args.get("loglevel", "2"));
         const std::string det = args.get("feature-detector");
         int limit = std::stoi(args.get("feature-limit", "10000"));
         if (limit >= SFM_MAX_ROWS) throw std::invalid_argument("feature-limit must stay below 262144");
+        if (!imagePaths.empty()) return runFromImages(args, imagePaths, det, limit, loglevel);
         std::ifstream f(path, std::ios::binary);
         if (!f) throw std::runtime_error("cannot open " + path);
         char magic[4]; uint32_t hdr[4];

@@ -96,9 +96,17 @@ void IFeatureMatchingStrategy::calculateShotMatches(const Scene& scene, std::sha
     o.distinct = stage_.distinct ? 1 : 0;
     o.min_match_count = stage_.minMatchCount;
     sfm_result* res = nullptr;
-    // one call for the whole scene: bank upload (pipelined with the matching when the Mats are page-locked) + all pairs
-    check(ctx, sfm_match_pairs_from_host(ctx, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(),
-                                         depth, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
+    if (scene.bankResident) {
+        // the feature extractor left descriptors + keypoints of these shots on the device: nothing to upload
+        int n_bank = 0;
+        check(ctx, sfm_bank_info(ctx, &n_bank, nullptr, nullptr));
+        if (n_bank != static_cast<int>(shots.size())) throw MatcherError(SFM_ERR_STATE, "resident bank does not belong to this scene");
+        check(ctx, sfm_match_pairs(ctx, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
+    } else {
+        // one call for the whole scene: bank upload (pipelined with the matching when the Mats are page-locked) + all pairs
+        check(ctx, sfm_match_pairs_from_host(ctx, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(),
+                                             depth, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
+    }
     const int64_t* off = sfm_result_offsets(res);
     const sfm_dmatch* m = sfm_result_matches(res);
     const uint8_t* dr = sfm_result_dropped(res);
@@ -127,6 +135,7 @@ std::vector<ShotMatches> MatchingStage::calculateShotMatches(const Scene& scene)
     const auto& dropped = strategy_->lastDropped();
     keptPair_.clear();
     lastShots_ = scene.getShots();
+    lastBankResident_ = scene.bankResident;
     lastPairs_ = strategy_->matchPairs(lastShots_.size());
     for (std::size_t p = 0; p < all.size(); ++p)
         if (!dropped[p]) { kept.push_back(std::move(all[p])); keptPair_.push_back(p); }
@@ -146,11 +155,12 @@ void MatchingStage::calculateHomography(std::vector<ShotMatches>& shotMatches) {
     for (std::size_t i = 0; i < n; ++i) {
         const Shot& s = *lastShots_[i];
         nrows[i] = s.descriptors.empty() ? 0 : s.descriptors.rows;
-        if (nrows[i] > 0 && !s.keypointPts) throw std::invalid_argument("calculateHomography: shot without keypoints");
+        if (nrows[i] > 0 && !s.keypointPts && !lastBankResident_) throw std::invalid_argument("calculateHomography: shot without keypoints");
         pts[i] = s.keypointPts;
         steps[i] = s.keypointStep ? s.keypointStep : 8;
     }
-    check(ctx, sfm_keypoints_upload(ctx, static_cast<int>(n), pts.data(), nrows.data(), steps.data()));
+    if (!lastBankResident_)          // sfm_bank_from_features already placed the keypoints next to the descriptors
+        check(ctx, sfm_keypoints_upload(ctx, static_cast<int>(n), pts.data(), nrows.data(), steps.data()));
     // SfM.cpp:615-620 (the reference takes rightSize.height twice; mirrored)
     std::vector<double> thr(lastPairs_.size());
     for (std::size_t p = 0; p < lastPairs_.size(); ++p) {
@@ -164,6 +174,45 @@ void MatchingStage::calculateHomography(std::vector<ShotMatches>& shotMatches) {
     check(ctx, sfm_homography_inlier_ratios(ctx, thr.data(), static_cast<int64_t>(thr.size()), nullptr, ratios.data(), nullptr,
                                             nullptr, nullptr));
     for (std::size_t k = 0; k < shotMatches.size(); ++k) shotMatches[k].homographyInlierRatio = ratios[keptPair_[k]];
+}
+
+GpuSiftFeatureDetector::GpuSiftFeatureDetector(const std::shared_ptr<GpuDescriptorMatcher>& matcher, int nfeatures, int nOctaveLayers,
+                                               double contrastThreshold, double edgeThreshold, double sigma)
+    : matcher_(matcher) {
+    if (!matcher) throw std::invalid_argument("Der Feature Detektor braucht den GPU Kontext des Matchers.");
+    sfm_sift_opts_default(&opts_);
+    opts_.n_features = nfeatures;
+    opts_.n_octave_layers = nOctaveLayers;
+    opts_.contrast_threshold = contrastThreshold;
+    opts_.edge_threshold = edgeThreshold;
+    opts_.sigma = sigma;
+}
+
+void GpuSiftFeatureDetector::extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features) {
+    sfm_ctx* ctx = matcher_->context();
+    if (scene.shots.empty())
+        for (std::size_t i = 0; i < images.size(); ++i) scene.shots.push_back(std::make_shared<Shot>());
+    if (scene.shots.size() != images.size()) throw std::invalid_argument("extractFeatures: one image per shot");
+    scene.bankResident = false;
+    features.assign(images.size(), Features{});
+    check(ctx, sfm_features_clear(ctx));
+    for (std::size_t i = 0; i < images.size(); ++i) {
+        const GrayImage& im = images[i];
+        int32_t n = 0;
+        check(ctx, sfm_features_extract_sift(ctx, im.data, im.rows, im.cols, im.step, &opts_, &n));
+        Features& f = features[i];
+        f.keypoints.resize(static_cast<std::size_t>(n));
+        f.descriptors.resize(static_cast<std::size_t>(n) * 128);
+        if (n > 0) check(ctx, sfm_features_download(ctx, static_cast<int>(i), &n, f.keypoints.data(), f.descriptors.data()));
+        Shot& s = *scene.shots[i];
+        s.descriptors = DescriptorMat{f.descriptors.data(), n, 128, 128, SFM_CV_8U};
+        s.keypointPts = n > 0 ? &f.keypoints[0].x : nullptr;
+        s.keypointStep = sizeof(sfm_keypoint);
+        s.imageWidth = im.cols;
+        s.imageHeight = im.rows;
+    }
+    check(ctx, sfm_bank_from_features(ctx));
+    scene.bankResident = true;
 }
 
 std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& det, const std::string& mat, int device,

@@ -9,6 +9,8 @@
 //   IFeatureMatchingStrategy + Unordered/Video/Grid strategies                (IFeatureMatchingStrategy.h:34-48 ...)
 //   MatchingStage                <-> SfM::calculateShotMatches + its setters  (SfM.cpp:542-575, :52-79) and
 //                                    SfM::calculateHomography                 (SfM.cpp:599-637)
+//   GpuSiftFeatureDetector       <-> cv::Ptr<cv::Feature2D> of PhotogrammetrieCli::configureFeatureDetector
+//                                    (PhotogrammetrieCli.cpp:342-357) + the loop of SfM::extractFeatures (SfM.cpp:577-597)
 //
 // The strategies here do not loop over pairs calling knnMatch: they hand the whole pair list to
 // sfm_match_pairs (one bank upload, batched kernels), which is the throughput path.
@@ -79,7 +81,22 @@ struct Shot {
 
 struct Scene {
     std::vector<std::shared_ptr<Shot>> shots;
+    // set by GpuSiftFeatureDetector::extractFeatures: descriptors and keypoints of exactly these shots already form the
+    // matcher's device bank (sfm_bank_from_features), the strategies and the homography stage upload nothing
+    bool bankResident = false;
     const std::vector<std::shared_ptr<Shot>>& getShots() const { return shots; }
+};
+
+// Features (CameraShot.h:39-42) as the device extractor returns them: cv::KeyPoint minus class_id, CV_8U descriptor rows
+struct Features {
+    std::vector<sfm_keypoint> keypoints;
+    std::vector<uint8_t> descriptors;       // keypoints.size() x 128
+};
+
+struct GrayImage {              // subset of the CV_8UC1 cv::Mat that Shot::loadImage + cv::SIFT's grey conversion yield
+    const uint8_t* data = nullptr;
+    int rows = 0, cols = 0;
+    std::size_t step = 0;       // bytes between rows (0 = dense)
 };
 
 struct ShotMatches {
@@ -181,6 +198,23 @@ private:
     std::vector<std::size_t> keptPair_;                      // pair-list position of every ShotMatches returned last
     std::vector<std::shared_ptr<Shot>> lastShots_;
     PairList lastPairs_;
+    bool lastBankResident_ = false;
+};
+
+// cv::SIFT::create(featureLimit, 3, 0.09) (PhotogrammetrieCli.cpp:355) running on the matcher's GPU context, and the loop of
+// SfM::extractFeatures around it.  The extracted descriptors stay on the device and become the matcher's bank.
+class GpuSiftFeatureDetector {
+public:
+    explicit GpuSiftFeatureDetector(const std::shared_ptr<GpuDescriptorMatcher>& matcher, int nfeatures = 10000, int nOctaveLayers = 3,
+                                    double contrastThreshold = 0.09, double edgeThreshold = 10.0, double sigma = 1.6);
+    // SfM::extractFeatures: detect + compute for every image (call order = shot order).  features[i] receives what
+    // Shot::setFeatures stores; the shots of `scene` (one per image, created if the scene is empty) get their descriptor /
+    // keypoint views pointed at features[i], their image size set, and scene.bankResident = true.
+    void extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features);
+
+private:
+    std::shared_ptr<GpuDescriptorMatcher> matcher_;
+    sfm_sift_opts opts_;
 };
 
 // PhotogrammetrieCli::configureFeatureMatcher / configureFeatureMatcherStrategy (PhotogrammetrieCli.cpp:320-392)

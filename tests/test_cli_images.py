@@ -1,0 +1,70 @@
+"""sfm_match_cli -Pimage=...: the C++ host mirror of SfM::extractFeatures -> calculateShotMatches -> calculateHomography
+(host/matching.{h,cpp}: GpuSiftFeatureDetector, MatchingStage) driven with the reference's switch grammar."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import workloads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "sfm-mvs-pipeline_b200", "sfm_match_cli")
+
+
+def write_pgm(path, img):
+    with open(path, "wb") as f:
+        f.write(b"P5\n# written by the test\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(np.ascontiguousarray(img, np.uint8).tobytes())
+
+
+def run_cli(*args):
+    return subprocess.run([CLI, *args], capture_output=True, text=True, timeout=300)
+
+
+def test_pgm_errors_are_reported_like_the_reference_reports_exceptions(tmp_path):
+    # main.cpp:26-34: the exception text is printed, the process returns 0
+    bad = tmp_path / "bad.pgm"
+    bad.write_bytes(b"P6\n4 4\n255\n" + bytes(48))
+    out = run_cli(f"-Pimage={bad}")
+    assert out.returncode == 0 and "not a binary PGM" in out.stderr
+    short = tmp_path / "short.pgm"
+    short.write_bytes(b"P5\n40 40\n255\n" + bytes(100))
+    out = run_cli(f"-Pimage={short}")
+    assert out.returncode == 0 and "truncated PGM" in out.stderr
+    good = tmp_path / "good.pgm"
+    write_pgm(good, workloads.synthetic_photo(0, 60, 80))
+    out = run_cli(f"-Pimage={good}", "-Pfeature-detector=ORB")
+    assert "ORB extraction is not built" in out.stderr
+    import torch
+    if not torch.cuda.is_available():
+        out = run_cli(f"-Pimage={good}")
+        assert out.returncode == 0 and "no CUDA device usable" in out.stderr      # parsed the image, then no silent CPU path
+
+
+@pytest.mark.gpu
+def test_cli_extracts_matches_and_rates_the_pairs(tmp_path, sfm):
+    a = workloads.synthetic_photo(11, 240, 320)
+    imgs = [a, np.roll(a, (3, 5), axis=(0, 1)), workloads.synthetic_photo(12, 200, 280)]
+    paths = []
+    for i, im in enumerate(imgs):
+        paths.append(str(tmp_path / f"shot{i}.pgm"))
+        write_pgm(paths[-1], im)
+    out = run_cli(*[f"-Pimage={p}" for p in paths], "-Pmatch-threshold=4", "-Pransac-matching-threshold=-3")
+    assert out.returncode == 0 and "[ERROR]" not in out.stderr, out.stderr
+    head = re.search(r"images=(\d+) keypoints=(\d+)", out.stdout)
+    tail = re.search(r"pairs=(\d+) kept=(\d+) matches=(\d+)", out.stdout)
+    assert head and tail, out.stdout
+    # the same through the Python binding of the same ABI
+    m = sfm.Matcher(0)
+    m.features_clear()
+    n_kp = sum(m.extract_sift(im, contrast_threshold=0.09, n_features=10000) for im in imgs)
+    m.bank_from_features()
+    res = m.match_pairs(sfm.select_pairs(3, 0, 0), sfm.NORM_L2, min_match_count=4)
+    kept = [p for p in range(3) if not res.dropped[p]]
+    assert (int(head.group(1)), int(head.group(2))) == (3, n_kp)
+    assert (int(tail.group(1)), int(tail.group(2)), int(tail.group(3))) == (3, len(kept), sum(len(res[p]) for p in kept))
+    ratios = {(l, r): float(v) for l, r, v in re.findall(r"shot(\d)\.pgm : \S*shot(\d)\.pgm -> \d+ homographyInlierRatio: (\S+)", out.stdout)}
+    assert ratios[("0", "1")] > 0.8
+    m.close()
