@@ -71,3 +71,19 @@ def test_shared_code_against_cv2_golden(harness):
     kp_h, desc_h, ncand = run_harness(harness, gpyr, n_oct, 3, 0.09)
     r = sc.assert_close(gold["insel1_kp_009"], gold["insel1_desc_009"], kp_h, desc_h, "harness vs cv2")
     assert r["n_b"] == 320 and ncand > 320
+
+
+@pytest.mark.parametrize("seed,shape", [(1, (97, 131)), (2, (64, 200)), (3, (150, 75))])
+def test_shared_code_on_random_images_of_odd_sizes(harness, seed, shape):
+    """Smoothed noise, odd sizes (ragged octave sizes, borders): the host build of the shared code and the restatement walk the
+    same pyramid to the same keypoints."""
+    rng = np.random.default_rng(seed)
+    img = rng.random(shape).astype(np.float32)
+    img = S.gaussian_blur(img, 1.5)
+    img = np.rint(255 * (img - img.min()) / (img.max() - img.min())).astype(np.uint8)
+    kp_o, gpyr = S.detect(img, contrast_threshold=0.03, return_pyramid=True)
+    desc_o = S.compute(img, kp_o, gpyr=gpyr)
+    kp_h, desc_h, ncand = run_harness(harness, gpyr, len(gpyr) // 6, 3, 0.03)
+    assert len(kp_o) > 5 and len(kp_h) == len(kp_o) and ncand >= len(kp_o) // 2
+    assert np.array_equal(kp_h["octave"], kp_o["octave"]) and np.array_equal(kp_h["x"], kp_o["x"]) and np.array_equal(kp_h["y"], kp_o["y"])
+    assert np.abs(desc_h.astype(np.int32) - desc_o.astype(np.int32)).max() <= 1
