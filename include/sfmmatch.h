@@ -195,7 +195,8 @@ int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t
  * sfm_features_download copies one image's keypoints / descriptors to the host (Shot::setFeatures needs them for the
  * later pipeline stages).  Parity with cv::SIFT is a tolerance (float arithmetic with data-dependent decisions):
  * tests/_sift_compare.py states it.  With n_features > 0 the survivors of retainBest keep the sorted order (OpenCV
- * leaves them in the order std::nth_element produced; the set is the same).
+ * leaves them in the order std::nth_element produced; the set is the same).  Descriptors come from the detection pyramid
+ * (cv::SIFT::compute on its own rebuilds it without the 2x upsampling when no keypoint lies in octave -1: DESIGN.md section 8).
  * max_keypoints bounds the per-image lists (0 = 262143, the matcher's per-image limit); more -> SFM_ERR_CAPACITY. */
 typedef struct sfm_keypoint {      /* cv::KeyPoint without class_id */
     float   x, y, size, angle, response;
