@@ -158,7 +158,7 @@ struct HomographyArgs {
     int32_t* best_hyp;           // out: hypothesis number that produced it (may be null)
 };
 cudaError_t launch_homography_ransac(const HomographyArgs& a, cudaStream_t s);
-// ---- sift.cu: feature extraction, SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:345-354)
+// ---- sift.cu: feature extraction, SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:342-357)
 struct SiftParams {
     int n_layers;                // nOctaveLayers
     int n_features;              // nfeatures (retainBest), 0 = all

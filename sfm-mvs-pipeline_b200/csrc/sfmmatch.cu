@@ -1342,7 +1342,7 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
     return SFM_OK;
 }
 
-// ---- SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:345-354) on the device
+// ---- SfM::extractFeatures (SfM.cpp:577-597) with cv::SIFT (PhotogrammetrieCli.cpp:342-357) on the device
 static_assert(sizeof(sfm_keypoint) == 24, "sfm_keypoint layout (= sift::Keypoint of csrc/sift_core.cuh)");
 static_assert(sizeof(sfm_sift_opts) == 40, "sfm_sift_opts layout");
 

@@ -1,21 +1,21 @@
 // sift.cu — feature extraction on the device: SfM::extractFeatures (SfM.cpp:577-597) with the
-// detector of PhotogrammetrieCli.cpp:345-354, cv::SIFT.  One grey image in, sorted + deduplicated keypoints and their
+// detector of PhotogrammetrieCli.cpp:342-357, cv::SIFT::create(featureLimit, 3, 0.09).  One grey image in, sorted + deduplicated keypoints and their
 // 128-byte descriptors out, both device-resident so that the descriptor bank of the matching stage is filled without a
 // host round trip (sfm_bank_from_features).
 //
-// Kernels (all HBM / L2 bound, fp32, compiled with --fmad=false so that the pyramid is reproducible to the bit):
+// Kernels (fp32, compiled with --fmad=false so that the pyramid is reproducible to the bit):
 //   upsample2x_kernel        u8 grey -> float, 2x INTER_LINEAR (createInitialImage)
 //   gauss_blur_kernel        separable Gaussian, BORDER_REFLECT_101, both passes fused through shared memory:
 //                            every pyramid level is read once and written once
 //   downsample_kernel        octave base = every second pixel of level [nOctaveLayers] of the previous octave
 //   extrema_kernel           26-neighbour extrema of the DoG (differences taken on the fly) -> candidate list
-//   refine_orient_kernel     adjustLocalExtrema + calcOrientationHist per candidate -> keypoint list
+//   refine_orient_kernel     adjustLocalExtrema + calcOrientationHist, one warp per candidate -> keypoint list
 //   bucket_* / scatter_kernel / dedupe_kernel      KeyPointsFilter::removeDuplicatedSorted + firstOctave correction
 //   retain_best_kernel       KeyPointsFilter::retainBest (nfeatures = the reference's feature-limit)
-//   descriptor_kernel        calcSIFTDescriptor per keypoint -> u8 rows
-// The per-keypoint arithmetic is sift_core.cuh (shared with the host test harness); one thread walks one keypoint in
-// OpenCV's sample order, which keeps the float accumulation order of the histograms — and with it every borderline
-// decision — identical to the serial algorithm.
+//   descriptor_kernel        calcSIFTDescriptor, one warp per keypoint -> u8 rows
+// The per-keypoint arithmetic is sift_core.cuh (shared with the host test harness).  The warps walk the samples of a
+// keypoint in OpenCV's order and add the contributions to every histogram bin in that order, which keeps the float sums —
+// and with them every borderline decision — identical to the serial algorithm.
 #include <cmath>
 #include <cstdio>
 #include <string>

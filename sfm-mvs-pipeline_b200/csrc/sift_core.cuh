@@ -1,5 +1,5 @@
 // sift_core.cuh — per-keypoint arithmetic of the feature-extraction stage (SfM::extractFeatures, SfM.cpp:577-597, with the
-// detector PhotogrammetrieCli.cpp:345-354 configures: cv::SIFT).  The functions follow the published algorithm of OpenCV's
+// detector PhotogrammetrieCli.cpp:342-357 configures: cv::SIFT).  The functions follow the published algorithm of OpenCV's
 // sift.simd.hpp (adjustLocalExtrema, calcOrientationHist, calcSIFTDescriptor) in float32 and in the same operation and
 // accumulation order; they are __host__ __device__ so that the kernels of sift.cu and the host test harness
 // (tests/sift_host_harness.cpp) run the very same code.

@@ -62,7 +62,7 @@ def test_keypoints_and_descriptors_equal_restatement(m, shape, ct):
 
 def test_reference_photo_against_cv2_golden(m, gold):
     m.features_clear()
-    m.extract_sift(gold["insel1_gray"], contrast_threshold=0.09)          # PhotogrammetrieCli.cpp:345-354
+    m.extract_sift(gold["insel1_gray"], contrast_threshold=0.09)          # PhotogrammetrieCli.cpp:355 (limit not reached)
     kp, desc = m.features_download(0)
     r = sc.assert_close(gold["insel1_kp_009"], gold["insel1_desc_009"], kp, desc, "insel vs cv2")
     assert r["n_b"] in range(316, 325)

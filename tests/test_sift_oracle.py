@@ -1,6 +1,8 @@
 """The numpy restatement of cv::SIFT (oracle/sift_np.py) against golden vectors written by cv2 4.13.0
 (tests/golden/make_golden_sift.py): the reference's own photograph with the reference's detector settings
-(PhotogrammetrieCli.cpp:345-354: SIFT::create(0, 3, 0.09); SfM.cpp:584-588: detect() then compute()), and a synthetic image."""
+(PhotogrammetrieCli.cpp:342-357: SIFT::create(featureLimit = 10000, 3, 0.09) — the limit is not reached on this image, so
+nfeatures = 0 gives the same list; a limit of 100 is exercised separately; SfM.cpp:584-588: detect() then compute()), and a
+synthetic image."""
 import os
 
 import numpy as np
