@@ -197,6 +197,8 @@ int sfm_homography_inlier_ratios(sfm_ctx *ctx, const double *thresholds, int64_t
  * tests/_sift_compare.py states it.  With n_features > 0 the survivors of retainBest keep the sorted order (OpenCV
  * leaves them in the order std::nth_element produced; the set is the same).  Descriptors come from the detection pyramid
  * (cv::SIFT::compute on its own rebuilds it without the 2x upsampling when no keypoint lies in octave -1: DESIGN.md section 8).
+ * n_octave_layers (1..8), edge_threshold and sigma are honoured; on the GPU only the reference's values (3, 10, 1.6) have
+ * been exercised so far, the other values through the host build of the same per-keypoint code (tests/test_sift_core_host.py).
  * max_keypoints bounds the per-image lists (0 = 262143, the matcher's per-image limit); more -> SFM_ERR_CAPACITY. */
 typedef struct sfm_keypoint {      /* cv::KeyPoint without class_id */
     float   x, y, size, angle, response;

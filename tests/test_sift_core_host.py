@@ -87,3 +87,15 @@ def test_shared_code_on_random_images_of_odd_sizes(harness, seed, shape):
     assert len(kp_o) > 5 and len(kp_h) == len(kp_o) and ncand >= len(kp_o) // 2
     assert np.array_equal(kp_h["octave"], kp_o["octave"]) and np.array_equal(kp_h["x"], kp_o["x"]) and np.array_equal(kp_h["y"], kp_o["y"])
     assert np.abs(desc_h.astype(np.int32) - desc_o.astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("n_layers,ct,et,sigma", [(4, 0.04, 10.0, 1.6), (2, 0.03, 5.0, 1.6), (3, 0.04, 10.0, 1.2)])
+def test_shared_code_with_other_detector_parameters(harness, n_layers, ct, et, sigma):
+    """nOctaveLayers / edgeThreshold / sigma other than the reference's (3, 10, 1.6): restatement and shared code still agree."""
+    img = workloads.synthetic_photo(4, 200, 260)
+    kp_o, gpyr = S.detect(img, n_layers, ct, et, sigma, return_pyramid=True)
+    desc_o = S.compute(img, kp_o, n_layers, sigma, gpyr=gpyr)
+    kp_h, desc_h, _ = run_harness(harness, gpyr, len(gpyr) // (n_layers + 3), n_layers, ct, et, sigma)
+    assert len(kp_o) > 100 and len(kp_h) == len(kp_o)
+    assert np.array_equal(kp_h["octave"], kp_o["octave"]) and np.array_equal(kp_h["x"], kp_o["x"]) and np.array_equal(kp_h["y"], kp_o["y"])
+    assert np.abs(desc_h.astype(np.int32) - desc_o.astype(np.int32)).max() <= 1

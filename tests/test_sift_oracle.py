@@ -148,3 +148,20 @@ def test_compute_without_octave_minus_one():
         one_call[i] = S.sift_descriptor(gpyr[(o + 1) * 6 + layer], k["x"] * scale, k["y"] * scale, angle, k["size"] * scale * np.float32(0.5))
     d = np.abs(one_call - separate)
     assert 0 < d.max() <= 8 and (d > 2).mean() < 0.03
+
+
+@pytest.mark.parametrize("n_layers,ct,et,sigma", [(4, 0.04, 10.0, 1.6), (2, 0.03, 5.0, 1.6), (3, 0.04, 10.0, 1.2)])
+def test_other_detector_parameters_against_cv2_run_here(n_layers, ct, et, sigma):
+    """The ABI exposes cv::SIFT::create's other arguments; the restatement follows cv2 there too (run live, skipped without cv2)."""
+    try:
+        import cv2
+    except ImportError:
+        pytest.skip("cv2 not importable")
+    img = workloads.synthetic_photo(4, 200, 260)
+    det = cv2.SIFT_create(0, n_layers, ct, et, sigma)
+    kp = det.detect(img, None)
+    kp, desc = det.compute(img, kp)
+    ref = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave) for k in kp], S.KEYPOINT_DTYPE)
+    kp_o = S.detect(img, n_layers, ct, et, sigma)
+    desc_o = S.compute(img, kp_o, n_layers, sigma)
+    sc.assert_close(ref, desc.astype(np.uint8), kp_o, desc_o.astype(np.uint8), f"{n_layers} {ct} {et} {sigma}")
