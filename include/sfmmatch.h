@@ -215,6 +215,11 @@ typedef struct sfm_sift_opts {
     int32_t reserved;
 } sfm_sift_opts;
 void sfm_sift_opts_default(sfm_sift_opts *o);
+/* Host-side helper in front of the extractor: the grey conversion cv::SIFT applies to a colour photograph
+ * (cvtColor COLOR_BGR2GRAY on 8-bit data: (B*3735 + G*19235 + R*9798 + 2^14) >> 15).  channels = 3 or 4 (alpha ignored),
+ * rgb_order != 0 for R,G,B[,A] input; steps in bytes, 0 = dense.  No GPU involved. */
+int sfm_gray_from_bgr(const uint8_t *src, int rows, int cols, size_t step_bytes, int channels, int rgb_order,
+                      uint8_t *gray, size_t gray_step_bytes);
 int sfm_features_clear(sfm_ctx *ctx);
 int sfm_features_extract_sift(sfm_ctx *ctx, const uint8_t *gray, int rows, int cols, size_t step_bytes,
                               const sfm_sift_opts *opts, int32_t *n_keypoints);

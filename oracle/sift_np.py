@@ -74,6 +74,13 @@ def cv_round(v):
     return int(np.rint(v))
 
 
+def bgr_to_gray(img):
+    """cvtColor(COLOR_BGR2GRAY) on 8-bit data, what cv::SIFT applies to a colour image first (color_rgb.simd.hpp RGB2Gray<uchar>:
+    BT.601 weights in 15-bit fixed point)."""
+    b, g, r = (np.asarray(img)[..., i].astype(np.int64) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
 # ---------------------------------------------------------------------------------------------- image pyramid
 def gaussian_kernel(sigma):
     """cv::GaussianBlur(src, dst, Size(), sigma) on CV_32F: ksize = cvRound(sigma * 4 * 2 + 1) | 1, normalised exp kernel."""

@@ -34,7 +34,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios",
            "sfm_homography_opts_default", "sfm_sift_opts_default", "sfm_features_clear", "sfm_features_extract_sift",
            "sfm_features_count", "sfm_features_download", "sfm_bank_from_features", "sfm_features_last_counts",
-           "sfm_features_pyramid_level", "sfm_features_last_profile"]
+           "sfm_features_pyramid_level", "sfm_features_last_profile", "sfm_gray_from_bgr"]
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4")])          # sfm_keypoint = cv::KeyPoint without class_id
@@ -90,6 +90,22 @@ def select_pairs(n_shots: int, feature_sequence: int = 0, feature_gridlength: in
     out = np.zeros((n.value, 2), np.int32)
     _lib.sfm_select_pairs(C.c_int(n_shots), C.c_int(feature_sequence), C.c_int(feature_gridlength),
                           out.ctypes.data_as(C.c_void_p), C.c_int64(n.value), C.byref(n))
+    return out
+
+
+def gray_from_bgr(img: np.ndarray, rgb_order: bool = False) -> np.ndarray:
+    """The grey image cv::SIFT derives from a colour photograph (cvtColor BGR2GRAY, 8 bit); host arithmetic, no GPU."""
+    img = np.asarray(img)
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4):
+        raise SfmError(ERR_INVALID, "gray_from_bgr needs a uint8 [rows, cols, 3 or 4] image")
+    if img.size and (img.strides[2] != 1 or img.strides[1] != img.shape[2]):
+        img = np.ascontiguousarray(img)
+    out = np.empty(img.shape[:2], np.uint8)
+    rc = _lib.sfm_gray_from_bgr(C.c_void_p(img.ctypes.data if img.size else None), C.c_int(img.shape[0]), C.c_int(img.shape[1]),
+                                C.c_size_t(img.strides[0] if img.shape[0] > 1 else 0), C.c_int(img.shape[2]), C.c_int(int(rgb_order)),
+                                C.c_void_p(out.ctypes.data if out.size else None), C.c_size_t(0))
+    if rc != OK:
+        raise SfmError(rc, "sfm_gray_from_bgr failed")
     return out
 
 
@@ -328,8 +344,10 @@ class Matcher:
         """detect() + compute() of cv::SIFT::create(n_features, n_octave_layers, contrast_threshold, edge_threshold, sigma) on one grey
         uint8 image; the result is appended to the context's device-resident feature set.  Returns the keypoint count."""
         gray = np.asarray(gray)
+        if gray.dtype == np.uint8 and gray.ndim == 3 and gray.shape[2] in (3, 4):
+            gray = gray_from_bgr(gray)                     # a colour photograph as cv::imread returns it (BGR)
         if gray.dtype != np.uint8 or gray.ndim != 2:
-            raise SfmError(ERR_INVALID, "extract_sift needs a 2-D uint8 (grey) image")
+            raise SfmError(ERR_INVALID, "extract_sift needs a uint8 grey [rows, cols] or BGR [rows, cols, 3] image")
         if gray.size and gray.strides[1] != 1:
             gray = np.ascontiguousarray(gray)
         o = SiftOpts()

@@ -4,7 +4,7 @@
 //   -Pfeature-detector=SIFT|ORB  -Pfeature-matcher=BF|FLANN  -Pfeature-limit=N  -Pfeature-sequence=S
 //   -Pfeature-gridlength=L  -Pmatch-threshold=T  --distinct-matches  -Ploglevel=0..4
 // Input, either of
-//   -Pimage=<shot.pgm> (repeated, one per shot; binary PGM "P5", 8 bit): SfM::extractFeatures runs on the device
+//   -Pimage=<shot.pgm|shot.ppm> (repeated, one per shot; binary PGM "P5" or PPM "P6", 8 bit): SfM::extractFeatures runs on the device
 //                               (cv::SIFT::create(feature-limit, 3, 0.09), PhotogrammetrieCli.cpp:342-357), the descriptors and
 //                               keypoints stay there for the matching and homography stages
 // or descriptors computed elsewhere:
@@ -54,8 +54,9 @@ struct Args {
     }
 };
 
-// binary PGM (P5, maxval <= 255): what Shot::loadImage + the grey conversion of cv::SIFT hand to the detector
-static void readPgm(const std::string& path, std::vector<uint8_t>& pixels, int& width, int& height) {
+// binary PGM (P5) or PPM (P6), maxval <= 255: what Shot::loadImage hands to the detector.  A colour image goes through the
+// grey conversion cv::SIFT applies first (sfm_gray_from_bgr; PPM stores R, G, B).
+static void readPnm(const std::string& path, std::vector<uint8_t>& pixels, int& width, int& height) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("cannot open " + path);
     auto token = [&]() {
@@ -68,14 +69,19 @@ static void readPgm(const std::string& path, std::vector<uint8_t>& pixels, int& 
         }
         return t;
     };
-    if (token() != "P5") throw std::runtime_error(path + ": not a binary PGM (P5)");
+    const std::string magic = token();
+    if (magic != "P5" && magic != "P6") throw std::runtime_error(path + ": not a binary PGM (P5) or PPM (P6)");
+    const int channels = magic == "P6" ? 3 : 1;
     width = std::stoi(token());
     height = std::stoi(token());
     const int maxval = std::stoi(token());
-    if (width <= 0 || height <= 0 || maxval <= 0 || maxval > 255) throw std::runtime_error(path + ": unsupported PGM header");
+    if (width <= 0 || height <= 0 || maxval <= 0 || maxval > 255) throw std::runtime_error(path + ": unsupported PNM header");
+    std::vector<uint8_t> raw(static_cast<size_t>(width) * height * channels);
+    f.read(reinterpret_cast<char*>(raw.data()), static_cast<std::streamsize>(raw.size()));
+    if (!f) throw std::runtime_error(path + ": truncated PNM");
+    if (channels == 1) { pixels.swap(raw); return; }
     pixels.resize(static_cast<size_t>(width) * height);
-    f.read(reinterpret_cast<char*>(pixels.data()), static_cast<std::streamsize>(pixels.size()));
-    if (!f) throw std::runtime_error(path + ": truncated PGM");
+    if (sfm_gray_from_bgr(raw.data(), height, width, 0, 3, 1, pixels.data(), 0) != SFM_OK) throw std::runtime_error(path + ": grey conversion failed");
 }
 
 static void usage() {
@@ -103,7 +109,7 @@ static int runFromImages(const Args& args, const std::vector<std::string>& paths
     Scene scene;
     for (size_t i = 0; i < paths.size(); ++i) {
         int w = 0, h = 0;
-        readPgm(paths[i], pixels[i], w, h);
+        readPnm(paths[i], pixels[i], w, h);
         images[i] = GrayImage{pixels[i].data(), h, w, static_cast<size_t>(w)};
         auto shot = std::make_shared<Shot>();
         shot->imagePath = paths[i];

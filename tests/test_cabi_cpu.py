@@ -150,3 +150,29 @@ def test_bench_extract_reference_arm_contract():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["value"] > 0 and "SIFT" in d["metric"]
+
+
+def test_gray_conversion_equals_cvtcolor(sfm):
+    """sfm_gray_from_bgr (host arithmetic in front of the extractor) = cv2.cvtColor(BGR2GRAY) on 8-bit data = the restatement,
+    on every 5th value of each channel plus random images; RGB order, 4 channels and strided input included."""
+    from oracle import sift_np as S
+    vals = np.arange(0, 256, 5, dtype=np.uint8)
+    grid = np.stack(np.meshgrid(vals, vals, vals, indexing="ij"), -1).reshape(-1, 52, 3)
+    rng = np.random.default_rng(0)
+    rnd = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    for img in (grid, rnd):
+        got = sfm.gray_from_bgr(img)
+        assert np.array_equal(got, S.bgr_to_gray(img))
+        try:
+            import cv2
+            assert np.array_equal(got, cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+        except ImportError:
+            pass
+    assert np.array_equal(sfm.gray_from_bgr(rnd[..., ::-1], rgb_order=True), sfm.gray_from_bgr(rnd))
+    rgba = np.concatenate([rnd, np.full(rnd.shape[:2] + (1,), 7, np.uint8)], -1)
+    assert np.array_equal(sfm.gray_from_bgr(rgba), sfm.gray_from_bgr(rnd))
+    wide = rng.integers(0, 256, (20, 64, 3), dtype=np.uint8)
+    assert np.array_equal(sfm.gray_from_bgr(wide[:, 8:40]), sfm.gray_from_bgr(np.ascontiguousarray(wide[:, 8:40])))
+    assert sfm.gray_from_bgr(np.zeros((0, 5, 3), np.uint8)).shape == (0, 5)
+    with pytest.raises(sfm.SfmError):
+        sfm.gray_from_bgr(np.zeros((4, 4), np.uint8))

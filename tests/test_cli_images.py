@@ -26,19 +26,24 @@ def run_cli(*args):
 def test_pgm_errors_are_reported_like_the_reference_reports_exceptions(tmp_path):
     # main.cpp:26-34: the exception text is printed, the process returns 0
     bad = tmp_path / "bad.pgm"
-    bad.write_bytes(b"P6\n4 4\n255\n" + bytes(48))
+    bad.write_bytes(b"P3\n4 4\n255\n" + bytes(48))
     out = run_cli(f"-Pimage={bad}")
     assert out.returncode == 0 and "not a binary PGM" in out.stderr
     short = tmp_path / "short.pgm"
     short.write_bytes(b"P5\n40 40\n255\n" + bytes(100))
     out = run_cli(f"-Pimage={short}")
-    assert out.returncode == 0 and "truncated PGM" in out.stderr
+    assert out.returncode == 0 and "truncated PNM" in out.stderr
     good = tmp_path / "good.pgm"
     write_pgm(good, workloads.synthetic_photo(0, 60, 80))
     out = run_cli(f"-Pimage={good}", "-Pfeature-detector=ORB")
     assert "ORB extraction is not built" in out.stderr
+    colour = tmp_path / "colour.ppm"                       # binary PPM: converted with cv::SIFT's grey conversion on the host
+    rgb = np.stack([workloads.synthetic_photo(s, 60, 80) for s in (1, 2, 3)], -1)
+    colour.write_bytes(b"P6\n80 60\n255\n" + rgb.tobytes())
     import torch
     if not torch.cuda.is_available():
+        out = run_cli(f"-Pimage={colour}")
+        assert out.returncode == 0 and "no CUDA device usable" in out.stderr
         out = run_cli(f"-Pimage={good}")
         assert out.returncode == 0 and "no CUDA device usable" in out.stderr      # parsed the image, then no silent CPU path
 
