@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 import workloads  # noqa: E402
 
 METRIC = "image-pairs/sec matched @8192 SIFT/img"
+ORB_METRIC = "image-pairs/sec matched @30000 ORB/img"
 UNIT = "pairs/s"
 
 
@@ -37,12 +38,17 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=200, help="images in the synthetic bank (C3: 200)")
     ap.add_argument("--rows", type=int, default=8192, help="descriptors per image (C3: 8192)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-pairs", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "extract"],
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5", "orb", "knnmatch", "extract"],
                     help="c3 (default, the metric's config) | c4 big-grid 1000x4096 grid(40,3) | c5 big-unordered 500x16384 | "
+                         "orb: 12 images x 30000 ORB (run-orb-sequence.sh's feature limit), all pairs, Hamming | "
+                         "knnmatch: the per-pair cv::DescriptorMatcher integration (host matrices per call) | "
                          "extract: the stage before matching (SfM::extractFeatures, cv::SIFT), a secondary line with its own metric")
+    ap.add_argument("--orb-engine", default="tensor", choices=["tensor", "popc"], help="orb workload: tcgen05 engine (default) or the __popc kernel")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs from ONE process (sfm_mgpu_*: one worker thread per GPU) instead of one process per GPU")
     ap.add_argument("--photo", default="1200x1600", help="extract workload: image size HEIGHTxWIDTH")
     return ap.parse_args()
 
@@ -54,6 +60,8 @@ def apply_workload(a):
         a.images, a.rows, a.seq, a.grid = 1000, 4096, 3, 40
     elif a.workload == "c5":
         a.images, a.rows = 500, 16384
+    elif a.workload == "orb":
+        a.images, a.rows = 12, 30000
     return a
 
 
@@ -62,6 +70,8 @@ def workload_name(a):
         return "C4 synthetic big-grid featurelimit: 1000 images x 4096 SIFT, grid rowLength 40 / sequenceLength 3 (4741 pairs)"
     if a.workload == "c5":
         return "C5 synthetic big-unordered: 500 images x 16384 SIFT 128-d (124750 pairs)"
+    if a.workload == "orb":
+        return f"ORB-like (SURVEY 8d): {a.images} images x {a.rows} 256-bit descriptors, all {a.images * (a.images - 1) // 2} pairs, NORM_HAMMING"
     if a.images == 200 and a.rows == 8192:
         return "C3 synthetic unordered all-pairs: 200 images x 8192 SIFT 128-d (19900 pairs)"
     return f"synthetic unordered all-pairs: {a.images} images x {a.rows} SIFT 128-d ({a.images * (a.images - 1) // 2} pairs)"
@@ -138,24 +148,29 @@ def make_pairs(sfm_or_none, n_images, seq=0, grid=0):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_baseline(bank_getter, pairs, sample_pairs, seed=7):
+def _sample_pairs(pairs, k, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return pairs[rng.choice(len(pairs), size=min(k, len(pairs)), replace=False)]
+
+
+def cpu_baseline(bank_getter, pairs, sample_pairs, seed=7, norm=None, what="NORM_L2"):
     """cv2 (the OpenCV routines the reference's knnMatch resolves to) on a fixed random sample of the pair list."""
     from oracle import cv2_ref
     from oracle.oracle_np import NORM_L2
-    rng = np.random.Generator(np.random.PCG64(seed))
-    sel = pairs[rng.choice(len(pairs), size=min(sample_pairs, len(pairs)), replace=False)]
+    norm = NORM_L2 if norm is None else norm
+    sel = _sample_pairs(pairs, sample_pairs, seed)
     imgs = sorted(set(sel.reshape(-1).tolist()))
     bank = {i: bank_getter(i) for i in imgs}
     cores = os.cpu_count() or 1
     best = None
     for topo in ("inner", "outer"):
-        dt, good = cv2_ref.time_pairs(bank, sel, NORM_L2, 0.7, topology=topo, threads=cores)
+        dt, good = cv2_ref.time_pairs(bank, sel, norm, 0.7, topology=topo, threads=cores)
         v = len(sel) / dt
         if best is None or v > best[0]:
             best = (v, topo, dt, good)
     return {"value": best[0], "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"{len(sel)} random pairs (seed {seed}) of the workload, cv2 {cv2_ref.cv2.__version__} "
-                      f"batchDistance(NORM_L2,K=2)+ratio 0.7 = the OpenCV routine the reference's knnMatch calls; "
+            "sample": f"{len(sel)} random pairs (seed {seed}) drawn from the whole pair list, cv2 {cv2_ref.cv2.__version__} "
+                      f"batchDistance({what},K=2)+ratio 0.7 = the OpenCV routine the reference's knnMatch calls; "
                       f"topology '{best[1]}' (best of pairs-serial/threads-inside and threads-over-pairs), {best[2]:.1f} s",
             "good_matches_in_sample": int(best[3])}
 
@@ -165,246 +180,374 @@ def run_reference(a):
     if rank != 0:
         return
     from oracle import cv2_ref
-    from oracle.oracle_np import NORM_L2
+    from oracle.oracle_np import NORM_L2, NORM_HAMMING
     if not cv2_ref.available():
         _emit(json.dumps({"impl": "reference", "unavailable": "cv2 not importable on this box"}))
         return
+    orb = a.workload == "orb"
+    norm = NORM_HAMMING if orb else NORM_L2
     pairs = make_pairs(None, a.images, a.seq, a.grid)
-    cache = {}
-
-    def get(i):
-        if i not in cache:
-            prev = get(i - 1) if i > 0 else None
-            cache[i] = workloads.sift_like_image(i, a.rows, prev)
-        return cache[i]
-
     cores = os.cpu_count() or 1
     rng = np.random.Generator(np.random.PCG64(7))
     per_step = max(1, min(a.cpu_sample_pairs // 2, len(pairs)))
-    # cap the image range so that bank generation stays bounded
-    pool = pairs[(pairs[:, 1] < min(a.images, 24))] if a.workload == "c3" else pairs[pairs[:, 1] < 90]
-    steps = []
-    for s in range(a.warmup + a.steps):
-        steps.append(pool[rng.choice(len(pool), size=min(per_step, len(pool)), replace=False)])
-    bank = {i: get(i) for i in sorted(set(np.concatenate(steps).reshape(-1).tolist()))}
+    # every step draws its pairs from the WHOLE pair list (C3 / ORB: the whole bank is generated, as in our arm);
+    # the big configurations cap the image range so that bank generation stays bounded
+    if a.workload in ("c3", "orb", "knnmatch"):
+        pool, pool_note = pairs, "the whole pair list"
+    else:
+        pool, pool_note = pairs[pairs[:, 1] < 90], "pairs among images 0..89 (bank generation bounded)"
+    steps = [pool[rng.choice(len(pool), size=min(per_step, len(pool)), replace=False)] for _ in range(a.warmup + a.steps)]
+    need = int(np.concatenate(steps).max()) + 1
+    gen = workloads.orb_like_bank(need, a.rows) if orb else workloads.sift_like_bank(need, a.rows)
+    used = set(np.concatenate(steps).reshape(-1).tolist())
+    bank = {i: gen[i] for i in used}
+    del gen
     # pick the faster thread topology once (untimed)
-    t_in, _ = cv2_ref.time_pairs(bank, steps[0][:4], NORM_L2, 0.7, "inner", cores)
-    t_out, _ = cv2_ref.time_pairs(bank, steps[0][:max(4, min(cores, len(steps[0])))], NORM_L2, 0.7, "outer", cores)
-    topo = "inner" if t_in / 4 <= t_out / max(4, min(cores, len(steps[0]))) else "outer"
+    t_in, _ = cv2_ref.time_pairs(bank, steps[0][:4], norm, 0.7, "inner", cores)
+    n_out = max(4, min(cores, len(steps[0])))
+    t_out, _ = cv2_ref.time_pairs(bank, steps[0][:n_out], norm, 0.7, "outer", cores)
+    topo = "inner" if t_in / min(4, len(steps[0])) <= t_out / min(n_out, len(steps[0])) else "outer"
     for s in range(a.warmup):
-        cv2_ref.time_pairs(bank, steps[s], NORM_L2, 0.7, topo, cores)
-    t0 = time.perf_counter()
+        cv2_ref.time_pairs(bank, steps[s], norm, 0.7, topo, cores)
+    per = []
     n = 0
+    t0 = time.perf_counter()
     for s in range(a.warmup, a.warmup + a.steps):
-        cv2_ref.time_pairs(bank, steps[s], NORM_L2, 0.7, topo, cores)
+        ts = time.perf_counter()
+        cv2_ref.time_pairs(bank, steps[s], norm, 0.7, topo, cores)
+        per.append(len(steps[s]) / (time.perf_counter() - ts))
         n += len(steps[s])
     dt = time.perf_counter() - t0
     v = n / dt
-    sample = (f"each step = {per_step} random pairs of the workload (images 0..23), cv2 {cv2_ref.cv2.__version__} "
-              f"batchDistance+ratio on {cores} host threads, topology '{topo}'")
+    sample = (f"each step = {per_step} random pairs drawn from {pool_note}, cv2 {cv2_ref.cv2.__version__} "
+              f"batchDistance+ratio on {cores} host threads, topology '{topo}'; value = mean over the timed steps")
     _emit(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": ORB_METRIC if orb else METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": sample},
+        "vs_baseline": None, "dtype": "u8" if orb else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample, "median_step_value": float(np.median(per))},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def _sha1_lists(res):
+    import hashlib
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(res.offsets).tobytes())
+    h.update(np.ascontiguousarray(res.matches).tobytes())
+    h.update(np.ascontiguousarray(res.dropped).tobytes())
+    return h.hexdigest()
+
+
+class _Group:
+    """The multi-GPU group behind one interface: 'torchrun' = one process per GPU (sfm_dist_* on this rank's context,
+    the id travels over torch.distributed), 'single' = one process, one worker thread per GPU (sfm_mgpu_*)."""
+
+    def __init__(self, sfm, a, torch, dist):
+        self.sfm, self.torch, self.dist = sfm, torch, dist
+        self.single = bool(a.single_process)
+        self.world = a.gpus if self.single else int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = 0 if self.single else int(os.environ.get("RANK", "0"))
+        self.local = 0 if self.single else int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.multi_proc = (not self.single) and self.world > 1
+        if self.multi_proc:
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+        if self.single:
+            self.g = sfm.MultiGpuMatcher(list(range(self.world)))
+            self.m = self.g.ctx(0)
+            self.ctxs = [self.g.ctx(i) for i in range(self.world)]
+        else:
+            self.g = None
+            self.m = sfm.Matcher(self.local)
+            self.ctxs = [self.m]
+            if self.multi_proc:
+                t = torch.zeros(sfm.DIST_ID_BYTES, dtype=torch.uint8, device=self.dev)
+                if self.rank == 0:
+                    t.copy_(torch.frombuffer(bytearray(sfm.dist_unique_id()), dtype=torch.uint8))
+                dist.broadcast(t, 0)
+                self.m.dist_init(bytes(t.cpu().numpy().tobytes()), self.rank, self.world)
+        self.stream = torch.cuda.ExternalStream(self.m.stream, device=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.multi_proc:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def match(self, pairs, norm, **kw):            # bank resident -> lists in pinned host memory on participant 0
+        if self.single:
+            return self.g.match_pairs(pairs, norm, **kw)
+        return self.m.dist_match_pairs(pairs, norm, **kw)
+
+    def from_host(self, host_list, pairs, norm, **kw):
+        if self.single:
+            return self.g.match_pairs_from_host(host_list, pairs, norm, **kw)
+        return self.m.dist_match_pairs_from_host(host_list, pairs, norm, **kw)
+
+    def reduce_max(self, x):
+        if not self.multi_proc:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(self, xs):
+        if not self.multi_proc:
+            return [int(x) for x in xs]
+        t = self.torch.tensor(list(xs), dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t)
+        return [int(v) for v in t.tolist()]
+
+    def stats(self):
+        out = {"kernel_launches": 0, "h2d_bytes": 0, "d2h_bytes": 0}
+        for c in self.ctxs:
+            for k, v in c.stats().items():
+                out[k] += v
+        return out
+
+    def close(self):
+        if self.single:
+            self.g.close()
+        else:
+            self.m.close()
+        if self.multi_proc:
+            self.dist.destroy_process_group()
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the matcher has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
     sfm = ge.load_package()
-    spec = __import__("importlib").util.spec_from_file_location("sfm_shard", os.path.join(ge.PKG_DIR, "shard.py"))
-    shard = __import__("importlib").util.module_from_spec(spec)
-    spec.loader.exec_module(shard)
-
+    G = _Group(sfm, a, torch, dist)
+    world, rank, dev, m = G.world, G.rank, G.dev, G.m
+    orb = a.workload == "orb"
+    norm = sfm.NORM_HAMMING if orb else sfm.NORM_L2
     n_img, n_rows = a.images, a.rows
+    width = 32 if orb else 128
     pairs = make_pairs(sfm, n_img, a.seq, a.grid)
-    # ---- synthetic bank: rank 0 generates, NCCL broadcast gives every GPU its replica
-    bank_dev = torch.empty((n_img * n_rows, 128), dtype=torch.uint8, device=dev)
+    # ---- the scene as the reference holds it: one host matrix per shot (SIFT: CV_32F integer-valued, ORB: CV_8U),
+    # page-locked.  Rank 0 generates, NCCL hands the bytes to the other processes (each keeps its own host copy).
+    bank_dev = torch.empty((n_img * n_rows, width), dtype=torch.uint8, device=dev)
     if rank == 0:
-        host = np.concatenate(workloads.sift_like_bank(n_img, n_rows))
-        bank_dev.copy_(torch.from_numpy(host))
-    if world > 1:
-        shard.broadcast_bank(bank_dev, 0)
+        gen = workloads.orb_like_bank(n_img, n_rows) if orb else workloads.sift_like_bank(n_img, n_rows)
+        bank_dev.copy_(torch.from_numpy(np.concatenate(gen)))
+        del gen
+    if G.multi_proc:
+        dist.broadcast(bank_dev, 0)
     torch.cuda.synchronize()
-    m = sfm.Matcher(local_rank)
-    rows_per = [n_rows] * n_img
-    offs = [i * n_rows for i in range(n_img)]
-    m.upload_bank_device(bank_dev.data_ptr(), offs, rows_per, 128, sfm.CV_8U)
-    # host copy as the reference holds it: CV_32F integer-valued Mats, page-locked
-    host_f32 = torch.empty((n_img * n_rows, 128), dtype=torch.float32, pin_memory=True)
-    host_f32.copy_(bank_dev.to(torch.float32).cpu())
-    host_np = host_f32.numpy()
+    host = torch.empty((n_img * n_rows, width), dtype=torch.uint8 if orb else torch.float32, pin_memory=True)
+    host.copy_(bank_dev.cpu() if orb else bank_dev.to(torch.float32).cpu())
+    host_np = host.numpy()
     host_list = [host_np[i * n_rows:(i + 1) * n_rows] for i in range(n_img)]
     del bank_dev
+    torch.cuda.empty_cache()
+    rows_per = [n_rows] * n_img
+    kw = {"engine": sfm.ENGINE_SIMT} if (orb and a.orb_engine == "popc") else {}
 
-    all_mine = shard.assign_pairs(pairs, rows_per, world)
-    mine = all_mine[rank]
-    my_pairs = np.ascontiguousarray(pairs[mine])
-    stream = torch.cuda.ExternalStream(m.stream, device=dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    # ---- bank resident on every GPU (one untimed end-to-end call), then warm-up
+    res = G.from_host(host_list, pairs, norm, **kw)
     for _ in range(a.warmup):
-        m.enqueue(my_pairs, sfm.NORM_L2)
-    m.set_profiling(True)
-    barrier()
-    sampler = ClockSampler(local_rank)
+        res = G.match(pairs, norm, **kw)
+    for c in G.ctxs:
+        c.set_profiling(True)
+    G.barrier()
+    sampler = ClockSampler(G.local)
     if rank == 0:
         sampler.start()
-    st0 = m.stats()
+    st0 = G.stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     knn_ms = post_ms = 0.0
     knn_launches = 0
-    e0.record(stream)
+    step_ms = []
+    # SURVEY 8d timing protocol: bank resident; timed region = submit the pair list -> every filtered match list in
+    # pinned host memory on participant 0 (kernels, compaction, gather, D2H), every step
+    e0.record(G.stream)
+    t_wall = time.perf_counter()
     for _ in range(a.steps):
-        m.enqueue(my_pairs, sfm.NORM_L2)
-        pr = m.last_profile()            # waits for this step's last kernel: steps run back to back on the stream
+        ts = time.perf_counter()
+        res = G.match(pairs, norm, **kw)
+        step_ms.append((time.perf_counter() - ts) * 1e3)
+        pr = m.last_profile()
         knn_ms += pr["knn_ms"]; post_ms += pr["post_ms"]; knn_launches += pr["knn_launches"]
-    e1.record(stream)
+    e1.record(G.stream)
     e1.synchronize()
-    barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    G.barrier()
     clocks = sampler.stop() if rank == 0 else None
-    st1 = m.stats()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    launches = torch.tensor([st1["kernel_launches"] - st0["kernel_launches"]], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(launches)
-    m.set_profiling(False)
-    result = m.collect()
+    st1 = G.stats()
+    ms_total = G.reduce_max(e0.elapsed_time(e1))
+    wall_ms = G.reduce_max(wall_ms)
+    launches, = G.reduce_sum([st1["kernel_launches"] - st0["kernel_launches"]])
+    for c in G.ctxs:
+        c.set_profiling(False)
     refine_stats = m.float_stats()
     value = len(pairs) * a.steps / (ms_total / 1e3)
+    sha_value = _sha1_lists(res) if rank == 0 else None
+    total_matches = int(res.offsets[-1]) if rank == 0 else None
 
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with HOST buffers: descriptors of every shot in pinned host memory ->
+    # (each GPU uploads its share, NVLink exchange) -> kernels -> lists in pinned host memory on participant 0
     e2e_ms, h2d, d2h = [], 0, 0
-    if world > 1:
-        packer = sfm.Matcher(local_rank)
-        gathered = torch.empty(n_img * n_rows * 128, dtype=torch.uint8, device=dev)
-    total_matches = None
-    for _ in range(max(2, a.e2e_steps)):             # the first pass also warms allocations; the best pass is reported
-        barrier()
-        s0 = m.stats()
-        ps0 = packer.stats() if world > 1 else None
+    sha_e2e = None
+    for it in range(max(3, a.e2e_steps) + 1):        # the first pass is a warm-up (allocations), not reported
+        G.barrier()
+        s0 = G.stats()
         t0 = time.perf_counter()
-        tr = [t0]
-        if world == 1:
-            pass                                                   # upload is part of the fused call below
-        else:
-            # every rank uploads + packs 1/N of the scene over its own PCIe link, NCCL all-gathers the packed
-            # u8 bank over NVLink, the library adopts the replica (sfm_bank_upload_device)
-            lo, hi = rank * n_img // world, (rank + 1) * n_img // world
-            packer.upload_bank(host_list[lo:hi])
-            ptr, _ = packer.bank_device_ptr(0)
-            part = shard.cuda_view(ptr, (hi - lo) * n_rows * 128, dev)
-            parts = [gathered[r * n_img // world * n_rows * 128:(r + 1) * n_img // world * n_rows * 128] for r in range(world)]
-            dist.all_gather(parts, part)
-            stream.wait_stream(torch.cuda.current_stream(dev))     # the library's stream reads `gathered` next
-            tr.append(time.perf_counter())
-            m.upload_bank_device(gathered.data_ptr(), offs, rows_per, 128, sfm.CV_8U)
-        tr.append(time.perf_counter())
-        if world == 1:
-            # sfm_match_pairs_from_host: pinned CV_32F descriptors -> device (packed to u8 on the GPU, group by group,
-            # overlapped with the matching of resident pairs) -> kernels -> D2H of the compacted lists
-            res = m.match_pairs_from_host(host_list, my_pairs, sfm.NORM_L2)
-            total_matches = int(res.offsets[-1])
-            tr.append(time.perf_counter())
-        else:
-            m.enqueue(my_pairs, sfm.NORM_L2)                       # kernels; lists stay on the GPU ...
-            if os.environ.get("SFM_BENCH_TRACE"):
-                stream.synchronize()                               # trace only: separate the kernels from the gather
-            tr.append(time.perf_counter())
-            g = shard.gather_matches_device(m, mine, all_mine, len(pairs), dev, 0)   # ... NCCL gather, one D2H on rank 0
-            if rank == 0:
-                total_matches = int(g[0][-1])
-        tr.append(time.perf_counter())
-        barrier()
-        e2e_ms.append((time.perf_counter() - t0) * 1e3)
-        if os.environ.get("SFM_BENCH_TRACE") and rank == 0:
-            print("e2e phases ms:", [round((b_ - a_) * 1e3, 2) for a_, b_ in zip(tr[:-1], tr[1:])], file=sys.stderr)
-        s1 = m.stats()
+        r2 = G.from_host(host_list, pairs, norm, **kw)
+        G.barrier()
+        dt = (time.perf_counter() - t0) * 1e3
+        if it > 0:
+            e2e_ms.append(dt)
+        s1 = G.stats()
         h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
-        if world > 1:
-            ps1 = packer.stats()
-            h2d += ps1["h2d_bytes"] - ps0["h2d_bytes"]
-            d2h += shard.LAST_D2H_BYTES if rank == 0 else 8       # rank 0: the gathered lists; others: their match total
-    t = torch.tensor([min(e2e_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        hb = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
-        dist.all_reduce(hb)
-        h2d, d2h = int(hb[0].item()), int(hb[1].item())
-    e2e_value = len(pairs) / (float(t.item()) / 1e3)
+        if os.environ.get("SFM_BENCH_TRACE") and not G.single:
+            print(f"rank {rank} e2e {dt:.2f} ms phases", [round(x, 2) for x in m.dist_last_phases()[:5]], file=sys.stderr)
+        if rank == 0:
+            sha_e2e = _sha1_lists(r2)
+    e2e_med = G.reduce_max(float(np.median(e2e_ms)))
+    e2e_best = G.reduce_max(min(e2e_ms))
+    h2d, d2h = G.reduce_sum([h2d, d2h])
+
+    # ---- byte identity: participant 0 matches the WHOLE list alone on its replica and compares SHA-1s
+    sha_single = None
+    if rank == 0:
+        single = m.match_pairs(pairs, norm, **kw)
+        sha_single = _sha1_lists(single)
+        if not (sha_single == sha_value == sha_e2e):
+            raise SystemExit(f"byte identity violated: single-GPU {sha_single} / {world}-GPU {sha_value} / e2e {sha_e2e}")
 
     if rank == 0:
         bf16_burst, bf16_sust, hbm, src = measured_peaks()
-        ops_per_step_rank = 2.0 * n_rows * n_rows * 128 * len(my_pairs)
-        achieved = ops_per_step_rank * a.steps / (knn_ms / 1e3) / 1e12 if knn_ms > 0 else None
-        peak_i8 = 2.0 * bf16_sust
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "knn_tcv_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        n_mine = int((sfm.dist_assign_pairs(pairs, rows_per, world) == 0).sum())
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "metric": ORB_METRIC if orb else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name(a), "pairs": int(len(pairs)), "parallelism": f"pair-list x{world}",
+            "config": {"workload": workload_name(a), "pairs": int(len(pairs)),
+                       "parallelism": f"pair-list x{world}" + (" (one process, one thread per GPU: sfm_mgpu_*)" if G.single else
+                                                               (" (one process per GPU: sfm_dist_*)" if world > 1 else "")),
+                       "timed_region": "SURVEY 8d: descriptor bank resident; submit the pair list -> all filtered match lists in pinned "
+                                       "host memory on participant 0 (kernels + compaction + NCCL gather + D2H), every step; CUDA events on "
+                                       "the library stream, max over ranks",
+                       "wall_ms_per_step": wall_ms / a.steps, "median_step_ms_rank0": float(np.median(step_ms)),
                        "l2": "inputs larger than L2 (bank 200 MiB + 512 MiB top-2 staging per batch vs 126 MB L2); no flush",
-                       "engine": "tcgen05 kind::i8, value-only fused top-k epilogue (knn2_l2_u8_tcv_kernel; the library picks the norm-less 4-K-step variant with 64-row chunks when few rows need exact re-ranking, the 5-K-step variant with 32-row chunks otherwise) + exact refine", "matches_per_step": total_matches,
-                       "matches_device_run": int(result.offsets[-1]),
+                       "matches_per_step": total_matches,
+                       "sha1_lists": sha_value, "sha1_single_gpu": sha_single, "sha1_e2e": sha_e2e,
+                       "byte_identical_to_single_gpu": True,
                        "refine": {"rows_reranked_exactly": refine_stats["rows_reranked"], "rows_brute_forced": refine_stats["rows_brute_forced"],
-                                  "query_rows": int(n_rows) * int(len(my_pairs))}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": float(t.item()), "host_buffers": "pinned CV_32F descriptors, as the reference holds them",
-                    "bytes_are": "summed over ranks (every rank uploads 1/N of the scene; NCCL all-gathers the packed bank)"},
-            "gpu_launches": int(launches.item()),
+                                  "query_rows": int(n_rows) * n_mine}},
+            "e2e": {"value": len(pairs) / (e2e_med / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_med, "best_value": len(pairs) / (e2e_best / 1e3), "passes": len(e2e_ms),
+                    "value_is": "median over the passes (max over ranks each)",
+                    "host_buffers": "pinned host matrices, one per shot, as the reference holds them (SIFT: CV_32F)",
+                    "bytes_are": "summed over ranks (every GPU uploads 1/N of the scene over its own PCIe link; NCCL moves the packed bank)"},
+            "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_i8, "unit": "TFLOP/s",
-                         "frac": (achieved / peak_i8) if achieved else None, "traffic": traffic,
-                         "kernel": "knn2_l2_u8_tcv_kernel", "launches": knn_launches,
-                         "avg_launch_ms": knn_ms / max(1, knn_launches),
-                         "algorithmic": "2*Nq*Nt*128 op per pair (SURVEY 8d) x pairs per launch",
-                         "peak_source": f"{src}: 2 x bf16_tflops_sustained ({bf16_sust}) for kind::i8",
-                         "frac_of_bf16_rate": (achieved / bf16_sust) if achieved else None,
-                         "knn_share_of_step": knn_ms / ms_total if ms_total else None},
         }
+        if orb:
+            # SURVEY 8d, ORB: algorithmic bytes = 32 (Nq + Nt) read + 16 per good match written; binding roof = POPC issue rate
+            bytes_step = 32.0 * 2 * n_rows * n_mine + 16.0 * (total_matches or 0) / world
+            popc_step = 8.0 * n_rows * n_rows * n_mine
+            sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+            popc_peak = 148 * 16 * sm_mhz * 1e6
+            ach = bytes_step * a.steps / (knn_ms / 1e3) / 1e9 if knn_ms > 0 else None
+            out["config"]["engine"] = ("knn2_hamming_popc (north_star's kernel: 128-bit loads, __popc on shared-memory tiles)" if kw else
+                                       "tcgen05 kind::i8 on bit-expanded rows (K = 256), exact; --orb-engine popc selects the __popc kernel")
+            out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
+                               "traffic": None, "kernel": "knn2_hamming_popc" if kw else "knn2_l2_u8_tc_kernel<2>", "launches": knn_launches,
+                               "avg_launch_ms": knn_ms / max(1, knn_launches), "peak_source": src,
+                               "algorithmic": "32*(Nq+Nt) B read + 16 B per good match, per pair (SURVEY 8d)",
+                               "note": "all-pairs Hamming is O(Nq*Nt) work over O(N) bytes: HBM is structurally not the binding roof",
+                               "popc_per_s": popc_step * a.steps / (knn_ms / 1e3) if knn_ms > 0 else None,
+                               "popc_roof_per_s": popc_peak,
+                               "popc_roof_frac": (popc_step * a.steps / (knn_ms / 1e3) / popc_peak) if knn_ms > 0 else None,
+                               "knn_share_of_step": knn_ms / ms_total if ms_total else None}
+        else:
+            ops_per_step_rank = 2.0 * n_rows * n_rows * 128 * n_mine
+            achieved = ops_per_step_rank * a.steps / (knn_ms / 1e3) / 1e12 if knn_ms > 0 else None
+            peak_i8 = 2.0 * bf16_sust
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "knn_tcv_traffic.json")
+            if world == 1 and a.workload == "c3" and os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            out["config"]["engine"] = ("tcgen05 kind::i8 (TMA-fed tiles, TMEM accumulators), fused epilogue: per-row top-k of chunk maxima + "
+                                       "ratio-test bound, survivors re-ranked exactly (knn2_l2_u8_tcv_kernel)")
+            out["roofline"] = {"bound": "tensor", "achieved": achieved, "peak": peak_i8, "unit": "TFLOP/s",
+                               "frac": (achieved / peak_i8) if achieved else None, "traffic": traffic,
+                               "traffic_source": "ncu --set full capture of this command committed under profiles/ (N=1 only; null otherwise)",
+                               "kernel": "knn2_l2_u8_tcv_kernel", "launches": knn_launches,
+                               "avg_launch_ms": knn_ms / max(1, knn_launches),
+                               "algorithmic": "2*Nq*Nt*128 op per pair (SURVEY 8d) x pairs per launch",
+                               "peak_source": f"{src}: 2 x bf16_tflops_sustained ({bf16_sust}) for kind::i8",
+                               "frac_of_bf16_rate": (achieved / bf16_sust) if achieved else None,
+                               "knn_share_of_step": knn_ms / ms_total if ms_total else None,
+                               "post_kernels_ms_per_step": post_ms / a.steps}
         if world == 1 and not a.no_cpu_baseline:
             try:
-                cache = {}
-
-                def get(i):
-                    if i not in cache:
-                        cache[i] = host_np[i * n_rows:(i + 1) * n_rows]
-                    return cache[i]
-                out["cpu_baseline"] = cpu_baseline(get, pairs, a.cpu_sample_pairs)
+                out["cpu_baseline"] = cpu_baseline(lambda i: host_list[i], pairs, a.cpu_sample_pairs if not orb else 8,
+                                                   norm=None if not orb else 6, what="NORM_HAMMING" if orb else "NORM_L2")
             except Exception as ex:  # pragma: no cover
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                                        "sample": f"failed: {ex}"}
         _emit(json.dumps(out))
+    G.close()
+
+
+# ------------------------------------------------------------------------------------------ knnmatch workload
+# The Level-1 integration (INTEGRATION.md): the reference's own per-pair loop calling knnMatch(query, train, k = 2) on an
+# injected cv::DescriptorMatcher (UnorderedFeatureMatchingStrategy.cpp:40-65), here sfm_knn_match with HOST matrices for
+# every pair: two H2D + one D2H per pair, ratio filter on the host as the reference does it.
+def run_knnmatch(a):
+    import torch
+    import __graft_entry__ as ge
+    if a.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--workload knnmatch is a single-GPU line")
+    sfm = ge.load_package()
+    m = sfm.Matcher(0)
+    n_img = min(a.images, 24)
+    gen = workloads.sift_like_bank(n_img, a.rows)
+    host = [torch.from_numpy(g.astype(np.float32)).pin_memory().numpy() for g in gen]
+    pairs = make_pairs(sfm, n_img, 0, 0)
+    per_step = min(len(pairs), 64)
+    rng = np.random.Generator(np.random.PCG64(11))
+
+    def step():
+        good = 0
+        for l, r in pairs[rng.choice(len(pairs), size=per_step, replace=False)]:
+            idx, dist = m.knn_match(host[l], host[r], sfm.NORM_L2, 2)
+            good += int((dist[:, 0].astype(np.float64) < dist[:, 1].astype(np.float64) * 0.7).sum())
+        return good
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    s0 = m.stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    s1 = m.stats()
+    v = per_step * a.steps / dt
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"Level-1 integration: knnMatch(query, train, k=2) per pair with host CV_32F matrices, {per_step} random pairs "
+                                   f"of {n_img} images x {a.rows} SIFT per step (sfm_knn_match: 2 H2D + 1 D2H per pair, host ratio filter)",
+                       "note": "secondary line: what the 3-line cv::DescriptorMatcher swap costs against the plugin-level path"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int((s1["h2d_bytes"] - s0["h2d_bytes"]) / a.steps),
+                    "d2h_bytes_per_step": int((s1["d2h_bytes"] - s0["d2h_bytes"]) / a.steps)},
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]), "clocks": sampler.stop()}
+    if not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(lambda i: gen[i], pairs, 16)
+    _emit(json.dumps(line))
     m.close()
-    if world > 1:
-        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------- extract workload
@@ -555,5 +698,7 @@ if __name__ == "__main__":
         (run_extract_reference if args.impl == "reference" else run_extract_ours)(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "knnmatch":
+        run_knnmatch(args)
     else:
         run_ours(args)

@@ -27,6 +27,7 @@ extern "C" {
 #define SFM_ERR_CAPACITY   -3   /* caller buffer too small / train rows >= 2^18 (IMGIDX_ONE) */
 #define SFM_ERR_UNSUPPORTED -4  /* e.g. radius match, k > 2, cross_check with k != 1 semantics */
 #define SFM_ERR_STATE      -5   /* call order violated (e.g. match before bank upload) */
+#define SFM_ERR_NCCL       -6   /* NCCL not loadable, or a collective failed (multi-GPU group only) */
 
 /* cv::NormTypes values used by the reference (PhotogrammetrieCli.cpp:378, :387) */
 #define SFM_NORM_L2        4
@@ -149,6 +150,58 @@ const int64_t    *sfm_result_offsets(const sfm_result *r);   /* n_pairs + 1 entr
 const sfm_dmatch *sfm_result_matches(const sfm_result *r);   /* offsets[n_pairs] entries */
 const uint8_t    *sfm_result_dropped(const sfm_result *r);   /* n_pairs flags: 1 = erased by min_match_count */
 void              sfm_result_free(sfm_result *r);       /* call before sfm_ctx_destroy of the producing context */
+
+/* Multi-GPU group ------------------------------------------------------------------------------------
+ * Replaces the `#pragma omp parallel for` over image pairs of the three strategies
+ * (UnorderedFeatureMatchingStrategy.cpp:40, VideoFeatureMatchingStrategy.cpp:51, GridFeatureMatchingStrategy.cpp:94)
+ * when more than one GPU is used: every GPU holds a replica of the descriptor bank, the pair list is dealt by cost
+ * Nq*Nt, NCCL is used only to exchange the packed descriptors and to gather the match lists on participant 0
+ * (SURVEY 8e).  Results on participant 0 are BYTE-IDENTICAL to a single-GPU run of the same list (same kernels per
+ * pair, input pair order).  NCCL (libnccl.so.2) is opened with dlopen at first use.
+ *
+ * (a) one process, one thread per GPU — what the reference's single-process pipeline uses:  sfm_mgpu_*.
+ *     The calls mirror sfm_bank_upload / sfm_match_pairs / sfm_match_pairs_from_host; the result is released with
+ *     sfm_result_free before sfm_mgpu_destroy.
+ * (b) one process per GPU (torchrun / MPI launchers): participant 0 makes an id (sfm_dist_unique_id), the launcher
+ *     hands its SFM_DIST_ID_BYTES bytes to every participant by its own means, each calls sfm_dist_init on its context.
+ *     sfm_dist_match_pairs* are COLLECTIVE: every participant calls them with the same pair list / scene description;
+ *     *out is the gathered result on participant 0 and NULL elsewhere.  With world == 1 (or without sfm_dist_init) they
+ *     behave like the single-GPU calls.
+ * from_host: participant r uploads only the images sfm_dist_upload_share names, over its own PCIe link, and the packed
+ * chunks are exchanged over NVLink while matching of the already-complete pairs runs (128-column descriptors, NORM_L2,
+ * k = 2); for any other configuration every participant reads the WHOLE scene, so `rows` must then be valid for all
+ * images on every participant. */
+#define SFM_DIST_ID_BYTES 128
+typedef struct sfm_mgpu sfm_mgpu;
+int  sfm_mgpu_create(sfm_mgpu **out, const int *devices, int n_devices);
+void sfm_mgpu_destroy(sfm_mgpu *g);
+int  sfm_mgpu_device_count(const sfm_mgpu *g);
+sfm_ctx *sfm_mgpu_ctx(sfm_mgpu *g, int participant);        /* per-GPU context (stats, profiling, homography stage) */
+const char *sfm_mgpu_last_error(const sfm_mgpu *g);
+int sfm_mgpu_bank_upload(sfm_mgpu *g, int n_images, const void *const *rows, const int32_t *n_rows, int cols,
+                         const size_t *step_bytes, int cv_depth);
+int sfm_mgpu_match_pairs(sfm_mgpu *g, const int32_t *pairs, int64_t n_pairs, const sfm_opts *opts, sfm_result **out);
+int sfm_mgpu_match_pairs_from_host(sfm_mgpu *g, int n_images, const void *const *rows, const int32_t *n_rows, int cols,
+                                   const size_t *step_bytes, int cv_depth, const int32_t *pairs, int64_t n_pairs,
+                                   const sfm_opts *opts, sfm_result **out);
+
+int sfm_dist_unique_id(uint8_t *id /* SFM_DIST_ID_BYTES */);
+int sfm_dist_init(sfm_ctx *ctx, const uint8_t *id, int rank, int world);
+int sfm_dist_info(const sfm_ctx *ctx, int *rank, int *world);
+int sfm_dist_match_pairs(sfm_ctx *ctx, const int32_t *pairs, int64_t n_pairs, const sfm_opts *opts, sfm_result **out);
+int sfm_dist_match_pairs_from_host(sfm_ctx *ctx, int n_images, const void *const *rows, const int32_t *n_rows, int cols,
+                                   const size_t *step_bytes, int cv_depth, const int32_t *pairs, int64_t n_pairs,
+                                   const sfm_opts *opts, sfm_result **out);
+/* The deal (host arithmetic, no GPU): owner[p] = participant that matches pair p — stable sort by descending cost
+ * Nq*Nt, dealt in snake order, ascending pair index inside a participant. */
+int sfm_dist_assign_pairs(const int32_t *pairs, int64_t n_pairs, const int32_t *n_rows, int n_images, int world,
+                          int32_t *owner);
+/* Images [*first_image, *end_image) are the ones participant `rank` uploads in the from_host exchange path. */
+int sfm_dist_upload_share(const int32_t *n_rows, int n_images, int world, int rank, int *first_image, int *end_image);
+/* Host-clock phases (ms) of the last collective on this participant: [0] upload + exchange enqueued / deal,
+ * [1] kernels enqueued, [3] totals all-gather incl. waiting for the kernels, [4] send/recv + reorder + D2H. */
+int sfm_dist_last_phases(const sfm_ctx *ctx, double *ms /* 8 */);
+
 /* Homography stage -------------------------------------------------------------------------
  * Replaces SfM::calculateHomography (SfM.cpp:599-637): per ShotMatches of the last sfm_match_pairs* run,
  * cv::findHomography(left points, right points, cv::RANSAC, threshold, mask) -> inlier count / match count.

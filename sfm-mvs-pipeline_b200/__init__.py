@@ -22,7 +22,8 @@ NORM_L2, NORM_HAMMING = 4, 6
 CV_8U, CV_32F = 0, 5
 ENGINE_AUTO, ENGINE_TENSOR, ENGINE_SIMT, ENGINE_TENSOR_IMAD = 0, 1, 2, 3
 MAX_ROWS = 1 << 18
-OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4, -5
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+DIST_ID_BYTES = 128
 
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 
@@ -34,7 +35,11 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_last_float_stats", "sfm_keypoints_upload", "sfm_homography_inlier_ratios",
            "sfm_homography_opts_default", "sfm_sift_opts_default", "sfm_features_clear", "sfm_features_extract_sift",
            "sfm_features_count", "sfm_features_download", "sfm_bank_from_features", "sfm_features_last_counts",
-           "sfm_features_pyramid_level", "sfm_features_last_profile", "sfm_gray_from_bgr"]
+           "sfm_features_pyramid_level", "sfm_features_last_profile", "sfm_gray_from_bgr",
+           "sfm_mgpu_create", "sfm_mgpu_destroy", "sfm_mgpu_device_count", "sfm_mgpu_ctx", "sfm_mgpu_last_error",
+           "sfm_mgpu_bank_upload", "sfm_mgpu_match_pairs", "sfm_mgpu_match_pairs_from_host", "sfm_dist_unique_id",
+           "sfm_dist_init", "sfm_dist_info", "sfm_dist_match_pairs", "sfm_dist_match_pairs_from_host",
+           "sfm_dist_assign_pairs", "sfm_dist_upload_share", "sfm_dist_last_phases"]
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4")])          # sfm_keypoint = cv::KeyPoint without class_id
@@ -75,6 +80,9 @@ def load_library():
     lib.sfm_ctx_destroy.restype = None
     lib.sfm_opts_default.restype = None
     lib.sfm_homography_opts_default.restype = None
+    lib.sfm_mgpu_destroy.restype = None
+    lib.sfm_mgpu_ctx.restype = C.c_void_p
+    lib.sfm_mgpu_last_error.restype = C.c_char_p
     return lib
 
 
@@ -107,6 +115,37 @@ def gray_from_bgr(img: np.ndarray, rgb_order: bool = False) -> np.ndarray:
     if rc != OK:
         raise SfmError(rc, "sfm_gray_from_bgr failed")
     return out
+
+
+def dist_unique_id() -> bytes:
+    """Id of a new multi-GPU group (made by participant 0, handed to the others by the launcher)."""
+    buf = (C.c_uint8 * DIST_ID_BYTES)()
+    rc = _lib.sfm_dist_unique_id(buf)
+    if rc != OK:
+        raise SfmError(rc, _lib.sfm_last_error(None).decode())
+    return bytes(buf)
+
+
+def dist_assign_pairs(pairs, n_rows, world: int) -> np.ndarray:
+    """owner[p] = participant that matches pair p (the library's deal; host arithmetic, no GPU)."""
+    pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+    n_rows = np.ascontiguousarray(n_rows, np.int32)
+    owner = np.zeros(len(pairs), np.int32)
+    rc = _lib.sfm_dist_assign_pairs(pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)), n_rows.ctypes.data_as(C.c_void_p),
+                                    C.c_int(len(n_rows)), C.c_int(world), owner.ctypes.data_as(C.c_void_p))
+    if rc != OK:
+        raise SfmError(rc, "sfm_dist_assign_pairs: bad arguments")
+    return owner
+
+
+def dist_upload_share(n_rows, world: int, rank: int):
+    n_rows = np.ascontiguousarray(n_rows, np.int32)
+    a, b = C.c_int(), C.c_int()
+    rc = _lib.sfm_dist_upload_share(n_rows.ctypes.data_as(C.c_void_p), C.c_int(len(n_rows)), C.c_int(world), C.c_int(rank),
+                                    C.byref(a), C.byref(b))
+    if rc != OK:
+        raise SfmError(rc, "sfm_dist_upload_share: bad arguments")
+    return a.value, b.value
 
 
 def _depth_of(a: np.ndarray) -> int:
@@ -270,12 +309,48 @@ class Matcher:
                                                    C.byref(o), C.byref(res)))
         return self._wrap_result(res)
 
+    # ---- multi-GPU group, one process per GPU (sfm_dist_*): collective calls, result on participant 0 only
+    def dist_init(self, uid: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * DIST_ID_BYTES).from_buffer_copy(uid) if uid is not None else None
+        self._check(_lib.sfm_dist_init(self._ctx, buf, C.c_int(rank), C.c_int(world)))
+
+    def dist_info(self):
+        a, b = C.c_int(), C.c_int()
+        _lib.sfm_dist_info(self._ctx, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def dist_last_phases(self):
+        ms = (C.c_double * 8)()
+        _lib.sfm_dist_last_phases(self._ctx, ms)
+        return list(ms)
+
+    def dist_match_pairs(self, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False, min_match_count=0,
+                         engine=ENGINE_AUTO):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        o = self._opts(norm, k, ratio, cross_check, distinct, min_match_count, engine)
+        res = C.c_void_p()
+        self._check(_lib.sfm_dist_match_pairs(self._ctx, pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)), C.byref(o),
+                                              C.byref(res)))
+        return self._wrap_result(res) if res else None
+
+    def dist_match_pairs_from_host(self, descriptors, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False,
+                                   min_match_count=0, engine=ENGINE_AUTO):
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        keep, ptrs, nrows, steps, cols, depth = self._bank_args(descriptors)
+        o = self._opts(norm, k, ratio, cross_check, distinct, min_match_count, engine)
+        res = C.c_void_p()
+        self._check(_lib.sfm_dist_match_pairs_from_host(self._ctx, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps,
+                                                        C.c_int(depth), pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
+                                                        C.byref(o), C.byref(res)))
+        return self._wrap_result(res) if res else None
+
     def collect(self) -> MatchResult:
         res = C.c_void_p()
         self._check(_lib.sfm_match_pairs_collect(self._ctx, C.byref(res)))
         return self._wrap_result(res)
 
-    def _wrap_result(self, res) -> MatchResult:
+    @staticmethod
+    def _wrap_result(res) -> MatchResult:
         try:
             n = _lib.sfm_result_n_pairs(res)
             offsets = np.ctypeslib.as_array(_lib.sfm_result_offsets(res), shape=(n + 1,)).copy()
@@ -419,3 +494,70 @@ class Matcher:
                                        C.c_size_t(ts), C.c_int(cols), C.c_int(dq), C.c_int(norm), C.c_int(k),
                                        C.c_int(engine), nidx.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p)))
         return nidx, dist
+
+
+class _CtxView(Matcher):
+    """A context owned by a MultiGpuMatcher (stats / profiling / homography per participant); never destroyed here."""
+
+    def __init__(self, ctx_ptr, device):
+        self._ctx = C.c_void_p(ctx_ptr)
+        self.device = device
+
+    def close(self):
+        self._ctx = C.c_void_p()
+
+
+class MultiGpuMatcher:
+    """One process, one worker thread per GPU (sfm_mgpu_*): the multi-GPU form of Matcher for a single-process
+    pipeline like the reference's (UnorderedFeatureMatchingStrategy.cpp:40 runs pairs as an OpenMP parallel for)."""
+
+    def __init__(self, devices):
+        devices = [int(d) for d in devices]
+        arr = (C.c_int * len(devices))(*devices)
+        self._g = C.c_void_p()
+        rc = _lib.sfm_mgpu_create(C.byref(self._g), arr, C.c_int(len(devices)))
+        if rc != OK:
+            raise SfmError(rc, _lib.sfm_last_error(None).decode())
+        self.devices = devices
+
+    def close(self):
+        if self._g:
+            _lib.sfm_mgpu_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise SfmError(rc, _lib.sfm_mgpu_last_error(self._g).decode())
+
+    def ctx(self, i) -> Matcher:
+        return _CtxView(_lib.sfm_mgpu_ctx(self._g, C.c_int(i)), self.devices[i])
+
+    def upload_bank(self, descriptors):
+        keep, ptrs, nrows, steps, cols, depth = Matcher._bank_args(None, descriptors)
+        self._check(_lib.sfm_mgpu_bank_upload(self._g, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps, C.c_int(depth)))
+
+    def match_pairs(self, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False, min_match_count=0,
+                    engine=ENGINE_AUTO) -> MatchResult:
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        o = Matcher._opts(None, norm, k, ratio, cross_check, distinct, min_match_count, engine)
+        res = C.c_void_p()
+        self._check(_lib.sfm_mgpu_match_pairs(self._g, pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)), C.byref(o),
+                                              C.byref(res)))
+        return Matcher._wrap_result(res)
+
+    def match_pairs_from_host(self, descriptors, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False,
+                              min_match_count=0, engine=ENGINE_AUTO) -> MatchResult:
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        keep, ptrs, nrows, steps, cols, depth = Matcher._bank_args(None, descriptors)
+        o = Matcher._opts(None, norm, k, ratio, cross_check, distinct, min_match_count, engine)
+        res = C.c_void_p()
+        self._check(_lib.sfm_mgpu_match_pairs_from_host(self._g, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps,
+                                                        C.c_int(depth), pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
+                                                        C.byref(o), C.byref(res)))
+        return Matcher._wrap_result(res)

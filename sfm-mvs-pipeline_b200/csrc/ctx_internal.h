@@ -180,6 +180,7 @@ struct sfm_ctx {
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
+    void* dist = nullptr;            // multi-GPU group membership (sfmhost::DistState, csrc/dist.cu)
 };
 
 namespace sfmhost {
@@ -210,6 +211,7 @@ int bank_upload_host(sfm_ctx* c, Bank& b, int n_images, const void* const* rows,
                      const size_t* step_bytes, int depth);
 int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm_opts* o, const Schedule* sched = nullptr);
 int collect_impl(sfm_ctx* c, sfm_result** out);
+void dist_state_destroy(sfm_ctx* c);      // dist.cu
 int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
                    const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
                    sfm_result** out);

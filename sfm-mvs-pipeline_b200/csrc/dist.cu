@@ -1,0 +1,773 @@
+// dist.cu — the multi-GPU group behind the C ABI (include/sfmmatch.h, "Multi-GPU group").
+//
+// The stage shards by image pair (the reference already runs pairs as an OpenMP `parallel for`,
+// UnorderedFeatureMatchingStrategy.cpp:40): every GPU holds a replica of the descriptor bank, pairs are dealt by
+// cost Nq*Nt, and NCCL is used only to exchange the packed descriptors and to gather the match lists on
+// participant 0 (north_star).  A participant is one sfm_ctx (one GPU) plus one NCCL communicator rank; the
+// participants of a group are either threads of ONE process (sfm_mgpu_*: what a maintainer of the one-process reference
+// uses) or one process each (sfm_dist_* under torchrun) — the per-participant code below is the same.
+//
+//   from host   : participant r uploads only ITS share of the images over its own PCIe link (chunk by chunk: H2D, pack
+//                 to u8), the chunk is exchanged with in-place ncclBroadcasts inside one group call, every participant
+//                 computes norms / keys for what it received, and the compute stream starts matching the pairs whose
+//                 two images have arrived (availability schedule of enqueue_impl) while later chunks are in flight.
+//   gather      : ncclAllGather of the 16-byte (total, overflow) scalars -> ONE host sync; grouped ncclSend / ncclRecv
+//                 of (offsets, dropped flags, DMatch records) to participant 0; one kernel pass there puts the lists
+//                 into input pair order (launch_reorder) and one D2H lands them in pinned host memory.
+//
+// NCCL is opened with dlopen at first use, so the single-GPU library has no link-time dependency on it and a process
+// that already carries a libnccl.so.2 (PyTorch's) shares that copy.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <thread>
+
+#include "ctx_internal.h"
+
+using namespace sfm;
+using namespace sfmhost;
+
+namespace sfmhost {
+
+// ------------------------------------------------------------------------------------------------ NCCL, loaded lazily
+struct NcclApi {
+    void* handle = nullptr;
+    std::string error;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) { api.error = std::string("libnccl.so.2 not loadable: ") + dlerror(); return; }
+        bool ok = true;
+        auto sym = [&](const char* name) { void* p = dlsym(api.handle, name); if (!p) { ok = false; api.error = std::string("NCCL symbol missing: ") + name; } return p; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+        api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+        api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+    });
+    return api;
+}
+
+#define NCCL_TRY(ctx, expr)                                                                                     \
+    do {                                                                                                        \
+        ncclResult_t _r = (expr);                                                                               \
+        if (_r != ncclSuccess)                                                                                  \
+            return fail(ctx, SFM_ERR_NCCL, std::string(#expr) + ": " + nccl_api().GetErrorString(_r));          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ the deal
+// Pairs to participants by cost Nq*Nt: stable sort by descending cost, dealt in snake order (0..W-1, W-1..0, ...), ascending
+// pair index inside a participant (pairs that share the left image stay adjacent: their train images stay L2-resident).
+// Equal costs degenerate to a strided deal.  Deterministic, so every participant computes the same table.
+void deal_pairs(const int32_t* pairs, int64_t n_pairs, const int32_t* n_rows, int world, std::vector<int32_t>& owner) {
+    owner.assign(static_cast<size_t>(n_pairs), 0);
+    if (world <= 1 || n_pairs == 0) return;
+    std::vector<int64_t> cost(static_cast<size_t>(n_pairs));
+    bool equal = true;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        cost[p] = static_cast<int64_t>(n_rows[pairs[2 * p]]) * n_rows[pairs[2 * p + 1]];
+        equal = equal && cost[p] == cost[0];
+    }
+    std::vector<int64_t> order(static_cast<size_t>(n_pairs));
+    for (int64_t p = 0; p < n_pairs; ++p) order[p] = p;
+    if (!equal) std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[a] > cost[b]; });
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        const int64_t rnd = k / world;
+        const int pos = static_cast<int>(k % world);
+        owner[order[k]] = (rnd % 2 == 0) ? pos : world - 1 - pos;
+    }
+}
+
+// Which images participant r uploads in the from-host path: contiguous ranges balanced by padded rows.
+void upload_shares(const int32_t* n_rows, int n_images, int world, std::vector<int>& first /* world + 1 */) {
+    first.assign(static_cast<size_t>(world) + 1, n_images);
+    int64_t total = 0;
+    for (int i = 0; i < n_images; ++i) total += (n_rows[i] + kRowAlign - 1) / kRowAlign * kRowAlign;
+    first[0] = 0;
+    int64_t acc = 0;
+    int r = 1;
+    for (int i = 0; i < n_images && r < world; ++i) {
+        acc += (n_rows[i] + kRowAlign - 1) / kRowAlign * kRowAlign;
+        while (r < world && acc * world >= total * r) first[r++] = i + 1;
+    }
+}
+
+struct DistState {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    bool owns_comm = true;
+    // the deal of the last pair list (cached: bench loops and SfM re-runs repeat one list)
+    uint64_t deal_key = 0;
+    std::vector<int32_t> owner;
+    std::vector<int32_t> my_pairs;                 // [2 * n_mine]
+    std::vector<int64_t> seg_start;                // world + 1: first gathered position of every participant
+    std::vector<int64_t> gorder;                   // gathered position -> input pair index
+    bool gorder_on_device = false;
+    DevBuf d_tot_all, d_goff, d_gdrop, d_gout, d_gorder, d_grand;
+    PinBuf h_tot_all;
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int chunks = 4;
+};
+
+void dist_state_destroy(sfm_ctx* c) {
+    DistState* d = static_cast<DistState*>(c->dist);
+    if (!d) return;
+    if (d->comm && d->owns_comm && nccl_api().handle) nccl_api().CommDestroy(d->comm);
+    d->d_tot_all.release(); d->d_goff.release(); d->d_gdrop.release(); d->d_gout.release(); d->d_gorder.release(); d->d_grand.release();
+    d->h_tot_all.release();
+    delete d;
+    c->dist = nullptr;
+}
+
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+static int init_state(sfm_ctx* c, ncclComm_t comm, int rank, int world, bool owns) {
+    dist_state_destroy(c);
+    DistState* d = new DistState();
+    d->comm = comm; d->rank = rank; d->world = world; d->owns_comm = owns;
+    if (const char* env = std::getenv("SFM_DIST_CHUNKS")) { const int t = std::atoi(env); if (t >= 1 && t <= 16) d->chunks = t; }
+    c->dist = d;
+    cudaError_t e = d->d_tot_all.ensure(static_cast<size_t>(world) * 16);
+    if (e == cudaSuccess) e = d->h_tot_all.ensure(static_cast<size_t>(world) * 16);
+    if (e == cudaSuccess) e = d->d_grand.ensure(16);
+    if (e != cudaSuccess) return fail(c, SFM_ERR_CUDA, cudaGetErrorString(e));
+    return SFM_OK;
+}
+
+// this participant's share of the pair list (cached by content)
+static int prepare_deal(sfm_ctx* c, DistState* d, const int32_t* pairs, int64_t n_pairs) {
+    const Bank& b = c->bank;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int l = pairs[2 * p], r = pairs[2 * p + 1];
+        if (l < 0 || r < 0 || l >= b.n_images || r >= b.n_images) return fail(c, SFM_ERR_INVALID, "pair index out of range");
+    }
+    uint64_t key = fnv1a(pairs, static_cast<size_t>(n_pairs) * 8);
+    key = fnv1a(b.n_rows.data(), b.n_rows.size() * 4, key);
+    key = fnv1a(&n_pairs, 8, key) | 1ull;
+    if (key == d->deal_key) return SFM_OK;
+    deal_pairs(pairs, n_pairs, b.n_rows.data(), d->world, d->owner);
+    d->seg_start.assign(static_cast<size_t>(d->world) + 1, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) d->seg_start[d->owner[p] + 1]++;
+    for (int r = 0; r < d->world; ++r) d->seg_start[r + 1] += d->seg_start[r];
+    d->gorder.assign(static_cast<size_t>(n_pairs), 0);
+    std::vector<int64_t> fill(d->seg_start.begin(), d->seg_start.end() - 1);
+    d->my_pairs.clear();
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        d->gorder[fill[d->owner[p]]++] = p;
+        if (d->owner[p] == d->rank) { d->my_pairs.push_back(pairs[2 * p]); d->my_pairs.push_back(pairs[2 * p + 1]); }
+    }
+    d->gorder_on_device = false;
+    d->deal_key = key;
+    return SFM_OK;
+}
+
+__global__ void rebase_offsets_kernel(int64_t* __restrict__ off, int64_t n, const int64_t* __restrict__ seg_start,
+                                      const int64_t* __restrict__ base, int world) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int r = 0;
+    while (r + 1 < world && k >= seg_start[r + 1]) ++r;
+    off[k] += base[r];
+}
+
+static double ms_since(const std::chrono::steady_clock::time_point& t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// Gather the lists of the last enqueue on participant 0, in input pair order, in pinned host memory.
+static int gather_impl(sfm_ctx* c, DistState* d, int64_t n_pairs, sfm_result** out) {
+    NvtxRange nvtx_range("sfm:dist_gather");
+    NcclApi& nc = nccl_api();
+    cudaStream_t s = c->stream;
+    const int W = d->world, me = d->rank;
+    auto t0 = std::chrono::steady_clock::now();
+    int64_t* h_tot = d->h_tot_all.as<int64_t>();
+    for (int attempt = 0;; ++attempt) {
+        // (total, overflow) of every participant; this is the one place the host has to wait for the kernels
+        NCCL_TRY(c, nc.AllGather(c->d_scalars.p, d->d_tot_all.p, 16, ncclUint8, d->comm, s));
+        CU_TRY(c, cudaMemcpyAsync(h_tot, d->d_tot_all.p, static_cast<size_t>(W) * 16, cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaStreamSynchronize(s));
+        bool any = false;
+        for (int r = 0; r < W; ++r) any = any || reinterpret_cast<int*>(h_tot + 2 * r)[2] != 0;
+        if (!any) break;
+        if (attempt == 1) return fail(c, SFM_ERR_CAPACITY, "output capacity overflow after retry");
+        if (reinterpret_cast<int*>(h_tot + 2 * me)[2] != 0) {
+            // this participant ran out of output capacity: once more with the worst case (as sfm_match_pairs_collect does)
+            c->out_capacity = std::max<int64_t>(c->run.total_query_rows, 1);
+            std::vector<int32_t> keep;
+            keep.swap(c->run.pairs);
+            sfm_opts o = c->run.opts;
+            int rc = enqueue_impl(c, keep.data(), c->run.n_pairs, &o);
+            c->run.pairs.swap(keep);
+            if (rc != SFM_OK) return rc;
+        }
+    }
+    d->phase_ms[3] = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    c->stat_d2h += W * 16;
+    std::vector<int64_t> base(static_cast<size_t>(W) + 1, 0);
+    for (int r = 0; r < W; ++r) base[r + 1] = base[r] + h_tot[2 * r];
+    const int64_t grand = base[W];
+    const int64_t n_mine = d->seg_start[me + 1] - d->seg_start[me];
+    const int64_t my_total = h_tot[2 * me];
+    if (me == 0) {
+        CU_TRY(c, d->d_goff.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8 + static_cast<size_t>(2 * W + 2) * 8)));
+        CU_TRY(c, d->d_gdrop.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs))));
+        CU_TRY(c, d->d_gout.ensure(std::max<size_t>(16, static_cast<size_t>(grand) * sizeof(DMatch))));
+    }
+    NCCL_TRY(c, nc.GroupStart());
+    if (me != 0) {
+        if (n_mine > 0) {
+            NCCL_TRY(c, nc.Send(c->d_pair_offsets.p, static_cast<size_t>(n_mine) * 8, ncclUint8, 0, d->comm, s));
+            NCCL_TRY(c, nc.Send(c->d_dropped.p, static_cast<size_t>(n_mine), ncclUint8, 0, d->comm, s));
+        }
+        if (my_total > 0) NCCL_TRY(c, nc.Send(c->d_out.p, static_cast<size_t>(my_total) * sizeof(DMatch), ncclUint8, 0, d->comm, s));
+    } else {
+        for (int r = 1; r < W; ++r) {
+            const int64_t nr = d->seg_start[r + 1] - d->seg_start[r];
+            if (nr > 0) {
+                NCCL_TRY(c, nc.Recv(d->d_goff.as<int64_t>() + d->seg_start[r], static_cast<size_t>(nr) * 8, ncclUint8, r, d->comm, s));
+                NCCL_TRY(c, nc.Recv(d->d_gdrop.as<uint8_t>() + d->seg_start[r], static_cast<size_t>(nr), ncclUint8, r, d->comm, s));
+            }
+            if (h_tot[2 * r] > 0)
+                NCCL_TRY(c, nc.Recv(d->d_gout.as<DMatch>() + base[r], static_cast<size_t>(h_tot[2 * r]) * sizeof(DMatch), ncclUint8, r, d->comm, s));
+        }
+    }
+    NCCL_TRY(c, nc.GroupEnd());
+    if (me != 0) {
+        // the send buffers belong to the next enqueue as soon as this returns
+        CU_TRY(c, cudaStreamSynchronize(s));
+        d->phase_ms[4] = ms_since(t0);
+        if (out) *out = nullptr;
+        return SFM_OK;
+    }
+    if (n_mine > 0) {
+        CU_TRY(c, cudaMemcpyAsync(d->d_goff.p, c->d_pair_offsets.p, static_cast<size_t>(n_mine) * 8, cudaMemcpyDeviceToDevice, s));
+        CU_TRY(c, cudaMemcpyAsync(d->d_gdrop.p, c->d_dropped.p, static_cast<size_t>(n_mine), cudaMemcpyDeviceToDevice, s));
+    }
+    if (my_total > 0) CU_TRY(c, cudaMemcpyAsync(d->d_gout.p, c->d_out.p, static_cast<size_t>(my_total) * sizeof(DMatch), cudaMemcpyDeviceToDevice, s));
+    // small tables behind the offsets: seg_start[W + 1] | base[W + 1]
+    int64_t* d_tab = d->d_goff.as<int64_t>() + n_pairs;
+    std::vector<int64_t> tab(d->seg_start);
+    tab.insert(tab.end(), base.begin(), base.end());
+    CU_TRY(c, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, s));
+    CU_TRY(c, cudaMemcpyAsync(d->d_grand.p, &grand, 8, cudaMemcpyHostToDevice, s));
+    if (!d->gorder_on_device && n_pairs > 0) {
+        CU_TRY(c, d->d_gorder.ensure(static_cast<size_t>(n_pairs) * 8));
+        CU_TRY(c, cudaMemcpyAsync(d->d_gorder.p, d->gorder.data(), static_cast<size_t>(n_pairs) * 8, cudaMemcpyHostToDevice, s));
+        d->gorder_on_device = true;
+    }
+    sfm_result* r;
+    if (!c->result_pool.empty()) { r = c->result_pool.back(); c->result_pool.pop_back(); }
+    else r = new sfm_result();
+    r->owner = c;
+    r->n_pairs = n_pairs;
+    auto fill = [&]() -> int {
+        CU_TRY(c, r->offsets.ensure(static_cast<size_t>(n_pairs + 1) * 8));
+        CU_TRY(c, r->dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs))));
+        CU_TRY(c, r->matches.ensure(std::max<size_t>(16, static_cast<size_t>(grand) * sizeof(DMatch))));
+        if (n_pairs > 0) {
+            rebase_offsets_kernel<<<static_cast<unsigned>((n_pairs + 255) / 256), 256, 0, s>>>(d->d_goff.as<int64_t>(), n_pairs, d_tab, d_tab + W + 1, W);
+            CU_TRY(c, cudaGetLastError());
+            CU_TRY(c, c->d_cnt_tmp.ensure(static_cast<size_t>(n_pairs) * 8));
+            CU_TRY(c, c->d_pair_offsets2.ensure(static_cast<size_t>(n_pairs) * 8));
+            CU_TRY(c, c->d_dropped2.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs))));
+            CU_TRY(c, c->d_out2.ensure(std::max<size_t>(16, static_cast<size_t>(grand) * sizeof(DMatch))));
+            CU_TRY(c, launch_reorder(d->d_gout.as<DMatch>(), d->d_goff.as<int64_t>(), d->d_grand.as<int64_t>(), d->d_gorder.as<int64_t>(),
+                                     d->d_gdrop.as<uint8_t>(), n_pairs, c->d_cnt_tmp.as<int64_t>(), c->d_pair_offsets2.as<int64_t>(),
+                                     c->d_out2.as<DMatch>(), c->d_dropped2.as<uint8_t>(), s));
+            c->stat_launches += 4;
+            CU_TRY(c, cudaMemcpyAsync(r->offsets.p, c->d_pair_offsets2.p, static_cast<size_t>(n_pairs) * 8, cudaMemcpyDeviceToHost, s));
+            CU_TRY(c, cudaMemcpyAsync(r->dropped.p, c->d_dropped2.p, static_cast<size_t>(n_pairs), cudaMemcpyDeviceToHost, s));
+        }
+        if (grand > 0)
+            CU_TRY(c, cudaMemcpyAsync(r->matches.p, c->d_out2.p, static_cast<size_t>(grand) * sizeof(DMatch), cudaMemcpyDeviceToHost, s));
+        CU_TRY(c, cudaStreamSynchronize(s));
+        return SFM_OK;
+    };
+    const int rc = fill();
+    if (rc != SFM_OK) { c->result_pool.push_back(r); return rc; }
+    r->offsets.as<int64_t>()[n_pairs] = grand;
+    c->stat_d2h += n_pairs * 9 + grand * static_cast<int64_t>(sizeof(DMatch));
+    d->phase_ms[4] = ms_since(t0);
+    // the gathered result is not a run of THIS context's bank order: later stages (homography) work per participant
+    *out = r;
+    return SFM_OK;
+}
+
+// bank resident on every participant: deal, match the own share, gather
+static int dist_match_impl(sfm_ctx* c, DistState* d, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o, sfm_result** out) {
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(c, SFM_ERR_INVALID, "bad pair list");
+    if (c->bank.n_images == 0 && n_pairs > 0) return fail(c, SFM_ERR_STATE, "match_pairs before bank upload");
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = prepare_deal(c, d, pairs, n_pairs);
+    if (rc != SFM_OK) return rc;
+    d->phase_ms[0] = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    rc = enqueue_impl(c, d->my_pairs.data(), static_cast<int64_t>(d->my_pairs.size() / 2), o);
+    if (rc != SFM_OK) return rc;
+    d->phase_ms[1] = ms_since(t0);
+    d->phase_ms[2] = 0;
+    return gather_impl(c, d, n_pairs, out);
+}
+
+// descriptors in host memory: exchange path (see the header of this file) when the data qualifies, else every participant
+// uploads the whole scene itself
+static int dist_from_host_impl(sfm_ctx* c, DistState* d, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                               const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
+                               sfm_result** out) {
+    NvtxRange nvtx_range("sfm:dist_match_pairs_from_host");
+    NcclApi& nc = nccl_api();
+    const int W = d->world, me = d->rank;
+    if (n_images > 0 && (!rows || !n_rows)) return fail(c, SFM_ERR_INVALID, "bank: null arrays");
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(c, SFM_ERR_INVALID, "bad pair list");
+    auto whole_scene = [&]() -> int {
+        int rc = bank_upload_host(c, c->bank, n_images, rows, n_rows, cols, step_bytes, depth);
+        if (rc != SFM_OK) return rc;
+        return dist_match_impl(c, d, pairs, n_pairs, o, out);
+    };
+    // the decision must be the same on every participant: it only looks at what all of them were given
+    bool exchange = cols == 128 && (depth == SFM_CV_32F || depth == SFM_CV_8U) && o->norm == SFM_NORM_L2 && o->k == 2 &&
+                    !o->cross_check && (o->engine == SFM_ENGINE_AUTO || o->engine == SFM_ENGINE_TENSOR) && n_images >= 2 * W &&
+                    n_pairs > 0;
+    for (int i = 0; exchange && i < n_images; ++i)
+        if (n_rows[i] < 0 || n_rows[i] > 32768) exchange = false;
+    for (int64_t p = 0; exchange && p < n_pairs; ++p) {
+        const int l = pairs[2 * p], r = pairs[2 * p + 1];
+        if (l < 0 || r < 0 || l >= n_images || r >= n_images) exchange = false;        // let the plain path report it
+    }
+    if (!exchange) return whole_scene();
+
+    auto t0 = std::chrono::steady_clock::now();
+    Bank& b = c->bank;
+    int rc = bank_layout(c, b, n_images, n_rows, cols, depth);
+    if (rc != SFM_OK) return rc;
+    if (b.padded_rows == 0) return whole_scene();
+    std::vector<int> first;
+    upload_shares(n_rows, n_images, W, first);
+    const size_t esz = depth == SFM_CV_32F ? 4 : 1;
+    const size_t row_bytes = static_cast<size_t>(cols) * esz;
+    for (int i = first[me]; i < first[me + 1]; ++i) {
+        if (n_rows[i] == 0) continue;
+        if (!rows[i]) return fail(c, SFM_ERR_INVALID, "bank: null descriptor pointer for an image of this participant's share");
+        if (step_bytes && step_bytes[i] < row_bytes) return fail(c, SFM_ERR_INVALID, "bank: step smaller than a row");
+    }
+    cudaStream_t cs = c->copy_stream, s = c->stream;
+    CU_TRY(c, cudaStreamSynchronize(s));
+    const int64_t nblk = b.padded_rows / kRowAlign;
+    CU_TRY(c, cudaEventSynchronize(c->valid_ev));
+    CU_TRY(c, c->h_valid.ensure(static_cast<size_t>(nblk) * 4));
+    int32_t* valid = c->h_valid.as<int32_t>();
+    for (int i = 0; i < n_images; ++i) {
+        const int64_t b0 = b.row0[i] / kRowAlign, nbk = (b.row0[i + 1] - b.row0[i]) / kRowAlign;
+        for (int64_t k = 0; k < nbk; ++k)
+            valid[b0 + k] = static_cast<int32_t>(std::min<int64_t>(kRowAlign, std::max<int64_t>(0, b.n_rows[i] - k * kRowAlign)));
+    }
+    CU_TRY(c, b.d_valid.ensure(static_cast<size_t>(nblk) * 4));
+    CU_TRY(c, b.d_u8.ensure(static_cast<size_t>(b.padded_rows) * 128));
+    const int64_t my_r0 = b.row0[first[me]], my_r1 = b.row0[first[me + 1]];
+    // CV_32F staging only for the own share, at the bank positions of the own share (relative to my_r0)
+    if (depth == SFM_CV_32F) CU_TRY(c, b.d_f32.ensure(std::max<size_t>(16, static_cast<size_t>(my_r1 - my_r0) * 512)));
+    CU_TRY(c, b.d_norm2.ensure(b.padded_rows * 4));
+    CU_TRY(c, b.d_ckey.ensure(b.padded_rows * 4));
+    CU_TRY(c, b.d_ext.ensure(static_cast<size_t>(b.padded_rows) * kExtBytes));
+    CU_TRY(c, cudaMemcpyAsync(b.d_valid.p, valid, static_cast<size_t>(nblk) * 4, cudaMemcpyHostToDevice, cs));
+    CU_TRY(c, cudaEventRecord(c->valid_ev, cs));
+    int* flags = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 16);
+    CU_TRY(c, cudaMemsetAsync(flags, 0, 8, cs));
+    CU_TRY(c, cudaMemsetAsync(flags + 2, 0x7f, 4, cs));
+    const size_t nblk_b = static_cast<size_t>(nblk) * 4;
+    CU_TRY(c, b.d_blkmin.ensure(nblk_b));
+    CU_TRY(c, b.d_blkmax.ensure(nblk_b));
+    CU_TRY(c, cudaMemsetAsync(b.d_blkmin.p, 0x7f, nblk_b, cs));
+    CU_TRY(c, cudaMemsetAsync(b.d_blkmax.p, 0, nblk_b, cs));
+    b.u8_valued = true; b.have_f32 = false; b.ext_ok = true; b.nb_min = c->prev_nb_min; b.nb_max = c->prev_nb_max;
+    rc = make_tmaps(c, b);
+    if (rc != SFM_OK) return rc;
+    // ---- chunks: every participant's share is cut into G pieces of roughly equal size
+    int G = d->chunks;
+    for (int r = 0; r < W; ++r) G = std::min(G, std::max(1, first[r + 1] - first[r]));
+    std::vector<int> cb(static_cast<size_t>(W) * (G + 1));       // cb[r * (G + 1) + g] = first image of chunk g of participant r
+    std::vector<int> chunk_of(n_images, 0);
+    for (int r = 0; r < W; ++r) {
+        const int lo = first[r], hi = first[r + 1];
+        const int64_t r0 = b.row0[lo], span = b.row0[hi] - r0;
+        int g = 0;
+        cb[r * (G + 1)] = lo;
+        for (int i = lo; i < hi; ++i) {
+            chunk_of[i] = g;
+            if (g + 1 < G && (b.row0[i + 1] - r0) * G >= span * (g + 1) && hi - (i + 1) >= G - (g + 1)) cb[r * (G + 1) + ++g] = i + 1;
+        }
+        for (int k = g + 1; k <= G; ++k) cb[r * (G + 1) + k] = hi;
+    }
+    while (static_cast<int>(c->group_ev.size()) < G) {
+        cudaEvent_t ev;
+        CU_TRY(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->group_ev.push_back(ev);
+    }
+    const int32_t* d_valid = b.d_valid.as<int32_t>();
+    for (int g = 0; g < G; ++g) {
+        // own chunk: H2D + pack (CV_32F) or zero the padding rows (CV_8U)
+        const int lo = cb[me * (G + 1) + g], hi = cb[me * (G + 1) + g + 1];
+        const int64_t r0 = b.row0[lo], r1 = b.row0[hi];
+        for (int i = lo; i < hi; ++i) {
+            if (n_rows[i] == 0) continue;
+            const size_t step = step_bytes ? step_bytes[i] : row_bytes;
+            uint8_t* d_img = depth == SFM_CV_32F ? b.d_f32.as<uint8_t>() + static_cast<size_t>(b.row0[i] - my_r0) * 512
+                                                 : b.d_u8.as<uint8_t>() + static_cast<size_t>(b.row0[i]) * 128;
+            if (step == row_bytes)
+                CU_TRY(c, cudaMemcpyAsync(d_img, rows[i], static_cast<size_t>(n_rows[i]) * row_bytes, cudaMemcpyHostToDevice, cs));
+            else
+                CU_TRY(c, cudaMemcpy2DAsync(d_img, row_bytes, rows[i], step, row_bytes, static_cast<size_t>(n_rows[i]),
+                                            cudaMemcpyHostToDevice, cs));
+            c->stat_h2d += static_cast<int64_t>(n_rows[i]) * static_cast<int64_t>(row_bytes);
+        }
+        if (r1 > r0) {
+            if (depth == SFM_CV_32F)
+                CU_TRY(c, launch_pack_f32_to_u8(b.d_f32.as<float>() + (r0 - my_r0) * 128, 128, static_cast<int>(r1 - r0), 128,
+                                                d_valid + r0 / kRowAlign, b.d_u8.as<uint8_t>() + r0 * 128, flags, cs));
+            else
+                CU_TRY(c, launch_zero_padding(b.d_u8.as<uint8_t>() + r0 * 128, 128, r1 - r0, d_valid + r0 / kRowAlign, cs));
+            c->stat_launches++;
+        }
+        // exchange chunk g of every participant (in place: the bank has the same layout everywhere)
+        NCCL_TRY(c, nc.GroupStart());
+        for (int r = 0; r < W; ++r) {
+            const int64_t q0 = b.row0[cb[r * (G + 1) + g]], q1 = b.row0[cb[r * (G + 1) + g + 1]];
+            if (q1 > q0) {
+                uint8_t* p = b.d_u8.as<uint8_t>() + q0 * 128;
+                NCCL_TRY(c, nc.Broadcast(p, p, static_cast<size_t>(q1 - q0) * 128, ncclUint8, r, d->comm, cs));
+            }
+        }
+        NCCL_TRY(c, nc.GroupEnd());
+        for (int r = 0; r < W; ++r) {
+            const int64_t q0 = b.row0[cb[r * (G + 1) + g]], q1 = b.row0[cb[r * (G + 1) + g + 1]];
+            if (q1 > q0) {
+                CU_TRY(c, launch_norms_ckeys(b.d_u8.as<uint8_t>() + q0 * 128, q1 - q0, d_valid + q0 / kRowAlign,
+                                             b.d_norm2.as<int32_t>() + q0, b.d_ckey.as<int32_t>() + q0,
+                                             b.d_ext.as<int8_t>() + q0 * kExtBytes, flags + 1,
+                                             b.d_blkmin.as<int32_t>() + q0 / kRowAlign, b.d_blkmax.as<int32_t>() + q0 / kRowAlign, cs));
+                c->stat_launches++;
+            }
+        }
+        CU_TRY(c, cudaEventRecord(c->group_ev[g], cs));
+    }
+    // "not integer-valued" is only seen by the participant that packed the row: make it global
+    NCCL_TRY(c, nc.AllReduce(flags, flags, 1, ncclInt32, ncclMax, d->comm, cs));
+    int* h = c->h_scalars.as<int>() + 8;
+    CU_TRY(c, cudaMemcpyAsync(h, flags, 12, cudaMemcpyDeviceToHost, cs));
+    d->phase_ms[0] = ms_since(t0);
+    t0 = std::chrono::steady_clock::now();
+    // ---- my pairs, scheduled by the chunk that completes them
+    rc = prepare_deal(c, d, pairs, n_pairs);
+    if (rc != SFM_OK) return rc;
+    const int64_t n_mine = static_cast<int64_t>(d->my_pairs.size() / 2);
+    std::vector<int64_t> order(static_cast<size_t>(n_mine));
+    std::vector<int> avail_in(static_cast<size_t>(n_mine)), avail(static_cast<size_t>(n_mine));
+    for (int64_t p = 0; p < n_mine; ++p) {
+        order[p] = p;
+        avail_in[p] = std::max(chunk_of[d->my_pairs[2 * p]], chunk_of[d->my_pairs[2 * p + 1]]);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return avail_in[x] < avail_in[y]; });
+    for (int64_t k = 0; k < n_mine; ++k) avail[k] = avail_in[order[k]];
+    Schedule sc;
+    sc.order = order.data(); sc.avail = avail.data(); sc.events = c->group_ev.data();
+    if (n_mine > 0) rc = enqueue_impl(c, d->my_pairs.data(), n_mine, o, &sc);
+    else {
+        CU_TRY(c, cudaStreamWaitEvent(s, c->group_ev[G - 1], 0));
+        rc = enqueue_impl(c, d->my_pairs.data(), 0, o);
+    }
+    CU_TRY(c, cudaStreamSynchronize(cs));
+    if (rc != SFM_OK) return rc;
+    d->phase_ms[1] = ms_since(t0);
+    b.nb_max = h[1]; b.nb_min = std::min(h[2], h[1]);
+    c->prev_nb_min = b.nb_min; c->prev_nb_max = b.nb_max;
+    if (h[0] != 0 || h[1] > kExtMaxNorm2) {
+        // not integer-valued, or norms beyond the digit range (the same verdict on every participant): plain path
+        CU_TRY(c, cudaStreamSynchronize(s));
+        c->run.valid = false;
+        c->bank.n_images = 0;
+        return whole_scene();
+    }
+    return gather_impl(c, d, n_pairs, out);
+}
+
+}  // namespace sfmhost
+
+// ==================================================================================================== C ABI
+struct sfm_mgpu {
+    std::vector<sfm_ctx*> ctx;
+    std::string err;
+    // one worker thread per device, alive for the lifetime of the group
+    struct Worker {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::function<int()> job;
+        bool has_job = false, done = false, quit = false;
+        int rc = 0;
+    };
+    std::vector<std::unique_ptr<Worker>> workers;
+    std::mutex call_mu;
+};
+
+namespace {
+
+void worker_loop(sfm_mgpu::Worker* w, int device) {
+    cudaSetDevice(device);
+    std::unique_lock<std::mutex> lk(w->mu);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+        if (w->quit) return;
+        std::function<int()> job = std::move(w->job);
+        w->has_job = false;
+        lk.unlock();
+        const int rc = job();
+        lk.lock();
+        w->rc = rc;
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+
+// run fn(i) on every participant's thread, wait for all; the first non-zero status wins
+int run_all(sfm_mgpu* g, const std::function<int(int)>& fn) {
+    const int n = static_cast<int>(g->ctx.size());
+    for (int i = 0; i < n; ++i) {
+        sfm_mgpu::Worker* w = g->workers[i].get();
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->job = [&fn, i] { return fn(i); };
+        w->has_job = true; w->done = false;
+        w->cv.notify_all();
+    }
+    int rc = SFM_OK;
+    for (int i = 0; i < n; ++i) {
+        sfm_mgpu::Worker* w = g->workers[i].get();
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv.wait(lk, [&] { return w->done; });
+        if (w->rc != SFM_OK && rc == SFM_OK) { rc = w->rc; g->err = "device " + std::to_string(g->ctx[i]->device) + ": " + g->ctx[i]->err; }
+    }
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfm_dist_unique_id(uint8_t* id) {
+    if (!id) return SFM_ERR_INVALID;
+    NcclApi& nc = nccl_api();
+    if (!nc.handle) return fail(nullptr, SFM_ERR_NCCL, nc.error);
+    static_assert(sizeof(ncclUniqueId) == SFM_DIST_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    ncclResult_t r = nc.GetUniqueId(&u);
+    if (r != ncclSuccess) return fail(nullptr, SFM_ERR_NCCL, std::string("ncclGetUniqueId: ") + nc.GetErrorString(r));
+    std::memcpy(id, &u, sizeof u);
+    return SFM_OK;
+}
+
+int sfm_dist_init(sfm_ctx* c, const uint8_t* id, int rank, int world) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, SFM_ERR_INVALID, "dist: bad rank / world");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (world == 1) return init_state(c, nullptr, 0, 1, false);
+    if (!id) return fail(c, SFM_ERR_INVALID, "dist: null id");
+    NcclApi& nc = nccl_api();
+    if (!nc.handle) return fail(c, SFM_ERR_NCCL, nc.error);
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof u);
+    ncclComm_t comm = nullptr;
+    NCCL_TRY(c, nc.CommInitRank(&comm, world, u, rank));
+    return init_state(c, comm, rank, world, true);
+}
+
+int sfm_dist_info(const sfm_ctx* c, int* rank, int* world) {
+    if (!c) return SFM_ERR_INVALID;
+    const DistState* d = static_cast<const DistState*>(c->dist);
+    if (rank) *rank = d ? d->rank : 0;
+    if (world) *world = d ? d->world : 1;
+    return SFM_OK;
+}
+
+int sfm_dist_assign_pairs(const int32_t* pairs, int64_t n_pairs, const int32_t* n_rows, int n_images, int world, int32_t* owner) {
+    if (n_pairs < 0 || world < 1 || (n_pairs > 0 && (!pairs || !n_rows || !owner))) return SFM_ERR_INVALID;
+    for (int64_t p = 0; p < n_pairs; ++p)
+        if (pairs[2 * p] < 0 || pairs[2 * p + 1] < 0 || pairs[2 * p] >= n_images || pairs[2 * p + 1] >= n_images) return SFM_ERR_INVALID;
+    std::vector<int32_t> o;
+    deal_pairs(pairs, n_pairs, n_rows, world, o);
+    if (n_pairs > 0) std::memcpy(owner, o.data(), static_cast<size_t>(n_pairs) * 4);
+    return SFM_OK;
+}
+
+int sfm_dist_upload_share(const int32_t* n_rows, int n_images, int world, int rank, int* first_image, int* end_image) {
+    if (n_images < 0 || world < 1 || rank < 0 || rank >= world || (n_images > 0 && !n_rows)) return SFM_ERR_INVALID;
+    std::vector<int> first;
+    upload_shares(n_rows, n_images, world, first);
+    if (first_image) *first_image = first[rank];
+    if (end_image) *end_image = first[rank + 1];
+    return SFM_OK;
+}
+
+int sfm_dist_match_pairs(sfm_ctx* c, const int32_t* pairs, int64_t n_pairs, const sfm_opts* opts, sfm_result** out) {
+    if (!c || !opts || !out) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = nullptr;
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    DistState* d = static_cast<DistState*>(c->dist);
+    if (!d || d->world == 1) {
+        int rc = enqueue_impl(c, pairs, n_pairs, opts);
+        if (rc != SFM_OK) return rc;
+        return collect_impl(c, out);
+    }
+    return dist_match_impl(c, d, pairs, n_pairs, opts, out);
+}
+
+int sfm_dist_match_pairs_from_host(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                                   const size_t* step_bytes, int cv_depth, const int32_t* pairs, int64_t n_pairs,
+                                   const sfm_opts* opts, sfm_result** out) {
+    if (!c || !opts || !out) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = nullptr;
+    CU_TRY(c, cudaSetDevice(c->device));
+    c->run.valid = false;
+    DistState* d = static_cast<DistState*>(c->dist);
+    if (!d || d->world == 1) {
+        if (n_images > 0 && (!rows || !n_rows)) return fail(c, SFM_ERR_INVALID, "bank: null arrays");
+        return from_host_impl(c, n_images, rows, n_rows, cols, step_bytes, cv_depth, pairs, n_pairs, opts, out);
+    }
+    return dist_from_host_impl(c, d, n_images, rows, n_rows, cols, step_bytes, cv_depth, pairs, n_pairs, opts, out);
+}
+
+int sfm_dist_last_phases(const sfm_ctx* c, double* ms) {
+    if (!c || !ms) return SFM_ERR_INVALID;
+    const DistState* d = static_cast<const DistState*>(c->dist);
+    for (int k = 0; k < 8; ++k) ms[k] = d ? d->phase_ms[k] : 0.0;
+    return SFM_OK;
+}
+
+// ---- one process, one thread per GPU (what the reference's single-process pipeline uses)
+int sfm_mgpu_create(sfm_mgpu** out, const int* devices, int n_devices) {
+    if (!out) return SFM_ERR_INVALID;
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > 64 || !devices) return fail(nullptr, SFM_ERR_INVALID, "mgpu: bad device list");
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, SFM_ERR_INVALID, "mgpu: a device appears twice");
+    std::unique_ptr<sfm_mgpu> g(new sfm_mgpu());
+    auto destroy_all = [&] { for (sfm_ctx* c : g->ctx) sfm_ctx_destroy(c); g->ctx.clear(); };
+    for (int i = 0; i < n_devices; ++i) {
+        sfm_ctx* c = nullptr;
+        const int rc = sfm_ctx_create(&c, devices[i]);
+        if (rc != SFM_OK) { destroy_all(); return rc; }
+        g->ctx.push_back(c);
+    }
+    if (n_devices > 1) {
+        NcclApi& nc = nccl_api();
+        if (!nc.handle) { destroy_all(); return fail(nullptr, SFM_ERR_NCCL, nc.error); }
+        std::vector<ncclComm_t> comms(n_devices);
+        ncclResult_t r = nc.CommInitAll(comms.data(), n_devices, devices);
+        if (r != ncclSuccess) { destroy_all(); return fail(nullptr, SFM_ERR_NCCL, std::string("ncclCommInitAll: ") + nc.GetErrorString(r)); }
+        for (int i = 0; i < n_devices; ++i) {
+            cudaSetDevice(devices[i]);
+            const int rc = init_state(g->ctx[i], comms[i], i, n_devices, true);
+            if (rc != SFM_OK) { destroy_all(); return rc; }
+        }
+    } else {
+        cudaSetDevice(devices[0]);
+        init_state(g->ctx[0], nullptr, 0, 1, false);
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        g->workers.emplace_back(new sfm_mgpu::Worker());
+        sfm_mgpu::Worker* w = g->workers.back().get();
+        w->th = std::thread(worker_loop, w, devices[i]);
+    }
+    *out = g.release();
+    return SFM_OK;
+}
+
+void sfm_mgpu_destroy(sfm_mgpu* g) {
+    if (!g) return;
+    for (auto& w : g->workers) {
+        { std::lock_guard<std::mutex> lk(w->mu); w->quit = true; w->cv.notify_all(); }
+        if (w->th.joinable()) w->th.join();
+    }
+    for (sfm_ctx* c : g->ctx) sfm_ctx_destroy(c);
+    delete g;
+}
+
+int sfm_mgpu_device_count(const sfm_mgpu* g) { return g ? static_cast<int>(g->ctx.size()) : 0; }
+sfm_ctx* sfm_mgpu_ctx(sfm_mgpu* g, int i) { return (g && i >= 0 && i < static_cast<int>(g->ctx.size())) ? g->ctx[i] : nullptr; }
+const char* sfm_mgpu_last_error(const sfm_mgpu* g) { return g ? g->err.c_str() : sfm_last_error(nullptr); }
+
+int sfm_mgpu_bank_upload(sfm_mgpu* g, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                         const size_t* step_bytes, int cv_depth) {
+    if (!g) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g->call_mu);
+    return run_all(g, [&](int i) { return sfm_bank_upload(g->ctx[i], n_images, rows, n_rows, cols, step_bytes, cv_depth); });
+}
+
+int sfm_mgpu_match_pairs(sfm_mgpu* g, const int32_t* pairs, int64_t n_pairs, const sfm_opts* opts, sfm_result** out) {
+    if (!g || !opts || !out) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g->call_mu);
+    *out = nullptr;
+    std::vector<sfm_result*> res(g->ctx.size(), nullptr);
+    const int rc = run_all(g, [&](int i) { return sfm_dist_match_pairs(g->ctx[i], pairs, n_pairs, opts, &res[i]); });
+    if (rc == SFM_OK) *out = res[0];
+    else if (res[0]) sfm_result_free(res[0]);
+    return rc;
+}
+
+int sfm_mgpu_match_pairs_from_host(sfm_mgpu* g, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                                   const size_t* step_bytes, int cv_depth, const int32_t* pairs, int64_t n_pairs,
+                                   const sfm_opts* opts, sfm_result** out) {
+    if (!g || !opts || !out) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g->call_mu);
+    *out = nullptr;
+    std::vector<sfm_result*> res(g->ctx.size(), nullptr);
+    const int rc = run_all(g, [&](int i) {
+        return sfm_dist_match_pairs_from_host(g->ctx[i], n_images, rows, n_rows, cols, step_bytes, cv_depth, pairs, n_pairs, opts, &res[i]);
+    });
+    if (rc == SFM_OK) *out = res[0];
+    else if (res[0]) sfm_result_free(res[0]);
+    return rc;
+}
+
+}  // extern "C"

@@ -876,6 +876,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    dist_state_destroy(c);
     c->bank.release(); c->scratch.release();
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
                       &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,

@@ -5,6 +5,10 @@ The stage shards naturally: every image pair is independent (the reference alrea
 descriptor bank, takes a cost-balanced share of the pair list, and only the compacted match lists travel:
 NCCL (or gloo in the CPU tests) is used to broadcast the bank and to gather (counts, matches) on rank 0.
 No data-path collective runs while the kernels work.
+
+This module is the torch.distributed form of the group, kept for launchers that already own a process group and for
+the gloo tests; the product path is native (csrc/dist.cu: sfm_dist_* / sfm_mgpu_*, NCCL inside the library), and
+``assign_pairs`` here is the same deal as ``sfm_dist_assign_pairs`` (tests/test_cabi_cpu.py checks they agree).
 """
 from __future__ import annotations
 
@@ -150,16 +154,16 @@ def gather_matches_device(matcher, local_idx, all_local_idx, n_pairs_total: int,
     payload[2 * max_local:2 * max_local + 4 * n_match] = cuda_view(pm, n_match * 16, device, torch.int32)
     gathered = torch.empty((world, width), dtype=torch.int32, device=device) if rank == dst else None
     dist.gather(payload, list(gathered.unbind(0)) if rank == dst else None, dst=dst, group=group)
+    # the payload copies read library-owned buffers on torch's stream: the library's next enqueue must not overwrite them
+    lib_stream.wait_stream(torch.cuda.current_stream(device))
     if rank != dst:
         return None
-    # global pair index of every (rank, local position), padded positions point at a dummy slot
-    key = ("idx", world, n_pairs_total, max_local)
-    if _PINNED.get("idx_key") != key:
-        idx = np.full((world, max_local), n_pairs_total, np.int64)
-        for r in range(world):
-            idx[r, :len(all_local_idx[r])] = all_local_idx[r]
-        _PINNED["idx_key"], _PINNED["idx_dev"] = key, torch.from_numpy(idx).to(device)
-    idx_dev = _PINNED["idx_dev"]
+    # global pair index of every (rank, local position), padded positions point at a dummy slot (rebuilt on every call:
+    # the deal depends on the row counts, not only on the pair count)
+    idx = np.full((world, max_local), n_pairs_total, np.int64)
+    for r in range(world):
+        idx[r, :len(all_local_idx[r])] = all_local_idx[r]
+    idx_dev = torch.from_numpy(idx).to(device)
     cnt = gathered[:, :max_local].to(torch.int64)                       # [world, max_local], 0 in padded positions
     total_counts = torch.zeros(n_pairs_total + 1, dtype=torch.int64, device=device)
     total_counts[idx_dev.reshape(-1)] = cnt.reshape(-1)

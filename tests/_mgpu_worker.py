@@ -45,10 +45,41 @@ def main():
     all_mine = shard.assign_pairs(pairs, sizes, world)
     m.enqueue(pairs[mine], sfm.NORM_L2, min_match_count=20)
     g2 = shard.gather_matches_device(m, mine, all_mine, len(pairs), dev, 0)
+    # the native group (sfm_dist_*: NCCL inside the library): bank resident, and from host matrices (exchange path needs
+    # >= 2 images per participant; ragged sizes, an empty image, unequal shares)
+    uid = torch.zeros(sfm.DIST_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(sfm.dist_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    m.dist_init(uid.cpu().numpy().tobytes(), rank, world)
+    assert m.dist_info() == (rank, world)
+    g3 = m.dist_match_pairs(pairs, sfm.NORM_L2, min_match_count=20)
+    host_bank = []
+    prev = None
+    for i, n in enumerate(sizes):
+        d = workloads.sift_like_image(i, n, prev if prev is not None and len(prev) else None)
+        host_bank.append(d.astype(np.float32))
+        prev = d
+    g4 = m.dist_match_pairs_from_host(host_bank, pairs, sfm.NORM_L2, min_match_count=20)
+    g5 = m.dist_match_pairs(pairs, sfm.NORM_L2, min_match_count=20, distinct=True)        # bank stays resident after from_host
+    # a configuration the exchange path does not take (cross-check): every participant uploads the whole scene
+    g6 = m.dist_match_pairs_from_host(host_bank, pairs, sfm.NORM_L2, k=1, cross_check=True)
     ok = True
+    if rank != 0:
+        ok = g3 is None and g4 is None and g5 is None and g6 is None
     if rank == 0:
         full = m.match_pairs(pairs, sfm.NORM_L2, min_match_count=20)
-        ok = (np.array_equal(g[0], full.offsets) and g[1].tobytes() == full.matches.tobytes()
+        for name, g in (("dist_match_pairs", g3), ("dist_match_pairs_from_host", g4)):
+            same = (np.array_equal(g.offsets, full.offsets) and g.matches.tobytes() == full.matches.tobytes()
+                    and np.array_equal(g.dropped, full.dropped))
+            if not same:
+                print("MISMATCH in", name, flush=True)
+            ok = ok and same
+        f5 = m.match_pairs(pairs, sfm.NORM_L2, min_match_count=20, distinct=True)
+        ok = ok and np.array_equal(g5.offsets, f5.offsets) and g5.matches.tobytes() == f5.matches.tobytes()
+        f6 = m.match_pairs(pairs, sfm.NORM_L2, k=1, cross_check=True)
+        ok = ok and np.array_equal(g6.offsets, f6.offsets) and g6.matches.tobytes() == f6.matches.tobytes()
+        ok = ok and (np.array_equal(g[0], full.offsets) and g[1].tobytes() == full.matches.tobytes()
               and np.array_equal(g[2], full.dropped))
         ok = ok and (np.array_equal(g2[0], full.offsets) and g2[1].tobytes() == full.matches.tobytes()
                      and np.array_equal(g2[2], full.dropped))

@@ -176,3 +176,29 @@ def test_gray_conversion_equals_cvtcolor(sfm):
     assert sfm.gray_from_bgr(np.zeros((0, 5, 3), np.uint8)).shape == (0, 5)
     with pytest.raises(sfm.SfmError):
         sfm.gray_from_bgr(np.zeros((4, 4), np.uint8))
+
+
+def test_native_deal_equals_the_python_deal(sfm):
+    """sfm_dist_assign_pairs (csrc/dist.cu) and shard.assign_pairs are the same deal (no GPU involved)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sfm_shard", os.path.join(os.path.dirname(sfm.LIB_PATH), "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 8):
+        for n_img in (2, 9, 33):
+            for equal in (False, True):
+                n_rows = np.full(n_img, 8192) if equal else rng.integers(0, 5000, n_img)
+                pairs = sfm.select_pairs(n_img, 0, 0)
+                owner = sfm.dist_assign_pairs(pairs, n_rows, world)
+                ref = shard.assign_pairs(pairs, n_rows, world)
+                for r in range(world):
+                    assert np.array_equal(np.nonzero(owner == r)[0], ref[r])
+    # upload shares: contiguous, cover every image once, balanced by padded rows
+    n_rows = rng.integers(0, 9000, 57)
+    prev_end = 0
+    for r in range(5):
+        lo, hi = sfm.dist_upload_share(n_rows, 5, r)
+        assert lo == prev_end and hi >= lo
+        prev_end = hi
+    assert prev_end == 57

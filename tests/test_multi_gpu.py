@@ -20,3 +20,50 @@ def test_two_gpu_result_is_byte_identical_to_one_gpu():
                         os.path.join(ROOT, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MGPU_IDENTICAL" in r.stdout
+
+
+def test_single_process_group_is_byte_identical_to_one_gpu():
+    """sfm_mgpu_*: one process, one worker thread per GPU, NCCL inside the library."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    import workloads
+    sfm = ge.load_package()
+    n = min(torch.cuda.device_count(), 4)
+    sizes = [1500, 1024, 777, 2048, 300, 1300, 0, 640, 900, 33]
+    bank, prev = [], None
+    for i, k in enumerate(sizes):
+        d = workloads.sift_like_image(i, k, prev if prev is not None and len(prev) else None)
+        bank.append(d)
+        prev = d
+    pairs = sfm.select_pairs(len(sizes), 0, 0)[:-2]
+    one = sfm.Matcher(0)
+    one.upload_bank(bank)
+    full = one.match_pairs(pairs, sfm.NORM_L2, min_match_count=5)
+    g = sfm.MultiGpuMatcher(list(range(n)))
+    for attempt in range(2):                       # second pass: cached deal, recycled buffers
+        r1 = g.match_pairs_from_host([b.astype(np.float32) for b in bank], pairs, sfm.NORM_L2, min_match_count=5)
+        r2 = g.match_pairs(pairs, sfm.NORM_L2, min_match_count=5)
+        for r in (r1, r2):
+            assert np.array_equal(r.offsets, full.offsets)
+            assert r.matches.tobytes() == full.matches.tobytes()
+            assert np.array_equal(r.dropped, full.dropped)
+    # another scene with the same pair count and other row counts: the cached deal must not be reused
+    bank2 = [b[: max(0, len(b) - 100 * (i % 3))] for i, b in enumerate(bank)]
+    one.upload_bank(bank2)
+    full2 = one.match_pairs(pairs, sfm.NORM_L2)
+    g.upload_bank(bank2)
+    r3 = g.match_pairs(pairs, sfm.NORM_L2)
+    assert np.array_equal(r3.offsets, full2.offsets) and r3.matches.tobytes() == full2.matches.tobytes()
+    # ORB through the group (whole-scene upload on every participant)
+    ob = workloads.orb_like_bank(5, 700)
+    op = sfm.select_pairs(5, 0, 0)
+    one.upload_bank(ob)
+    fo = one.match_pairs(op, sfm.NORM_HAMMING)
+    ro = g.match_pairs_from_host(ob, op, sfm.NORM_HAMMING)
+    assert np.array_equal(ro.offsets, fo.offsets) and ro.matches.tobytes() == fo.matches.tobytes()
+    g.close()
+    one.close()
