@@ -105,6 +105,26 @@ struct NvtxRange {
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
+// Per-batch device buffers, two sets: the knn kernel of batch i + 1 runs on the compute stream while the post kernels
+// (exact re-rank, filters, scan, compaction) of batch i run on the post stream.
+struct BatchSlot {
+    DevBuf top2, rev;                // raw top-2 / candidate records per staging row (rev: roles swapped, cross-check)
+    DevBuf aux, aux_rev;             // fifth-best chunk maximum per staging row (norm-less and 3xTF32 paths)
+    DevBuf need, bf;                 // value-only path: rows that survived the fused ratio bound; rows that need the whole train image
+    DevBuf keep;                     // value-only path: one keep bit per staging row
+    DevBuf counters;                 // [0] brute-force queue length, [1] need-list length
+    DevBuf blk_pair;                 // pair index of every 256-row staging block
+    DevBuf chunk_counts, chunk_excl, pair_counts, pair_nb, train_cnt;
+    cudaEvent_t knn_done = nullptr, post_done = nullptr;
+    void release() {
+        DevBuf* all[] = {&top2, &rev, &aux, &aux_rev, &need, &bf, &keep, &counters, &blk_pair, &chunk_counts, &chunk_excl, &pair_counts, &pair_nb, &train_cnt};
+        for (DevBuf* b : all) b->release();
+        if (knn_done) cudaEventDestroy(knn_done);
+        if (post_done) cudaEventDestroy(post_done);
+        knn_done = post_done = nullptr;
+    }
+};
+
 struct RunState {                    // what collect() needs from the last enqueue
     bool valid = false;
     int64_t n_pairs = 0;
@@ -133,14 +153,12 @@ struct sfm_ctx {
     Bank bank, scratch;
     // workspace
     DevBuf d_pairs, d_rev_pairs, d_unit_prefix, d_rev_unit_prefix, d_out_prefix, d_t_prefix;
-    DevBuf d_top2, d_rev, d_train_cnt, d_chunk_counts, d_chunk_excl, d_pair_counts, d_pair_offsets, d_dropped;
+    BatchSlot slot[2];
+    cudaStream_t post_stream = nullptr;
+    DevBuf d_pair_offsets, d_dropped;
     DevBuf d_scalars;                // [0..7] int64 running_total, [8..11] int overflow, [12..15] int not_integer
     DevBuf d_out, d_knn;
-    DevBuf d_blk_pair;               // pair index of every 256-row staging block of the current batch
-    DevBuf d_need, d_pair_nb;        // norm-less path: rows that survived the quick reject; train-image norm range per pair
-    DevBuf d_bf;                     // norm-less path: queue of staged rows that need the whole train image
     DevBuf d_hom;                    // homography stage: row0[2n] int64 | thresholds | inliers | best hypothesis
-    DevBuf d_aux, d_aux_rev;         // 3xTF32 path: fifth-best chunk maximum per staged row
     DevBuf d_out2, d_pair_offsets2, d_dropped2, d_order, d_cnt_tmp;   // reorder targets of the pipelined host path
     cudaStream_t copy_stream = nullptr;                               // uploads of the pipelined host path
     std::vector<cudaEvent_t> group_ev;                                // image group g is resident + packed
@@ -180,6 +198,8 @@ struct sfm_ctx {
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
+    int min_batches = 6;             // a long pair list is cut into at least this many batches (SFM_MIN_BATCHES): post kernels of
+                                     // batch i overlap the knn kernel of batch i + 1
     void* dist = nullptr;            // multi-GPU group membership (sfmhost::DistState, csrc/dist.cu)
 };
 

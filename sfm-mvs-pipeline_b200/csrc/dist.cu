@@ -349,7 +349,22 @@ static int dist_match_impl(sfm_ctx* c, DistState* d, const int32_t* pairs, int64
 
 // descriptors in host memory: exchange path (see the header of this file) when the data qualifies, else every participant
 // uploads the whole scene itself
+static int dist_from_host_body(sfm_ctx* c, DistState* d, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                               const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
+                               sfm_result** out);
 static int dist_from_host_impl(sfm_ctx* c, DistState* d, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                               const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
+                               sfm_result** out) {
+    const int rc = dist_from_host_body(c, d, n_images, rows, n_rows, cols, step_bytes, depth, pairs, n_pairs, o, out);
+    if (rc != SFM_OK) {           // as from_host_impl: nothing may look resident after a failure
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        c->bank.n_images = 0; c->bank.have_tmap = false; c->bank.n_rows.clear();
+        c->run.valid = false;
+    }
+    return rc;
+}
+static int dist_from_host_body(sfm_ctx* c, DistState* d, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
                                const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
                                sfm_result** out) {
     NvtxRange nvtx_range("sfm:dist_match_pairs_from_host");
@@ -522,7 +537,6 @@ static int dist_from_host_impl(sfm_ctx* c, DistState* d, int n_images, const voi
         // not integer-valued, or norms beyond the digit range (the same verdict on every participant): plain path
         CU_TRY(c, cudaStreamSynchronize(s));
         c->run.valid = false;
-        c->bank.n_images = 0;
         return whole_scene();
     }
     return gather_impl(c, d, n_pairs, out);

@@ -28,10 +28,20 @@ cudaError_t launch_knn2_l2_u8_tc(const void* tmap_a_host, const void* tmap_b_hos
                                  int n_pairs, int64_t n_units, Top2* out, int sm_count, int slabs, cudaStream_t s);
 
 // ---- knn_l2_tcv.cu  (tcgen05, value-only epilogue; needs every |b|^2 <= kExtMaxNorm2)
+// What the fused ratio-test bound of the epilogue needs: |a|^2 of every bank row, the |b|^2 range per 256-row bank block
+// (norm-less variant), the ratio, and the list the surviving staging rows are appended to.
+struct TcvFuse {
+    const int32_t* norm2;
+    const int32_t* blk_min;
+    const int32_t* blk_max;
+    int32_t* need_list;          // capacity = staged rows of the batch
+    int* need_count;
+    double ratio;
+};
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
                                   Top2* out, int32_t* aux, int sm_count, int layout, int tile_rows, int issuers, int chunk_rows,
-                                  cudaStream_t s);
+                                  const TcvFuse& fz, cudaStream_t s);
 
 // ---- knn_l2_tf32.cu  (tcgen05 kind::tf32, 3xTF32 candidate search for non-integer float descriptors)
 cudaError_t launch_knn2_l2_f32_tc3(const void* tmaps /* 5 CUtensorMap: hi_a, lo_a, hi_b, lo_b, ext */, const PairDesc* pairs,
@@ -69,6 +79,10 @@ struct FilterArgs {
     FilterParams fp;
     int32_t* train_cnt;          // distinct: zeroed by the caller
     const int32_t* blk_pair;     // pair of every 256-row staging block (launch_block_pairs), or null: binary search
+    // sparse form (value-only tcgen05 path, see post.cu): one keep bit per staging row, set for rows of need_list only
+    uint32_t* keep_bits;         // null: dense form (every staging row carries a Top2 record)
+    const int32_t* need_list;
+    const int* need_count;
 };
 // tcgen05 path only: tighten the provisional second neighbour (see refine_second_kernel in post.cu)
 struct RefineArgs {
@@ -104,6 +118,12 @@ cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s);
 cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s);
 // norm-less value-only path: four candidate chunks + bounds -> exact best match and a decided ratio test (see post.cu)
 cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s);
+// sparse form: keep decision of the rows of need_list -> keep bits (+ the distinct filter's two passes)
+cudaError_t launch_mark_keep(const FilterArgs& a, cudaStream_t s);
+cudaError_t launch_count_keep_bits(const uint32_t* keep_bits, int64_t n_blocks, int32_t* chunk_counts, cudaStream_t s);
+cudaError_t launch_compact_keep_bits(const FilterArgs& a, const int64_t* chunk_excl, const int64_t* pair_offsets,
+                                     const uint8_t* pair_dropped, DMatch* out, int64_t out_capacity, int* overflow_flag,
+                                     cudaStream_t s);
 // pass 1 (only with distinct): count how often each train row is the best match of a kept query row
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s);
 // pass 2: number of surviving matches per 256-row chunk

@@ -19,6 +19,8 @@
 // Precondition (checked on the host): every |b|^2 of the bank <= kExtMaxNorm2.  Otherwise knn_l2_tc.cu is used.
 #include <cuda.h>
 
+#include <climits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(128 + 128 * kParity * kHalves, 1)
 knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
                       const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out,
-                      int32_t* __restrict__ aux, int n_issuers) {
+                      int32_t* __restrict__ aux, int n_issuers, const TcvFuse fz) {
     using namespace tcv;
     using C = Cfg<kBN>;
     constexpr int BN = C::BN, kAccStages = C::kAccStages, kBStages = C::kBStages, kBBytes = C::kBBytes, kEBytes = C::kEBytes;
@@ -369,19 +371,39 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                         if (kNorm) top4_max64(k, r[0], r[1], r[2], r[3]);
                         else top5_max64(k, r[0], r[1], r[2], r[3], r[4]);
                     }
+                // ---- fused ratio-test bound (north_star: "fused epilogue ... ratio test"): a row can only pass
+                //     sqrtf(d0^2) < ratio * sqrtf(d1^2)   if it passes with the smallest possible d0^2 and the largest possible
+                // d1^2 the chunk maxima allow.  kNorm:  d0^2 >= |a|^2 - 2 D1,  d1^2 <= |a|^2 - 2 D2 + 1.  Norm-less:
+                // d0^2 >= |a|^2 + N- - 2 V1,  d1^2 <= |a|^2 + N+ - 2 V2  with [N-, N+] the |b|^2 range of the train image
+                // (reduced here from the per-256-row-block ranges).  ~99.5 % of C3's rows stop here and write NOTHING;
+                // survivors write their candidate record and append their staging row to the need list (one atomic per warp)
+                // for the exact re-rank (post.cu: refine_dot_rows_kernel / refine_value_rows_kernel).
                 const int row = u.rb * BM + row_in_unit;
-                if (row < u.pd.nq) {
-                    int32_t vv[5], ch[5];
-                    bool has[5];
+                const bool in_range = row < u.pd.nq && u.pd.nt > 0;
+                int32_t vv[5], ch[5];
+                bool has[5];
 #pragma unroll
-                    for (int i = 0; i < kKeys; ++i) {
-                        vv[i] = static_cast<int32_t>(r[i] >> 32);
-                        ch[i] = 0x7FFFFFFF - static_cast<int32_t>(r[i] & 0xFFFFFFFF);
-                        // value part 0: kNorm: D == -bias, a chunk of padding rows only; norm-less: a.b == 0, padding rows or
-                        // rows orthogonal to the query (the refine pass treats everything outside the candidates as a.b <= V5)
-                        has[i] = r[i] != kEmpty && vv[i] > 0;
-                    }
-                    Top2 o;
+                for (int i = 0; i < kKeys; ++i) {
+                    vv[i] = static_cast<int32_t>(r[i] >> 32);
+                    ch[i] = 0x7FFFFFFF - static_cast<int32_t>(r[i] & 0xFFFFFFFF);
+                    // value part 0: kNorm: D == -bias, a chunk of padding rows only; norm-less: a.b == 0, padding rows or
+                    // rows orthogonal to the query (the refine pass treats everything outside the candidates as a.b <= V5)
+                    has[i] = r[i] != kEmpty && vv[i] > 0;
+                }
+                int nbmin = 0, nbmax = 0;
+                if (!kNorm) {
+                    const int b0 = u.pd.t_row0 / kRowAlign, nblk = (u.pd.nt + kRowAlign - 1) / kRowAlign;
+                    int mn = INT_MAX, mx = 0;
+                    for (int b = lane; b < nblk; b += 32) { mn = min(mn, __ldg(fz.blk_min + b0 + b)); mx = max(mx, __ldg(fz.blk_max + b0 + b)); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+                    nbmin = mn; nbmax = mx;
+                }
+                bool need = false;
+                Top2 o;
+                o.i0 = -1; o.i1 = -1; o.d0 = 0.f; o.d1 = 0.f;
+                if (in_range) {
+                    const int na = __ldg(fz.norm2 + u.pd.q_row0 + row);
                     if (kNorm) {
                         o.i0 = has[0] ? ch[0] : -1;                                          // chunk of the best D
                         o.i1 = has[1] ? ch[1] : -1;                                          // second chunk
@@ -389,18 +411,44 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                             o.i0 |= (ch[2] + 1) << 16;                                       // a third chunk ties the second
                             if (has[3] && vv[3] == vv[1]) o.i1 |= 0x40000000;                // and a fourth: ambiguous
                         }
-                        o.d0 = __int_as_float(vv[0] - kValueBias);
-                        o.d1 = __int_as_float(vv[1] - kValueBias);
+                        const int D1 = vv[0] - kValueBias, D2 = vv[1] - kValueBias;
+                        o.d0 = __int_as_float(D1);
+                        o.d1 = __int_as_float(D2);
+                        if (o.i0 >= 0) {
+                            if (o.i1 < 0 || (o.i1 & 0x40000000)) need = true;
+                            else {
+                                const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na - 2 * D1)));      // parity can make it -1
+                                const float hi1 = __fsqrt_rn(static_cast<float>(na - 2 * D2 + 1));
+                                need = static_cast<double>(lo0) < static_cast<double>(hi1) * fz.ratio;
+                            }
+                        }
                     } else {
                         // four candidate chunks (0xFFFF = none; only chunks with a positive maximum, i.e. with a real row),
                         // V1, V2 and V5 >= 0 = an upper bound of a.b for every train row outside those chunks
                         o.i0 = (has[0] ? ch[0] : 0xFFFF) | (has[1] ? ch[1] : 0xFFFF) << 16;
                         o.i1 = (has[2] ? ch[2] : 0xFFFF) | (has[3] ? ch[3] : 0xFFFF) << 16;
-                        o.d0 = __int_as_float(has[0] ? vv[0] : -1);
-                        o.d1 = __int_as_float(has[1] ? vv[1] : -1);
-                        aux[u.pd.out_row0 + row] = has[4] ? vv[4] : 0;
+                        const int V1 = has[0] ? vv[0] : -1, V2 = has[1] ? vv[1] : -1;
+                        o.d0 = __int_as_float(V1);
+                        o.d1 = __int_as_float(V2);
+                        if (V2 <= 0) need = true;                                            // fewer than two chunks with a real maximum
+                        else {
+                            const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na + nbmin - 2 * V1)));
+                            const float hi1 = __fsqrt_rn(static_cast<float>(max(0, na + nbmax - 2 * V2)));
+                            need = static_cast<double>(lo0) < static_cast<double>(hi1) * fz.ratio;
+                        }
                     }
-                    out[u.pd.out_row0 + row] = o;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, need);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(fz.need_count, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (need) {
+                        const int64_t srow = u.pd.out_row0 + row;
+                        out[srow] = o;
+                        if (!kNorm) aux[srow] = has[4] ? vv[4] : 0;
+                        fz.need_list[base + __popc(bal & ((1u << lane) - 1))] = static_cast<int32_t>(srow);
+                    }
                 }
             }
             asm volatile("bar.sync 2, %0;" ::"n"(128 * kGroups) : "memory");
@@ -415,13 +463,13 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 template <int kParity, int kHalves, int kBN, bool kNorm, int kCC>
 static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
                               const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int32_t* aux, int grid,
-                              int issuers, cudaStream_t s) {
+                              int issuers, const TcvFuse& fz, cudaStream_t s) {
     // per launch: the attribute is per device, and one process may drive several GPUs
     cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, tcv::Cfg<kBN>::kSmemBytes);
     if (e != cudaSuccess) return e;
     knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
-        ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out, aux, issuers);
+        ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out, aux, issuers, fz);
     return cudaGetLastError();
 }
 
@@ -432,7 +480,7 @@ static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, cons
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
                                   Top2* out, int32_t* aux /* non-null selects the norm-less variant */, int sm_count, int layout,
-                                  int tile_rows, int issuers, int chunk_rows, cudaStream_t s) {
+                                  int tile_rows, int issuers, int chunk_rows, const TcvFuse& fz, cudaStream_t s) {
     if (n_units == 0) return cudaSuccess;
     const CUtensorMap* ta = static_cast<const CUtensorMap*>(tmap_a_host);
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
@@ -441,10 +489,10 @@ cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_ho
 #define SFM_TCV_CASE(P, H, T)                                                                                          \
     if (layout == 10 * P + H && tile_rows == T) {                                                                      \
         if (chunk_rows == 64)                                                                                          \
-            return aux ? launch_tcv<P, H, T, false, 64>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s) \
-                       : launch_tcv<P, H, T, true, 64>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s); \
-        return aux ? launch_tcv<P, H, T, false, 32>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s) \
-                   : launch_tcv<P, H, T, true, 32>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, s); \
+            return aux ? launch_tcv<P, H, T, false, 64>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s) \
+                       : launch_tcv<P, H, T, true, 64>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s); \
+        return aux ? launch_tcv<P, H, T, false, 32>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s) \
+                   : launch_tcv<P, H, T, true, 32>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s); \
     }
     SFM_TCV_CASE(1, 2, 256) SFM_TCV_CASE(1, 4, 256) SFM_TCV_CASE(2, 1, 256)
 #undef SFM_TCV_CASE

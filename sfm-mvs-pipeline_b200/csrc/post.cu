@@ -218,6 +218,38 @@ __device__ __forceinline__ bool keep_final(const FilterArgs& a, const RowCtx& c,
     return k;
 }
 
+// Sparse form (value-only tcgen05 path): the knn kernel's fused ratio bound leaves only a short list of staging rows
+// (need_list) with a Top2 record at all; after their exact re-rank mark_keep_kernel evaluates the keep decision for
+// those rows only and sets one bit per kept row.  The count / compact passes then read 1 bit per staging row instead of
+// a 16-byte record, and the record itself only for kept rows.
+__device__ __forceinline__ bool keep_bit(const uint32_t* __restrict__ bits, int64_t srow) {
+    return (__ldg(bits + (srow >> 5)) >> (srow & 31)) & 1u;
+}
+
+__global__ void __launch_bounds__(256) mark_keep_kernel(FilterArgs a) {
+    const int n = *a.need_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int64_t srow = a.need_list[i];
+        const RowCtx c = load_row(a, srow);
+        float d;
+        if (keep_basic(a, c, d)) {
+            atomicOr(a.keep_bits + (srow >> 5), 1u << (srow & 31));
+            if (a.fp.distinct) atomicAdd(a.train_cnt + a.t_prefix[c.p] + c.t.i0, 1);
+        }
+    }
+}
+
+// distinct filter, second pass: kept rows whose best train row is shared lose their bit (SfM.cpp:547-564)
+__global__ void __launch_bounds__(256) distinct_prune_kernel(FilterArgs a) {
+    const int n = *a.need_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int64_t srow = a.need_list[i];
+        if (!keep_bit(a.keep_bits, srow)) continue;
+        const RowCtx c = load_row(a, srow);
+        if (a.train_cnt[a.t_prefix[c.p] + c.t.i0] != 1) atomicAnd(a.keep_bits + (srow >> 5), ~(1u << (srow & 31)));
+    }
+}
+
 __global__ void __launch_bounds__(256) filter_mark_kernel(FilterArgs a) {
     const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
     if (srow >= a.staged_rows) return;
@@ -267,6 +299,54 @@ __global__ void __launch_bounds__(256) compact_kernel(FilterArgs a, const int64_
     DMatch m;
     m.queryIdx = c.row; m.trainIdx = c.t.i0; m.imgIdx = 0; m.distance = d;
     out[pos] = m;
+}
+
+// sparse count: one thread per 256-row staging block = 8 keep words
+__global__ void __launch_bounds__(256) count_keep_bits_kernel(const uint32_t* __restrict__ keep_bits, int64_t n_blocks,
+                                                              int32_t* __restrict__ chunk_counts) {
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint4* w = reinterpret_cast<const uint4*>(keep_bits + b * 8);
+    const uint4 x = __ldg(w), y = __ldg(w + 1);
+    chunk_counts[b] = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w) + __popc(y.x) + __popc(y.y) + __popc(y.z) + __popc(y.w);
+}
+
+// sparse compaction: one warp per 256-row staging block (persistent grid); lane l < 8 owns keep word l and emits the DMatch
+// records of its set bits in ascending row order (a block holds ~1 kept row on an all-pairs list)
+__global__ void __launch_bounds__(256) compact_keep_bits_kernel(FilterArgs a, int64_t n_blocks, const int64_t* __restrict__ chunk_excl,
+                                                                const int64_t* __restrict__ pair_offsets,
+                                                                const uint8_t* __restrict__ pair_dropped, DMatch* __restrict__ out,
+                                                                int64_t capacity, int* __restrict__ overflow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+    for (int64_t b = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+        uint32_t w = lane < 8 ? __ldg(a.keep_bits + b * 8 + lane) : 0u;
+        if (__ballot_sync(0xffffffffu, w != 0) == 0) continue;
+        // kept rows in the words before mine
+        int before = 0;
+        const int cnt = __popc(w);
+#pragma unroll
+        for (int l = 0; l < 7; ++l) {
+            const int cl = __shfl_sync(0xffffffffu, cnt, l);
+            if (lane > l) before += cl;
+        }
+        if (w == 0) continue;
+        const int p = a.blk_pair[b];
+        if (pair_dropped[p]) continue;
+        const int64_t first_chunk = a.out_prefix[p] >> 8;
+        int64_t pos = pair_offsets[p] + (chunk_excl[b] - chunk_excl[first_chunk]) + before;
+        const int64_t row0 = a.out_prefix[p];
+        while (w) {
+            const int bit = __ffs(w) - 1;
+            w &= w - 1;
+            const int64_t srow = b * 256 + lane * 32 + bit;
+            if (pos >= capacity) { atomicOr(overflow, 1); break; }
+            const Top2 t = a.top2[srow];
+            DMatch m;
+            m.queryIdx = static_cast<int>(srow - row0); m.trainIdx = t.i0; m.imgIdx = 0; m.distance = final_distance(a.fp.norm, t.d0);
+            out[pos++] = m;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ refine
@@ -404,54 +484,30 @@ __device__ __forceinline__ void warp_brute_force(const uint8_t* __restrict__ ban
     for (; c < groups; ++c) warp_chunk_candidates(bank, norm2, q, na, tr0, ntr, c, lane, a1, a2);
 }
 
-__global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
-    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+// one warp per row that survived the fused ratio bound of the knn kernel (persistent grid over need_list)
+__global__ void __launch_bounds__(256, 4) refine_value_rows_kernel(RefineArgs a) {
     const int lane = threadIdx.x & 31;
-    bool need = false, valid = false;
-    Top2 t;
-    t.i0 = -1; t.i1 = -1; t.d0 = 0.f; t.d1 = 0.f;
-    int q_bank_row = 0, t_row0 = 0, nt = 0;
-    if (srow < a.staged_rows) {
+    const int n = *a.need_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) atomicAdd(a.stats, static_cast<unsigned long long>(n));   // feedback for the host
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    const float inf = __int_as_float(0x7f800000);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const int64_t srow = a.need_list[i];
         const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
         const PairDesc pd = a.pairs[p];
-        const int row = static_cast<int>(srow - a.out_prefix[p]);
-        if (row < pd.nq) {
-            valid = true;
-            t = a.top2[srow];
-            q_bank_row = pd.q_row0 + row; t_row0 = pd.t_row0; nt = pd.nt;
-            if (t.i0 >= 0) {
-                if (a.all_rows || t.i1 < 0 || (t.i1 & 0x40000000)) need = true;
-                else {
-                    const int na = a.norm2[q_bank_row];
-                    const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na - 2 * __float_as_int(t.d0))));   // parity can make it -1
-                    const float hi1 = __fsqrt_rn(static_cast<float>(na - 2 * __float_as_int(t.d1) + 1));
-                    need = static_cast<double>(lo0) < static_cast<double>(hi1) * a.ratio;
-                }
-            }
-        }
-    }
-    const float inf = __int_as_float(0x7f800000);
-    Top2 o;
-    o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
-    unsigned mask = __ballot_sync(0xffffffffu, need);
-    if (lane == 0 && mask && a.stats) atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));   // feedback for the host
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int qrow = __shfl_sync(0xffffffffu, q_bank_row, src);
-        const int tr0 = __shfl_sync(0xffffffffu, t_row0, src);
-        const int ntr = __shfl_sync(0xffffffffu, nt, src);
-        const int c1raw = __shfl_sync(0xffffffffu, t.i0, src);
-        const int c2raw = __shfl_sync(0xffffffffu, t.i1, src);
+        const int qrow = pd.q_row0 + static_cast<int>(srow - a.out_prefix[p]);
+        const int tr0 = pd.t_row0, ntr = pd.nt;
+        const Top2 t = a.top2[srow];
+        const int c1raw = t.i0, c2raw = t.i1;
         const int c1 = c1raw & 0xFFFF, c3 = (c1raw >> 16) - 1;      // c3 >= 0: a third chunk ties the second
         const int na = a.norm2[qrow];
         uint4 q[8];
         const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
+        for (int k = 0; k < 8; ++k) q[k] = __ldg(qv + k);
         long long a1 = LLONG_MAX, a2 = LLONG_MAX;
         if (c2raw >= 0 && (c2raw & 0x40000000)) {
-            // ambiguous: a third chunk ties the second one -> exact brute force over the whole train image
+            // ambiguous: a fourth chunk ties the second one -> exact brute force over the whole train image
             warp_brute_force(a.bank, a.norm2, q, na, tr0, ntr, lane, a1, a2);
         } else {
             const int sub = a.chunk_rows / 32;                      // a candidate chunk = sub groups of 32 train rows
@@ -467,12 +523,15 @@ __global__ void __launch_bounds__(256) refine_value_kernel(RefineArgs a) {
             a2 = min(max(a1, b1), min(a2, b2));
             a1 = min(a1, b1);
         }
-        if (lane == src) {
+        __syncwarp();                                               // every lane has read the candidate record
+        if (lane == 0) {
+            Top2 o;
+            o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
             if (a1 != LLONG_MAX) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(a1 >> 32)); }
             if (a2 != LLONG_MAX) { o.i1 = static_cast<int>(a2 & 0xFFFFFFFFll); o.d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
+            a.top2[srow] = o;
         }
     }
-    if (valid) a.top2[srow] = o;        // rows that cannot pass keep i0 = -1 (rejected)
 }
 
 // ------------------------------------------------------------------------------------------------ refine (norm-less)
@@ -633,50 +692,7 @@ __global__ void pair_norm_range_kernel(RefineArgs a) {
     if (lane == 0) { a.pair_nb[2 * p] = mn; a.pair_nb[2 * p + 1] = mx; }
 }
 
-// pass 1, one thread per staged row at memory speed: quick reject (1); rows that survive go to need_list (their candidate
-// record stays in top2 for pass 2), all others get their final 'no match' record
-__global__ void __launch_bounds__(256) refine_dot_select_kernel(RefineArgs a) {
-    const int64_t srow = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool need = false, valid = false;
-    if (srow < a.staged_rows) {
-        const int p = pair_of_row(a.blk_pair, a.out_prefix, a.n_pairs, srow);
-        const PairDesc pd = a.pairs[p];
-        const int row = static_cast<int>(srow - a.out_prefix[p]);
-        if (row < pd.nq) {
-            valid = true;
-            if (pd.nt > 0) {
-                const Top2 t = a.top2[srow];
-                const int na = a.norm2[pd.q_row0 + row];
-                const int nbmin = a.pair_nb[2 * p], nbmax = a.pair_nb[2 * p + 1];
-                const int V1 = __float_as_int(t.d0), V2 = __float_as_int(t.d1);
-                if (a.all_rows || V2 <= 0) need = true;                       // fewer than two chunks with a real maximum
-                else {
-                    const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na + nbmin - 2 * V1)));
-                    const float hi1 = __fsqrt_rn(static_cast<float>(max(0, na + nbmax - 2 * V2)));
-                    need = static_cast<double>(lo0) < static_cast<double>(hi1) * a.ratio;
-                }
-            }
-        }
-    }
-    if (valid && !need) {
-        Top2 o;
-        o.i0 = -1; o.i1 = -1; o.d0 = __int_as_float(0x7f800000); o.d1 = o.d0;
-        a.top2[srow] = o;                                                     // cannot pass (or empty train image)
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, need);
-    if (mask) {
-        int base = 0;
-        if (lane == 0) {
-            base = atomicAdd(a.need_count, __popc(mask));
-            atomicAdd(a.stats, static_cast<unsigned long long>(__popc(mask)));
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (need) a.need_list[base + __popc(mask & ((1u << lane) - 1))] = static_cast<int32_t>(srow);
-    }
-}
-
-// pass 2: one warp per surviving row (persistent grid over need_list).  The row's metadata is a chain of five dependent
+// one warp per row that survived the fused ratio bound of the knn kernel (persistent grid over need_list).  The row's metadata is a chain of five dependent
 // loads (list -> block table -> pair -> candidates / norm / bounds): it is fetched one row ahead of the row being refined.
 struct DotRowMeta { int64_t srow; Top2 t; int v5, na, qrow, tr0, nt, nbmin, nbmax; };
 __device__ __forceinline__ DotRowMeta load_dot_row(const RefineArgs& a, int i) {
@@ -696,6 +712,7 @@ __device__ __forceinline__ DotRowMeta load_dot_row(const RefineArgs& a, int i) {
 __global__ void __launch_bounds__(256, 4) refine_dot_rows_kernel(RefineArgs a) {
     const int lane = threadIdx.x & 31;
     const int n = *a.need_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) atomicAdd(a.stats, static_cast<unsigned long long>(n));   // feedback for the host
     const int warps = gridDim.x * (blockDim.x >> 5);
     int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -766,8 +783,7 @@ __global__ void __launch_bounds__(256) brute_force_rows_kernel(RefineArgs a) {
 cudaError_t launch_refine_dot(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
     pair_norm_range_kernel<<<static_cast<unsigned>((a.n_pairs + 7) / 8), 256, 0, s>>>(a);
-    refine_dot_select_kernel<<<static_cast<unsigned>((a.staged_rows + 255) / 256), 256, 0, s>>>(a);
-    refine_dot_rows_kernel<<<148 * 8, 256, 0, s>>>(a);       // persistent over the rows that survived the quick reject
+    refine_dot_rows_kernel<<<148 * 4, 256, 0, s>>>(a);       // persistent over the rows that survived the fused ratio bound
     brute_force_rows_kernel<<<592, 256, 0, s>>>(a);          // persistent over the queue (usually a few dozen rows)
     return cudaGetLastError();
 }
@@ -782,7 +798,26 @@ cudaError_t launch_refine_second(const RefineArgs& a, cudaStream_t s) {
 }
 cudaError_t launch_refine_value(const RefineArgs& a, cudaStream_t s) {
     if (a.staged_rows == 0) return cudaSuccess;
-    refine_value_kernel<<<chunks_of(a.staged_rows), 256, 0, s>>>(a);
+    refine_value_rows_kernel<<<148 * 4, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_count_keep_bits(const uint32_t* keep_bits, int64_t n_blocks, int32_t* chunk_counts, cudaStream_t s) {
+    if (n_blocks == 0) return cudaSuccess;
+    count_keep_bits_kernel<<<static_cast<unsigned>((n_blocks + 255) / 256), 256, 0, s>>>(keep_bits, n_blocks, chunk_counts);
+    return cudaGetLastError();
+}
+cudaError_t launch_compact_keep_bits(const FilterArgs& a, const int64_t* chunk_excl, const int64_t* pair_offsets,
+                                     const uint8_t* pair_dropped, DMatch* out, int64_t out_capacity, int* overflow_flag,
+                                     cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    compact_keep_bits_kernel<<<148 * 2, 256, 0, s>>>(a, a.staged_rows / 256, chunk_excl, pair_offsets, pair_dropped, out, out_capacity,
+                                                      overflow_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_mark_keep(const FilterArgs& a, cudaStream_t s) {
+    if (a.staged_rows == 0) return cudaSuccess;
+    mark_keep_kernel<<<148 * 2, 256, 0, s>>>(a);
+    if (a.fp.distinct) distinct_prune_kernel<<<148 * 2, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_filter_mark(const FilterArgs& a, cudaStream_t s) {

@@ -282,9 +282,10 @@ int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out)
 }
 
 int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, const int64_t* d_unit_prefix, int n_pairs,
-               int64_t n_units, Top2* out, float* aux = nullptr) {
+               int64_t n_units, Top2* out, float* aux = nullptr, const TcvFuse* fz = nullptr) {
     cudaStream_t s = c->stream;
     c->stat_launches++;
+    const TcvFuse none{};
     switch (eng) {
         case Engine::TC:
             CU_TRY(c, launch_knn2_l2_u8_tc(&b.tmap_a, &b.tmap_b, b.d_ckey.as<int32_t>(), b.d_norm2.as<int32_t>(), d_pairs,
@@ -292,12 +293,12 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk_run, s));
+                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk_run, fz ? *fz : none, s));
             break;
         case Engine::TCN:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
                                             reinterpret_cast<int32_t*>(aux), c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers,
-                                            c->tcv_chunk_run, s));
+                                            c->tcv_chunk_run, fz ? *fz : none, s));
             break;
         case Engine::TF32:
             CU_TRY(c, launch_knn2_l2_f32_tc3(b.tmaps_f, d_pairs, d_unit_prefix, n_pairs, n_units, out, aux, c->sm_count, s));
@@ -381,12 +382,17 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
     struct Batch { int64_t p0, p1, staged_rows, t_rows, n_units, n_rev_units; };
     std::vector<Batch> batches;
     {
+        // the post kernels of batch i run beside the knn kernel of batch i + 1 (second stream, two buffer sets): a long list is
+        // cut into at least c->min_batches pieces so that only the last piece's post work is exposed; short lists stay whole
+        int64_t all_rows = 0;
+        for (int64_t p = 0; p < n_pairs; ++p) all_rows += pad_rows(b.n_rows[pairs[2 * p]]);
+        const int64_t budget = std::min<int64_t>(static_cast<int64_t>(c->staging_budget_rows),
+                                                 std::max<int64_t>(all_rows / std::max(1, c->min_batches) + 1, int64_t(1) << 20));
         Batch cur{0, 0, 0, 0, 0, 0};
         for (int64_t p = 0; p < n_pairs; ++p) {
             const int64_t q = pad_rows(b.n_rows[pairs[2 * p]]), t = pad_rows(b.n_rows[pairs[2 * p + 1]]);
             const bool avail_break = sched && sched->avail && p > 0 && sched->avail[p] != sched->avail[p - 1];
-            if (cur.p1 > cur.p0 && (avail_break || cur.staged_rows + q > static_cast<int64_t>(c->staging_budget_rows) ||
-                                    cur.t_rows + t > static_cast<int64_t>(c->staging_budget_rows))) {
+            if (cur.p1 > cur.p0 && (avail_break || cur.staged_rows + q > budget || cur.t_rows + t > budget)) {
                 batches.push_back(cur);
                 cur = Batch{p, p, 0, 0, 0, 0};
             }
@@ -476,24 +482,30 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
     const int64_t* d_outp = d_runit + npre;
     const int64_t* d_tp = d_outp + npre;
 
-    CU_TRY(c, c->d_top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
-    if (need_rev) CU_TRY(c, c->d_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
-    if (eng == Engine::TCN) {
-        CU_TRY(c, c->d_bf.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
-        CU_TRY(c, c->d_need.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
-        CU_TRY(c, c->d_pair_nb.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
+    const bool sparse = eng == Engine::TCV || eng == Engine::TCN;       // fused ratio bound: need list + keep bits
+    const int n_slots = nb > 1 ? 2 : 1;
+    for (int k = 0; k < n_slots; ++k) {
+        BatchSlot& S = c->slot[k];
+        CU_TRY(c, S.top2.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * sizeof(Top2))));
+        if (need_rev) CU_TRY(c, S.rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * sizeof(Top2))));
+        if (sparse) {
+            CU_TRY(c, S.bf.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+            CU_TRY(c, S.need.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+            CU_TRY(c, S.keep.ensure(std::max<size_t>(32, static_cast<size_t>(max_staged) / 8)));
+            CU_TRY(c, S.pair_nb.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
+        }
+        CU_TRY(c, S.counters.ensure(16));
+        if (eng == Engine::TF32 || eng == Engine::TCN) {
+            CU_TRY(c, S.aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+            if (need_rev) CU_TRY(c, S.aux_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
+        }
+        if (need_cnt) CU_TRY(c, S.train_cnt.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
+        CU_TRY(c, S.chunk_counts.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
+        CU_TRY(c, S.blk_pair.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
+        CU_TRY(c, S.chunk_excl.ensure(static_cast<size_t>(max_chunks + 1) * 8));
+        CU_TRY(c, S.pair_counts.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
     }
-    if (eng == Engine::TCV) CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
-    if (eng == Engine::TF32 || eng == Engine::TCN) {
-        CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
-        CU_TRY(c, c->d_aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
-        if (need_rev) CU_TRY(c, c->d_aux_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
-    }
-    if (need_cnt) CU_TRY(c, c->d_train_cnt.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
-    CU_TRY(c, c->d_chunk_counts.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
-    CU_TRY(c, c->d_blk_pair.ensure(std::max<size_t>(16, static_cast<size_t>(max_chunks) * 4)));
-    CU_TRY(c, c->d_chunk_excl.ensure(static_cast<size_t>(max_chunks + 1) * 8));
-    CU_TRY(c, c->d_pair_counts.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
+    if (sparse || eng == Engine::TF32) CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));   // stats of this run
     CU_TRY(c, c->d_pair_offsets.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
     CU_TRY(c, c->d_dropped.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs))));
     // output capacity: grown on demand (collect() retries with the worst case if a run overflows)
@@ -514,75 +526,104 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             c->prof_ev.push_back(ev);
         }
     }
+    cudaStream_t ps = c->post_stream;
     for (int64_t bi = 0; bi < nb; ++bi) {
         const Batch& B = batches[bi];
+        BatchSlot& S = c->slot[bi & 1];
         const int np = static_cast<int>(B.p1 - B.p0);
         const int64_t base = B.p0 + bi;
+        // ---- compute stream: the knn kernel(s) of this batch.  The slot's buffers are free once the post kernels of batch
+        // bi - 2 are done.
+        if (bi >= 2) CU_TRY(c, cudaStreamWaitEvent(s, S.post_done, 0));
         if (sched && sched->avail && sched->events) CU_TRY(c, cudaStreamWaitEvent(s, sched->events[sched->avail[B.p0]], 0));
-        CU_TRY(c, launch_block_pairs(d_outp + base, np, B.staged_rows / 256, c->d_blk_pair.as<int32_t>(), s));
+        CU_TRY(c, launch_block_pairs(d_outp + base, np, B.staged_rows / 256, S.blk_pair.as<int32_t>(), s));
         c->stat_launches++;
+        TcvFuse fz{};
+        if (sparse) {
+            CU_TRY(c, cudaMemsetAsync(S.counters.p, 0, 16, s));                            // brute-force queue + need list lengths
+            CU_TRY(c, cudaMemsetAsync(S.keep.p, 0, static_cast<size_t>(B.staged_rows) / 8, s));
+            fz.norm2 = b.d_norm2.as<int32_t>(); fz.blk_min = b.d_blkmin.as<int32_t>(); fz.blk_max = b.d_blkmax.as<int32_t>();
+            fz.need_list = S.need.as<int32_t>(); fz.need_count = S.counters.as<int>() + 1; fz.ratio = o->ratio;
+        }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
-        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, c->d_top2.as<Top2>(), c->d_aux.as<float>());
+        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, S.top2.as<Top2>(), S.aux.as<float>(), &fz);
         if (rc != SFM_OK) return rc;
         if (need_rev) {
-            rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, c->d_rev.as<Top2>(), c->d_aux_rev.as<float>());
+            rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, S.rev.as<Top2>(), S.aux_rev.as<float>());
             if (rc != SFM_OK) return rc;
         }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 1], s));
+        CU_TRY(c, cudaEventRecord(S.knn_done, s));
+        // ---- post stream: exact re-rank, filters, scan, ordered compaction (in batch order: the scan continues a running total)
+        CU_TRY(c, cudaStreamWaitEvent(ps, S.knn_done, 0));
         if (eng == Engine::TF32) {
             // candidates -> exact fp32 top-2 (+ certificate); everything downstream sees ordinary Top2 rows
             RefineF32Args fa;
-            fa.blk_pair = c->d_blk_pair.as<int32_t>();
-            fa.top2 = c->d_top2.as<Top2>(); fa.aux = c->d_aux.as<float>(); fa.pairs = d_pd + B.p0; fa.out_prefix = d_outp + base;
+            fa.blk_pair = S.blk_pair.as<int32_t>();
+            fa.top2 = S.top2.as<Top2>(); fa.aux = S.aux.as<float>(); fa.pairs = d_pd + B.p0; fa.out_prefix = d_outp + base;
             fa.n_pairs = np; fa.staged_rows = B.staged_rows; fa.bank = b.d_f32.as<float>(); fa.fnorm2 = b.d_fnorm.as<float>();
             fa.nb_max = b.f_nb_max; fa.all_rows = (o->k == 1 || need_rev) ? 1 : 0; fa.swap_roles = 0; fa.ratio = o->ratio;
             fa.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
-            CU_TRY(c, launch_refine_f32(fa, s));
+            CU_TRY(c, launch_refine_f32(fa, ps));
             c->stat_launches++;
             if (need_rev) {
-                fa.top2 = c->d_rev.as<Top2>(); fa.aux = c->d_aux_rev.as<float>(); fa.swap_roles = 1; fa.blk_pair = nullptr;
+                fa.top2 = S.rev.as<Top2>(); fa.aux = S.aux_rev.as<float>(); fa.swap_roles = 1; fa.blk_pair = nullptr;
                 fa.out_prefix = d_tp + base; fa.staged_rows = B.t_rows; fa.all_rows = 1;
-                CU_TRY(c, launch_refine_f32(fa, s));
+                CU_TRY(c, launch_refine_f32(fa, ps));
                 c->stat_launches++;
             }
         }
-        if ((eng == Engine::TC || eng == Engine::TCV || eng == Engine::TCN) && o->k == 2 && !need_rev) {
+        if ((eng == Engine::TC || sparse) && o->k == 2 && !need_rev) {
             RefineArgs ra{};
-            ra.aux = c->d_aux.as<int32_t>(); ra.blk_min = b.d_blkmin.as<int32_t>(); ra.blk_max = b.d_blkmax.as<int32_t>();
+            ra.aux = S.aux.as<int32_t>(); ra.blk_min = b.d_blkmin.as<int32_t>(); ra.blk_max = b.d_blkmax.as<int32_t>();
             ra.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
-            ra.chunk_rows = c->tcv_chunk_run; ra.blk_pair = c->d_blk_pair.as<int32_t>();
-            ra.bf_list = c->d_bf.as<int32_t>(); ra.bf_count = reinterpret_cast<int*>(c->d_scalars.as<uint8_t>() + 48);
-            ra.need_list = c->d_need.as<int32_t>(); ra.need_count = ra.bf_count + 1; ra.pair_nb = c->d_pair_nb.as<int32_t>();
-            ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
+            ra.chunk_rows = c->tcv_chunk_run; ra.blk_pair = S.blk_pair.as<int32_t>();
+            ra.bf_list = S.bf.as<int32_t>(); ra.bf_count = S.counters.as<int>();
+            ra.need_list = S.need.as<int32_t>(); ra.need_count = ra.bf_count + 1; ra.pair_nb = S.pair_nb.as<int32_t>();
+            ra.top2 = S.top2.as<Top2>(); ra.pairs = d_pd + B.p0; ra.out_prefix = d_outp + base; ra.n_pairs = np;
             ra.staged_rows = B.staged_rows; ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
             ra.all_rows = 0; ra.ratio = o->ratio; ra.hamming = o->norm == SFM_NORM_HAMMING;
             if (eng == Engine::TCN) {
-                CU_TRY(c, cudaMemsetAsync(ra.bf_count, 0, 8, s));          // brute-force queue + need list counters
-                CU_TRY(c, launch_refine_dot(ra, s));
-                c->stat_launches += 3;                                      // 4 kernels
+                CU_TRY(c, launch_refine_dot(ra, ps));
+                c->stat_launches += 2;                                      // 3 kernels
             }
-            else if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, s));
-            else CU_TRY(c, launch_refine_second(ra, s));
+            else if (eng == Engine::TCV) CU_TRY(c, launch_refine_value(ra, ps));
+            else CU_TRY(c, launch_refine_second(ra, ps));
             c->stat_launches++;
         }
-        FilterArgs a;
-        a.top2 = c->d_top2.as<Top2>(); a.rev = c->d_rev.as<Top2>(); a.pairs = d_pd + B.p0;
+        FilterArgs a{};
+        a.top2 = S.top2.as<Top2>(); a.rev = S.rev.as<Top2>(); a.pairs = d_pd + B.p0;
         a.out_prefix = d_outp + base; a.t_prefix = d_tp + base; a.n_pairs = np; a.staged_rows = B.staged_rows;
-        a.fp = fp; a.train_cnt = c->d_train_cnt.as<int32_t>(); a.blk_pair = c->d_blk_pair.as<int32_t>();
-        if (need_cnt) {
-            CU_TRY(c, cudaMemsetAsync(c->d_train_cnt.p, 0, static_cast<size_t>(B.t_rows) * 4, s));
-            CU_TRY(c, launch_filter_mark(a, s));
+        a.fp = fp; a.train_cnt = S.train_cnt.as<int32_t>(); a.blk_pair = S.blk_pair.as<int32_t>();
+        if (need_cnt) CU_TRY(c, cudaMemsetAsync(S.train_cnt.p, 0, static_cast<size_t>(B.t_rows) * 4, ps));
+        if (sparse) {
+            a.keep_bits = S.keep.as<uint32_t>(); a.need_list = S.need.as<int32_t>(); a.need_count = S.counters.as<int>() + 1;
+            CU_TRY(c, launch_mark_keep(a, ps));
+            CU_TRY(c, launch_count_keep_bits(a.keep_bits, B.staged_rows / 256, S.chunk_counts.as<int32_t>(), ps));
+            c->stat_launches += need_cnt ? 3 : 2;
+        } else {
+            if (need_cnt) {
+                CU_TRY(c, launch_filter_mark(a, ps));
+                c->stat_launches++;
+            }
+            CU_TRY(c, launch_filter_count(a, S.chunk_counts.as<int32_t>(), ps));
             c->stat_launches++;
         }
-        CU_TRY(c, launch_filter_count(a, c->d_chunk_counts.as<int32_t>(), s));
-        CU_TRY(c, launch_scan_offsets(c->d_chunk_counts.as<int32_t>(), B.staged_rows / 256, d_outp + base, np,
-                                      o->min_match_count, c->d_chunk_excl.as<int64_t>(), c->d_pair_counts.as<int64_t>(),
-                                      c->d_pair_offsets.as<int64_t>() + B.p0, c->d_dropped.as<uint8_t>() + B.p0, d_total, s));
-        CU_TRY(c, launch_compact(a, c->d_chunk_excl.as<int64_t>(), c->d_pair_offsets.as<int64_t>() + B.p0,
-                                 c->d_dropped.as<uint8_t>() + B.p0, c->d_out.as<DMatch>(), c->out_capacity, d_overflow, s));
-        c->stat_launches += 3;
-        if (c->profiling) { CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 2], s)); c->prof_used = static_cast<int>(3 * (bi + 1)); }
+        CU_TRY(c, launch_scan_offsets(S.chunk_counts.as<int32_t>(), B.staged_rows / 256, d_outp + base, np,
+                                      o->min_match_count, S.chunk_excl.as<int64_t>(), S.pair_counts.as<int64_t>(),
+                                      c->d_pair_offsets.as<int64_t>() + B.p0, c->d_dropped.as<uint8_t>() + B.p0, d_total, ps));
+        if (sparse)
+            CU_TRY(c, launch_compact_keep_bits(a, S.chunk_excl.as<int64_t>(), c->d_pair_offsets.as<int64_t>() + B.p0,
+                                               c->d_dropped.as<uint8_t>() + B.p0, c->d_out.as<DMatch>(), c->out_capacity, d_overflow, ps));
+        else
+            CU_TRY(c, launch_compact(a, S.chunk_excl.as<int64_t>(), c->d_pair_offsets.as<int64_t>() + B.p0,
+                                     c->d_dropped.as<uint8_t>() + B.p0, c->d_out.as<DMatch>(), c->out_capacity, d_overflow, ps));
+        c->stat_launches += 2;
+        if (c->profiling) { CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi + 2], ps)); c->prof_used = static_cast<int>(3 * (bi + 1)); }
+        CU_TRY(c, cudaEventRecord(S.post_done, ps));
     }
+    // join: everything after this on the compute stream (reorder, collect, homography, the next run) sees the finished lists
+    if (nb > 0) CU_TRY(c, cudaStreamWaitEvent(s, c->slot[(nb - 1) & 1].post_done, 0));
     if (sched && sched->order && n_pairs > 0) {
         // schedule order -> input order (swap the buffers so that collect / device_view see input order)
         CU_TRY(c, c->d_order.ensure(static_cast<size_t>(n_pairs) * 8));
@@ -671,9 +712,28 @@ int collect_impl(sfm_ctx* c, sfm_result** out) {
 // compute stream already matches the pairs whose two images are resident; pairs are scheduled by availability and the
 // lists are brought back to input order at the end.  Bank properties (integer-valued, norm range) are assumed and
 // verified after the fact; if the assumption fails the call falls back to the sequential path.
+static int from_host_body(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                          const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
+                          sfm_result** out);
+
 int from_host_impl(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
                    const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
                    sfm_result** out) {
+    const int rc = from_host_body(c, n_images, rows, n_rows, cols, step_bytes, depth, pairs, n_pairs, o, out);
+    if (rc != SFM_OK) {
+        // the pipelined path sets the bank's properties before the data has been verified: after a failure nothing may
+        // look resident (a later sfm_match_pairs would match against unverified or partly uploaded rows)
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        c->bank.n_images = 0; c->bank.have_tmap = false; c->bank.n_rows.clear();
+        c->run.valid = false;
+    }
+    return rc;
+}
+
+static int from_host_body(sfm_ctx* c, int n_images, const void* const* rows, const int32_t* n_rows, int cols,
+                          const size_t* step_bytes, int depth, const int32_t* pairs, int64_t n_pairs, const sfm_opts* o,
+                          sfm_result** out) {
     auto sequential = [&]() -> int {
         int rc = bank_upload_host(c, c->bank, n_images, rows, n_rows, cols, step_bytes, depth);
         if (rc != SFM_OK) return rc;
@@ -847,6 +907,11 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     auto bail = [&](const std::string& m) { g_create_error = m; sfm_ctx_destroy(c); return SFM_ERR_CUDA; };
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&c->post_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    for (int k = 0; k < 2; ++k) {
+        if ((e = cudaEventCreateWithFlags(&c->slot[k].knn_done, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+        if ((e = cudaEventCreateWithFlags(&c->slot[k].post_done, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
+    }
     for (int k = 0; k < 2; ++k)
         if ((e = cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
     if ((e = cudaEventCreateWithFlags(&c->meta_ev, cudaEventDisableTiming)) != cudaSuccess) return bail(cudaGetErrorString(e));
@@ -863,6 +928,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     size_t mb = 512;
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
+    if (const char* env = std::getenv("SFM_MIN_BATCHES")) { const int t = std::atoi(env); if (t >= 1 && t <= 64) c->min_batches = t; }
     if (const char* env = std::getenv("SFM_TCV_SPREAD_DIV")) { const int t = std::atoi(env); if (t >= 1) c->tcv_spread_div = t; }
     if (const char* env = std::getenv("SFM_TCV_NORMLESS")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_normless = t; }
     if (const char* env = std::getenv("SFM_TCV_CHUNK")) { const int t = std::atoi(env); if (t == 32 || t == 64) c->tcv_chunk = t; }
@@ -876,12 +942,14 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->post_stream) cudaStreamSynchronize(c->post_stream);
     dist_state_destroy(c);
+    c->slot[0].release(); c->slot[1].release();
+    if (c->post_stream) cudaStreamDestroy(c->post_stream);
     c->bank.release(); c->scratch.release();
     DevBuf* bufs[] = {&c->d_pairs, &c->d_rev_pairs, &c->d_unit_prefix, &c->d_rev_unit_prefix, &c->d_out_prefix, &c->d_t_prefix,
-                      &c->d_top2, &c->d_rev, &c->d_train_cnt, &c->d_chunk_counts, &c->d_chunk_excl, &c->d_pair_counts,
                       &c->d_pair_offsets, &c->d_dropped, &c->d_scalars, &c->d_out, &c->d_knn,
-                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_aux, &c->d_aux_rev, &c->d_hom, &c->d_bf, &c->d_blk_pair, &c->d_need, &c->d_pair_nb};
+                      &c->d_out2, &c->d_pair_offsets2, &c->d_dropped2, &c->d_order, &c->d_cnt_tmp, &c->d_hom};
     for (DevBuf* b : bufs) b->release();
     c->feat_kp.release(); c->feat_desc.release();
     sift_workspace_destroy(c->sift);
@@ -1351,19 +1419,19 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     CU_TRY(c, c->d_pairs.ensure(sizeof(Meta)));
     CU_TRY(c, cudaMemcpyAsync(c->d_pairs.p, &meta, sizeof(Meta), cudaMemcpyHostToDevice, s));
     CU_TRY(c, cudaStreamSynchronize(s));
-    CU_TRY(c, c->d_top2.ensure(static_cast<size_t>(pad_rows(nq)) * sizeof(Top2)));
+    CU_TRY(c, c->slot[0].top2.ensure(static_cast<size_t>(pad_rows(nq)) * sizeof(Top2)));
     const PairDesc* d_pd = c->d_pairs.as<PairDesc>();
     const int64_t* d_unit = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, unit_prefix));
     if (eng == Engine::TF32) {
-        CU_TRY(c, c->d_aux.ensure(static_cast<size_t>(pad_rows(nq)) * 4));
+        CU_TRY(c, c->slot[0].aux.ensure(static_cast<size_t>(pad_rows(nq)) * 4));
         CU_TRY(c, cudaMemsetAsync(c->d_scalars.as<uint8_t>() + 32, 0, 16, s));
     }
-    rc = launch_knn(c, b, eng, d_pd, d_unit, 1, meta.unit_prefix[1], c->d_top2.as<Top2>(), c->d_aux.as<float>());
+    rc = launch_knn(c, b, eng, d_pd, d_unit, 1, meta.unit_prefix[1], c->slot[0].top2.as<Top2>(), c->slot[0].aux.as<float>());
     if (rc != SFM_OK) return rc;
     if (eng == Engine::TF32) {
         RefineF32Args fa;
         fa.blk_pair = nullptr;
-        fa.top2 = c->d_top2.as<Top2>(); fa.aux = c->d_aux.as<float>(); fa.pairs = d_pd;
+        fa.top2 = c->slot[0].top2.as<Top2>(); fa.aux = c->slot[0].aux.as<float>(); fa.pairs = d_pd;
         fa.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
         fa.n_pairs = 1; fa.staged_rows = pad_rows(nq); fa.bank = b.d_f32.as<float>(); fa.fnorm2 = b.d_fnorm.as<float>();
         fa.nb_max = b.f_nb_max; fa.all_rows = 1; fa.swap_roles = 0; fa.ratio = 0.0;
@@ -1373,7 +1441,7 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     }
     if (eng == Engine::TC && k == 2) {
         RefineArgs ra{};
-        ra.top2 = c->d_top2.as<Top2>(); ra.pairs = d_pd;
+        ra.top2 = c->slot[0].top2.as<Top2>(); ra.pairs = d_pd;
         ra.out_prefix = reinterpret_cast<const int64_t*>(c->d_pairs.as<uint8_t>() + offsetof(Meta, out_prefix));
         ra.n_pairs = 1; ra.staged_rows = pad_rows(nq); ra.bank = b.d_u8.as<uint8_t>(); ra.norm2 = b.d_norm2.as<int32_t>();
         ra.all_rows = 1; ra.ratio = 0.0; ra.hamming = norm == SFM_NORM_HAMMING;
@@ -1384,7 +1452,7 @@ int sfm_knn_match(sfm_ctx* c, const void* query, int nq, size_t q_step, const vo
     CU_TRY(c, c->d_knn.ensure(2 * out_bytes));
     int32_t* d_idx = c->d_knn.as<int32_t>();
     float* d_dist = reinterpret_cast<float*>(c->d_knn.as<uint8_t>() + out_bytes);
-    CU_TRY(c, launch_top2_to_arrays(c->d_top2.as<Top2>(), nq, k, norm, d_idx, d_dist, s));
+    CU_TRY(c, launch_top2_to_arrays(c->slot[0].top2.as<Top2>(), nq, k, norm, d_idx, d_dist, s));
     c->stat_launches++;
     CU_TRY(c, c->h_knn.ensure(2 * out_bytes));
     CU_TRY(c, cudaMemcpyAsync(c->h_knn.p, d_idx, 2 * out_bytes, cudaMemcpyDeviceToHost, s));

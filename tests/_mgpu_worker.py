@@ -76,13 +76,18 @@ def main():
                 print("MISMATCH in", name, flush=True)
             ok = ok and same
         f5 = m.match_pairs(pairs, sfm.NORM_L2, min_match_count=20, distinct=True)
-        ok = ok and np.array_equal(g5.offsets, f5.offsets) and g5.matches.tobytes() == f5.matches.tobytes()
         f6 = m.match_pairs(pairs, sfm.NORM_L2, k=1, cross_check=True)
-        ok = ok and np.array_equal(g6.offsets, f6.offsets) and g6.matches.tobytes() == f6.matches.tobytes()
-        ok = ok and (np.array_equal(g[0], full.offsets) and g[1].tobytes() == full.matches.tobytes()
-              and np.array_equal(g[2], full.dropped))
-        ok = ok and (np.array_equal(g2[0], full.offsets) and g2[1].tobytes() == full.matches.tobytes()
-                     and np.array_equal(g2[2], full.dropped))
+        for name, g, f in (("distinct", g5, f5), ("cross-check", g6, f6)):
+            same = np.array_equal(g.offsets, f.offsets) and g.matches.tobytes() == f.matches.tobytes()
+            if not same:
+                print("MISMATCH in", name, int(g.offsets[-1]), int(f.offsets[-1]), flush=True)
+            ok = ok and same
+        for name, gg in (("torch gather (host)", g), ("torch gather (device)", g2)):
+            same = (np.array_equal(gg[0], full.offsets) and gg[1].tobytes() == full.matches.tobytes()
+                    and np.array_equal(gg[2], full.dropped))
+            if not same:
+                print("MISMATCH in", name, flush=True)
+            ok = ok and same
         print("MGPU_IDENTICAL" if ok else "MGPU_MISMATCH", int(full.offsets[-1]), flush=True)
     m.close()
     dist.barrier()

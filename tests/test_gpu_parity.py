@@ -469,3 +469,73 @@ def test_pipelined_from_host_equals_two_call_form(sfm, matcher):
     ref3 = matcher.match_pairs(pairs[:40], NORM_L2, ratio=0.95)
     got3 = matcher.match_pairs_from_host([x.numpy() for x in big], pairs[:40], NORM_L2, ratio=0.95)
     assert got3.matches.tobytes() == ref3.matches.tobytes()
+
+
+# ------------------------------------------------------------------ BASELINE shapes C5 / C4 under the default settings
+def test_c5_shape_pair_default_layout_vs_oracle(sfm):
+    """C5's shape: 16 384-row images under the DEFAULT epilogue layout (12: two groups, 32-bit keys number 512 chunks per
+    warp) against the C oracle — both directions of one pair, plus the pair against a ragged 16 001-row image."""
+    from oracle import oracle_c
+    m = sfm.Matcher(0)
+    try:
+        bank = workloads.sift_like_bank(3, 16384)
+        bank[2] = bank[2][:16001]
+        pairs = np.array([(0, 1), (1, 0), (1, 2), (2, 1)], np.int32)
+        m.upload_bank([b.astype(np.float32) for b in bank])
+        res = m.match_pairs(pairs, NORM_L2)
+        exp = oracle_c.match_pairs(bank, pairs, NORM_L2)
+        for p in range(len(pairs)):
+            assert orc.dmatch_equal(res[p], exp[p]), pairs[p].tolist()
+        assert len(res[0]) > 1000
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("settings", [{}, {"SFM_TCV_NORMLESS": "0", "SFM_TCV_CHUNK": "32"}, {"SFM_TCV_NORMLESS": "0", "SFM_TCV_CHUNK": "64"},
+                                      {"SFM_TCV_NORMLESS": "2", "SFM_TCV_CHUNK": "32"}])
+def test_c4_shape_grid_list_dense_branch(sfm, settings, monkeypatch):
+    """C4's shape: 4 096-row images, grid pairing (neighbouring shots share 30 % planted rows: the DENSE branch, 7 % of the
+    rows re-ranked).  64 images as an 8 x 8 grid, sequenceLength 3: every variant the adaptive choice can land on gives the
+    same bytes; a sample of the pairs is checked against the C oracle, the whole list against the independent CUDA-core
+    (dp4a) engine."""
+    from oracle import oracle_c
+    for k, v in settings.items():
+        monkeypatch.setenv(k, v)
+    m = sfm.Matcher(0)
+    try:
+        bank = workloads.sift_like_bank(64, 4096)
+        pairs = sfm.select_pairs(64, 3, 8)
+        assert len(pairs) == len(orc.select_pairs(64, 3, 8)) and len(pairs) > 200
+        m.upload_bank(bank)
+        res = m.match_pairs(pairs, NORM_L2)
+        res2 = m.match_pairs(pairs, NORM_L2)                    # second run: the adaptive feedback of the first has arrived
+        assert np.array_equal(res.offsets, res2.offsets) and res.matches.tobytes() == res2.matches.tobytes()
+        simt = m.match_pairs(pairs, NORM_L2, engine=sfm.ENGINE_SIMT)
+        assert np.array_equal(res.offsets, simt.offsets) and res.matches.tobytes() == simt.matches.tobytes()
+        rng = np.random.default_rng(4)
+        sample = np.sort(rng.choice(len(pairs), 12, replace=False))
+        exp = oracle_c.match_pairs(bank, pairs[sample], NORM_L2)
+        for k, p in enumerate(sample):
+            assert orc.dmatch_equal(res[p], exp[k]), pairs[p].tolist()
+        assert int(res.offsets[-1]) > 20000                     # the neighbours really share matches
+    finally:
+        m.close()
+
+
+def test_from_host_failure_leaves_no_half_built_bank(sfm):
+    """A failing sfm_match_pairs_from_host must not leave a bank that later calls would match garbage against."""
+    import torch
+    m = sfm.Matcher(0)
+    try:
+        bank = [torch.from_numpy(b.astype(np.float32)).pin_memory().numpy() for b in workloads.sift_like_bank(16, 300)]
+        bad = np.array([(0, 1), (3, 99)], np.int32)
+        with pytest.raises(sfm.SfmError):
+            m.match_pairs_from_host(bank, bad, NORM_L2)
+        with pytest.raises(sfm.SfmError) as e:
+            m.match_pairs([[0, 1]], NORM_L2)
+        assert e.value.code == sfm.ERR_STATE
+        good = m.match_pairs_from_host(bank, [[0, 1], [1, 2]], NORM_L2)
+        exp = orc.match_pairs([b.astype(np.uint8) for b in bank], [[0, 1], [1, 2]], NORM_L2)
+        assert orc.dmatch_equal(good[0], exp[0]) and orc.dmatch_equal(good[1], exp[1])
+    finally:
+        m.close()

@@ -148,3 +148,25 @@ def test_extracted_features_feed_the_matching_stage(m, sfm):
     assert np.median(np.abs(dx - 5)) < 0.1 and np.median(np.abs(dy - 3)) < 0.1
     h = m.homography_inlier_ratios(3.0, seed=1)
     assert h["ratio"][0] > 0.8 and h["ratio"][1] == -1
+
+
+@pytest.mark.parametrize("n_layers,sigma,edge,ct", [(2, 1.6, 10.0, 0.04), (4, 1.2, 5.0, 0.04), (5, 2.0, 20.0, 0.09)])
+def test_non_default_detector_parameters_equal_restatement(m, n_layers, sigma, edge, ct):
+    """cv::SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma) with values other than the
+    reference's (3, 10, 1.6): pyramid depth, blur schedule and the edge test all change.  Device == restatement with the
+    SAME keypoint count."""
+    img = workloads.synthetic_photo(9, 180, 260)
+    m.features_clear()
+    n = m.extract_sift(img, contrast_threshold=ct, n_octave_layers=n_layers, edge_threshold=edge, sigma=sigma)
+    kp, desc = m.features_download(0)
+    kp_o, desc_o = S.detect_and_compute(img, n_layers=n_layers, contrast_threshold=ct, edge_threshold=edge, sigma=sigma)
+    assert n == len(kp) == len(kp_o), (n, len(kp_o))
+    assert len(kp) > 20
+    sc.assert_close(kp_o, desc_o.astype(np.uint8), kp, desc, f"layers {n_layers} sigma {sigma} edge {edge}")
+    base = S.create_initial_image(img, sigma=sigma)
+    gpyr = S.build_gaussian_pyramid(base, S.n_octaves_for(base.shape), n_layers=n_layers, sigma=sigma)
+    for o in (0, 1):
+        for i in (0, n_layers + 2):
+            got = m.pyramid_level(o, i)
+            exp = gpyr[o * (n_layers + 3) + i]
+            assert got.shape == exp.shape and np.abs(got - exp).max() < 1e-4, (o, i)
