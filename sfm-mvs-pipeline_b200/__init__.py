@@ -174,6 +174,41 @@ class MatchResult:
         return np.diff(self.offsets)
 
 
+class MatchResultView:
+    """The library-owned result itself: numpy VIEWS of the pinned host buffers the lists were copied into (no second copy).
+    Valid until release() — call it (or use `with`) before the producing context is closed."""
+
+    def __init__(self, res):
+        self._res = res
+        n = _lib.sfm_result_n_pairs(res)
+        self.offsets = np.ctypeslib.as_array(_lib.sfm_result_offsets(res), shape=(n + 1,))
+        total = int(self.offsets[n])
+        self.dropped = np.ctypeslib.as_array(_lib.sfm_result_dropped(res), shape=(n,)) if n else np.zeros(0, np.uint8)
+        if total:
+            buf = (C.c_char * (total * 16)).from_address(_lib.sfm_result_matches(res))
+            self.matches = np.frombuffer(buf, dtype=DMATCH_DTYPE, count=total)
+        else:
+            self.matches = np.zeros(0, DMATCH_DTYPE)
+
+    def release(self):
+        if self._res:
+            self.offsets = self.matches = self.dropped = None
+            _lib.sfm_result_free(self._res)
+            self._res = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class Matcher:
     """One context = one GPU.  Mirrors the role of the injected cv::Ptr<cv::DescriptorMatcher> plus the
     strategy object of the reference (SfM.cpp:52-65)."""
@@ -325,16 +360,16 @@ class Matcher:
         return list(ms)
 
     def dist_match_pairs(self, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False, min_match_count=0,
-                         engine=ENGINE_AUTO):
+                         engine=ENGINE_AUTO, view=False):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         o = self._opts(norm, k, ratio, cross_check, distinct, min_match_count, engine)
         res = C.c_void_p()
         self._check(_lib.sfm_dist_match_pairs(self._ctx, pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)), C.byref(o),
                                               C.byref(res)))
-        return self._wrap_result(res) if res else None
+        return (self._view_result(res) if view else self._wrap_result(res)) if res else None
 
     def dist_match_pairs_from_host(self, descriptors, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False,
-                                   min_match_count=0, engine=ENGINE_AUTO):
+                                   min_match_count=0, engine=ENGINE_AUTO, view=False):
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         keep, ptrs, nrows, steps, cols, depth = self._bank_args(descriptors)
         o = self._opts(norm, k, ratio, cross_check, distinct, min_match_count, engine)
@@ -342,12 +377,16 @@ class Matcher:
         self._check(_lib.sfm_dist_match_pairs_from_host(self._ctx, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps,
                                                         C.c_int(depth), pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
                                                         C.byref(o), C.byref(res)))
-        return self._wrap_result(res) if res else None
+        return (self._view_result(res) if view else self._wrap_result(res)) if res else None
 
     def collect(self) -> MatchResult:
         res = C.c_void_p()
         self._check(_lib.sfm_match_pairs_collect(self._ctx, C.byref(res)))
         return self._wrap_result(res)
+
+    @staticmethod
+    def _view_result(res) -> "MatchResultView":
+        return MatchResultView(res)
 
     @staticmethod
     def _wrap_result(res) -> MatchResult:
@@ -543,16 +582,16 @@ class MultiGpuMatcher:
         self._check(_lib.sfm_mgpu_bank_upload(self._g, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps, C.c_int(depth)))
 
     def match_pairs(self, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False, min_match_count=0,
-                    engine=ENGINE_AUTO) -> MatchResult:
+                    engine=ENGINE_AUTO, view=False) -> MatchResult:
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         o = Matcher._opts(None, norm, k, ratio, cross_check, distinct, min_match_count, engine)
         res = C.c_void_p()
         self._check(_lib.sfm_mgpu_match_pairs(self._g, pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)), C.byref(o),
                                               C.byref(res)))
-        return Matcher._wrap_result(res)
+        return Matcher._view_result(res) if view else Matcher._wrap_result(res)
 
     def match_pairs_from_host(self, descriptors, pairs, norm, k=2, ratio=0.7, cross_check=False, distinct=False,
-                              min_match_count=0, engine=ENGINE_AUTO) -> MatchResult:
+                              min_match_count=0, engine=ENGINE_AUTO, view=False) -> MatchResult:
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         keep, ptrs, nrows, steps, cols, depth = Matcher._bank_args(None, descriptors)
         o = Matcher._opts(None, norm, k, ratio, cross_check, distinct, min_match_count, engine)
@@ -560,4 +599,4 @@ class MultiGpuMatcher:
         self._check(_lib.sfm_mgpu_match_pairs_from_host(self._g, C.c_int(len(keep)), ptrs, nrows, C.c_int(cols), steps,
                                                         C.c_int(depth), pairs.ctypes.data_as(C.c_void_p), C.c_int64(len(pairs)),
                                                         C.byref(o), C.byref(res)))
-        return Matcher._wrap_result(res)
+        return Matcher._view_result(res) if view else Matcher._wrap_result(res)

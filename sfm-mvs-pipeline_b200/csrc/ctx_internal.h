@@ -110,14 +110,15 @@ struct NvtxRange {
 struct BatchSlot {
     DevBuf top2, rev;                // raw top-2 / candidate records per staging row (rev: roles swapped, cross-check)
     DevBuf aux, aux_rev;             // fifth-best chunk maximum per staging row (norm-less and 3xTF32 paths)
-    DevBuf need, bf;                 // value-only path: rows that survived the fused ratio bound; rows that need the whole train image
+    DevBuf need, bf, done;           // value-only path: rows that survived the fused ratio bound (for the post pass); rows that need
+                                     // the whole train image; rows re-ranked by the refine warps inside the knn kernel
     DevBuf keep;                     // value-only path: one keep bit per staging row
-    DevBuf counters;                 // [0] brute-force queue length, [1] need-list length
+    DevBuf counters;                 // [0] brute-force queue length, [1] need-list length, [2] done-list length
     DevBuf blk_pair;                 // pair index of every 256-row staging block
     DevBuf chunk_counts, chunk_excl, pair_counts, pair_nb, train_cnt;
     cudaEvent_t knn_done = nullptr, post_done = nullptr;
     void release() {
-        DevBuf* all[] = {&top2, &rev, &aux, &aux_rev, &need, &bf, &keep, &counters, &blk_pair, &chunk_counts, &chunk_excl, &pair_counts, &pair_nb, &train_cnt};
+        DevBuf* all[] = {&top2, &rev, &aux, &aux_rev, &need, &bf, &done, &keep, &counters, &blk_pair, &chunk_counts, &chunk_excl, &pair_counts, &pair_nb, &train_cnt};
         for (DevBuf* b : all) b->release();
         if (knn_done) cudaEventDestroy(knn_done);
         if (post_done) cudaEventDestroy(post_done);
@@ -198,6 +199,8 @@ struct sfm_ctx {
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
+    bool tcv_inkernel_refine = true; // SFM_TCV_INKERNEL_REFINE = 0: survivors of the fused ratio bound go to the post pass instead of
+                                     // the knn CTA's own refine warps
     int min_batches = 6;             // a long pair list is cut into at least this many batches (SFM_MIN_BATCHES): post kernels of
                                      // batch i overlap the knn kernel of batch i + 1
     void* dist = nullptr;            // multi-GPU group membership (sfmhost::DistState, csrc/dist.cu)

@@ -132,6 +132,7 @@ struct DistState {
     uint64_t deal_key = 0;
     std::vector<int32_t> owner;
     std::vector<int32_t> my_pairs;                 // [2 * n_mine]
+    std::vector<int32_t> all_pairs;                // [2 * n_pairs], participant 0 only
     std::vector<int64_t> seg_start;                // world + 1: first gathered position of every participant
     std::vector<int64_t> gorder;                   // gathered position -> input pair index
     bool gorder_on_device = false;
@@ -192,6 +193,7 @@ static int prepare_deal(sfm_ctx* c, DistState* d, const int32_t* pairs, int64_t 
         d->gorder[fill[d->owner[p]]++] = p;
         if (d->owner[p] == d->rank) { d->my_pairs.push_back(pairs[2 * p]); d->my_pairs.push_back(pairs[2 * p + 1]); }
     }
+    if (d->rank == 0) d->all_pairs.assign(pairs, pairs + 2 * n_pairs);
     d->gorder_on_device = false;
     d->deal_key = key;
     return SFM_OK;
@@ -326,7 +328,16 @@ static int gather_impl(sfm_ctx* c, DistState* d, int64_t n_pairs, sfm_result** o
     r->offsets.as<int64_t>()[n_pairs] = grand;
     c->stat_d2h += n_pairs * 9 + grand * static_cast<int64_t>(sizeof(DMatch));
     d->phase_ms[4] = ms_since(t0);
-    // the gathered result is not a run of THIS context's bank order: later stages (homography) work per participant
+    // participant 0 adopts the gathered lists as ITS last run: the device-resident lists of the whole pair list are what the
+    // next stage (sfm_homography_inlier_ratios on sfm_mgpu_ctx(g, 0) / this context) works on
+    if (n_pairs > 0) {
+        std::swap(c->d_out, c->d_out2);
+        std::swap(c->d_pair_offsets, c->d_pair_offsets2);
+        std::swap(c->d_dropped, c->d_dropped2);
+        CU_TRY(c, cudaMemcpyAsync(c->d_scalars.p, d->d_grand.p, 8, cudaMemcpyDeviceToDevice, s));
+        c->run.n_pairs = n_pairs;
+        c->run.pairs.assign(d->all_pairs.begin(), d->all_pairs.end());
+    }
     *out = r;
     return SFM_OK;
 }

@@ -37,6 +37,16 @@ struct TcvFuse {
     int32_t* need_list;          // capacity = staged rows of the batch
     int* need_count;
     double ratio;
+    // in-kernel re-rank (norm-less variant, 8 epilogue warps): four extra warps of the CTA take the surviving rows from a
+    // shared-memory queue, re-rank them exactly (refine_dot_row) and append them to done_list; rows they cannot decide go
+    // to bf_list.  refine = 0: survivors go to need_list for the post pass instead.
+    int refine;
+    const uint8_t* bank;
+    int32_t* done_list;
+    int* done_count;
+    int32_t* bf_list;
+    int* bf_count;
+    unsigned long long* stats;
 };
 cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_host, const void* tmap_e_host,
                                   const PairDesc* pairs, const int64_t* unit_prefix, int n_pairs, int64_t n_units,
@@ -81,8 +91,12 @@ struct FilterArgs {
     const int32_t* blk_pair;     // pair of every 256-row staging block (launch_block_pairs), or null: binary search
     // sparse form (value-only tcgen05 path, see post.cu): one keep bit per staging row, set for rows of need_list only
     uint32_t* keep_bits;         // null: dense form (every staging row carries a Top2 record)
-    const int32_t* need_list;
+    const int32_t* need_list;    // rows re-ranked by the post pass
     const int* need_count;
+    const int32_t* done_list;    // rows re-ranked by the refine warps inside the knn kernel (may be null)
+    const int* done_count;
+    const int32_t* bf_list;      // rows finished by brute_force_rows_kernel (may be null)
+    const int* bf_count;
 };
 // tcgen05 path only: tighten the provisional second neighbour (see refine_second_kernel in post.cu)
 struct RefineArgs {

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "refine_dot.cuh"
 
 namespace sfm {
 
@@ -58,6 +59,19 @@ struct Cfg {
     static constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
     static constexpr uint32_t kIdescExt = umma_idesc_u8s8(BM, BN);
 };
+// In-kernel re-rank (kRefine): rows that survive the fused ratio bound are handed to four refine warps of the same CTA
+// through a shared-memory ticket queue (multi-producer: the four warps of epilogue group 0; multi-consumer: the refine
+// warps).  The queue lives where the digit tiles of the kNorm variant would (the norm-less variant loads none).
+struct __align__(16) QRec {
+    Top2 t;                                    // candidate record (chunks, V1, V2)
+    int64_t srow;
+    int32_t v5, na, qrow, tr0, ntr, nbmin, nbmax;
+    uint32_t seq;                              // ticket + 1 once the record is complete
+};
+static_assert(sizeof(QRec) == 64, "queue record");
+struct QCtl { uint32_t reserved, claimed, freed, producers_done; };
+constexpr int kQCap = 256;                     // records; producers divert to the global need list above kQHigh outstanding
+constexpr int kQHigh = 96;                     // 96 + 4 producer warps x 32 rows + 4 claimed tickets < kQCap
 }  // namespace tcv
 
 struct UnitInfoV { PairDesc pd; int rb; int n_tiles; };
@@ -145,8 +159,8 @@ __device__ __forceinline__ void top3_max64(int64_t k, int64_t& m1, int64_t& m2, 
 // kCC = columns (train rows) per chunk: 32 or 64.  The epilogue is ALU-bound (ncu: ALU pipe 67 %, 0.85 instructions per
 // accumulator element with 32-column chunks); the per-chunk bookkeeping (key, top-4/5 insert) halves with 64-column chunks,
 // the refine pass then recomputes 64 train rows per candidate chunk.
-template <int kParity, int kHalves, int kBN, bool kNorm, int kCC>
-__global__ void __launch_bounds__(128 + 128 * kParity * kHalves, 1)
+template <int kParity, int kHalves, int kBN, bool kNorm, int kCC, bool kRefine = false>
+__global__ void __launch_bounds__(128 + 128 * kParity * kHalves + (kRefine ? 128 : 0), 1)
 knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_e, const PairDesc* __restrict__ pairs,
                       const int64_t* __restrict__ unit_prefix, int n_pairs, int64_t n_units, Top2* __restrict__ out,
@@ -158,7 +172,9 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr int offBar = C::offBar, offTmemPtr = C::offTmemPtr;
     constexpr uint32_t kIdesc = C::kIdesc, kIdescExt = C::kIdescExt;
     constexpr int kGroups = kParity * kHalves;
-    constexpr int kThreads = 128 + 128 * kGroups;
+    constexpr int kThreads = 128 + 128 * kGroups + (kRefine ? 128 : 0);
+    static_assert(!kRefine || (!kNorm && kGroups == 2), "refine warps: norm-less variant with 8 epilogue warps (512 threads x 128 registers)");
+    static_assert(!kRefine || kQCap * static_cast<int>(sizeof(QRec)) + 64 <= C::kBStages * C::kEBytes, "queue fits the unused digit-tile area");
     constexpr int kLoadsPerVisit = BN / 32 / kHalves;               // 32-column tcgen05.ld one warp issues per tile
     constexpr int kChunksPerVisit = BN / kCC / kHalves;             // chunks one warp reads per tile
     static_assert(kCC == 32 || kCC == 64, "chunk = one or two 32-column loads");
@@ -197,6 +213,12 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     for (int i = threadIdx.x; i < kAExtBytes / 4; i += kThreads) {
         const int word = i & 3;                                     // word inside a 16-byte half
         reinterpret_cast<uint32_t*>(base_ptr + offAExt)[i] = word < 3 ? 0xFFFFFFFFu : 0x01010101u;
+    }
+    QRec* ring = reinterpret_cast<QRec*>(base_ptr + offE);
+    QCtl* qctl = reinterpret_cast<QCtl*>(base_ptr + offE + kQCap * sizeof(QRec));
+    if (kRefine) {
+        for (int i = threadIdx.x; i < kQCap; i += kThreads) ring[i].seq = 0;
+        if (threadIdx.x == 0) { qctl->reserved = 0; qctl->claimed = 0; qctl->freed = 0; qctl->producers_done = 0; }
     }
     fence_proxy_async();                                            // generic-proxy writes -> visible to the MMA
     tc_fence_before();
@@ -282,7 +304,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             tile0 += u.n_tiles;
             ++unit_iter;
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * kGroups) {
         // ================================================================ epilogue: top-4 of chunk maxima per query row
         // 16 warps = 4 groups; group g works on the tiles of parity (g & 1) and on the column half (g >> 1), so four
         // tcgen05.ld are in flight per SM sub-partition (the loads are latency- not bandwidth-limited).
@@ -440,19 +462,85 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, need);
                 if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(fz.need_count, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (need) {
-                        const int64_t srow = u.pd.out_row0 + row;
-                        out[srow] = o;
-                        if (!kNorm) aux[srow] = has[4] ? vv[4] : 0;
-                        fz.need_list[base + __popc(bal & ((1u << lane) - 1))] = static_cast<int32_t>(srow);
+                    const int rank = __popc(bal & ((1u << lane) - 1));
+                    const int64_t srow = u.pd.out_row0 + row;
+                    int to_ring = 0;
+                    uint32_t ticket0 = 0;
+                    if (kRefine && fz.refine) {
+                        // hand the rows to this CTA's refine warps unless they are behind (then: the post pass)
+                        if (lane == 0) {
+                            const uint32_t res = *reinterpret_cast<volatile uint32_t*>(&qctl->reserved);
+                            const uint32_t fre = *reinterpret_cast<volatile uint32_t*>(&qctl->freed);
+                            to_ring = (res - fre) <= static_cast<uint32_t>(kQHigh);
+                            if (to_ring) ticket0 = atomicAdd(&qctl->reserved, static_cast<uint32_t>(__popc(bal)));
+                        }
+                        to_ring = __shfl_sync(0xffffffffu, to_ring, 0);
+                        ticket0 = __shfl_sync(0xffffffffu, ticket0, 0);
+                    }
+                    if (to_ring) {
+                        if (need) {
+                            const uint32_t ticket = ticket0 + rank;
+                            QRec* q = ring + (ticket % kQCap);
+                            q->t = o; q->srow = srow; q->v5 = has[4] ? vv[4] : 0; q->na = __ldg(fz.norm2 + u.pd.q_row0 + row);
+                            q->qrow = u.pd.q_row0 + row; q->tr0 = u.pd.t_row0; q->ntr = u.pd.nt; q->nbmin = nbmin; q->nbmax = nbmax;
+                            __threadfence_block();
+                            *reinterpret_cast<volatile uint32_t*>(&q->seq) = ticket + 1;
+                        }
+                    } else {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(fz.need_count, __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (need) {
+                            out[srow] = o;
+                            if (!kNorm) aux[srow] = has[4] ? vv[4] : 0;
+                            fz.need_list[base + rank] = static_cast<int32_t>(srow);
+                        }
                     }
                 }
             }
             asm volatile("bar.sync 2, %0;" ::"n"(128 * kGroups) : "memory");
         }
+        if (kRefine && group == 0) {
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&qctl->producers_done, 1u);
+        }
+    } else if (kRefine && warp >= kEpiWarp0 + 4 * kGroups) {
+        // ================================================================ refine warps: exact re-rank of the surviving rows
+        // Ticket queue: a warp takes the next ticket and waits until that slot is published (or until every producer has
+        // finished and the ticket was never issued).  The record is copied to registers and the slot released before the
+        // re-rank, which runs on L2-resident bank rows (__dp4a) beside the epilogue — ~0.5 % of the rows on an all-pairs list.
+        RefineCtx rc;
+        rc.bank = fz.bank; rc.norm2 = fz.norm2; rc.top2 = out; rc.stats = fz.stats; rc.bf_list = fz.bf_list; rc.bf_count = fz.bf_count;
+        rc.chunk_rows = kCC; rc.all_rows = 0; rc.ratio = fz.ratio;
+        unsigned long long n_rows_done = 0;
+        if (fz.refine) {
+            for (;;) {
+                uint32_t ticket = 0;
+                if (lane == 0) ticket = atomicAdd(&qctl->claimed, 1u);
+                ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                QRec* q = ring + (ticket % kQCap);
+                bool have = false;
+                for (;;) {
+                    if (*reinterpret_cast<volatile uint32_t*>(&q->seq) == ticket + 1) { have = true; break; }
+                    if (*reinterpret_cast<volatile uint32_t*>(&qctl->producers_done) == 4u &&
+                        ticket >= *reinterpret_cast<volatile uint32_t*>(&qctl->reserved)) break;
+                    __nanosleep(200);
+                }
+                have = __shfl_sync(0xffffffffu, have ? 1 : 0, 0) != 0;       // one decision per warp
+                if (!have) break;
+                __threadfence_block();
+                const Top2 t = q->t;
+                const int64_t srow = q->srow;
+                const int v5 = q->v5, na = q->na, qrow = q->qrow, tr0 = q->tr0, ntr = q->ntr, nbmin = q->nbmin, nbmax = q->nbmax;
+                __syncwarp();
+                if (lane == 0) atomicAdd(&qctl->freed, 1u);                   // the slot may be reused
+                refine_dot_row(rc, srow, lane, t, v5, na, qrow, tr0, ntr, nbmin, nbmax);
+                if (lane == 0) fz.done_list[atomicAdd(fz.done_count, 1)] = static_cast<int32_t>(srow);
+                ++n_rows_done;
+            }
+        }
+        if (lane == 0 && n_rows_done && fz.stats) atomicAdd(fz.stats, n_rows_done);
     }
 
     tc_fence_before();
@@ -460,15 +548,15 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int kParity, int kHalves, int kBN, bool kNorm, int kCC>
+template <int kParity, int kHalves, int kBN, bool kNorm, int kCC, bool kRefine = false>
 static cudaError_t launch_tcv(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& te, const PairDesc* pairs,
                               const int64_t* unit_prefix, int n_pairs, int64_t n_units, Top2* out, int32_t* aux, int grid,
                               int issuers, const TcvFuse& fz, cudaStream_t s) {
     // per launch: the attribute is per device, and one process may drive several GPUs
-    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC>,
+    cudaError_t e = cudaFuncSetAttribute(knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC, kRefine>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, tcv::Cfg<kBN>::kSmemBytes);
     if (e != cudaSuccess) return e;
-    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC><<<grid, 128 + 128 * kParity * kHalves, tcv::Cfg<kBN>::kSmemBytes, s>>>(
+    knn2_l2_u8_tcv_kernel<kParity, kHalves, kBN, kNorm, kCC, kRefine><<<grid, 128 + 128 * kParity * kHalves + (kRefine ? 128 : 0), tcv::Cfg<kBN>::kSmemBytes, s>>>(
         ta, tb, te, pairs, unit_prefix, n_pairs, n_units, out, aux, issuers, fz);
     return cudaGetLastError();
 }
@@ -486,6 +574,11 @@ cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_ho
     const CUtensorMap* tb = static_cast<const CUtensorMap*>(tmap_b_host);
     const CUtensorMap* te = static_cast<const CUtensorMap*>(tmap_e_host);
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
+    if (fz.refine && aux && layout == 12 && tile_rows == 256) {
+        // norm-less variant with in-kernel re-rank: 8 epilogue warps + 4 refine warps
+        if (chunk_rows == 64) return launch_tcv<1, 2, 256, false, 64, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s);
+        return launch_tcv<1, 2, 256, false, 32, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s);
+    }
 #define SFM_TCV_CASE(P, H, T)                                                                                          \
     if (layout == 10 * P + H && tile_rows == T) {                                                                      \
         if (chunk_rows == 64)                                                                                          \

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "refine_dot.cuh"
 
 namespace sfm {
 
@@ -227,26 +228,41 @@ __device__ __forceinline__ bool keep_bit(const uint32_t* __restrict__ bits, int6
 }
 
 __global__ void __launch_bounds__(256) mark_keep_kernel(FilterArgs a) {
-    const int n = *a.need_count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int64_t srow = a.need_list[i];
-        const RowCtx c = load_row(a, srow);
-        float d;
-        if (keep_basic(a, c, d)) {
-            atomicOr(a.keep_bits + (srow >> 5), 1u << (srow & 31));
-            if (a.fp.distinct) atomicAdd(a.train_cnt + a.t_prefix[c.p] + c.t.i0, 1);
+    // the rows that carry a final Top2 record sit in up to three lists: re-ranked by the post pass (need_list), re-ranked by
+    // the refine warps inside the knn kernel (done_list), finished by brute force (bf_list; may repeat rows of the other two)
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+        const int32_t* list = l == 0 ? a.need_list : (l == 1 ? a.done_list : a.bf_list);
+        const int* cnt = l == 0 ? a.need_count : (l == 1 ? a.done_count : a.bf_count);
+        if (!list) continue;
+        const int n = *cnt;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int64_t srow = list[i];
+            const RowCtx c = load_row(a, srow);
+            float d;
+            if (keep_basic(a, c, d)) {
+                const uint32_t bit = 1u << (srow & 31);
+                const uint32_t old = atomicOr(a.keep_bits + (srow >> 5), bit);
+                if (a.fp.distinct && !(old & bit)) atomicAdd(a.train_cnt + a.t_prefix[c.p] + c.t.i0, 1);
+            }
         }
     }
 }
 
 // distinct filter, second pass: kept rows whose best train row is shared lose their bit (SfM.cpp:547-564)
 __global__ void __launch_bounds__(256) distinct_prune_kernel(FilterArgs a) {
-    const int n = *a.need_count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int64_t srow = a.need_list[i];
-        if (!keep_bit(a.keep_bits, srow)) continue;
-        const RowCtx c = load_row(a, srow);
-        if (a.train_cnt[a.t_prefix[c.p] + c.t.i0] != 1) atomicAnd(a.keep_bits + (srow >> 5), ~(1u << (srow & 31)));
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+        const int32_t* list = l == 0 ? a.need_list : (l == 1 ? a.done_list : a.bf_list);
+        const int* cnt = l == 0 ? a.need_count : (l == 1 ? a.done_count : a.bf_count);
+        if (!list) continue;
+        const int n = *cnt;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int64_t srow = list[i];
+            if (!keep_bit(a.keep_bits, srow)) continue;
+            const RowCtx c = load_row(a, srow);
+            if (a.train_cnt[a.t_prefix[c.p] + c.t.i0] != 1) atomicAnd(a.keep_bits + (srow >> 5), ~(1u << (srow & 31)));
+        }
     }
 }
 
@@ -429,61 +445,6 @@ __global__ void __launch_bounds__(256) refine_second_kernel(RefineArgs a) {
 //   bounds: d0^2 >= |a|^2 - 2 D1 and d1^2 <= |a|^2 - 2 D2 + 1  (the parity bit of |b|^2 is in [0,1]); sqrtf and the
 //   double product are monotonic, so  sqrtf(lo0) >= ratio * sqrtf(hi1)  implies the real test fails.
 // One warp per row that needs work: lane = train row of the chunk, 32 x __dp4a, lexicographic (d^2, idx) keys.
-__device__ __forceinline__ void warp_chunk_candidates(const uint8_t* __restrict__ bank, const int32_t* __restrict__ norm2,
-                                                      const uint4 (&q)[8], int na, int tr0, int ntr, int chunk, int lane,
-                                                      long long& a1, long long& a2) {
-    const int j = chunk * 32 + lane;
-    const uint4* tv = reinterpret_cast<const uint4*>(bank + (static_cast<size_t>(tr0) + j) * 128);
-    uint32_t dot = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint4 y = __ldg(tv + i);
-        dot = __dp4a(q[i].x, y.x, dot); dot = __dp4a(q[i].y, y.y, dot);
-        dot = __dp4a(q[i].z, y.z, dot); dot = __dp4a(q[i].w, y.w, dot);
-    }
-    if (j < ntr) {
-        const int32_t d = na + norm2[tr0 + j] - 2 * static_cast<int32_t>(dot);
-        const long long key = (static_cast<long long>(d) << 32) | static_cast<unsigned>(j);
-        a2 = min(a2, max(a1, key));
-        a1 = min(a1, key);
-    }
-}
-
-// exact top-2 over the WHOLE train image for one query row, one warp: four 32-row groups per step so that their loads
-// are in flight together (a warp that has to brute-force a row is the tail of the refine kernels)
-__device__ __forceinline__ void warp_brute_force(const uint8_t* __restrict__ bank, const int32_t* __restrict__ norm2,
-                                                 const uint4 (&q)[8], int na, int tr0, int ntr, int lane, long long& a1,
-                                                 long long& a2) {
-    const int groups = (ntr + 31) / 32;
-    int c = 0;
-    for (; c + 4 <= groups; c += 4) {
-        uint32_t dot[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint4 y[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-                y[g] = __ldg(reinterpret_cast<const uint4*>(bank + (static_cast<size_t>(tr0) + (c + g) * 32 + lane) * 128) + i);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                dot[g] = __dp4a(q[i].x, y[g].x, dot[g]); dot[g] = __dp4a(q[i].y, y[g].y, dot[g]);
-                dot[g] = __dp4a(q[i].z, y[g].z, dot[g]); dot[g] = __dp4a(q[i].w, y[g].w, dot[g]);
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int j = (c + g) * 32 + lane;
-            if (j < ntr) {
-                const int32_t d = na + norm2[tr0 + j] - 2 * static_cast<int32_t>(dot[g]);
-                const long long key = (static_cast<long long>(d) << 32) | static_cast<unsigned>(j);
-                a2 = min(a2, max(a1, key));
-                a1 = min(a1, key);
-            }
-        }
-    }
-    for (; c < groups; ++c) warp_chunk_candidates(bank, norm2, q, na, tr0, ntr, c, lane, a1, a2);
-}
-
 // one warp per row that survived the fused ratio bound of the knn kernel (persistent grid over need_list)
 __global__ void __launch_bounds__(256, 4) refine_value_rows_kernel(RefineArgs a) {
     const int lane = threadIdx.x & 31;
@@ -553,129 +514,11 @@ __global__ void __launch_bounds__(256, 4) refine_value_rows_kernel(RefineArgs a)
 //     reported (d0, idx0) never depends on d1.  In that case d1 is written as the end that was used (keep_basic re-runs
 //     the same comparison); the lists equal cv::BFMatcher + ratio test bit for bit.
 // (3) anything else (not certified, or the two ends disagree) is brute-forced over the whole train image.
-// one warp, one query row that survived the quick reject: stages (2a), (2b), (3) of the comment above.  All arguments are
-// warp-uniform; lane 0 writes the row (or queues it for brute_force_rows_kernel).
-__device__ __forceinline__ void refine_dot_row(const RefineArgs& a, int64_t srow, int lane, const Top2 t, int rv5, int rna,
-                                               int qrow, int tr0, int ntr, int nbmin, int nbmax) {
-    const float inf = __int_as_float(0x7f800000);
-    const int i0 = t.i0, i1 = t.i1;
-    uint4 q[8];
-    const uint4* qv = reinterpret_cast<const uint4*>(a.bank + static_cast<size_t>(qrow) * 128);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = __ldg(qv + i);
-    const int cand[4] = {i0 & 0xFFFF, (i0 >> 16) & 0xFFFF, i1 & 0xFFFF, (i1 >> 16) & 0xFFFF};
-    const int rV2 = __float_as_int(t.d1);
-    const int sub = a.chunk_rows / 32;                          // a candidate chunk = sub groups of 32 train rows
-    long long a1 = LLONG_MAX, a2 = LLONG_MAX;
-    // ---- stage A: the best chunk alone.  Every row outside it has a.b <= V2, i.e. d^2 >= |a|^2 + N- - 2 V2 =: lb2,
-    // and chunk 2 holds a real row with d^2 <= |a|^2 + N+ - 2 V2 =: ub2.  A planted match has e0 far below lb2: the
-    // nearest neighbour is certified and d1^2 lies in [min(e1', lb2), min(e1', ub2)] (e1' = second best inside the
-    // chunk) -- if the ratio test agrees at both ends the row is finished after 32-64 exact distances.
-    if (!a.all_rows && cand[0] != 0xFFFF && rV2 > 0) {
-        for (int h = 0; h < sub; ++h)
-            warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[0] * sub + h, lane, a1, a2);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
-            a2 = min(max(a1, b1), min(a2, b2));
-            a1 = min(a1, b1);
-        }
-        if (a1 != LLONG_MAX) {
-            const long long e0 = a1 >> 32;
-            const long long lb2 = static_cast<long long>(rna) + nbmin - 2ll * rV2;
-            const long long ub2 = static_cast<long long>(rna) + nbmax - 2ll * rV2;
-            if (e0 < lb2) {
-                const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
-                const long long lo1 = min(e1, lb2), hi1 = min(e1, ub2);
-                const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
-                const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lo1)))) * a.ratio;
-                const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(hi1)))) * a.ratio;
-                if (pass_lo == pass_hi) {
-                    if (lane == 0) {
-                        Top2 o;
-                        o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(e0));
-                        // the second neighbour itself is not reported by the ratio-filtered stage: any index >= 0 marks
-                        // "a second neighbour exists", d1 = the end of the interval that was tested
-                        o.i1 = a2 != LLONG_MAX ? static_cast<int>(a2 & 0xFFFFFFFFll) : ntr;
-                        o.d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lo1 : hi1));
-                        a.top2[srow] = o;
-                    }
-                    return;
-                }
-            }
-        }
-        a1 = LLONG_MAX; a2 = LLONG_MAX;
-    }
-    // ---- stage B: all candidate chunks
-    int covered = 0;                                                // real train rows inside the candidate chunks
-    for (int k = 0; k < 4; ++k)
-        if (cand[k] != 0xFFFF) {
-            for (int h = 0; h < sub; ++h)
-                warp_chunk_candidates(a.bank, a.norm2, q, rna, tr0, ntr, cand[k] * sub + h, lane, a1, a2);
-            covered += max(0, min(a.chunk_rows, ntr - a.chunk_rows * cand[k]));
-        }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
-        a2 = min(max(a1, b1), min(a2, b2));
-        a1 = min(a1, b1);
-    }
-    // decide (all lanes hold the same a1, a2)
-    bool done = false;
-    float out_d1 = inf;
-    int out_i1 = -1;
-    const bool outside = covered < ntr;                             // train rows exist outside the candidate chunks
-    const long long lbo = outside ? static_cast<long long>(rna) + nbmin - 2ll * rv5 : LLONG_MAX;
-    if (a1 != LLONG_MAX) {
-        const long long e0 = a1 >> 32;
-        if (!outside) {                                             // the chunks cover the whole train image: exact
-            done = true;
-            if (a2 != LLONG_MAX) { out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll); out_d1 = static_cast<float>(static_cast<int32_t>(a2 >> 32)); }
-        } else if (e0 < lbo && !a.all_rows) {
-            const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
-            const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
-            const long long lb1 = min(e1, lbo);                     // <= true d1^2 <= e1 (e1 = none: only the bound)
-            const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb1)))) * a.ratio;
-            if (e1 == LLONG_MAX) {
-                // a second neighbour exists outside the chunks (outside == true): only 'pass at the lower end' decides
-                if (pass_lo) { done = true; out_i1 = ntr; out_d1 = static_cast<float>(static_cast<int32_t>(lb1)); }
-            } else {
-                const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)))) * a.ratio;
-                if (pass_lo == pass_hi) {
-                    done = true;
-                    out_i1 = static_cast<int>(a2 & 0xFFFFFFFFll);
-                    out_d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lb1 : e1));
-                }
-            }
-        }
-    }
-    // not certified, but perhaps certainly failing: the true d0^2 is >= min(e0, lbo) and the true d1^2 is <= e1 (the
-    // second best candidate is a real row), so  sqrtf(min(e0, lbo)) >= ratio * sqrtf(e1)  means the ratio test fails
-    // whatever lies outside the candidates -- the usual case of a row without a planted match
-    bool rejected = false;
-    if (!done && !a.all_rows && a1 != LLONG_MAX && a2 != LLONG_MAX && outside) {
-        const long long lb0 = max(0ll, min(a1 >> 32, lbo)), e1 = a2 >> 32;
-        const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(lb0)));
-        const float s1 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e1)));
-        if (!(static_cast<double>(s0) < static_cast<double>(s1) * a.ratio)) { done = true; rejected = true; }
-    }
-    if (!done) {
-        // exact brute force over the whole train image: queued for brute_force_rows_kernel (a whole CTA per row)
-        if (lane == 0) {
-            atomicAdd(a.stats + 1, 1ull);
-            a.bf_list[atomicAdd(a.bf_count, 1)] = static_cast<int32_t>(srow);
-        }
-        rejected = true;                                            // placeholder until that kernel writes the row
-    }
-    if (lane == 0) {
-        Top2 o;
-        o.i0 = -1; o.i1 = -1; o.d0 = inf; o.d1 = inf;
-        if (!rejected) {
-            if (a1 != LLONG_MAX) { o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(a1 >> 32)); }
-            o.i1 = out_i1; o.d1 = out_d1;
-        }
-        a.top2[srow] = o;
-    }
+__device__ __forceinline__ RefineCtx refine_ctx_of(const RefineArgs& a) {
+    RefineCtx c;
+    c.bank = a.bank; c.norm2 = a.norm2; c.top2 = a.top2; c.stats = a.stats; c.bf_list = a.bf_list; c.bf_count = a.bf_count;
+    c.chunk_rows = a.chunk_rows; c.all_rows = a.all_rows; c.ratio = a.ratio;
+    return c;
 }
 
 // |b|^2 range of the train image of every pair of the batch (from the per-256-row-block ranges): one warp per pair
@@ -721,7 +564,7 @@ __global__ void __launch_bounds__(256, 4) refine_dot_rows_kernel(RefineArgs a) {
         const int ni = i + warps;
         DotRowMeta nxt = cur;
         if (ni < n) nxt = load_dot_row(a, ni);
-        refine_dot_row(a, cur.srow, lane, cur.t, cur.v5, cur.na, cur.qrow, cur.tr0, cur.nt, cur.nbmin, cur.nbmax);
+        refine_dot_row(refine_ctx_of(a), cur.srow, lane, cur.t, cur.v5, cur.na, cur.qrow, cur.tr0, cur.nt, cur.nbmin, cur.nbmax);
         if (ni >= n) break;
         cur = nxt; i = ni;
     }

@@ -491,10 +491,11 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         if (sparse) {
             CU_TRY(c, S.bf.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
             CU_TRY(c, S.need.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
+            CU_TRY(c, S.done.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
             CU_TRY(c, S.keep.ensure(std::max<size_t>(32, static_cast<size_t>(max_staged) / 8)));
             CU_TRY(c, S.pair_nb.ensure(std::max<size_t>(16, static_cast<size_t>(n_pairs) * 8)));
         }
-        CU_TRY(c, S.counters.ensure(16));
+        CU_TRY(c, S.counters.ensure(32));
         if (eng == Engine::TF32 || eng == Engine::TCN) {
             CU_TRY(c, S.aux.ensure(std::max<size_t>(16, static_cast<size_t>(max_staged) * 4)));
             if (need_rev) CU_TRY(c, S.aux_rev.ensure(std::max<size_t>(16, static_cast<size_t>(max_t) * 4)));
@@ -540,10 +541,15 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         c->stat_launches++;
         TcvFuse fz{};
         if (sparse) {
-            CU_TRY(c, cudaMemsetAsync(S.counters.p, 0, 16, s));                            // brute-force queue + need list lengths
+            CU_TRY(c, cudaMemsetAsync(S.counters.p, 0, 32, s));                            // brute-force queue, need list, done list lengths
             CU_TRY(c, cudaMemsetAsync(S.keep.p, 0, static_cast<size_t>(B.staged_rows) / 8, s));
             fz.norm2 = b.d_norm2.as<int32_t>(); fz.blk_min = b.d_blkmin.as<int32_t>(); fz.blk_max = b.d_blkmax.as<int32_t>();
             fz.need_list = S.need.as<int32_t>(); fz.need_count = S.counters.as<int>() + 1; fz.ratio = o->ratio;
+            // norm-less variant with 8 epilogue warps: four more warps of every CTA re-rank the survivors in the kernel
+            fz.refine = (eng == Engine::TCN && c->tcv_layout_run == 12 && c->tcv_inkernel_refine) ? 1 : 0;
+            fz.bank = b.d_u8.as<uint8_t>(); fz.done_list = S.done.as<int32_t>(); fz.done_count = S.counters.as<int>() + 2;
+            fz.bf_list = S.bf.as<int32_t>(); fz.bf_count = S.counters.as<int>();
+            fz.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
         }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
         rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, S.top2.as<Top2>(), S.aux.as<float>(), &fz);
@@ -598,6 +604,8 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         if (need_cnt) CU_TRY(c, cudaMemsetAsync(S.train_cnt.p, 0, static_cast<size_t>(B.t_rows) * 4, ps));
         if (sparse) {
             a.keep_bits = S.keep.as<uint32_t>(); a.need_list = S.need.as<int32_t>(); a.need_count = S.counters.as<int>() + 1;
+            a.done_list = S.done.as<int32_t>(); a.done_count = S.counters.as<int>() + 2;
+            if (eng == Engine::TCN) { a.bf_list = S.bf.as<int32_t>(); a.bf_count = S.counters.as<int>(); }
             CU_TRY(c, launch_mark_keep(a, ps));
             CU_TRY(c, launch_count_keep_bits(a.keep_bits, B.staged_rows / 256, S.chunk_counts.as<int32_t>(), ps));
             c->stat_launches += need_cnt ? 3 : 2;
@@ -928,6 +936,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     size_t mb = 512;
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
+    if (const char* env = std::getenv("SFM_TCV_INKERNEL_REFINE")) c->tcv_inkernel_refine = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_MIN_BATCHES")) { const int t = std::atoi(env); if (t >= 1 && t <= 64) c->min_batches = t; }
     if (const char* env = std::getenv("SFM_TCV_SPREAD_DIV")) { const int t = std::atoi(env); if (t >= 1) c->tcv_spread_div = t; }
     if (const char* env = std::getenv("SFM_TCV_NORMLESS")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_normless = t; }

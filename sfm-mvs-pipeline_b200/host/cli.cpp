@@ -14,7 +14,7 @@
 //                               then per image: u32 n_rows, u32 width, u32 height, n_rows x (float x, float y)
 //   -Pransac-matching-threshold=0.006   as PhotogrammetrieCli.cpp:98-99 (< 0: pixels, > 0: fraction of the image size)
 //   -Pout=<matches.bin>         u64 n_pairs, then per kept pair: i32 left, i32 right, u64 n, n x DMatch(16 B)
-//   -Pdevice=<gpu>
+//   -Pdevice=<gpu>   or   -Pdevices=<gpu>,<gpu>,...  (one process, one worker thread per GPU; lists gathered on the first)
 #include <cctype>
 #include <chrono>
 #include <cstdio>
@@ -88,7 +88,7 @@ static void usage() {
     std::puts("sfm_match_cli (-Pimage=<shot.pgm> ... | -Pdescriptors=<bank.sfmd>) [-Pfeature-detector=SIFT|ORB] [-Pfeature-matcher=BF|FLANN]\n"
               "              [-Pfeature-limit=10000] [-Pfeature-sequence=0] [-Pfeature-gridlength=0] [-Pmatch-threshold=20]\n"
               "              [--distinct-matches] [-Pkeypoints=<bank.sfmk>] [-Pransac-matching-threshold=0.006]\n"
-              "              [-Pout=matches.bin] [-Pdevice=0] [-Ploglevel=2]");
+              "              [-Pout=matches.bin] [-Pdevice=0 | -Pdevices=0,1,...] [-Ploglevel=2]");
 }
 
 static void report(const std::vector<ShotMatches>& res, size_t n_pairs, double dt, bool ratios) {
@@ -204,7 +204,21 @@ int main(int argc, char** argv) {
         std::vector<std::string> warnings;
         if (det != "ORB" && det != "SIFT" && !det.empty())
             warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
-        auto matcher = configureFeatureMatcher(det, args.get("feature-matcher"), std::stoi(args.get("device", "0")), &warnings);
+        // -Pdevices=0,1,2,...: several GPUs from this one process (the reference is one process with an OpenMP loop over pairs)
+        std::vector<int> devices;
+        {
+            const std::string dl = args.get("devices");
+            size_t pos = 0;
+            while (pos < dl.size()) {
+                const size_t comma = dl.find(',', pos);
+                const std::string tok = dl.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+                if (!tok.empty()) devices.push_back(std::stoi(tok));
+                if (comma == std::string::npos) break;
+                pos = comma + 1;
+            }
+            if (devices.empty()) devices.push_back(std::stoi(args.get("device", "0")));
+        }
+        auto matcher = configureFeatureMatcher(det, args.get("feature-matcher"), devices, &warnings);
         auto strategy = configureFeatureMatcherStrategy(std::stoi(args.get("feature-sequence", "0")),
                                                         std::stoi(args.get("feature-gridlength", "0")), &warnings);
         for (auto& w : warnings) std::fprintf(stderr, "[WARN] %s\n", w.c_str());

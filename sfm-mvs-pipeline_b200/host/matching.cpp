@@ -17,7 +17,24 @@ GpuDescriptorMatcher::GpuDescriptorMatcher(int normType, bool crossCheck, int de
     if (rc != SFM_OK) throw MatcherError(rc, sfm_last_error(nullptr));
 }
 
-GpuDescriptorMatcher::~GpuDescriptorMatcher() { sfm_ctx_destroy(ctx_); }
+GpuDescriptorMatcher::GpuDescriptorMatcher(int normType, bool crossCheck, const std::vector<int>& devices, bool flannMode)
+    : norm_(normType), crossCheck_(crossCheck), flann_(flannMode) {
+    if (normType != SFM_NORM_L2 && normType != SFM_NORM_HAMMING) throw std::invalid_argument("unsupported normType");
+    if (devices.empty()) throw std::invalid_argument("empty device list");
+    if (devices.size() == 1) {
+        const int rc = sfm_ctx_create(&ctx_, devices[0]);
+        if (rc != SFM_OK) throw MatcherError(rc, sfm_last_error(nullptr));
+        return;
+    }
+    const int rc = sfm_mgpu_create(&group_, devices.data(), static_cast<int>(devices.size()));
+    if (rc != SFM_OK) throw MatcherError(rc, sfm_last_error(nullptr));
+    ctx_ = sfm_mgpu_ctx(group_, 0);
+}
+
+GpuDescriptorMatcher::~GpuDescriptorMatcher() {
+    if (group_) sfm_mgpu_destroy(group_);        // owns its contexts
+    else sfm_ctx_destroy(ctx_);
+}
 
 void GpuDescriptorMatcher::knnMatch(const DescriptorMat& q, const DescriptorMat& t,
                                     std::vector<std::vector<DMatch>>& matches, int k) const {
@@ -96,7 +113,14 @@ void IFeatureMatchingStrategy::calculateShotMatches(const Scene& scene, std::sha
     o.distinct = stage_.distinct ? 1 : 0;
     o.min_match_count = stage_.minMatchCount;
     sfm_result* res = nullptr;
-    if (scene.bankResident) {
+    sfm_mgpu* group = matcher->group();
+    if (group && !scene.bankResident) {
+        // several GPUs: every device uploads its share of the scene, NVLink exchange, pairs dealt by cost, lists gathered in
+        // pair-list order on devices[0] (byte-identical to the single-GPU result)
+        const int rc = sfm_mgpu_match_pairs_from_host(group, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(),
+                                                      depth, flat.data(), static_cast<int64_t>(pl.size()), &o, &res);
+        if (rc != SFM_OK) throw MatcherError(rc, sfm_mgpu_last_error(group));
+    } else if (scene.bankResident) {
         // the feature extractor left descriptors + keypoints of these shots on the device: nothing to upload
         int n_bank = 0;
         check(ctx, sfm_bank_info(ctx, &n_bank, nullptr, nullptr));
@@ -222,6 +246,15 @@ std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string&
         warnings->push_back("Unbekannter Algorithmus fuer den Merkmalsvergleich: " + mat + ". Benutze BF.");
     const int norm = det == "ORB" ? SFM_NORM_HAMMING : SFM_NORM_L2;      // anything else than ORB -> SIFT
     return std::make_shared<GpuDescriptorMatcher>(norm, false, device, flann);
+}
+
+std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& det, const std::string& mat, const std::vector<int>& devices,
+                                                              std::vector<std::string>* warnings) {
+    const bool flann = mat == "FLANN";
+    if (!flann && mat != "BF" && !mat.empty() && warnings)
+        warnings->push_back("Unbekannter Algorithmus fuer den Merkmalsvergleich: " + mat + ". Benutze BF.");
+    const int norm = det == "ORB" ? SFM_NORM_HAMMING : SFM_NORM_L2;
+    return std::make_shared<GpuDescriptorMatcher>(norm, false, devices, flann);
 }
 
 std::shared_ptr<IFeatureMatchingStrategy> configureFeatureMatcherStrategy(int seq, int grid, std::vector<std::string>* warnings) {

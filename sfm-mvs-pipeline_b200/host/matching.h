@@ -48,6 +48,9 @@ public:
     // normType: SFM_NORM_L2 (BFMatcher::create(NORM_L2)) or SFM_NORM_HAMMING; crossCheck as in cv::BFMatcher.
     // `flannMode` records that -Pfeature-matcher=FLANN was requested: the exact GPU matcher replaces it.
     explicit GpuDescriptorMatcher(int normType = SFM_NORM_L2, bool crossCheck = false, int device = 0, bool flannMode = false);
+    // several GPUs from this one process (sfm_mgpu_*: one worker thread per device, NCCL inside the library): the strategies
+    // deal the pair list over the devices; knnMatch / match and the homography stage run on devices[0]
+    GpuDescriptorMatcher(int normType, bool crossCheck, const std::vector<int>& devices, bool flannMode = false);
     ~GpuDescriptorMatcher();
     GpuDescriptorMatcher(const GpuDescriptorMatcher&) = delete;
     GpuDescriptorMatcher& operator=(const GpuDescriptorMatcher&) = delete;
@@ -61,9 +64,11 @@ public:
     bool crossCheck() const { return crossCheck_; }
     bool flannMode() const { return flann_; }
     sfm_ctx* context() const { return ctx_; }
+    sfm_mgpu* group() const { return group_; }          // null with one device
 
 private:
     sfm_ctx* ctx_ = nullptr;
+    sfm_mgpu* group_ = nullptr;
     int norm_;
     bool crossCheck_, flann_;
 };
@@ -220,6 +225,9 @@ private:
 // PhotogrammetrieCli::configureFeatureMatcher / configureFeatureMatcherStrategy (PhotogrammetrieCli.cpp:320-392)
 std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& featureDetector,
                                                               const std::string& featureMatcher, int device,
+                                                              std::vector<std::string>* warnings);
+std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& featureDetector,
+                                                              const std::string& featureMatcher, const std::vector<int>& devices,
                                                               std::vector<std::string>* warnings);
 std::shared_ptr<IFeatureMatchingStrategy> configureFeatureMatcherStrategy(int featureSequence, int featureGridLength,
                                                                           std::vector<std::string>* warnings);

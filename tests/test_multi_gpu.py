@@ -67,3 +67,36 @@ def test_single_process_group_is_byte_identical_to_one_gpu():
     assert np.array_equal(ro.offsets, fo.offsets) and ro.matches.tobytes() == fo.matches.tobytes()
     g.close()
     one.close()
+
+
+def test_cli_devices_switch_is_byte_identical(tmp_path):
+    """sfm_match_cli -Pdevices=0,1 (C++ host, one process, sfm_mgpu_*) writes the same artifact as -Pdevice=0, including
+    the homography stage that runs on the gathered lists of the first device."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import workloads
+    cli = os.path.join(ROOT, "sfm-mvs-pipeline_b200", "sfm_match_cli")
+    n_img, n_rows = 8, 900
+    bank = workloads.sift_like_bank(n_img, n_rows)
+    kps = workloads.sift_like_keypoints(n_img, n_rows)
+    dpath, kpath = tmp_path / "bank.sfmd", tmp_path / "bank.sfmk"
+    with open(dpath, "wb") as f:
+        f.write(b"SFMD" + np.array([1, n_img, 128, 5], np.uint32).tobytes())
+        for d in bank:
+            f.write(np.uint32(d.shape[0]).tobytes() + d.astype(np.float32).tobytes())
+    with open(kpath, "wb") as f:
+        f.write(b"SFMK" + np.array([1, n_img], np.uint32).tobytes())
+        for k in kps:
+            f.write(np.array([len(k), 4000, 3000], np.uint32).tobytes() + np.ascontiguousarray(k, np.float32).tobytes())
+    outs = []
+    for dev in ("-Pdevice=0", "-Pdevices=0,1"):
+        out = tmp_path / f"m{len(outs)}.bin"
+        r = subprocess.run([cli, f"-Pdescriptors={dpath}", f"-Pkeypoints={kpath}", "-Pmatch-threshold=20", f"-Pout={out}", dev],
+                           capture_output=True, text=True, timeout=300)
+        assert "pairs=28" in r.stdout and "[ERROR]" not in r.stderr, r.stdout + r.stderr
+        outs.append((open(out, "rb").read(), [ln for ln in r.stdout.splitlines() if "homographyInlierRatio" in ln]))
+    assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 10000
+    assert outs[0][1] == outs[1][1] and len(outs[0][1]) >= 7
