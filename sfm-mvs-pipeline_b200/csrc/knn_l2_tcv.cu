@@ -324,9 +324,9 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
                 if (kParity == 2 && (tile_iter & 1) != static_cast<uint32_t>(parity)) continue;
                 const int acc = tile_iter % kAccStages;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / kHalves);
                 mbar_wait(acc_full(acc), (tile_iter / kAccStages) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / kHalves);
                 uint32_t v[2][32];
                 tmem_ld_32x32(taddr, v[0]);
                 int32_t cm_even = 0;

@@ -64,6 +64,30 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint8_t* __restri
     dst[static_cast<size_t>(y) * (2 * w) + x] = a * (1.f - fy) + b * fy;
 }
 
+// createInitialImage without the 2x upsampling (cv::SIFT::compute when no keypoint lies in octave -1): u8 grey -> float
+__global__ void __launch_bounds__(256) gray_to_float_kernel(const uint8_t* __restrict__ src, int w, int h, size_t step,
+                                                            float* __restrict__ dst) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x < w && y < h) dst[static_cast<size_t>(y) * w + x] = static_cast<float>(src[static_cast<size_t>(y) * step + x]);
+}
+
+// octave range of the final keypoints: range[0] = min octave + 128 (starts at 0x7fffffff), range[1] = max octave + 128
+__global__ void __launch_bounds__(256) octave_range_kernel(const Keypoint* __restrict__ kps, const int* __restrict__ n_kps, int capacity,
+                                                           int* __restrict__ range) {
+    const int n = min(*n_kps, capacity);
+    int mn = 0x7fffffff, mx = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        int octave, layer;
+        float scale;
+        unpack_octave(kps[i].octave, octave, layer, scale);
+        mn = min(mn, octave + 128);
+        mx = max(mx, octave + 128);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0 && mx > 0) { atomicMin(range, mn); atomicMax(range + 1, mx); }
+}
+
 constexpr int kBlurTW = 64, kBlurTH = 32;
 constexpr int kBlurMidStride = kBlurTW + 1;      // odd strides: a warp walking down a column of the tile hits 32 banks
 __host__ __device__ inline int blur_in_stride(int radius) { return (kBlurTW + 2 * radius) | 1; }
@@ -408,7 +432,7 @@ struct DescScratch {
 };
 __global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const PyramidView P, const Keypoint* __restrict__ kps,
                                                                     const int* __restrict__ n_kps, int capacity,
-                                                                    uint8_t* __restrict__ desc) {
+                                                                    uint8_t* __restrict__ desc, int first_octave) {
     __shared__ DescScratch scratch[kDescWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DescScratch& S = scratch[warp];
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const Pyram
         int octave, layer;
         float scale;
         unpack_octave(kp.octave, octave, layer, scale);
-        const int o = octave + 1;                // firstOctave = -1
+        const int o = octave - first_octave;     // detection pyramid: firstOctave = -1
         float angle = 360.f - kp.angle;
         if (fabsf(angle - 360.f) < 1.1920929e-07f) angle = 0.f;
         const float* img = P.level(o, layer);
@@ -509,8 +533,9 @@ struct SiftWorkspace {
     int* d_grouped = nullptr;    size_t grouped_cap = 0;
     int* d_bucket = nullptr;     size_t bucket_cap = 0;   // count [nb + 1] | start [nb + 1] | cursor [nb + 1]
     uint8_t* d_desc = nullptr;   size_t desc_cap = 0;
-    int* d_counts = nullptr;     // [0] candidates, [1] raw keypoints, [2] final keypoints
+    int* d_counts = nullptr;     // [0] candidates, [1] raw keypoints, [2] final keypoints, [4] / [5] min / max octave + 128 of the final keypoints
     int* h_counts = nullptr;     // pinned
+    bool recomputed = false;     // the last extraction rebuilt the pyramid without upsampling for the descriptors (compute() semantics)
     PyramidView view{};
     bool smem_set = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};      // start | pyramid built | descriptors written
@@ -595,14 +620,15 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
     const int n_buckets = bw + 1;                 // floor(x) of a keypoint in base-image coordinates
     SIFT_TRY(grow(ws->d_bucket, ws->bucket_cap, 3 * static_cast<size_t>(n_buckets + 1)));
     SIFT_TRY(grow(ws->d_desc, ws->desc_cap, static_cast<size_t>(max_keypoints) * kDescLen));
-    if (!ws->d_counts) SIFT_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->d_counts), 16));
-    if (!ws->h_counts) SIFT_TRY(cudaMallocHost(reinterpret_cast<void**>(&ws->h_counts), 16));
+    if (!ws->d_counts) SIFT_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->d_counts), 32));
+    if (!ws->h_counts) SIFT_TRY(cudaMallocHost(reinterpret_cast<void**>(&ws->h_counts), 32));
     if (!ws->smem_set) {
         SIFT_TRY(cudaFuncSetAttribute(gauss_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         ws->smem_set = true;
     }
     for (cudaEvent_t& e : ws->ev) if (!e) SIFT_TRY(cudaEventCreate(&e));
-    SIFT_TRY(cudaMemsetAsync(ws->d_counts, 0, 16, s));
+    SIFT_TRY(cudaMemsetAsync(ws->d_counts, 0, 32, s));
+    SIFT_TRY(cudaMemsetAsync(ws->d_counts + 4, 0x7f, 4, s));          // [4] min octave + 128, [5] max octave + 128 of the final keypoints
     SIFT_TRY(cudaEventRecord(ws->ev[0], s));
     // ---- grey image to the device, doubled, first blur (createInitialImage)
     SIFT_TRY(cudaMemcpy2DAsync(ws->d_gray, cols, gray, step, cols, rows, cudaMemcpyHostToDevice, s));
@@ -630,17 +656,25 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
         const double sig_total = sig_prev * kfac;
         sig[i] = std::sqrt(sig_total * sig_total - sig_prev * sig_prev);
     }
-    for (int o = 0; o < n_octaves; ++o) {
-        const int w = P.w[o], h = P.h[o];
-        const size_t plane = static_cast<size_t>(w) * h;
-        float* lv0 = ws->d_pyr + P.off[o];
-        if (o > 0) {
-            const float* src = ws->d_pyr + P.off[o - 1] + static_cast<size_t>(L) * P.w[o - 1] * P.h[o - 1];
-            downsample_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, s>>>(src, P.w[o - 1], lv0, w, h);
-            ++launches;
+    // level 0 of octave 0 is in place: the remaining levels and octaves (buildGaussianPyramid)
+    auto build_levels = [&](int octaves) -> cudaError_t {
+        for (int o = 0; o < octaves; ++o) {
+            const int w = P.w[o], h = P.h[o];
+            const size_t plane = static_cast<size_t>(w) * h;
+            float* lv0 = ws->d_pyr + P.off[o];
+            if (o > 0) {
+                const float* src = ws->d_pyr + P.off[o - 1] + static_cast<size_t>(L) * P.w[o - 1] * P.h[o - 1];
+                downsample_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), blk, 0, s>>>(src, P.w[o - 1], lv0, w, h);
+                ++launches;
+            }
+            for (int i = 1; i < levels; ++i) {
+                const cudaError_t e = blur(lv0 + (i - 1) * plane, lv0 + i * plane, w, h, sig[i]);
+                if (e != cudaSuccess) return e;
+            }
         }
-        for (int i = 1; i < levels; ++i) SIFT_TRY(blur(lv0 + (i - 1) * plane, lv0 + i * plane, w, h, sig[i]));
-    }
+        return cudaSuccess;
+    };
+    SIFT_TRY(build_levels(n_octaves));
     SIFT_TRY(cudaEventRecord(ws->ev[1], s));
     // ---- findScaleSpaceExtrema
     const float threshold = static_cast<float>(static_cast<int>(std::floor(0.5 * prm.contrast_threshold / L * 255)));
@@ -672,12 +706,48 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
         ++launches;
     }
     // ---- calcDescriptors
-    descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc);
-    launches += 8;
+    descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc, -1);
+    octave_range_kernel<<<64, 256, 0, s>>>(ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_counts + 4);
+    launches += 9;
     SIFT_TRY(cudaGetLastError());
     SIFT_TRY(cudaEventRecord(ws->ev[2], s));
-    SIFT_TRY(cudaMemcpyAsync(ws->h_counts, ws->d_counts, 12, cudaMemcpyDeviceToHost, s));
+    SIFT_TRY(cudaMemcpyAsync(ws->h_counts, ws->d_counts, 24, cudaMemcpyDeviceToHost, s));
     SIFT_TRY(cudaStreamSynchronize(s));
+    // The reference calls detect() and compute() separately (SfM.cpp:586-587), and cv::SIFT::compute rebuilds the pyramid from
+    // the octave range of the keypoints it is given: when NONE lies in octave -1 the image is not upsampled
+    // (createInitialImage(img, doubleImageSize = false): grey -> float -> blur sqrt(sigma^2 - 0.25)) and only max octave + 1
+    // octaves are built, so the descriptors come from slightly different pixels.  Photographs always have octave -1 keypoints;
+    // a picture of a few wide blobs does not: mirror compute() then (one more pass, rare).
+    {
+        const int n_final = std::min(ws->h_counts[2], max_keypoints);
+        const int oct_min = ws->h_counts[4] - 128, oct_max = ws->h_counts[5] - 128;
+        if (n_final > 0 && ws->h_counts[1] <= max_keypoints && oct_min >= 0) {
+            const int n_oct2 = oct_max + 1;
+            int64_t total2 = 0;
+            P.n_octaves = 0;
+            for (int o = 0; o < n_oct2; ++o) {
+                P.w[o] = o == 0 ? cols : P.w[o - 1] / 2;
+                P.h[o] = o == 0 ? rows : P.h[o - 1] / 2;
+                if (P.w[o] < 1 || P.h[o] < 1) break;
+                P.off[o] = total2;
+                total2 += static_cast<int64_t>(levels) * P.w[o] * P.h[o];
+                P.n_octaves = o + 1;
+            }
+            if (P.n_octaves != n_oct2) { if (err) *err = "feature extraction: keypoint octave beyond the non-doubled pyramid"; return cudaErrorInvalidValue; }
+            // d_pyr / d_up are large enough: the doubled pyramid had four times the pixels per octave
+            gray_to_float_kernel<<<dim3((cols + 31) / 32, (rows + 7) / 8), blk, 0, s>>>(ws->d_gray, cols, rows, cols, ws->d_up);
+            ++launches;
+            const float sig_diff1 = sqrtf(std::max(sigma_f * sigma_f - 0.5f * 0.5f, 0.01f));
+            SIFT_TRY(blur(ws->d_up, ws->d_pyr + P.off[0], cols, rows, static_cast<double>(sig_diff1)));
+            SIFT_TRY(build_levels(n_oct2));
+            descriptor_kernel<<<persistent, kDescWarps * 32, 0, s>>>(P, ws->d_kp, ws->d_counts + 2, max_keypoints, ws->d_desc, 0);
+            ++launches;
+            SIFT_TRY(cudaGetLastError());
+            SIFT_TRY(cudaEventRecord(ws->ev[2], s));
+            SIFT_TRY(cudaStreamSynchronize(s));
+            ws->recomputed = true;
+        } else ws->recomputed = false;
+    }
     SIFT_TRY(cudaEventElapsedTime(&ws->pyramid_ms, ws->ev[0], ws->ev[1]));
     SIFT_TRY(cudaEventElapsedTime(&ws->total_ms, ws->ev[0], ws->ev[2]));
     if (counts_out) { counts_out[0] = ws->h_counts[0]; counts_out[1] = ws->h_counts[1]; counts_out[2] = ws->h_counts[2]; }

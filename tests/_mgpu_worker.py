@@ -86,7 +86,9 @@ def main():
             same = (np.array_equal(gg[0], full.offsets) and gg[1].tobytes() == full.matches.tobytes()
                     and np.array_equal(gg[2], full.dropped))
             if not same:
-                print("MISMATCH in", name, flush=True)
+                print("MISMATCH in", name, "offsets", np.array_equal(gg[0], full.offsets), "dropped", np.array_equal(gg[2], full.dropped),
+                      "first differing pair", int(np.argmax(np.diff(gg[0]) != np.diff(full.offsets))) if len(gg[0]) == len(full.offsets) else -1,
+                      np.diff(gg[0]).tolist(), np.diff(full.offsets).tolist(), flush=True)
             ok = ok and same
         print("MGPU_IDENTICAL" if ok else "MGPU_MISMATCH", int(full.offsets[-1]), flush=True)
     m.close()

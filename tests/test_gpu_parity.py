@@ -539,3 +539,35 @@ def test_from_host_failure_leaves_no_half_built_bank(sfm):
         assert orc.dmatch_equal(good[0], exp[0]) and orc.dmatch_equal(good[1], exp[1])
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("settings", [{}, {"SFM_TCV_NORMLESS": "2"}, {"SFM_TCV_NORMLESS": "0"}, {"SFM_TCV_INKERNEL_REFINE": "0"},
+                                      {"SFM_MIN_BATCHES": "1"}])
+def test_ragged_scene_first_run_every_variant(sfm, settings, monkeypatch):
+    """The scene of the multi-GPU worker (ragged sizes, an empty image, 30 % planted neighbours, min-match-count 20): the FIRST
+    run on a fresh context and the following ones (adaptive feedback switches the kernel variant) against the C oracle."""
+    from oracle import oracle_c
+    for k, v in settings.items():
+        monkeypatch.setenv(k, v)
+    sizes = [1500, 1024, 777, 2048, 300, 1300, 0, 640]
+    bank, prev = [], None
+    for i, n in enumerate(sizes):
+        d = workloads.sift_like_image(i, n, prev if prev is not None and len(prev) else None)
+        bank.append(d)
+        prev = d
+    pairs = sfm.select_pairs(len(sizes), 0, 0)
+    ne = np.array([p for p in pairs if sizes[p[0]] and sizes[p[1]]], np.int32)
+    exp = dict(zip(map(tuple, ne.tolist()), oracle_c.match_pairs(bank, ne, NORM_L2)))
+    m = sfm.Matcher(0)
+    try:
+        m.upload_bank(bank)
+        for run in range(3):
+            res = m.match_pairs(pairs, NORM_L2, min_match_count=20)
+            for p, (l, r) in enumerate(pairs.tolist()):
+                e = exp.get((l, r), np.zeros(0, orc.DMATCH_DTYPE))
+                if len(e) < 20:
+                    assert res.dropped[p] == 1 and res[p] is None, (run, l, r)
+                else:
+                    assert orc.dmatch_equal(res[p], e), (run, l, r, len(res[p]), len(e))
+    finally:
+        m.close()

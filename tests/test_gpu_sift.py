@@ -170,3 +170,31 @@ def test_non_default_detector_parameters_equal_restatement(m, n_layers, sigma, e
             got = m.pyramid_level(o, i)
             exp = gpyr[o * (n_layers + 3) + i]
             assert got.shape == exp.shape and np.abs(got - exp).max() < 1e-4, (o, i)
+
+
+def test_compute_semantics_without_octave_minus_one(m):
+    """The reference calls detect() then compute() (SfM.cpp:586-587); cv::SIFT::compute rebuilds the pyramid WITHOUT the 2x
+    upsampling when no keypoint lies in octave -1.  A picture of a few wide blobs has none: the device then takes its
+    descriptors from a second, non-doubled pyramid and equals the restatement of compute() exactly."""
+    yy, xx = np.mgrid[0:160, 0:200]
+    img = np.zeros((160, 200), np.float32)
+    rng = np.random.default_rng(5)
+    for _ in range(6):
+        cx, cy, sg = rng.uniform(40, 160), rng.uniform(40, 120), rng.uniform(6, 12)
+        img += rng.uniform(0.5, 1) * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * sg * sg))
+    img = np.rint(255 * img / img.max()).astype(np.uint8)
+    kp_o = S.detect(img)
+    assert len(kp_o) >= 10 and min(S.unpack_octave(int(o))[0] for o in kp_o["octave"]) >= 0
+    desc_o = S.compute(img, kp_o)                                     # own pyramid, not doubled
+    m.features_clear()
+    n = m.extract_sift(img)
+    kp, desc = m.features_download(0)
+    assert n == len(kp) == len(kp_o)
+    sc.assert_close(kp_o, desc_o.astype(np.uint8), kp, desc, "compute() without octave -1")
+    assert np.abs(desc.astype(np.int32) - desc_o.astype(np.int32)).max() <= 1
+    # the pyramid left behind is the non-doubled one: octave 0 has the size of the input image
+    assert m.pyramid_level(0, 0).shape == img.shape
+    # and a photograph right after it uses the doubled pyramid again
+    photo = workloads.synthetic_photo(3, 120, 160)
+    m.extract_sift(photo)
+    assert m.pyramid_level(0, 0).shape == (240, 320)

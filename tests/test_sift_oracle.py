@@ -117,8 +117,9 @@ def test_restatement_against_cv2_run_here(name, ct, nf):
 def test_compute_without_octave_minus_one():
     """cv::SIFT::compute called on its own (as SfM.cpp:587 does) rebuilds the pyramid from the octave range of the keypoints:
     without the 2x upsampling when none of them lies in octave -1.  The restatement follows that rule (pinned here against cv2
-    when it is importable); the device path always uses the detection pyramid — DESIGN.md section 8 records the deviation, this
-    test keeps its size on record."""
+    when it is importable) and so does the device path since round 2 (csrc/sift.cu: second, non-doubled pyramid in that case;
+    tests/test_gpu_sift.py::test_compute_semantics_without_octave_minus_one); this test keeps on record what ignoring the
+    rule would cost."""
     yy, xx = np.mgrid[0:160, 0:200]
     img = np.zeros((160, 200), np.float32)
     rng = np.random.default_rng(5)
@@ -139,7 +140,7 @@ def test_compute_without_octave_minus_one():
             assert np.abs(d2 - separate).max() <= 1                   # the rule is cv2's
     except ImportError:
         pass
-    one_call = np.zeros_like(separate)                                # what the device does: the detection pyramid
+    one_call = np.zeros_like(separate)                                # descriptors from the detection pyramid (detectAndCompute in one call)
     for i, k in enumerate(kp):
         o, layer, scale = S.unpack_octave(int(k["octave"]))
         angle = np.float32(360) - k["angle"]
