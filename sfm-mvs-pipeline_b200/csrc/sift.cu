@@ -113,21 +113,58 @@ __device__ __forceinline__ void blur_eight_outputs(const float* __restrict__ p, 
     }
 }
 
+// taps known at compile time: the tap loop is fully unrolled and the weights become constant-bank operands
+// (tools/blur_ab.cu v2: bit-identical to the generic form, 1.5-1.6x faster; profiles/r2_blur_ab.txt)
+template <int R>
+__device__ __forceinline__ void blur_eight_outputs_fixed(const float* __restrict__ p, int stride, const BlurWeights& k, float acc[8]) {
+    constexpr int taps = 2 * R + 1;
+    float win[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) { acc[o] = 0.f; win[o] = p[o * stride]; }
+#pragma unroll
+    for (int t = 0; t < taps; ++t) {
+        const float wt = k.w[t];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] += wt * win[(o + t) & 7];
+        win[t & 7] = p[(t + 8) * stride];
+    }
+}
+
+// source tile + halo into shared memory: 2-D thread mapping (no integer division per element); interior tiles skip the
+// reflect-101 index arithmetic (only the frame of the image needs it)
+__device__ __forceinline__ void blur_load_tile(const float* __restrict__ src, int w, int h, int x0, int y0, int R, float* in) {
+    const int IW = kBlurTW + 2 * R, IH = kBlurTH + 2 * R, IS = blur_in_stride(R);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const bool interior = x0 - R >= 0 && x0 + kBlurTW + R <= w && y0 - R >= 0 && y0 + kBlurTH + R <= h;
+    if (interior) {
+        const float* base = src + static_cast<size_t>(y0 - R) * w + (x0 - R);
+        for (int iy = ty; iy < IH; iy += 8) {
+            const float* row = base + static_cast<size_t>(iy) * w;
+            float* d = in + iy * IS;
+            for (int ix = tx; ix < IW; ix += 32) d[ix] = row[ix];
+        }
+    } else {
+        for (int iy = ty; iy < IH; iy += 8) {
+            const float* row = src + static_cast<size_t>(reflect101(y0 - R + iy, h)) * w;
+            float* d = in + iy * IS;
+            for (int ix = tx; ix < IW; ix += 32) d[ix] = row[reflect101(x0 - R + ix, w)];
+        }
+    }
+}
+
+// kR > 0: radius fixed at compile time (the radii cv::SIFT's blur schedule produces); kR = 0: any radius <= 32
+template <int kR>
 __global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict__ src, float* __restrict__ dst, int w, int h,
                                                          const BlurWeights k) {
     extern __shared__ float sm[];
-    const int R = k.radius;
-    const int IW = kBlurTW + 2 * R, IH = kBlurTH + 2 * R;
+    const int R = kR > 0 ? kR : k.radius;
+    const int IH = kBlurTH + 2 * R;
     const int IS = blur_in_stride(R);
     float* in = sm;                  // IH x IW source tile with halo (row stride IS), 8 floats of slack behind it
     float* mid = sm + IH * IS + 8;   // IH x kBlurTW, filtered along x (row stride kBlurMidStride), 8 rows of slack behind it
     const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
     const int tid = threadIdx.x;
-    for (int idx = tid; idx < IH * IW; idx += 256) {
-        const int iy = idx / IW, ix = idx - iy * IW;
-        const int gy = reflect101(y0 - R + iy, h), gx = reflect101(x0 - R + ix, w);
-        in[iy * IS + ix] = src[static_cast<size_t>(gy) * w + gx];
-    }
+    blur_load_tile(src, w, h, x0, y0, R, in);
     __syncthreads();
     const int taps = 2 * R + 1;
     // along x: unit = (eight outputs, one tile row); consecutive lanes take consecutive rows
@@ -135,7 +172,8 @@ __global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict
         const int iy = unit % IH, ix0 = (unit / IH) * 8;
         const float* p = in + iy * IS + ix0;
         float acc[8];
-        blur_eight_outputs(p, 1, taps, k, acc);
+        if (kR > 0) blur_eight_outputs_fixed<kR>(p, 1, k, acc);
+        else blur_eight_outputs(p, 1, taps, k, acc);
         float* q = mid + iy * kBlurMidStride + ix0;
 #pragma unroll
         for (int o = 0; o < 8; ++o) q[o] = acc[o];
@@ -146,12 +184,31 @@ __global__ void __launch_bounds__(256) gauss_blur_kernel(const float* __restrict
         const int ox = tid % kBlurTW, oy0 = (tid / kBlurTW) * 8;
         const float* p = mid + oy0 * kBlurMidStride + ox;
         float acc[8];
-        blur_eight_outputs(p, kBlurMidStride, taps, k, acc);
+        if (kR > 0) blur_eight_outputs_fixed<kR>(p, kBlurMidStride, k, acc);
+        else blur_eight_outputs(p, kBlurMidStride, taps, k, acc);
         if (x0 + ox < w) {
 #pragma unroll
             for (int o = 0; o < 8; ++o)
                 if (y0 + oy0 + o < h) dst[static_cast<size_t>(y0 + oy0 + o) * w + x0 + ox] = acc[o];
         }
+    }
+}
+
+typedef void (*BlurKernel)(const float*, float*, int, int, const BlurWeights);
+// the radii of cv::SIFT(nOctaveLayers = 3, sigma = 1.6): 5 (first blur of the doubled image), 6, 5, 6, 8, 10, 13 (levels 1..5)
+static BlurKernel blur_kernel_for(int radius) {
+    switch (radius) {
+        case 3: return gauss_blur_kernel<3>;
+        case 4: return gauss_blur_kernel<4>;
+        case 5: return gauss_blur_kernel<5>;
+        case 6: return gauss_blur_kernel<6>;
+        case 7: return gauss_blur_kernel<7>;
+        case 8: return gauss_blur_kernel<8>;
+        case 9: return gauss_blur_kernel<9>;
+        case 10: return gauss_blur_kernel<10>;
+        case 11: return gauss_blur_kernel<11>;
+        case 13: return gauss_blur_kernel<13>;
+        default: return gauss_blur_kernel<0>;
     }
 }
 
@@ -623,7 +680,8 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
     if (!ws->d_counts) SIFT_TRY(cudaMalloc(reinterpret_cast<void**>(&ws->d_counts), 32));
     if (!ws->h_counts) SIFT_TRY(cudaMallocHost(reinterpret_cast<void**>(&ws->h_counts), 32));
     if (!ws->smem_set) {
-        SIFT_TRY(cudaFuncSetAttribute(gauss_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        for (int r : {0, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13})
+            SIFT_TRY(cudaFuncSetAttribute(blur_kernel_for(r), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         ws->smem_set = true;
     }
     for (cudaEvent_t& e : ws->ev) if (!e) SIFT_TRY(cudaEventCreate(&e));
@@ -640,7 +698,7 @@ cudaError_t sift_extract(SiftWorkspace* ws, const uint8_t* gray, int rows, int c
         if (k.radius < 0) { if (err) *err = "Gaussian kernel radius above 32 (sigma / nOctaveLayers out of the supported range)"; return cudaErrorInvalidValue; }
         const size_t ih = static_cast<size_t>(kBlurTH + 2 * k.radius);
         const size_t smem = (ih * blur_in_stride(k.radius) + 8 + (ih + 8) * kBlurMidStride) * sizeof(float);
-        gauss_blur_kernel<<<dim3((w + kBlurTW - 1) / kBlurTW, (h + kBlurTH - 1) / kBlurTH), 256, smem, s>>>(src, dst, w, h, k);
+        blur_kernel_for(k.radius)<<<dim3((w + kBlurTW - 1) / kBlurTW, (h + kBlurTH - 1) / kBlurTH), 256, smem, s>>>(src, dst, w, h, k);
         ++launches;
         return cudaGetLastError();
     };

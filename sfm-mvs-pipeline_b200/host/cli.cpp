@@ -13,6 +13,8 @@
 //   -Pkeypoints=<bank.sfmk>     optional, enables the homography stage (SfM::calculateHomography): "SFMK" u32 version, u32 n_images,
 //                               then per image: u32 n_rows, u32 width, u32 height, n_rows x (float x, float y)
 //   -Pransac-matching-threshold=0.006   as PhotogrammetrieCli.cpp:98-99 (< 0: pixels, > 0: fraction of the image size)
+//   -Pout-matches-dir=<dir>     with -Pimage: one picture per kept pair (both shots side by side, a line per match), the stage's
+//                               on-disk artifact in the reference (PhotogrammetrieCli.cpp:174-199, written there as .jpg; here .ppm)
 //   -Pout=<matches.bin>         u64 n_pairs, then per kept pair: i32 left, i32 right, u64 n, n x DMatch(16 B)
 //   -Pdevice=<gpu>   or   -Pdevices=<gpu>,<gpu>,...  (one process, one worker thread per GPU; lists gathered on the first)
 #include <cctype>
@@ -23,6 +25,7 @@
 #include <map>
 #include <string>
 
+#include "draw_matches.h"
 #include "matching.h"
 
 using namespace sfmhost;
@@ -142,6 +145,24 @@ static int runFromImages(const Args& args, const std::vector<std::string>& paths
     stage.calculateHomography(res);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
     report(res, strategy->matchPairs(scene.shots.size()).size(), dt, true);
+    // the stage's on-disk artifact (PhotogrammetrieCli.cpp:174-199): one picture per ShotMatches, both shots side by side with
+    // a line per match, <dir>/<i><left>-<right>.ppm (the reference writes .jpg through cv::imwrite)
+    const std::string mdir = args.get("out-matches-dir");
+    if (!mdir.empty()) {
+        auto base = [](const std::string& p) { const size_t k = p.find_last_of('/'); return k == std::string::npos ? p : p.substr(k + 1); };
+        for (size_t i = 0; i < res.size(); ++i) {
+            size_t l = 0, r = 0;
+            for (size_t k = 0; k < scene.shots.size(); ++k) { if (scene.shots[k] == res[i].left) l = k; if (scene.shots[k] == res[i].right) r = k; }
+            const RgbImage img = draw_matches(images[l].data, images[l].rows, images[l].cols, images[l].step, 1,
+                                              features[l].keypoints.data(), sizeof(sfm_keypoint),
+                                              images[r].data, images[r].rows, images[r].cols, images[r].step, 1,
+                                              features[r].keypoints.data(), sizeof(sfm_keypoint),
+                                              res[i].matches.data(), res[i].matches.size());
+            const std::string path = mdir + "/" + std::to_string(i) + base(paths[l]) + "-" + base(paths[r]) + ".ppm";
+            if (!write_ppm(path, img)) throw std::runtime_error("cannot write " + path);
+        }
+        std::printf("match_pictures=%zu dir=%s\n", res.size(), mdir.c_str());
+    }
     return 0;
 }
 

@@ -72,4 +72,14 @@ def test_cli_extracts_matches_and_rates_the_pairs(tmp_path, sfm):
     assert (int(tail.group(1)), int(tail.group(2)), int(tail.group(3))) == (3, len(kept), sum(len(res[p]) for p in kept))
     ratios = {(l, r): float(v) for l, r, v in re.findall(r"shot(\d)\.pgm : \S*shot(\d)\.pgm -> \d+ homographyInlierRatio: (\S+)", out.stdout)}
     assert ratios[("0", "1")] > 0.8
+    # the stage's on-disk artifact (PhotogrammetrieCli.cpp:174-199): one side-by-side picture per kept pair, deterministic bytes
+    mdir = tmp_path / "matches"
+    mdir.mkdir()
+    out2 = run_cli(*[f"-Pimage={p}" for p in paths], "-Pmatch-threshold=4", "-Pransac-matching-threshold=-3", f"-Pout-matches-dir={mdir}")
+    assert f"match_pictures={len(kept)}" in out2.stdout, out2.stdout + out2.stderr
+    pic = (mdir / "0shot0.pgm-shot1.pgm.ppm").read_bytes()
+    assert pic.startswith(b"P6\n640 240\n255\n") and len(pic) == 15 + 640 * 240 * 3
+    px = np.frombuffer(pic[15:], np.uint8).reshape(240, 640, 3)
+    coloured = (px[..., 0] != px[..., 1]) | (px[..., 1] != px[..., 2])                 # the grey shots carry coloured lines
+    assert coloured.sum() > 50 * len(res[0]) and coloured[:, :320].any() and coloured[:, 320:].any()
     m.close()

@@ -18,7 +18,9 @@ def test_two_gpu_result_is_byte_identical_to_one_gpu():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                         "--master-addr", "127.0.0.1", "--master-port", "29611",
                         os.path.join(ROOT, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    diag = "\n".join(ln[:600] for ln in (r.stdout + "\n" + r.stderr).splitlines()
+                     if "MISMATCH" in ln or "MGPU_" in ln or "Error" in ln or "rror:" in ln or "line " in ln)
+    assert r.returncode == 0, diag[-6000:]
     assert "MGPU_IDENTICAL" in r.stdout
 
 
