@@ -268,6 +268,26 @@ typedef struct sfm_sift_opts {
     int32_t reserved;
 } sfm_sift_opts;
 void sfm_sift_opts_default(sfm_sift_opts *o);
+/* The reference's other detector: cv::ORB::create(featureLimit) (PhotogrammetrieCli.cpp:347-348; -Pfeature-detector=ORB,
+ * run-scripts/run-orb-sequence.sh:4), detect() + compute() on the device (csrc/orb.cu): 8-level pyramid (INTER_LINEAR_EXACT),
+ * FAST-9 + non-maximum suppression, Harris ranking with retainBest's tie rule per level, intensity-centroid orientation,
+ * 7 x 7 Gaussian blur, rotated 256-bit BRIEF.  Device == the numpy restatement (oracle/orb_np.py), which equals cv2 (keypoint
+ * SET, responses and descriptors identical, angles within 1e-3 degrees); keypoints come back ordered by (level, y, x) — cv::ORB's
+ * own order is a by-product of std::nth_element.  Only n_features may differ from cv::ORB::create's defaults (the reference
+ * passes nothing else); descriptors are 32 bytes, one feature set holds SIFT or ORB images, not both. */
+typedef struct sfm_orb_opts {
+    int32_t n_features;            /* cv::ORB::create's nfeatures (default 500); the reference passes its feature-limit */
+    int32_t max_keypoints;         /* capacity of the per-image lists, 0 = 262143; retainBest keeps ties, so slightly more than
+                                      n_features keypoints can come back */
+    int32_t n_levels, edge_threshold, patch_size, fast_threshold;   /* 8, 31, 31, 20: other values -> SFM_ERR_UNSUPPORTED */
+    float   scale_factor;          /* 1.2f */
+    int32_t reserved;
+} sfm_orb_opts;
+void sfm_orb_opts_default(sfm_orb_opts *o);
+int sfm_features_extract_orb(sfm_ctx *ctx, const uint8_t *gray, int rows, int cols, size_t step_bytes,
+                             const sfm_orb_opts *opts, int32_t *n_keypoints);
+/* Descriptor bytes per keypoint of the images extracted so far: 128 (SIFT), 32 (ORB), 0 = none yet. */
+int sfm_features_descriptor_bytes(const sfm_ctx *ctx, int *bytes);
 /* Host-side helper in front of the extractor: the grey conversion cv::SIFT applies to a colour photograph
  * (cvtColor COLOR_BGR2GRAY on 8-bit data: (B*3735 + G*19235 + R*9798 + 2^14) >> 15).  channels = 3 or 4 (alpha ignored),
  * rgb_order != 0 for R,G,B[,A] input; steps in bytes, 0 = dense.  No GPU involved. */
@@ -277,6 +297,7 @@ int sfm_features_clear(sfm_ctx *ctx);
 int sfm_features_extract_sift(sfm_ctx *ctx, const uint8_t *gray, int rows, int cols, size_t step_bytes,
                               const sfm_sift_opts *opts, int32_t *n_keypoints);
 int sfm_features_count(const sfm_ctx *ctx, int *n_images);
+/* descriptors: n_keypoints x sfm_features_descriptor_bytes() */
 int sfm_features_download(sfm_ctx *ctx, int image, int32_t *n_keypoints, sfm_keypoint *keypoints, uint8_t *descriptors);
 int sfm_bank_from_features(sfm_ctx *ctx);
 /* Measurement / test aids: [0] DoG extrema, [1] keypoints before removeDuplicatedSorted, [2] keypoints of the last

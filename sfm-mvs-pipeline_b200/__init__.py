@@ -36,6 +36,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_homography_opts_default", "sfm_sift_opts_default", "sfm_features_clear", "sfm_features_extract_sift",
            "sfm_features_count", "sfm_features_download", "sfm_bank_from_features", "sfm_features_last_counts",
            "sfm_features_pyramid_level", "sfm_features_last_profile", "sfm_gray_from_bgr",
+           "sfm_orb_opts_default", "sfm_features_extract_orb", "sfm_features_descriptor_bytes",
            "sfm_mgpu_create", "sfm_mgpu_destroy", "sfm_mgpu_device_count", "sfm_mgpu_ctx", "sfm_mgpu_last_error",
            "sfm_mgpu_bank_upload", "sfm_mgpu_match_pairs", "sfm_mgpu_match_pairs_from_host", "sfm_dist_unique_id",
            "sfm_dist_init", "sfm_dist_info", "sfm_dist_match_pairs", "sfm_dist_match_pairs_from_host",
@@ -60,6 +61,11 @@ class SiftOpts(C.Structure):
                 ("edge_threshold", C.c_double), ("sigma", C.c_double), ("n_features", C.c_int32), ("reserved", C.c_int32)]
 
 
+class OrbOpts(C.Structure):
+    _fields_ = [("n_features", C.c_int32), ("max_keypoints", C.c_int32), ("n_levels", C.c_int32), ("edge_threshold", C.c_int32),
+                ("patch_size", C.c_int32), ("fast_threshold", C.c_int32), ("scale_factor", C.c_float), ("reserved", C.c_int32)]
+
+
 class Opts(C.Structure):
     _fields_ = [("norm", C.c_int32), ("k", C.c_int32), ("ratio", C.c_double), ("cross_check", C.c_int32),
                 ("distinct", C.c_int32), ("min_match_count", C.c_int32), ("engine", C.c_int32)]
@@ -80,6 +86,7 @@ def load_library():
     lib.sfm_ctx_destroy.restype = None
     lib.sfm_opts_default.restype = None
     lib.sfm_homography_opts_default.restype = None
+    lib.sfm_orb_opts_default.restype = None
     lib.sfm_mgpu_destroy.restype = None
     lib.sfm_mgpu_ctx.restype = C.c_void_p
     lib.sfm_mgpu_last_error.restype = C.c_char_p
@@ -475,6 +482,32 @@ class Matcher:
                                                    C.byref(n)))
         return n.value
 
+    def extract_orb(self, gray: np.ndarray, n_features: int = 500, max_keypoints: int = 0, **other) -> int:
+        """detect() + compute() of cv::ORB::create(n_features) on one grey uint8 image, appended to the context's feature set
+        (32-byte descriptors).  `other`: n_levels / edge_threshold / patch_size / fast_threshold / scale_factor (defaults only)."""
+        gray = np.asarray(gray)
+        if gray.dtype == np.uint8 and gray.ndim == 3 and gray.shape[2] in (3, 4):
+            gray = gray_from_bgr(gray)
+        if gray.dtype != np.uint8 or gray.ndim != 2:
+            raise SfmError(ERR_INVALID, "extract_orb needs a uint8 grey [rows, cols] or BGR [rows, cols, 3] image")
+        if gray.size and gray.strides[1] != 1:
+            gray = np.ascontiguousarray(gray)
+        o = OrbOpts()
+        _lib.sfm_orb_opts_default(C.byref(o))
+        o.n_features, o.max_keypoints = n_features, max_keypoints
+        for k, v in other.items():
+            setattr(o, k, v)
+        n = C.c_int32(0)
+        step = gray.strides[0] if gray.shape[0] > 1 else gray.shape[1]
+        self._check(_lib.sfm_features_extract_orb(self._ctx, C.c_void_p(gray.ctypes.data if gray.size else None),
+                                                  C.c_int(gray.shape[0]), C.c_int(gray.shape[1]), C.c_size_t(step), C.byref(o), C.byref(n)))
+        return n.value
+
+    def features_descriptor_bytes(self) -> int:
+        b = C.c_int(0)
+        self._check(_lib.sfm_features_descriptor_bytes(self._ctx, C.byref(b)))
+        return b.value
+
     def features_count(self) -> int:
         n = C.c_int(0)
         self._check(_lib.sfm_features_count(self._ctx, C.byref(n)))
@@ -485,7 +518,7 @@ class Matcher:
         n = C.c_int32(0)
         self._check(_lib.sfm_features_download(self._ctx, C.c_int(image), C.byref(n), None, None))
         kps = np.zeros(n.value, KEYPOINT_DTYPE)
-        desc = np.zeros((n.value, 128), np.uint8)
+        desc = np.zeros((n.value, self.features_descriptor_bytes() or 128), np.uint8)
         if n.value:
             self._check(_lib.sfm_features_download(self._ctx, C.c_int(image), C.byref(n), kps.ctypes.data_as(C.c_void_p),
                                                    desc.ctypes.data_as(C.c_void_p)))

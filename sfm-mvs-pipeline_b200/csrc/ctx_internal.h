@@ -193,7 +193,9 @@ struct sfm_ctx {
     cudaEvent_t tune_ev = nullptr;
     // feature extraction stage (sift.cu): images extracted so far, device-resident
     SiftWorkspace* sift = nullptr;
-    DevBuf feat_kp, feat_desc;       // sfm_keypoint[total], u8[total][128]
+    OrbWorkspace* orb = nullptr;
+    int feat_cols = 0;               // descriptor bytes of the images extracted so far: 128 (SIFT) / 32 (ORB), 0 = none yet
+    DevBuf feat_kp, feat_desc;       // sfm_keypoint[total], u8[total][feat_cols]
     std::vector<int64_t> feat_off{0};
     int feat_counts[3] = {0, 0, 0};
     int tcv_issuers = 2;             // MMA-issuing warps of the value-only kernel (SFM_TCV_ISSUERS = 1 | 2)

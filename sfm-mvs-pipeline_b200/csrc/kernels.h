@@ -215,6 +215,17 @@ void sift_last_profile(const SiftWorkspace* w, double* pyramid_ms, double* total
 // test hook: geometry of the pyramid of the last extraction (float offsets of level 0 of every octave) and its base pointer
 int sift_pyramid_geometry(const SiftWorkspace* w, int* n_layers, int* widths, int* heights, int64_t* offsets, const float** base);
 cudaError_t launch_keypoint_xy(const void* keypoints, int n, float2* xy, cudaStream_t s);
+// ---- orb.cu: feature extraction with cv::ORB::create(featureLimit) (PhotogrammetrieCli.cpp:347-348)
+struct OrbWorkspace;
+OrbWorkspace* orb_workspace_create();
+void orb_workspace_destroy(OrbWorkspace* w);
+// One grey image (host memory) -> keypoints ordered by (level, y, x) in input-image coordinates and 32-byte descriptors in the
+// workspace's device buffers; synchronises the stream once at the end.
+cudaError_t orb_extract(OrbWorkspace* w, const uint8_t* gray, int rows, int cols, size_t step, int n_features, int max_keypoints,
+                        cudaStream_t s, int* n_keypoints, int* n_launches, std::string* err);
+const void* orb_keypoints_device_raw(const OrbWorkspace* w);         // sfm_keypoint[n]
+const uint8_t* orb_descriptors_device(const OrbWorkspace* w);        // n x 32
+float orb_last_ms(const OrbWorkspace* w);
 // schedule order -> input pair order (pipelined host path)
 cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
                            const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,

@@ -962,6 +962,7 @@ void sfm_ctx_destroy(sfm_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     c->feat_kp.release(); c->feat_desc.release();
     sift_workspace_destroy(c->sift);
+    orb_workspace_destroy(c->orb);
     c->h_meta.release(); c->h_stage[0].release(); c->h_stage[1].release(); c->h_scalars.release(); c->h_knn.release();
     for (int k = 0; k < 2; ++k) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
     if (c->meta_ev) cudaEventDestroy(c->meta_ev);
@@ -1232,6 +1233,27 @@ int sfm_homography_inlier_ratios(sfm_ctx* c, const double* thresholds, int64_t n
 static_assert(sizeof(sfm_keypoint) == 24, "sfm_keypoint layout (= sift::Keypoint of csrc/sift_core.cuh)");
 static_assert(sizeof(sfm_sift_opts) == 40, "sfm_sift_opts layout");
 
+}  // extern "C"
+
+// one extracted image joins the context's device-resident feature set (all images of a set share the descriptor width)
+static int append_features(sfm_ctx* c, const void* d_kp, const uint8_t* d_desc, int n, int desc_bytes) {
+    if (c->feat_cols != 0 && c->feat_cols != desc_bytes && c->feat_off.size() > 1)
+        return fail(c, SFM_ERR_STATE, "features: SIFT and ORB images cannot share one feature set (sfm_features_clear first)");
+    c->feat_cols = desc_bytes;
+    const int64_t used = c->feat_off.back();
+    const size_t db = static_cast<size_t>(desc_bytes);
+    CU_TRY(c, c->feat_kp.ensure_keep(static_cast<size_t>(used + n) * sizeof(sfm_keypoint) + 16, static_cast<size_t>(used) * sizeof(sfm_keypoint), c->stream));
+    CU_TRY(c, c->feat_desc.ensure_keep(static_cast<size_t>(used + n) * db + 16, static_cast<size_t>(used) * db, c->stream));
+    if (n > 0) {
+        CU_TRY(c, cudaMemcpyAsync(c->feat_kp.as<sfm_keypoint>() + used, d_kp, static_cast<size_t>(n) * sizeof(sfm_keypoint), cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(c->feat_desc.as<uint8_t>() + used * db, d_desc, static_cast<size_t>(n) * db, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->feat_off.push_back(used + n);
+    return SFM_OK;
+}
+
+extern "C" {
+
 void sfm_sift_opts_default(sfm_sift_opts* o) {
     if (!o) return;
     o->n_octave_layers = 3;          // cv::SIFT::create defaults (features2d.hpp); the reference CLI passes (0, 3, 0.09)
@@ -1247,6 +1269,7 @@ int sfm_features_clear(sfm_ctx* c) {
     if (!c) return SFM_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
     c->feat_off.assign(1, 0);
+    c->feat_cols = 0;
     return SFM_OK;
 }
 
@@ -1280,17 +1303,60 @@ int sfm_features_extract_sift(sfm_ctx* c, const uint8_t* gray, int rows, int col
                     err.empty() ? cudaGetErrorString(e) : err);
     c->stat_launches += launches;
     c->stat_h2d += static_cast<int64_t>(rows) * cols;
-    const int64_t used = c->feat_off.back();
-    CU_TRY(c, c->feat_kp.ensure_keep(static_cast<size_t>(used + n) * sizeof(sfm_keypoint) + 16, static_cast<size_t>(used) * sizeof(sfm_keypoint), c->stream));
-    CU_TRY(c, c->feat_desc.ensure_keep(static_cast<size_t>(used + n) * 128 + 16, static_cast<size_t>(used) * 128, c->stream));
-    if (n > 0) {
-        CU_TRY(c, cudaMemcpyAsync(c->feat_kp.as<sfm_keypoint>() + used, sift_keypoints_device_raw(c->sift), static_cast<size_t>(n) * sizeof(sfm_keypoint),
-                                  cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(c, cudaMemcpyAsync(c->feat_desc.as<uint8_t>() + used * 128, sift_descriptors_device(c->sift), static_cast<size_t>(n) * 128,
-                                  cudaMemcpyDeviceToDevice, c->stream));
-    }
-    c->feat_off.push_back(used + n);
+    const int rc_app = append_features(c, sift_keypoints_device_raw(c->sift), sift_descriptors_device(c->sift), n, 128);
+    if (rc_app != SFM_OK) return rc_app;
     if (n_keypoints) *n_keypoints = n;
+    return SFM_OK;
+}
+
+void sfm_orb_opts_default(sfm_orb_opts* o) {
+    if (!o) return;
+    o->n_features = 500;             // cv::ORB::create defaults (features2d.hpp); the reference passes its feature-limit
+    o->max_keypoints = 0;
+    o->n_levels = 8; o->edge_threshold = 31; o->patch_size = 31; o->fast_threshold = 20;
+    o->scale_factor = 1.2f;
+    o->reserved = 0;
+}
+
+int sfm_features_extract_orb(sfm_ctx* c, const uint8_t* gray, int rows, int cols, size_t step_bytes, const sfm_orb_opts* opts,
+                             int32_t* n_keypoints) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    NvtxRange nvtx_range("sfm:features_extract_orb");
+    sfm_orb_opts o;
+    sfm_orb_opts_default(&o);
+    if (opts) o = *opts;
+    if (!gray || rows <= 0 || cols <= 0) return fail(c, SFM_ERR_INVALID, "extract: empty image");
+    if (step_bytes == 0) step_bytes = static_cast<size_t>(cols);
+    if (step_bytes < static_cast<size_t>(cols)) return fail(c, SFM_ERR_INVALID, "extract: step smaller than a row");
+    if (rows > 32768 || cols > 32768) return fail(c, SFM_ERR_CAPACITY, "extract: image side above 32768 pixels");
+    if (o.n_features < 0) return fail(c, SFM_ERR_INVALID, "extract: nfeatures must be >= 0");
+    if (o.n_levels != 8 || o.edge_threshold != 31 || o.patch_size != 31 || o.fast_threshold != 20 || o.scale_factor != 1.2f)
+        return fail(c, SFM_ERR_UNSUPPORTED, "extract: only cv::ORB::create's defaults (scaleFactor 1.2, 8 levels, edgeThreshold 31, patchSize 31, "
+                                            "fastThreshold 20, HARRIS_SCORE, WTA_K 2) are built; the reference changes nfeatures only");
+    // ties of retainBest can exceed nfeatures: capacity = 2 x nfeatures + slack, capped by the matcher's per-image limit
+    int max_kp = o.max_keypoints > 0 ? o.max_keypoints : SFM_MAX_ROWS - 1;
+    if (max_kp >= SFM_MAX_ROWS) max_kp = SFM_MAX_ROWS - 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (!c->orb) c->orb = orb_workspace_create();
+    int n = 0, launches = 0;
+    std::string err;
+    cudaError_t e = orb_extract(c->orb, gray, rows, cols, step_bytes, o.n_features, max_kp, c->stream, &n, &launches, &err);
+    if (e != cudaSuccess)
+        return fail(c, e == cudaErrorMemoryAllocation && !err.empty() && err.find("capacity") != std::string::npos ? SFM_ERR_CAPACITY
+                       : (e == cudaErrorInvalidValue && !err.empty() ? SFM_ERR_INVALID : SFM_ERR_CUDA),
+                    err.empty() ? cudaGetErrorString(e) : err);
+    c->stat_launches += launches;
+    c->stat_h2d += static_cast<int64_t>(rows) * cols;
+    const int rc_app = append_features(c, orb_keypoints_device_raw(c->orb), orb_descriptors_device(c->orb), n, 32);
+    if (rc_app != SFM_OK) return rc_app;
+    if (n_keypoints) *n_keypoints = n;
+    return SFM_OK;
+}
+
+int sfm_features_descriptor_bytes(const sfm_ctx* c, int* bytes) {
+    if (!c || !bytes) return SFM_ERR_INVALID;
+    *bytes = c->feat_cols;
     return SFM_OK;
 }
 
@@ -1322,9 +1388,10 @@ int sfm_features_download(sfm_ctx* c, int image, int32_t* n_keypoints, sfm_keypo
     if (n == 0 || (!kps && !desc)) return SFM_OK;
     CU_TRY(c, cudaSetDevice(c->device));
     if (kps) CU_TRY(c, cudaMemcpyAsync(kps, c->feat_kp.as<sfm_keypoint>() + r0, static_cast<size_t>(n) * sizeof(sfm_keypoint), cudaMemcpyDeviceToHost, c->stream));
-    if (desc) CU_TRY(c, cudaMemcpyAsync(desc, c->feat_desc.as<uint8_t>() + r0 * 128, static_cast<size_t>(n) * 128, cudaMemcpyDeviceToHost, c->stream));
+    const size_t db = static_cast<size_t>(c->feat_cols);
+    if (desc) CU_TRY(c, cudaMemcpyAsync(desc, c->feat_desc.as<uint8_t>() + r0 * db, static_cast<size_t>(n) * db, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    c->stat_d2h += n * ((kps ? 24 : 0) + (desc ? 128 : 0));
+    c->stat_d2h += n * ((kps ? 24 : 0) + (desc ? static_cast<int64_t>(db) : 0));
     return SFM_OK;
 }
 
@@ -1357,14 +1424,15 @@ int sfm_bank_from_features(sfm_ctx* c) {
     std::vector<int32_t> n_rows(std::max(n_images, 1));
     for (int i = 0; i < n_images; ++i) n_rows[i] = static_cast<int32_t>(c->feat_off[i + 1] - c->feat_off[i]);
     Bank& b = c->bank;
-    int rc = bank_layout(c, b, n_images, n_rows.data(), 128, SFM_CV_8U);
+    const size_t db = static_cast<size_t>(c->feat_cols ? c->feat_cols : 128);        // 128: cv::SIFT rows, 32: cv::ORB rows
+    int rc = bank_layout(c, b, n_images, n_rows.data(), static_cast<int>(db), SFM_CV_8U);
     if (rc != SFM_OK) return rc;
-    CU_TRY(c, b.d_u8.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * 128)));
+    CU_TRY(c, b.d_u8.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * db)));
     CU_TRY(c, b.d_kp.ensure(std::max<size_t>(16, static_cast<size_t>(b.padded_rows) * 8)));
     for (int i = 0; i < n_images; ++i) {
         if (n_rows[i] == 0) continue;
-        CU_TRY(c, cudaMemcpyAsync(b.d_u8.as<uint8_t>() + static_cast<size_t>(b.row0[i]) * 128,
-                                  c->feat_desc.as<uint8_t>() + c->feat_off[i] * 128, static_cast<size_t>(n_rows[i]) * 128,
+        CU_TRY(c, cudaMemcpyAsync(b.d_u8.as<uint8_t>() + static_cast<size_t>(b.row0[i]) * db,
+                                  c->feat_desc.as<uint8_t>() + c->feat_off[i] * db, static_cast<size_t>(n_rows[i]) * db,
                                   cudaMemcpyDeviceToDevice, c->stream));
         CU_TRY(c, launch_keypoint_xy(c->feat_kp.as<sfm_keypoint>() + c->feat_off[i], n_rows[i], b.d_kp.as<float2>() + b.row0[i], c->stream));
         c->stat_launches++;

@@ -106,7 +106,6 @@ static void report(const std::vector<ShotMatches>& res, size_t n_pairs, double d
 
 // -Pimage=...: extractFeatures -> calculateShotMatches -> calculateHomography, all on the device (SfM.cpp:152-156 order)
 static int runFromImages(const Args& args, const std::vector<std::string>& paths, const std::string& det, int limit, int loglevel) {
-    if (det == "ORB") throw std::invalid_argument("-Pimage with feature-detector=ORB: ORB extraction is not built on the device");
     std::vector<std::vector<uint8_t>> pixels(paths.size());
     std::vector<GrayImage> images(paths.size());
     Scene scene;
@@ -119,15 +118,21 @@ static int runFromImages(const Args& args, const std::vector<std::string>& paths
         scene.shots.push_back(shot);
     }
     std::vector<std::string> warnings;
-    if (det != "SIFT" && !det.empty()) warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
-    auto matcher = configureFeatureMatcher("SIFT", args.get("feature-matcher"), std::stoi(args.get("device", "0")), &warnings);
+    const bool orb = det == "ORB";                    // PhotogrammetrieCli.cpp:344-356: ORB, else SIFT (+ warning for anything else)
+    if (!orb && det != "SIFT" && !det.empty()) warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
+    auto matcher = configureFeatureMatcher(orb ? "ORB" : "SIFT", args.get("feature-matcher"), std::stoi(args.get("device", "0")), &warnings);
     auto strategy = configureFeatureMatcherStrategy(std::stoi(args.get("feature-sequence", "0")),
                                                     std::stoi(args.get("feature-gridlength", "0")), &warnings);
     for (auto& w : warnings) std::fprintf(stderr, "[WARN] %s\n", w.c_str());
-    GpuSiftFeatureDetector detector(matcher, limit, 3, 0.09);         // cv::SIFT::create(featureLimit, 3, 0.09)
     std::vector<Features> features;
     const auto t0 = std::chrono::steady_clock::now();
-    detector.extractFeatures(images, scene, features);
+    if (orb) {
+        GpuOrbFeatureDetector detector(matcher, limit);               // cv::ORB::create(featureLimit)
+        detector.extractFeatures(images, scene, features);
+    } else {
+        GpuSiftFeatureDetector detector(matcher, limit, 3, 0.09);     // cv::SIFT::create(featureLimit, 3, 0.09)
+        detector.extractFeatures(images, scene, features);
+    }
     const double t_extract = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     size_t n_kp = 0;
     for (auto& f : features) n_kp += f.keypoints.size();

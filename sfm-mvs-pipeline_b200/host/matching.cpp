@@ -212,8 +212,10 @@ GpuSiftFeatureDetector::GpuSiftFeatureDetector(const std::shared_ptr<GpuDescript
     opts_.sigma = sigma;
 }
 
-void GpuSiftFeatureDetector::extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features) {
-    sfm_ctx* ctx = matcher_->context();
+// the loop of SfM::extractFeatures (SfM.cpp:577-597) around one detector; `extractOne` runs detect + compute of image i on the device
+template <class ExtractOne>
+static void extractAll(sfm_ctx* ctx, const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features, int descBytes,
+                       ExtractOne extractOne) {
     if (scene.shots.empty())
         for (std::size_t i = 0; i < images.size(); ++i) scene.shots.push_back(std::make_shared<Shot>());
     if (scene.shots.size() != images.size()) throw std::invalid_argument("extractFeatures: one image per shot");
@@ -223,13 +225,14 @@ void GpuSiftFeatureDetector::extractFeatures(const std::vector<GrayImage>& image
     for (std::size_t i = 0; i < images.size(); ++i) {
         const GrayImage& im = images[i];
         int32_t n = 0;
-        check(ctx, sfm_features_extract_sift(ctx, im.data, im.rows, im.cols, im.step, &opts_, &n));
+        check(ctx, extractOne(im, &n));
         Features& f = features[i];
+        f.descriptorBytes = descBytes;
         f.keypoints.resize(static_cast<std::size_t>(n));
-        f.descriptors.resize(static_cast<std::size_t>(n) * 128);
+        f.descriptors.resize(static_cast<std::size_t>(n) * descBytes);
         if (n > 0) check(ctx, sfm_features_download(ctx, static_cast<int>(i), &n, f.keypoints.data(), f.descriptors.data()));
         Shot& s = *scene.shots[i];
-        s.descriptors = DescriptorMat{f.descriptors.data(), n, 128, 128, SFM_CV_8U};
+        s.descriptors = DescriptorMat{f.descriptors.data(), n, descBytes, static_cast<std::size_t>(descBytes), SFM_CV_8U};
         s.keypointPts = n > 0 ? &f.keypoints[0].x : nullptr;
         s.keypointStep = sizeof(sfm_keypoint);
         s.imageWidth = im.cols;
@@ -237,6 +240,26 @@ void GpuSiftFeatureDetector::extractFeatures(const std::vector<GrayImage>& image
     }
     check(ctx, sfm_bank_from_features(ctx));
     scene.bankResident = true;
+}
+
+void GpuSiftFeatureDetector::extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features) {
+    sfm_ctx* ctx = matcher_->context();
+    extractAll(ctx, images, scene, features, 128, [&](const GrayImage& im, int32_t* n) {
+        return sfm_features_extract_sift(ctx, im.data, im.rows, im.cols, im.step, &opts_, n);
+    });
+}
+
+GpuOrbFeatureDetector::GpuOrbFeatureDetector(const std::shared_ptr<GpuDescriptorMatcher>& matcher, int nfeatures) : matcher_(matcher) {
+    if (!matcher) throw std::invalid_argument("Der Feature Detektor braucht den GPU Kontext des Matchers.");
+    sfm_orb_opts_default(&opts_);
+    opts_.n_features = nfeatures;
+}
+
+void GpuOrbFeatureDetector::extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features) {
+    sfm_ctx* ctx = matcher_->context();
+    extractAll(ctx, images, scene, features, 32, [&](const GrayImage& im, int32_t* n) {
+        return sfm_features_extract_orb(ctx, im.data, im.rows, im.cols, im.step, &opts_, n);
+    });
 }
 
 std::shared_ptr<GpuDescriptorMatcher> configureFeatureMatcher(const std::string& det, const std::string& mat, int device,

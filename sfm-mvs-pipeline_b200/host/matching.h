@@ -95,7 +95,8 @@ struct Scene {
 // Features (CameraShot.h:39-42) as the device extractor returns them: cv::KeyPoint minus class_id, CV_8U descriptor rows
 struct Features {
     std::vector<sfm_keypoint> keypoints;
-    std::vector<uint8_t> descriptors;       // keypoints.size() x 128
+    std::vector<uint8_t> descriptors;       // keypoints.size() x descriptorBytes
+    int descriptorBytes = 128;              // 128: cv::SIFT rows (as CV_8U), 32: cv::ORB rows
 };
 
 struct GrayImage {              // subset of the CV_8UC1 cv::Mat that Shot::loadImage + cv::SIFT's grey conversion yield
@@ -220,6 +221,18 @@ public:
 private:
     std::shared_ptr<GpuDescriptorMatcher> matcher_;
     sfm_sift_opts opts_;
+};
+
+// cv::ORB::create(featureLimit) (PhotogrammetrieCli.cpp:347-348) on the matcher's GPU context; same contract as the SIFT detector,
+// the bank it leaves behind holds 32-byte descriptors for NORM_HAMMING matching.
+class GpuOrbFeatureDetector {
+public:
+    explicit GpuOrbFeatureDetector(const std::shared_ptr<GpuDescriptorMatcher>& matcher, int nfeatures = 500);
+    void extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features);
+
+private:
+    std::shared_ptr<GpuDescriptorMatcher> matcher_;
+    sfm_orb_opts opts_;
 };
 
 // PhotogrammetrieCli::configureFeatureMatcher / configureFeatureMatcherStrategy (PhotogrammetrieCli.cpp:320-392)

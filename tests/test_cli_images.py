@@ -35,8 +35,6 @@ def test_pgm_errors_are_reported_like_the_reference_reports_exceptions(tmp_path)
     assert out.returncode == 0 and "truncated PNM" in out.stderr
     good = tmp_path / "good.pgm"
     write_pgm(good, workloads.synthetic_photo(0, 60, 80))
-    out = run_cli(f"-Pimage={good}", "-Pfeature-detector=ORB")
-    assert "ORB extraction is not built" in out.stderr
     colour = tmp_path / "colour.ppm"                       # binary PPM: converted with cv::SIFT's grey conversion on the host
     rgb = np.stack([workloads.synthetic_photo(s, 60, 80) for s in (1, 2, 3)], -1)
     colour.write_bytes(b"P6\n80 60\n255\n" + rgb.tobytes())
@@ -82,4 +80,28 @@ def test_cli_extracts_matches_and_rates_the_pairs(tmp_path, sfm):
     px = np.frombuffer(pic[15:], np.uint8).reshape(240, 640, 3)
     coloured = (px[..., 0] != px[..., 1]) | (px[..., 1] != px[..., 2])                 # the grey shots carry coloured lines
     assert coloured.sum() > 50 * len(res[0]) and coloured[:, :320].any() and coloured[:, 320:].any()
+    m.close()
+
+
+@pytest.mark.gpu
+def test_cli_orb_detector(tmp_path, sfm):
+    """-Pfeature-detector=ORB -Pimage=...: cv::ORB::create(feature-limit) + NORM_HAMMING matching on the device (run-orb-sequence.sh)."""
+    a = workloads.synthetic_photo(11, 240, 320)
+    imgs = [a, np.roll(a, (3, 5), axis=(0, 1))]
+    paths = []
+    for i, im in enumerate(imgs):
+        paths.append(str(tmp_path / f"shot{i}.pgm"))
+        write_pgm(paths[-1], im)
+    out = run_cli(*[f"-Pimage={p}" for p in paths], "-Pfeature-detector=ORB", "-Pfeature-limit=3000", "-Pfeature-sequence=2",
+                  "-Pmatch-threshold=4", "-Pransac-matching-threshold=-3")
+    assert out.returncode == 0 and "[ERROR]" not in out.stderr, out.stderr
+    head = re.search(r"images=(\d+) keypoints=(\d+)", out.stdout)
+    tail = re.search(r"pairs=(\d+) kept=(\d+) matches=(\d+)", out.stdout)
+    m = sfm.Matcher(0)
+    m.features_clear()
+    n_kp = sum(m.extract_orb(im, n_features=3000) for im in imgs)
+    m.bank_from_features()
+    res = m.match_pairs([[0, 1]], sfm.NORM_HAMMING, min_match_count=4)
+    assert (int(head.group(1)), int(head.group(2))) == (2, n_kp)
+    assert (int(tail.group(1)), int(tail.group(2)), int(tail.group(3))) == (1, 1, len(res[0])) and len(res[0]) > 100
     m.close()
