@@ -286,6 +286,9 @@ typedef struct sfm_orb_opts {
 void sfm_orb_opts_default(sfm_orb_opts *o);
 int sfm_features_extract_orb(sfm_ctx *ctx, const uint8_t *gray, int rows, int cols, size_t step_bytes,
                              const sfm_orb_opts *opts, int32_t *n_keypoints);
+/* Test aid: one per-pixel map of the last ORB extraction at pyramid level `level` (what: 0 level image, 1 blurred image, 2 FAST
+ * score, 3 score after non-maximum suppression + border filter — uint8; 4 Harris response — float); out may be NULL to query the size. */
+int sfm_features_orb_level(sfm_ctx *ctx, int what, int level, void *out, int32_t *width, int32_t *height);
 /* Descriptor bytes per keypoint of the images extracted so far: 128 (SIFT), 32 (ORB), 0 = none yet. */
 int sfm_features_descriptor_bytes(const sfm_ctx *ctx, int *bytes);
 /* Host-side helper in front of the extractor: the grey conversion cv::SIFT applies to a colour photograph

@@ -36,7 +36,7 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_homography_opts_default", "sfm_sift_opts_default", "sfm_features_clear", "sfm_features_extract_sift",
            "sfm_features_count", "sfm_features_download", "sfm_bank_from_features", "sfm_features_last_counts",
            "sfm_features_pyramid_level", "sfm_features_last_profile", "sfm_gray_from_bgr",
-           "sfm_orb_opts_default", "sfm_features_extract_orb", "sfm_features_descriptor_bytes",
+           "sfm_orb_opts_default", "sfm_features_extract_orb", "sfm_features_descriptor_bytes", "sfm_features_orb_level",
            "sfm_mgpu_create", "sfm_mgpu_destroy", "sfm_mgpu_device_count", "sfm_mgpu_ctx", "sfm_mgpu_last_error",
            "sfm_mgpu_bank_upload", "sfm_mgpu_match_pairs", "sfm_mgpu_match_pairs_from_host", "sfm_dist_unique_id",
            "sfm_dist_init", "sfm_dist_info", "sfm_dist_match_pairs", "sfm_dist_match_pairs_from_host",
@@ -502,6 +502,14 @@ class Matcher:
         self._check(_lib.sfm_features_extract_orb(self._ctx, C.c_void_p(gray.ctypes.data if gray.size else None),
                                                   C.c_int(gray.shape[0]), C.c_int(gray.shape[1]), C.c_size_t(step), C.byref(o), C.byref(n)))
         return n.value
+
+    def orb_level(self, what: int, level: int) -> np.ndarray:
+        """Test aid: 0 level image, 1 blurred, 2 FAST score, 3 candidates (uint8), 4 Harris response (float32)."""
+        w, h = C.c_int32(0), C.c_int32(0)
+        self._check(_lib.sfm_features_orb_level(self._ctx, C.c_int(what), C.c_int(level), None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.float32 if what == 4 else np.uint8)
+        self._check(_lib.sfm_features_orb_level(self._ctx, C.c_int(what), C.c_int(level), out.ctypes.data_as(C.c_void_p), C.byref(w), C.byref(h)))
+        return out
 
     def features_descriptor_bytes(self) -> int:
         b = C.c_int(0)

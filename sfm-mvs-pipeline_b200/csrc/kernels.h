@@ -226,6 +226,8 @@ cudaError_t orb_extract(OrbWorkspace* w, const uint8_t* gray, int rows, int cols
 const void* orb_keypoints_device_raw(const OrbWorkspace* w);         // sfm_keypoint[n]
 const uint8_t* orb_descriptors_device(const OrbWorkspace* w);        // n x 32
 float orb_last_ms(const OrbWorkspace* w);
+// test hook: per-pixel map of the last extraction; returns the element size (1 or 4 bytes) or -1
+int orb_level_map(const OrbWorkspace* w, int what, int level, const void** ptr, int* width, int* height);
 // schedule order -> input pair order (pipelined host path)
 cudaError_t launch_reorder(const DMatch* src, const int64_t* off_s, const int64_t* total, const int64_t* order,
                            const uint8_t* drop_s, int64_t n, int64_t* cnt_tmp, int64_t* off_in, DMatch* dst,

@@ -34,7 +34,7 @@ namespace sfm {
 namespace {
 
 constexpr int kOrbLevels = 8, kOrbEdge = 31, kOrbHalfPatch = 15, kOrbFastThreshold = 20, kOrbPatch = 31;
-constexpr int kOrbPatchPixels = 709;           // pixels of the circular patch (umax table)
+constexpr int kOrbPatchPixels = 749;           // pixels of the circular patch (umax table)
 
 struct OrbLevels {
     int w[kOrbLevels], h[kOrbLevels];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) orb_resize_kernel(const uint8_t* __restri
 }
 
 // cornerScore<16> where the pixel is a FAST-9 corner for the threshold, 0 elsewhere.  Window minima over the 16-cycle by
-// doubling: m9[k] = min(d[k .. k+8]);  bright score = max_k m9,  dark score = -min_k max(d[k .. k+8]).
+// doubling: m9[k] = min(d[k .. k+8]);  bright score = max_k m9 on d = centre - circle, dark score the same on circle - centre.
 __global__ void __launch_bounds__(256) orb_fast_kernel(const uint8_t* __restrict__ img, int w, int h, int threshold,
                                                        uint8_t* __restrict__ score) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
@@ -99,21 +99,27 @@ __global__ void __launch_bounds__(256) orb_fast_kernel(const uint8_t* __restrict
     if (x >= 3 && y >= 3 && x < w - 3 && y < h - 3) {
         const uint8_t* p = img + static_cast<size_t>(y) * w + x;
         const int v = p[0];
-        int d[16];
+        // d = centre - circle (bright centre), e = circle - centre (dark centre): two min-chains.  (Written without negating a
+        // max-chain: nvcc 12.9 folded  max(lo9, -hi9)  into one VIMNMX3 and lost the negation on sm_100a.)
+        int d[16], e[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - p[c_circle_dy[k] * w + c_circle_dx[k]];
-        int lo[16], hi[16];
+        for (int k = 0; k < 16; ++k) {
+            const int q = p[c_circle_dy[k] * w + c_circle_dx[k]];
+            d[k] = v - q;
+            e[k] = q - v;
+        }
+        int d2[16], e2[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { lo[k] = min(d[k], d[(k + 1) & 15]); hi[k] = max(d[k], d[(k + 1) & 15]); }          // 2
-        int lo4[16], hi4[16];
+        for (int k = 0; k < 16; ++k) { d2[k] = min(d[k], d[(k + 1) & 15]); e2[k] = min(e[k], e[(k + 1) & 15]); }            // 2
+        int d4[16], e4[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { lo4[k] = min(lo[k], lo[(k + 2) & 15]); hi4[k] = max(hi[k], hi[(k + 2) & 15]); }    // 4
+        for (int k = 0; k < 16; ++k) { d4[k] = min(d2[k], d2[(k + 2) & 15]); e4[k] = min(e2[k], e2[(k + 2) & 15]); }        // 4
         int best = -1000000;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const int lo8 = min(lo4[k], lo4[(k + 4) & 15]), hi8 = max(hi4[k], hi4[(k + 4) & 15]);                         // 8
-            const int lo9 = min(lo8, d[(k + 8) & 15]), hi9 = max(hi8, d[(k + 8) & 15]);                                   // 9
-            best = max(best, max(lo9, -hi9));
+            const int d9 = min(min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);                                               // 9
+            const int e9 = min(min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
+            best = max(best, max(d9, e9));
         }
         if (best > threshold) s = best - 1;
     }
@@ -404,6 +410,7 @@ struct OrbWorkspace {
     int* d_lxy = nullptr; size_t lxy_cap = 0;
     uint8_t* d_desc = nullptr; size_t desc_cap = 0;
     bool tables_set = false;
+    OrbLevels last{};                                      // geometry of the last extraction (test hook)
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float total_ms = 0.f;
 };
@@ -417,6 +424,21 @@ void orb_workspace_destroy(OrbWorkspace* w) {
     if (w->h_counts) cudaFreeHost(w->h_counts);
     for (cudaEvent_t e : w->ev) if (e) cudaEventDestroy(e);
     delete w;
+}
+// test hook: one per-pixel map of the last extraction (0 image, 1 blurred image, 2 FAST score, 3 candidates after the
+// non-maximum suppression: all u8; 4 Harris response: float) and the level geometry
+int orb_level_map(const OrbWorkspace* w, int what, int level, const void** ptr, int* width, int* height) {
+    if (level < 0 || level >= kOrbLevels || w->last.w[level] <= 0) return -1;
+    const int64_t off = w->last.off[level];
+    *width = w->last.w[level]; *height = w->last.h[level];
+    switch (what) {
+        case 0: *ptr = w->d_img + off; return 1;
+        case 1: *ptr = w->d_blur + off; return 1;
+        case 2: *ptr = w->d_score + off; return 1;
+        case 3: *ptr = w->d_cand + off; return 1;
+        case 4: *ptr = w->d_resp + off; return 4;
+        default: return -1;
+    }
 }
 const void* orb_keypoints_device_raw(const OrbWorkspace* w) { return w->d_kp; }
 const uint8_t* orb_descriptors_device(const OrbWorkspace* w) { return w->d_desc; }
@@ -443,6 +465,7 @@ cudaError_t orb_extract(OrbWorkspace* ws, const uint8_t* gray, int rows, int col
         total_rows += L.h[lv];
         max_w = std::max(max_w, L.w[lv]);
     }
+    ws->last = L;
     // nfeaturesPerLevel (computeKeyPoints)
     int quota[kOrbLevels], small_host[40] = {0};
     {

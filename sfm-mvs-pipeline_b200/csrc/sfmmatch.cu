@@ -1354,6 +1354,23 @@ int sfm_features_extract_orb(sfm_ctx* c, const uint8_t* gray, int rows, int cols
     return SFM_OK;
 }
 
+int sfm_features_orb_level(sfm_ctx* c, int what, int level, void* out, int32_t* width, int32_t* height) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->orb) return fail(c, SFM_ERR_STATE, "features: no ORB extraction has run");
+    const void* p = nullptr;
+    int w = 0, h = 0;
+    const int esz = orb_level_map(c->orb, what, level, &p, &w, &h);
+    if (esz < 0) return fail(c, SFM_ERR_INVALID, "features: no such ORB level / map");
+    if (width) *width = w;
+    if (height) *height = h;
+    if (!out) return SFM_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(out, p, static_cast<size_t>(w) * h * esz, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return SFM_OK;
+}
+
 int sfm_features_descriptor_bytes(const sfm_ctx* c, int* bytes) {
     if (!c || !bytes) return SFM_ERR_INVALID;
     *bytes = c->feat_cols;

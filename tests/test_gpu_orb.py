@@ -100,7 +100,7 @@ def test_orb_features_feed_the_hamming_matcher(m, sfm):
 def test_orb_edge_cases(m, sfm):
     m.features_clear()
     assert m.extract_orb(np.full((100, 100), 50, np.uint8)) == 0
-    assert m.extract_orb(workloads.synthetic_photo(1, 70, 70)) == 0         # every level is narrower than 2 x edgeThreshold + 1
+    assert m.extract_orb(workloads.synthetic_photo(1, 62, 62)) == 0         # no level is wider than 2 x edgeThreshold
     wide = workloads.synthetic_photo(5, 150, 400)
     m.features_clear()
     m.extract_orb(wide[:, 40:300], n_features=800)
@@ -116,5 +116,24 @@ def test_orb_edge_cases(m, sfm):
     with pytest.raises(sfm.SfmError) as e:                                   # one feature set holds SIFT or ORB images, not both
         m.extract_sift(wide)
     assert e.value.code == sfm.ERR_STATE
-    with pytest.raises(sfm.SfmError):
-        m.extract_orb(np.zeros((4, 4), np.uint8))                            # too small for 8 levels
+    m.features_clear()
+    assert m.extract_orb(np.zeros((4, 4), np.uint8)) == 0                    # 8 levels down to 1 x 1 pixel, no keypoints
+
+
+def test_pyramid_score_and_blur_maps_equal_restatement(m):
+    """The per-pixel maps behind the keypoints (test hook sfm_features_orb_level): every pyramid level (INTER_LINEAR_EXACT from the
+    previous level), the FAST score map, the candidates after non-maximum suppression + border filter and the blurred level."""
+    img = workloads.synthetic_photo(6, 240, 320)
+    m.features_clear()
+    m.extract_orb(img, n_features=30000)
+    levels = O.build_pyramid(img)
+    for lv in range(8):
+        assert np.array_equal(m.orb_level(0, lv), levels[lv]), lv
+        assert np.array_equal(m.orb_level(1, lv), O.blur_level(levels[lv])), lv
+        assert np.array_equal(m.orb_level(2, lv), O.fast9_scores(levels[lv])), lv
+        xs, ys, s = O.fast9_corners(levels[lv])
+        h, w = levels[lv].shape
+        inb = (xs >= 31) & (xs < w - 31) & (ys >= 31) & (ys < h - 31)
+        ref = np.zeros((h, w), np.uint8)
+        ref[ys[inb], xs[inb]] = s[inb]
+        assert np.array_equal(m.orb_level(3, lv), ref), lv
