@@ -198,6 +198,17 @@ int sfm_dist_assign_pairs(const int32_t *pairs, int64_t n_pairs, const int32_t *
                           int32_t *owner);
 /* Images [*first_image, *end_image) are the ones participant `rank` uploads in the from_host exchange path. */
 int sfm_dist_upload_share(const int32_t *n_rows, int n_images, int world, int rank, int *first_image, int *end_image);
+/* The images of a scene were extracted on different participants (the loop of SfM::extractFeatures, SfM.cpp:577-597, split
+ * over the GPUs): collective exchange after which EVERY participant's feature set holds all n_images_total images in scene order
+ * (then sfm_bank_from_features on each).  global_index[k] = scene position of the k-th image this participant extracted. */
+int sfm_dist_features_allgather(sfm_ctx *ctx, const int32_t *global_index, int n_local, int n_images_total);
+/* One process: image i is extracted on device i % n (detector: SFM_DETECTOR_SIFT with sfm_sift_opts, SFM_DETECTOR_ORB with
+ * sfm_orb_opts; opts may be NULL), the sets are exchanged, every device adopts the scene as its bank + keypoint table.
+ * n_keypoints[n_images] may be NULL; features are read back through sfm_features_download(sfm_mgpu_ctx(g, 0), ...). */
+#define SFM_DETECTOR_SIFT 0
+#define SFM_DETECTOR_ORB  1
+int sfm_mgpu_extract_features(sfm_mgpu *g, int detector, int n_images, const uint8_t *const *gray, const int32_t *rows,
+                              const int32_t *cols, const size_t *step_bytes, const void *opts, int32_t *n_keypoints);
 /* Host-clock phases (ms) of the last collective on this participant: [0] upload + exchange enqueued / deal,
  * [1] kernels enqueued, [3] totals all-gather incl. waiting for the kernels, [4] send/recv + reorder + D2H. */
 int sfm_dist_last_phases(const sfm_ctx *ctx, double *ms /* 8 */);

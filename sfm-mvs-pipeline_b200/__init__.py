@@ -40,7 +40,8 @@ EXPORTS = ["sfm_opts_default", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_er
            "sfm_mgpu_create", "sfm_mgpu_destroy", "sfm_mgpu_device_count", "sfm_mgpu_ctx", "sfm_mgpu_last_error",
            "sfm_mgpu_bank_upload", "sfm_mgpu_match_pairs", "sfm_mgpu_match_pairs_from_host", "sfm_dist_unique_id",
            "sfm_dist_init", "sfm_dist_info", "sfm_dist_match_pairs", "sfm_dist_match_pairs_from_host",
-           "sfm_dist_assign_pairs", "sfm_dist_upload_share", "sfm_dist_last_phases"]
+           "sfm_dist_assign_pairs", "sfm_dist_upload_share", "sfm_dist_last_phases", "sfm_dist_features_allgather",
+           "sfm_mgpu_extract_features"]
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4")])          # sfm_keypoint = cv::KeyPoint without class_id
@@ -356,6 +357,11 @@ class Matcher:
         buf = (C.c_uint8 * DIST_ID_BYTES).from_buffer_copy(uid) if uid is not None else None
         self._check(_lib.sfm_dist_init(self._ctx, buf, C.c_int(rank), C.c_int(world)))
 
+    def dist_features_allgather(self, global_index, n_images_total: int):
+        """Collective: afterwards this context's feature set holds every image of the scene in scene order."""
+        gi = np.ascontiguousarray(global_index, np.int32)
+        self._check(_lib.sfm_dist_features_allgather(self._ctx, gi.ctypes.data_as(C.c_void_p), C.c_int(len(gi)), C.c_int(n_images_total)))
+
     def dist_info(self):
         a, b = C.c_int(), C.c_int()
         _lib.sfm_dist_info(self._ctx, C.byref(a), C.byref(b))
@@ -617,6 +623,29 @@ class MultiGpuMatcher:
 
     def ctx(self, i) -> Matcher:
         return _CtxView(_lib.sfm_mgpu_ctx(self._g, C.c_int(i)), self.devices[i])
+
+    def extract_features(self, images, detector: str = "SIFT", **opts):
+        """SfM::extractFeatures over all devices (image i on device i % n), feature sets exchanged, every device adopts the scene
+        as its bank.  Returns the keypoint counts; read features back with ctx(0).features_download(i)."""
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        rows = (C.c_int32 * n)(*[im.shape[0] for im in imgs])
+        cols = (C.c_int32 * n)(*[im.shape[1] for im in imgs])
+        steps = (C.c_size_t * n)(*[im.strides[0] for im in imgs])
+        if detector.upper() == "ORB":
+            o = OrbOpts()
+            _lib.sfm_orb_opts_default(C.byref(o))
+            det = 1
+        else:
+            o = SiftOpts()
+            _lib.sfm_sift_opts_default(C.byref(o))
+            det = 0
+        for k, v in opts.items():
+            setattr(o, k, v)
+        counts = (C.c_int32 * n)()
+        self._check(_lib.sfm_mgpu_extract_features(self._g, C.c_int(det), C.c_int(n), ptrs, rows, cols, steps, C.byref(o), counts))
+        return list(counts)
 
     def upload_bank(self, descriptors):
         keep, ptrs, nrows, steps, cols, depth = Matcher._bank_args(None, descriptors)

@@ -553,6 +553,98 @@ static int dist_from_host_body(sfm_ctx* c, DistState* d, int n_images, const voi
     return gather_impl(c, d, n_pairs, out);
 }
 
+// The images of a scene were extracted on different participants (SfM::extractFeatures' loop split over the GPUs): replicate
+// the feature sets so that every participant holds all images in global order, ready for sfm_bank_from_features.
+//   global_index[k] = scene position of the k-th image THIS participant extracted (its feature set holds exactly those, in
+//   call order).  One all-reduce of 3 ints per image (count, owner, local position) tells everybody the layout; every
+//   participant's keypoint and descriptor blocks travel with one ncclBroadcast each; local copies sort the images into place.
+static int dist_features_allgather_impl(sfm_ctx* c, DistState* d, const int32_t* global_index, int n_local, int n_total) {
+    NvtxRange nvtx_range("sfm:dist_features_allgather");
+    NcclApi& nc = nccl_api();
+    cudaStream_t s = c->stream;
+    const int W = d->world, me = d->rank;
+    if (n_total < 0 || n_local < 0 || (n_local > 0 && !global_index)) return fail(c, SFM_ERR_INVALID, "features exchange: bad arguments");
+    if (n_local != static_cast<int>(c->feat_off.size()) - 1)
+        return fail(c, SFM_ERR_STATE, "features exchange: global_index must name every image of this participant's feature set");
+    std::vector<int32_t> tab(static_cast<size_t>(3 * n_total + 1), 0);
+    for (int k = 0; k < n_local; ++k) {
+        const int g = global_index[k];
+        if (g < 0 || g >= n_total || tab[3 * g + 1] != 0) return fail(c, SFM_ERR_INVALID, "features exchange: image index out of range or repeated");
+        tab[3 * g] = static_cast<int32_t>(c->feat_off[k + 1] - c->feat_off[k]);
+        tab[3 * g + 1] = me + 1;
+        tab[3 * g + 2] = k + 1;
+    }
+    tab[3 * n_total] = c->feat_cols;                       // every participant must use the same detector (max over ranks below)
+    DevBuf d_tab;
+    CU_TRY(c, d_tab.ensure(tab.size() * 4));
+    auto guard = [&](int rc) { d_tab.release(); return rc; };
+    if (cudaMemcpyAsync(d_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return guard(fail(c, SFM_ERR_CUDA, "features exchange: H2D"));
+    if (nc.AllReduce(d_tab.p, d_tab.p, tab.size(), ncclInt32, ncclMax, d->comm, s) != ncclSuccess) return guard(fail(c, SFM_ERR_NCCL, "features exchange: all-reduce"));
+    if (cudaMemcpyAsync(tab.data(), d_tab.p, tab.size() * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+        return guard(fail(c, SFM_ERR_CUDA, "features exchange: D2H"));
+    d_tab.release();
+    const int cols = tab[3 * n_total];
+    if (c->feat_cols != 0 && c->feat_cols != cols) return fail(c, SFM_ERR_STATE, "features exchange: participants used different detectors");
+    const size_t db = static_cast<size_t>(cols ? cols : 128);
+    // per participant: its images in local order, its block size
+    std::vector<std::vector<int>> imgs(W);
+    for (int g = 0; g < n_total; ++g) {
+        const int owner = tab[3 * g + 1] - 1;
+        if (owner < 0) return fail(c, SFM_ERR_INVALID, "features exchange: image " + std::to_string(g) + " was extracted by nobody");
+        imgs[owner].push_back(g);
+    }
+    std::vector<int64_t> block0(static_cast<size_t>(W) + 1, 0);
+    for (int r = 0; r < W; ++r) {
+        std::sort(imgs[r].begin(), imgs[r].end(), [&](int a, int b) { return tab[3 * a + 2] < tab[3 * b + 2]; });
+        int64_t n = 0;
+        for (int g : imgs[r]) n += tab[3 * g];
+        block0[r + 1] = block0[r] + n;
+    }
+    const int64_t total = block0[W];
+    DevBuf stage_kp, stage_desc, new_kp, new_desc;
+    auto fail_free = [&](int rc) { stage_kp.release(); stage_desc.release(); new_kp.release(); new_desc.release(); return rc; };
+    if (stage_kp.ensure(static_cast<size_t>(total) * sizeof(sfm_keypoint) + 16) != cudaSuccess || stage_desc.ensure(static_cast<size_t>(total) * db + 16) != cudaSuccess ||
+        new_kp.ensure(static_cast<size_t>(total) * sizeof(sfm_keypoint) + 16) != cudaSuccess || new_desc.ensure(static_cast<size_t>(total) * db + 16) != cudaSuccess)
+        return fail_free(fail(c, SFM_ERR_CUDA, "features exchange: out of device memory"));
+    const int64_t mine = block0[me + 1] - block0[me];
+    if (mine != c->feat_off.back()) return fail_free(fail(c, SFM_ERR_STATE, "features exchange: local feature set changed during the exchange"));
+    if (mine > 0) {
+        cudaMemcpyAsync(stage_kp.as<sfm_keypoint>() + block0[me], c->feat_kp.p, static_cast<size_t>(mine) * sizeof(sfm_keypoint), cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(stage_desc.as<uint8_t>() + block0[me] * db, c->feat_desc.p, static_cast<size_t>(mine) * db, cudaMemcpyDeviceToDevice, s);
+    }
+    if (nc.GroupStart() != ncclSuccess) return fail_free(fail(c, SFM_ERR_NCCL, "features exchange: group"));
+    for (int r = 0; r < W; ++r) {
+        const int64_t n = block0[r + 1] - block0[r];
+        if (n == 0) continue;
+        void* pk = stage_kp.as<sfm_keypoint>() + block0[r];
+        void* pd = stage_desc.as<uint8_t>() + block0[r] * db;
+        nc.Broadcast(pk, pk, static_cast<size_t>(n) * sizeof(sfm_keypoint), ncclUint8, r, d->comm, s);
+        nc.Broadcast(pd, pd, static_cast<size_t>(n) * db, ncclUint8, r, d->comm, s);
+    }
+    if (nc.GroupEnd() != ncclSuccess) return fail_free(fail(c, SFM_ERR_NCCL, "features exchange: broadcast"));
+    // into global image order
+    std::vector<int64_t> off(static_cast<size_t>(n_total) + 1, 0);
+    for (int g = 0; g < n_total; ++g) off[g + 1] = off[g] + tab[3 * g];
+    for (int r = 0; r < W; ++r) {
+        int64_t src = block0[r];
+        for (int g : imgs[r]) {
+            const int64_t n = tab[3 * g];
+            if (n > 0) {
+                cudaMemcpyAsync(new_kp.as<sfm_keypoint>() + off[g], stage_kp.as<sfm_keypoint>() + src, static_cast<size_t>(n) * sizeof(sfm_keypoint), cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(new_desc.as<uint8_t>() + off[g] * db, stage_desc.as<uint8_t>() + src * db, static_cast<size_t>(n) * db, cudaMemcpyDeviceToDevice, s);
+            }
+            src += n;
+        }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail_free(fail(c, SFM_ERR_CUDA, "features exchange: copies"));
+    stage_kp.release(); stage_desc.release();
+    c->feat_kp.release(); c->feat_desc.release();
+    c->feat_kp = new_kp; c->feat_desc = new_desc;             // ownership moves (DevBuf is a plain pointer + capacity)
+    c->feat_off = off;
+    c->feat_cols = cols;
+    return SFM_OK;
+}
+
 }  // namespace sfmhost
 
 // ==================================================================================================== C ABI
@@ -701,6 +793,20 @@ int sfm_dist_match_pairs_from_host(sfm_ctx* c, int n_images, const void* const* 
     return dist_from_host_impl(c, d, n_images, rows, n_rows, cols, step_bytes, cv_depth, pairs, n_pairs, opts, out);
 }
 
+int sfm_dist_features_allgather(sfm_ctx* c, const int32_t* global_index, int n_local, int n_images_total) {
+    if (!c) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU_TRY(c, cudaSetDevice(c->device));
+    DistState* d = static_cast<DistState*>(c->dist);
+    if (!d || d->world == 1) {
+        // one participant: the set is complete if it names every image once, in order
+        if (n_local != n_images_total || n_local != static_cast<int>(c->feat_off.size()) - 1) return fail(c, SFM_ERR_INVALID, "features exchange: incomplete set");
+        for (int k = 0; k < n_local; ++k) if (global_index[k] != k) return fail(c, SFM_ERR_UNSUPPORTED, "features exchange: one participant keeps call order");
+        return SFM_OK;
+    }
+    return dist_features_allgather_impl(c, d, global_index, n_local, n_images_total);
+}
+
 int sfm_dist_last_phases(const sfm_ctx* c, double* ms) {
     if (!c || !ms) return SFM_ERR_INVALID;
     const DistState* d = static_cast<const DistState*>(c->dist);
@@ -767,6 +873,34 @@ int sfm_mgpu_bank_upload(sfm_mgpu* g, int n_images, const void* const* rows, con
     if (!g) return SFM_ERR_INVALID;
     std::lock_guard<std::mutex> lk(g->call_mu);
     return run_all(g, [&](int i) { return sfm_bank_upload(g->ctx[i], n_images, rows, n_rows, cols, step_bytes, cv_depth); });
+}
+
+// SfM::extractFeatures' loop over the shots (SfM.cpp:577-597) split over the devices: image i goes to device i % n, the feature
+// sets are exchanged over NCCL and every device adopts the whole scene as its descriptor bank + keypoint table.
+int sfm_mgpu_extract_features(sfm_mgpu* g, int detector, int n_images, const uint8_t* const* gray, const int32_t* rows, const int32_t* cols,
+                              const size_t* step_bytes, const void* opts, int32_t* n_keypoints) {
+    if (!g || n_images < 0 || (n_images > 0 && (!gray || !rows || !cols))) return SFM_ERR_INVALID;
+    if (detector != SFM_DETECTOR_SIFT && detector != SFM_DETECTOR_ORB) return SFM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g->call_mu);
+    const int n = static_cast<int>(g->ctx.size());
+    return run_all(g, [&](int i) {
+        sfm_ctx* c = g->ctx[i];
+        int rc = sfm_features_clear(c);
+        std::vector<int32_t> mine;
+        for (int k = i; k < n_images && rc == SFM_OK; k += n) {
+            int32_t nk = 0;
+            const size_t st = step_bytes ? step_bytes[k] : 0;
+            rc = detector == SFM_DETECTOR_ORB
+                     ? sfm_features_extract_orb(c, gray[k], rows[k], cols[k], st, static_cast<const sfm_orb_opts*>(opts), &nk)
+                     : sfm_features_extract_sift(c, gray[k], rows[k], cols[k], st, static_cast<const sfm_sift_opts*>(opts), &nk);
+            if (n_keypoints) n_keypoints[k] = nk;
+            mine.push_back(k);
+        }
+        if (rc != SFM_OK) return rc;       // (a failing participant leaves the others waiting in the exchange: inputs are validated alike)
+        rc = sfm_dist_features_allgather(c, mine.data(), static_cast<int>(mine.size()), n_images);
+        if (rc != SFM_OK) return rc;
+        return sfm_bank_from_features(c);
+    });
 }
 
 int sfm_mgpu_match_pairs(sfm_mgpu* g, const int32_t* pairs, int64_t n_pairs, const sfm_opts* opts, sfm_result** out) {

@@ -102,3 +102,42 @@ def test_cli_devices_switch_is_byte_identical(tmp_path):
         outs.append((open(out, "rb").read(), [ln for ln in r.stdout.splitlines() if "homographyInlierRatio" in ln]))
     assert outs[0][0] == outs[1][0] and len(outs[0][0]) > 10000
     assert outs[0][1] == outs[1][1] and len(outs[0][1]) >= 7
+
+
+@pytest.mark.parametrize("detector", ["SIFT", "ORB"])
+def test_extraction_split_over_gpus_equals_one_gpu(detector):
+    """SfM::extractFeatures split over the devices (sfm_mgpu_extract_features: image i on device i % n, NCCL exchange of the feature
+    sets, every device adopts the scene): every device ends up with the single-GPU feature set, and matching on top of it is
+    byte-identical."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    import workloads
+    sfm = ge.load_package()
+    n = min(torch.cuda.device_count(), 4)
+    base = workloads.synthetic_photo(11, 200, 280)
+    imgs = [base, np.roll(base, (3, 5), axis=(0, 1)), workloads.synthetic_photo(12, 160, 240), np.full((70, 90), 9, np.uint8),
+            np.roll(base, (-4, 2), axis=(0, 1))]
+    one = sfm.Matcher(0)
+    one.features_clear()
+    kw = dict(n_features=1500) if detector == "ORB" else dict(contrast_threshold=0.09, n_features=10000)
+    counts1 = [(one.extract_orb if detector == "ORB" else one.extract_sift)(im, **kw) for im in imgs]
+    one.bank_from_features()
+    norm = sfm.NORM_HAMMING if detector == "ORB" else sfm.NORM_L2
+    pairs = sfm.select_pairs(len(imgs), 0, 0)
+    full = one.match_pairs(pairs, norm)
+    g = sfm.MultiGpuMatcher(list(range(n)))
+    counts = g.extract_features(imgs, detector, **kw)
+    assert counts == counts1
+    for dev in range(n):
+        c = g.ctx(dev)
+        for i in range(len(imgs)):
+            a, b = one.features_download(i), c.features_download(i)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (dev, i)
+    res = g.match_pairs(pairs, norm)
+    assert np.array_equal(res.offsets, full.offsets) and res.matches.tobytes() == full.matches.tobytes() and int(full.offsets[-1]) > 100
+    g.close()
+    one.close()
