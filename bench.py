@@ -475,10 +475,16 @@ def run_ours(a):
                                "avg_launch_ms": knn_ms / max(1, knn_launches), "peak_source": src,
                                "algorithmic": "32*(Nq+Nt) B read + 16 B per good match, per pair (SURVEY 8d)",
                                "note": "all-pairs Hamming is O(Nq*Nt) work over O(N) bytes: HBM is structurally not the binding roof",
-                               "popc_per_s": popc_step * a.steps / (knn_ms / 1e3) if knn_ms > 0 else None,
-                               "popc_roof_per_s": popc_peak,
-                               "popc_roof_frac": (popc_step * a.steps / (knn_ms / 1e3) / popc_peak) if knn_ms > 0 else None,
                                "knn_share_of_step": knn_ms / ms_total if ms_total else None}
+            if kw:          # the __popc kernel: its binding roof is the POPC issue rate
+                out["roofline"].update({"popc_per_s": popc_step * a.steps / (knn_ms / 1e3) if knn_ms > 0 else None,
+                                        "popc_roof_per_s": popc_peak, "popc_roof_source": f"148 SM x 16 POPC/clk x {sm_mhz} MHz",
+                                        "popc_roof_frac": (popc_step * a.steps / (knn_ms / 1e3) / popc_peak) if knn_ms > 0 else None})
+            else:           # bits expanded to bytes: the same contraction with K = 256 on the tensor cores
+                tops = 2.0 * n_rows * n_rows * 256 * n_mine * a.steps / (knn_ms / 1e3) / 1e12 if knn_ms > 0 else None
+                out["roofline"].update({"tensor_top_s": tops, "tensor_peak": 2.0 * bf16_sust,
+                                        "tensor_frac": (tops / (2.0 * bf16_sust)) if tops else None,
+                                        "tensor_algorithmic": "2*Nq*Nt*256 op per pair (one u8 per descriptor bit)"})
         else:
             ops_per_step_rank = 2.0 * n_rows * n_rows * 128 * n_mine
             achieved = ops_per_step_rank * a.steps / (knn_ms / 1e3) / 1e12 if knn_ms > 0 else None

@@ -467,6 +467,47 @@ __global__ void __launch_bounds__(256, 4) refine_value_rows_kernel(RefineArgs a)
 #pragma unroll
         for (int k = 0; k < 8; ++k) q[k] = __ldg(qv + k);
         long long a1 = LLONG_MAX, a2 = LLONG_MAX;
+        const int sub0 = a.chunk_rows / 32;
+        bool done = false;
+        // ---- stage A: the best chunk alone.  Every train row outside it has D <= D2, i.e. d^2 >= |a|^2 - 2 D2 =: lb2, and the best
+        // row of chunk 2 has d^2 in [lb2, lb2 + 1] (the parity bit of |b|^2).  A real match has e0 < lb2: it is certified as THE
+        // nearest neighbour, and the ratio test is decided from d1^2 in [min(e1', lb2), min(e1', lb2 + 1)] (e1' = second best inside
+        // the chunk) unless the two ends disagree — a third of the exact distances of the full path (dense pair lists: C4).
+        if (!a.all_rows && c2raw >= 0 && !(c2raw & 0x40000000)) {
+            for (int k = 0; k < sub0; ++k) warp_chunk_candidates(a.bank, a.norm2, q, na, tr0, ntr, c1 * sub0 + k, lane, a1, a2);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const long long b1 = __shfl_xor_sync(0xffffffffu, a1, off), b2 = __shfl_xor_sync(0xffffffffu, a2, off);
+                a2 = min(max(a1, b1), min(a2, b2));
+                a1 = min(a1, b1);
+            }
+            if (a1 != LLONG_MAX) {
+                const long long e0 = a1 >> 32;
+                const long long lb2 = static_cast<long long>(na) - 2ll * __float_as_int(t.d1);
+                if (e0 < lb2) {
+                    const long long e1 = a2 != LLONG_MAX ? (a2 >> 32) : LLONG_MAX;
+                    const long long lo1 = min(e1, lb2), hi1 = min(e1, lb2 + 1);
+                    const float s0 = __fsqrt_rn(static_cast<float>(static_cast<int32_t>(e0)));
+                    const bool pass_lo = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(lo1)))) * a.ratio;
+                    const bool pass_hi = static_cast<double>(s0) < static_cast<double>(__fsqrt_rn(static_cast<float>(static_cast<int32_t>(hi1)))) * a.ratio;
+                    if (pass_lo == pass_hi) {
+                        __syncwarp();
+                        if (lane == 0) {
+                            Top2 o;
+                            o.i0 = static_cast<int>(a1 & 0xFFFFFFFFll); o.d0 = static_cast<float>(static_cast<int32_t>(e0));
+                            // the second neighbour itself is not reported by the ratio-filtered stage: any index >= 0 marks "a
+                            // second neighbour exists", d1 = the end of the interval that was tested (keep_basic re-runs the test)
+                            o.i1 = a2 != LLONG_MAX ? static_cast<int>(a2 & 0xFFFFFFFFll) : ntr;
+                            o.d1 = static_cast<float>(static_cast<int32_t>(pass_lo ? lo1 : hi1));
+                            a.top2[srow] = o;
+                        }
+                        done = true;
+                    }
+                }
+            }
+            a1 = LLONG_MAX; a2 = LLONG_MAX;
+        }
+        if (done) continue;
         if (c2raw >= 0 && (c2raw & 0x40000000)) {
             // ambiguous: a fourth chunk ties the second one -> exact brute force over the whole train image
             warp_brute_force(a.bank, a.norm2, q, na, tr0, ntr, lane, a1, a2);
