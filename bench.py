@@ -2,12 +2,14 @@
 """bench.py — image-pairs/s of the matching stage on BASELINE config C3
 (synthetic unordered all-pairs: 200 images x 8192 SIFT 128-d descriptors, 19 900 pairs).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1, or --single-process)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU matcher
 
-A step = one pass of the hot path over the whole pair list.  `value` = pairs/s with the descriptor bank
-resident in HBM (device time, CUDA events on the library's stream, max over ranks); `e2e` = the same through
-the C-ABI with HOST buffers (pinned CV_32F descriptors uploaded and match lists copied back every step).
+A step = one pass of the hot path over the whole pair list.  `value` follows SURVEY 8d's timing protocol: descriptor bank
+resident in HBM; submit the pair list -> every filtered match list in pinned host memory on participant 0 (kernels,
+compaction, NCCL gather, D2H), CUDA events on the library's stream, max over ranks.  `e2e` = the same through the C ABI with
+HOST buffers (pinned CV_32F descriptors of every shot uploaded, lists copied back, every step; median over the passes).
+Every line carries the SHA-1 of the result and asserts it against a single-GPU run of the whole list.
 """
 from __future__ import annotations
 
@@ -617,10 +619,47 @@ def run_extract_reference(a):
                       "steps_images_per_s": [round(r, 2) for r in rates]}))
 
 
+def run_extract_group(a):
+    """--workload extract --gpus N --single-process: SfM::extractFeatures split over N GPUs from one process (image i on device
+    i % N), feature sets exchanged over NCCL, every device adopts the scene as its bank (sfm_mgpu_extract_features)."""
+    import torch
+    import __graft_entry__ as ge
+    sfm = ge.load_package()
+    imgs, name = _extract_images(a)
+    g = sfm.MultiGpuMatcher(list(range(a.gpus)))
+    opts = dict(contrast_threshold=0.09, n_features=10000)
+    for _ in range(max(a.warmup, 3)):
+        counts = g.extract_features(imgs, "SIFT", **opts)
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    per = []
+    for _ in range(a.steps):
+        t0 = time.perf_counter()
+        counts = g.extract_features(imgs, "SIFT", **opts)
+        per.append(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    v = len(imgs) / float(np.median(per))
+    launches = sum(g.ctx(i).stats()["kernel_launches"] for i in range(a.gpus))
+    _emit(json.dumps({"metric": EXTRACT_METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
+                      "ms_per_step": 1e3 * float(np.median(per)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": name, "keypoints_per_step": int(sum(counts)),
+                                 "parallelism": f"images x{a.gpus} (one process, one thread per GPU: sfm_mgpu_extract_features)",
+                                 "value_includes": "H2D of the grey images, NCCL exchange of the feature sets, bank adoption on every GPU; wall clock",
+                                 "note": "secondary line (SURVEY 8f rank 3), not the north-star metric"},
+                      "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": int(sum(i.nbytes for i in imgs)), "d2h_bytes_per_step": 0,
+                              "note": "value is already end to end from host images; features stay on the devices"},
+                      "gpu_launches": int(launches), "clocks": clocks}))
+    g.close()
+
+
 def run_extract_ours(a):
     import torch
+    if a.single_process and a.gpus > 1:
+        return run_extract_group(a)
     if a.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
-        raise SystemExit("--workload extract is a single-GPU line (images are independent: replicas only)")
+        raise SystemExit("--workload extract: one GPU, or --gpus N --single-process (images split over the GPUs of one process)")
     import __graft_entry__ as ge
     sfm = ge.load_package()
     m = sfm.Matcher(0)
