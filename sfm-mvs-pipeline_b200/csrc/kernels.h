@@ -41,6 +41,7 @@ struct TcvFuse {
     // shared-memory queue, re-rank them exactly (refine_dot_row) and append them to done_list; rows they cannot decide go
     // to bf_list.  refine = 0: survivors go to need_list for the post pass instead.
     int refine;
+    int uniform_units;           // > 0: every pair of the launch has this many 128-row units (pair of a unit = a division, no search)
     const uint8_t* bank;
     int32_t* done_list;
     int* done_count;

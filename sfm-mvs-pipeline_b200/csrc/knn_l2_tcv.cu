@@ -76,10 +76,20 @@ constexpr int kQHigh = 96;                     // 96 + 4 producer warps x 32 row
 
 struct UnitInfoV { PairDesc pd; int rb; int n_tiles; };
 
+// uniform_units > 0: every pair of the launch has that many units (all images of the same size: the BASELINE configurations), so the
+// pair of a unit is a division instead of a binary search over the prefix array — twelve dependent loads at the start of every
+// unit in every warp of the CTA otherwise
 template <int BN>
 __device__ __forceinline__ UnitInfoV decode_unit_v(const PairDesc* __restrict__ pairs, const int64_t* __restrict__ unit_prefix,
-                                                   int n_pairs, int64_t unit) {
+                                                   int n_pairs, int64_t unit, int uniform_units = 0) {
     UnitInfoV u;
+    if (uniform_units > 0) {
+        const int p = static_cast<int>(unit / uniform_units);
+        u.pd = pairs[p];
+        u.rb = static_cast<int>(unit - static_cast<int64_t>(p) * uniform_units);
+        u.n_tiles = (u.pd.nt + BN - 1) / BN;
+        return u;
+    }
     const int p = find_segment(unit_prefix, n_pairs, unit);
     u.pd = pairs[p];
     u.rb = static_cast<int>(unit - unit_prefix[p]);
@@ -114,6 +124,17 @@ __device__ __forceinline__ void top5_max(int32_t k, int32_t& m1, int32_t& m2, in
     const int32_t w = min(m3, u);
     m3 = max(m3, u);
     const int32_t x = min(m4, w);
+    m4 = max(m4, w);
+    m5 = max(m5, x);
+}
+__device__ __forceinline__ void top5_maxu(uint32_t k, uint32_t& m1, uint32_t& m2, uint32_t& m3, uint32_t& m4, uint32_t& m5) {
+    const uint32_t t = min(m1, k);
+    m1 = max(m1, k);
+    const uint32_t u = min(m2, t);
+    m2 = max(m2, t);
+    const uint32_t w = min(m3, u);
+    m3 = max(m3, u);
+    const uint32_t x = min(m4, w);
     m4 = max(m4, w);
     m5 = max(m5, x);
 }
@@ -173,6 +194,9 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr uint32_t kIdesc = C::kIdesc, kIdescExt = C::kIdescExt;
     constexpr int kGroups = kParity * kHalves;
     constexpr int kThreads = 128 + 128 * kGroups + (kRefine ? 128 : 0);
+    constexpr bool kKey32 = !kNorm && kParity == 1;                 // 32-bit keys with global chunk numbers (see the epilogue)
+    constexpr int kGchBits = 11;
+    constexpr uint32_t kGchMask = (1u << kGchBits) - 1;
     static_assert(!kRefine || (!kNorm && kGroups == 2), "refine warps: norm-less variant with 8 epilogue warps (512 threads x 128 registers)");
     static_assert(!kRefine || kQCap * static_cast<int>(sizeof(QRec)) + 64 <= C::kBStages * C::kEBytes, "queue fits the unused digit-tile area");
     constexpr int kLoadsPerVisit = BN / 32 / kHalves;               // 32-column tcgen05.ld one warp issues per tile
@@ -230,7 +254,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         // ================================================================ TMA producer
         uint32_t tile_iter = 0, unit_iter = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
@@ -263,7 +287,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t tile0 = 0, unit_iter = 0;                          // tile0: running tile number at the start of the unit
         const uint64_t aext = umma_desc_sw32(base + offAExt);
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
@@ -317,10 +341,27 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
         uint32_t tile_iter = 0;
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit);
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units);
             int32_t m1 = -1, m2 = -1, m3 = -1, m4 = -1, m5 = -1;        // m5: fifth-best chunk key (kNorm = false only)
+            // kKey32 (norm-less variant, every group sees every tile): the running keys carry the GLOBAL chunk number,
+            //     key = a.b << 11 | (2047 - chunk),   a.b < 2^21 (|b|^2 <= kExtMaxNorm2), chunk < 2048,
+            // so the groups' top-5 lists merge at unit end with 32-bit min / max only (the 64-bit merge of the other variants costs
+            // ~6 % of the epilogue's instructions); 0 = no chunk
+            uint32_t n1 = 0, n2 = 0, n3 = 0, n4 = 0, n5 = 0;
+            uint32_t gbase = kGchMask - static_cast<uint32_t>(half * kChunksPerVisit);      // - (BN / kCC) per tile
             const int t_first = kParity == 2 ? static_cast<int>((parity - tile_iter) & 1u) : 0;   // first tile of this unit we own
             int seq = 0;
+            // what the ratio bound at unit end needs from global memory is requested NOW (group 0 owns the unit end): |a|^2 of the
+            // row and this lane's share of the train image's |b|^2 block ranges; the loads complete under the tile loop
+            int na_pre = 0, mn_pre = INT_MAX, mx_pre = 0;
+            if (group == 0) {
+                const int prow = u.rb * BM + row_in_unit;
+                if (prow < u.pd.nq) na_pre = __ldg(fz.norm2 + u.pd.q_row0 + prow);
+                if (!kNorm) {
+                    const int b0 = u.pd.t_row0 / kRowAlign, nblk = (u.pd.nt + kRowAlign - 1) / kRowAlign;
+                    for (int b = lane; b < nblk; b += 32) { mn_pre = min(mn_pre, __ldg(fz.blk_min + b0 + b)); mx_pre = max(mx_pre, __ldg(fz.blk_max + b0 + b)); }
+                }
+            }
             for (int t = 0; t < u.n_tiles; ++t, ++tile_iter) {
                 if (kParity == 2 && (tile_iter & 1) != static_cast<uint32_t>(parity)) continue;
                 const int acc = tile_iter % kAccStages;
@@ -363,14 +404,17 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     if (kCC == 64) cmax = max(cmax, cm_even);
                     const int cs = seq + (kCC == 64 ? c / 2 : c);
                     if (kNorm) top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - cs), m1, m2, m3, m4);
+                    else if (kKey32) top5_maxu(static_cast<uint32_t>(cmax) * (1u << kGchBits) + (gbase - static_cast<uint32_t>(kCC == 64 ? c / 2 : c)), n1, n2, n3, n4, n5);
                     else top5_max(cmax * (1 << kSeqBits) + (511 - cs), m1, m2, m3, m4, m5);   // 0 <= a.b < 2^22
                 }
                 seq += kChunksPerVisit;
+                gbase -= BN / kCC;
             }
             // ---- unit end: to (D + bias, -global chunk) 64-bit keys, merge the groups, write the candidates
             constexpr int kKeys = kNorm ? 4 : 5;                    // the fifth key only carries a value
             int64_t r[5];
-            {
+            uint32_t r32[5] = {n1, n2, n3, n4, n5};
+            if (!kKey32) {
                 const int32_t mk[5] = {m1, m2, m3, m4, m5};
 #pragma unroll
                 for (int i = 0; i < kKeys; ++i) {
@@ -380,15 +424,20 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     r[i] = static_cast<int64_t>(mk[i] >> kSeqBits) * (1ll << 32) + (0x7FFFFFFF - gch);
                 }
             }
+            uint32_t* merge32 = reinterpret_cast<uint32_t*>(merge);           // kKey32: [groups - 1][5][128] (conflict-free columns)
             if (group != 0) {
 #pragma unroll
-                for (int i = 0; i < kKeys; ++i) merge[((group - 1) * BM + row_in_unit) * 5 + i] = r[i];
+                for (int i = 0; i < kKeys; ++i) {
+                    if (kKey32) merge32[((group - 1) * 5 + i) * BM + row_in_unit] = r32[i];
+                    else merge[((group - 1) * BM + row_in_unit) * 5 + i] = r[i];
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(128 * kGroups) : "memory");
             if (group == 0) {
                 for (int g = 0; g < kGroups - 1; ++g)
 #pragma unroll
                     for (int i = 0; i < kKeys; ++i) {
+                        if (kKey32) { top5_maxu(merge32[(g * 5 + i) * BM + row_in_unit], r32[0], r32[1], r32[2], r32[3], r32[4]); continue; }
                         const int64_t k = merge[(g * BM + row_in_unit) * 5 + i];
                         if (kNorm) top4_max64(k, r[0], r[1], r[2], r[3]);
                         else top5_max64(k, r[0], r[1], r[2], r[3], r[4]);
@@ -406,6 +455,12 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 bool has[5];
 #pragma unroll
                 for (int i = 0; i < kKeys; ++i) {
+                    if (kKey32) {
+                        vv[i] = static_cast<int32_t>(r32[i] >> kGchBits);
+                        ch[i] = static_cast<int32_t>(kGchMask - (r32[i] & kGchMask));
+                        has[i] = vv[i] > 0;
+                        continue;
+                    }
                     vv[i] = static_cast<int32_t>(r[i] >> 32);
                     ch[i] = 0x7FFFFFFF - static_cast<int32_t>(r[i] & 0xFFFFFFFF);
                     // value part 0: kNorm: D == -bias, a chunk of padding rows only; norm-less: a.b == 0, padding rows or
@@ -414,9 +469,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 }
                 int nbmin = 0, nbmax = 0;
                 if (!kNorm) {
-                    const int b0 = u.pd.t_row0 / kRowAlign, nblk = (u.pd.nt + kRowAlign - 1) / kRowAlign;
-                    int mn = INT_MAX, mx = 0;
-                    for (int b = lane; b < nblk; b += 32) { mn = min(mn, __ldg(fz.blk_min + b0 + b)); mx = max(mx, __ldg(fz.blk_max + b0 + b)); }
+                    int mn = mn_pre, mx = mx_pre;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
                     nbmin = mn; nbmax = mx;
@@ -425,7 +478,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 Top2 o;
                 o.i0 = -1; o.i1 = -1; o.d0 = 0.f; o.d1 = 0.f;
                 if (in_range) {
-                    const int na = __ldg(fz.norm2 + u.pd.q_row0 + row);
+                    const int na = na_pre;
                     if (kNorm) {
                         o.i0 = has[0] ? ch[0] : -1;                                          // chunk of the best D
                         o.i1 = has[1] ? ch[1] : -1;                                          // second chunk
@@ -481,7 +534,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                         if (need) {
                             const uint32_t ticket = ticket0 + rank;
                             QRec* q = ring + (ticket % kQCap);
-                            q->t = o; q->srow = srow; q->v5 = has[4] ? vv[4] : 0; q->na = __ldg(fz.norm2 + u.pd.q_row0 + row);
+                            q->t = o; q->srow = srow; q->v5 = has[4] ? vv[4] : 0; q->na = na_pre;
                             q->qrow = u.pd.q_row0 + row; q->tr0 = u.pd.t_row0; q->ntr = u.pd.nt; q->nbmin = nbmin; q->nbmax = nbmax;
                             __threadfence_block();
                             *reinterpret_cast<volatile uint32_t*>(&q->seq) = ticket + 1;
@@ -520,14 +573,18 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (lane == 0) ticket = atomicAdd(&qctl->claimed, 1u);
                 ticket = __shfl_sync(0xffffffffu, ticket, 0);
                 QRec* q = ring + (ticket % kQCap);
-                bool have = false;
-                for (;;) {
-                    if (*reinterpret_cast<volatile uint32_t*>(&q->seq) == ticket + 1) { have = true; break; }
-                    if (*reinterpret_cast<volatile uint32_t*>(&qctl->producers_done) == 4u &&
-                        ticket >= *reinterpret_cast<volatile uint32_t*>(&qctl->reserved)) break;
-                    __nanosleep(200);
+                int have = 0;
+                if (lane == 0) {
+                    // one lane polls, with a long back-off: the queue is 256 records deep and a survivor is in no hurry, while
+                    // every poll is shared-memory traffic and issue slots taken from the ALU-bound epilogue warps
+                    for (;;) {
+                        if (*reinterpret_cast<volatile uint32_t*>(&q->seq) == ticket + 1) { have = 1; break; }
+                        if (*reinterpret_cast<volatile uint32_t*>(&qctl->producers_done) == 4u &&
+                            ticket >= *reinterpret_cast<volatile uint32_t*>(&qctl->reserved)) break;
+                        __nanosleep(2000);
+                    }
                 }
-                have = __shfl_sync(0xffffffffu, have ? 1 : 0, 0) != 0;       // one decision per warp
+                have = __shfl_sync(0xffffffffu, have, 0);                     // one decision per warp
                 if (!have) break;
                 __threadfence_block();
                 const Top2 t = q->t;

@@ -541,6 +541,11 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
         c->stat_launches++;
         TcvFuse fz{};
         if (sparse) {
+            // all pairs of the batch with the same number of 128-row units (equal-size images): the kernels divide instead of searching
+            const int64_t u0 = h_unit[base + 1] - h_unit[base];
+            bool uniform = u0 > 0 && u0 < (int64_t(1) << 30);
+            for (int k = 1; k < np && uniform; ++k) uniform = h_unit[base + k + 1] - h_unit[base + k] == u0;
+            fz.uniform_units = uniform ? static_cast<int>(u0) : 0;
             CU_TRY(c, cudaMemsetAsync(S.counters.p, 0, 32, s));                            // brute-force queue, need list, done list lengths
             CU_TRY(c, cudaMemsetAsync(S.keep.p, 0, static_cast<size_t>(B.staged_rows) / 8, s));
             fz.norm2 = b.d_norm2.as<int32_t>(); fz.blk_min = b.d_blkmin.as<int32_t>(); fz.blk_max = b.d_blkmax.as<int32_t>();
