@@ -201,7 +201,9 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     static_assert(!kRefine || kQCap * static_cast<int>(sizeof(QRec)) + 64 <= C::kBStages * C::kEBytes, "queue fits the unused digit-tile area");
     constexpr int kLoadsPerVisit = BN / 32 / kHalves;               // 32-column tcgen05.ld one warp issues per tile
     constexpr int kChunksPerVisit = BN / kCC / kHalves;             // chunks one warp reads per tile
-    static_assert(kCC == 32 || kCC == 64, "chunk = one or two 32-column loads");
+    static_assert(kCC == 32 || kCC == 64 || kCC == 128, "chunk = one, two or four 32-column loads");
+    static_assert(kCC != 128 || (!kNorm && kParity == 1), "128-row chunks: norm-less variant with global chunk keys only");
+    constexpr int kLoadsPerChunk = kCC / 32;
     static_assert(kChunksPerVisit >= 1, "a warp reads at least one whole chunk per tile");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -400,11 +402,13 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     const int32_t b0 = __vimax3_s32(a[0], a[1], a[2]), b1 = __vimax3_s32(a[3], a[4], a[5]);
                     const int32_t b2 = __vimax3_s32(a[6], a[7], a[8]), b3 = max(a[9], a[10]);
                     int32_t cmax = max(__vimax3_s32(b0, b1, b2), b3);
-                    if (kCC == 64 && (c & 1) == 0) { cm_even = cmax; continue; }       // first half of a 64-column chunk
-                    if (kCC == 64) cmax = max(cmax, cm_even);
-                    const int cs = seq + (kCC == 64 ? c / 2 : c);
+                    if (kLoadsPerChunk > 1) {                                          // a chunk spans several 32-column loads
+                        if (c % kLoadsPerChunk != 0) cmax = max(cmax, cm_even);
+                        if (c % kLoadsPerChunk != kLoadsPerChunk - 1) { cm_even = cmax; continue; }
+                    }
+                    const int cs = seq + c / kLoadsPerChunk;
                     if (kNorm) top4_max(cmax * (1 << kSeqBits) + (kValueBias * (1 << kSeqBits) + 511 - cs), m1, m2, m3, m4);
-                    else if (kKey32) top5_maxu(static_cast<uint32_t>(cmax) * (1u << kGchBits) + (gbase - static_cast<uint32_t>(kCC == 64 ? c / 2 : c)), n1, n2, n3, n4, n5);
+                    else if (kKey32) top5_maxu(static_cast<uint32_t>(cmax) * (1u << kGchBits) + (gbase - static_cast<uint32_t>(c / kLoadsPerChunk)), n1, n2, n3, n4, n5);
                     else top5_max(cmax * (1 << kSeqBits) + (511 - cs), m1, m2, m3, m4, m5);   // 0 <= a.b < 2^22
                 }
                 seq += kChunksPerVisit;
@@ -633,6 +637,7 @@ cudaError_t launch_knn2_l2_u8_tcv(const void* tmap_a_host, const void* tmap_b_ho
     const int grid = static_cast<int>(n_units < sm_count ? n_units : sm_count);
     if (fz.refine && aux && layout == 12 && tile_rows == 256) {
         // norm-less variant with in-kernel re-rank: 8 epilogue warps + 4 refine warps
+        if (chunk_rows == 128) return launch_tcv<1, 2, 256, false, 128, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s);
         if (chunk_rows == 64) return launch_tcv<1, 2, 256, false, 64, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s);
         return launch_tcv<1, 2, 256, false, 32, true>(*ta, *tb, *te, pairs, unit_prefix, n_pairs, n_units, out, aux, grid, issuers, fz, s);
     }

@@ -362,11 +362,16 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
                 c->tune_pending = false;
             }
             c->tcv_chunk_run = c->tcv_chunk ? c->tcv_chunk : (c->dense_matches ? 32 : 64);
+            if (c->tcv_chunk_run == 128) c->tcv_chunk_run = 64;     // 128-row chunks exist for the in-kernel re-rank variant only (set below)
             // norms within 1/2 of each other (cv::SIFT: ~1 %, the SURVEY 8d recipe: 20-36 %): the norm-less variant, one K-step
             // less per tile; its bounds lose their grip when norms vary a lot, the exactness does not depend on the choice
             if (c->tcv_normless == 2 || (c->tcv_normless == 1 && !c->dense_matches &&
                                          static_cast<int64_t>(b.nb_max - b.nb_min) * c->tcv_spread_div <= b.nb_max))
                 eng = Engine::TCN;
+            // sparse lists with the in-kernel re-rank: 128-row chunks (half the per-chunk bookkeeping of the epilogue, twice the rows per
+            // re-ranked chunk: +1.7 % on C3, profiles/r2_epilogue_experiments.txt)
+            if (eng == Engine::TCN && (c->tcv_chunk == 128 || c->tcv_chunk == 0) && c->tcv_layout_run == 12 && c->tcv_inkernel_refine)
+                c->tcv_chunk_run = 128;
         }
     }
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -945,7 +950,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     if (const char* env = std::getenv("SFM_MIN_BATCHES")) { const int t = std::atoi(env); if (t >= 1 && t <= 64) c->min_batches = t; }
     if (const char* env = std::getenv("SFM_TCV_SPREAD_DIV")) { const int t = std::atoi(env); if (t >= 1) c->tcv_spread_div = t; }
     if (const char* env = std::getenv("SFM_TCV_NORMLESS")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_normless = t; }
-    if (const char* env = std::getenv("SFM_TCV_CHUNK")) { const int t = std::atoi(env); if (t == 32 || t == 64) c->tcv_chunk = t; }
+    if (const char* env = std::getenv("SFM_TCV_CHUNK")) { const int t = std::atoi(env); if (t == 32 || t == 64 || t == 128) c->tcv_chunk = t; }
     if (const char* env = std::getenv("SFM_TCV_ISSUERS")) { const int t = std::atoi(env); if (t == 1 || t == 2) c->tcv_issuers = t; }
     if (const char* env = std::getenv("SFM_TCV_LAYOUT")) { const int g = std::atoi(env); if (g == 12 || g == 14 || g == 21 || g == 22) c->tcv_layout = g; }
     *out = c;
