@@ -365,12 +365,15 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             if (c->tcv_chunk_run == 128) c->tcv_chunk_run = 64;     // 128-row chunks exist for the in-kernel re-rank variant only (set below)
             // norms within 1/2 of each other (cv::SIFT: ~1 %, the SURVEY 8d recipe: 20-36 %): the norm-less variant, one K-step
             // less per tile; its bounds lose their grip when norms vary a lot, the exactness does not depend on the choice
-            if (c->tcv_normless == 2 || (c->tcv_normless == 1 && !c->dense_matches &&
+            // (round 2: also for dense lists — with the re-rank inside the kernel the norm-less variant with 32-row chunks beats
+            // the norm K-step there too: C4 538 k vs 488 k pairs/s, profiles/r2_epilogue_experiments.txt)
+            if (c->tcv_normless == 2 || (c->tcv_normless == 1 &&
                                          static_cast<int64_t>(b.nb_max - b.nb_min) * c->tcv_spread_div <= b.nb_max))
                 eng = Engine::TCN;
             // sparse lists with the in-kernel re-rank: 128-row chunks (half the per-chunk bookkeeping of the epilogue, twice the rows per
             // re-ranked chunk: +1.7 % on C3, profiles/r2_epilogue_experiments.txt)
-            if (eng == Engine::TCN && (c->tcv_chunk == 128 || c->tcv_chunk == 0) && c->tcv_layout_run == 12 && c->tcv_inkernel_refine)
+            if (eng == Engine::TCN && (c->tcv_chunk == 128 || (c->tcv_chunk == 0 && !c->dense_matches)) && c->tcv_layout_run == 12 &&
+                c->tcv_inkernel_refine)
                 c->tcv_chunk_run = 128;
         }
     }
