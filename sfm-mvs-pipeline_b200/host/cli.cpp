@@ -120,7 +120,20 @@ static int runFromImages(const Args& args, const std::vector<std::string>& paths
     std::vector<std::string> warnings;
     const bool orb = det == "ORB";                    // PhotogrammetrieCli.cpp:344-356: ORB, else SIFT (+ warning for anything else)
     if (!orb && det != "SIFT" && !det.empty()) warnings.push_back("Unbekannter Merkmalsalgorithmus: " + det + ". Benutze SIFT.");
-    auto matcher = configureFeatureMatcher(orb ? "ORB" : "SIFT", args.get("feature-matcher"), std::stoi(args.get("device", "0")), &warnings);
+    std::vector<int> devices;                        // -Pdevices=0,1,...: extraction and matching split over the GPUs of this process
+    {
+        const std::string dl = args.get("devices");
+        size_t pos = 0;
+        while (pos < dl.size()) {
+            const size_t comma = dl.find(',', pos);
+            const std::string tok = dl.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+            if (!tok.empty()) devices.push_back(std::stoi(tok));
+            if (comma == std::string::npos) break;
+            pos = comma + 1;
+        }
+        if (devices.empty()) devices.push_back(std::stoi(args.get("device", "0")));
+    }
+    auto matcher = configureFeatureMatcher(orb ? "ORB" : "SIFT", args.get("feature-matcher"), devices, &warnings);
     auto strategy = configureFeatureMatcherStrategy(std::stoi(args.get("feature-sequence", "0")),
                                                     std::stoi(args.get("feature-gridlength", "0")), &warnings);
     for (auto& w : warnings) std::fprintf(stderr, "[WARN] %s\n", w.c_str());

@@ -121,11 +121,15 @@ void IFeatureMatchingStrategy::calculateShotMatches(const Scene& scene, std::sha
                                                       depth, flat.data(), static_cast<int64_t>(pl.size()), &o, &res);
         if (rc != SFM_OK) throw MatcherError(rc, sfm_mgpu_last_error(group));
     } else if (scene.bankResident) {
-        // the feature extractor left descriptors + keypoints of these shots on the device: nothing to upload
+        // the feature extractor left descriptors + keypoints of these shots on the device(s): nothing to upload
         int n_bank = 0;
         check(ctx, sfm_bank_info(ctx, &n_bank, nullptr, nullptr));
         if (n_bank != static_cast<int>(shots.size())) throw MatcherError(SFM_ERR_STATE, "resident bank does not belong to this scene");
-        check(ctx, sfm_match_pairs(ctx, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
+        if (group) {
+            const int rc = sfm_mgpu_match_pairs(group, flat.data(), static_cast<int64_t>(pl.size()), &o, &res);
+            if (rc != SFM_OK) throw MatcherError(rc, sfm_mgpu_last_error(group));
+        } else
+            check(ctx, sfm_match_pairs(ctx, flat.data(), static_cast<int64_t>(pl.size()), &o, &res));
     } else {
         // one call for the whole scene: bank upload (pipelined with the matching when the Mats are page-locked) + all pairs
         check(ctx, sfm_match_pairs_from_host(ctx, static_cast<int>(shots.size()), rows.data(), nrows.data(), cols, steps.data(),
@@ -214,18 +218,31 @@ GpuSiftFeatureDetector::GpuSiftFeatureDetector(const std::shared_ptr<GpuDescript
 
 // the loop of SfM::extractFeatures (SfM.cpp:577-597) around one detector; `extractOne` runs detect + compute of image i on the device
 template <class ExtractOne>
-static void extractAll(sfm_ctx* ctx, const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features, int descBytes,
-                       ExtractOne extractOne) {
+static void extractAll(const GpuDescriptorMatcher& matcher, const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features,
+                       int descBytes, int detector, const void* opts, ExtractOne extractOne) {
+    sfm_ctx* ctx = matcher.context();
     if (scene.shots.empty())
         for (std::size_t i = 0; i < images.size(); ++i) scene.shots.push_back(std::make_shared<Shot>());
     if (scene.shots.size() != images.size()) throw std::invalid_argument("extractFeatures: one image per shot");
     scene.bankResident = false;
     features.assign(images.size(), Features{});
-    check(ctx, sfm_features_clear(ctx));
+    std::vector<int32_t> counts(images.size(), 0);
+    sfm_mgpu* group = matcher.group();
+    if (group) {
+        // several GPUs: image i on device i % n, feature sets exchanged over NCCL, every device adopts the scene as its bank
+        std::vector<const uint8_t*> gray(images.size());
+        std::vector<int32_t> rows(images.size()), cols(images.size());
+        std::vector<std::size_t> steps(images.size());
+        for (std::size_t i = 0; i < images.size(); ++i) { gray[i] = images[i].data; rows[i] = images[i].rows; cols[i] = images[i].cols; steps[i] = images[i].step; }
+        const int rc = sfm_mgpu_extract_features(group, detector, static_cast<int>(images.size()), gray.data(), rows.data(), cols.data(),
+                                                 steps.data(), opts, counts.data());
+        if (rc != SFM_OK) throw MatcherError(rc, sfm_mgpu_last_error(group));
+    } else
+        check(ctx, sfm_features_clear(ctx));
     for (std::size_t i = 0; i < images.size(); ++i) {
         const GrayImage& im = images[i];
-        int32_t n = 0;
-        check(ctx, extractOne(im, &n));
+        int32_t n = counts[i];
+        if (!group) check(ctx, extractOne(im, &n));
         Features& f = features[i];
         f.descriptorBytes = descBytes;
         f.keypoints.resize(static_cast<std::size_t>(n));
@@ -238,13 +255,13 @@ static void extractAll(sfm_ctx* ctx, const std::vector<GrayImage>& images, Scene
         s.imageWidth = im.cols;
         s.imageHeight = im.rows;
     }
-    check(ctx, sfm_bank_from_features(ctx));
+    if (!group) check(ctx, sfm_bank_from_features(ctx));
     scene.bankResident = true;
 }
 
 void GpuSiftFeatureDetector::extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features) {
     sfm_ctx* ctx = matcher_->context();
-    extractAll(ctx, images, scene, features, 128, [&](const GrayImage& im, int32_t* n) {
+    extractAll(*matcher_, images, scene, features, 128, SFM_DETECTOR_SIFT, &opts_, [&](const GrayImage& im, int32_t* n) {
         return sfm_features_extract_sift(ctx, im.data, im.rows, im.cols, im.step, &opts_, n);
     });
 }
@@ -257,7 +274,7 @@ GpuOrbFeatureDetector::GpuOrbFeatureDetector(const std::shared_ptr<GpuDescriptor
 
 void GpuOrbFeatureDetector::extractFeatures(const std::vector<GrayImage>& images, Scene& scene, std::vector<Features>& features) {
     sfm_ctx* ctx = matcher_->context();
-    extractAll(ctx, images, scene, features, 32, [&](const GrayImage& im, int32_t* n) {
+    extractAll(*matcher_, images, scene, features, 32, SFM_DETECTOR_ORB, &opts_, [&](const GrayImage& im, int32_t* n) {
         return sfm_features_extract_orb(ctx, im.data, im.rows, im.cols, im.step, &opts_, n);
     });
 }

@@ -141,3 +141,33 @@ def test_extraction_split_over_gpus_equals_one_gpu(detector):
     assert np.array_equal(res.offsets, full.offsets) and res.matches.tobytes() == full.matches.tobytes() and int(full.offsets[-1]) > 100
     g.close()
     one.close()
+
+
+def test_cli_images_over_two_devices(tmp_path):
+    """sfm_match_cli -Pimage=... -Pdevices=0,1: extractFeatures, calculateShotMatches and calculateHomography with the scene split over the
+    GPUs of one process print exactly what the single-device run prints."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    import workloads
+    cli = os.path.join(ROOT, "sfm-mvs-pipeline_b200", "sfm_match_cli")
+    base = workloads.synthetic_photo(11, 200, 280)
+    imgs = [base, np.roll(base, (3, 5), axis=(0, 1)), np.roll(base, (-2, 4), axis=(0, 1)), workloads.synthetic_photo(12, 160, 240)]
+    paths = []
+    for i, im in enumerate(imgs):
+        paths.append(str(tmp_path / f"shot{i}.pgm"))
+        with open(paths[-1], "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (im.shape[1], im.shape[0]) + np.ascontiguousarray(im, np.uint8).tobytes())
+    outs = []
+    for det in ("SIFT", "ORB"):
+        for dev in ("-Pdevice=0", "-Pdevices=0,1"):
+            r = subprocess.run([cli, *[f"-Pimage={p}" for p in paths], f"-Pfeature-detector={det}", "-Pfeature-limit=2000", "-Pmatch-threshold=4",
+                                "-Pransac-matching-threshold=-3", dev], capture_output=True, text=True, timeout=300)
+            assert "[ERROR]" not in r.stderr and "pairs=6" in r.stdout, r.stdout + r.stderr
+            lines = [ln for ln in r.stdout.splitlines() if "seconds" not in ln]
+            lines.append(r.stdout.split("keypoints=")[1].split()[0])
+            outs.append(lines)
+        assert outs[-2] == outs[-1], (det, outs[-2], outs[-1])
+        assert any("homographyInlierRatio" in ln for ln in outs[-1])
