@@ -203,6 +203,8 @@ struct sfm_ctx {
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
     bool tcv_inkernel_refine = true; // SFM_TCV_INKERNEL_REFINE = 0: survivors of the fused ratio bound go to the post pass instead of
                                      // the knn CTA's own refine warps
+    int knn_grid_limit = 0;          // > 0: the persistent knn kernels launch at most this many CTAs (dist from-host path: SMs left
+                                     // free for the NCCL broadcasts of the chunks still in flight)
     int min_batches = 6;             // a long pair list is cut into at least this many batches (SFM_MIN_BATCHES): post kernels of
                                      // batch i overlap the knn kernel of batch i + 1
     void* dist = nullptr;            // multi-GPU group membership (sfmhost::DistState, csrc/dist.cu)
@@ -228,6 +230,7 @@ struct Schedule {
     const int64_t* order = nullptr;
     const int* avail = nullptr;
     const cudaEvent_t* events = nullptr;
+    int n_groups = 0;                 // > 0: number of availability groups (batches of the earlier ones may leave SMs free)
 };
 int make_tmaps(sfm_ctx* c, Bank& b);
 int bank_layout(sfm_ctx* c, Bank& b, int n_images, const int32_t* n_rows, int cols, int depth);

@@ -140,6 +140,7 @@ struct DistState {
     PinBuf h_tot_all;
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int chunks = 4;
+    int spare_sms = 0;             // SFM_DIST_SPARE_SMS: SMs the knn kernels leave to NCCL while chunks are still in flight
 };
 
 void dist_state_destroy(sfm_ctx* c) {
@@ -163,6 +164,7 @@ static int init_state(sfm_ctx* c, ncclComm_t comm, int rank, int world, bool own
     DistState* d = new DistState();
     d->comm = comm; d->rank = rank; d->world = world; d->owns_comm = owns;
     if (const char* env = std::getenv("SFM_DIST_CHUNKS")) { const int t = std::atoi(env); if (t >= 1 && t <= 16) d->chunks = t; }
+    if (const char* env = std::getenv("SFM_DIST_SPARE_SMS")) { const int t = std::atoi(env); if (t >= 0 && t <= 64) d->spare_sms = t; }
     c->dist = d;
     cudaError_t e = d->d_tot_all.ensure(static_cast<size_t>(world) * 16);
     if (e == cudaSuccess) e = d->h_tot_all.ensure(static_cast<size_t>(world) * 16);
@@ -534,6 +536,8 @@ static int dist_from_host_body(sfm_ctx* c, DistState* d, int n_images, const voi
     for (int64_t k = 0; k < n_mine; ++k) avail[k] = avail_in[order[k]];
     Schedule sc;
     sc.order = order.data(); sc.avail = avail.data(); sc.events = c->group_ev.data();
+    sc.n_groups = G;
+    c->knn_grid_limit = d->spare_sms > 0 ? std::max(1, c->sm_count - d->spare_sms) : 0;
     if (n_mine > 0) rc = enqueue_impl(c, d->my_pairs.data(), n_mine, o, &sc);
     else {
         CU_TRY(c, cudaStreamWaitEvent(s, c->group_ev[G - 1], 0));

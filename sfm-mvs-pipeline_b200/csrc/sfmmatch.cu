@@ -282,10 +282,11 @@ int pick_engine(sfm_ctx* c, const Bank& b, int norm, int requested, Engine* out)
 }
 
 int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, const int64_t* d_unit_prefix, int n_pairs,
-               int64_t n_units, Top2* out, float* aux = nullptr, const TcvFuse* fz = nullptr) {
+               int64_t n_units, Top2* out, float* aux = nullptr, const TcvFuse* fz = nullptr, int grid_limit = 0) {
     cudaStream_t s = c->stream;
     c->stat_launches++;
     const TcvFuse none{};
+    const int sms = grid_limit > 0 ? std::min(grid_limit, c->sm_count) : c->sm_count;
     switch (eng) {
         case Engine::TC:
             CU_TRY(c, launch_knn2_l2_u8_tc(&b.tmap_a, &b.tmap_b, b.d_ckey.as<int32_t>(), b.d_norm2.as<int32_t>(), d_pairs,
@@ -293,11 +294,11 @@ int launch_knn(sfm_ctx* c, const Bank& b, Engine eng, const PairDesc* d_pairs, c
             break;
         case Engine::TCV:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            nullptr, c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk_run, fz ? *fz : none, s));
+                                            nullptr, sms, c->tcv_layout_run, 256, c->tcv_issuers, c->tcv_chunk_run, fz ? *fz : none, s));
             break;
         case Engine::TCN:
             CU_TRY(c, launch_knn2_l2_u8_tcv(&b.tmap_a, &b.tmap_b, &b.tmap_e, d_pairs, d_unit_prefix, n_pairs, n_units, out,
-                                            reinterpret_cast<int32_t*>(aux), c->sm_count, c->tcv_layout_run, 256, c->tcv_issuers,
+                                            reinterpret_cast<int32_t*>(aux), sms, c->tcv_layout_run, 256, c->tcv_issuers,
                                             c->tcv_chunk_run, fz ? *fz : none, s));
             break;
         case Engine::TF32:
@@ -565,7 +566,10 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             fz.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
         }
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->prof_ev[3 * bi], s));
-        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, S.top2.as<Top2>(), S.aux.as<float>(), &fz);
+        // batches that run while later chunks of the bank are still being exchanged leave SMs to the NCCL kernels (dist from-host path)
+        const bool chunks_pending = sched && sched->avail && sched->n_groups > 0 && sched->avail[B.p0] + 1 < sched->n_groups;
+        rc = launch_knn(c, b, eng, d_ppd + B.p0, d_unit + base, np, B.n_units, S.top2.as<Top2>(), S.aux.as<float>(), &fz,
+                        chunks_pending ? c->knn_grid_limit : 0);
         if (rc != SFM_OK) return rc;
         if (need_rev) {
             rc = launch_knn(c, b, eng, d_rpd + B.p0, d_runit + base, np, B.n_rev_units, S.rev.as<Top2>(), S.aux_rev.as<float>());

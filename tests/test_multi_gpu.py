@@ -166,7 +166,7 @@ def test_cli_images_over_two_devices(tmp_path):
             r = subprocess.run([cli, *[f"-Pimage={p}" for p in paths], f"-Pfeature-detector={det}", "-Pfeature-limit=2000", "-Pmatch-threshold=4",
                                 "-Pransac-matching-threshold=-3", dev], capture_output=True, text=True, timeout=300)
             assert "[ERROR]" not in r.stderr and "pairs=6" in r.stdout, r.stdout + r.stderr
-            lines = [ln for ln in r.stdout.splitlines() if "seconds" not in ln]
+            lines = [ln for ln in r.stdout.splitlines() if "seconds" not in ln and not ln.startswith("NCCL version")]
             lines.append(r.stdout.split("keypoints=")[1].split()[0])
             outs.append(lines)
         assert outs[-2] == outs[-1], (det, outs[-2], outs[-1])
