@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--single-process", action="store_true",
                     help="N GPUs from ONE process (sfm_mgpu_*: one worker thread per GPU) instead of one process per GPU")
     ap.add_argument("--photo", default="1200x1600", help="extract workload: image size HEIGHTxWIDTH")
+    ap.add_argument("--detector", default="SIFT", choices=["SIFT", "ORB"],
+                    help="extract workload: cv::SIFT::create(10000, 3, 0.09) (default) or cv::ORB::create(30000) (run-orb-sequence.sh)")
     return ap.parse_args()
 
 
@@ -592,6 +594,7 @@ def run_knnmatch(a):
 # Secondary line for the widened row SURVEY 8f rank 3 (SfM::extractFeatures, SfM.cpp:577-597; detector
 # PhotogrammetrieCli.cpp:342-357).  NOT the north-star metric: its own metric / unit, same JSON contract.
 EXTRACT_METRIC = "images/sec SIFT detect+compute (cv::SIFT(feature-limit 10000, 3, 0.09))"
+EXTRACT_METRIC_ORB = "images/sec ORB detect+compute (cv::ORB(feature-limit 30000))"
 
 
 def _extract_images(a):
@@ -602,13 +605,13 @@ def _extract_images(a):
     return imgs, f"{n} synthetic photographs {w}x{h} (workloads.synthetic_photo)"
 
 
-def _cv2_extract_rate(imgs, threads):
+def _cv2_extract_rate(imgs, threads, detector="SIFT"):
     import cv2
     from concurrent.futures import ThreadPoolExecutor
     cv2.setNumThreads(1)                       # one image per thread, like the reference's OpenMP loop (SfM.cpp:582)
 
     def one(img):
-        det = cv2.SIFT_create(10000, 3, 0.09)
+        det = cv2.ORB_create(30000) if detector == "ORB" else cv2.SIFT_create(10000, 3, 0.09)
         kp = det.detect(img, None)
         kp, d = det.compute(img, kp)
         return len(kp)
@@ -624,16 +627,16 @@ def run_extract_reference(a):
     imgs, name = _extract_images(a)
     threads = len(os.sched_getaffinity(0))
     for _ in range(a.warmup):
-        _cv2_extract_rate(imgs[:2], threads)
+        _cv2_extract_rate(imgs[:2], threads, a.detector)
     t0 = time.perf_counter()
-    rates = [_cv2_extract_rate(imgs, threads)[0] for _ in range(a.steps)]
+    rates = [_cv2_extract_rate(imgs, threads, a.detector)[0] for _ in range(a.steps)]
     dt = time.perf_counter() - t0
     v = len(imgs) * a.steps / dt
     import cv2
-    sample = f"each step = all {len(imgs)} images, cv2 {cv2.__version__} SIFT detect + compute, one image per thread"
-    _emit(json.dumps({"impl": "reference", "metric": EXTRACT_METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+    sample = f"each step = all {len(imgs)} images, cv2 {cv2.__version__} {a.detector} detect + compute, one image per thread"
+    _emit(json.dumps({"impl": "reference", "metric": EXTRACT_METRIC_ORB if a.detector == "ORB" else EXTRACT_METRIC, "value": v, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
                       "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": name, "sample": sample},
+                      "vs_baseline": None, "dtype": "u8" if a.detector == "ORB" else "f32", "data": "synthetic", "config": {"workload": name, "sample": sample},
                       "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "reference", "sample": sample},
                       "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "steps_images_per_s": [round(r, 2) for r in rates]}))
@@ -687,14 +690,17 @@ def run_extract_ours(a):
     imgs = [torch.from_numpy(i).pin_memory().numpy() for i in imgs]         # page-locked host images
     torch.cuda.set_device(0)
     stream = torch.cuda.ExternalStream(m.stream, device=torch.device("cuda", 0))
-    opts = dict(contrast_threshold=0.09, n_features=10000)
+    orb = a.detector == "ORB"
+    opts = dict(n_features=30000) if orb else dict(contrast_threshold=0.09, n_features=10000)
 
     def step(download):
         m.features_clear()
         prof = {"pyramid_ms": 0.0, "total_ms": 0.0, "pyramid_bytes": 0.0}
         n_kp = 0
         for im in imgs:
-            n_kp += m.extract_sift(im, **opts)
+            n_kp += m.extract_orb(im, **opts) if orb else m.extract_sift(im, **opts)
+            if orb:
+                continue
             p = m.features_last_profile()
             for k in prof:
                 prof[k] += p[k]
@@ -733,26 +739,26 @@ def run_extract_ours(a):
     pyr_ms = float(np.mean([p["pyramid_ms"] for p in profs]))
     tot_ms = float(np.mean([p["total_ms"] for p in profs]))
     pyr_bytes = float(np.mean([p["pyramid_bytes"] for p in profs]))
-    line = {"metric": EXTRACT_METRIC, "value": len(imgs) / (ms * 1e-3), "unit": "images/s", "n_gpus": 1, "steps": a.steps,
+    line = {"metric": EXTRACT_METRIC_ORB if orb else EXTRACT_METRIC, "value": len(imgs) / (ms * 1e-3), "unit": "images/s", "n_gpus": 1, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "u8" if orb else "f32", "data": "synthetic",
             "config": {"workload": name, "keypoints_per_step": int(n_kp), "l2_policy": "pyramid of one image (246 MB at 1600x1200) exceeds L2",
                        "value_includes": "H2D of each grey image (the ABI takes host images); device time on the library stream",
                        "note": "secondary line (SURVEY 8f rank 3), not the north-star metric"},
             "e2e": {"value": len(imgs) / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(sum(i.nbytes for i in imgs)),
                     "d2h_bytes_per_step": int(d2h), "includes": "features downloaded to the host + sfm_bank_from_features"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "Gaussian pyramid (upsample + blur + downsample launches of one step)",
+            "roofline": None if orb else {"bound": "hbm", "kernel": "Gaussian pyramid (upsample + blur + downsample launches of one step)",
                          "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else None, "peak": hbm, "peak_source": src,
                          "unit": "GB/s", "frac": (pyr_bytes / (pyr_ms * 1e-3) / 1e9 / hbm) if pyr_ms > 0 else None, "traffic": None,
                          "pyramid_ms_per_step": pyr_ms, "device_ms_per_step": tot_ms, "share_of_step": pyr_ms / tot_ms if tot_ms else None},
             "clocks": clocks}
     if not a.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
-        rate, counts = _cv2_extract_rate(imgs[:max(2, min(len(imgs), threads))], threads)
+        rate, counts = _cv2_extract_rate(imgs[:max(2, min(len(imgs), threads))], threads, a.detector)
         import cv2
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "reference",
-                                "sample": f"{max(2, min(len(imgs), threads))} images of the workload, cv2 {cv2.__version__} SIFT, one image per thread",
+                                "sample": f"{max(2, min(len(imgs), threads))} images of the workload, cv2 {cv2.__version__} {a.detector}, one image per thread",
                                 "keypoints_per_image": int(np.mean(counts))}
     _emit(json.dumps(line))
     m.close()
