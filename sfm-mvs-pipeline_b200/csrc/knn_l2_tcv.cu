@@ -53,25 +53,19 @@ struct Cfg {
     static constexpr int offAExt = offA + kAStages * kABytes;      // constant weight rows
     static constexpr int offMerge = offAExt + kAExtBytes;          // [3 groups][128][5] int64
     static constexpr int offBar = offMerge + 3 * BM * 5 * 8;
-    static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages;
+    static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages + 4;   // + unit hand-off to the finishing warps
     static constexpr int offTmemPtr = offBar + kNumBars * 8;
     static constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
     static constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
     static constexpr uint32_t kIdescExt = umma_idesc_u8s8(BM, BN);
 };
-// In-kernel re-rank (kRefine): rows that survive the fused ratio bound are handed to four refine warps of the same CTA
-// through a shared-memory ticket queue (multi-producer: the four warps of epilogue group 0; multi-consumer: the refine
-// warps).  The queue lives where the digit tiles of the kNorm variant would (the norm-less variant loads none).
-struct __align__(16) QRec {
-    Top2 t;                                    // candidate record (chunks, V1, V2)
-    int64_t srow;
-    int32_t v5, na, qrow, tr0, ntr, nbmin, nbmax;
-    uint32_t seq;                              // ticket + 1 once the record is complete
-};
-static_assert(sizeof(QRec) == 64, "queue record");
-struct QCtl { uint32_t reserved, claimed, freed, producers_done; };
-constexpr int kQCap = 256;                     // records; producers divert to the global need list above kQHigh outstanding
-constexpr int kQHigh = 96;                     // 96 + 4 producer warps x 32 rows + 4 claimed tickets < kQCap
+// In-kernel unit end and re-rank (kRefine): the epilogue warps only stream accumulators.  At the end of a unit each of them
+// leaves its five running keys per query row in shared memory (two buffers, alternating by unit) and goes on with the next
+// unit; the four FINISHING warps merge the two column halves, apply the fused ratio bound and re-rank the few surviving rows
+// exactly (refine_dot_row) while the epilogue is already in the next unit.  Measured before this split: ~2460 cycles per
+// unit with both epilogue groups parked at two bar.sync around the unit end of group 0 (C3: 32 tiles per unit -> 77 of
+// 620 cycles per tile; C5's 64-tile units ran 6.6 % faster per tile for that reason alone).
+constexpr int kFinBufWords = 2 * 5 * BM;       // [column half][key][row] uint32 per buffer
 }  // namespace tcv
 
 struct UnitInfoV { PairDesc pd; int rb; int n_tiles; };
@@ -210,7 +204,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr int kGchBits = 11;
     constexpr uint32_t kGchMask = (1u << kGchBits) - 1;
     static_assert(!kRefine || (!kNorm && kGroups == 2), "refine warps: norm-less variant with 8 epilogue warps (512 threads x 128 registers)");
-    static_assert(!kRefine || kQCap * static_cast<int>(sizeof(QRec)) + 64 <= C::kBStages * C::kEBytes, "queue fits the unused digit-tile area");
+    static_assert(2 * kFinBufWords * 4 <= 3 * BM * 5 * 8, "hand-off buffers fit the merge area");
     constexpr int kLoadsPerVisit = BN / 32 / kHalves;               // 32-column tcgen05.ld one warp issues per tile
     constexpr int kChunksPerVisit = BN / kCC / kHalves;             // chunks one warp reads per tile
     static_assert(kCC == 32 || kCC == 64 || kCC == 128, "chunk = one, two or four 32-column loads");
@@ -227,6 +221,8 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     auto a_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + kAStages + i); };
     auto acc_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + i); };
     auto acc_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + kAccStages + i); };
+    auto fin_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + 2 * kAccStages + i); };
+    auto fin_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + 2 * kAccStages + 2 + i); };
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + offTmemPtr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -240,6 +236,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), n_issuers); }   // every MMA warp releases A
         for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4 * kHalves); }   // one arrival per reading warp
+        for (int i = 0; i < 2; ++i) { mbar_init(fin_full(i), 4 * kGroups); mbar_init(fin_empty(i), 4); }   // per epilogue warp / per finishing warp
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -252,12 +249,6 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int word = i & 3;                                     // word inside a 16-byte half
         reinterpret_cast<uint32_t*>(base_ptr + offAExt)[i] = word < 3 ? 0xFFFFFFFFu : 0x01010101u;
     }
-    QRec* ring = reinterpret_cast<QRec*>(base_ptr + offE);
-    QCtl* qctl = reinterpret_cast<QCtl*>(base_ptr + offE + kQCap * sizeof(QRec));
-    if (kRefine) {
-        for (int i = threadIdx.x; i < kQCap; i += kThreads) ring[i].seq = 0;
-        if (threadIdx.x == 0) { qctl->reserved = 0; qctl->claimed = 0; qctl->freed = 0; qctl->producers_done = 0; }
-    }
     fence_proxy_async();                                            // generic-proxy writes -> visible to the MMA
     tc_fence_before();
     __syncthreads();
@@ -268,8 +259,11 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         // ================================================================ TMA producer
         uint32_t tile_iter = 0, unit_iter = 0;
         int p_hint = 0;
+        // the descriptor of the NEXT unit is requested at the start of the current one: its global loads finish under the tile loop
+        UnitInfoV nxt = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, blockIdx.x, fz.uniform_units, p_hint);
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units, p_hint);
+            const UnitInfoV u = nxt;
+            if (unit + gridDim.x < n_units) nxt = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit + gridDim.x, fz.uniform_units, p_hint);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_empty(as), ((unit_iter / kAStages) & 1) ^ 1);
@@ -302,8 +296,11 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         uint32_t tile0 = 0, unit_iter = 0;                          // tile0: running tile number at the start of the unit
         const uint64_t aext = umma_desc_sw32(base + offAExt);
         int p_hint = 0;
+        // the descriptor of the NEXT unit is requested at the start of the current one: its global loads finish under the tile loop
+        UnitInfoV nxt = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, blockIdx.x, fz.uniform_units, p_hint);
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units, p_hint);
+            const UnitInfoV u = nxt;
+            if (unit + gridDim.x < n_units) nxt = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit + gridDim.x, fz.uniform_units, p_hint);
             if (u.n_tiles == 0) continue;
             const int as = unit_iter % kAStages;
             mbar_wait(a_full(as), (unit_iter / kAStages) & 1);
@@ -355,10 +352,13 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         const int quarter = warp & 3;
         const int row_in_unit = quarter * 32 + lane;
         int64_t* merge = reinterpret_cast<int64_t*>(base_ptr + offMerge);
-        uint32_t tile_iter = 0;
+        uint32_t tile_iter = 0, unit_no = 0;
         int p_hint = 0;
+        // the descriptor of the NEXT unit is requested at the start of the current one: its global loads finish under the tile loop
+        UnitInfoV nxt = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, blockIdx.x, fz.uniform_units, p_hint);
         for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units, p_hint);
+            const UnitInfoV u = nxt;
+            if (unit + gridDim.x < n_units) nxt = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit + gridDim.x, fz.uniform_units, p_hint);
             int32_t m1 = -1, m2 = -1, m3 = -1, m4 = -1, m5 = -1;        // m5: fifth-best chunk key (kNorm = false only)
             // kKey32 (norm-less variant, every group sees every tile): the running keys carry the GLOBAL chunk number,
             //     key = a.b << 11 | (2047 - chunk),   a.b < 2^21 (|b|^2 <= kExtMaxNorm2), chunk < 2048,
@@ -371,7 +371,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             // what the ratio bound at unit end needs from global memory is requested NOW (group 0 owns the unit end): |a|^2 of the
             // row and this lane's share of the train image's |b|^2 block ranges; the loads complete under the tile loop
             int na_pre = 0, mn_pre = INT_MAX, mx_pre = 0;
-            if (group == 0) {
+            if (!kRefine && group == 0) {
                 const int prow = u.rb * BM + row_in_unit;
                 if (prow < u.pd.nq) na_pre = __ldg(fz.norm2 + u.pd.q_row0 + prow);
                 if (!kNorm) {
@@ -428,6 +428,17 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 }
                 seq += kChunksPerVisit;
                 gbase -= BN / kCC;
+            }
+            if constexpr (kRefine) {
+                // ---- unit end, handed over: five keys per row into the buffer of this unit's parity, one arrival per warp
+                const uint32_t fpar = unit_no & 1u;
+                mbar_wait(fin_empty(fpar), ((unit_no >> 1) & 1u) ^ 1u);
+                uint32_t* fin = reinterpret_cast<uint32_t*>(merge) + fpar * kFinBufWords + group * 5 * BM + row_in_unit;
+                fin[0 * BM] = n1; fin[1 * BM] = n2; fin[2 * BM] = n3; fin[3 * BM] = n4; fin[4 * BM] = n5;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fin_full(fpar));         // release: the finishing warps acquire on the barrier
+                ++unit_no;
+                continue;
             }
             // ---- unit end: to (D + bias, -global chunk) 64-bit keys, merge the groups, write the candidates
             constexpr int kKeys = kNorm ? 4 : 5;                    // the fifth key only carries a value
@@ -536,29 +547,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 if (bal) {
                     const int rank = __popc(bal & ((1u << lane) - 1));
                     const int64_t srow = u.pd.out_row0 + row;
-                    int to_ring = 0;
-                    uint32_t ticket0 = 0;
-                    if (kRefine && fz.refine) {
-                        // hand the rows to this CTA's refine warps unless they are behind (then: the post pass)
-                        if (lane == 0) {
-                            const uint32_t res = *reinterpret_cast<volatile uint32_t*>(&qctl->reserved);
-                            const uint32_t fre = *reinterpret_cast<volatile uint32_t*>(&qctl->freed);
-                            to_ring = (res - fre) <= static_cast<uint32_t>(kQHigh);
-                            if (to_ring) ticket0 = atomicAdd(&qctl->reserved, static_cast<uint32_t>(__popc(bal)));
-                        }
-                        to_ring = __shfl_sync(0xffffffffu, to_ring, 0);
-                        ticket0 = __shfl_sync(0xffffffffu, ticket0, 0);
-                    }
-                    if (to_ring) {
-                        if (need) {
-                            const uint32_t ticket = ticket0 + rank;
-                            QRec* q = ring + (ticket % kQCap);
-                            q->t = o; q->srow = srow; q->v5 = has[4] ? vv[4] : 0; q->na = na_pre;
-                            q->qrow = u.pd.q_row0 + row; q->tr0 = u.pd.t_row0; q->ntr = u.pd.nt; q->nbmin = nbmin; q->nbmax = nbmax;
-                            __threadfence_block();
-                            *reinterpret_cast<volatile uint32_t*>(&q->seq) = ticket + 1;
-                        }
-                    } else {
+                    {
                         int base = 0;
                         if (lane == 0) base = atomicAdd(fz.need_count, __popc(bal));
                         base = __shfl_sync(0xffffffffu, base, 0);
@@ -572,46 +561,92 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             asm volatile("bar.sync 2, %0;" ::"n"(128 * kGroups) : "memory");
         }
-        if (kRefine && group == 0) {
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) atomicAdd(&qctl->producers_done, 1u);
-        }
     } else if (kRefine && warp >= kEpiWarp0 + 4 * kGroups) {
-        // ================================================================ refine warps: exact re-rank of the surviving rows
-        // Ticket queue: a warp takes the next ticket and waits until that slot is published (or until every producer has
-        // finished and the ticket was never issued).  The record is copied to registers and the slot released before the
-        // re-rank, which runs on L2-resident bank rows (__dp4a) beside the epilogue — ~0.5 % of the rows on an all-pairs list.
+        // ================================================================ finishing warps: unit end + exact re-rank
+        // Warp w owns query rows 32 w .. 32 w + 31 of every unit.  Per unit: merge the two column halves' top-5 lists (32-bit
+        // keys with global chunk numbers: min / max only), give the buffer back, then the fused ratio-test bound (north_star:
+        // "fused epilogue ... ratio test"): a row can only pass  sqrtf(d0^2) < ratio * sqrtf(d1^2)  if it passes with the
+        // smallest d0^2 and the largest d1^2 the chunk maxima allow,  d0^2 >= |a|^2 + N- - 2 V1,  d1^2 <= |a|^2 + N+ - 2 V2  with
+        // [N-, N+] the |b|^2 range of the train image.  ~99.5 % of C3's rows stop here and write NOTHING.  Survivors are re-ranked
+        // on the spot (refine_dot_row: __dp4a on L2-resident bank rows) — unless the epilogue has already delivered the NEXT unit
+        // (this warp is a whole unit behind: a pair with many true matches): then the rest of the rows go to the need list and
+        // the post pass (post.cu), which has the whole GPU.
         RefineCtx rc;
         rc.bank = fz.bank; rc.norm2 = fz.norm2; rc.top2 = out; rc.stats = fz.stats; rc.bf_list = fz.bf_list; rc.bf_count = fz.bf_count;
         rc.chunk_rows = kCC; rc.all_rows = 0; rc.ratio = fz.ratio;
+        const int row_in_unit = (warp & 3) * 32 + lane;
+        const uint32_t* fin0 = reinterpret_cast<const uint32_t*>(base_ptr + offMerge);
         unsigned long long n_rows_done = 0;
-        if (fz.refine) {
-            for (;;) {
-                uint32_t ticket = 0;
-                if (lane == 0) ticket = atomicAdd(&qctl->claimed, 1u);
-                ticket = __shfl_sync(0xffffffffu, ticket, 0);
-                QRec* q = ring + (ticket % kQCap);
-                int have = 0;
-                if (lane == 0) {
-                    // one lane polls, with a long back-off: the queue is 256 records deep and a survivor is in no hurry, while
-                    // every poll is shared-memory traffic and issue slots taken from the ALU-bound epilogue warps
-                    for (;;) {
-                        if (*reinterpret_cast<volatile uint32_t*>(&q->seq) == ticket + 1) { have = 1; break; }
-                        if (*reinterpret_cast<volatile uint32_t*>(&qctl->producers_done) == 4u &&
-                            ticket >= *reinterpret_cast<volatile uint32_t*>(&qctl->reserved)) break;
-                        __nanosleep(2000);
-                    }
+        uint32_t unit_no = 0;
+        int p_hint = 0, range_of = -1, nbmin = 0, nbmax = 0;
+        for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++unit_no) {
+            const UnitInfoV u = decode_unit_v<BN>(pairs, unit_prefix, n_pairs, unit, fz.uniform_units, p_hint);
+            const int row = u.rb * BM + row_in_unit;
+            const bool in_range = row < u.pd.nq && u.pd.nt > 0;
+            const int na = in_range ? __ldg(fz.norm2 + u.pd.q_row0 + row) : 0;
+            if (range_of != u.pd.t_row0) {                          // |b|^2 range of the train image, from the per-block ranges
+                int mn = INT_MAX, mx = 0;
+                const int b0 = u.pd.t_row0 / kRowAlign, nblk = (u.pd.nt + kRowAlign - 1) / kRowAlign;
+                for (int b = lane; b < nblk; b += 32) { mn = min(mn, __ldg(fz.blk_min + b0 + b)); mx = max(mx, __ldg(fz.blk_max + b0 + b)); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+                nbmin = mn; nbmax = mx; range_of = u.pd.t_row0;
+            }
+            const uint32_t fpar = unit_no & 1u;
+            mbar_wait(fin_full(fpar), (unit_no >> 1) & 1u);
+            const uint32_t* fin = fin0 + fpar * kFinBufWords + row_in_unit;
+            uint32_t r0 = fin[0 * BM], r1 = fin[1 * BM], r2 = fin[2 * BM], r3 = fin[3 * BM], r4 = fin[4 * BM];   // half 0: descending
+#pragma unroll
+            for (int i = 0; i < 5; ++i) top5_maxu(fin[(5 + i) * BM], r0, r1, r2, r3, r4);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fin_empty(fpar));
+            // key = a.b << 11 | (2047 - chunk); value 0 = no chunk with a real row (padding, or orthogonal to the query: the re-rank
+            // treats everything outside the candidates as a.b <= V5)
+            const uint32_t rk[5] = {r0, r1, r2, r3, r4};
+            int32_t vv[5], ch[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { vv[i] = static_cast<int32_t>(rk[i] >> kGchBits); ch[i] = static_cast<int32_t>(kGchMask - (rk[i] & kGchMask)); }
+            Top2 o;
+            o.i0 = (vv[0] > 0 ? ch[0] : 0xFFFF) | (vv[1] > 0 ? ch[1] : 0xFFFF) << 16;       // four candidate chunks, 0xFFFF = none
+            o.i1 = (vv[2] > 0 ? ch[2] : 0xFFFF) | (vv[3] > 0 ? ch[3] : 0xFFFF) << 16;
+            const int V1 = vv[0] > 0 ? vv[0] : -1, V2 = vv[1] > 0 ? vv[1] : -1, V5 = vv[4] > 0 ? vv[4] : 0;
+            o.d0 = __int_as_float(V1);
+            o.d1 = __int_as_float(V2);
+            bool need = false;
+            if (in_range) {
+                if (V2 <= 0) need = true;                           // fewer than two chunks with a real maximum
+                else {
+                    const float lo0 = __fsqrt_rn(static_cast<float>(max(0, na + nbmin - 2 * V1)));
+                    const float hi1 = __fsqrt_rn(static_cast<float>(max(0, na + nbmax - 2 * V2)));
+                    need = static_cast<double>(lo0) < static_cast<double>(hi1) * fz.ratio;
                 }
-                have = __shfl_sync(0xffffffffu, have, 0);                     // one decision per warp
-                if (!have) break;
-                __threadfence_block();
-                const Top2 t = q->t;
-                const int64_t srow = q->srow;
-                const int v5 = q->v5, na = q->na, qrow = q->qrow, tr0 = q->tr0, ntr = q->ntr, nbmin = q->nbmin, nbmax = q->nbmax;
-                __syncwarp();
-                if (lane == 0) atomicAdd(&qctl->freed, 1u);                   // the slot may be reused
-                refine_dot_row(rc, srow, lane, t, v5, na, qrow, tr0, ntr, nbmin, nbmax);
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, need);
+            const uint32_t next_par = (unit_no + 1) & 1u, next_phase = ((unit_no + 1) >> 1) & 1u;
+            while (bal) {
+                if (mbar_test(fin_full(next_par), next_phase)) {
+                    // a unit behind: the remaining rows go to the post pass (candidate record + need list, one atomic per warp)
+                    const bool mine = (bal >> lane) & 1u;
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(fz.need_count, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (mine) {
+                        const int64_t srow = u.pd.out_row0 + row;
+                        out[srow] = o;
+                        aux[srow] = V5;
+                        fz.need_list[base + __popc(bal & ((1u << lane) - 1))] = static_cast<int32_t>(srow);
+                    }
+                    break;
+                }
+                const int src = __ffs(bal) - 1;
+                bal &= bal - 1;
+                Top2 t;
+                t.i0 = __shfl_sync(0xffffffffu, o.i0, src); t.i1 = __shfl_sync(0xffffffffu, o.i1, src);
+                t.d0 = __shfl_sync(0xffffffffu, o.d0, src); t.d1 = __shfl_sync(0xffffffffu, o.d1, src);
+                const int v5 = __shfl_sync(0xffffffffu, V5, src), na_s = __shfl_sync(0xffffffffu, na, src);
+                const int row_s = u.rb * BM + (warp & 3) * 32 + src;
+                const int64_t srow = u.pd.out_row0 + row_s;
+                refine_dot_row(rc, srow, lane, t, v5, na_s, u.pd.q_row0 + row_s, u.pd.t_row0, u.pd.nt, nbmin, nbmax);
                 if (lane == 0) fz.done_list[atomicAdd(fz.done_count, 1)] = static_cast<int32_t>(srow);
                 ++n_rows_done;
             }
