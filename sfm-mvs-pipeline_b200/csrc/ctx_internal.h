@@ -202,7 +202,9 @@ struct sfm_ctx {
     int tcv_layout = 0;              // epilogue organisation of the value-only kernel (10 * parity + halves): 0 = auto,
                                      // SFM_TCV_LAYOUT = 12 | 14 | 21 forces
     bool tcv_inkernel_refine = true; // SFM_TCV_INKERNEL_REFINE = 0: survivors of the fused ratio bound go to the post pass instead of
-                                     // the knn CTA's own refine warps
+                                     // the knn CTA's own finishing warps
+    bool tcv_backpressure = true;    // SFM_TCV_BACKPRESSURE = 0: on dense lists, too, a finishing warp that falls behind diverts its rows
+                                     // to the post pass (default there: the epilogue waits for it)
     int knn_grid_limit = 0;          // > 0: the persistent knn kernels launch at most this many CTAs (dist from-host path: SMs left
                                      // free for the NCCL broadcasts of the chunks still in flight)
     int min_batches = 6;             // a long pair list is cut into at least this many batches (SFM_MIN_BATCHES): post kernels of

@@ -53,19 +53,22 @@ struct Cfg {
     static constexpr int offAExt = offA + kAStages * kABytes;      // constant weight rows
     static constexpr int offMerge = offAExt + kAExtBytes;          // [3 groups][128][5] int64
     static constexpr int offBar = offMerge + 3 * BM * 5 * 8;
-    static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages + 4;   // + unit hand-off to the finishing warps
+    static constexpr int kNumBars = 2 * kBStages + 2 * kAStages + 2 * kAccStages + 2 * 4;   // + unit hand-off to the finishing warps (kFinDepth each way)
     static constexpr int offTmemPtr = offBar + kNumBars * 8;
     static constexpr int kSmemBytes = offTmemPtr + 16 + 1024;
     static constexpr uint32_t kIdesc = umma_idesc_u8(BM, BN);
     static constexpr uint32_t kIdescExt = umma_idesc_u8s8(BM, BN);
 };
 // In-kernel unit end and re-rank (kRefine): the epilogue warps only stream accumulators.  At the end of a unit each of them
-// leaves its five running keys per query row in shared memory (two buffers, alternating by unit) and goes on with the next
+// leaves its five running keys per query row in shared memory (a ring of kFinDepth buffers) and goes on with the next
 // unit; the four FINISHING warps merge the two column halves, apply the fused ratio bound and re-rank the few surviving rows
 // exactly (refine_dot_row) while the epilogue is already in the next unit.  Measured before this split: ~2460 cycles per
 // unit with both epilogue groups parked at two bar.sync around the unit end of group 0 (C3: 32 tiles per unit -> 77 of
 // 620 cycles per tile; C5's 64-tile units ran 6.6 % faster per tile for that reason alone).
 constexpr int kFinBufWords = 2 * 5 * BM;       // [column half][key][row] uint32 per buffer
+struct __align__(16) SurvRec { Top2 t; int32_t v5, na, row, pad; };         // a row that survived the ratio bound (row: inside the query image)
+struct SurvList { SurvRec rec[BM]; int count; };
+constexpr int kFinDepth = 4;                   // buffers (units) the finishing warps may lag behind the epilogue; in the unused digit-tile area
 }  // namespace tcv
 
 struct UnitInfoV { PairDesc pd; int rb; int n_tiles; };
@@ -204,7 +207,8 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     constexpr int kGchBits = 11;
     constexpr uint32_t kGchMask = (1u << kGchBits) - 1;
     static_assert(!kRefine || (!kNorm && kGroups == 2), "refine warps: norm-less variant with 8 epilogue warps (512 threads x 128 registers)");
-    static_assert(2 * kFinBufWords * 4 <= 3 * BM * 5 * 8, "hand-off buffers fit the merge area");
+    static_assert(!kRefine || kFinDepth * kFinBufWords * 4 + static_cast<int>(sizeof(SurvList)) <= C::kBStages * C::kEBytes,
+                  "hand-off buffers and the survivor list fit the unused digit-tile area");
     constexpr int kLoadsPerVisit = BN / 32 / kHalves;               // 32-column tcgen05.ld one warp issues per tile
     constexpr int kChunksPerVisit = BN / kCC / kHalves;             // chunks one warp reads per tile
     static_assert(kCC == 32 || kCC == 64 || kCC == 128, "chunk = one, two or four 32-column loads");
@@ -222,7 +226,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     auto acc_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + i); };
     auto acc_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + kAccStages + i); };
     auto fin_full = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + 2 * kAccStages + i); };
-    auto fin_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + 2 * kAccStages + 2 + i); };
+    auto fin_empty = [&](int i) { return bar0 + 8u * (2 * kBStages + 2 * kAStages + 2 * kAccStages + kFinDepth + i); };
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(base_ptr + offTmemPtr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,7 +240,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         for (int i = 0; i < kBStages; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
         for (int i = 0; i < kAStages; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), n_issuers); }   // every MMA warp releases A
         for (int i = 0; i < kAccStages; ++i) { mbar_init(acc_full(i), 1); mbar_init(acc_empty(i), 4 * kHalves); }   // one arrival per reading warp
-        for (int i = 0; i < 2; ++i) { mbar_init(fin_full(i), 4 * kGroups); mbar_init(fin_empty(i), 4); }   // per epilogue warp / per finishing warp
+        for (int i = 0; i < kFinDepth; ++i) { mbar_init(fin_full(i), 4 * kGroups); mbar_init(fin_empty(i), 4); }   // per epilogue warp / per finishing warp
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -431,9 +435,9 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             }
             if constexpr (kRefine) {
                 // ---- unit end, handed over: five keys per row into the buffer of this unit's parity, one arrival per warp
-                const uint32_t fpar = unit_no & 1u;
-                mbar_wait(fin_empty(fpar), ((unit_no >> 1) & 1u) ^ 1u);
-                uint32_t* fin = reinterpret_cast<uint32_t*>(merge) + fpar * kFinBufWords + group * 5 * BM + row_in_unit;
+                const uint32_t fpar = unit_no % kFinDepth;
+                mbar_wait(fin_empty(fpar), ((unit_no / kFinDepth) & 1u) ^ 1u);
+                uint32_t* fin = reinterpret_cast<uint32_t*>(base_ptr + offE) + fpar * kFinBufWords + group * 5 * BM + row_in_unit;
                 fin[0 * BM] = n1; fin[1 * BM] = n2; fin[2 * BM] = n3; fin[3 * BM] = n4; fin[4 * BM] = n5;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(fin_full(fpar));         // release: the finishing warps acquire on the barrier
@@ -563,19 +567,20 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         }
     } else if (kRefine && warp >= kEpiWarp0 + 4 * kGroups) {
         // ================================================================ finishing warps: unit end + exact re-rank
-        // Warp w owns query rows 32 w .. 32 w + 31 of every unit.  Per unit: merge the two column halves' top-5 lists (32-bit
+        // Warp w evaluates query rows 32 w .. 32 w + 31 of every unit.  Per unit: merge the two column halves' top-5 lists (32-bit
         // keys with global chunk numbers: min / max only), give the buffer back, then the fused ratio-test bound (north_star:
         // "fused epilogue ... ratio test"): a row can only pass  sqrtf(d0^2) < ratio * sqrtf(d1^2)  if it passes with the
         // smallest d0^2 and the largest d1^2 the chunk maxima allow,  d0^2 >= |a|^2 + N- - 2 V1,  d1^2 <= |a|^2 + N+ - 2 V2  with
         // [N-, N+] the |b|^2 range of the train image.  ~99.5 % of C3's rows stop here and write NOTHING.  Survivors are re-ranked
-        // on the spot (refine_dot_row: __dp4a on L2-resident bank rows) — unless the epilogue has already delivered the NEXT unit
-        // (this warp is a whole unit behind: a pair with many true matches): then the rest of the rows go to the need list and
-        // the post pass (post.cu), which has the whole GPU.
+        // by the four warps together (refine_dot_row: __dp4a on L2-resident bank rows), a unit's survivors dealt round-robin.
         RefineCtx rc;
         rc.bank = fz.bank; rc.norm2 = fz.norm2; rc.top2 = out; rc.stats = fz.stats; rc.bf_list = fz.bf_list; rc.bf_count = fz.bf_count;
         rc.chunk_rows = kCC; rc.all_rows = 0; rc.ratio = fz.ratio;
         const int row_in_unit = (warp & 3) * 32 + lane;
-        const uint32_t* fin0 = reinterpret_cast<const uint32_t*>(base_ptr + offMerge);
+        const uint32_t* fin0 = reinterpret_cast<const uint32_t*>(base_ptr + offE);
+        SurvList* surv = reinterpret_cast<SurvList*>(base_ptr + offE + kFinDepth * kFinBufWords * 4);
+        if (warp == kEpiWarp0 + 4 * kGroups && lane == 0) surv->count = 0;
+        asm volatile("bar.sync 3, 128;" ::: "memory");
         unsigned long long n_rows_done = 0;
         uint32_t unit_no = 0;
         int p_hint = 0, range_of = -1, nbmin = 0, nbmax = 0;
@@ -592,8 +597,8 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
                 nbmin = mn; nbmax = mx; range_of = u.pd.t_row0;
             }
-            const uint32_t fpar = unit_no & 1u;
-            mbar_wait(fin_full(fpar), (unit_no >> 1) & 1u);
+            const uint32_t fpar = unit_no % kFinDepth;
+            mbar_wait(fin_full(fpar), (unit_no / kFinDepth) & 1u);
             const uint32_t* fin = fin0 + fpar * kFinBufWords + row_in_unit;
             uint32_t r0 = fin[0 * BM], r1 = fin[1 * BM], r2 = fin[2 * BM], r3 = fin[3 * BM], r4 = fin[4 * BM];   // half 0: descending
 #pragma unroll
@@ -621,35 +626,54 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     need = static_cast<double>(lo0) < static_cast<double>(hi1) * fz.ratio;
                 }
             }
-            unsigned bal = __ballot_sync(0xffffffffu, need);
-            const uint32_t next_par = (unit_no + 1) & 1u, next_phase = ((unit_no + 1) >> 1) & 1u;
-            while (bal) {
-                if (mbar_test(fin_full(next_par), next_phase)) {
-                    // a unit behind: the remaining rows go to the post pass (candidate record + need list, one atomic per warp)
-                    const bool mine = (bal >> lane) & 1u;
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(fz.need_count, __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (mine) {
-                        const int64_t srow = u.pd.out_row0 + row;
-                        out[srow] = o;
-                        aux[srow] = V5;
-                        fz.need_list[base + __popc(bal & ((1u << lane) - 1))] = static_cast<int32_t>(srow);
-                    }
-                    break;
+            // survivors of the whole unit into one shared list, then dealt round-robin: a unit's survivors cluster in few warps' rows
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&surv->count, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need) {
+                    SurvRec& q = surv->rec[base + __popc(bal & ((1u << lane) - 1))];
+                    q.t = o; q.v5 = V5; q.na = na; q.row = row;
                 }
-                const int src = __ffs(bal) - 1;
-                bal &= bal - 1;
-                Top2 t;
-                t.i0 = __shfl_sync(0xffffffffu, o.i0, src); t.i1 = __shfl_sync(0xffffffffu, o.i1, src);
-                t.d0 = __shfl_sync(0xffffffffu, o.d0, src); t.d1 = __shfl_sync(0xffffffffu, o.d1, src);
-                const int v5 = __shfl_sync(0xffffffffu, V5, src), na_s = __shfl_sync(0xffffffffu, na, src);
-                const int row_s = u.rb * BM + (warp & 3) * 32 + src;
-                const int64_t srow = u.pd.out_row0 + row_s;
-                refine_dot_row(rc, srow, lane, t, v5, na_s, u.pd.q_row0 + row_s, u.pd.t_row0, u.pd.nt, nbmin, nbmax);
-                if (lane == 0) fz.done_list[atomicAdd(fz.done_count, 1)] = static_cast<int32_t>(srow);
-                ++n_rows_done;
             }
+            asm volatile("bar.sync 3, 128;" ::: "memory");
+            const int n_surv = *reinterpret_cast<volatile int*>(&surv->count);
+            // "behind": the epilogue has filled every other buffer of the ring; one more unit and it would wait for these warps.
+            // Sparse lists (fz.refine == 1): the rest of this warp's share goes to the need list and the post pass, which has the
+            // whole GPU.  Dense lists (fz.refine == 2): the epilogue waits — a re-rank under the MMA costs less than one in the post pass.
+            const uint32_t next_par = (unit_no + kFinDepth - 1) % kFinDepth, next_phase = ((unit_no + kFinDepth - 1) / kFinDepth) & 1u;
+            int it = warp & 3, n_mine = 0;
+            for (; it < n_surv; it += 4) {
+                if (fz.refine == 1 && mbar_test(fin_full(next_par), next_phase)) break;
+                const SurvRec q = surv->rec[it];
+                const int64_t srow = u.pd.out_row0 + q.row;
+                refine_dot_row(rc, srow, lane, q.t, q.v5, q.na, u.pd.q_row0 + q.row, u.pd.t_row0, u.pd.nt, nbmin, nbmax);
+                ++n_mine;
+            }
+            if (n_mine) {                                            // rows this warp re-ranked: one append for all of them
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fz.done_count, n_mine);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lane < n_mine) fz.done_list[base + lane] = static_cast<int32_t>(u.pd.out_row0 + surv->rec[(warp & 3) + 4 * lane].row);
+                n_rows_done += n_mine;
+            }
+            if (it < n_surv) {
+                // candidate record + need list, one atomic per warp
+                const int n_left = (n_surv - it + 3) / 4;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fz.need_count, n_left);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lane < n_left) {
+                    const SurvRec q = surv->rec[it + 4 * lane];
+                    const int64_t srow = u.pd.out_row0 + q.row;
+                    out[srow] = q.t;
+                    aux[srow] = q.v5;
+                    fz.need_list[base + lane] = static_cast<int32_t>(srow);
+                }
+            }
+            asm volatile("bar.sync 3, 128;" ::: "memory");           // every warp is done with the list
+            if (warp == kEpiWarp0 + 4 * kGroups && lane == 0) surv->count = 0;
         }
         if (lane == 0 && n_rows_done && fz.stats) atomicAdd(fz.stats, n_rows_done);
     }
