@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 measurement pass on one B200 (run under gpurun): the whole -m gpu suite, then every bench line.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/r2_gputest_full.log 2>&1; tail -4 gpurun_out/r2_gputest_full.log | cut -c1-300
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r2_gputest_full.log 2>&1; tail -4 gpurun_out/r2_gputest_full.log | cut -c1-300
 run() { name=$1; shift; python bench.py "$@" > gpurun_out/r2_bench_$name.json 2> gpurun_out/r2_bench_$name.err || tail -3 gpurun_out/r2_bench_$name.err; python - "$name" <<'PY'
 import json, sys
 n = sys.argv[1]
@@ -22,3 +22,4 @@ run knnmatch --workload knnmatch --steps 3 --warmup 1
 run c4 --workload c4 --steps 10 --warmup 3 --no-cpu-baseline
 run extract --workload extract --steps 5 --warmup 3
 run c5 --workload c5 --steps 3 --warmup 1 --no-cpu-baseline --e2e-steps 3
+run extract_orb --workload extract --detector ORB --steps 5 --warmup 3
