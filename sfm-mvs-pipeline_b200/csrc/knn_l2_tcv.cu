@@ -645,7 +645,12 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             const uint32_t next_par = (unit_no + kFinDepth - 1) % kFinDepth, next_phase = ((unit_no + kFinDepth - 1) / kFinDepth) & 1u;
             int it = warp & 3, n_mine = 0;
             for (; it < n_surv; it += 4) {
-                if (fz.refine == 1 && mbar_test(fin_full(next_par), next_phase)) break;
+                if (fz.refine == 1) {
+                    // ONE lane reads the barrier: the warp must take this branch as a whole (refine_dot_row shuffles), and two
+                    // lanes testing an mbarrier a few cycles apart may see different phases
+                    const int behind = lane == 0 ? static_cast<int>(mbar_test(fin_full(next_par), next_phase)) : 0;
+                    if (__shfl_sync(0xffffffffu, behind, 0)) break;
+                }
                 const SurvRec q = surv->rec[it];
                 const int64_t srow = u.pd.out_row0 + q.row;
                 refine_dot_row(rc, srow, lane, q.t, q.v5, q.na, u.pd.q_row0 + q.row, u.pd.t_row0, u.pd.nt, nbmin, nbmax);
