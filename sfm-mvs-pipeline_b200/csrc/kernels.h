@@ -40,7 +40,7 @@ struct TcvFuse {
     // in-kernel re-rank (norm-less variant, 8 epilogue warps): four extra warps of the CTA take the surviving rows from a
     // shared-memory queue, re-rank them exactly (refine_dot_row) and append them to done_list; rows they cannot decide go
     // to bf_list.  refine = 0: survivors go to need_list for the post pass instead.
-    int refine;
+    int refine;                  // 1: divert when behind (sparse lists), 2: never divert (dense lists), 3: test mode, see knn_l2_tcv.cu
     int uniform_units;           // > 0: every pair of the launch has this many 128-row units (pair of a unit = a division, no search)
     const uint8_t* bank;
     int32_t* done_list;

@@ -650,7 +650,7 @@ knn2_l2_u8_tcv_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                     // lanes testing an mbarrier a few cycles apart may see different phases
                     const int behind = lane == 0 ? static_cast<int>(mbar_test(fin_full(next_par), next_phase)) : 0;
                     if (__shfl_sync(0xffffffffu, behind, 0)) break;
-                }
+                } else if (fz.refine == 3 && n_mine >= 1) break;       // test mode: one row per warp and unit here, the rest diverted
                 const SurvRec q = surv->rec[it];
                 const int64_t srow = u.pd.out_row0 + q.row;
                 refine_dot_row(rc, srow, lane, q.t, q.v5, q.na, u.pd.q_row0 + q.row, u.pd.t_row0, u.pd.nt, nbmin, nbmax);

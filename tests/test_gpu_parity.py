@@ -492,7 +492,7 @@ def test_c5_shape_pair_default_layout_vs_oracle(sfm):
 
 
 @pytest.mark.parametrize("settings", [{}, {"SFM_TCV_NORMLESS": "0", "SFM_TCV_CHUNK": "32"}, {"SFM_TCV_NORMLESS": "0", "SFM_TCV_CHUNK": "64"},
-                                      {"SFM_TCV_NORMLESS": "2", "SFM_TCV_CHUNK": "32"}, {"SFM_TCV_BACKPRESSURE": "0"}])
+                                      {"SFM_TCV_NORMLESS": "2", "SFM_TCV_CHUNK": "32"}, {"SFM_TCV_BACKPRESSURE": "0"}, {"SFM_TCV_DIVERT_TEST": "1"}])
 def test_c4_shape_grid_list_dense_branch(sfm, settings, monkeypatch):
     """C4's shape: 4 096-row images, grid pairing (neighbouring shots share 30 % planted rows: the DENSE branch, 7 % of the
     rows re-ranked).  64 images as an 8 x 8 grid, sequenceLength 3: every variant the adaptive choice can land on gives the
@@ -542,7 +542,7 @@ def test_from_host_failure_leaves_no_half_built_bank(sfm):
 
 
 @pytest.mark.parametrize("settings", [{}, {"SFM_TCV_NORMLESS": "2"}, {"SFM_TCV_NORMLESS": "0"}, {"SFM_TCV_INKERNEL_REFINE": "0"},
-                                      {"SFM_MIN_BATCHES": "1"}, {"SFM_TCV_BACKPRESSURE": "0"}])
+                                      {"SFM_MIN_BATCHES": "1"}, {"SFM_TCV_BACKPRESSURE": "0"}, {"SFM_TCV_DIVERT_TEST": "1"}])
 def test_ragged_scene_first_run_every_variant(sfm, settings, monkeypatch):
     """The scene of the multi-GPU worker (ragged sizes, an empty image, 30 % planted neighbours, min-match-count 20): the FIRST
     run on a fresh context and the following ones (adaptive feedback switches the kernel variant) against the C oracle."""
