@@ -37,9 +37,10 @@ struct TcvFuse {
     int32_t* need_list;          // capacity = staged rows of the batch
     int* need_count;
     double ratio;
-    // in-kernel re-rank (norm-less variant, 8 epilogue warps): four extra warps of the CTA take the surviving rows from a
-    // shared-memory queue, re-rank them exactly (refine_dot_row) and append them to done_list; rows they cannot decide go
-    // to bf_list.  refine = 0: survivors go to need_list for the post pass instead.
+    // in-kernel unit end and re-rank (norm-less variant, 8 epilogue warps): four extra "finishing" warps of the CTA merge the
+    // epilogue warps' keys at the end of a unit, apply the ratio bound, re-rank the surviving rows exactly (refine_dot_row) and
+    // append them to done_list; rows they cannot decide go to bf_list, rows they have no time for to need_list.
+    // refine = 0: the epilogue warps finish the unit themselves and all survivors go to need_list for the post pass.
     int refine;                  // 1: divert when behind (sparse lists), 2: never divert (dense lists), 3: test mode, see knn_l2_tcv.cu
     int uniform_units;           // > 0: every pair of the launch has this many 128-row units (pair of a unit = a division, no search)
     const uint8_t* bank;
