@@ -204,8 +204,8 @@ struct sfm_ctx {
     bool tcv_inkernel_refine = true; // SFM_TCV_INKERNEL_REFINE = 0: survivors of the fused ratio bound go to the post pass instead of
                                      // the knn CTA's own finishing warps
     bool tcv_divert_test = false;    // SFM_TCV_DIVERT_TEST = 1 (tests): every finishing warp re-ranks one row per unit and diverts the rest
-    bool tcv_backpressure = true;    // SFM_TCV_BACKPRESSURE = 0: on dense lists, too, a finishing warp that falls behind diverts its rows
-                                     // to the post pass (default there: the epilogue waits for it)
+    int tcv_backpressure = 1;        // SFM_TCV_BACKPRESSURE: 1 = on dense lists the epilogue waits for the finishing warps, 0 = a warp that
+                                     // falls behind always diverts its rows to the post pass, 2 = the epilogue always waits
     int knn_grid_limit = 0;          // > 0: the persistent knn kernels launch at most this many CTAs (dist from-host path: SMs left
                                      // free for the NCCL broadcasts of the chunks still in flight)
     int min_batches = 6;             // a long pair list is cut into at least this many batches (SFM_MIN_BATCHES): post kernels of

@@ -562,7 +562,7 @@ int enqueue_impl(sfm_ctx* c, const int32_t* pairs_in, int64_t n_pairs, const sfm
             // norm-less variant with 8 epilogue warps: four more warps of every CTA re-rank the survivors in the kernel
             // dense lists (grid neighbours: ~7 % of the rows survive the bound): 2 = the epilogue waits for the finishing warps instead
             // of diverting their backlog to the post pass — a re-rank under the MMA costs ~0.78 of one in the post pass (C4, measured)
-            fz.refine = (eng == Engine::TCN && c->tcv_layout_run == 12 && c->tcv_inkernel_refine) ? (c->tcv_divert_test ? 3 : c->dense_matches && c->tcv_backpressure ? 2 : 1) : 0;
+            fz.refine = (eng == Engine::TCN && c->tcv_layout_run == 12 && c->tcv_inkernel_refine) ? (c->tcv_divert_test ? 3 : (c->tcv_backpressure == 2 || (c->dense_matches && c->tcv_backpressure)) ? 2 : 1) : 0;
             fz.bank = b.d_u8.as<uint8_t>(); fz.done_list = S.done.as<int32_t>(); fz.done_count = S.counters.as<int>() + 2;
             fz.bf_list = S.bf.as<int32_t>(); fz.bf_count = S.counters.as<int>();
             fz.stats = reinterpret_cast<unsigned long long*>(c->d_scalars.as<uint8_t>() + 32);
@@ -956,7 +956,7 @@ int sfm_ctx_create(sfm_ctx** out, int device) {
     if (const char* env = std::getenv("SFM_STAGING_MB")) { long v = std::atol(env); if (v > 0) mb = static_cast<size_t>(v); }
     c->staging_budget_rows = (mb << 20) / sizeof(Top2);
     if (const char* env = std::getenv("SFM_TCV_INKERNEL_REFINE")) c->tcv_inkernel_refine = std::atoi(env) != 0;
-    if (const char* env = std::getenv("SFM_TCV_BACKPRESSURE")) c->tcv_backpressure = std::atoi(env) != 0;
+    if (const char* env = std::getenv("SFM_TCV_BACKPRESSURE")) { const int t = std::atoi(env); if (t >= 0 && t <= 2) c->tcv_backpressure = t; }
     if (const char* env = std::getenv("SFM_TCV_DIVERT_TEST")) c->tcv_divert_test = std::atoi(env) != 0;
     if (const char* env = std::getenv("SFM_MIN_BATCHES")) { const int t = std::atoi(env); if (t >= 1 && t <= 64) c->min_batches = t; }
     if (const char* env = std::getenv("SFM_TCV_SPREAD_DIV")) { const int t = std::atoi(env); if (t >= 1) c->tcv_spread_div = t; }
